@@ -1,0 +1,180 @@
+/*
+ * jlp_b200.h -- C ABI of the B200-native Illumina read generator.
+ *
+ * This is the drop-in boundary for jackalope's Illumina hot path.  The entry
+ * points below are what the package's Rcpp glue would bind in place of the
+ * bodies of
+ *     illumina_ref_cpp   /root/reference/src/hts_illumina.cpp:589-649
+ *     illumina_hap_cpp   /root/reference/src/hts_illumina.cpp:662-739
+ * (INTEGRATION.md shows that glue).  Plain pointers and sizes only; no
+ * exceptions cross the boundary; every function returns 0 on success and a
+ * negative jlp_status otherwise, with a message available from
+ * jlp_last_error().  The caller owns every input buffer; the library owns all
+ * device and pinned memory.  There is no CPU fallback: without a CUDA device
+ * jlp_ctx_create fails with JLP_ERR_NO_DEVICE.
+ */
+#ifndef JLP_B200_H
+#define JLP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct jlp_ctx jlp_ctx;
+
+enum jlp_status {
+    JLP_OK = 0,
+    JLP_ERR_ARG = -1,        /* invalid argument (the reference would Rcpp::stop) */
+    JLP_ERR_NO_DEVICE = -2,  /* no usable CUDA device */
+    JLP_ERR_CUDA = -3,       /* CUDA runtime error */
+    JLP_ERR_IO = -4,         /* cannot open / write an output file (src/io.h:288-290) */
+    JLP_ERR_ABORTED = -5,    /* abort callback asked to stop (Progress::check_abort, src/hts.h:396-399) */
+    JLP_ERR_UNSUPPORTED = -6 /* a feature of the reference not built yet (see jlp_illumina_params.compress) */
+};
+
+/* ---- context: one per GPU (one process per GPU under torchrun) -------------- */
+
+int jlp_ctx_create(int device, jlp_ctx** out);
+void jlp_ctx_destroy(jlp_ctx* ctx);
+/* Last error text of this context (or of context creation when ctx == NULL). */
+const char* jlp_last_error(const jlp_ctx* ctx);
+
+/* ---- genome data model (replaces reading RefGenome / HapSet through XPtr,
+ *      src/hts_illumina.cpp:614,689; layouts src/ref_classes.h:36-116,
+ *      src/hap_classes.h:100-104,287-296) ------------------------------------- */
+
+/* Reference genome: chromosome c is bases[chrom_off[c] .. chrom_off[c+1]).
+ * genome_name is what fill_fq_lines prints first ("REF", src/ref_classes.h:138). */
+int jlp_set_genome(jlp_ctx* ctx, const char* bases, const uint64_t* chrom_off, uint64_t n_chroms,
+                   const char* const* chrom_names, const char* genome_name);
+
+/* Drop all haplotypes previously added. */
+int jlp_clear_haplotypes(jlp_ctx* ctx);
+
+/* One haplotype = per chromosome the sorted AllMutations arrays
+ * (old_pos, new_pos, nucleos) plus the mutated chromosome size.  nuc_off[c][i]
+ * indexes nuc_pool[c]; a deletion has nuc_len 0, a substitution 1, an insertion
+ * 1+k.  The chromosome is materialised on the device at once
+ * (HapChrom::get_chrom_full, src/hap_classes.cpp:80-116).  Returns the
+ * haplotype's index through *hap_index. */
+int jlp_add_haplotype(jlp_ctx* ctx, const char* name, const uint64_t* n_muts,
+                      const uint64_t* const* old_pos, const uint64_t* const* new_pos,
+                      const uint64_t* const* nuc_off, const char* const* nuc_pool,
+                      const uint64_t* nuc_pool_len, const uint64_t* chrom_sizes,
+                      uint64_t* hap_index);
+
+/* Copy a materialised haplotype chromosome back to the host (parity tests of
+ * the materialisation kernel; ~ HapChrom::get_chrom_full). */
+int jlp_get_haplotype_chrom(jlp_ctx* ctx, uint64_t hap, uint64_t chrom, char* out, uint64_t cap,
+                            uint64_t* len);
+
+/* ---- ART quality profile for one read end (0 or 1), flattened
+ *      [nt in T,C,A,G][pos][k]: nq[nt*L+pos] entries per position, probs and
+ *      quals concatenated in that order (the nested vectors qual_probs{1,2} /
+ *      quals{1,2} of src/hts_illumina.cpp:604-609). ---------------------------- */
+int jlp_set_profile(jlp_ctx* ctx, int end, uint64_t read_length, const uint32_t* nq,
+                    const double* probs, const uint8_t* quals);
+
+/* ---- run --------------------------------------------------------------------- */
+
+typedef int (*jlp_abort_cb)(void* user);                       /* non-zero = abort */
+typedef void (*jlp_progress_cb)(void* user, uint64_t reads);   /* reads written since last call */
+
+typedef struct jlp_illumina_params {
+    /* the arguments of illumina_{ref,hap}_cpp, same meaning */
+    int paired;
+    int matepair;
+    const char* out_prefix;      /* files <prefix>[_<hap>]_R{1,2}.fq, src/hts.h:344,541 */
+    int sep_files;               /* haplotype runs only */
+    int compress;                /* 0 = plain FASTQ; >0: JLP_ERR_UNSUPPORTED in this round */
+    const char* comp_method;     /* "gzip" | "bgzip" (validated, src/hts.h:470) */
+    uint64_t n_reads;
+    double prob_dup;
+    uint64_t n_threads;          /* advisory: host writer threads */
+    int show_progress;           /* unused by the library; see progress callback */
+    uint64_t read_pool_size;     /* duplicate chains stop at pool boundaries, src/hts.h:266-267 */
+    const double* haplotype_probs; /* [n_haps], haplotype runs only */
+    double frag_len_shape, frag_len_scale;
+    uint64_t frag_len_min, frag_len_max;
+    double ins_prob1, del_prob1, ins_prob2, del_prob2;
+    const char* const* barcodes; /* [1] for a reference run, [n_haps] for haplotypes; NULL = none */
+    /* additions of this implementation */
+    uint64_t seed;               /* run seed; the glue draws it from R's RNG (src/pcg.h:37-46) */
+    uint64_t batch_pairs;        /* pairs per device batch; 0 = default */
+    uint32_t shard_index;        /* this process handles batches b with b % shard_count == shard_index */
+    uint32_t shard_count;        /* 0 or 1 = everything */
+    jlp_abort_cb abort_cb;
+    jlp_progress_cb progress_cb;
+    void* cb_user;
+} jlp_illumina_params;
+
+typedef struct jlp_run_stats {
+    uint64_t pairs;              /* read pairs (or single reads) generated by this call */
+    uint64_t bytes_out[2];       /* FASTQ bytes produced per end */
+    uint64_t batches;
+    uint64_t kernel_launches;    /* launches of this library's kernels */
+    double device_ms;            /* sum of CUDA-event time of the kernels */
+    double gen_ms;               /* ... of which the quality/error kernel */
+    double fmt_ms;               /* ... of which the FASTQ formatter */
+    uint64_t d2h_bytes;
+    uint64_t h2d_bytes;
+} jlp_run_stats;
+
+/* Reads from the reference genome (illumina_ref_cpp). */
+int jlp_illumina_ref(jlp_ctx* ctx, const jlp_illumina_params* p, jlp_run_stats* stats);
+/* Reads from the haplotypes added so far (illumina_hap_cpp). */
+int jlp_illumina_hap(jlp_ctx* ctx, const jlp_illumina_params* p, jlp_run_stats* stats);
+
+/* Same generators, output captured in caller-provided HOST buffers instead of
+ * files (tests; bench.py's end-to-end leg).  With sep_files the haplotypes'
+ * outputs are concatenated in haplotype order.  *len receives the bytes
+ * needed; JLP_ERR_ARG if a buffer is too small. */
+int jlp_illumina_to_memory(jlp_ctx* ctx, int use_haplotypes, const jlp_illumina_params* p,
+                           char* out1, uint64_t cap1, uint64_t* len1,
+                           char* out2, uint64_t cap2, uint64_t* len2, jlp_run_stats* stats);
+
+/* Same generators with the FASTQ left in device memory and dropped (bench.py's
+ * device-resident leg: everything but the D2H copy and the file write). */
+int jlp_illumina_device_only(jlp_ctx* ctx, int use_haplotypes, const jlp_illumina_params* p,
+                             jlp_run_stats* stats);
+
+/* Pairs apportioned to each (haplotype, chromosome) group, haplotype-major, for
+ * exactly the run `p` describes (reads_per_group is seeded from p->seed, so the
+ * generators above make the same split).  A reference run has n_chroms groups. */
+int jlp_illumina_group_counts(jlp_ctx* ctx, int use_haplotypes, const jlp_illumina_params* p,
+                              uint64_t* counts, uint64_t cap, uint64_t* n_groups);
+
+/* ---- host-side pieces exposed for CPU tests (no device needed) --------------- */
+
+/* reads_per_group (src/hts.h:58-103): multinomial apportioning by conditional
+ * binomials.  Statistically equivalent to the reference (own engine). */
+int jlp_reads_per_group(uint64_t n_reads, const double* probs, uint64_t n, uint64_t seed,
+                        uint64_t* out);
+/* AliasSampler::construct (src/alias_sampler.h:68-106). */
+int jlp_alias_build(const double* probs, uint64_t n, double* prob_out, uint64_t* alias_out);
+/* Integer thresholds equivalent to the reference's comparisons on
+ * u = runif_01(x): kind 1 -> #{x : double(u) < p}; kind 2 -> #{x : !(double(u) > p)};
+ * kind 3 -> #{x : u < p} (long double).  *all is set when the count is 2^64. */
+int jlp_threshold(int kind, double p, uint64_t* thr, int* all);
+/* The exact integer restatements used by the kernels, kinds as in
+ * oracle/ref_driver.cpp jref_unif_expr (0: die, 4: N quality, 5: frag start). */
+uint64_t jlp_unif_expr(int kind, uint64_t x, double p, uint64_t n);
+/* Fragment-length table: frag_len = frag_min + #{i : X >= cdf[i]} reproduces
+ * min(max((uint64)Gamma(shape, scale), frag_min), frag_max)
+ * (src/hts_illumina.cpp:206-208).  Returns the entry count through *n. */
+int jlp_frag_table(double shape, double scale, uint64_t frag_min, uint64_t frag_max,
+                   uint64_t* cdf, uint64_t cap, uint64_t* n);
+/* Philox4x32-10 block and a logical draw, as the kernels address them. */
+void jlp_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+uint64_t jlp_draw_pos(uint64_t seed, uint64_t j, uint32_t end, uint32_t purpose, uint32_t pos);
+uint64_t jlp_draw_pair(uint64_t seed, uint64_t j, int which);
+
+const char* jlp_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

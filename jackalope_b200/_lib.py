@@ -1,0 +1,100 @@
+"""ctypes binding of the C ABI in include/jlp_b200.h (libjlp_b200.so, built
+in-tree by jackalope_b200/build.py).  There is no fallback: if the library is
+missing this module raises, and if no CUDA device is present jlp_ctx_create
+fails."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libjlp_b200.so")
+
+u8p, u32p, u64p, f64p = (C.POINTER(t) for t in (C.c_uint8, C.c_uint32, C.c_uint64, C.c_double))
+ABORT_CB = C.CFUNCTYPE(C.c_int, C.c_void_p)
+PROGRESS_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_uint64)
+
+JLP_OK, JLP_ERR_ARG, JLP_ERR_NO_DEVICE, JLP_ERR_CUDA, JLP_ERR_IO, JLP_ERR_ABORTED, JLP_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("paired", C.c_int), ("matepair", C.c_int), ("out_prefix", C.c_char_p), ("sep_files", C.c_int),
+        ("compress", C.c_int), ("comp_method", C.c_char_p), ("n_reads", C.c_uint64), ("prob_dup", C.c_double),
+        ("n_threads", C.c_uint64), ("show_progress", C.c_int), ("read_pool_size", C.c_uint64),
+        ("haplotype_probs", f64p), ("frag_len_shape", C.c_double), ("frag_len_scale", C.c_double),
+        ("frag_len_min", C.c_uint64), ("frag_len_max", C.c_uint64),
+        ("ins_prob1", C.c_double), ("del_prob1", C.c_double), ("ins_prob2", C.c_double), ("del_prob2", C.c_double),
+        ("barcodes", C.POINTER(C.c_char_p)), ("seed", C.c_uint64), ("batch_pairs", C.c_uint64),
+        ("shard_index", C.c_uint32), ("shard_count", C.c_uint32),
+        ("abort_cb", ABORT_CB), ("progress_cb", PROGRESS_CB), ("cb_user", C.c_void_p),
+    ]
+
+
+class RunStats(C.Structure):
+    _fields_ = [
+        ("pairs", C.c_uint64), ("bytes_out", C.c_uint64 * 2), ("batches", C.c_uint64),
+        ("kernel_launches", C.c_uint64), ("device_ms", C.c_double), ("gen_ms", C.c_double),
+        ("fmt_ms", C.c_double), ("d2h_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64),
+    ]
+
+    def as_dict(self):
+        return dict(pairs=self.pairs, bytes_out=list(self.bytes_out), batches=self.batches,
+                    kernel_launches=self.kernel_launches, device_ms=self.device_ms, gen_ms=self.gen_ms,
+                    fmt_ms=self.fmt_ms, d2h_bytes=self.d2h_bytes, h2d_bytes=self.h2d_bytes)
+
+
+# every symbol include/jlp_b200.h declares
+SYMBOLS = [
+    "jlp_ctx_create", "jlp_ctx_destroy", "jlp_last_error", "jlp_set_genome", "jlp_clear_haplotypes",
+    "jlp_add_haplotype", "jlp_get_haplotype_chrom", "jlp_set_profile", "jlp_illumina_ref", "jlp_illumina_hap",
+    "jlp_illumina_to_memory", "jlp_illumina_device_only", "jlp_illumina_group_counts", "jlp_reads_per_group", "jlp_alias_build",
+    "jlp_threshold", "jlp_unif_expr", "jlp_frag_table", "jlp_philox4x32_10", "jlp_draw_pos", "jlp_draw_pair",
+    "jlp_version",
+]
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "jackalope_b200: %s is missing -- run `python -m jackalope_b200.build` "
+            "(or __graft_entry__.build()); there is no CPU fallback" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    pp = C.POINTER(C.c_char_p)
+    L.jlp_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    L.jlp_ctx_destroy.argtypes = [C.c_void_p]
+    L.jlp_ctx_destroy.restype = None
+    L.jlp_last_error.argtypes = [C.c_void_p]
+    L.jlp_last_error.restype = C.c_char_p
+    L.jlp_set_genome.argtypes = [C.c_void_p, C.c_void_p, u64p, C.c_uint64, pp, C.c_char_p]
+    L.jlp_clear_haplotypes.argtypes = [C.c_void_p]
+    L.jlp_add_haplotype.argtypes = [C.c_void_p, C.c_char_p, u64p, C.POINTER(u64p), C.POINTER(u64p),
+                                    C.POINTER(u64p), C.POINTER(C.c_void_p), u64p, u64p, u64p]
+    L.jlp_get_haplotype_chrom.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, u64p]
+    L.jlp_set_profile.argtypes = [C.c_void_p, C.c_int, C.c_uint64, u32p, f64p, u8p]
+    L.jlp_illumina_ref.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(RunStats)]
+    L.jlp_illumina_hap.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(RunStats)]
+    L.jlp_illumina_to_memory.argtypes = [C.c_void_p, C.c_int, C.POINTER(Params), C.c_void_p, C.c_uint64, u64p,
+                                         C.c_void_p, C.c_uint64, u64p, C.POINTER(RunStats)]
+    L.jlp_illumina_device_only.argtypes = [C.c_void_p, C.c_int, C.POINTER(Params), C.POINTER(RunStats)]
+    L.jlp_illumina_group_counts.argtypes = [C.c_void_p, C.c_int, C.POINTER(Params), u64p, C.c_uint64, u64p]
+    L.jlp_reads_per_group.argtypes = [C.c_uint64, f64p, C.c_uint64, C.c_uint64, u64p]
+    L.jlp_alias_build.argtypes = [f64p, C.c_uint64, f64p, u64p]
+    L.jlp_threshold.argtypes = [C.c_int, C.c_double, u64p, C.POINTER(C.c_int)]
+    L.jlp_unif_expr.argtypes = [C.c_int, C.c_uint64, C.c_double, C.c_uint64]
+    L.jlp_unif_expr.restype = C.c_uint64
+    L.jlp_frag_table.argtypes = [C.c_double, C.c_double, C.c_uint64, C.c_uint64, u64p, C.c_uint64, u64p]
+    L.jlp_philox4x32_10.argtypes = [u32p, u32p, u32p]
+    L.jlp_philox4x32_10.restype = None
+    L.jlp_draw_pos.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.jlp_draw_pos.restype = C.c_uint64
+    L.jlp_draw_pair.argtypes = [C.c_uint64, C.c_uint64, C.c_int]
+    L.jlp_draw_pair.restype = C.c_uint64
+    L.jlp_version.restype = C.c_char_p
+    _lib = L
+    return L

@@ -1,0 +1,740 @@
+// C ABI (include/jlp_b200.h): context, genome / haplotype / profile upload, and
+// the batch pipeline that stands in for write_reads_cpp_ / write_reads_cpp_sep_files_
+// / write_reads_one_filetype_ (/root/reference/src/hts.h:323-552).
+#include "../../include/jlp_b200.h"
+
+#include <cuda_runtime.h>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cerrno>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "jlp_draws.h"
+#include "jlp_host.h"
+#include "jlp_kernels.cuh"
+
+using namespace jlp;
+
+namespace {
+
+std::string g_create_error;
+
+struct CudaErr : std::runtime_error {
+    explicit CudaErr(const std::string& m) : std::runtime_error(m) {}
+};
+struct ArgErr : std::runtime_error {
+    explicit ArgErr(const std::string& m) : std::runtime_error(m) {}
+};
+struct IoErr : std::runtime_error {
+    explicit IoErr(const std::string& m) : std::runtime_error(m) {}
+};
+struct Unsupported : std::runtime_error {
+    explicit Unsupported(const std::string& m) : std::runtime_error(m) {}
+};
+struct Aborted : std::runtime_error {
+    Aborted() : std::runtime_error("aborted by user") {}
+};
+
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess)                                                            \
+            throw CudaErr(std::string(#call) + ": " + cudaGetErrorString(e_));            \
+    } while (0)
+
+template <typename T> struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    void ensure(size_t count) {
+        if (count <= n) return;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        CK(cudaMalloc(reinterpret_cast<void**>(&p), std::max<size_t>(count, 1) * sizeof(T)));
+        n = count;
+    }
+    void upload(const std::vector<T>& v, cudaStream_t s) {
+        ensure(v.size());
+        if (!v.empty()) CK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    ~DevBuf() { release(); }
+};
+
+template <typename T> struct PinBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    void ensure(size_t count) {
+        if (count <= n) return;
+        if (p) cudaFreeHost(p);
+        p = nullptr; n = 0;
+        CK(cudaMallocHost(reinterpret_cast<void**>(&p), std::max<size_t>(count, 1) * sizeof(T)));
+        n = count;
+    }
+    ~PinBuf() { if (p) cudaFreeHost(p); }
+};
+
+struct HapDev {
+    std::string name;
+    std::vector<const uint8_t*> seq;    // per chromosome; aliases the reference when unmutated
+    std::vector<uint64_t> len;
+    std::vector<uint8_t*> owned;        // device allocations to free
+};
+
+struct Slot {
+    DevBuf<uint8_t> seq, qual, out[2];
+    DevBuf<RecMeta> rec;
+    DevBuf<uint32_t> rec_len, rec_local;
+    DevBuf<uint64_t> block_tot, block_base, totals;
+    PinBuf<uint8_t> h_out[2];
+    PinBuf<uint64_t> h_totals;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // start, gen, scan, fmt, copied
+    uint32_t pairs = 0;
+    bool busy = false;
+};
+
+}  // namespace
+
+struct jlp_ctx {
+    int device = 0;
+    std::string err;
+    cudaStream_t s_compute = nullptr, s_copy = nullptr;
+    // genome
+    DevBuf<uint8_t> genome;
+    std::vector<uint64_t> chrom_off;
+    std::vector<std::string> chrom_names;
+    std::string genome_name;
+    std::vector<HapDev> haps;
+    // profiles
+    EndTables tab[2];
+    bool have_prof[2] = {false, false};
+    DevBuf<uint32_t> d_meta[2], d_entry[2];
+    DevBuf<uint64_t> d_coin[2], d_mis[2];
+    DevBuf<uint16_t> d_mis16[2];
+    // run-scoped device data
+    DevBuf<uint64_t> d_frag, d_group_off;
+    DevBuf<GroupDev> d_groups;
+    DevBuf<uint8_t> d_strpool;
+    DevBuf<uint32_t> d_status;
+    Slot slot[2];
+    uint64_t h2d_bytes = 0;
+};
+
+namespace {
+
+void free_haps(jlp_ctx* c) {
+    for (HapDev& h : c->haps)
+        for (uint8_t* p : h.owned) cudaFree(p);
+    c->haps.clear();
+}
+
+int fail(jlp_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+
+template <typename F> int guarded(jlp_ctx* c, F f) {
+    try {
+        if (c) CK(cudaSetDevice(c->device));
+        f();
+        return JLP_OK;
+    } catch (const ArgErr& e) { return fail(c, JLP_ERR_ARG, e.what());
+    } catch (const CudaErr& e) { return fail(c, JLP_ERR_CUDA, e.what());
+    } catch (const IoErr& e) { return fail(c, JLP_ERR_IO, e.what());
+    } catch (const Unsupported& e) { return fail(c, JLP_ERR_UNSUPPORTED, e.what());
+    } catch (const Aborted& e) { return fail(c, JLP_ERR_ABORTED, e.what());
+    } catch (const std::exception& e) { return fail(c, JLP_ERR_ARG, e.what()); }
+}
+
+// ---------------------------------------------------------------- the run ---
+
+enum SinkKind { SINK_FILES, SINK_MEMORY, SINK_NONE };
+
+struct Sink {
+    SinkKind kind = SINK_NONE;
+    // memory
+    char* mem[2] = {nullptr, nullptr};
+    uint64_t cap[2] = {0, 0}, len[2] = {0, 0};
+    // files
+    int fd[2] = {-1, -1};
+    std::string names[2];
+    void close_files() {
+        for (int e = 0; e < 2; e++) if (fd[e] >= 0) { ::close(fd[e]); fd[e] = -1; }
+    }
+    ~Sink() { close_files(); }
+};
+
+struct Job {
+    uint64_t lo, hi;          // pair-instance range
+    std::string file_prefix;  // <prefix> or <prefix>_<hap>
+};
+
+void write_all(int fd, const uint8_t* p, uint64_t n, const std::string& name) {
+    while (n) {
+        ssize_t w = ::write(fd, p, n > (1u << 30) ? (1u << 30) : n);
+        if (w < 0) {
+            if (errno == EINTR) continue;
+            throw IoErr("Error writing to file " + name + ": " + std::strerror(errno));
+        }
+        p += w; n -= (uint64_t)w;
+    }
+}
+
+// Pairs per (haplotype, chromosome): threads -> haplotypes -> chromosomes
+// (write_reads_one_filetype_ src/hts.h:334-353, add_n_reads src/hts_illumina.h:410-418 and :620-644,
+//  write_reads_cpp_sep_files_ src/hts.h:527-529).  One "thread"; n_pairs = floor(n_reads / n_ends).
+// A reference run has one pseudo-haplotype.  Both the pooled and the sep_files haplotype paths first
+// split pairs over haplotypes by haplotype_probs, then each haplotype's pairs over its chromosomes
+// by size, so one routine serves both.
+std::vector<std::vector<uint64_t>> apportion(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, uint64_t n_pairs) {
+    uint64_t sub_seed = P->seed * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+    auto next_seed = [&]() { sub_seed = sub_seed * 6364136223846793005ull + 1442695040888963407ull; return sub_seed; };
+    const uint64_t n_chroms = c->chrom_off.size() - 1;
+    std::vector<std::vector<uint64_t>> out;
+    if (!use_haps) {
+        std::vector<double> w(n_chroms);
+        for (uint64_t i = 0; i < n_chroms; i++) w[i] = (double)(c->chrom_off[i + 1] - c->chrom_off[i]);
+        out.push_back(reads_per_group(n_pairs, w, next_seed()));
+        return out;
+    }
+    const uint64_t n_haps = c->haps.size();
+    if (!P->haplotype_probs) throw ArgErr("haplotype_probs is NULL");
+    std::vector<double> hp(P->haplotype_probs, P->haplotype_probs + n_haps);
+    bool any = false;
+    for (double v : hp) { if (!(v >= 0)) throw ArgErr("haplotype_probs must be >= 0"); any |= v > 0; }
+    if (!any) throw ArgErr("haplotype_probs must have at least one value > 0");
+    std::vector<uint64_t> hap_pairs = reads_per_group(n_pairs, hp, next_seed());
+    for (uint64_t h = 0; h < n_haps; h++) {
+        std::vector<double> w(n_chroms);
+        for (uint64_t i = 0; i < n_chroms; i++) w[i] = (double)c->haps[h].len[i];
+        out.push_back(reads_per_group(hap_pairs[h], w, next_seed()));
+    }
+    return out;
+}
+
+void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jlp_run_stats* stats) {
+    if (!P) throw ArgErr("params is NULL");
+    const int n_ends = P->paired || P->matepair ? 2 : 1;
+    const bool matepair = P->matepair != 0;
+    // --- argument checks the C++ layer of the reference performs
+    if (c->chrom_off.size() < 2) throw ArgErr("no reference genome has been set");
+    if (use_haps && c->haps.empty()) throw ArgErr("no haplotypes have been added");
+    if (!c->have_prof[0]) throw ArgErr("no quality profile for read 1");
+    if (n_ends == 2) {
+        if (!c->have_prof[1]) throw ArgErr("no quality profile for read 2");
+        if (c->tab[0].L != c->tab[1].L)   // src/hts_illumina.h:348-352
+            throw ArgErr("In IlluminaOneGenome constr., read lengths for R1 and R2 don't match.");
+    }
+    if (P->compress > 0) {
+        std::string m = P->comp_method ? P->comp_method : "";
+        if (m != "gzip" && m != "bgzip") throw ArgErr("\nUnrecognized compression method.");  // src/hts.h:470
+        throw Unsupported("compressed output (compress > 0) is not built yet; write plain FASTQ");
+    }
+    if (!(P->prob_dup >= 0 && P->prob_dup <= 1)) throw ArgErr("prob_dup must be in [0,1]");
+    const double insp[2] = {P->ins_prob1, P->ins_prob2}, delp[2] = {P->del_prob1, P->del_prob2};
+    for (int e = 0; e < n_ends; e++)
+        if (!(insp[e] >= 0 && insp[e] <= 1 && delp[e] >= 0 && delp[e] <= 1))
+            throw ArgErr("insertion / deletion probabilities must be in [0,1]");
+    if (P->frag_len_min < 1 || P->frag_len_min > P->frag_len_max)
+        throw ArgErr("frag_len_min must be >= 1 and <= frag_len_max");
+    if (!(P->frag_len_shape > 0 && P->frag_len_scale > 0)) throw ArgErr("fragment Gamma shape and scale must be > 0");
+    if (P->read_pool_size < 1) throw ArgErr("read_pool_size must be >= 1");
+    if (sink.kind == SINK_FILES && (!P->out_prefix || !*P->out_prefix)) throw ArgErr("out_prefix is empty");
+    const uint32_t L = (uint32_t)c->tab[0].L;
+    const uint64_t n_haps = c->haps.size();
+    const uint64_t n_chroms = c->chrom_off.size() - 1;
+    const bool sep = use_haps && P->sep_files;
+    if (use_haps && !P->haplotype_probs) throw ArgErr("haplotype_probs is NULL");
+
+    // --- barcodes (T/C/A/G only, R/hts_illumina.R:385-391)
+    std::vector<std::string> barcodes(use_haps ? n_haps : 1);
+    if (P->barcodes)
+        for (size_t i = 0; i < barcodes.size(); i++) barcodes[i] = P->barcodes[i] ? P->barcodes[i] : "";
+    for (const std::string& bcs : barcodes) {
+        for (char ch : bcs)
+            if (ch != 'T' && ch != 'C' && ch != 'A' && ch != 'G') throw ArgErr("barcodes may only contain T, C, A, G");
+        if (bcs.size() >= L) throw ArgErr("a barcode is as long as the read");
+    }
+
+    // --- apportion pairs: threads -> haplotypes -> chromosomes
+    //     (write_reads_one_filetype_ src/hts.h:334-353, add_n_reads src/hts_illumina.h:410-418, :620-644,
+    //      write_reads_cpp_sep_files_ src/hts.h:527-529); one "thread", n_pairs = floor(n_reads / n_ends)
+    const uint64_t n_pairs = P->n_reads / n_ends;
+    const std::vector<std::vector<uint64_t>> counts = apportion(c, use_haps, P, n_pairs);
+
+    std::vector<uint64_t> group_off(1, 0);
+    std::vector<GroupDev> groups;
+    std::vector<uint8_t> strpool;
+    std::vector<Job> jobs;
+    uint64_t min_len_with_reads = ~0ull;
+    auto add_group = [&](const std::string& gname, uint64_t chrom, const uint8_t* seq, uint64_t len,
+                         const std::string& bc, uint64_t count) {
+        GroupDev g;
+        std::string pre = "@" + gname + "-" + c->chrom_names[chrom] + "-";
+        g.seq = seq; g.len = len;
+        g.prefix_off = (uint32_t)strpool.size(); g.prefix_len = (uint32_t)pre.size();
+        strpool.insert(strpool.end(), pre.begin(), pre.end());
+        g.bc_off = (uint32_t)strpool.size(); g.bc_len = (uint32_t)bc.size();
+        strpool.insert(strpool.end(), bc.begin(), bc.end());
+        groups.push_back(g);
+        group_off.push_back(group_off.back() + count);
+        if (count > 0 && len < min_len_with_reads) min_len_with_reads = len;
+        if (count > 0 && len == 0) throw ArgErr("a chromosome of length 0 was given reads");
+    };
+    const std::string prefix = P->out_prefix ? P->out_prefix : "";
+    if (!use_haps) {
+        for (uint64_t i = 0; i < n_chroms; i++)
+            add_group(c->genome_name, i, c->genome.p + c->chrom_off[i], c->chrom_off[i + 1] - c->chrom_off[i],
+                      barcodes[0], counts[0][i]);
+        jobs.push_back(Job{0, n_pairs, prefix});
+    } else {
+        for (uint64_t h = 0; h < n_haps; h++) {
+            const HapDev& H = c->haps[h];
+            uint64_t lo = group_off.back();
+            for (uint64_t i = 0; i < n_chroms; i++) add_group(H.name, i, H.seq[i], H.len[i], barcodes[h], counts[h][i]);
+            if (sep) jobs.push_back(Job{lo, group_off.back(), prefix + "_" + H.name});
+        }
+        if (!sep) jobs.push_back(Job{0, group_off.back(), prefix});
+    }
+    if (group_off.back() != n_pairs) throw std::runtime_error("internal: apportioning does not add up");
+
+    // --- thresholds
+    GenParams gp;
+    std::memset(&gp, 0, sizeof gp);
+    gp.seed = P->seed;
+    gp.n_ends = n_ends; gp.L = L; gp.matepair = matepair;
+    gp.row_stride = (L + 15u) & ~15u;
+    gp.pool_pairs = (P->read_pool_size + n_ends - 1) / n_ends;   // pool closes at >= read_pool_size reads
+    Thr td = thr_double_lt(P->prob_dup);
+    gp.c_dup = td.thr; gp.dup_never = td.thr == 0;
+    gp.c_rev = thr_ld_lt(0.5).thr;
+    for (int e = 0; e < n_ends; e++) {
+        EndDev& E = gp.end[e];
+        E.meta = c->d_meta[e].p; E.entry = c->d_entry[e].p; E.coin = c->d_coin[e].p;
+        E.mis16 = c->d_mis16[e].p; E.mis = c->d_mis[e].p;
+        E.entry_n = (uint32_t)c->tab[e].entry.size();
+        Thr ta = thr_double_le(insp[e] + delp[e]);   // u > ins + del  <=>  x >= tA
+        Thr ti = thr_double_le(insp[e]);             // u > ins        <=>  x >= tI
+        E.tA = ta.thr; E.tA_all = ta.all; E.tI = ti.thr; E.tI_all = ti.all;
+        E.hA = ta.all ? 0x10000u : (uint32_t)(ta.thr >> 48);
+    }
+    std::vector<uint64_t> frag = frag_table(P->frag_len_shape, P->frag_len_scale, P->frag_len_min, P->frag_len_max);
+    c->d_frag.upload(frag, c->s_compute);
+    c->d_group_off.upload(group_off, c->s_compute);
+    c->d_groups.upload(groups, c->s_compute);
+    c->d_strpool.upload(strpool, c->s_compute);
+    c->d_status.ensure(1);
+    CK(cudaMemsetAsync(c->d_status.p, 0, sizeof(uint32_t), c->s_compute));
+    c->h2d_bytes += frag.size() * 8 + group_off.size() * 8 + groups.size() * sizeof(GroupDev) + strpool.size();
+    gp.frag_cdf = c->d_frag.p; gp.frag_n = (uint32_t)frag.size(); gp.frag_min = P->frag_len_min;
+    gp.group_off = c->d_group_off.p; gp.n_groups = (uint32_t)groups.size();
+    gp.groups = c->d_groups.p; gp.strpool = c->d_strpool.p; gp.status = c->d_status.p;
+
+    size_t smem = gen_smem_bytes(gp);
+    if (smem > 100 * 1024) smem = 0;               // big profiles: tables stay in global / L1
+
+    // --- batch buffers
+    uint64_t max_job = 0;
+    for (const Job& j : jobs) max_job = std::max(max_job, j.hi - j.lo);
+    uint64_t B = P->batch_pairs ? P->batch_pairs : (1ull << 20);
+    B = std::max<uint64_t>(1, std::min(B, max_job));
+    uint32_t max_prefix = 0;
+    for (const GroupDev& g : groups) max_prefix = std::max(max_prefix, g.prefix_len);
+    const uint64_t max_rec = (uint64_t)max_prefix + 20 + 5 + 2ull * L + 4;
+    const uint64_t n_rec_max = B * n_ends;
+    const uint32_t nsb_max = (uint32_t)((B + kScanBlock - 1) / kScanBlock);
+    const bool need_host = sink.kind != SINK_NONE;
+    for (Slot& s : c->slot) {
+        s.seq.ensure(n_rec_max * gp.row_stride);
+        s.qual.ensure(n_rec_max * gp.row_stride);
+        s.rec.ensure(n_rec_max);
+        s.rec_len.ensure(n_rec_max);
+        s.rec_local.ensure(n_rec_max);
+        s.block_tot.ensure((size_t)nsb_max * 2);
+        s.block_base.ensure((size_t)nsb_max * 2);
+        s.totals.ensure(2);
+        s.h_totals.ensure(2);
+        for (int e = 0; e < n_ends; e++) {
+            s.out[e].ensure(B * max_rec);
+            if (need_host) s.h_out[e].ensure(B * max_rec);
+        }
+        for (cudaEvent_t& ev : s.ev) if (!ev) CK(cudaEventCreate(&ev));
+        s.busy = false;
+    }
+
+    jlp_run_stats st;
+    std::memset(&st, 0, sizeof st);
+
+    // finish a batch: wait for its totals, copy the FASTQ to the host, hand it to the sink
+    auto finish = [&](Slot& s, const Job& job) {
+        (void)job;
+        CK(cudaEventSynchronize(s.ev[3]));
+        float ms_gen = 0, ms_all = 0, ms_fmt = 0;
+        CK(cudaEventElapsedTime(&ms_gen, s.ev[0], s.ev[1]));
+        CK(cudaEventElapsedTime(&ms_fmt, s.ev[2], s.ev[3]));
+        CK(cudaEventElapsedTime(&ms_all, s.ev[0], s.ev[3]));
+        st.gen_ms += ms_gen; st.fmt_ms += ms_fmt; st.device_ms += ms_all;
+        for (int e = 0; e < n_ends; e++) st.bytes_out[e] += s.h_totals.p[e];
+        st.pairs += s.pairs;
+        st.batches++;
+        if (need_host) {
+            for (int e = 0; e < n_ends; e++) {
+                uint64_t n = s.h_totals.p[e];
+                CK(cudaMemcpyAsync(s.h_out[e].p, s.out[e].p, n, cudaMemcpyDeviceToHost, c->s_copy));
+                st.d2h_bytes += n;
+            }
+            CK(cudaEventRecord(s.ev[4], c->s_copy));
+            CK(cudaEventSynchronize(s.ev[4]));
+            for (int e = 0; e < n_ends; e++) {
+                uint64_t n = s.h_totals.p[e];
+                if (sink.kind == SINK_FILES) write_all(sink.fd[e], s.h_out[e].p, n, sink.names[e]);
+                else {
+                    if (sink.len[e] + n <= sink.cap[e]) std::memcpy(sink.mem[e] + sink.len[e], s.h_out[e].p, n);
+                    sink.len[e] += n;
+                }
+            }
+        }
+        if (P->progress_cb) P->progress_cb(P->cb_user, (uint64_t)s.pairs * n_ends);
+        s.busy = false;
+    };
+
+    const uint32_t S = P->shard_count > 1 ? P->shard_count : 1;
+    const uint32_t si = P->shard_count > 1 ? P->shard_index : 0;
+    if (si >= S) throw ArgErr("shard_index >= shard_count");
+
+    for (const Job& job : jobs) {
+        if (P->abort_cb && P->abort_cb(P->cb_user)) throw Aborted();   // src/hts.h:536
+        if (sink.kind == SINK_FILES) {
+            sink.close_files();
+            for (int e = 0; e < n_ends; e++) {
+                sink.names[e] = job.file_prefix + "_R" + std::to_string(e + 1) + ".fq";   // src/hts.h:344
+                sink.fd[e] = ::open(sink.names[e].c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+                if (sink.fd[e] < 0) throw IoErr("Unable to open file " + sink.names[e] + ".\n");  // src/io.h:288-290
+            }
+        }
+        const uint64_t nj = job.hi - job.lo;
+        const uint64_t lo = job.lo + nj / S * si + std::min<uint64_t>(si, nj % S);
+        const uint64_t hi = lo + nj / S + (si < nj % S ? 1 : 0);
+        int cur = 0;
+        Slot* prev = nullptr;
+        for (uint64_t b0 = lo; b0 < hi; b0 += B) {
+            Slot& s = c->slot[cur];
+            if (s.busy) finish(s, job);
+            const uint32_t np = (uint32_t)std::min<uint64_t>(B, hi - b0);
+            gp.job_lo = job.lo; gp.job_hi = job.hi; gp.batch_lo = b0; gp.batch_pairs = np;
+            gp.seq = s.seq.p; gp.qual = s.qual.p; gp.rec = s.rec.p; gp.rec_len = s.rec_len.p;
+            const uint32_t n_rec = np * n_ends;
+            const uint32_t nsb = (np + kScanBlock - 1) / kScanBlock;
+            CK(cudaEventRecord(s.ev[0], c->s_compute));
+            CK(launch_gen(gp, smem, c->s_compute));
+            CK(cudaEventRecord(s.ev[1], c->s_compute));
+            CK(launch_scan(s.rec_len.p, n_rec, n_ends, kScanBlock, s.rec_local.p, s.block_tot.p, s.block_base.p,
+                           s.totals.p, c->s_compute));
+            CK(cudaEventRecord(s.ev[2], c->s_compute));
+            FmtParams fp;
+            std::memset(&fp, 0, sizeof fp);
+            fp.n_records = n_rec; fp.n_ends = n_ends; fp.row_stride = gp.row_stride; fp.scan_block = kScanBlock;
+            fp.seq = s.seq.p; fp.qual = s.qual.p; fp.rec = s.rec.p; fp.rec_local = s.rec_local.p;
+            fp.block_base = s.block_base.p; fp.n_scan_blocks = nsb;
+            fp.groups = c->d_groups.p; fp.strpool = c->d_strpool.p;
+            fp.out[0] = s.out[0].p; fp.out[1] = s.out[1].p;
+            CK(launch_fmt(fp, c->s_compute));
+            CK(cudaMemcpyAsync(s.h_totals.p, s.totals.p, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->s_compute));
+            CK(cudaEventRecord(s.ev[3], c->s_compute));
+            st.kernel_launches += 4;
+            s.pairs = np; s.busy = true;
+            if (prev && prev->busy) finish(*prev, job);
+            prev = &s;
+            cur ^= 1;
+            if (P->abort_cb && P->abort_cb(P->cb_user)) {
+                for (Slot& t : c->slot) if (t.busy) { cudaEventSynchronize(t.ev[3]); t.busy = false; }
+                throw Aborted();
+            }
+        }
+        for (Slot& s : c->slot) if (s.busy) finish(s, job);
+    }
+    sink.close_files();
+    uint32_t status = 0;
+    CK(cudaMemcpy(&status, c->d_status.p, sizeof status, cudaMemcpyDeviceToHost));
+    if (status & 1u) throw ArgErr("a barcode is at least as long as a read's template (fragment or chromosome too short)");
+    st.h2d_bytes = c->h2d_bytes;
+    if (stats) *stats = st;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ C ABI ---
+
+extern "C" {
+
+int jlp_ctx_create(int device, jlp_ctx** out) {
+    if (!out) return fail(nullptr, JLP_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, JLP_ERR_NO_DEVICE,
+                    std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                        "); this library has no CPU fallback");
+    if (device < 0 || device >= n) return fail(nullptr, JLP_ERR_ARG, "device index out of range");
+    std::unique_ptr<jlp_ctx> c(new jlp_ctx);
+    c->device = device;
+    int rc = guarded(c.get(), [&]() {
+        CK(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
+    });
+    if (rc != JLP_OK) { g_create_error = c->err; return rc; }
+    *out = c.release();
+    return JLP_OK;
+}
+
+void jlp_ctx_destroy(jlp_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    free_haps(c);
+    for (Slot& s : c->slot) for (cudaEvent_t ev : s.ev) if (ev) cudaEventDestroy(ev);
+    if (c->s_compute) cudaStreamDestroy(c->s_compute);
+    if (c->s_copy) cudaStreamDestroy(c->s_copy);
+    delete c;
+}
+
+const char* jlp_last_error(const jlp_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int jlp_set_genome(jlp_ctx* c, const char* bases, const uint64_t* chrom_off, uint64_t n_chroms,
+                   const char* const* chrom_names, const char* genome_name) {
+    if (!c) return JLP_ERR_ARG;
+    return guarded(c, [&]() {
+        if (!bases || !chrom_off || !chrom_names || n_chroms == 0) throw ArgErr("empty genome");
+        for (uint64_t i = 0; i < n_chroms; i++)
+            if (chrom_off[i + 1] < chrom_off[i]) throw ArgErr("chrom_off must be non-decreasing");
+        free_haps(c);
+        c->chrom_off.assign(chrom_off, chrom_off + n_chroms + 1);
+        c->chrom_names.clear();
+        for (uint64_t i = 0; i < n_chroms; i++) c->chrom_names.push_back(chrom_names[i] ? chrom_names[i] : "");
+        c->genome_name = genome_name ? genome_name : "REF";
+        if (chrom_off[0] != 0) throw ArgErr("chrom_off[0] must be 0");
+        uint64_t total = chrom_off[n_chroms];
+        c->genome.ensure(total + 64);
+        CK(cudaMemcpyAsync(c->genome.p, bases, total, cudaMemcpyHostToDevice, c->s_compute));
+        CK(cudaStreamSynchronize(c->s_compute));
+        c->h2d_bytes += total;
+    });
+}
+
+int jlp_clear_haplotypes(jlp_ctx* c) {
+    if (!c) return JLP_ERR_ARG;
+    return guarded(c, [&]() { free_haps(c); });
+}
+
+int jlp_add_haplotype(jlp_ctx* c, const char* name, const uint64_t* n_muts, const uint64_t* const* old_pos,
+                      const uint64_t* const* new_pos, const uint64_t* const* nuc_off,
+                      const char* const* nuc_pool, const uint64_t* nuc_pool_len,
+                      const uint64_t* chrom_sizes, uint64_t* hap_index) {
+    if (!c) return JLP_ERR_ARG;
+    return guarded(c, [&]() {
+        if (c->chrom_off.size() < 2) throw ArgErr("set the reference genome first");
+        if (!n_muts || !chrom_sizes) throw ArgErr("n_muts / chrom_sizes is NULL");
+        const uint64_t nc = c->chrom_off.size() - 1;
+        HapDev H;
+        H.name = name ? name : "";
+        DevBuf<uint64_t> d_old, d_new, d_off;
+        DevBuf<int64_t> d_sm;
+        DevBuf<uint8_t> d_pool;
+        try {
+            for (uint64_t ci = 0; ci < nc; ci++) {
+                const uint64_t M = n_muts[ci];
+                const uint64_t ref_size = c->chrom_off[ci + 1] - c->chrom_off[ci];
+                const uint8_t* ref = c->genome.p + c->chrom_off[ci];
+                if (M == 0) {   // get_chrom_full returns the reference string (src/hap_classes.cpp:82)
+                    if (chrom_sizes[ci] != ref_size) throw ArgErr("chromosome without mutations must keep the reference size");
+                    H.seq.push_back(ref); H.len.push_back(ref_size);
+                    continue;
+                }
+                // size_modifier per record, src/hap_classes.h:314-333
+                std::vector<int64_t> sm(M);
+                for (uint64_t i = 0; i < M; i++) {
+                    if (i && new_pos[ci][i] < new_pos[ci][i - 1]) throw ArgErr("mutations must be sorted by new_pos");
+                    int64_t s = (i + 1 < M) ? (int64_t)(new_pos[ci][i + 1] - old_pos[ci][i + 1])
+                                            : (int64_t)(chrom_sizes[ci] - ref_size);
+                    sm[i] = s + (int64_t)(old_pos[ci][i] - new_pos[ci][i]);
+                }
+                std::vector<uint64_t> vo(old_pos[ci], old_pos[ci] + M), vn(new_pos[ci], new_pos[ci] + M),
+                    vf(nuc_off[ci], nuc_off[ci] + M);
+                std::vector<uint8_t> vp(nuc_pool[ci], nuc_pool[ci] + nuc_pool_len[ci]);
+                d_old.upload(vo, c->s_compute); d_new.upload(vn, c->s_compute); d_off.upload(vf, c->s_compute);
+                d_sm.upload(sm, c->s_compute); d_pool.upload(vp, c->s_compute);
+                c->h2d_bytes += M * 32 + vp.size();
+                uint8_t* out = nullptr;
+                CK(cudaMalloc(reinterpret_cast<void**>(&out), chrom_sizes[ci] + 64));
+                H.owned.push_back(out);
+                CK(launch_materialize(ref, ref_size, M, d_old.p, d_new.p, d_sm.p, d_off.p, d_pool.p, chrom_sizes[ci],
+                                      out, c->s_compute));
+                CK(cudaStreamSynchronize(c->s_compute));
+                H.seq.push_back(out); H.len.push_back(chrom_sizes[ci]);
+            }
+        } catch (...) {
+            for (uint8_t* p : H.owned) cudaFree(p);
+            throw;
+        }
+        if (hap_index) *hap_index = c->haps.size();
+        c->haps.push_back(std::move(H));
+    });
+}
+
+int jlp_get_haplotype_chrom(jlp_ctx* c, uint64_t hap, uint64_t chrom, char* out, uint64_t cap, uint64_t* len) {
+    if (!c) return JLP_ERR_ARG;
+    return guarded(c, [&]() {
+        if (hap >= c->haps.size() || chrom >= c->haps[hap].seq.size()) throw ArgErr("haplotype / chromosome index out of range");
+        uint64_t n = c->haps[hap].len[chrom];
+        if (len) *len = n;
+        if (n > cap) throw ArgErr("output buffer too small");
+        if (n) CK(cudaMemcpy(out, c->haps[hap].seq[chrom], n, cudaMemcpyDeviceToHost));
+    });
+}
+
+int jlp_set_profile(jlp_ctx* c, int end, uint64_t read_length, const uint32_t* nq, const double* probs,
+                    const uint8_t* quals) {
+    if (!c) return JLP_ERR_ARG;
+    return guarded(c, [&]() {
+        if (end < 0 || end > 1) throw ArgErr("end must be 0 or 1");
+        if (!nq || !probs || !quals) throw ArgErr("profile arrays are NULL");
+        if (read_length >= 65536) throw ArgErr("read_length too large");
+        build_end_tables(read_length, nq, probs, quals, c->tab[end]);
+        const EndTables& t = c->tab[end];
+        c->d_meta[end].upload(t.meta, c->s_compute);
+        c->d_entry[end].upload(t.entry, c->s_compute);
+        c->d_coin[end].upload(t.coin, c->s_compute);
+        c->d_mis16[end].upload(t.mis16, c->s_compute);
+        c->d_mis[end].upload(t.mis, c->s_compute);
+        CK(cudaStreamSynchronize(c->s_compute));
+        c->h2d_bytes += t.meta.size() * 4 + t.entry.size() * 12 + 256 * 10;
+        c->have_prof[end] = true;
+    });
+}
+
+int jlp_illumina_ref(jlp_ctx* c, const jlp_illumina_params* p, jlp_run_stats* stats) {
+    if (!c) return JLP_ERR_ARG;
+    return guarded(c, [&]() { Sink s; s.kind = SINK_FILES; run(c, false, p, s, stats); });
+}
+int jlp_illumina_hap(jlp_ctx* c, const jlp_illumina_params* p, jlp_run_stats* stats) {
+    if (!c) return JLP_ERR_ARG;
+    return guarded(c, [&]() { Sink s; s.kind = SINK_FILES; run(c, true, p, s, stats); });
+}
+
+int jlp_illumina_to_memory(jlp_ctx* c, int use_haplotypes, const jlp_illumina_params* p, char* out1, uint64_t cap1,
+                           uint64_t* len1, char* out2, uint64_t cap2, uint64_t* len2, jlp_run_stats* stats) {
+    if (!c) return JLP_ERR_ARG;
+    return guarded(c, [&]() {
+        Sink s;
+        s.kind = SINK_MEMORY;
+        s.mem[0] = out1; s.cap[0] = out1 ? cap1 : 0;
+        s.mem[1] = out2; s.cap[1] = out2 ? cap2 : 0;
+        run(c, use_haplotypes != 0, p, s, stats);
+        if (len1) *len1 = s.len[0];
+        if (len2) *len2 = s.len[1];
+        if (s.len[0] > s.cap[0] || s.len[1] > s.cap[1]) throw ArgErr("output buffer too small");
+    });
+}
+
+int jlp_illumina_device_only(jlp_ctx* c, int use_haplotypes, const jlp_illumina_params* p, jlp_run_stats* stats) {
+    if (!c) return JLP_ERR_ARG;
+    return guarded(c, [&]() { Sink s; s.kind = SINK_NONE; run(c, use_haplotypes != 0, p, s, stats); });
+}
+
+int jlp_illumina_group_counts(jlp_ctx* c, int use_haplotypes, const jlp_illumina_params* p, uint64_t* counts,
+                              uint64_t cap, uint64_t* n_groups) {
+    if (!c) return JLP_ERR_ARG;
+    return guarded(c, [&]() {
+        if (!p) throw ArgErr("params is NULL");
+        if (c->chrom_off.size() < 2) throw ArgErr("no reference genome has been set");
+        if (use_haplotypes && c->haps.empty()) throw ArgErr("no haplotypes have been added");
+        const int n_ends = p->paired || p->matepair ? 2 : 1;
+        std::vector<std::vector<uint64_t>> cnt = apportion(c, use_haplotypes != 0, p, p->n_reads / n_ends);
+        uint64_t n = 0;
+        for (const auto& v : cnt) n += v.size();
+        if (n_groups) *n_groups = n;
+        if (n > cap) throw ArgErr("counts buffer too small");
+        uint64_t k = 0;
+        for (const auto& v : cnt) for (uint64_t x : v) counts[k++] = x;
+    });
+}
+
+// ---- host-side pieces (no device) ----
+
+int jlp_reads_per_group(uint64_t n_reads, const double* probs, uint64_t n, uint64_t seed, uint64_t* out) {
+    if (!probs || !out) return JLP_ERR_ARG;
+    std::vector<uint64_t> r = reads_per_group(n_reads, std::vector<double>(probs, probs + n), seed);
+    std::copy(r.begin(), r.end(), out);
+    return JLP_OK;
+}
+int jlp_alias_build(const double* probs, uint64_t n, double* prob_out, uint64_t* alias_out) {
+    if (!probs || !prob_out || !alias_out) return JLP_ERR_ARG;
+    alias_build(probs, n, prob_out, alias_out);
+    return JLP_OK;
+}
+int jlp_threshold(int kind, double p, uint64_t* thr, int* all) {
+    Thr t;
+    if (kind == 1) t = thr_double_lt(p);
+    else if (kind == 2) t = thr_double_le(p);
+    else if (kind == 3) t = thr_ld_lt(p);
+    else return JLP_ERR_ARG;
+    if (thr) *thr = t.thr;
+    if (all) *all = t.all;
+    return JLP_OK;
+}
+uint64_t jlp_unif_expr(int kind, uint64_t x, double p, uint64_t n) {
+    (void)p;
+    switch (kind) {
+    case 0: return mul_floor_x87(x, n);
+    case 4: return nqual_x87(x);
+    case 5: {
+        double u = (x == ~0ull) ? 1.0 : (double)(x + 1) * 5.421010862427522170037e-20;
+        return (uint64_t)(u * (double)n);
+    }
+    case 6: return ins_base_index(x);
+    }
+    return 0;
+}
+int jlp_frag_table(double shape, double scale, uint64_t frag_min, uint64_t frag_max, uint64_t* cdf, uint64_t cap,
+                   uint64_t* n) {
+    std::vector<uint64_t> t = frag_table(shape, scale, frag_min, frag_max);
+    if (n) *n = t.size();
+    if (t.size() > cap) return JLP_ERR_ARG;
+    if (cdf) std::copy(t.begin(), t.end(), cdf);
+    return JLP_OK;
+}
+void jlp_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    U4 w = philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
+    out[0] = w.w0; out[1] = w.w1; out[2] = w.w2; out[3] = w.w3;
+}
+uint64_t jlp_draw_pos(uint64_t seed, uint64_t j, uint32_t end, uint32_t purpose, uint32_t pos) {
+    if (purpose == PU_INS) return slow64(seed, j, end, PU_INS, pos);
+    uint32_t H;
+    if (purpose == PU_INDEL) {
+        U4 w = draw_block(seed, j, pos >> 3, PL_INDEL, end);
+        uint32_t f = pos & 7u;
+        uint32_t v = (f >> 1) == 0 ? w.w0 : (f >> 1) == 1 ? w.w1 : (f >> 1) == 2 ? w.w2 : w.w3;
+        H = (f & 1) ? (v >> 16) : (v & 0xffffu);
+    } else {
+        U4 w = draw_block(seed, j, pos >> 1, PL_QUAL, end);
+        uint32_t a = (pos & 1) ? w.w2 : w.w0, b = (pos & 1) ? w.w3 : w.w1;
+        H = purpose == PU_DIE ? (a & 0xffffu) : purpose == PU_COIN ? (a >> 16) : purpose == PU_MIS ? (b & 0xffffu) : (b >> 16);
+    }
+    return full_draw(H, seed, j, end, purpose, pos);
+}
+uint64_t jlp_draw_pair(uint64_t seed, uint64_t j, int which) {
+    U4 w = draw_block(seed, j, (uint32_t)(which >> 1), PL_PAIR, 0);
+    return (which & 1) ? hi64(w) : lo64(w);
+}
+
+const char* jlp_version(void) { return "jackalope-b200 0.1 (sm_100a)"; }
+
+}  // extern "C"

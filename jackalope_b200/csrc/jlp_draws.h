@@ -1,0 +1,170 @@
+// Draw addressing and exact uniform arithmetic, shared by host and device code.
+//
+// The reference consumes one pcg64 output per uniform draw, sequentially, and
+// turns it into u = (x+1)/2^64 with x87 long-double arithmetic
+// (/root/reference/src/pcg.h:21,99-101).  Here every logical draw
+// X(pair instance j, end, purpose, position) is a pure function of a
+// Philox4x32-10 counter, so a read does not depend on which GPU, CTA or thread
+// produced it:
+//
+//   counter = (j_lo, j_hi, block, plane | end << 8),  key = (seed_lo, seed_hi)
+//   plane PAIR : block 0 -> X_fraglen = w1:w0, X_start = w3:w2
+//                block 1 -> X_strand  = w1:w0, X_dup   = w3:w2
+//   plane INDEL: block t>>3, 16-bit field t&7      -> high 16 bits of X_indel(t)
+//   plane QUAL : block p>>1, base h = p&1:
+//                die = w[2h] & 0xffff, coin = w[2h] >> 16,
+//                mis = w[2h+1] & 0xffff, sub = w[2h+1] >> 16   (high 16 bits)
+//   plane SLOW : block pos<<3 | purpose, S = w1:w0 -> low 48 bits of X
+//                (the whole of X for purpose INS)
+//   X = H << 48 | (S & (2^48 - 1))
+//
+// A kernel decides on the 16 high bits alone whenever that is provably enough
+// and fetches the SLOW plane only for the (rare) ambiguous cases, so the result
+// always equals the one a full 64-bit draw gives.
+//
+// The integer forms below reproduce the reference's floating-point expressions
+// bit for bit, including the x87 round-to-64-bit-mantissa step (tests/
+// test_exact_arith.py checks them against the compiled reference expressions).
+#ifndef JLP_DRAWS_H
+#define JLP_DRAWS_H
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define JLP_HD __host__ __device__ __forceinline__
+#else
+#define JLP_HD inline
+#endif
+
+namespace jlp {
+
+enum Plane : uint32_t { PL_PAIR = 0, PL_INDEL = 1, PL_QUAL = 2, PL_SLOW = 3 };
+enum Purpose : uint32_t { PU_INDEL = 0, PU_DIE = 1, PU_COIN = 2, PU_MIS = 3, PU_SUB = 4, PU_INS = 5 };
+
+struct U4 { uint32_t w0, w1, w2, w3; };
+
+JLP_HD void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+#if defined(__CUDA_ARCH__)
+    lo = a * b;
+    hi = __umulhi(a, b);
+#else
+    uint64_t p = (uint64_t)a * b;
+    lo = (uint32_t)p;
+    hi = (uint32_t)(p >> 32);
+#endif
+}
+
+// Philox4x32-10, Salmon et al. SC'11, standard multipliers and Weyl constants.
+JLP_HD U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t h0, l0, h1, l1;
+        mulhilo(0xD2511F53u, c0, h0, l0);
+        mulhilo(0xCD9E8D57u, c2, h1, l1);
+        c0 = h1 ^ c1 ^ k0;
+        c2 = h0 ^ c3 ^ k1;
+        c1 = l1;
+        c3 = l0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    U4 o = {c0, c1, c2, c3};
+    return o;
+}
+
+JLP_HD U4 draw_block(uint64_t seed, uint64_t j, uint32_t block, uint32_t plane, uint32_t end) {
+    return philox4x32_10((uint32_t)j, (uint32_t)(j >> 32), block, plane | (end << 8),
+                         (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+
+JLP_HD uint64_t lo64(const U4& w) { return ((uint64_t)w.w1 << 32) | w.w0; }
+JLP_HD uint64_t hi64(const U4& w) { return ((uint64_t)w.w3 << 32) | w.w2; }
+
+JLP_HD uint64_t slow64(uint64_t seed, uint64_t j, uint32_t end, uint32_t purpose, uint32_t pos) {
+    return lo64(draw_block(seed, j, (pos << 3) | purpose, PL_SLOW, end));
+}
+JLP_HD uint64_t full_draw(uint32_t H, uint64_t seed, uint64_t j, uint32_t end, uint32_t purpose, uint32_t pos) {
+    return ((uint64_t)H << 48) | (slow64(seed, j, end, purpose, pos) & 0xFFFFFFFFFFFFull);
+}
+
+// ---- exact restatements of the reference's uses of u = runif_01(x) ----
+
+// bit length of a 128-bit value (hi:lo)
+JLP_HD int bitlen128(uint64_t hi, uint64_t lo) {
+#if defined(__CUDA_ARCH__)
+    return hi ? 128 - __clzll((long long)hi) : (lo ? 64 - __clzll((long long)lo) : 0);
+#else
+    return hi ? 128 - __builtin_clzll(hi) : (lo ? 64 - __builtin_clzll(lo) : 0);
+#endif
+}
+
+// Round the 128-bit integer (hi:lo) to 64 significant bits, ties to even -- what
+// an x87 multiply/add does to an exact result.  Returns the rounded value as
+// (hi:lo) again (it may gain one bit).
+JLP_HD void round64(uint64_t& hi, uint64_t& lo) {
+    int B = bitlen128(hi, lo);
+    if (B <= 64) return;
+    int d = B - 64;                      // low bits to drop; operands here keep d <= 40
+    uint64_t q = (hi << (64 - d)) | (lo >> d);
+    uint64_t rem = lo & ((1ull << d) - 1);
+    uint64_t half = 1ull << (d - 1);
+    if (rem > half || (rem == half && (q & 1))) {
+        q++;
+        if (q == 0) {                    // mantissa overflowed: value is 2^(64+d)
+            hi = 1ull << d;
+            lo = 0;
+            return;
+        }
+    }
+    hi = q >> (64 - d);
+    lo = q << d;
+}
+
+// (uint64)(runif_01(x) * n) with the product formed in 80-bit long double
+// (src/alias_sampler.h:55 die roll; src/hts_illumina.h:216 n=4, :254 n=3).
+// y = x + 1 <= 2^64; product y*n/2^64 rounded to a 64-bit mantissa, then truncated.
+JLP_HD uint64_t mul_floor_x87(uint64_t x, uint64_t n) {
+    // P = (x + 1) * n as 128 bits
+    uint64_t hi, lo;
+#if defined(__CUDA_ARCH__)
+    lo = x * n;
+    hi = __umul64hi(x, n);
+#else
+    unsigned __int128 p = (unsigned __int128)x * n;
+    lo = (uint64_t)p;
+    hi = (uint64_t)(p >> 64);
+#endif
+    uint64_t lo2 = lo + n;
+    hi += (lo2 < lo);
+    lo = lo2;
+    round64(hi, lo);
+    return hi;                           // floor(P' / 2^64)
+}
+
+// (uint8)(runif_01(x) * 10 + 33)  (src/hts_illumina.h:238): two x87 roundings.
+JLP_HD uint32_t nqual_x87(uint64_t x) {
+    uint64_t hi, lo;
+#if defined(__CUDA_ARCH__)
+    lo = x * 10ull;
+    hi = __umul64hi(x, 10ull);
+#else
+    unsigned __int128 p = (unsigned __int128)x * 10u;
+    lo = (uint64_t)p;
+    hi = (uint64_t)(p >> 64);
+#endif
+    uint64_t lo2 = lo + 10ull;
+    hi += (lo2 < lo);
+    lo = lo2;
+    round64(hi, lo);                     // u * 10
+    hi += 33;                            // + '!' (exact), then rounded again
+    round64(hi, lo);
+    return (uint32_t)(hi & 0xff);
+}
+
+// bases[(uint64)(runif_01(x) * 4.0)] index (src/hts_illumina.h:216): exact, 0..4
+JLP_HD uint32_t ins_base_index(uint64_t x) {
+    return x == ~0ull ? 4u : (uint32_t)((x + 1) >> 62);
+}
+
+}  // namespace jlp
+#endif

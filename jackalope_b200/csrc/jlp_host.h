@@ -1,0 +1,64 @@
+// Host-side model preparation for the Illumina kernels: alias tables, integer
+// thresholds, fragment-length table, read apportioning.  Plain C++ (g++), no
+// CUDA.  Each function cites the reference code it stands in for
+// (paths relative to /root/reference).
+#ifndef JLP_HOST_H
+#define JLP_HOST_H
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace jlp {
+
+// --- comparison thresholds -------------------------------------------------
+// A comparison of u = runif_01(x) against a constant is monotone in x, so it
+// equals an integer comparison on x.  `thr` counts the x for which the
+// predicate holds from the low end; all == true means every x (count 2^64).
+struct Thr {
+    uint64_t thr;
+    bool all;
+};
+// #{x : (double)u <  p}   src/alias_sampler.h:57-58, src/hts_illumina.h:251-252, src/hts.h:265-266
+Thr thr_double_lt(double p);
+// #{x : !((double)u > p)} src/hts_illumina.cpp:132-135
+Thr thr_double_le(double p);
+// #{x : u < p} (long double compare) src/hts_illumina.cpp:352
+Thr thr_ld_lt(double p);
+
+// --- alias tables ------------------------------------------------------------
+// AliasSampler::construct, src/alias_sampler.h:68-106
+void alias_build(const double* probs, uint64_t n, double* Prob, uint64_t* Alias);
+
+// One read end's quality/error model in the layout the kernels read.
+struct EndTables {
+    uint64_t L = 0;
+    std::vector<uint32_t> meta;     // [4*L]  offset << 8 | n
+    std::vector<uint32_t> entry;    // per table slot: coin16 | q_self << 16 | q_alias << 24
+    std::vector<uint64_t> coin;     // full coin threshold per slot (slow path)
+    std::vector<uint16_t> mis16;    // [256] high 16 bits of the mismatch threshold per quality
+    std::vector<uint64_t> mis;      // [256] full mismatch threshold per quality
+    uint32_t max_n = 0;
+};
+// IlluminaQualityError ctor (src/hts_illumina.h:154-189) + IllQualPos ctor (:102-116).
+// Throws std::runtime_error with the reference's message on malformed input.
+void build_end_tables(uint64_t L, const uint32_t* nq, const double* probs, const uint8_t* quals,
+                      EndTables& out);
+
+// --- fragment lengths ----------------------------------------------------------
+// Table of P(frag_len <= frag_min + i) * 2^64 for
+// frag_len = clamp((uint64)Gamma(shape, scale), frag_min, frag_max)
+// (src/hts_illumina.cpp:206-208).  Entry count = hi - frag_min where hi is
+// frag_max or the point past which the tail mass is < 2^-64.
+std::vector<uint64_t> frag_table(double shape, double scale, uint64_t frag_min, uint64_t frag_max);
+// regularised lower incomplete gamma P(a, x)
+long double gamma_p(long double a, long double x);
+
+// --- read apportioning ---------------------------------------------------------
+// reads_per_group, src/hts.h:58-103 (own engine; statistically equivalent)
+std::vector<uint64_t> reads_per_group(uint64_t n_reads, std::vector<double> probs, uint64_t seed);
+// split_int, src/util.h:245-258
+std::vector<uint64_t> split_int(uint64_t x, uint64_t n);
+
+}  // namespace jlp
+#endif

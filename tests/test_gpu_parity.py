@@ -1,0 +1,101 @@
+"""GPU parity tests proper: every call goes through the C ABI (jackalope_b200._lib)
+and is compared byte for byte with the CPU oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+
+import jackalope_b200 as J
+from common import fastq_records, first_diff, hap_sequences, oracle_run
+
+pytestmark = pytest.mark.gpu
+
+
+def small_genome(seed=1, n=3, length=5000, with_n=True):
+    g = J.random_genome(n, length, seed=seed)
+    if with_n:
+        s = g.seqs[0].copy()
+        s[100:160] = ord("N")
+        s[1000] = ord("x")
+        g.seqs[0] = s
+    return g
+
+
+def check(ctx, obj, n_reads, L, paired, seed, **kw):
+    r1, r2, st = J.illumina(obj, "", n_reads, L, paired, seed=seed, ctx=ctx, sink="memory", **kw)
+    o = oracle_run(ctx, obj, n_reads, L, paired, seed, **kw)
+    d1, d2 = first_diff(r1, o["r1"]), first_diff(r2, o["r2"])
+    assert d1 is None, "R1 differs at byte %d: gpu=%r oracle=%r" % (d1, r1[max(0, d1 - 80):d1 + 40], o["r1"][max(0, d1 - 80):d1 + 40])
+    assert d2 is None, "R2 differs at byte %d: gpu=%r oracle=%r" % (d2, r2[max(0, d2 - 80):d2 + 40], o["r2"][max(0, d2 - 80):d2 + 40])
+    return r1, r2, st
+
+
+def test_materialize_matches_oracle(ctx):
+    g = small_genome(seed=3, n=4, length=20000, with_n=False)
+    haps = J.random_haplotypes(g, 3, sub_rate=0.02, indel_rate=0.01, seed=5)
+    ctx.set_haplotypes(haps)
+    want = hap_sequences(haps)
+    for h in range(3):
+        for c in range(4):
+            assert ctx.haplotype_chrom(h, c) == want[h][c]
+
+
+@pytest.mark.parametrize("paired,matepair", [(False, False), (True, False), (True, True)])
+def test_ref_default_args(ctx, paired, matepair):
+    g = small_genome()
+    check(ctx, g, 2000, 100, paired, seed=11, matepair=matepair)
+
+
+def test_ref_pe150_hs25(ctx):
+    g = small_genome(seed=2, n=5, length=20000)
+    check(ctx, g, 6000, 150, True, seed=12, seq_sys="HS25")
+
+
+def test_high_indels_dups_barcode(ctx):
+    g = small_genome(seed=4)
+    check(ctx, g, 3000, 100, True, seed=13, ins_prob1=0.02, del_prob1=0.03, ins_prob2=0.05, del_prob2=0.01,
+          prob_dup=0.4, read_pool_size=14, barcodes=["ACGTTG"])
+
+
+def test_short_fragments_and_chromosomes(ctx):
+    # fragments shorter than the read, and a chromosome shorter than any fragment
+    g = J.RefGenome(["a", "b", "c"], [J.random_genome(1, 60, seed=5).seqs[0], J.random_genome(1, 4000, seed=6).seqs[0],
+                                      J.random_genome(1, 130, seed=7).seqs[0]])
+    check(ctx, g, 3000, 100, True, seed=14, frag_mean=120, frag_sd=40, frag_len_min=20, ins_prob1=0.01, del_prob1=0.01)
+
+
+def test_haplotypes_pooled_and_sep(ctx):
+    g = small_genome(seed=8, n=3, length=8000, with_n=False)
+    haps = J.random_haplotypes(g, 4, sub_rate=0.02, indel_rate=0.005, seed=9)
+    check(ctx, haps, 4000, 100, True, seed=15, haplotype_probs=[1, 2, 0, 4], barcodes=["AC", "GT", "TT", "CA"])
+    check(ctx, haps, 4000, 100, True, seed=16, haplotype_probs=[1, 2, 0.5, 4], sep_files=True)
+    check(ctx, haps, 1500, 100, False, seed=17)
+
+
+def test_batches_and_shards_do_not_change_output(ctx):
+    g = small_genome(seed=10)
+    r1, r2, _ = check(ctx, g, 5000, 100, True, seed=18, prob_dup=0.3)
+    b1, b2, st = J.illumina(g, "", 5000, 100, True, seed=18, ctx=ctx, sink="memory", prob_dup=0.3, batch_pairs=333)
+    assert (b1, b2) == (r1, r2) and st["batches"] == 8
+    parts = [J.illumina(g, "", 5000, 100, True, seed=18, ctx=ctx, sink="memory", prob_dup=0.3, batch_pairs=400,
+                        shard=(i, 3)) for i in range(3)]
+    assert b"".join(p[0] for p in parts) == r1 and b"".join(p[1] for p in parts) == r2
+
+
+def test_files_and_sep_files(ctx, tmp_path):
+    g = small_genome(seed=11, with_n=False)
+    haps = J.random_haplotypes(g, 3, seed=12)
+    pre = str(tmp_path / "reads")
+    assert J.illumina(g, pre, 1000, 100, True, seed=19, ctx=ctx) is None
+    r1, r2, _ = J.illumina(g, "", 1000, 100, True, seed=19, ctx=ctx, sink="memory")
+    assert open(pre + "_R1.fq", "rb").read() == r1 and open(pre + "_R2.fq", "rb").read() == r2
+    with pytest.raises(J.JackalopeError):
+        J.illumina(g, pre, 1000, 100, True, seed=19, ctx=ctx)           # exists, overwrite = FALSE
+    J.illumina(haps, pre, 900, 100, True, seed=20, ctx=ctx, sep_files=True, overwrite=True)
+    m1, m2, _ = J.illumina(haps, "", 900, 100, True, seed=20, ctx=ctx, sep_files=True, sink="memory")
+    cat1 = b"".join(open("%s_%s_R1.fq" % (pre, h), "rb").read() for h in haps.hap_names)
+    cat2 = b"".join(open("%s_%s_R2.fq" % (pre, h), "rb").read() for h in haps.hap_names)
+    assert cat1 == m1 and cat2 == m2
+    # shape checks of tests/testthat/test-sequencer.R:31-77,172-272
+    for fq in (r1, r2, m1, m2):
+        recs = fastq_records(fq)
+        assert all(r[0].startswith(b"@") and r[2] == b"+" and len(r[1]) == len(r[3]) for r in recs)
+    assert len(fastq_records(r1)) == len(fastq_records(r2)) == 500
