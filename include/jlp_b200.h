@@ -104,7 +104,7 @@ typedef struct jlp_illumina_params {
     /* additions of this implementation */
     uint64_t seed;               /* run seed; the glue draws it from R's RNG (src/pcg.h:37-46) */
     uint64_t batch_pairs;        /* pairs per device batch; 0 = default */
-    uint32_t shard_index;        /* this process handles batches b with b % shard_count == shard_index */
+    uint32_t shard_index;        /* this process generates jlp_shard_range(job, shard_index, shard_count) of every job */
     uint32_t shard_count;        /* 0 or 1 = everything */
     jlp_abort_cb abort_cb;
     jlp_progress_cb progress_cb;
@@ -121,6 +121,8 @@ typedef struct jlp_run_stats {
     double fmt_ms;               /* ... of which the FASTQ formatter */
     uint64_t d2h_bytes;
     uint64_t h2d_bytes;
+    double run_ms;               /* CUDA-event time on the compute stream from the start of the call's device
+                                    work to the end of its last kernel (includes waits on the D2H double buffer) */
 } jlp_run_stats;
 
 /* Reads from the reference genome (illumina_ref_cpp). */
@@ -136,6 +138,16 @@ int jlp_illumina_to_memory(jlp_ctx* ctx, int use_haplotypes, const jlp_illumina_
                            char* out1, uint64_t cap1, uint64_t* len1,
                            char* out2, uint64_t cap2, uint64_t* len2, jlp_run_stats* stats);
 
+/* Same generators, FASTQ handed to the caller batch by batch in the library's
+ * double-buffered PINNED host buffers (the buffers FileUncomp::write would be fed
+ * from, src/hts.h:225-241): cb(user, job, end, data, n) is called on the calling
+ * thread, R1 then R2 of a batch, batches in order; `job` counts output file sets
+ * (one per haplotype with sep_files, else 0).  `data` is valid during the call
+ * only.  A non-zero return stops the run with JLP_ERR_IO. */
+typedef int (*jlp_chunk_cb)(void* user, uint64_t job, int end, const char* data, uint64_t n);
+int jlp_illumina_stream(jlp_ctx* ctx, int use_haplotypes, const jlp_illumina_params* p,
+                        jlp_chunk_cb cb, void* user, jlp_run_stats* stats);
+
 /* Same generators with the FASTQ left in device memory and dropped (bench.py's
  * device-resident leg: everything but the D2H copy and the file write). */
 int jlp_illumina_device_only(jlp_ctx* ctx, int use_haplotypes, const jlp_illumina_params* p,
@@ -148,6 +160,19 @@ int jlp_illumina_group_counts(jlp_ctx* ctx, int use_haplotypes, const jlp_illumi
                               uint64_t* counts, uint64_t cap, uint64_t* n_groups);
 
 /* ---- host-side pieces exposed for CPU tests (no device needed) --------------- */
+
+/* The apportioning jlp_illumina_group_counts reports, from sizes alone: pairs ->
+ * haplotypes by hap_probs, then each haplotype's pairs -> chromosomes by size
+ * (write_reads_one_filetype_ src/hts.h:334-353, add_n_reads src/hts_illumina.h:410-418
+ * and :620-644).  hap_probs == NULL is a reference-genome run (n_haps ignored,
+ * sizes[n_chroms]); otherwise sizes is [n_haps][n_chroms].  counts has the same shape. */
+int jlp_apportion(uint64_t seed, uint64_t n_pairs, uint64_t n_haps, uint64_t n_chroms,
+                  const double* hap_probs, const uint64_t* sizes, uint64_t* counts);
+/* Pair-index range [lo, hi) of job [job_lo, job_hi) that shard `shard_index` of
+ * `shard_count` generates (jlp_illumina_params.shard_index / shard_count): contiguous
+ * and near-equal, as split_int (src/util.h:245-258) splits reads over threads. */
+int jlp_shard_range(uint64_t job_lo, uint64_t job_hi, uint32_t shard_index, uint32_t shard_count,
+                    uint64_t* lo, uint64_t* hi);
 
 /* reads_per_group (src/hts.h:58-103): multinomial apportioning by conditional
  * binomials.  Statistically equivalent to the reference (own engine). */

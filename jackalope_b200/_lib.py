@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(HERE, "libjlp_b200.so")
 u8p, u32p, u64p, f64p = (C.POINTER(t) for t in (C.c_uint8, C.c_uint32, C.c_uint64, C.c_double))
 ABORT_CB = C.CFUNCTYPE(C.c_int, C.c_void_p)
 PROGRESS_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_uint64)
+CHUNK_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_uint64)
 
 JLP_OK, JLP_ERR_ARG, JLP_ERR_NO_DEVICE, JLP_ERR_CUDA, JLP_ERR_IO, JLP_ERR_ABORTED, JLP_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
 
@@ -36,19 +37,20 @@ class RunStats(C.Structure):
         ("pairs", C.c_uint64), ("bytes_out", C.c_uint64 * 2), ("batches", C.c_uint64),
         ("kernel_launches", C.c_uint64), ("device_ms", C.c_double), ("gen_ms", C.c_double),
         ("fmt_ms", C.c_double), ("d2h_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64),
+        ("run_ms", C.c_double),
     ]
 
     def as_dict(self):
         return dict(pairs=self.pairs, bytes_out=list(self.bytes_out), batches=self.batches,
                     kernel_launches=self.kernel_launches, device_ms=self.device_ms, gen_ms=self.gen_ms,
-                    fmt_ms=self.fmt_ms, d2h_bytes=self.d2h_bytes, h2d_bytes=self.h2d_bytes)
+                    fmt_ms=self.fmt_ms, d2h_bytes=self.d2h_bytes, h2d_bytes=self.h2d_bytes, run_ms=self.run_ms)
 
 
 # every symbol include/jlp_b200.h declares
 SYMBOLS = [
     "jlp_ctx_create", "jlp_ctx_destroy", "jlp_last_error", "jlp_set_genome", "jlp_clear_haplotypes",
     "jlp_add_haplotype", "jlp_get_haplotype_chrom", "jlp_set_profile", "jlp_illumina_ref", "jlp_illumina_hap",
-    "jlp_illumina_to_memory", "jlp_illumina_device_only", "jlp_illumina_group_counts", "jlp_reads_per_group", "jlp_alias_build",
+    "jlp_illumina_to_memory", "jlp_illumina_stream", "jlp_illumina_device_only", "jlp_illumina_group_counts", "jlp_apportion", "jlp_shard_range", "jlp_reads_per_group", "jlp_alias_build",
     "jlp_threshold", "jlp_unif_expr", "jlp_frag_table", "jlp_philox4x32_10", "jlp_draw_pos", "jlp_draw_pair",
     "jlp_version",
 ]
@@ -81,8 +83,11 @@ def lib():
     L.jlp_illumina_hap.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(RunStats)]
     L.jlp_illumina_to_memory.argtypes = [C.c_void_p, C.c_int, C.POINTER(Params), C.c_void_p, C.c_uint64, u64p,
                                          C.c_void_p, C.c_uint64, u64p, C.POINTER(RunStats)]
+    L.jlp_illumina_stream.argtypes = [C.c_void_p, C.c_int, C.POINTER(Params), CHUNK_CB, C.c_void_p, C.POINTER(RunStats)]
     L.jlp_illumina_device_only.argtypes = [C.c_void_p, C.c_int, C.POINTER(Params), C.POINTER(RunStats)]
     L.jlp_illumina_group_counts.argtypes = [C.c_void_p, C.c_int, C.POINTER(Params), u64p, C.c_uint64, u64p]
+    L.jlp_apportion.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, f64p, u64p, u64p]
+    L.jlp_shard_range.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, u64p, u64p]
     L.jlp_reads_per_group.argtypes = [C.c_uint64, f64p, C.c_uint64, C.c_uint64, u64p]
     L.jlp_alias_build.argtypes = [f64p, C.c_uint64, f64p, u64p]
     L.jlp_threshold.argtypes = [C.c_int, C.c_double, u64p, C.POINTER(C.c_int)]

@@ -124,6 +124,7 @@ struct jlp_ctx {
     DevBuf<uint8_t> d_strpool;
     DevBuf<uint32_t> d_status;
     Slot slot[2];
+    cudaEvent_t ev_run[2] = {nullptr, nullptr};
     uint64_t h2d_bytes = 0;
 };
 
@@ -155,13 +156,16 @@ template <typename F> int guarded(jlp_ctx* c, F f) {
 
 // ---------------------------------------------------------------- the run ---
 
-enum SinkKind { SINK_FILES, SINK_MEMORY, SINK_NONE };
+enum SinkKind { SINK_FILES, SINK_MEMORY, SINK_STREAM, SINK_NONE };
 
 struct Sink {
     SinkKind kind = SINK_NONE;
     // memory
     char* mem[2] = {nullptr, nullptr};
     uint64_t cap[2] = {0, 0}, len[2] = {0, 0};
+    // stream
+    jlp_chunk_cb chunk_cb = nullptr;
+    void* chunk_user = nullptr;
     // files
     int fd[2] = {-1, -1};
     std::string names[2];
@@ -187,36 +191,54 @@ void write_all(int fd, const uint8_t* p, uint64_t n, const std::string& name) {
     }
 }
 
+// Contiguous, near-equal split of a job's pair-index range over shards (the even split of
+// split_int, src/util.h:245-258, applied to GPUs instead of threads).
+void shard_range(uint64_t job_lo, uint64_t job_hi, uint32_t si, uint32_t S, uint64_t& lo, uint64_t& hi) {
+    const uint64_t nj = job_hi - job_lo;
+    lo = job_lo + nj / S * si + std::min<uint64_t>(si, nj % S);
+    hi = lo + nj / S + (si < nj % S ? 1 : 0);
+}
+
 // Pairs per (haplotype, chromosome): threads -> haplotypes -> chromosomes
 // (write_reads_one_filetype_ src/hts.h:334-353, add_n_reads src/hts_illumina.h:410-418 and :620-644,
 //  write_reads_cpp_sep_files_ src/hts.h:527-529).  One "thread"; n_pairs = floor(n_reads / n_ends).
 // A reference run has one pseudo-haplotype.  Both the pooled and the sep_files haplotype paths first
 // split pairs over haplotypes by haplotype_probs, then each haplotype's pairs over its chromosomes
 // by size, so one routine serves both.
-std::vector<std::vector<uint64_t>> apportion(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, uint64_t n_pairs) {
-    uint64_t sub_seed = P->seed * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+std::vector<std::vector<uint64_t>> apportion_sizes(uint64_t seed, uint64_t n_pairs, uint64_t n_haps, uint64_t n_chroms,
+                                                   const double* hap_probs, const uint64_t* sizes) {
+    uint64_t sub_seed = seed * 0x9E3779B97F4A7C15ull + 0x1234567ull;
     auto next_seed = [&]() { sub_seed = sub_seed * 6364136223846793005ull + 1442695040888963407ull; return sub_seed; };
-    const uint64_t n_chroms = c->chrom_off.size() - 1;
     std::vector<std::vector<uint64_t>> out;
-    if (!use_haps) {
+    if (!hap_probs) {
         std::vector<double> w(n_chroms);
-        for (uint64_t i = 0; i < n_chroms; i++) w[i] = (double)(c->chrom_off[i + 1] - c->chrom_off[i]);
+        for (uint64_t i = 0; i < n_chroms; i++) w[i] = (double)sizes[i];
         out.push_back(reads_per_group(n_pairs, w, next_seed()));
         return out;
     }
-    const uint64_t n_haps = c->haps.size();
-    if (!P->haplotype_probs) throw ArgErr("haplotype_probs is NULL");
-    std::vector<double> hp(P->haplotype_probs, P->haplotype_probs + n_haps);
+    std::vector<double> hp(hap_probs, hap_probs + n_haps);
     bool any = false;
     for (double v : hp) { if (!(v >= 0)) throw ArgErr("haplotype_probs must be >= 0"); any |= v > 0; }
     if (!any) throw ArgErr("haplotype_probs must have at least one value > 0");
     std::vector<uint64_t> hap_pairs = reads_per_group(n_pairs, hp, next_seed());
     for (uint64_t h = 0; h < n_haps; h++) {
         std::vector<double> w(n_chroms);
-        for (uint64_t i = 0; i < n_chroms; i++) w[i] = (double)c->haps[h].len[i];
+        for (uint64_t i = 0; i < n_chroms; i++) w[i] = (double)sizes[h * n_chroms + i];
         out.push_back(reads_per_group(hap_pairs[h], w, next_seed()));
     }
     return out;
+}
+
+std::vector<std::vector<uint64_t>> apportion(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, uint64_t n_pairs) {
+    const uint64_t n_chroms = c->chrom_off.size() - 1;
+    std::vector<uint64_t> sizes;
+    if (!use_haps) {
+        for (uint64_t i = 0; i < n_chroms; i++) sizes.push_back(c->chrom_off[i + 1] - c->chrom_off[i]);
+        return apportion_sizes(P->seed, n_pairs, 1, n_chroms, nullptr, sizes.data());
+    }
+    if (!P->haplotype_probs) throw ArgErr("haplotype_probs is NULL");
+    for (const HapDev& h : c->haps) sizes.insert(sizes.end(), h.len.begin(), h.len.end());
+    return apportion_sizes(P->seed, n_pairs, c->haps.size(), n_chroms, P->haplotype_probs, sizes.data());
 }
 
 void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jlp_run_stats* stats) {
@@ -325,6 +347,8 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
         E.tA = ta.thr; E.tA_all = ta.all; E.tI = ti.thr; E.tI_all = ti.all;
         E.hA = ta.all ? 0x10000u : (uint32_t)(ta.thr >> 48);
     }
+    for (cudaEvent_t& ev : c->ev_run) if (!ev) CK(cudaEventCreate(&ev));
+    CK(cudaEventRecord(c->ev_run[0], c->s_compute));
     std::vector<uint64_t> frag = frag_table(P->frag_len_shape, P->frag_len_scale, P->frag_len_min, P->frag_len_max);
     c->d_frag.upload(frag, c->s_compute);
     c->d_group_off.upload(group_off, c->s_compute);
@@ -373,6 +397,7 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
     std::memset(&st, 0, sizeof st);
 
     // finish a batch: wait for its totals, copy the FASTQ to the host, hand it to the sink
+    uint64_t job_index = 0;
     auto finish = [&](Slot& s, const Job& job) {
         (void)job;
         CK(cudaEventSynchronize(s.ev[3]));
@@ -395,7 +420,10 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
             for (int e = 0; e < n_ends; e++) {
                 uint64_t n = s.h_totals.p[e];
                 if (sink.kind == SINK_FILES) write_all(sink.fd[e], s.h_out[e].p, n, sink.names[e]);
-                else {
+                else if (sink.kind == SINK_STREAM) {
+                    if (sink.chunk_cb(sink.chunk_user, job_index, e, reinterpret_cast<const char*>(s.h_out[e].p), n))
+                        throw IoErr("the chunk callback reported an error");
+                } else {
                     if (sink.len[e] + n <= sink.cap[e]) std::memcpy(sink.mem[e] + sink.len[e], s.h_out[e].p, n);
                     sink.len[e] += n;
                 }
@@ -419,9 +447,8 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
                 if (sink.fd[e] < 0) throw IoErr("Unable to open file " + sink.names[e] + ".\n");  // src/io.h:288-290
             }
         }
-        const uint64_t nj = job.hi - job.lo;
-        const uint64_t lo = job.lo + nj / S * si + std::min<uint64_t>(si, nj % S);
-        const uint64_t hi = lo + nj / S + (si < nj % S ? 1 : 0);
+        uint64_t lo, hi;
+        shard_range(job.lo, job.hi, si, S, lo, hi);
         int cur = 0;
         Slot* prev = nullptr;
         for (uint64_t b0 = lo; b0 < hi; b0 += B) {
@@ -459,6 +486,14 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
             }
         }
         for (Slot& s : c->slot) if (s.busy) finish(s, job);
+        job_index++;
+    }
+    CK(cudaEventRecord(c->ev_run[1], c->s_compute));
+    CK(cudaEventSynchronize(c->ev_run[1]));
+    {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, c->ev_run[0], c->ev_run[1]));
+        st.run_ms = ms;
     }
     sink.close_files();
     uint32_t status = 0;
@@ -501,6 +536,7 @@ void jlp_ctx_destroy(jlp_ctx* c) {
     cudaDeviceSynchronize();
     free_haps(c);
     for (Slot& s : c->slot) for (cudaEvent_t ev : s.ev) if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : c->ev_run) if (ev) cudaEventDestroy(ev);
     if (c->s_compute) cudaStreamDestroy(c->s_compute);
     if (c->s_copy) cudaStreamDestroy(c->s_copy);
     delete c;
@@ -644,6 +680,17 @@ int jlp_illumina_to_memory(jlp_ctx* c, int use_haplotypes, const jlp_illumina_pa
     });
 }
 
+int jlp_illumina_stream(jlp_ctx* c, int use_haplotypes, const jlp_illumina_params* p, jlp_chunk_cb cb, void* user,
+                        jlp_run_stats* stats) {
+    if (!c) return JLP_ERR_ARG;
+    return guarded(c, [&]() {
+        if (!cb) throw ArgErr("chunk callback is NULL");
+        Sink s;
+        s.kind = SINK_STREAM; s.chunk_cb = cb; s.chunk_user = user;
+        run(c, use_haplotypes != 0, p, s, stats);
+    });
+}
+
 int jlp_illumina_device_only(jlp_ctx* c, int use_haplotypes, const jlp_illumina_params* p, jlp_run_stats* stats) {
     if (!c) return JLP_ERR_ARG;
     return guarded(c, [&]() { Sink s; s.kind = SINK_NONE; run(c, use_haplotypes != 0, p, s, stats); });
@@ -668,6 +715,24 @@ int jlp_illumina_group_counts(jlp_ctx* c, int use_haplotypes, const jlp_illumina
 }
 
 // ---- host-side pieces (no device) ----
+
+int jlp_shard_range(uint64_t job_lo, uint64_t job_hi, uint32_t shard_index, uint32_t shard_count, uint64_t* lo,
+                    uint64_t* hi) {
+    if (!lo || !hi || job_hi < job_lo || shard_count == 0 || shard_index >= shard_count) return JLP_ERR_ARG;
+    shard_range(job_lo, job_hi, shard_index, shard_count, *lo, *hi);
+    return JLP_OK;
+}
+
+int jlp_apportion(uint64_t seed, uint64_t n_pairs, uint64_t n_haps, uint64_t n_chroms, const double* hap_probs,
+                  const uint64_t* sizes, uint64_t* counts) {
+    if (!sizes || !counts || n_chroms == 0 || (hap_probs && n_haps == 0)) return JLP_ERR_ARG;
+    try {
+        std::vector<std::vector<uint64_t>> cnt = apportion_sizes(seed, n_pairs, n_haps, n_chroms, hap_probs, sizes);
+        uint64_t k = 0;
+        for (const auto& v : cnt) for (uint64_t x : v) counts[k++] = x;
+    } catch (const std::exception&) { return JLP_ERR_ARG; }
+    return JLP_OK;
+}
 
 int jlp_reads_per_group(uint64_t n_reads, const double* probs, uint64_t n, uint64_t seed, uint64_t* out) {
     if (!probs || !out) return JLP_ERR_ARG;

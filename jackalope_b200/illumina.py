@@ -178,6 +178,9 @@ class Context:
 
     def set_profile(self, end, flat):
         L, nq, probs, quals = flat
+        old = self._profiles[end]
+        if old is not None and old[0] == L and all(np.array_equal(a, b) for a, b in zip(old[1:], flat[1:])):
+            return
         self._check(self.lib.jlp_set_profile(self.h, end, L, nq.ctypes.data_as(u32p), probs.ctypes.data_as(f64p),
                                              quals.ctypes.data_as(u8p)), "jlp_set_profile")
         self._profiles[end] = flat
@@ -282,14 +285,16 @@ def illumina(obj, out_prefix, n_reads, read_length, paired, frag_mean=400, frag_
     the part of ``set.seed``), ``device``/``ctx`` (which GPU), ``batch_pairs``,
     ``shard=(index, count)``, and ``sink``: "files" (default, returns ``None``
     like the reference), "memory" (returns ``(r1_bytes, r2_bytes, stats)``) or
-    "device" (generate and discard on the GPU; returns ``stats``)."""
+    "device" (generate and discard on the GPU; returns ``stats``), or a callable
+    ``sink(job, end, buffer)`` that receives every batch's FASTQ bytes from the library's
+    pinned host buffers (returns ``stats``)."""
     if seed is None:
         seed = int(np.random.randint(0, 2 ** 63 - 1, dtype=np.int64))
     p, keep, (prof1, prof2), is_haps, fns = _prepare(
         obj, out_prefix, n_reads, read_length, paired, frag_mean, frag_sd, matepair, seq_sys, profile1, profile2,
         ins_prob1, del_prob1, ins_prob2, del_prob2, frag_len_min, frag_len_max, haplotype_probs, barcodes, prob_dup,
         sep_files, compress, comp_method, n_threads, read_pool_size, show_progress, overwrite, seed, batch_pairs,
-        shard, check_files=(sink == "files"))
+        shard, check_files=(isinstance(sink, str) and sink == "files"))
     ctx = ctx or default_context(device)
     if is_haps:
         ctx.set_haplotypes(obj)
@@ -300,10 +305,23 @@ def illumina(obj, out_prefix, n_reads, read_length, paired, frag_mean=400, frag_
         ctx.set_profile(1, prof2)
     stats = _lib.RunStats()
     lib = ctx.lib
-    if sink == "files":
+    if isinstance(sink, str) and sink == "files":
         fn = lib.jlp_illumina_hap if is_haps else lib.jlp_illumina_ref
         ctx._check(fn(ctx.h, C.byref(p), C.byref(stats)), "illumina")
         return None
+    if callable(sink):
+        # sink(job, end, memoryview) for every batch, from the library's pinned host buffers
+        def _cb(_user, job, end, data, n):
+            try:
+                sink(int(job), int(end), (C.c_char * n).from_address(data) if n else b"")
+                return 0
+            except Exception:
+                import traceback
+                traceback.print_exc()
+                return 1
+        cb = _lib.CHUNK_CB(_cb)
+        ctx._check(lib.jlp_illumina_stream(ctx.h, int(is_haps), C.byref(p), cb, None, C.byref(stats)), "illumina")
+        return stats.as_dict()
     if sink == "device":
         ctx._check(lib.jlp_illumina_device_only(ctx.h, int(is_haps), C.byref(p), C.byref(stats)), "illumina")
         return stats.as_dict()

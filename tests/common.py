@@ -1,118 +1,3 @@
-"""Shared helpers of the test-suite: run the CPU oracle on exactly the inputs a
-product run used (same seed, same group counts, same fragment table)."""
-import ctypes as C
-
-import numpy as np
-
-import jackalope_b200 as J
-from jackalope_b200 import _lib
-from jackalope_b200.illumina import _prepare
-from oracle import harness as H
-
-DEFAULTS = dict(frag_mean=400, frag_sd=100, matepair=False, seq_sys=None, profile1=None, profile2=None,
-                ins_prob1=0.00009, del_prob1=0.00011, ins_prob2=0.00015, del_prob2=0.00023, frag_len_min=None,
-                frag_len_max=None, haplotype_probs=None, barcodes=None, prob_dup=0.02, sep_files=False,
-                compress=False, comp_method="bgzip", n_threads=1, read_pool_size=1000, show_progress=False,
-                overwrite=True)
-
-
-def frag_table(shape, scale, fmin, fmax):
-    lib = _lib.lib()
-    n = C.c_uint64()
-    lib.jlp_frag_table(shape, scale, fmin, fmax, None, 0, C.byref(n))
-    cdf = np.zeros(max(n.value, 1), dtype=np.uint64)
-    assert lib.jlp_frag_table(shape, scale, fmin, fmax, cdf.ctypes.data_as(_lib.u64p), n.value, C.byref(n)) == 0
-    return cdf[:n.value]
-
-
-def hap_sequences(haps: J.Haplotypes):
-    """Materialise every haplotype chromosome with the oracle (get_chrom_full restatement)."""
-    out = []
-    for h in range(haps.n_haps()):
-        row = []
-        for c, m in enumerate(haps.muts[h]):
-            row.append(H.materialize(haps.reference.chrom(c), m.old_pos, m.new_pos, m.nuc_off, m.pool.tobytes(),
-                                     m.chrom_size))
-        out.append(row)
-    return out
-
-
-def oracle_run(ctx, obj, n_reads, read_length, paired, seed, lo=None, hi=None, want_ledger=False, hap_seqs=None,
-               **kw):
-    """Oracle output for the run illumina(obj, ..., seed=seed) performs on `ctx`.
-    Returns dict(r1, r2[, plan, ledger, ledger_cnt, groups]); with sep_files the
-    jobs' outputs are concatenated in haplotype order (as sink="memory" does)."""
-    a = dict(DEFAULTS)
-    a.update(kw)
-    p, keep, (prof1, prof2), is_haps, _ = _prepare(obj, "x", n_reads, read_length, paired, a["frag_mean"],
-                                                   a["frag_sd"], a["matepair"], a["seq_sys"], a["profile1"],
-                                                   a["profile2"], a["ins_prob1"], a["del_prob1"], a["ins_prob2"],
-                                                   a["del_prob2"], a["frag_len_min"], a["frag_len_max"],
-                                                   a["haplotype_probs"], a["barcodes"], a["prob_dup"], a["sep_files"],
-                                                   a["compress"], a["comp_method"], a["n_threads"],
-                                                   a["read_pool_size"], a["show_progress"], True, seed, None, None,
-                                                   check_files=False)
-    if is_haps:
-        ctx.set_haplotypes(obj)
-    else:
-        ctx.set_genome(obj)
-    n_ends = 2 if p.paired else 1
-    ref = obj.reference if is_haps else obj
-    nc = ref.n_chroms()
-    nh = obj.n_haps() if is_haps else 1
-    counts = np.zeros(nh * nc, dtype=np.uint64)
-    ng = C.c_uint64()
-    ctx._check(ctx.lib.jlp_illumina_group_counts(ctx.h, int(is_haps), C.byref(p), counts.ctypes.data_as(_lib.u64p),
-                                                 counts.size, C.byref(ng)), "group_counts")
-    assert ng.value == nh * nc
-    if is_haps:
-        hap_seqs = hap_seqs or hap_sequences(obj)
-        seqs = [hap_seqs[h][c] for h in range(nh) for c in range(nc)]
-        gnames = [obj.hap_names[h] for h in range(nh) for c in range(nc)]
-        cnames = [ref.names[c] for h in range(nh) for c in range(nc)]
-        bcs = [p.barcodes[h].decode() for h in range(nh) for c in range(nc)]
-    else:
-        seqs = [ref.chrom(c) for c in range(nc)]
-        gnames = [ref.name] * nc
-        cnames = list(ref.names)
-        bcs = [p.barcodes[0].decode()] * nc
-    groups = H.Groups(counts, seqs, gnames, cnames, bcs)
-    cdf = frag_table(p.frag_len_shape, p.frag_len_scale, p.frag_len_min, p.frag_len_max)
-    pool_pairs = (p.read_pool_size + n_ends - 1) // n_ends
-    if is_haps and p.sep_files:
-        jobs = [(int(groups.off[h * nc]), int(groups.off[(h + 1) * nc])) for h in range(nh)]
-    else:
-        jobs = [(0, int(groups.off[-1]))]
-    res = dict(r1=b"", r2=b"", groups=groups, jobs=jobs)
-    for (jl, jh) in jobs:
-        a_lo = jl if lo is None else max(jl, lo)
-        a_hi = jh if hi is None else min(jh, hi)
-        if a_hi <= a_lo:
-            continue
-        r = H.generate(seed=p.seed, paired=bool(p.paired), matepair=bool(p.matepair), groups=groups, prof1=prof1,
-                       prof2=prof2, ins_prob=[p.ins_prob1, p.ins_prob2], del_prob=[p.del_prob1, p.del_prob2],
-                       prob_dup=p.prob_dup, pool_pairs=pool_pairs, frag_cdf=cdf, frag_min=p.frag_len_min,
-                       lo=a_lo, hi=a_hi, job_lo=jl, job_hi=jh, want_ledger=want_ledger, want_plan=want_ledger)
-        res["r1"] += r["r1"]
-        res["r2"] += r["r2"]
-        if want_ledger:
-            for k in ("plan", "ledger", "ledger_cnt"):
-                res.setdefault(k, []).append(r[k])
-    return res
-
-
-def fastq_records(b: bytes):
-    lines = b.split(b"\n")
-    assert lines[-1] == b""
-    lines = lines[:-1]
-    assert len(lines) % 4 == 0
-    return [tuple(lines[i:i + 4]) for i in range(0, len(lines), 4)]
-
-
-def first_diff(a: bytes, b: bytes):
-    n = min(len(a), len(b))
-    aa, bb = np.frombuffer(a[:n], np.uint8), np.frombuffer(b[:n], np.uint8)
-    d = np.nonzero(aa != bb)[0]
-    if d.size == 0:
-        return None if len(a) == len(b) else n
-    return int(d[0])
+"""Shared helpers of the test-suite (the oracle-side comparison lives in oracle/compare.py)."""
+from oracle.compare import *  # noqa: F401,F403
+from oracle.compare import DEFAULTS, fastq_records, first_diff, frag_table, group_counts, hap_sequences, oracle_run  # noqa: F401

@@ -21,7 +21,7 @@ def small_genome(seed=1, n=3, length=5000, with_n=True):
 
 def check(ctx, obj, n_reads, L, paired, seed, **kw):
     r1, r2, st = J.illumina(obj, "", n_reads, L, paired, seed=seed, ctx=ctx, sink="memory", **kw)
-    o = oracle_run(ctx, obj, n_reads, L, paired, seed, **kw)
+    o = oracle_run(obj, n_reads, L, paired, seed, **kw)
     d1, d2 = first_diff(r1, o["r1"]), first_diff(r2, o["r2"])
     assert d1 is None, "R1 differs at byte %d: gpu=%r oracle=%r" % (d1, r1[max(0, d1 - 80):d1 + 40], o["r1"][max(0, d1 - 80):d1 + 40])
     assert d2 is None, "R2 differs at byte %d: gpu=%r oracle=%r" % (d2, r2[max(0, d2 - 80):d2 + 40], o["r2"][max(0, d2 - 80):d2 + 40])
