@@ -99,3 +99,62 @@ def test_files_and_sep_files(ctx, tmp_path):
         recs = fastq_records(fq)
         assert all(r[0].startswith(b"@") and r[2] == b"+" and len(r[1]) == len(r[3]) for r in recs)
     assert len(fastq_records(r1)) == len(fastq_records(r2)) == 500
+
+
+# ---- golden vectors (bytes produced by the unmodified reference, tests/golden/make_golden.py)
+
+from golden.cases import CASES, load  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_cuda_reproduces_golden(ctx, name):
+    make, n_reads, L, paired, seed, kw = CASES[name]
+    want1, want2, _ = load(name)
+    r1, r2, st = J.illumina(make(), "", n_reads, L, paired, seed=seed, ctx=ctx, sink="memory", **kw)
+    assert first_diff(r1, want1) is None and first_diff(r2, want2) is None
+    assert st["kernel_launches"] >= 4
+
+
+def test_pair_geometry_known_answers(ctx, tmp_path):
+    """tests/testthat/test-sequencer.R:81-161: error-free custom profile (quality 255),
+    chromosome C25 N150 T25, fragment forced to 200, no indels."""
+    prof = str(tmp_path / "prof.txt")
+    with open(prof, "w") as fh:
+        for nt in "ACGT":
+            for pos in range(100):
+                fh.write("%s\t%d\t255\n%s\t%d\t1000000\n" % (nt, pos, nt, pos))
+    g = J.RefGenome(["chrom0"], [b"C" * 25 + b"N" * 150 + b"T" * 25])
+    common = dict(profile1=prof, profile2=prof, frag_mean=400, frag_sd=100, frag_len_min=200, frag_len_max=200,
+                  ins_prob1=0, del_prob1=0, ins_prob2=0, del_prob2=0, ctx=ctx, sink="memory")
+    for matepair, want in ((False, {b"C" * 25 + b"N" * 75, b"A" * 25 + b"N" * 75}),
+                           (True, {b"N" * 75 + b"T" * 25, b"N" * 75 + b"G" * 25})):
+        r1, r2, _ = J.illumina(g, "", 1000, 100, True, seed=5, matepair=matepair, **common)
+        for fq in (r1, r2):
+            recs = fastq_records(fq)
+            assert len(recs) == 500 and {r[1] for r in recs} == want
+            assert all(len(r[3]) == 100 for r in recs)
+
+
+def test_stream_sink_hands_out_the_same_bytes(ctx):
+    g = small_genome(seed=21)
+    r1, r2, _ = J.illumina(g, "", 3000, 100, True, seed=22, ctx=ctx, sink="memory")
+    got = {0: bytearray(), 1: bytearray()}
+    st = J.illumina(g, "", 3000, 100, True, seed=22, ctx=ctx, batch_pairs=256,
+                    sink=lambda job, end, buf: got[end].extend(bytes(buf)))
+    assert bytes(got[0]) == r1 and bytes(got[1]) == r2 and st["batches"] == 6 and st["d2h_bytes"] == len(r1) + len(r2)
+    dev = J.illumina(g, "", 3000, 100, True, seed=22, ctx=ctx, sink="device")
+    assert dev["bytes_out"] == [len(r1), len(r2)] and dev["d2h_bytes"] == 0 and dev["run_ms"] > 0
+
+
+def test_errors_surface_like_the_reference(ctx, tmp_path):
+    g = small_genome(seed=23)
+    with pytest.raises(J.JackalopeError):          # haplotype_probs with a ref_genome
+        J.illumina(g, "", 100, 100, True, seed=1, ctx=ctx, sink="memory", haplotype_probs=[1.0])
+    with pytest.raises(J.JackalopeError):          # params == NULL -> JLP_ERR_ARG with a message
+        ctx._check(ctx.lib.jlp_illumina_ref(ctx.h, None, None), "jlp_illumina_ref")
+    blocker = tmp_path / "blocker"
+    blocker.write_text("a file where a directory is needed")
+    with pytest.raises((RuntimeError, OSError)):   # unopenable output file (src/io.h:288-290)
+        J.illumina(g, str(blocker / "reads"), 100, 100, True, seed=1, ctx=ctx, overwrite=True)
+    with pytest.raises(RuntimeError, match="not built"):
+        J.illumina(g, str(tmp_path / "z"), 100, 100, True, seed=1, ctx=ctx, compress=True)
