@@ -117,8 +117,8 @@ typedef struct jlp_run_stats {
     uint64_t batches;
     uint64_t kernel_launches;    /* launches of this library's kernels */
     double device_ms;            /* sum of CUDA-event time of the kernels */
-    double gen_ms;               /* ... of which the quality/error kernel */
-    double fmt_ms;               /* ... of which the FASTQ formatter */
+    double place_ms;             /* ... of which the placement kernel (k_place) */
+    double reads_ms;             /* ... of which the fused quality/error + FASTQ kernel (k_reads) */
     uint64_t d2h_bytes;
     uint64_t h2d_bytes;
     double run_ms;               /* CUDA-event time on the compute stream from the start of the call's device

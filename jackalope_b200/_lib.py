@@ -35,15 +35,15 @@ class Params(C.Structure):
 class RunStats(C.Structure):
     _fields_ = [
         ("pairs", C.c_uint64), ("bytes_out", C.c_uint64 * 2), ("batches", C.c_uint64),
-        ("kernel_launches", C.c_uint64), ("device_ms", C.c_double), ("gen_ms", C.c_double),
-        ("fmt_ms", C.c_double), ("d2h_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64),
+        ("kernel_launches", C.c_uint64), ("device_ms", C.c_double), ("place_ms", C.c_double),
+        ("reads_ms", C.c_double), ("d2h_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64),
         ("run_ms", C.c_double),
     ]
 
     def as_dict(self):
         return dict(pairs=self.pairs, bytes_out=list(self.bytes_out), batches=self.batches,
-                    kernel_launches=self.kernel_launches, device_ms=self.device_ms, gen_ms=self.gen_ms,
-                    fmt_ms=self.fmt_ms, d2h_bytes=self.d2h_bytes, h2d_bytes=self.h2d_bytes, run_ms=self.run_ms)
+                    kernel_launches=self.kernel_launches, device_ms=self.device_ms, place_ms=self.place_ms,
+                    reads_ms=self.reads_ms, d2h_bytes=self.d2h_bytes, h2d_bytes=self.h2d_bytes, run_ms=self.run_ms)
 
 
 # every symbol include/jlp_b200.h declares

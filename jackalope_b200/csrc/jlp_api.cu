@@ -89,13 +89,13 @@ struct HapDev {
 };
 
 struct Slot {
-    DevBuf<uint8_t> seq, qual, out[2];
-    DevBuf<RecMeta> rec;
+    DevBuf<uint8_t> out[2];
+    DevBuf<EndPlan> plan;
     DevBuf<uint32_t> rec_len, rec_local;
     DevBuf<uint64_t> block_tot, block_base, totals;
     PinBuf<uint8_t> h_out[2];
     PinBuf<uint64_t> h_totals;
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // start, gen, scan, fmt, copied
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // start, placed, scanned, reads done, copied
     uint32_t pairs = 0;
     bool busy = false;
 };
@@ -116,10 +116,11 @@ struct jlp_ctx {
     EndTables tab[2];
     bool have_prof[2] = {false, false};
     DevBuf<uint32_t> d_meta[2], d_entry[2];
-    DevBuf<uint64_t> d_coin[2], d_mis[2];
-    DevBuf<uint16_t> d_mis16[2];
+    DevBuf<uint64_t> d_coin[2], d_mis[2], d_entry64[2];
+    int n_sm = 148;
     // run-scoped device data
     DevBuf<uint64_t> d_frag, d_group_off;
+    DevBuf<uint32_t> d_frag_guide;
     DevBuf<GroupDev> d_groups;
     DevBuf<uint8_t> d_strpool;
     DevBuf<uint32_t> d_status;
@@ -332,15 +333,14 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
     std::memset(&gp, 0, sizeof gp);
     gp.seed = P->seed;
     gp.n_ends = n_ends; gp.L = L; gp.matepair = matepair;
-    gp.row_stride = (L + 15u) & ~15u;
     gp.pool_pairs = (P->read_pool_size + n_ends - 1) / n_ends;   // pool closes at >= read_pool_size reads
     Thr td = thr_double_lt(P->prob_dup);
     gp.c_dup = td.thr; gp.dup_never = td.thr == 0;
     gp.c_rev = thr_ld_lt(0.5).thr;
     for (int e = 0; e < n_ends; e++) {
         EndDev& E = gp.end[e];
-        E.meta = c->d_meta[e].p; E.entry = c->d_entry[e].p; E.coin = c->d_coin[e].p;
-        E.mis16 = c->d_mis16[e].p; E.mis = c->d_mis[e].p;
+        E.meta = c->d_meta[e].p; E.entry = c->d_entry[e].p; E.entry64 = c->d_entry64[e].p; E.coin = c->d_coin[e].p;
+        E.mis = c->d_mis[e].p;
         E.entry_n = (uint32_t)c->tab[e].entry.size();
         Thr ta = thr_double_le(insp[e] + delp[e]);   // u > ins + del  <=>  x >= tA
         Thr ti = thr_double_le(insp[e]);             // u > ins        <=>  x >= tI
@@ -350,19 +350,18 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
     for (cudaEvent_t& ev : c->ev_run) if (!ev) CK(cudaEventCreate(&ev));
     CK(cudaEventRecord(c->ev_run[0], c->s_compute));
     std::vector<uint64_t> frag = frag_table(P->frag_len_shape, P->frag_len_scale, P->frag_len_min, P->frag_len_max);
+    std::vector<uint32_t> guide = frag_guide(frag);
     c->d_frag.upload(frag, c->s_compute);
+    c->d_frag_guide.upload(guide, c->s_compute);
     c->d_group_off.upload(group_off, c->s_compute);
     c->d_groups.upload(groups, c->s_compute);
     c->d_strpool.upload(strpool, c->s_compute);
     c->d_status.ensure(1);
     CK(cudaMemsetAsync(c->d_status.p, 0, sizeof(uint32_t), c->s_compute));
     c->h2d_bytes += frag.size() * 8 + group_off.size() * 8 + groups.size() * sizeof(GroupDev) + strpool.size();
-    gp.frag_cdf = c->d_frag.p; gp.frag_n = (uint32_t)frag.size(); gp.frag_min = P->frag_len_min;
+    gp.frag_cdf = c->d_frag.p; gp.frag_guide = c->d_frag_guide.p; gp.frag_n = (uint32_t)frag.size(); gp.frag_min = P->frag_len_min;
     gp.group_off = c->d_group_off.p; gp.n_groups = (uint32_t)groups.size();
     gp.groups = c->d_groups.p; gp.strpool = c->d_strpool.p; gp.status = c->d_status.p;
-
-    size_t smem = gen_smem_bytes(gp);
-    if (smem > 100 * 1024) smem = 0;               // big profiles: tables stay in global / L1
 
     // --- batch buffers
     uint64_t max_job = 0;
@@ -372,13 +371,12 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
     uint32_t max_prefix = 0;
     for (const GroupDev& g : groups) max_prefix = std::max(max_prefix, g.prefix_len);
     const uint64_t max_rec = (uint64_t)max_prefix + 20 + 5 + 2ull * L + 4;
+    gp.rec_buf = (uint32_t)((16 + max_rec + 15) & ~15ull);
     const uint64_t n_rec_max = B * n_ends;
     const uint32_t nsb_max = (uint32_t)((B + kScanBlock - 1) / kScanBlock);
     const bool need_host = sink.kind != SINK_NONE;
     for (Slot& s : c->slot) {
-        s.seq.ensure(n_rec_max * gp.row_stride);
-        s.qual.ensure(n_rec_max * gp.row_stride);
-        s.rec.ensure(n_rec_max);
+        s.plan.ensure(n_rec_max);
         s.rec_len.ensure(n_rec_max);
         s.rec_local.ensure(n_rec_max);
         s.block_tot.ensure((size_t)nsb_max * 2);
@@ -401,11 +399,11 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
     auto finish = [&](Slot& s, const Job& job) {
         (void)job;
         CK(cudaEventSynchronize(s.ev[3]));
-        float ms_gen = 0, ms_all = 0, ms_fmt = 0;
-        CK(cudaEventElapsedTime(&ms_gen, s.ev[0], s.ev[1]));
-        CK(cudaEventElapsedTime(&ms_fmt, s.ev[2], s.ev[3]));
+        float ms_place = 0, ms_all = 0, ms_reads = 0;
+        CK(cudaEventElapsedTime(&ms_place, s.ev[0], s.ev[1]));
+        CK(cudaEventElapsedTime(&ms_reads, s.ev[2], s.ev[3]));
         CK(cudaEventElapsedTime(&ms_all, s.ev[0], s.ev[3]));
-        st.gen_ms += ms_gen; st.fmt_ms += ms_fmt; st.device_ms += ms_all;
+        st.place_ms += ms_place; st.reads_ms += ms_reads; st.device_ms += ms_all;
         for (int e = 0; e < n_ends; e++) st.bytes_out[e] += s.h_totals.p[e];
         st.pairs += s.pairs;
         st.batches++;
@@ -456,23 +454,17 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
             if (s.busy) finish(s, job);
             const uint32_t np = (uint32_t)std::min<uint64_t>(B, hi - b0);
             gp.job_lo = job.lo; gp.job_hi = job.hi; gp.batch_lo = b0; gp.batch_pairs = np;
-            gp.seq = s.seq.p; gp.qual = s.qual.p; gp.rec = s.rec.p; gp.rec_len = s.rec_len.p;
             const uint32_t n_rec = np * n_ends;
             const uint32_t nsb = (np + kScanBlock - 1) / kScanBlock;
+            gp.plan = s.plan.p; gp.rec_len = s.rec_len.p; gp.rec_local = s.rec_local.p; gp.block_base = s.block_base.p;
+            gp.n_scan_blocks = nsb; gp.out[0] = s.out[0].p; gp.out[1] = s.out[1].p;
             CK(cudaEventRecord(s.ev[0], c->s_compute));
-            CK(launch_gen(gp, smem, c->s_compute));
+            CK(launch_place(gp, c->s_compute));
             CK(cudaEventRecord(s.ev[1], c->s_compute));
-            CK(launch_scan(s.rec_len.p, n_rec, n_ends, kScanBlock, s.rec_local.p, s.block_tot.p, s.block_base.p,
-                           s.totals.p, c->s_compute));
+            CK(launch_scan(s.rec_len.p, n_rec, n_ends, s.rec_local.p, s.block_tot.p, s.block_base.p, s.totals.p,
+                           c->s_compute));
             CK(cudaEventRecord(s.ev[2], c->s_compute));
-            FmtParams fp;
-            std::memset(&fp, 0, sizeof fp);
-            fp.n_records = n_rec; fp.n_ends = n_ends; fp.row_stride = gp.row_stride; fp.scan_block = kScanBlock;
-            fp.seq = s.seq.p; fp.qual = s.qual.p; fp.rec = s.rec.p; fp.rec_local = s.rec_local.p;
-            fp.block_base = s.block_base.p; fp.n_scan_blocks = nsb;
-            fp.groups = c->d_groups.p; fp.strpool = c->d_strpool.p;
-            fp.out[0] = s.out[0].p; fp.out[1] = s.out[1].p;
-            CK(launch_fmt(fp, c->s_compute));
+            CK(launch_reads(gp, c->n_sm, c->s_compute));
             CK(cudaMemcpyAsync(s.h_totals.p, s.totals.p, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->s_compute));
             CK(cudaEventRecord(s.ev[3], c->s_compute));
             st.kernel_launches += 4;
@@ -522,6 +514,7 @@ int jlp_ctx_create(int device, jlp_ctx** out) {
     std::unique_ptr<jlp_ctx> c(new jlp_ctx);
     c->device = device;
     int rc = guarded(c.get(), [&]() {
+        CK(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device));
         CK(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
     });
@@ -647,11 +640,11 @@ int jlp_set_profile(jlp_ctx* c, int end, uint64_t read_length, const uint32_t* n
         const EndTables& t = c->tab[end];
         c->d_meta[end].upload(t.meta, c->s_compute);
         c->d_entry[end].upload(t.entry, c->s_compute);
+        c->d_entry64[end].upload(t.entry64, c->s_compute);
         c->d_coin[end].upload(t.coin, c->s_compute);
-        c->d_mis16[end].upload(t.mis16, c->s_compute);
         c->d_mis[end].upload(t.mis, c->s_compute);
         CK(cudaStreamSynchronize(c->s_compute));
-        c->h2d_bytes += t.meta.size() * 4 + t.entry.size() * 12 + 256 * 10;
+        c->h2d_bytes += t.meta.size() * 4 + t.entry.size() * 20 + 256 * 8;
         c->have_prof[end] = true;
     });
 }

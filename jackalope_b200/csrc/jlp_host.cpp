@@ -114,6 +114,12 @@ void build_end_tables(uint64_t L, const uint32_t* nq, const double* probs, const
         out.mis[q] = t.thr;
         out.mis16[q] = static_cast<uint16_t>(t.thr >> 48);
     }
+    out.entry64.resize(tot);
+    for (uint64_t k = 0; k < tot; k++) {
+        uint32_t e = out.entry[k];
+        out.entry64[k] = static_cast<uint64_t>(e) | (static_cast<uint64_t>(out.mis16[(e >> 16) & 0xffu]) << 32) |
+                         (static_cast<uint64_t>(out.mis16[e >> 24]) << 48);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -176,6 +182,16 @@ std::vector<uint64_t> frag_table(double shape, double scale, uint64_t frag_min, 
         prev = c;
     }
     return cdf;
+}
+
+std::vector<uint32_t> frag_guide(const std::vector<uint64_t>& cdf) {
+    std::vector<uint32_t> g(257);
+    for (uint32_t b = 0; b < 256; b++) {
+        uint64_t x = static_cast<uint64_t>(b) << 56;
+        g[b] = static_cast<uint32_t>(std::upper_bound(cdf.begin(), cdf.end(), x) - cdf.begin());
+    }
+    g[256] = static_cast<uint32_t>(cdf.size());
+    return g;
 }
 
 std::vector<uint64_t> reads_per_group(uint64_t n_reads, std::vector<double> probs, uint64_t seed) {

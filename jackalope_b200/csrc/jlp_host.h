@@ -35,6 +35,7 @@ struct EndTables {
     uint64_t L = 0;
     std::vector<uint32_t> meta;     // [4*L]  offset << 8 | n
     std::vector<uint32_t> entry;    // per table slot: coin16 | q_self << 16 | q_alias << 24
+    std::vector<uint64_t> entry64;  // entry | mis16[q_self] << 32 | mis16[q_alias] << 48 (one load per base)
     std::vector<uint64_t> coin;     // full coin threshold per slot (slow path)
     std::vector<uint16_t> mis16;    // [256] high 16 bits of the mismatch threshold per quality
     std::vector<uint64_t> mis;      // [256] full mismatch threshold per quality
@@ -51,6 +52,9 @@ void build_end_tables(uint64_t L, const uint32_t* nq, const double* probs, const
 // (src/hts_illumina.cpp:206-208).  Entry count = hi - frag_min where hi is
 // frag_max or the point past which the tail mass is < 2^-64.
 std::vector<uint64_t> frag_table(double shape, double scale, uint64_t frag_min, uint64_t frag_max);
+// guide[b] = #{i : cdf[i] <= (b << 56)} for b = 0..256 (guide[256] = cdf.size()): the inverse-CDF
+// search for a draw x only has to look at cdf[guide[x >> 56] .. guide[(x >> 56) + 1]).
+std::vector<uint32_t> frag_guide(const std::vector<uint64_t>& cdf);
 // regularised lower incomplete gamma P(a, x)
 long double gamma_p(long double a, long double x);
 

@@ -2,12 +2,15 @@
 //
 //   k_materialize  haplotype chromosome from sorted mutation records
 //                  (HapChrom::get_chrom_full, /root/reference/src/hap_classes.cpp:80-116)
-//   k_gen          fragment placement + indels + ART quality/error model, one
-//                  thread per read end (chrom_indels_frag / sample_indels /
-//                  append_pools / fill_read_qual, src/hts_illumina.cpp:116-482,
-//                  src/hts_illumina.h:202-259)
+//   k_place        one thread per read end: duplicate leader, (haplotype, chromosome),
+//                  fragment length/start, strand, indel counts -> span and read length,
+//                  FASTQ record length (chrom_indels_frag / sample_indels /
+//                  adjust_chrom_spaces, src/hts_illumina.cpp:116-265)
 //   k_scan_*       exclusive scan of FASTQ record lengths -> output offsets
-//   k_fmt          FASTQ record assembly (fill_fq_lines, src/hts_illumina.cpp:285-326)
+//   k_reads        one warp per pair: template gather, ART quality/error model and FASTQ
+//                  record assembly in shared memory, 128-bit stores to the final offset
+//                  (append_pools / fill_read_qual / fill_fq_lines, src/hts_illumina.cpp:285-482,
+//                  src/hts_illumina.h:202-259)
 //
 // None of this is a dense contraction, so no tensor-core path exists here; the
 // kernels are integer/byte work bounded by HBM traffic and integer issue rate
@@ -78,22 +81,20 @@ cudaError_t launch_materialize(const uint8_t* ref, uint64_t ref_size, uint64_t n
     return cudaGetLastError();
 }
 
-// ------------------------------------------------------- quality / errors ---
+// ------------------------------------------------------------ primitives ---
 
 // nt_map (src/hts.h:36-44) as codes: T,C,A,G -> 0..3, anything else 4.
 __device__ __forceinline__ uint32_t nt_code(uint32_t c) {
-    return c == 'T' ? 0u : c == 'C' ? 1u : c == 'A' ? 2u : c == 'G' ? 3u : 4u;
+    // (c >> 1) & 3 sends A,C,T,G to 0,1,2,3; the byte-permute turns that into T0 C1 A2 G3,
+    // and a second one rebuilds the ASCII letter to reject every other byte
+    uint32_t code = __byte_perm(0x03000102u, 0u, (c >> 1) & 3u) & 0xffu;
+    uint32_t asc = __byte_perm(0x47414354u, 0u, code) & 0xffu;
+    return asc == c ? code : 4u;
 }
 // "TCAGN"[code]
 __device__ __forceinline__ uint32_t code_ascii(uint32_t code) {
     return __byte_perm(0x47414354u, 0x0000004Eu, code | 0x5550u);   // bytes 1..3 select a zero byte
 }
-
-struct Tables {
-    const uint32_t* meta[2];
-    const uint32_t* entry[2];
-    const uint16_t* mis16[2];
-};
 
 // classification of one template position (sample_indels, src/hts_illumina.cpp:131-146):
 // 0 plain base, 1 deletion, 2 insertion
@@ -110,6 +111,131 @@ __device__ __forceinline__ uint32_t field16(const U4& w, uint32_t f) {
     uint32_t v = (f >> 1) == 0 ? w.w0 : (f >> 1) == 1 ? w.w1 : (f >> 1) == 2 ? w.w2 : w.w3;
     return (f & 1) ? (v >> 16) : (v & 0xffffu);
 }
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
+    const uint32_t lane = threadIdx.x & 31u;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= (uint32_t)d) v += t;
+    }
+    return v;
+}
+
+// -------------------------------------------------------------- placement ---
+
+// One thread per read end: everything scalar about the read.
+//   duplicate-chain leader      ReadWriterOneThread::create_reads, src/hts.h:254-280
+//   (haplotype, chromosome)     src/hts_illumina.cpp:199-201, :505-528
+//   fragment length and start   chrom_indels_frag / indels_frag, src/hts_illumina.cpp:203-217, :245-258
+//   strand                      append_pools, src/hts_illumina.cpp:352
+//   indel counts -> span, len   sample_indels :116-150, adjust_chrom_spaces :153-184
+//   record length, start digits fill_fq_lines :285-326
+__global__ void __launch_bounds__(256)
+k_place(const __grid_constant__ GenParams p) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= p.batch_pairs * p.n_ends) return;
+    const uint32_t e = (p.n_ends == 2) ? (r & 1u) : 0u;
+    const uint64_t j = p.batch_lo + (p.n_ends == 2 ? (r >> 1) : r);
+    const uint32_t L = p.L;
+
+    uint64_t k = j;
+    if (!p.dup_never) {
+        while (k > p.job_lo && ((k - p.job_lo) % p.pool_pairs) != 0) {
+            uint64_t xd = hi64(draw_block(p.seed, k - 1, 1, PL_PAIR, 0));
+            if (!(xd < p.c_dup)) break;
+            k--;
+        }
+    }
+    uint32_t g;
+    {
+        uint32_t lo = 0, hi = p.n_groups;
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (p.group_off[mid] <= k) lo = mid; else hi = mid;
+        }
+        g = lo;
+    }
+    const GroupDev G = p.groups[g];
+    const uint64_t chrom_len = G.len;
+
+    uint64_t frag_len, frag_start;
+    {
+        U4 w = draw_block(p.seed, k, 0, PL_PAIR, 0);
+        uint64_t xf = lo64(w);
+        uint32_t lo = 0, hi = p.frag_n;                // first i with cdf[i] > xf
+        if (hi) { lo = p.frag_guide[xf >> 56]; hi = p.frag_guide[(xf >> 56) + 1]; }
+        while (lo < hi) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (p.frag_cdf[mid] <= xf) lo = mid + 1; else hi = mid;
+        }
+        frag_len = p.frag_min + lo;
+        if (frag_len >= chrom_len) { frag_len = chrom_len; frag_start = 0; }
+        else {
+            // double u = runif_01(eng); frag_start = u * (chrom_len - frag_len + 1)   (src/hts_illumina.cpp:215-216)
+            uint64_t xs = hi64(w);
+            double u = (xs == ~0ull) ? 1.0 : __ull2double_rn(xs + 1) * 5.421010862427522170037e-20;
+            frag_start = __double2ull_rz(__dmul_rn(u, __ull2double_rn(chrom_len - frag_len + 1)));
+        }
+    }
+    bool reverse = lo64(draw_block(p.seed, j, 1, PL_PAIR, 0)) < p.c_rev;
+    if (e) reverse = !reverse;
+
+    uint32_t frag_pos = 0, length_now = 0, n_ev = 0;
+    const uint32_t frag_cap = frag_len > 0xffffffffull ? 0xffffffffu : (uint32_t)frag_len;
+    const uint32_t hA = p.end[e].hA;
+    while (length_now < L && frag_pos < frag_cap) {
+        U4 w = draw_block(p.seed, j, frag_pos >> 3, PL_INDEL, e);
+        bool plain = ((w.w0 & 0xffffu) > hA) & ((w.w0 >> 16) > hA) & ((w.w1 & 0xffffu) > hA) & ((w.w1 >> 16) > hA) &
+                     ((w.w2 & 0xffffu) > hA) & ((w.w2 >> 16) > hA) & ((w.w3 & 0xffffu) > hA) & ((w.w3 >> 16) > hA);
+        if (plain && (frag_pos & 7u) == 0 && length_now + 8 <= L && frag_pos + 8 <= frag_cap) {
+            length_now += 8; frag_pos += 8;
+            continue;
+        }
+        uint32_t f = frag_pos & 7u;
+        for (; f < 8 && length_now < L && frag_pos < frag_cap; f++, frag_pos++) {
+            int cls = indel_class(p, e, j, frag_pos, field16(w, f));
+            if (cls == 0) length_now++;
+            else if (cls == 1) n_ev++;
+            else if (length_now == L - 1) length_now++;   // src/hts_illumina.cpp:138-139: treated as a plain base
+            else { length_now += 2; n_ev++; }
+        }
+    }
+    uint32_t S = frag_pos, len = length_now;
+    const uint32_t b = G.bc_len;
+    if (S <= b) {                                       // barcode covers the whole template: undefined in the reference
+        atomicOr(p.status, 1u);
+        S = b; len = 0; n_ev = 0;
+    }
+    const uint32_t space = S - b;
+    const uint64_t start = (p.matepair != 0) == reverse ? frag_start : frag_start + frag_len - space;
+
+    EndPlan pl;
+    pl.start = start; pl.group = g; pl.S = S; pl.len = (uint16_t)len;
+    pl.flags = (uint8_t)((reverse ? 1u : 0u) | (n_ev ? 2u : 0u));
+    uint32_t nd = 0;
+    uint8_t tmp[24];
+    {
+        uint64_t v = start;
+        do { tmp[nd++] = (uint8_t)('0' + (uint32_t)(v % 10)); v /= 10; } while (v);
+    }
+#pragma unroll
+    for (uint32_t t = 0; t < 24; t++) pl.digits[t] = t < nd ? tmp[nd - 1 - t] : 0;
+    pl.nd = (uint8_t)nd;
+    // '@' name '-' chrom '-' | digits | '-' F/R | ['/' 1/2] | '\n' | read '\n' '+' '\n' qual '\n'
+    pl.rec_len = G.prefix_len + nd + 3u + (p.n_ends == 2 ? 2u : 0u) + 2u * len + 4u;
+    p.plan[r] = pl;
+    p.rec_len[r] = pl.rec_len;
+}
+
+cudaError_t launch_place(const GenParams& p, cudaStream_t s) {
+    uint32_t n = p.batch_pairs * p.n_ends;
+    if (n == 0) return cudaSuccess;
+    k_place<<<(n + 255) / 256, 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------- quality / errors / FASTQ ---
 
 // Exact (full 64-bit draws) evaluation of one base; used when the 16 high bits
 // of any draw do not decide it.  fill_read_qual, src/hts_illumina.h:230-256.
@@ -138,8 +264,17 @@ __device__ __noinline__ uint32_t sub_slow(const GenParams& p, uint32_t e, uint64
     return si > 2 ? 2u : (uint32_t)si;
 }
 
-// One base: quality draw, mismatch draw, substitution.  Returns ascii | qualchar << 8.
-__device__ __forceinline__ uint32_t do_base(const GenParams& p, const Tables& T, uint32_t e, uint64_t j,
+// where this lane's end keeps its tables: 32-bit word index of meta and 64-bit
+// word index of entry64 inside the CTA's shared memory (SMEM) or nothing (global)
+struct TabRef {
+    uint32_t meta_w;
+    uint32_t ent_d;
+};
+
+// One base: quality draw, mismatch draw, substitution (fill_read_qual, src/hts_illumina.h:230-256).
+// Returns ascii | qualchar << 8.
+template <bool SMEM>
+__device__ __forceinline__ uint32_t do_base(const GenParams& p, const uint8_t* smem, TabRef tr, uint32_t e, uint64_t j,
                                             uint32_t pos, uint32_t code, uint32_t wa, uint32_t wb) {
     uint32_t Hdie = wa & 0xffffu, Hcoin = wa >> 16, Hmis = wb & 0xffffu, Hsub = wb >> 16;
     uint32_t q;
@@ -152,13 +287,18 @@ __device__ __forceinline__ uint32_t do_base(const GenParams& p, const Tables& T,
         if ((prod & 0xffffu) + 10u > 0xffffu) base_slow(p, e, j, pos, code, Hdie, Hcoin, Hmis, q, mism);
         return 0x4Eu | (((q + 33u) & 0xffu) << 8);
     }
-    uint32_t m = T.meta[e][code * p.L + pos];
+    uint32_t m;
+    if (SMEM) m = reinterpret_cast<const uint32_t*>(smem)[tr.meta_w + code * p.L + pos];
+    else m = p.end[e].meta[code * p.L + pos];
     uint32_t n = m & 0xffu, off = m >> 8;
     uint32_t prod = Hdie * n;
-    uint32_t ent = T.entry[e][off + (prod >> 16)];
-    uint32_t thr = ent & 0xffffu;
-    q = Hcoin < thr ? ((ent >> 16) & 0xffu) : (ent >> 24);
-    uint32_t mt = T.mis16[e][q];
+    uint2 ent;
+    if (SMEM) ent = reinterpret_cast<const uint2*>(smem)[tr.ent_d + off + (prod >> 16)];
+    else ent = reinterpret_cast<const uint2*>(p.end[e].entry64)[off + (prod >> 16)];
+    uint32_t thr = ent.x & 0xffffu;
+    bool self = Hcoin < thr;
+    q = self ? ((ent.x >> 16) & 0xffu) : (ent.x >> 24);
+    uint32_t mt = self ? (ent.y & 0xffffu) : (ent.y >> 16);
     mism = Hmis < mt;
     bool amb = ((prod & 0xffffu) + n > 0xffffu) | (Hcoin == thr) | (Hmis == mt);
     if (amb) base_slow(p, e, j, pos, code, Hdie, Hcoin, Hmis, q, mism);
@@ -172,229 +312,229 @@ __device__ __forceinline__ uint32_t do_base(const GenParams& p, const Tables& T,
     return code_ascii(code) | (((q + 33u) & 0xffu) << 8);
 }
 
-template <bool SMEM_TABLES>
-__global__ void __launch_bounds__(256)
-k_gen(const __grid_constant__ GenParams p) {
-    extern __shared__ __align__(16) uint32_t smem[];
-    Tables T;
-    if (SMEM_TABLES) {
-        uint32_t o = 0;
+// Base code at template position t of a read end (fill_read / rev_comp / barcode,
+// src/hts_illumina.cpp:369-391): barcode first, then the template, reverse-complemented
+// (cmp_map: T<->A, C<->G, everything else becomes 'N' later) on the reverse strand.
+__device__ __forceinline__ uint32_t template_code(const uint8_t* __restrict__ seg, const uint8_t* __restrict__ bc,
+                                                  uint32_t t, uint32_t b, uint32_t space, bool reverse) {
+    if (t < b) return nt_code(bc[t]);
+    uint32_t i = t - b;
+    uint32_t code = nt_code(reverse ? seg[space - 1u - i] : seg[i]);
+    if (reverse && code < 4u) code ^= 2u;
+    return code;
+}
+
+// One warp per read pair.  Phase A (per end): ID line and template base codes into the
+// end's record buffer in shared memory; phase B (both ends together, two bases per lane
+// and Philox block): qualities, mismatches; phase C (per end): the finished FASTQ record is
+// copied to its final place in the output with 128-bit stores.  The record sits in shared
+// memory at the same offset mod 16 as in the output file, so whole 16-byte chunks move as
+// one vector; only a record's first and last partial chunk use byte stores.
+template <bool SMEM>
+__global__ void __launch_bounds__(512, 2)
+k_reads(const __grid_constant__ GenParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t L = p.L;
+    uint32_t tab_bytes = 0;
+    TabRef tabs[2] = {{0, 0}, {0, 0}};
+    if (SMEM) {
         for (uint32_t e = 0; e < p.n_ends; e++) {
             const EndDev& E = p.end[e];
-            uint32_t* m = smem + o;            o += 4 * p.L;
-            uint32_t* en = smem + o;           o += E.entry_n;
-            uint32_t* mi = smem + o;           o += 128;
-            for (uint32_t i = threadIdx.x; i < 4 * p.L; i += blockDim.x) m[i] = E.meta[i];
-            for (uint32_t i = threadIdx.x; i < E.entry_n; i += blockDim.x) en[i] = E.entry[i];
-            for (uint32_t i = threadIdx.x; i < 128; i += blockDim.x) mi[i] = reinterpret_cast<const uint32_t*>(E.mis16)[i];
-            T.meta[e] = m; T.entry[e] = en; T.mis16[e] = reinterpret_cast<const uint16_t*>(mi);
+            tabs[e].ent_d = tab_bytes >> 3;
+            uint64_t* en = reinterpret_cast<uint64_t*>(smem + tab_bytes);
+            for (uint32_t i = threadIdx.x; i < E.entry_n; i += blockDim.x) en[i] = E.entry64[i];
+            tab_bytes += E.entry_n * 8u;
+            tabs[e].meta_w = tab_bytes >> 2;
+            uint32_t* m = reinterpret_cast<uint32_t*>(smem + tab_bytes);
+            for (uint32_t i = threadIdx.x; i < 4 * L; i += blockDim.x) m[i] = E.meta[i];
+            tab_bytes += 4u * L * 4u;
+            tab_bytes = (tab_bytes + 15u) & ~15u;
         }
         __syncthreads();
-    } else {
-        for (uint32_t e = 0; e < p.n_ends; e++) {
-            T.meta[e] = p.end[e].meta; T.entry[e] = p.end[e].entry; T.mis16[e] = p.end[e].mis16;
-        }
     }
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    const uint32_t n_ends = p.n_ends;
+    const uint32_t R0 = tab_bytes + warp * n_ends * p.rec_buf;     // this warp's record buffers
 
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= p.batch_pairs * p.n_ends) return;
-    const uint32_t e = (p.n_ends == 2) ? (r & 1u) : 0u;
-    const uint64_t j = p.batch_lo + (p.n_ends == 2 ? (r >> 1) : r);
-    const uint32_t L = p.L;
+    for (uint32_t i = blockIdx.x * wpc + warp; i < p.batch_pairs; i += gridDim.x * wpc) {
+        const uint64_t j = p.batch_lo + i;
+        uint32_t sq[2] = {0, 0}, len[2] = {0, 0}, al[2] = {0, 0}, rlen[2] = {0, 0};
+        uint64_t off[2] = {0, 0};
 
-    // ---- duplicate-chain leader (ReadWriterOneThread::create_reads, src/hts.h:254-280)
-    uint64_t k = j;
-    if (!p.dup_never) {
-        while (k > p.job_lo && ((k - p.job_lo) % p.pool_pairs) != 0) {
-            uint64_t xd = hi64(draw_block(p.seed, k - 1, 1, PL_PAIR, 0));
-            if (!(xd < p.c_dup)) break;
-            k--;
-        }
-    }
-    // ---- (haplotype, chromosome) group of the leader
-    uint32_t g;
-    {
-        uint32_t lo = 0, hi = p.n_groups;
-        while (hi - lo > 1) {
-            uint32_t mid = (lo + hi) >> 1;
-            if (p.group_off[mid] <= k) lo = mid; else hi = mid;
-        }
-        g = lo;
-    }
-    const GroupDev G = p.groups[g];
-    const uint64_t chrom_len = G.len;
-
-    // ---- fragment length and start (chrom_indels_frag, src/hts_illumina.cpp:203-217)
-    uint64_t frag_len, frag_start;
-    {
-        U4 w = draw_block(p.seed, k, 0, PL_PAIR, 0);
-        uint64_t xf = lo64(w);
-        uint32_t lo = 0, hi = p.frag_n;                // first i with cdf[i] > xf
-        while (lo < hi) {
-            uint32_t mid = (lo + hi) >> 1;
-            if (p.frag_cdf[mid] <= xf) lo = mid + 1; else hi = mid;
-        }
-        frag_len = p.frag_min + lo;
-        if (frag_len >= chrom_len) { frag_len = chrom_len; frag_start = 0; }
-        else {
-            uint64_t xs = hi64(w);
-            double u = (xs == ~0ull) ? 1.0 : __ull2double_rn(xs + 1) * 5.421010862427522170037e-20;
-            frag_start = __double2ull_rz(__dmul_rn(u, __ull2double_rn(chrom_len - frag_len + 1)));
-        }
-    }
-    // ---- strand (append_pools, src/hts_illumina.cpp:352); the second end is the opposite
-    bool reverse = lo64(draw_block(p.seed, j, 1, PL_PAIR, 0)) < p.c_rev;
-    if (e) reverse = !reverse;
-
-    // ---- indels, pass 1: counts only (sample_indels, src/hts_illumina.cpp:116-150)
-    uint32_t frag_pos = 0, length_now = 0, n_ev = 0;
-    const uint32_t frag_cap = frag_len > 0xffffffffull ? 0xffffffffu : (uint32_t)frag_len;
-    while (length_now < L && frag_pos < frag_cap) {
-        U4 w = draw_block(p.seed, j, frag_pos >> 3, PL_INDEL, e);
-        const uint32_t hA = p.end[e].hA;
-        bool plain = ((w.w0 & 0xffffu) > hA) & ((w.w0 >> 16) > hA) & ((w.w1 & 0xffffu) > hA) & ((w.w1 >> 16) > hA) &
-                     ((w.w2 & 0xffffu) > hA) & ((w.w2 >> 16) > hA) & ((w.w3 & 0xffffu) > hA) & ((w.w3 >> 16) > hA);
-        if (plain && (frag_pos & 7u) == 0 && length_now + 8 <= L && frag_pos + 8 <= frag_cap) {
-            length_now += 8; frag_pos += 8;
-            continue;
-        }
-        uint32_t f = frag_pos & 7u;
-        for (; f < 8 && length_now < L && frag_pos < frag_cap; f++, frag_pos++) {
-            int cls = indel_class(p, e, j, frag_pos, field16(w, f));
-            if (cls == 0) length_now++;
-            else if (cls == 1) n_ev++;
-            else if (length_now == L - 1) length_now++;
-            else { length_now += 2; n_ev++; }
-        }
-    }
-    // adjust_chrom_spaces (src/hts_illumina.cpp:153-184): the template span equals the
-    // number of positions visited; the read ends up `length_now` long.
-    uint32_t S = frag_pos, len = length_now;
-    const uint32_t b = G.bc_len;
-    if (S <= b) {                                       // barcode covers the whole template: undefined in the reference
-        atomicOr(p.status, 1u);
-        S = b; len = 0;
-    }
-    const uint32_t space = S - b;
-    const uint64_t start = (p.matepair != 0) == reverse ? frag_start : frag_start + frag_len - space;
-
-    uint8_t* row = p.seq + (size_t)r * p.row_stride;
-    uint8_t* qrow = p.qual + (size_t)r * p.row_stride;
-    const uint8_t* seg = G.seq + start;
-    const uint8_t* bc = p.strpool + G.bc_off;
-
-    // ---- template -> oriented, indel-applied read as base codes in `row`
-    //      (fill_read / rev_comp / barcode, src/hts_illumina.cpp:369-391; indel application
-    //       from fill_read_qual, src/hts_illumina.h:213-225)
-    if (len == 0) {
-        // nothing to build
-    } else if (n_ev == 0) {
-        for (uint32_t t = 0; t < S; t++) {
-            uint32_t code;
-            if (t < b) code = nt_code(bc[t]);
-            else {
-                uint32_t i = t - b;
-                code = nt_code(reverse ? seg[space - 1 - i] : seg[i]);
-                if (reverse && code < 4) code ^= 2u;    // cmp_map: T<->A, C<->G
-            }
-            row[t] = (uint8_t)code;
-        }
-    } else {
-        uint32_t out = 0, ln = 0;
-        for (uint32_t t = 0; t < S; t++) {
-            U4 w = draw_block(p.seed, j, t >> 3, PL_INDEL, e);
-            int cls = indel_class(p, e, j, t, field16(w, t & 7u));
-            if (cls == 2 && ln == L - 1) cls = 0;
-            if (cls == 1) continue;
-            uint32_t code;
-            if (t < b) code = nt_code(bc[t]);
-            else {
-                uint32_t i = t - b;
-                code = nt_code(reverse ? seg[space - 1 - i] : seg[i]);
-                if (reverse && code < 4) code ^= 2u;
-            }
-            row[out++] = (uint8_t)code;
-            ln++;
-            if (cls == 2) {
-                // bases[(uint64)(u * 4)], src/hts_illumina.h:216; index 4 reads the
-                // string terminator, which nt_map then turns into 'N'
-                row[out++] = (uint8_t)ins_base_index(slow64(p.seed, j, e, PU_INS, t));
-                ln++;
-            }
-        }
-    }
-
-    // ---- qualities, mismatches (fill_read_qual, src/hts_illumina.h:230-256), 16 bases per step
-    for (uint32_t blk = 0; blk * 16 < len; blk++) {
-        uint4 cw = *reinterpret_cast<const uint4*>(row + blk * 16);
-        uint32_t c[4] = {cw.x, cw.y, cw.z, cw.w};
-        uint32_t sw[4] = {0, 0, 0, 0}, qw[4] = {0, 0, 0, 0};
+        // ---- phase A: ID line + template codes
 #pragma unroll
-        for (uint32_t h = 0; h < 8; h++) {
-            uint32_t pos = blk * 16 + 2 * h;
-            if (pos < len) {
-                U4 w = draw_block(p.seed, j, pos >> 1, PL_QUAL, e);
-                uint32_t code0 = (c[h >> 1] >> (16 * (h & 1))) & 0xffu;
-                uint32_t r0 = do_base(p, T, e, j, pos, code0, w.w0, w.w1);
-                sw[h >> 1] |= (r0 & 0xffu) << (16 * (h & 1));
-                qw[h >> 1] |= (r0 >> 8) << (16 * (h & 1));
-                if (pos + 1 < len) {
-                    uint32_t code1 = (c[h >> 1] >> (16 * (h & 1) + 8)) & 0xffu;
-                    uint32_t r1 = do_base(p, T, e, j, pos + 1, code1, w.w2, w.w3);
-                    sw[h >> 1] |= (r1 & 0xffu) << (16 * (h & 1) + 8);
-                    qw[h >> 1] |= (r1 >> 8) << (16 * (h & 1) + 8);
+        for (uint32_t e = 0; e < 2; e++) {
+            if (e >= n_ends) break;
+            const uint32_t r = i * n_ends + e;
+            const uint4* pp = reinterpret_cast<const uint4*>(p.plan + r);
+            const uint4 pa = pp[0], pb = pp[1], pc = pp[2];
+            const uint64_t start = ((uint64_t)pa.y << 32) | pa.x;
+            const uint32_t S = pa.w;
+            const uint32_t ln = pb.x & 0xffffu, flags = (pb.x >> 16) & 0xffu, nd = pb.x >> 24;
+            const bool reverse = flags & 1u;
+            const GroupDev* Gp = p.groups + pa.z;
+            const uint8_t* gseq = Gp->seq;
+            const uint32_t prefix_off = Gp->prefix_off, prefix_len = Gp->prefix_len, bc_off = Gp->bc_off, b = Gp->bc_len;
+            const uint64_t o = p.block_base[(size_t)e * p.n_scan_blocks + i / kScanBlock] + p.rec_local[r];
+            const uint32_t a = (uint32_t)o & 15u;
+            const uint32_t R = R0 + e * p.rec_buf;
+            uint32_t w = R + a;
+            for (uint32_t t = lane; t < prefix_len; t += 32) smem[w + t] = p.strpool[prefix_off + t];
+            w += prefix_len;
+            if (lane < nd) {
+                uint32_t word = lane < 4 ? pb.z : lane < 8 ? pb.w : lane < 12 ? pc.x : lane < 16 ? pc.y : lane < 20 ? pc.z : pc.w;
+                smem[w + lane] = (uint8_t)(word >> (8u * (lane & 3u)));
+            }
+            w += nd;
+            if (lane == 0) {
+                uint32_t q = w;
+                smem[q++] = '-';
+                smem[q++] = reverse ? 'R' : 'F';
+                if (n_ends == 2) { smem[q++] = '/'; smem[q++] = (uint8_t)('1' + e); }
+                smem[q] = '\n';
+            }
+            w += 3u + (n_ends == 2 ? 2u : 0u);
+            const uint8_t* seg = gseq + start;
+            const uint8_t* bc = p.strpool + bc_off;
+            const uint32_t space = S - b;
+            if (!(flags & 2u)) {
+                // no insertion or deletion: position t of the read is position t of the template
+                for (uint32_t t = lane; t < ln; t += 32) smem[w + t] = (uint8_t)template_code(seg, bc, t, b, space, reverse);
+            } else {
+                // indels: every template position gets its class again (same draws as the placement
+                // kernel), a warp prefix sum gives each surviving base its place in the read
+                // (fill_read_qual applies the same edits from the back, src/hts_illumina.h:213-225)
+                uint32_t carry = 0;
+                for (uint32_t t0 = 0; t0 < S; t0 += 256) {
+                    const uint32_t tb = t0 + 8u * lane;
+                    uint32_t cls = 0, wsum = 0;
+                    if (tb < S) {
+                        U4 dw = draw_block(p.seed, j, tb >> 3, PL_INDEL, e);
+#pragma unroll
+                        for (uint32_t f = 0; f < 8; f++) {
+                            if (tb + f < S) {
+                                uint32_t c = (uint32_t)indel_class(p, e, j, tb + f, field16(dw, f));
+                                cls |= c << (2u * f);
+                                wsum += c == 0 ? 1u : c == 1 ? 0u : 2u;
+                            }
+                        }
+                    }
+                    uint32_t incl = warp_incl_scan(wsum);
+                    uint32_t o2 = carry + incl - wsum;
+                    carry += __shfl_sync(0xffffffffu, incl, 31);
+                    if (tb < S) {
+#pragma unroll
+                        for (uint32_t f = 0; f < 8; f++) {
+                            const uint32_t t = tb + f;
+                            if (t < S) {
+                                uint32_t c = (cls >> (2u * f)) & 3u;
+                                if (c == 2u && o2 == L - 1u) c = 0;     // src/hts_illumina.cpp:138-139
+                                if (c != 1u && o2 < ln) {
+                                    smem[w + o2++] = (uint8_t)template_code(seg, bc, t, b, space, reverse);
+                                    if (c == 2u && o2 < ln) {
+                                        // bases[(uint64)(u * 4)], src/hts_illumina.h:216; index 4 reads the
+                                        // string terminator, which nt_map then turns into 'N'
+                                        smem[w + o2++] = (uint8_t)ins_base_index(slow64(p.seed, j, e, PU_INS, t));
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            if (lane == 0) {
+                smem[w + ln] = '\n'; smem[w + ln + 1] = '+'; smem[w + ln + 2] = '\n';
+                smem[w + 2 * ln + 3] = '\n';
+            }
+            sq[e] = w; len[e] = ln; al[e] = a; off[e] = o; rlen[e] = pb.y;
+        }
+        __syncwarp();
+
+        // ---- phase B: qualities and mismatches, two bases per lane per step, both ends in one index space
+        {
+            const uint32_t nb0 = (len[0] + 1u) >> 1, nb1 = (len[1] + 1u) >> 1;
+            for (uint32_t q = lane; q < nb0 + nb1; q += 32) {
+                const uint32_t e = q >= nb0 ? 1u : 0u;
+                const uint32_t blk = q - (e ? nb0 : 0u);
+                const uint32_t pos = 2u * blk;
+                const uint32_t ln = e ? len[1] : len[0];
+                const uint32_t s0 = (e ? sq[1] : sq[0]) + pos;
+                const uint32_t q0 = s0 + ln + 3u;
+                TabRef tr;
+                tr.meta_w = e ? tabs[1].meta_w : tabs[0].meta_w;
+                tr.ent_d = e ? tabs[1].ent_d : tabs[0].ent_d;
+                U4 w = draw_block(p.seed, j, blk, PL_QUAL, e);
+                uint32_t r0 = do_base<SMEM>(p, smem, tr, e, j, pos, smem[s0], w.w0, w.w1);
+                smem[s0] = (uint8_t)r0;
+                smem[q0] = (uint8_t)(r0 >> 8);
+                if (pos + 1u < ln) {
+                    uint32_t r1 = do_base<SMEM>(p, smem, tr, e, j, pos + 1u, smem[s0 + 1u], w.w2, w.w3);
+                    smem[s0 + 1u] = (uint8_t)r1;
+                    smem[q0 + 1u] = (uint8_t)(r1 >> 8);
                 }
             }
         }
-        *reinterpret_cast<uint4*>(row + blk * 16) = make_uint4(sw[0], sw[1], sw[2], sw[3]);
-        *reinterpret_cast<uint4*>(qrow + blk * 16) = make_uint4(qw[0], qw[1], qw[2], qw[3]);
-    }
+        __syncwarp();
 
-    // ---- record metadata + FASTQ record length (fill_fq_lines, src/hts_illumina.cpp:285-326)
-    RecMeta rm;
-    rm.start = start; rm.group = g; rm.len = (uint16_t)len; rm.reverse = reverse ? 1 : 0; rm.pad = 0;
-    p.rec[r] = rm;
-    uint32_t nd = 1;
-    for (uint64_t v = start; v >= 10; v /= 10) nd++;
-    // '@' name '-' chrom '-' | digits | '-' F/R | ['/' 1/2] | '\n' | read '\n' '+' '\n' qual '\n'
-    p.rec_len[r] = G.prefix_len + nd + 3u + (p.n_ends == 2 ? 2u : 0u) + 2u * len + 4u;
-}
-
-size_t gen_smem_bytes(const GenParams& p) {
-    size_t words = 0;
-    for (uint32_t e = 0; e < p.n_ends; e++) words += 4 * (size_t)p.L + p.end[e].entry_n + 128;
-    return words * 4;
-}
-
-cudaError_t launch_gen(const GenParams& p, size_t smem_bytes, cudaStream_t s) {
-    uint32_t n = p.batch_pairs * p.n_ends;
-    if (n == 0) return cudaSuccess;
-    uint32_t blocks = (n + 255) / 256;
-    if (smem_bytes) {
-        static size_t configured = 0;
-        if (smem_bytes > configured) {
-            cudaError_t err = cudaFuncSetAttribute(k_gen<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-            if (err != cudaSuccess) return err;
-            configured = smem_bytes;
+        // ---- phase C: records to their final offsets
+#pragma unroll
+        for (uint32_t e = 0; e < 2; e++) {
+            if (e >= n_ends) break;
+            const uint32_t R = R0 + e * p.rec_buf;
+            const uint32_t a = al[e], total = a + rlen[e];
+            uint8_t* dst = p.out[e] + (off[e] - a);
+            for (uint32_t c = lane; c * 16u < total; c += 32) {
+                const uint32_t lo = c * 16u, hi = lo + 16u;
+                if (lo >= a && hi <= total) {
+                    *reinterpret_cast<uint4*>(dst + lo) = *reinterpret_cast<const uint4*>(smem + R + lo);
+                } else {
+                    const uint32_t k0 = lo > a ? lo : a, k1 = hi < total ? hi : total;
+                    for (uint32_t k = k0; k < k1; k++) dst[k] = smem[R + k];
+                }
+            }
         }
-        k_gen<true><<<blocks, 256, smem_bytes, s>>>(p);
-    } else {
-        k_gen<false><<<blocks, 256, 0, s>>>(p);
+        __syncwarp();
     }
+}
+
+static size_t reads_table_bytes(const GenParams& p) {
+    size_t b = 0;
+    for (uint32_t e = 0; e < p.n_ends; e++) {
+        b += (size_t)p.end[e].entry_n * 8 + 4 * (size_t)p.L * 4;
+        b = (b + 15) & ~(size_t)15;
+    }
+    return b;
+}
+
+cudaError_t launch_reads(const GenParams& p, int n_sm, cudaStream_t s) {
+    if (p.batch_pairs == 0) return cudaSuccess;
+    const int threads = 512, wpc = threads / 32;
+    const size_t rec_bytes = (size_t)wpc * p.n_ends * p.rec_buf;
+    const size_t tab = reads_table_bytes(p);
+    const bool use_smem = tab + rec_bytes <= 200 * 1024;
+    const size_t smem_bytes = rec_bytes + (use_smem ? tab : 0);
+    cudaError_t err;
+    int per_sm = 0;
+    if (use_smem) {
+        err = cudaFuncSetAttribute(k_reads<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        if (err != cudaSuccess) return err;
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_reads<true>, threads, smem_bytes);
+    } else {
+        err = cudaFuncSetAttribute(k_reads<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        if (err != cudaSuccess) return err;
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_reads<false>, threads, smem_bytes);
+    }
+    if (err != cudaSuccess) return err;
+    if (per_sm < 1) per_sm = 1;
+    uint32_t blocks = (p.batch_pairs + wpc - 1) / wpc;
+    const uint32_t cap = (uint32_t)(n_sm > 0 ? n_sm : 148) * (uint32_t)per_sm;
+    if (blocks > cap) blocks = cap;
+    if (use_smem) k_reads<true><<<blocks, threads, smem_bytes, s>>>(p);
+    else k_reads<false><<<blocks, threads, smem_bytes, s>>>(p);
     return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------ scan ---
-
-__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
-    const uint32_t lane = threadIdx.x & 31u;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
-        if (lane >= (uint32_t)d) v += t;
-    }
-    return v;
-}
 
 // block (file e, scan block b): exclusive prefix of up to kScanBlock record lengths
 __global__ void __launch_bounds__(1024)
@@ -443,66 +583,13 @@ k_scan_tops(const uint64_t* __restrict__ block_tot, uint32_t n_blocks, uint64_t*
 }
 
 cudaError_t launch_scan(const uint32_t* rec_len, uint32_t n_records, uint32_t n_ends,
-                        uint32_t scan_block, uint32_t* rec_local, uint64_t* block_tot,
+                        uint32_t* rec_local, uint64_t* block_tot,
                         uint64_t* block_base, uint64_t* totals_out, cudaStream_t s) {
-    (void)scan_block;
     uint32_t per_file = n_records / n_ends;
     uint32_t n_blocks = (per_file + kScanBlock - 1) / kScanBlock;
     if (n_blocks == 0) return cudaSuccess;
     k_scan_local<<<n_blocks * n_ends, 1024, 0, s>>>(rec_len, n_records, n_ends, n_blocks, rec_local, block_tot);
     k_scan_tops<<<n_ends, 1024, 0, s>>>(block_tot, n_blocks, block_base, totals_out);
-    return cudaGetLastError();
-}
-
-// ---------------------------------------------------------------- format ---
-
-// One warp per record; lanes copy consecutive bytes, so every store instruction
-// covers one contiguous 32-byte run of the output file.
-__global__ void __launch_bounds__(256)
-k_fmt(const __grid_constant__ FmtParams p) {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (r >= p.n_records) return;
-    const uint32_t e = (p.n_ends == 2) ? (r & 1u) : 0u;
-    const uint32_t i = (p.n_ends == 2) ? (r >> 1) : r;
-    const RecMeta rm = p.rec[r];
-    const GroupDev G = p.groups[rm.group];
-    uint8_t* dst = p.out[e] + p.block_base[(size_t)e * p.n_scan_blocks + i / kScanBlock] + p.rec_local[r];
-
-    // ID line: "@<genome>-<chrom>-" <start> "-" F|R ["/" 1|2] "\n"
-    const uint8_t* pre = p.strpool + G.prefix_off;
-    for (uint32_t t = lane; t < G.prefix_len; t += 32) dst[t] = pre[t];
-    dst += G.prefix_len;
-    uint32_t nd = 1;
-    for (uint64_t v = rm.start; v >= 10; v /= 10) nd++;
-    if (lane < nd) {
-        uint64_t v = rm.start;
-        for (uint32_t t = 0; t < nd - 1 - lane; t++) v /= 10;
-        dst[lane] = (uint8_t)('0' + (v % 10));
-    }
-    dst += nd;
-    if (lane == 0) {
-        uint32_t o = 0;
-        dst[o++] = '-';
-        dst[o++] = rm.reverse ? 'R' : 'F';
-        if (p.n_ends == 2) { dst[o++] = '/'; dst[o++] = (uint8_t)('1' + e); }
-        dst[o++] = '\n';
-    }
-    dst += 3u + (p.n_ends == 2 ? 2u : 0u);
-    const uint32_t len = rm.len;
-    const uint8_t* srow = p.seq + (size_t)r * p.row_stride;
-    const uint8_t* qrow = p.qual + (size_t)r * p.row_stride;
-    for (uint32_t t = lane; t < len; t += 32) dst[t] = srow[t];
-    if (lane == 0) { dst[len] = '\n'; dst[len + 1] = '+'; dst[len + 2] = '\n'; }
-    dst += len + 3;
-    for (uint32_t t = lane; t < len; t += 32) dst[t] = qrow[t];
-    if (lane == 0) dst[len] = '\n';
-}
-
-cudaError_t launch_fmt(const FmtParams& p, cudaStream_t s) {
-    if (p.n_records == 0) return cudaSuccess;
-    uint32_t blocks = (p.n_records + 7) / 8;
-    k_fmt<<<blocks, 256, 0, s>>>(p);
     return cudaGetLastError();
 }
 

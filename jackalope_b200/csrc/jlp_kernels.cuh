@@ -18,21 +18,26 @@ struct GroupDev {
     uint32_t bc_len;
 };
 
-// Per read end, written by the quality/error kernel, read by the formatter.
-struct RecMeta {
+// Everything scalar about one read end, written by the placement kernel (one
+// thread per end), read by the read kernel (one warp per pair).
+struct EndPlan {
     uint64_t start;        // leftmost template coordinate (fill_fq_lines `start`)
     uint32_t group;
+    uint32_t S;            // template positions consumed, barcode included (adjust_chrom_spaces)
     uint16_t len;          // final read length
-    uint8_t reverse;
-    uint8_t pad;
+    uint8_t flags;         // bit 0: reverse strand, bit 1: the end has insertions/deletions
+    uint8_t nd;            // decimal digits of `start`
+    uint32_t rec_len;      // FASTQ bytes of the record
+    uint8_t digits[24];    // `start` in decimal, most significant first
 };
+static_assert(sizeof(EndPlan) == 48, "EndPlan layout");
 
 struct EndDev {
     const uint32_t* meta;    // [4*L] offset << 8 | n
-    const uint32_t* entry;   // coin16 | q_self << 16 | q_alias << 24
+    const uint64_t* entry64; // coin16 | q_self << 16 | q_alias << 24 | mis16[q_self] << 32 | mis16[q_alias] << 48
+    const uint32_t* entry;   // low half of entry64 (slow path)
     const uint64_t* coin;    // full thresholds (slow path)
-    const uint16_t* mis16;   // [256]
-    const uint64_t* mis;     // [256]
+    const uint64_t* mis;     // [256] full mismatch thresholds (slow path)
     uint32_t entry_n;
     uint32_t hA;             // high-16 gate of the indel draw (0x10000 = always slow)
     uint64_t tA, tI;         // x >= tA: plain base; else x >= tI: deletion; else insertion
@@ -48,39 +53,26 @@ struct GenParams {
     uint32_t n_ends;
     uint32_t L;
     uint32_t matepair;
-    uint32_t row_stride;
     uint32_t dup_never;      // prob_dup threshold is 0
+    uint32_t rec_buf;        // bytes of shared memory per (warp, end) record buffer
     uint64_t c_dup;          // x < c_dup: duplicate of the previous fragment
     uint64_t c_rev;          // x < c_rev: reverse strand first
     EndDev end[2];
     const uint64_t* frag_cdf;
+    const uint32_t* frag_guide;  // [257]
     uint32_t frag_n;
     uint32_t n_groups;
     uint64_t frag_min;
     const uint64_t* group_off;   // [n_groups + 1] pair-index prefix offsets
     const GroupDev* groups;
     const uint8_t* strpool;
-    uint8_t* seq;                // [records][row_stride]
-    uint8_t* qual;               // [records][row_stride]
-    RecMeta* rec;                // [records]
-    uint32_t* rec_len;           // [records] FASTQ bytes of each record
-    uint32_t* status;            // device error bits (1: barcode >= template)
-};
-
-struct FmtParams {
-    uint32_t n_records;
-    uint32_t n_ends;
-    uint32_t row_stride;
-    uint32_t scan_block;         // records per scan block (per file)
-    const uint8_t* seq;
-    const uint8_t* qual;
-    const RecMeta* rec;
-    const uint32_t* rec_local;   // exclusive prefix inside the scan block
+    EndPlan* plan;               // [records]
+    uint32_t* rec_len;           // [records] FASTQ bytes of each record (scan input)
+    const uint32_t* rec_local;   // [records] exclusive prefix inside the scan block
     const uint64_t* block_base;  // [n_ends][n_scan_blocks] exclusive prefix of block totals
     uint32_t n_scan_blocks;
-    const GroupDev* groups;
-    const uint8_t* strpool;
-    uint8_t* out[2];
+    uint8_t* out[2];             // FASTQ output of the batch, per file
+    uint32_t* status;            // device error bits (1: barcode >= template)
 };
 
 // haplotype materialisation (HapChrom::get_chrom_full)
@@ -90,18 +82,18 @@ cudaError_t launch_materialize(const uint8_t* ref, uint64_t ref_size, uint64_t n
                                const uint8_t* pool, uint64_t chrom_size, uint8_t* out,
                                cudaStream_t s);
 
-// quality / error kernel; smem_bytes = 0 selects the global-table variant
-cudaError_t launch_gen(const GenParams& p, size_t smem_bytes, cudaStream_t s);
-size_t gen_smem_bytes(const GenParams& p);
+// fragment placement + indel summary + record lengths, one thread per read end
+cudaError_t launch_place(const GenParams& p, cudaStream_t s);
 
 // record-offset scan: local exclusive prefixes + per-block totals, then the
 // exclusive prefix of the totals (and the grand total per file in totals_out)
 cudaError_t launch_scan(const uint32_t* rec_len, uint32_t n_records, uint32_t n_ends,
-                        uint32_t scan_block, uint32_t* rec_local, uint64_t* block_tot,
-                        uint64_t* block_base, uint64_t* totals_out, cudaStream_t s);
+                        uint32_t* rec_local, uint64_t* block_tot, uint64_t* block_base,
+                        uint64_t* totals_out, cudaStream_t s);
 
-// FASTQ formatter
-cudaError_t launch_fmt(const FmtParams& p, cudaStream_t s);
+// template gather + quality/error model + FASTQ record assembly, one warp per pair;
+// n_sm sizes the persistent grid
+cudaError_t launch_reads(const GenParams& p, int n_sm, cudaStream_t s);
 
 constexpr uint32_t kScanBlock = 1024;
 
