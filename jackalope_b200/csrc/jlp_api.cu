@@ -27,6 +27,10 @@ namespace {
 
 std::string g_create_error;
 
+// Bytes of padding in front of and behind every sequence allocation: the read kernel
+// fetches template bases as aligned words and may touch a few bytes outside a chromosome.
+constexpr size_t kPad = 64;
+
 struct CudaErr : std::runtime_error {
     explicit CudaErr(const std::string& m) : std::runtime_error(m) {}
 };
@@ -314,7 +318,7 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
     const std::string prefix = P->out_prefix ? P->out_prefix : "";
     if (!use_haps) {
         for (uint64_t i = 0; i < n_chroms; i++)
-            add_group(c->genome_name, i, c->genome.p + c->chrom_off[i], c->chrom_off[i + 1] - c->chrom_off[i],
+            add_group(c->genome_name, i, c->genome.p + kPad + c->chrom_off[i], c->chrom_off[i + 1] - c->chrom_off[i],
                       barcodes[0], counts[0][i]);
         jobs.push_back(Job{0, n_pairs, prefix});
     } else {
@@ -551,8 +555,8 @@ int jlp_set_genome(jlp_ctx* c, const char* bases, const uint64_t* chrom_off, uin
         c->genome_name = genome_name ? genome_name : "REF";
         if (chrom_off[0] != 0) throw ArgErr("chrom_off[0] must be 0");
         uint64_t total = chrom_off[n_chroms];
-        c->genome.ensure(total + 64);
-        CK(cudaMemcpyAsync(c->genome.p, bases, total, cudaMemcpyHostToDevice, c->s_compute));
+        c->genome.ensure(total + 2 * kPad);
+        CK(cudaMemcpyAsync(c->genome.p + kPad, bases, total, cudaMemcpyHostToDevice, c->s_compute));
         CK(cudaStreamSynchronize(c->s_compute));
         c->h2d_bytes += total;
     });
@@ -581,7 +585,7 @@ int jlp_add_haplotype(jlp_ctx* c, const char* name, const uint64_t* n_muts, cons
             for (uint64_t ci = 0; ci < nc; ci++) {
                 const uint64_t M = n_muts[ci];
                 const uint64_t ref_size = c->chrom_off[ci + 1] - c->chrom_off[ci];
-                const uint8_t* ref = c->genome.p + c->chrom_off[ci];
+                const uint8_t* ref = c->genome.p + kPad + c->chrom_off[ci];
                 if (M == 0) {   // get_chrom_full returns the reference string (src/hap_classes.cpp:82)
                     if (chrom_sizes[ci] != ref_size) throw ArgErr("chromosome without mutations must keep the reference size");
                     H.seq.push_back(ref); H.len.push_back(ref_size);
@@ -602,12 +606,12 @@ int jlp_add_haplotype(jlp_ctx* c, const char* name, const uint64_t* n_muts, cons
                 d_sm.upload(sm, c->s_compute); d_pool.upload(vp, c->s_compute);
                 c->h2d_bytes += M * 32 + vp.size();
                 uint8_t* out = nullptr;
-                CK(cudaMalloc(reinterpret_cast<void**>(&out), chrom_sizes[ci] + 64));
+                CK(cudaMalloc(reinterpret_cast<void**>(&out), chrom_sizes[ci] + 2 * kPad));
                 H.owned.push_back(out);
                 CK(launch_materialize(ref, ref_size, M, d_old.p, d_new.p, d_sm.p, d_off.p, d_pool.p, chrom_sizes[ci],
-                                      out, c->s_compute));
+                                      out + kPad, c->s_compute));
                 CK(cudaStreamSynchronize(c->s_compute));
-                H.seq.push_back(out); H.len.push_back(chrom_sizes[ci]);
+                H.seq.push_back(out + kPad); H.len.push_back(chrom_sizes[ci]);
             }
         } catch (...) {
             for (uint8_t* p : H.owned) cudaFree(p);

@@ -237,17 +237,30 @@ cudaError_t launch_place(const GenParams& p, cudaStream_t s) {
 
 // ------------------------------------------- quality / errors / FASTQ ---
 
+// Shared memory is addressed through 32-bit shared-window addresses and explicit
+// ld.shared / st.shared, so that no access goes through a generic pointer.
+__device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(a), "r"(x), "r"(y) : "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 lds128s(uint32_t a) { return lds128(a); }
+// tables: written once before the CTA-wide barrier, read-only afterwards (no "memory" clobber,
+// so the loads can be scheduled freely)
+__device__ __forceinline__ uint32_t lds32_ro(uint32_t a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint2 lds64_ro(uint32_t a) { uint2 v; asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+
 // Exact (full 64-bit draws) evaluation of one base; used when the 16 high bits
 // of any draw do not decide it.  fill_read_qual, src/hts_illumina.h:230-256.
-__device__ __noinline__ void base_slow(const GenParams& p, uint32_t e, uint64_t j, uint32_t pos,
-                                       uint32_t code, uint32_t Hdie, uint32_t Hcoin, uint32_t Hmis,
-                                       uint32_t& q_out, bool& mism_out) {
+// Returns quality | mismatch << 8.
+__device__ __noinline__ uint32_t base_slow(const GenParams& p, uint32_t e, uint64_t j, uint32_t pos,
+                                           uint32_t code, uint32_t Hdie, uint32_t Hcoin, uint32_t Hmis) {
     const EndDev& E = p.end[e];
-    if (code > 3) {
-        q_out = nqual_x87(full_draw(Hdie, p.seed, j, e, PU_DIE, pos)) - 33u;
-        mism_out = false;
-        return;
-    }
+    if (code > 3) return nqual_x87(full_draw(Hdie, p.seed, j, e, PU_DIE, pos)) - 33u;
     uint32_t m = E.meta[code * p.L + pos];
     uint32_t n = m & 0xffu, off = m >> 8;
     uint64_t i = mul_floor_x87(full_draw(Hdie, p.seed, j, e, PU_DIE, pos), n);
@@ -255,8 +268,8 @@ __device__ __noinline__ void base_slow(const GenParams& p, uint32_t e, uint64_t 
     uint32_t ent = E.entry[off + i];
     bool self = full_draw(Hcoin, p.seed, j, e, PU_COIN, pos) < E.coin[off + i];
     uint32_t q = self ? ((ent >> 16) & 0xffu) : (ent >> 24);
-    q_out = q;
-    mism_out = full_draw(Hmis, p.seed, j, e, PU_MIS, pos) < E.mis[q];
+    bool mism = full_draw(Hmis, p.seed, j, e, PU_MIS, pos) < E.mis[q];
+    return q | (mism ? 0x100u : 0u);
 }
 
 __device__ __noinline__ uint32_t sub_slow(const GenParams& p, uint32_t e, uint64_t j, uint32_t pos, uint32_t Hsub) {
@@ -264,52 +277,50 @@ __device__ __noinline__ uint32_t sub_slow(const GenParams& p, uint32_t e, uint64
     return si > 2 ? 2u : (uint32_t)si;
 }
 
-// where this lane's end keeps its tables: 32-bit word index of meta and 64-bit
-// word index of entry64 inside the CTA's shared memory (SMEM) or nothing (global)
-struct TabRef {
-    uint32_t meta_w;
-    uint32_t ent_d;
-};
-
 // One base: quality draw, mismatch draw, substitution (fill_read_qual, src/hts_illumina.h:230-256).
+// meta_a / ent_a: shared-window byte addresses of this end's meta[] and entry64[] (SMEM), unused otherwise.
 // Returns ascii | qualchar << 8.
 template <bool SMEM>
-__device__ __forceinline__ uint32_t do_base(const GenParams& p, const uint8_t* smem, TabRef tr, uint32_t e, uint64_t j,
+__device__ __forceinline__ uint32_t do_base(const GenParams& p, uint32_t meta_a, uint32_t ent_a, uint32_t e, uint64_t j,
                                             uint32_t pos, uint32_t code, uint32_t wa, uint32_t wb) {
-    uint32_t Hdie = wa & 0xffffu, Hcoin = wa >> 16, Hmis = wb & 0xffffu, Hsub = wb >> 16;
+    const uint32_t Hdie = wa & 0xffffu, Hcoin = wa >> 16, Hmis = wb & 0xffffu;
     uint32_t q;
     bool mism;
     if (code > 3) {
         // non-TCAG: 'N' with a quality below 10 (src/hts_illumina.h:237-242)
         uint32_t prod = Hdie * 10u;
         q = prod >> 16;
-        mism = false;
-        if ((prod & 0xffffu) + 10u > 0xffffu) base_slow(p, e, j, pos, code, Hdie, Hcoin, Hmis, q, mism);
-        return 0x4Eu | (((q + 33u) & 0xffu) << 8);
+        if ((prod & 0xffffu) + 10u > 0xffffu) q = base_slow(p, e, j, pos, code, Hdie, Hcoin, Hmis) & 0xffu;
+        return 0x4Eu | ((q + 33u) << 8);
     }
     uint32_t m;
-    if (SMEM) m = reinterpret_cast<const uint32_t*>(smem)[tr.meta_w + code * p.L + pos];
+    if (SMEM) m = lds32_ro(meta_a + (code * p.L + pos) * 4u);
     else m = p.end[e].meta[code * p.L + pos];
-    uint32_t n = m & 0xffu, off = m >> 8;
-    uint32_t prod = Hdie * n;
+    const uint32_t n = m & 0xffu, off = m >> 8;
+    const uint32_t prod = Hdie * n;
     uint2 ent;
-    if (SMEM) ent = reinterpret_cast<const uint2*>(smem)[tr.ent_d + off + (prod >> 16)];
+    if (SMEM) ent = lds64_ro(ent_a + (off + (prod >> 16)) * 8u);
     else ent = reinterpret_cast<const uint2*>(p.end[e].entry64)[off + (prod >> 16)];
-    uint32_t thr = ent.x & 0xffffu;
-    bool self = Hcoin < thr;
+    const uint32_t thr = ent.x & 0xffffu;
+    const bool self = Hcoin < thr;
     q = self ? ((ent.x >> 16) & 0xffu) : (ent.x >> 24);
-    uint32_t mt = self ? (ent.y & 0xffffu) : (ent.y >> 16);
+    const uint32_t mt = self ? (ent.y & 0xffffu) : (ent.y >> 16);
     mism = Hmis < mt;
-    bool amb = ((prod & 0xffffu) + n > 0xffffu) | (Hcoin == thr) | (Hmis == mt);
-    if (amb) base_slow(p, e, j, pos, code, Hdie, Hcoin, Hmis, q, mism);
+    const bool amb = ((prod & 0xffffu) + n > 0xffffu) | (Hcoin == thr) | (Hmis == mt);
+    if (amb) {
+        uint32_t r = base_slow(p, e, j, pos, code, Hdie, Hcoin, Hmis);
+        q = r & 0xffu;
+        mism = r >> 8;
+    }
     if (mism) {
         // mm_nucleos[nt][(uint64)(u * 3)] (src/hts.h:46): the si-th code other than `code`
+        const uint32_t Hsub = wb >> 16;
         uint32_t p3 = Hsub * 3u;
         uint32_t si = p3 >> 16;
         if ((p3 & 0xffffu) + 3u > 0xffffu) si = sub_slow(p, e, j, pos, Hsub);
         code = si + (si >= code ? 1u : 0u);
     }
-    return code_ascii(code) | (((q + 33u) & 0xffu) << 8);
+    return code_ascii(code) | ((q + 33u) << 8);
 }
 
 // Base code at template position t of a read end (fill_read / rev_comp / barcode,
@@ -324,6 +335,33 @@ __device__ __forceinline__ uint32_t template_code(const uint8_t* __restrict__ se
     return code;
 }
 
+// Four ASCII bases in one word -> four base codes (T0 C1 A2 G3, anything else 4),
+// complemented on the reverse strand.
+__device__ __forceinline__ uint32_t codes4(uint32_t x, bool reverse) {
+    uint32_t x1 = (x >> 1) & 0x03030303u;                       // A0 C1 T2 G3
+    uint32_t code = x1 ^ 0x02020202u ^ ((x1 << 1) & 0x02020202u);  // T0 C1 A2 G3
+    uint32_t t = code | (code >> 4);
+    uint32_t sel = __byte_perm(t, 0u, 0x4420u);                 // one selector nibble per base
+    uint32_t bad = __byte_perm(0x47414354u, 0u, sel) ^ x;       // non-zero byte: not T/C/A/G
+    if (reverse) code ^= 0x02020202u;
+    if (bad) {
+#pragma unroll
+        for (uint32_t k = 0; k < 4; k++)
+            if ((bad >> (8u * k)) & 0xffu) code = (code & ~(0xffu << (8u * k))) | (4u << (8u * k));
+    }
+    return code;
+}
+
+// 8 consecutive bytes starting at an arbitrary address, from three aligned word loads
+__device__ __forceinline__ void load8(const uint8_t* a, uint32_t& lo, uint32_t& hi) {
+    const uintptr_t u = reinterpret_cast<uintptr_t>(a);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(u & ~(uintptr_t)3);
+    const uint32_t sh = ((uint32_t)u & 3u) * 8u;
+    const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+    lo = __funnelshift_r(w0, w1, sh);
+    hi = __funnelshift_r(w1, w2, sh);
+}
+
 // One warp per read pair.  Phase A (per end): ID line and template base codes into the
 // end's record buffer in shared memory; phase B (both ends together, two bases per lane
 // and Philox block): qualities, mismatches; phase C (per end): the finished FASTQ record is
@@ -334,32 +372,34 @@ template <bool SMEM>
 __global__ void __launch_bounds__(512, 2)
 k_reads(const __grid_constant__ GenParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
     const uint32_t L = p.L;
-    uint32_t tab_bytes = 0;
-    TabRef tabs[2] = {{0, 0}, {0, 0}};
+    // table placement is a function of the launch parameters only
+    const uint32_t ent0 = 0;
+    const uint32_t meta0 = ent0 + p.end[0].entry_n * 8u;
+    const uint32_t ent1 = (meta0 + 16u * L + 15u) & ~15u;
+    const uint32_t meta1 = ent1 + (p.n_ends == 2 ? p.end[1].entry_n * 8u : 0u);
+    const uint32_t tab_bytes = !SMEM ? 0u : p.n_ends == 2 ? ((meta1 + 16u * L + 15u) & ~15u) : ent1;
     if (SMEM) {
         for (uint32_t e = 0; e < p.n_ends; e++) {
             const EndDev& E = p.end[e];
-            tabs[e].ent_d = tab_bytes >> 3;
-            uint64_t* en = reinterpret_cast<uint64_t*>(smem + tab_bytes);
+            uint64_t* en = reinterpret_cast<uint64_t*>(smem + (e ? ent1 : ent0));
             for (uint32_t i = threadIdx.x; i < E.entry_n; i += blockDim.x) en[i] = E.entry64[i];
-            tab_bytes += E.entry_n * 8u;
-            tabs[e].meta_w = tab_bytes >> 2;
-            uint32_t* m = reinterpret_cast<uint32_t*>(smem + tab_bytes);
+            uint32_t* m = reinterpret_cast<uint32_t*>(smem + (e ? meta1 : meta0));
             for (uint32_t i = threadIdx.x; i < 4 * L; i += blockDim.x) m[i] = E.meta[i];
-            tab_bytes += 4u * L * 4u;
-            tab_bytes = (tab_bytes + 15u) & ~15u;
         }
         __syncthreads();
     }
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     const uint32_t n_ends = p.n_ends;
-    const uint32_t R0 = tab_bytes + warp * n_ends * p.rec_buf;     // this warp's record buffers
+    const uint32_t idtail = 3u + (n_ends == 2 ? 2u : 0u);
+    // this warp's shared memory: 32 bytes of scratch, then one record buffer per end
+    const uint32_t W0 = sbase + tab_bytes + warp * (32u + n_ends * p.rec_buf);
+    const uint32_t R0 = W0 + 32u;
 
     for (uint32_t i = blockIdx.x * wpc + warp; i < p.batch_pairs; i += gridDim.x * wpc) {
         const uint64_t j = p.batch_lo + i;
-        uint32_t sq[2] = {0, 0}, len[2] = {0, 0}, al[2] = {0, 0}, rlen[2] = {0, 0};
-        uint64_t off[2] = {0, 0};
+        uint32_t sq0 = 0, sq1 = 0, len0 = 0, len1 = 0;
 
         // ---- phase A: ID line + template codes
 #pragma unroll
@@ -367,7 +407,7 @@ k_reads(const __grid_constant__ GenParams p) {
             if (e >= n_ends) break;
             const uint32_t r = i * n_ends + e;
             const uint4* pp = reinterpret_cast<const uint4*>(p.plan + r);
-            const uint4 pa = pp[0], pb = pp[1], pc = pp[2];
+            const uint4 pa = __ldg(pp), pb = __ldg(pp + 1), pc = __ldg(pp + 2);
             const uint64_t start = ((uint64_t)pa.y << 32) | pa.x;
             const uint32_t S = pa.w;
             const uint32_t ln = pb.x & 0xffffu, flags = (pb.x >> 16) & 0xffu, nd = pb.x >> 24;
@@ -377,29 +417,53 @@ k_reads(const __grid_constant__ GenParams p) {
             const uint32_t prefix_off = Gp->prefix_off, prefix_len = Gp->prefix_len, bc_off = Gp->bc_off, b = Gp->bc_len;
             const uint64_t o = p.block_base[(size_t)e * p.n_scan_blocks + i / kScanBlock] + p.rec_local[r];
             const uint32_t a = (uint32_t)o & 15u;
-            const uint32_t R = R0 + e * p.rec_buf;
-            uint32_t w = R + a;
-            for (uint32_t t = lane; t < prefix_len; t += 32) smem[w + t] = p.strpool[prefix_off + t];
+            if (lane == 0) { sts64(W0 + 16u * e, (uint32_t)o, (uint32_t)(o >> 32)); sts32(W0 + 16u * e + 8u, pb.y); }
+            uint32_t w = R0 + e * p.rec_buf + a;
+            for (uint32_t t = lane; t < prefix_len; t += 32) sts8(w + t, p.strpool[prefix_off + t]);
             w += prefix_len;
             if (lane < nd) {
                 uint32_t word = lane < 4 ? pb.z : lane < 8 ? pb.w : lane < 12 ? pc.x : lane < 16 ? pc.y : lane < 20 ? pc.z : pc.w;
-                smem[w + lane] = (uint8_t)(word >> (8u * (lane & 3u)));
+                sts8(w + lane, (word >> (8u * (lane & 3u))) & 0xffu);
             }
             w += nd;
             if (lane == 0) {
-                uint32_t q = w;
-                smem[q++] = '-';
-                smem[q++] = reverse ? 'R' : 'F';
-                if (n_ends == 2) { smem[q++] = '/'; smem[q++] = (uint8_t)('1' + e); }
-                smem[q] = '\n';
+                sts8(w, '-');
+                sts8(w + 1, reverse ? 'R' : 'F');
+                if (n_ends == 2) { sts8(w + 2, '/'); sts8(w + 3, '1' + e); }
+                sts8(w + idtail - 1u, '\n');
             }
-            w += 3u + (n_ends == 2 ? 2u : 0u);
+            w += idtail;
             const uint8_t* seg = gseq + start;
             const uint8_t* bc = p.strpool + bc_off;
             const uint32_t space = S - b;
             if (!(flags & 2u)) {
-                // no insertion or deletion: position t of the read is position t of the template
-                for (uint32_t t = lane; t < ln; t += 32) smem[w + t] = (uint8_t)template_code(seg, bc, t, b, space, reverse);
+                // no insertion or deletion: position t of the read is position t of the template;
+                // 8 positions per lane from three aligned word loads
+                for (uint32_t tb = 8u * lane; tb < ln; tb += 256u) {
+                    uint32_t c0, c1;
+                    if (tb >= b) {
+                        uint32_t x0, x1;
+                        if (!reverse) load8(seg + (tb - b), x0, x1);
+                        else {
+                            uint32_t y0, y1;
+                            load8(seg + (space - 1u - (tb - b)) - 7, y0, y1);     // may reach below seg: allocations carry front padding
+                            x0 = __byte_perm(y1, 0u, 0x0123u);
+                            x1 = __byte_perm(y0, 0u, 0x0123u);
+                        }
+                        c0 = codes4(x0, reverse);
+                        c1 = codes4(x1, reverse);
+                    } else {
+                        c0 = c1 = 0;
+#pragma unroll
+                        for (uint32_t f = 0; f < 8; f++) {
+                            uint32_t c = tb + f < ln ? template_code(seg, bc, tb + f, b, space, reverse) : 0u;
+                            if (f < 4) c0 |= c << (8u * f); else c1 |= c << (8u * (f - 4u));
+                        }
+                    }
+#pragma unroll
+                    for (uint32_t f = 0; f < 8; f++)
+                        if (tb + f < ln) sts8(w + tb + f, ((f < 4 ? c0 : c1) >> (8u * (f & 3u))) & 0xffu);
+                }
             } else {
                 // indels: every template position gets its class again (same draws as the placement
                 // kernel), a warp prefix sum gives each surviving base its place in the read
@@ -423,18 +487,18 @@ k_reads(const __grid_constant__ GenParams p) {
                     uint32_t o2 = carry + incl - wsum;
                     carry += __shfl_sync(0xffffffffu, incl, 31);
                     if (tb < S) {
-#pragma unroll
+#pragma unroll 1
                         for (uint32_t f = 0; f < 8; f++) {
                             const uint32_t t = tb + f;
                             if (t < S) {
                                 uint32_t c = (cls >> (2u * f)) & 3u;
                                 if (c == 2u && o2 == L - 1u) c = 0;     // src/hts_illumina.cpp:138-139
                                 if (c != 1u && o2 < ln) {
-                                    smem[w + o2++] = (uint8_t)template_code(seg, bc, t, b, space, reverse);
+                                    sts8(w + o2++, template_code(seg, bc, t, b, space, reverse));
                                     if (c == 2u && o2 < ln) {
                                         // bases[(uint64)(u * 4)], src/hts_illumina.h:216; index 4 reads the
                                         // string terminator, which nt_map then turns into 'N'
-                                        smem[w + o2++] = (uint8_t)ins_base_index(slow64(p.seed, j, e, PU_INS, t));
+                                        sts8(w + o2++, ins_base_index(slow64(p.seed, j, e, PU_INS, t)));
                                     }
                                 }
                             }
@@ -443,34 +507,33 @@ k_reads(const __grid_constant__ GenParams p) {
                 }
             }
             if (lane == 0) {
-                smem[w + ln] = '\n'; smem[w + ln + 1] = '+'; smem[w + ln + 2] = '\n';
-                smem[w + 2 * ln + 3] = '\n';
+                sts8(w + ln, '\n'); sts8(w + ln + 1, '+'); sts8(w + ln + 2, '\n');
+                sts8(w + 2 * ln + 3, '\n');
             }
-            sq[e] = w; len[e] = ln; al[e] = a; off[e] = o; rlen[e] = pb.y;
+            if (e == 0) { sq0 = w; len0 = ln; } else { sq1 = w; len1 = ln; }
         }
         __syncwarp();
 
         // ---- phase B: qualities and mismatches, two bases per lane per step, both ends in one index space
         {
-            const uint32_t nb0 = (len[0] + 1u) >> 1, nb1 = (len[1] + 1u) >> 1;
-            for (uint32_t q = lane; q < nb0 + nb1; q += 32) {
+            const uint32_t nb0 = (len0 + 1u) >> 1, nbt = nb0 + ((len1 + 1u) >> 1);
+#pragma unroll 1
+            for (uint32_t q = lane; q < nbt; q += 32) {
                 const uint32_t e = q >= nb0 ? 1u : 0u;
                 const uint32_t blk = q - (e ? nb0 : 0u);
                 const uint32_t pos = 2u * blk;
-                const uint32_t ln = e ? len[1] : len[0];
-                const uint32_t s0 = (e ? sq[1] : sq[0]) + pos;
+                const uint32_t ln = e ? len1 : len0;
+                const uint32_t s0 = (e ? sq1 : sq0) + pos;
                 const uint32_t q0 = s0 + ln + 3u;
-                TabRef tr;
-                tr.meta_w = e ? tabs[1].meta_w : tabs[0].meta_w;
-                tr.ent_d = e ? tabs[1].ent_d : tabs[0].ent_d;
-                U4 w = draw_block(p.seed, j, blk, PL_QUAL, e);
-                uint32_t r0 = do_base<SMEM>(p, smem, tr, e, j, pos, smem[s0], w.w0, w.w1);
-                smem[s0] = (uint8_t)r0;
-                smem[q0] = (uint8_t)(r0 >> 8);
+                const uint32_t meta_a = sbase + (e ? meta1 : meta0), ent_a = sbase + (e ? ent1 : ent0);
+                const U4 w = draw_block(p.seed, j, blk, PL_QUAL, e);
+                const uint32_t r0 = do_base<SMEM>(p, meta_a, ent_a, e, j, pos, lds8(s0), w.w0, w.w1);
+                sts8(s0, r0 & 0xffu);
+                sts8(q0, r0 >> 8);
                 if (pos + 1u < ln) {
-                    uint32_t r1 = do_base<SMEM>(p, smem, tr, e, j, pos + 1u, smem[s0 + 1u], w.w2, w.w3);
-                    smem[s0 + 1u] = (uint8_t)r1;
-                    smem[q0 + 1u] = (uint8_t)(r1 >> 8);
+                    const uint32_t r1 = do_base<SMEM>(p, meta_a, ent_a, e, j, pos + 1u, lds8(s0 + 1u), w.w2, w.w3);
+                    sts8(s0 + 1u, r1 & 0xffu);
+                    sts8(q0 + 1u, r1 >> 8);
                 }
             }
         }
@@ -481,15 +544,17 @@ k_reads(const __grid_constant__ GenParams p) {
         for (uint32_t e = 0; e < 2; e++) {
             if (e >= n_ends) break;
             const uint32_t R = R0 + e * p.rec_buf;
-            const uint32_t a = al[e], total = a + rlen[e];
-            uint8_t* dst = p.out[e] + (off[e] - a);
-            for (uint32_t c = lane; c * 16u < total; c += 32) {
-                const uint32_t lo = c * 16u, hi = lo + 16u;
+            const uint4 sc = lds128(W0 + 16u * e);
+            const uint64_t o = ((uint64_t)sc.y << 32) | sc.x;
+            const uint32_t a = sc.x & 15u, total = a + sc.z;
+            uint8_t* dst = p.out[e] + (o - a);
+            for (uint32_t lo = lane * 16u; lo < total; lo += 512u) {
+                const uint32_t hi = lo + 16u;
                 if (lo >= a && hi <= total) {
-                    *reinterpret_cast<uint4*>(dst + lo) = *reinterpret_cast<const uint4*>(smem + R + lo);
+                    *reinterpret_cast<uint4*>(dst + lo) = lds128(R + lo);
                 } else {
                     const uint32_t k0 = lo > a ? lo : a, k1 = hi < total ? hi : total;
-                    for (uint32_t k = k0; k < k1; k++) dst[k] = smem[R + k];
+                    for (uint32_t k = k0; k < k1; k++) dst[k] = (uint8_t)lds8(R + k);
                 }
             }
         }
@@ -498,9 +563,11 @@ k_reads(const __grid_constant__ GenParams p) {
 }
 
 static size_t reads_table_bytes(const GenParams& p) {
-    size_t b = 0;
-    for (uint32_t e = 0; e < p.n_ends; e++) {
-        b += (size_t)p.end[e].entry_n * 8 + 4 * (size_t)p.L * 4;
+    // same layout as in k_reads: entry64[0], meta[0], (entry64[1], meta[1]), each end 16-byte aligned
+    size_t b = (size_t)p.end[0].entry_n * 8 + 16 * (size_t)p.L;
+    b = (b + 15) & ~(size_t)15;
+    if (p.n_ends == 2) {
+        b += (size_t)p.end[1].entry_n * 8 + 16 * (size_t)p.L;
         b = (b + 15) & ~(size_t)15;
     }
     return b;
@@ -509,7 +576,7 @@ static size_t reads_table_bytes(const GenParams& p) {
 cudaError_t launch_reads(const GenParams& p, int n_sm, cudaStream_t s) {
     if (p.batch_pairs == 0) return cudaSuccess;
     const int threads = 512, wpc = threads / 32;
-    const size_t rec_bytes = (size_t)wpc * p.n_ends * p.rec_buf;
+    const size_t rec_bytes = (size_t)wpc * (32 + (size_t)p.n_ends * p.rec_buf);
     const size_t tab = reads_table_bytes(p);
     const bool use_smem = tab + rec_bytes <= 200 * 1024;
     const size_t smem_bytes = rec_bytes + (use_smem ? tab : 0);
