@@ -336,6 +336,7 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
     GenParams gp;
     std::memset(&gp, 0, sizeof gp);
     gp.seed = P->seed;
+    philox_round_keys(P->seed, gp.rk);
     gp.n_ends = n_ends; gp.L = L; gp.matepair = matepair;
     gp.pool_pairs = (P->read_pool_size + n_ends - 1) / n_ends;   // pool closes at >= read_pool_size reads
     Thr td = thr_double_lt(P->prob_dup);
@@ -375,7 +376,7 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
     uint32_t max_prefix = 0;
     for (const GroupDev& g : groups) max_prefix = std::max(max_prefix, g.prefix_len);
     const uint64_t max_rec = (uint64_t)max_prefix + 20 + 5 + 2ull * L + 4;
-    gp.rec_buf = (uint32_t)((16 + max_rec + 15) & ~15ull);
+    gp.rec_buf = (uint32_t)((max_rec + 64 + 15) & ~15ull);   // + alignment pad, gather overrun, copy-out over-read
     const uint64_t n_rec_max = B * n_ends;
     const uint32_t nsb_max = (uint32_t)((B + kScanBlock - 1) / kScanBlock);
     const bool need_host = sink.kind != SINK_NONE;

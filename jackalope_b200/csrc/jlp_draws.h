@@ -72,6 +72,28 @@ JLP_HD U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint
     return o;
 }
 
+// The same block with the ten round keys precomputed (rk[2r] = k0 + r * 0x9E3779B9,
+// rk[2r+1] = k1 + r * 0xBB67AE85): in a kernel they sit in the constant bank and feed the
+// XORs directly.
+JLP_HD U4 philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const uint32_t* rk) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t h0, l0, h1, l1;
+        mulhilo(0xD2511F53u, c0, h0, l0);
+        mulhilo(0xCD9E8D57u, c2, h1, l1);
+        c0 = h1 ^ c1 ^ rk[2 * r];
+        c2 = h0 ^ c3 ^ rk[2 * r + 1];
+        c1 = l1;
+        c3 = l0;
+    }
+    U4 o = {c0, c1, c2, c3};
+    return o;
+}
+inline void philox_round_keys(uint64_t seed, uint32_t rk[20]) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; r++) { rk[2 * r] = k0; rk[2 * r + 1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+}
+
 JLP_HD U4 draw_block(uint64_t seed, uint64_t j, uint32_t block, uint32_t plane, uint32_t end) {
     return philox4x32_10((uint32_t)j, (uint32_t)(j >> 32), block, plane | (end << 8),
                          (uint32_t)seed, (uint32_t)(seed >> 32));

@@ -210,22 +210,38 @@ k_place(const __grid_constant__ GenParams p) {
     const uint32_t space = S - b;
     const uint64_t start = (p.matepair != 0) == reverse ? frag_start : frag_start + frag_len - space;
 
-    EndPlan pl;
-    pl.start = start; pl.group = g; pl.S = S; pl.len = (uint16_t)len;
-    pl.flags = (uint8_t)((reverse ? 1u : 0u) | (n_ev ? 2u : 0u));
+    // ---- the ID line "@<genome>-<chrom>-<start>-<F|R>[/<1|2>]\n" (fill_fq_lines, src/hts_illumina.cpp:296-312)
+    uint8_t digits[20];
     uint32_t nd = 0;
-    uint8_t tmp[24];
     {
         uint64_t v = start;
-        do { tmp[nd++] = (uint8_t)('0' + (uint32_t)(v % 10)); v /= 10; } while (v);
+        do { digits[nd++] = (uint8_t)('0' + (uint32_t)(v % 10)); v /= 10; } while (v);
     }
+    const uint32_t idlen = G.prefix_len + nd + 3u + (p.n_ends == 2 ? 2u : 0u);
+    uint32_t flags = (reverse ? kPlanReverse : 0u) | (n_ev ? kPlanIndels : 0u) | (b ? kPlanBarcode : 0u);
+    uint4* dst = reinterpret_cast<uint4*>(p.plan + r);
+    if (idlen <= 64u) {
+        __align__(16) uint8_t line[64];
 #pragma unroll
-    for (uint32_t t = 0; t < 24; t++) pl.digits[t] = t < nd ? tmp[nd - 1 - t] : 0;
-    pl.nd = (uint8_t)nd;
-    // '@' name '-' chrom '-' | digits | '-' F/R | ['/' 1/2] | '\n' | read '\n' '+' '\n' qual '\n'
-    pl.rec_len = G.prefix_len + nd + 3u + (p.n_ends == 2 ? 2u : 0u) + 2u * len + 4u;
-    p.plan[r] = pl;
-    p.rec_len[r] = pl.rec_len;
+        for (uint32_t t = 0; t < 16; t++) reinterpret_cast<uint32_t*>(line)[t] = 0;
+        uint32_t w = 0;
+        const uint8_t* pre = p.strpool + G.prefix_off;
+        for (; w < G.prefix_len; w++) line[w] = pre[w];
+        for (uint32_t t = 0; t < nd; t++) line[w++] = digits[nd - 1u - t];
+        line[w++] = '-';
+        line[w++] = reverse ? 'R' : 'F';
+        if (p.n_ends == 2) { line[w++] = '/'; line[w++] = (uint8_t)('1' + e); }
+        line[w++] = '\n';
+#pragma unroll
+        for (uint32_t t = 0; t < 4; t++) dst[2 + t] = reinterpret_cast<const uint4*>(line)[t];
+    } else {
+        flags |= kPlanLongId;
+    }
+    const uint32_t rec_len = idlen + 2u * len + 4u;   // ID line | read '\n' '+' '\n' qual '\n'
+    const uint64_t sega = reinterpret_cast<uint64_t>(G.seq + start);
+    dst[0] = make_uint4((uint32_t)sega, (uint32_t)(sega >> 32), S, len | (flags << 16) | ((idlen & 0xffu) << 24));
+    dst[1] = make_uint4(rec_len, g, (uint32_t)start, (uint32_t)(start >> 32));
+    p.rec_len[r] = rec_len;
 }
 
 cudaError_t launch_place(const GenParams& p, cudaStream_t s) {
@@ -254,73 +270,82 @@ __device__ __forceinline__ uint4 lds128s(uint32_t a) { return lds128(a); }
 __device__ __forceinline__ uint32_t lds32_ro(uint32_t a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint2 lds64_ro(uint32_t a) { uint2 v; asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
 
-// Exact (full 64-bit draws) evaluation of one base; used when the 16 high bits
-// of any draw do not decide it.  fill_read_qual, src/hts_illumina.h:230-256.
-// Returns quality | mismatch << 8.
-__device__ __noinline__ uint32_t base_slow(const GenParams& p, uint32_t e, uint64_t j, uint32_t pos,
-                                           uint32_t code, uint32_t Hdie, uint32_t Hcoin, uint32_t Hmis) {
+__device__ __forceinline__ uint32_t lds16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v) { asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
+
+__device__ __forceinline__ U4 qual_block(const GenParams& p, uint64_t j, uint32_t blk, uint32_t e) {
+    return philox4x32_10_rk((uint32_t)j, (uint32_t)(j >> 32), blk, PL_QUAL | (e << 8), p.rk);
+}
+
+// One base evaluated exactly (full 64-bit draws wherever the 16 high bits do not decide);
+// every rare case of fill_read_qual (src/hts_illumina.h:230-256) lands here: non-TCAG bases,
+// ambiguous high bits, mismatches.  Returns ascii | qualchar << 8.
+__device__ __noinline__ uint32_t base_rare(const GenParams& p, uint32_t e, uint64_t j, uint32_t pos,
+                                           uint32_t code, uint32_t wa, uint32_t wb) {
     const EndDev& E = p.end[e];
-    if (code > 3) return nqual_x87(full_draw(Hdie, p.seed, j, e, PU_DIE, pos)) - 33u;
-    uint32_t m = E.meta[code * p.L + pos];
-    uint32_t n = m & 0xffu, off = m >> 8;
-    uint64_t i = mul_floor_x87(full_draw(Hdie, p.seed, j, e, PU_DIE, pos), n);
-    if (i >= n) i = n - 1;
-    uint32_t ent = E.entry[off + i];
-    bool self = full_draw(Hcoin, p.seed, j, e, PU_COIN, pos) < E.coin[off + i];
-    uint32_t q = self ? ((ent >> 16) & 0xffu) : (ent >> 24);
-    bool mism = full_draw(Hmis, p.seed, j, e, PU_MIS, pos) < E.mis[q];
-    return q | (mism ? 0x100u : 0u);
-}
-
-__device__ __noinline__ uint32_t sub_slow(const GenParams& p, uint32_t e, uint64_t j, uint32_t pos, uint32_t Hsub) {
-    uint64_t si = mul_floor_x87(full_draw(Hsub, p.seed, j, e, PU_SUB, pos), 3);
-    return si > 2 ? 2u : (uint32_t)si;
-}
-
-// One base: quality draw, mismatch draw, substitution (fill_read_qual, src/hts_illumina.h:230-256).
-// meta_a / ent_a: shared-window byte addresses of this end's meta[] and entry64[] (SMEM), unused otherwise.
-// Returns ascii | qualchar << 8.
-template <bool SMEM>
-__device__ __forceinline__ uint32_t do_base(const GenParams& p, uint32_t meta_a, uint32_t ent_a, uint32_t e, uint64_t j,
-                                            uint32_t pos, uint32_t code, uint32_t wa, uint32_t wb) {
-    const uint32_t Hdie = wa & 0xffffu, Hcoin = wa >> 16, Hmis = wb & 0xffffu;
-    uint32_t q;
-    bool mism;
+    const uint32_t Hdie = wa & 0xffffu, Hcoin = wa >> 16, Hmis = wb & 0xffffu, Hsub = wb >> 16;
     if (code > 3) {
-        // non-TCAG: 'N' with a quality below 10 (src/hts_illumina.h:237-242)
+        // 'N' with a quality below 10 (src/hts_illumina.h:237-242)
         uint32_t prod = Hdie * 10u;
-        q = prod >> 16;
-        if ((prod & 0xffffu) + 10u > 0xffffu) q = base_slow(p, e, j, pos, code, Hdie, Hcoin, Hmis) & 0xffu;
-        return 0x4Eu | ((q + 33u) << 8);
+        uint32_t qc = (prod >> 16) + 33u;
+        if ((prod & 0xffffu) + 10u > 0xffffu) qc = nqual_x87(full_draw(Hdie, p.seed, j, e, PU_DIE, pos));
+        return 0x4Eu | ((qc & 0xffu) << 8);
     }
-    uint32_t m;
-    if (SMEM) m = lds32_ro(meta_a + (code * p.L + pos) * 4u);
-    else m = p.end[e].meta[code * p.L + pos];
+    const uint32_t m = E.meta[code * p.L + pos];
     const uint32_t n = m & 0xffu, off = m >> 8;
-    const uint32_t prod = Hdie * n;
-    uint2 ent;
-    if (SMEM) ent = lds64_ro(ent_a + (off + (prod >> 16)) * 8u);
-    else ent = reinterpret_cast<const uint2*>(p.end[e].entry64)[off + (prod >> 16)];
-    const uint32_t thr = ent.x & 0xffffu;
-    const bool self = Hcoin < thr;
-    q = self ? ((ent.x >> 16) & 0xffu) : (ent.x >> 24);
-    const uint32_t mt = self ? (ent.y & 0xffffu) : (ent.y >> 16);
-    mism = Hmis < mt;
-    const bool amb = ((prod & 0xffffu) + n > 0xffffu) | (Hcoin == thr) | (Hmis == mt);
-    if (amb) {
-        uint32_t r = base_slow(p, e, j, pos, code, Hdie, Hcoin, Hmis);
-        q = r & 0xffu;
-        mism = r >> 8;
+    uint32_t prod = Hdie * n;
+    uint32_t i = prod >> 16;
+    if ((prod & 0xffffu) + n > 0xffffu) {
+        uint64_t ii = mul_floor_x87(full_draw(Hdie, p.seed, j, e, PU_DIE, pos), n);
+        i = ii >= n ? n - 1u : (uint32_t)ii;
     }
+    const uint32_t ent = E.entry[off + i];
+    const uint32_t thr = ent & 0xffffu;
+    bool self = Hcoin < thr;
+    if (Hcoin == thr) self = full_draw(Hcoin, p.seed, j, e, PU_COIN, pos) < E.coin[off + i];
+    const uint32_t q = self ? ((ent >> 16) & 0xffu) : (ent >> 24);
+    const uint64_t mfull = E.mis[q];
+    const uint32_t mt = (uint32_t)(mfull >> 48);
+    bool mism = Hmis < mt;
+    if (Hmis == mt) mism = full_draw(Hmis, p.seed, j, e, PU_MIS, pos) < mfull;
     if (mism) {
         // mm_nucleos[nt][(uint64)(u * 3)] (src/hts.h:46): the si-th code other than `code`
-        const uint32_t Hsub = wb >> 16;
         uint32_t p3 = Hsub * 3u;
         uint32_t si = p3 >> 16;
-        if ((p3 & 0xffffu) + 3u > 0xffffu) si = sub_slow(p, e, j, pos, Hsub);
+        if ((p3 & 0xffffu) + 3u > 0xffffu) {
+            uint64_t s3 = mul_floor_x87(full_draw(Hsub, p.seed, j, e, PU_SUB, pos), 3);
+            si = s3 > 2 ? 2u : (uint32_t)s3;
+        }
         code = si + (si >= code ? 1u : 0u);
     }
-    return code_ascii(code) | ((q + 33u) << 8);
+    return (code_ascii(code) & 0xffu) | (((q + 33u) & 0xffu) << 8);
+}
+
+// The common case of one base, decided on the 16 high bits of its three draws: quality by the
+// alias method (IllQualPos::sample, src/hts_illumina.h:128-132; AliasSampler::sample,
+// src/alias_sampler.h:53-60) and the mismatch test (src/hts_illumina.h:251-252).
+// ct: base code clamped to 0..3 (keeps the table walk in bounds for 'N').  Outputs the table
+// entry's low word, which of its two qualities was drawn, and whether base_rare() must
+// decide instead (ambiguous high bits or a mismatch).
+template <bool SMEM>
+__device__ __forceinline__ void base_fast(const GenParams& p, uint32_t meta_a, uint32_t ent_a, uint32_t e, uint32_t pos,
+                                          uint32_t ct, uint32_t wa, uint32_t wb, uint32_t& entx, bool& self, bool& rare) {
+    uint32_t m;
+    if (SMEM) m = lds32_ro(meta_a + (ct * p.L + pos) * 4u);
+    else m = __ldg(p.end[e].meta + ct * p.L + pos);
+    const uint32_t n = m & 0xffu;
+    const uint32_t prod = (wa & 0xffffu) * n;
+    const uint32_t slot = (m >> 8) + (prod >> 16);
+    uint2 ent;
+    if (SMEM) ent = lds64_ro(ent_a + slot * 8u);
+    else ent = __ldg(reinterpret_cast<const uint2*>(p.end[e].entry64) + slot);
+    const uint32_t thr = ent.x & 0xffffu, Hcoin = wa >> 16;
+    self = Hcoin < thr;
+    const uint32_t mt = self ? (ent.y & 0xffffu) : (ent.y >> 16);    // high 16 bits of the quality's mismatch threshold
+    rare = ((((prod + n) ^ prod) & 0x10000u) != 0u) || (Hcoin == thr) || ((wb & 0xffffu) <= mt);
+    entx = ent.x;
 }
 
 // Base code at template position t of a read end (fill_read / rev_comp / barcode,
@@ -335,6 +360,13 @@ __device__ __forceinline__ uint32_t template_code(const uint8_t* __restrict__ se
     return code;
 }
 
+__device__ __noinline__ uint32_t codes4_fix(uint32_t code, uint32_t bad) {
+#pragma unroll
+    for (uint32_t k = 0; k < 4; k++)
+        if ((bad >> (8u * k)) & 0xffu) code = (code & ~(0xffu << (8u * k))) | (4u << (8u * k));
+    return code;
+}
+
 // Four ASCII bases in one word -> four base codes (T0 C1 A2 G3, anything else 4),
 // complemented on the reverse strand.
 __device__ __forceinline__ uint32_t codes4(uint32_t x, bool reverse) {
@@ -344,11 +376,7 @@ __device__ __forceinline__ uint32_t codes4(uint32_t x, bool reverse) {
     uint32_t sel = __byte_perm(t, 0u, 0x4420u);                 // one selector nibble per base
     uint32_t bad = __byte_perm(0x47414354u, 0u, sel) ^ x;       // non-zero byte: not T/C/A/G
     if (reverse) code ^= 0x02020202u;
-    if (bad) {
-#pragma unroll
-        for (uint32_t k = 0; k < 4; k++)
-            if ((bad >> (8u * k)) & 0xffu) code = (code & ~(0xffu << (8u * k))) | (4u << (8u * k));
-    }
+    if (bad) code = codes4_fix(code, bad);
     return code;
 }
 
@@ -362,14 +390,92 @@ __device__ __forceinline__ void load8(const uint8_t* a, uint32_t& lo, uint32_t& 
     hi = __funnelshift_r(w1, w2, sh);
 }
 
-// One warp per read pair.  Phase A (per end): ID line and template base codes into the
-// end's record buffer in shared memory; phase B (both ends together, two bases per lane
-// and Philox block): qualities, mismatches; phase C (per end): the finished FASTQ record is
-// copied to its final place in the output with 128-bit stores.  The record sits in shared
-// memory at the same offset mod 16 as in the output file, so whole 16-byte chunks move as
-// one vector; only a record's first and last partial chunk use byte stores.
+// ID line of a record whose line did not fit the plan (very long genome / chromosome names):
+// lane 0 writes it byte by byte.
+__device__ __noinline__ void long_idline(const GenParams& p, uint32_t dst, const GroupDev* Gp, uint64_t start,
+                                         bool reverse, uint32_t e) {
+    const uint8_t* pre = p.strpool + Gp->prefix_off;
+    const uint32_t n = Gp->prefix_len;
+    for (uint32_t t = 0; t < n; t++) sts8(dst + t, pre[t]);
+    dst += n;
+    uint8_t dg[20];
+    uint32_t nd = 0;
+    do { dg[nd++] = (uint8_t)('0' + (uint32_t)(start % 10)); start /= 10; } while (start);
+    for (uint32_t t = 0; t < nd; t++) sts8(dst + t, dg[nd - 1u - t]);
+    dst += nd;
+    sts8(dst++, '-');
+    sts8(dst++, reverse ? 'R' : 'F');
+    if (p.n_ends == 2) { sts8(dst++, '/'); sts8(dst++, '1' + e); }
+    sts8(dst, '\n');
+}
+
+// Template codes of an end WITH insertions / deletions: every template position gets its
+// class again (same draws as the placement kernel); a warp prefix sum gives each surviving
+// base its place in the read (fill_read_qual applies the same edits from the back,
+// src/hts_illumina.h:213-225).
+__device__ __noinline__ void gather_indels(const GenParams& p, uint32_t e, uint64_t j, uint32_t w, const uint8_t* seg,
+                                           const uint8_t* bc, uint32_t S, uint32_t b, uint32_t ln, bool reverse) {
+    const uint32_t lane = threadIdx.x & 31u, L = p.L, space = S - b;
+    uint32_t carry = 0;
+    for (uint32_t t0 = 0; t0 < S; t0 += 256) {
+        const uint32_t tb = t0 + 8u * lane;
+        uint32_t cls = 0, wsum = 0;
+        if (tb < S) {
+            U4 dw = draw_block(p.seed, j, tb >> 3, PL_INDEL, e);
+#pragma unroll
+            for (uint32_t f = 0; f < 8; f++) {
+                if (tb + f < S) {
+                    uint32_t c = (uint32_t)indel_class(p, e, j, tb + f, field16(dw, f));
+                    cls |= c << (2u * f);
+                    wsum += c == 0 ? 1u : c == 1 ? 0u : 2u;
+                }
+            }
+        }
+        uint32_t incl = warp_incl_scan(wsum);
+        uint32_t o2 = carry + incl - wsum;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+        if (tb < S) {
+#pragma unroll 1
+            for (uint32_t f = 0; f < 8; f++) {
+                const uint32_t t = tb + f;
+                if (t < S) {
+                    uint32_t c = (cls >> (2u * f)) & 3u;
+                    if (c == 2u && o2 == L - 1u) c = 0;     // src/hts_illumina.cpp:138-139
+                    if (c != 1u && o2 < ln) {
+                        sts8(w + o2++, template_code(seg, bc, t, b, space, reverse));
+                        if (c == 2u && o2 < ln) {
+                            // bases[(uint64)(u * 4)], src/hts_illumina.h:216; index 4 reads the
+                            // string terminator, which nt_map then turns into 'N'
+                            sts8(w + o2++, ins_base_index(slow64(p.seed, j, e, PU_INS, t)));
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Template codes of an end with a barcode and no indels (8 positions per lane, byte-wise)
+__device__ __noinline__ void gather_barcode(uint32_t w, const uint8_t* seg, const uint8_t* bc, uint32_t S, uint32_t b,
+                                            uint32_t ln, bool reverse) {
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t t = lane; t < ln; t += 32) sts8(w + t, template_code(seg, bc, t, b, S - b, reverse));
+}
+
+constexpr int kReadsThreads = 384;
+
+// One warp per read pair.
+//   phase A (per end): the ID line (prepared by k_place) and the template's base codes go
+//     into the end's record buffer in shared memory, placed so that the sequence line
+//     starts 8-byte aligned: 8 template positions per lane from three aligned word loads,
+//     one 64-bit shared store;
+//   phase B (both ends in one index space, two bases per lane and Philox block): quality
+//     by the alias method, mismatch test, substitution; rare cases branch to base_rare();
+//   phase C (per end): the finished FASTQ record moves to its final offset in the output
+//     with 128-bit stores; the shift between the record's place in shared memory and its
+//     place in the file is taken out with funnel shifts.
 template <bool SMEM>
-__global__ void __launch_bounds__(512, 2)
+__global__ void __launch_bounds__(kReadsThreads, 2)
 k_reads(const __grid_constant__ GenParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
@@ -392,7 +498,6 @@ k_reads(const __grid_constant__ GenParams p) {
     }
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     const uint32_t n_ends = p.n_ends;
-    const uint32_t idtail = 3u + (n_ends == 2 ? 2u : 0u);
     // this warp's shared memory: 32 bytes of scratch, then one record buffer per end
     const uint32_t W0 = sbase + tab_bytes + warp * (32u + n_ends * p.rec_buf);
     const uint32_t R0 = W0 + 32u;
@@ -401,160 +506,132 @@ k_reads(const __grid_constant__ GenParams p) {
         const uint64_t j = p.batch_lo + i;
         uint32_t sq0 = 0, sq1 = 0, len0 = 0, len1 = 0;
 
-        // ---- phase A: ID line + template codes
+        // ---- phase A
 #pragma unroll
         for (uint32_t e = 0; e < 2; e++) {
             if (e >= n_ends) break;
             const uint32_t r = i * n_ends + e;
             const uint4* pp = reinterpret_cast<const uint4*>(p.plan + r);
-            const uint4 pa = __ldg(pp), pb = __ldg(pp + 1), pc = __ldg(pp + 2);
-            const uint64_t start = ((uint64_t)pa.y << 32) | pa.x;
-            const uint32_t S = pa.w;
-            const uint32_t ln = pb.x & 0xffffu, flags = (pb.x >> 16) & 0xffu, nd = pb.x >> 24;
-            const bool reverse = flags & 1u;
-            const GroupDev* Gp = p.groups + pa.z;
-            const uint8_t* gseq = Gp->seq;
-            const uint32_t prefix_off = Gp->prefix_off, prefix_len = Gp->prefix_len, bc_off = Gp->bc_off, b = Gp->bc_len;
-            const uint64_t o = p.block_base[(size_t)e * p.n_scan_blocks + i / kScanBlock] + p.rec_local[r];
-            const uint32_t a = (uint32_t)o & 15u;
-            if (lane == 0) { sts64(W0 + 16u * e, (uint32_t)o, (uint32_t)(o >> 32)); sts32(W0 + 16u * e + 8u, pb.y); }
-            uint32_t w = R0 + e * p.rec_buf + a;
-            for (uint32_t t = lane; t < prefix_len; t += 32) sts8(w + t, p.strpool[prefix_off + t]);
-            w += prefix_len;
-            if (lane < nd) {
-                uint32_t word = lane < 4 ? pb.z : lane < 8 ? pb.w : lane < 12 ? pc.x : lane < 16 ? pc.y : lane < 20 ? pc.z : pc.w;
-                sts8(w + lane, (word >> (8u * (lane & 3u))) & 0xffu);
-            }
-            w += nd;
-            if (lane == 0) {
-                sts8(w, '-');
-                sts8(w + 1, reverse ? 'R' : 'F');
-                if (n_ends == 2) { sts8(w + 2, '/'); sts8(w + 3, '1' + e); }
-                sts8(w + idtail - 1u, '\n');
-            }
-            w += idtail;
-            const uint8_t* seg = gseq + start;
-            const uint8_t* bc = p.strpool + bc_off;
-            const uint32_t space = S - b;
-            if (!(flags & 2u)) {
-                // no insertion or deletion: position t of the read is position t of the template;
-                // 8 positions per lane from three aligned word loads
+            const uint4 pa = __ldg(pp);
+            const uint32_t S = pa.z, ln = pa.w & 0xffffu, flags = (pa.w >> 16) & 0xffu;
+            uint32_t idlen = pa.w >> 24;
+            const bool reverse = flags & kPlanReverse;
+            const uint8_t* seg = reinterpret_cast<const uint8_t*>(((uint64_t)pa.y << 32) | pa.x);
+            const uint32_t R = R0 + e * p.rec_buf;
+            if (flags & kPlanLongId) idlen = __ldg(&pp[1].x) - 2u * ln - 4u;
+            // the record starts at rs so that the sequence line (rs + idlen) is 8-byte aligned
+            const uint32_t rs = R + ((8u - (idlen & 7u)) & 7u);
+            const uint32_t w = rs + idlen;
+            // template codes first: the last lane's 8-byte store may run past the line's end
+            if (!(flags & (kPlanIndels | kPlanBarcode))) {
                 for (uint32_t tb = 8u * lane; tb < ln; tb += 256u) {
-                    uint32_t c0, c1;
-                    if (tb >= b) {
-                        uint32_t x0, x1;
-                        if (!reverse) load8(seg + (tb - b), x0, x1);
-                        else {
-                            uint32_t y0, y1;
-                            load8(seg + (space - 1u - (tb - b)) - 7, y0, y1);     // may reach below seg: allocations carry front padding
-                            x0 = __byte_perm(y1, 0u, 0x0123u);
-                            x1 = __byte_perm(y0, 0u, 0x0123u);
-                        }
-                        c0 = codes4(x0, reverse);
-                        c1 = codes4(x1, reverse);
-                    } else {
-                        c0 = c1 = 0;
-#pragma unroll
-                        for (uint32_t f = 0; f < 8; f++) {
-                            uint32_t c = tb + f < ln ? template_code(seg, bc, tb + f, b, space, reverse) : 0u;
-                            if (f < 4) c0 |= c << (8u * f); else c1 |= c << (8u * (f - 4u));
-                        }
+                    uint32_t x0, x1;
+                    if (!reverse) load8(seg + tb, x0, x1);
+                    else {
+                        uint32_t y0, y1;
+                        load8(seg + (S - 1u - tb) - 7, y0, y1);       // may reach below seg: allocations carry front padding
+                        x0 = __byte_perm(y1, 0u, 0x0123u);
+                        x1 = __byte_perm(y0, 0u, 0x0123u);
                     }
-#pragma unroll
-                    for (uint32_t f = 0; f < 8; f++)
-                        if (tb + f < ln) sts8(w + tb + f, ((f < 4 ? c0 : c1) >> (8u * (f & 3u))) & 0xffu);
+                    sts64(w + tb, codes4(x0, reverse), codes4(x1, reverse));
                 }
             } else {
-                // indels: every template position gets its class again (same draws as the placement
-                // kernel), a warp prefix sum gives each surviving base its place in the read
-                // (fill_read_qual applies the same edits from the back, src/hts_illumina.h:213-225)
-                uint32_t carry = 0;
-                for (uint32_t t0 = 0; t0 < S; t0 += 256) {
-                    const uint32_t tb = t0 + 8u * lane;
-                    uint32_t cls = 0, wsum = 0;
-                    if (tb < S) {
-                        U4 dw = draw_block(p.seed, j, tb >> 3, PL_INDEL, e);
-#pragma unroll
-                        for (uint32_t f = 0; f < 8; f++) {
-                            if (tb + f < S) {
-                                uint32_t c = (uint32_t)indel_class(p, e, j, tb + f, field16(dw, f));
-                                cls |= c << (2u * f);
-                                wsum += c == 0 ? 1u : c == 1 ? 0u : 2u;
-                            }
-                        }
-                    }
-                    uint32_t incl = warp_incl_scan(wsum);
-                    uint32_t o2 = carry + incl - wsum;
-                    carry += __shfl_sync(0xffffffffu, incl, 31);
-                    if (tb < S) {
-#pragma unroll 1
-                        for (uint32_t f = 0; f < 8; f++) {
-                            const uint32_t t = tb + f;
-                            if (t < S) {
-                                uint32_t c = (cls >> (2u * f)) & 3u;
-                                if (c == 2u && o2 == L - 1u) c = 0;     // src/hts_illumina.cpp:138-139
-                                if (c != 1u && o2 < ln) {
-                                    sts8(w + o2++, template_code(seg, bc, t, b, space, reverse));
-                                    if (c == 2u && o2 < ln) {
-                                        // bases[(uint64)(u * 4)], src/hts_illumina.h:216; index 4 reads the
-                                        // string terminator, which nt_map then turns into 'N'
-                                        sts8(w + o2++, ins_base_index(slow64(p.seed, j, e, PU_INS, t)));
-                                    }
-                                }
-                            }
-                        }
-                    }
-                }
+                const GroupDev* Gp = p.groups + __ldg(&pp[1].y);
+                const uint8_t* bc = p.strpool + Gp->bc_off;
+                if (flags & kPlanIndels) gather_indels(p, e, j, w, seg, bc, S, Gp->bc_len, ln, reverse);
+                else gather_barcode(w, seg, bc, S, Gp->bc_len, ln, reverse);
+            }
+            __syncwarp();
+            // ID line, separators
+            if (!(flags & kPlanLongId)) {
+                for (uint32_t t = lane; t < idlen; t += 32) sts8(rs + t, __ldg(reinterpret_cast<const uint8_t*>(pp + 2) + t));
+            } else if (lane == 0) {
+                const uint4 pb = __ldg(pp + 1);
+                long_idline(p, rs, p.groups + pb.y, ((uint64_t)pb.w << 32) | pb.z, reverse, e);
             }
             if (lane == 0) {
                 sts8(w + ln, '\n'); sts8(w + ln + 1, '+'); sts8(w + ln + 2, '\n');
                 sts8(w + 2 * ln + 3, '\n');
+                sts32(W0 + 4u * e, rs | (idlen << 24));
             }
             if (e == 0) { sq0 = w; len0 = ln; } else { sq1 = w; len1 = ln; }
         }
         __syncwarp();
 
-        // ---- phase B: qualities and mismatches, two bases per lane per step, both ends in one index space
+        // ---- phase B
         {
             const uint32_t nb0 = (len0 + 1u) >> 1, nbt = nb0 + ((len1 + 1u) >> 1);
+            const uint32_t mA0 = sbase + meta0, mA1 = sbase + meta1, eA0 = sbase + ent0, eA1 = sbase + ent1;
 #pragma unroll 1
             for (uint32_t q = lane; q < nbt; q += 32) {
-                const uint32_t e = q >= nb0 ? 1u : 0u;
-                const uint32_t blk = q - (e ? nb0 : 0u);
+                const bool second = q >= nb0;
+                const uint32_t e = second ? 1u : 0u;
+                const uint32_t blk = q - (second ? nb0 : 0u);
                 const uint32_t pos = 2u * blk;
-                const uint32_t ln = e ? len1 : len0;
-                const uint32_t s0 = (e ? sq1 : sq0) + pos;
+                const uint32_t ln = second ? len1 : len0;
+                const uint32_t s0 = (second ? sq1 : sq0) + pos;
                 const uint32_t q0 = s0 + ln + 3u;
-                const uint32_t meta_a = sbase + (e ? meta1 : meta0), ent_a = sbase + (e ? ent1 : ent0);
-                const U4 w = draw_block(p.seed, j, blk, PL_QUAL, e);
-                const uint32_t r0 = do_base<SMEM>(p, meta_a, ent_a, e, j, pos, lds8(s0), w.w0, w.w1);
-                sts8(s0, r0 & 0xffu);
-                sts8(q0, r0 >> 8);
-                if (pos + 1u < ln) {
-                    const uint32_t r1 = do_base<SMEM>(p, meta_a, ent_a, e, j, pos + 1u, lds8(s0 + 1u), w.w2, w.w3);
-                    sts8(s0 + 1u, r1 & 0xffu);
-                    sts8(q0 + 1u, r1 >> 8);
+                const uint32_t meta_a = second ? mA1 : mA0, ent_a = second ? eA1 : eA0;
+                const bool two = pos + 1u < ln;
+                const U4 w = qual_block(p, j, blk, e);
+                const uint32_t cc = lds16(s0);
+                const uint32_t c0 = cc & 0xffu, c1 = two ? cc >> 8 : 0u, pos1 = two ? pos + 1u : pos;
+                const uint32_t ct0 = min(c0, 3u), ct1 = min(c1, 3u);
+                uint32_t x0, x1;
+                bool self0, self1, rare0, rare1;
+                base_fast<SMEM>(p, meta_a, ent_a, e, pos, ct0, w.w0, w.w1, x0, self0, rare0);
+                base_fast<SMEM>(p, meta_a, ent_a, e, pos1, ct1, w.w2, w.w3, x1, self1, rare1);
+                // both quality characters with one byte permute, both letters with another
+                uint32_t qq = __byte_perm(x0, x1, (self0 ? 2u : 3u) | (self1 ? 0x60u : 0x70u));
+                uint32_t asc = __byte_perm(0x47414354u, 0u, ct0 | (ct1 << 4));
+                if (rare0 || rare1 || (c0 | c1) > 3u) {
+                    if (rare0 || c0 > 3u) {
+                        uint32_t r = base_rare(p, e, j, pos, c0, w.w0, w.w1);
+                        asc = (asc & 0xff00u) | (r & 0xffu);
+                        qq = (qq & 0xff00u) | (r >> 8);
+                    }
+                    if (two && (rare1 || c1 > 3u)) {
+                        uint32_t r = base_rare(p, e, j, pos1, c1, w.w2, w.w3);
+                        asc = (asc & 0xffu) | ((r & 0xffu) << 8);
+                        qq = (qq & 0xffu) | (r & 0xff00u);
+                    }
+                }
+                if (two) {
+                    sts16(s0, asc);
+                    sts8(q0, qq);
+                    sts8(q0 + 1u, qq >> 8);
+                } else {
+                    sts8(s0, asc);
+                    sts8(q0, qq);
                 }
             }
         }
         __syncwarp();
 
-        // ---- phase C: records to their final offsets
+        // ---- phase C
 #pragma unroll
         for (uint32_t e = 0; e < 2; e++) {
             if (e >= n_ends) break;
-            const uint32_t R = R0 + e * p.rec_buf;
-            const uint4 sc = lds128(W0 + 16u * e);
-            const uint64_t o = ((uint64_t)sc.y << 32) | sc.x;
-            const uint32_t a = sc.x & 15u, total = a + sc.z;
+            const uint32_t r = i * n_ends + e;
+            const uint64_t o = p.block_base[(size_t)e * p.n_scan_blocks + i / kScanBlock] + p.rec_local[r];
+            const uint32_t rs = lds32(W0 + 4u * e) & 0xffffffu;
+            const uint32_t ln = e ? len1 : len0;
+            const uint32_t idlen = (e ? sq1 : sq0) - rs;
+            const uint32_t a = (uint32_t)o & 15u, total = a + idlen + 2u * ln + 4u;
             uint8_t* dst = p.out[e] + (o - a);
+            const uint32_t src = rs - a;                       // shared address of the byte that lands on dst[0]
+            const uint32_t sh = (src & 3u) * 8u, srcw = src & ~3u;
             for (uint32_t lo = lane * 16u; lo < total; lo += 512u) {
                 const uint32_t hi = lo + 16u;
                 if (lo >= a && hi <= total) {
-                    *reinterpret_cast<uint4*>(dst + lo) = lds128(R + lo);
+                    const uint32_t x0 = lds32(srcw + lo), x1 = lds32(srcw + lo + 4u), x2 = lds32(srcw + lo + 8u),
+                                   x3 = lds32(srcw + lo + 12u), x4 = lds32(srcw + lo + 16u);
+                    *reinterpret_cast<uint4*>(dst + lo) =
+                        make_uint4(__funnelshift_r(x0, x1, sh), __funnelshift_r(x1, x2, sh), __funnelshift_r(x2, x3, sh),
+                                   __funnelshift_r(x3, x4, sh));
                 } else {
                     const uint32_t k0 = lo > a ? lo : a, k1 = hi < total ? hi : total;
-                    for (uint32_t k = k0; k < k1; k++) dst[k] = (uint8_t)lds8(R + k);
+                    for (uint32_t k = k0; k < k1; k++) dst[k] = (uint8_t)lds8(src + k);
                 }
             }
         }
@@ -575,7 +652,7 @@ static size_t reads_table_bytes(const GenParams& p) {
 
 cudaError_t launch_reads(const GenParams& p, int n_sm, cudaStream_t s) {
     if (p.batch_pairs == 0) return cudaSuccess;
-    const int threads = 512, wpc = threads / 32;
+    const int threads = kReadsThreads, wpc = threads / 32;
     const size_t rec_bytes = (size_t)wpc * (32 + (size_t)p.n_ends * p.rec_buf);
     const size_t tab = reads_table_bytes(p);
     const bool use_smem = tab + rec_bytes <= 200 * 1024;

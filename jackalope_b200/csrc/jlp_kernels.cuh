@@ -21,20 +21,22 @@ struct GroupDev {
 // Everything scalar about one read end, written by the placement kernel (one
 // thread per end), read by the read kernel (one warp per pair).
 struct EndPlan {
-    uint64_t start;        // leftmost template coordinate (fill_fq_lines `start`)
-    uint32_t group;
+    const uint8_t* seg;    // first template base in HBM (chromosome + start)
     uint32_t S;            // template positions consumed, barcode included (adjust_chrom_spaces)
     uint16_t len;          // final read length
-    uint8_t flags;         // bit 0: reverse strand, bit 1: the end has insertions/deletions
-    uint8_t nd;            // decimal digits of `start`
+    uint8_t flags;         // bit 0 reverse strand, 1 insertions/deletions, 2 barcode, 3 ID line not inlined
+    uint8_t idlen;         // bytes of the ID line, '\n' included (when inlined)
     uint32_t rec_len;      // FASTQ bytes of the record
-    uint8_t digits[24];    // `start` in decimal, most significant first
+    uint32_t group;
+    uint64_t start;        // leftmost template coordinate (fill_fq_lines `start`)
+    uint8_t idline[64];    // "@<genome>-<chrom>-<start>-<F|R>[/<1|2>]\n"
 };
-static_assert(sizeof(EndPlan) == 48, "EndPlan layout");
+static_assert(sizeof(EndPlan) == 96, "EndPlan layout");
+constexpr uint32_t kPlanReverse = 1, kPlanIndels = 2, kPlanBarcode = 4, kPlanLongId = 8;
 
 struct EndDev {
     const uint32_t* meta;    // [4*L] offset << 8 | n
-    const uint64_t* entry64; // coin16 | q_self << 16 | q_alias << 24 | mis16[q_self] << 32 | mis16[q_alias] << 48
+    const uint64_t* entry64; // coin16 | (q_self + 33) << 16 | (q_alias + 33) << 24 | mis16[q_self] << 32 | mis16[q_alias] << 48
     const uint32_t* entry;   // low half of entry64 (slow path)
     const uint64_t* coin;    // full thresholds (slow path)
     const uint64_t* mis;     // [256] full mismatch thresholds (slow path)
@@ -46,6 +48,7 @@ struct EndDev {
 
 struct GenParams {
     uint64_t seed;
+    uint32_t rk[20];         // Philox round keys of `seed`
     uint64_t job_lo, job_hi;
     uint64_t pool_pairs;
     uint64_t batch_lo;
