@@ -468,11 +468,12 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
             CK(cudaEventRecord(s.ev[1], c->s_compute));
             CK(launch_scan(s.rec_len.p, n_rec, n_ends, s.rec_local.p, s.block_tot.p, s.block_base.p, s.totals.p,
                            c->s_compute));
+            CK(launch_offsets(gp, c->s_compute));
             CK(cudaEventRecord(s.ev[2], c->s_compute));
             CK(launch_reads(gp, c->n_sm, c->s_compute));
             CK(cudaMemcpyAsync(s.h_totals.p, s.totals.p, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->s_compute));
             CK(cudaEventRecord(s.ev[3], c->s_compute));
-            st.kernel_launches += 4;
+            st.kernel_launches += 5;
             s.pairs = np; s.busy = true;
             if (prev && prev->busy) finish(*prev, job);
             prev = &s;

@@ -240,7 +240,7 @@ k_place(const __grid_constant__ GenParams p) {
     const uint32_t rec_len = idlen + 2u * len + 4u;   // ID line | read '\n' '+' '\n' qual '\n'
     const uint64_t sega = reinterpret_cast<uint64_t>(G.seq + start);
     dst[0] = make_uint4((uint32_t)sega, (uint32_t)(sega >> 32), S, len | (flags << 16) | ((idlen & 0xffu) << 24));
-    dst[1] = make_uint4(rec_len, g, (uint32_t)start, (uint32_t)(start >> 32));
+    dst[1] = make_uint4(rec_len, g, 0u, 0u);          // the offset is filled in by k_offsets after the scan
     p.rec_len[r] = rec_len;
 }
 
@@ -248,6 +248,22 @@ cudaError_t launch_place(const GenParams& p, cudaStream_t s) {
     uint32_t n = p.batch_pairs * p.n_ends;
     if (n == 0) return cudaSuccess;
     k_place<<<(n + 255) / 256, 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+// One thread per record: its absolute offset in the batch's output buffer.
+__global__ void __launch_bounds__(256)
+k_offsets(const __grid_constant__ GenParams p) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= p.batch_pairs * p.n_ends) return;
+    const uint32_t e = (p.n_ends == 2) ? (r & 1u) : 0u, i = (p.n_ends == 2) ? (r >> 1) : r;
+    p.plan[r].off = p.block_base[(size_t)e * p.n_scan_blocks + i / kScanBlock] + p.rec_local[r];
+}
+
+cudaError_t launch_offsets(const GenParams& p, cudaStream_t s) {
+    uint32_t n = p.batch_pairs * p.n_ends;
+    if (n == 0) return cudaSuccess;
+    k_offsets<<<(n + 255) / 256, 256, 0, s>>>(p);
     return cudaGetLastError();
 }
 
@@ -282,8 +298,9 @@ __device__ __forceinline__ U4 qual_block(const GenParams& p, uint64_t j, uint32_
 // One base evaluated exactly (full 64-bit draws wherever the 16 high bits do not decide);
 // every rare case of fill_read_qual (src/hts_illumina.h:230-256) lands here: non-TCAG bases,
 // ambiguous high bits, mismatches.  Returns ascii | qualchar << 8.
-__device__ __noinline__ uint32_t base_rare(const GenParams& p, uint32_t e, uint64_t j, uint32_t pos,
-                                           uint32_t code, uint32_t wa, uint32_t wb) {
+template <bool SMEM>
+__device__ __noinline__ uint32_t base_rare(const GenParams& p, uint32_t meta_a, uint32_t ent_a, uint32_t e, uint64_t j,
+                                           uint32_t pos, uint32_t code, uint32_t wa, uint32_t wb) {
     const EndDev& E = p.end[e];
     const uint32_t Hdie = wa & 0xffffu, Hcoin = wa >> 16, Hmis = wb & 0xffffu, Hsub = wb >> 16;
     if (code > 3) {
@@ -293,7 +310,9 @@ __device__ __noinline__ uint32_t base_rare(const GenParams& p, uint32_t e, uint6
         if ((prod & 0xffffu) + 10u > 0xffffu) qc = nqual_x87(full_draw(Hdie, p.seed, j, e, PU_DIE, pos));
         return 0x4Eu | ((qc & 0xffu) << 8);
     }
-    const uint32_t m = E.meta[code * p.L + pos];
+    uint32_t m;
+    if (SMEM) m = lds32_ro(meta_a + (code * p.L + pos) * 4u);
+    else m = __ldg(E.meta + code * p.L + pos);
     const uint32_t n = m & 0xffu, off = m >> 8;
     uint32_t prod = Hdie * n;
     uint32_t i = prod >> 16;
@@ -301,15 +320,16 @@ __device__ __noinline__ uint32_t base_rare(const GenParams& p, uint32_t e, uint6
         uint64_t ii = mul_floor_x87(full_draw(Hdie, p.seed, j, e, PU_DIE, pos), n);
         i = ii >= n ? n - 1u : (uint32_t)ii;
     }
-    const uint32_t ent = E.entry[off + i];
-    const uint32_t thr = ent & 0xffffu;
+    uint2 ent;
+    if (SMEM) ent = lds64_ro(ent_a + (off + i) * 8u);
+    else ent = __ldg(reinterpret_cast<const uint2*>(E.entry64) + off + i);
+    const uint32_t thr = ent.x & 0xffffu;
     bool self = Hcoin < thr;
     if (Hcoin == thr) self = full_draw(Hcoin, p.seed, j, e, PU_COIN, pos) < E.coin[off + i];
-    const uint32_t q = self ? ((ent >> 16) & 0xffu) : (ent >> 24);
-    const uint64_t mfull = E.mis[q];
-    const uint32_t mt = (uint32_t)(mfull >> 48);
+    const uint32_t qc = self ? ((ent.x >> 16) & 0xffu) : (ent.x >> 24);          // quality character
+    const uint32_t mt = self ? (ent.y & 0xffffu) : (ent.y >> 16);
     bool mism = Hmis < mt;
-    if (Hmis == mt) mism = full_draw(Hmis, p.seed, j, e, PU_MIS, pos) < mfull;
+    if (Hmis == mt) mism = full_draw(Hmis, p.seed, j, e, PU_MIS, pos) < E.mis[(qc - 33u) & 0xffu];
     if (mism) {
         // mm_nucleos[nt][(uint64)(u * 3)] (src/hts.h:46): the si-th code other than `code`
         uint32_t p3 = Hsub * 3u;
@@ -320,7 +340,7 @@ __device__ __noinline__ uint32_t base_rare(const GenParams& p, uint32_t e, uint6
         }
         code = si + (si >= code ? 1u : 0u);
     }
-    return (code_ascii(code) & 0xffu) | (((q + 33u) & 0xffu) << 8);
+    return (code_ascii(code) & 0xffu) | (qc << 8);
 }
 
 // The common case of one base, decided on the 16 high bits of its three draws: quality by the
@@ -392,8 +412,9 @@ __device__ __forceinline__ void load8(const uint8_t* a, uint32_t& lo, uint32_t& 
 
 // ID line of a record whose line did not fit the plan (very long genome / chromosome names):
 // lane 0 writes it byte by byte.
-__device__ __noinline__ void long_idline(const GenParams& p, uint32_t dst, const GroupDev* Gp, uint64_t start,
+__device__ __noinline__ void long_idline(const GenParams& p, uint32_t dst, const GroupDev* Gp, const uint8_t* seg,
                                          bool reverse, uint32_t e) {
+    uint64_t start = (uint64_t)(seg - Gp->seq);
     const uint8_t* pre = p.strpool + Gp->prefix_off;
     const uint32_t n = Gp->prefix_len;
     for (uint32_t t = 0; t < n; t++) sts8(dst + t, pre[t]);
@@ -502,17 +523,57 @@ k_reads(const __grid_constant__ GenParams p) {
     const uint32_t W0 = sbase + tab_bytes + warp * (32u + n_ends * p.rec_buf);
     const uint32_t R0 = W0 + 32u;
 
-    for (uint32_t i = blockIdx.x * wpc + warp; i < p.batch_pairs; i += gridDim.x * wpc) {
+    const uint32_t stride = gridDim.x * wpc;
+    for (uint32_t i = blockIdx.x * wpc + warp; i < p.batch_pairs; i += stride) {
         const uint64_t j = p.batch_lo + i;
-        uint32_t sq0 = 0, sq1 = 0, len0 = 0, len1 = 0;
+        // ---- software prefetch, so that the loads of later iterations find their lines on chip:
+        //      the plan records of the pair after next, and -- through the next pair's plan, which
+        //      was prefetched an iteration ago -- the next pair's template bases
+        if (i + 2u * stride < p.batch_pairs) {
+            const uint8_t* pn = reinterpret_cast<const uint8_t*>(p.plan + (size_t)(i + 2u * stride) * n_ends);
+            if (lane < 3u * n_ends) asm volatile("prefetch.global.L1 [%0];" :: "l"(pn + 32u * lane));
+        }
+        if (i + stride < p.batch_pairs) {
+            const uint4 pn = __ldg(reinterpret_cast<const uint4*>(p.plan + (size_t)(i + stride) * n_ends + ((lane >> 3) & (n_ends - 1u))));
+            const uint64_t sa = ((uint64_t)pn.y << 32) | pn.x;
+            const uint64_t pa = (sa & ~(uint64_t)31) + 32u * (lane & 7u);
+            if (lane < 8u * n_ends && pa < sa + pn.z) asm volatile("prefetch.global.L1 [%0];" :: "l"(pa));
+        }
 
-        // ---- phase A
+        // ---- phase A: everything both ends need from global memory is requested before any
+        //      of it is used: plan heads, ID-line bytes, then the template words of both ends
+        const uint4* pp0 = reinterpret_cast<const uint4*>(p.plan + (size_t)i * n_ends);
+        const uint4* pp1 = reinterpret_cast<const uint4*>(p.plan + (size_t)i * n_ends + (n_ends - 1u));
+        const uint4 pa0 = __ldg(pp0), pa1 = __ldg(pp1);
+        const uint2 of0 = __ldg(reinterpret_cast<const uint2*>(pp0 + 1) + 1), of1 = __ldg(reinterpret_cast<const uint2*>(pp1 + 1) + 1);
+        const uint32_t idA0 = __ldg(reinterpret_cast<const uint8_t*>(pp0 + 2) + lane);
+        const uint32_t idA1 = __ldg(reinterpret_cast<const uint8_t*>(pp1 + 2) + lane);
+        uint32_t sq0 = 0, sq1 = 0, len0 = 0, len1 = 0;
+        uint32_t gw[2][3] = {{0, 0, 0}, {0, 0, 0}}, gsh[2] = {0, 0};
+        bool fast[2];
+#pragma unroll
+        for (uint32_t e = 0; e < 2; e++) {
+            fast[e] = false;
+            if (e >= n_ends) break;
+            const uint4 pa = e ? pa1 : pa0;
+            const uint32_t S = pa.z, ln = pa.w & 0xffffu, flags = (pa.w >> 16) & 0xffu;
+            const uint64_t sa = ((uint64_t)pa.y << 32) | pa.x;
+            fast[e] = !(flags & (kPlanIndels | kPlanBarcode));
+            const uint32_t tb = 8u * lane;
+            if (fast[e] && tb < ln) {
+                // 8 template bytes from three aligned words; forward: seg[tb .. tb+8),
+                // reverse: seg[S-1-tb-7 .. S-1-tb] (may reach below seg: allocations carry front padding)
+                const uint64_t u = (flags & kPlanReverse) ? sa + (S - 1u - tb) - 7u : sa + tb;
+                const uint32_t* wp = reinterpret_cast<const uint32_t*>(u & ~(uint64_t)3);
+                gsh[e] = ((uint32_t)u & 3u) * 8u;
+                gw[e][0] = __ldg(wp); gw[e][1] = __ldg(wp + 1); gw[e][2] = __ldg(wp + 2);
+            }
+        }
 #pragma unroll
         for (uint32_t e = 0; e < 2; e++) {
             if (e >= n_ends) break;
-            const uint32_t r = i * n_ends + e;
-            const uint4* pp = reinterpret_cast<const uint4*>(p.plan + r);
-            const uint4 pa = __ldg(pp);
+            const uint4 pa = e ? pa1 : pa0;
+            const uint4* pp = e ? pp1 : pp0;
             const uint32_t S = pa.z, ln = pa.w & 0xffffu, flags = (pa.w >> 16) & 0xffu;
             uint32_t idlen = pa.w >> 24;
             const bool reverse = flags & kPlanReverse;
@@ -523,13 +584,23 @@ k_reads(const __grid_constant__ GenParams p) {
             const uint32_t rs = R + ((8u - (idlen & 7u)) & 7u);
             const uint32_t w = rs + idlen;
             // template codes first: the last lane's 8-byte store may run past the line's end
-            if (!(flags & (kPlanIndels | kPlanBarcode))) {
-                for (uint32_t tb = 8u * lane; tb < ln; tb += 256u) {
+            if (fast[e]) {
+                const uint32_t tb0 = 8u * lane;
+                if (tb0 < ln) {
+                    uint32_t x0 = __funnelshift_r(gw[e][0], gw[e][1], gsh[e]), x1 = __funnelshift_r(gw[e][1], gw[e][2], gsh[e]);
+                    if (reverse) {
+                        const uint32_t t = __byte_perm(x1, 0u, 0x0123u);
+                        x1 = __byte_perm(x0, 0u, 0x0123u);
+                        x0 = t;
+                    }
+                    sts64(w + tb0, codes4(x0, reverse), codes4(x1, reverse));
+                }
+                for (uint32_t tb = tb0 + 256u; tb < ln; tb += 256u) {          // reads longer than 256
                     uint32_t x0, x1;
                     if (!reverse) load8(seg + tb, x0, x1);
                     else {
                         uint32_t y0, y1;
-                        load8(seg + (S - 1u - tb) - 7, y0, y1);       // may reach below seg: allocations carry front padding
+                        load8(seg + (S - 1u - tb) - 7, y0, y1);
                         x0 = __byte_perm(y1, 0u, 0x0123u);
                         x1 = __byte_perm(y0, 0u, 0x0123u);
                     }
@@ -544,15 +615,15 @@ k_reads(const __grid_constant__ GenParams p) {
             __syncwarp();
             // ID line, separators
             if (!(flags & kPlanLongId)) {
-                for (uint32_t t = lane; t < idlen; t += 32) sts8(rs + t, __ldg(reinterpret_cast<const uint8_t*>(pp + 2) + t));
+                if (lane < idlen) sts8(rs + lane, e ? idA1 : idA0);
+                if (lane + 32u < idlen) sts8(rs + 32u + lane, __ldg(reinterpret_cast<const uint8_t*>(pp + 2) + 32u + lane));
             } else if (lane == 0) {
-                const uint4 pb = __ldg(pp + 1);
-                long_idline(p, rs, p.groups + pb.y, ((uint64_t)pb.w << 32) | pb.z, reverse, e);
+                long_idline(p, rs, p.groups + __ldg(&pp[1].y), seg, reverse, e);
             }
             if (lane == 0) {
                 sts8(w + ln, '\n'); sts8(w + ln + 1, '+'); sts8(w + ln + 2, '\n');
                 sts8(w + 2 * ln + 3, '\n');
-                sts32(W0 + 4u * e, rs | (idlen << 24));
+                sts128(W0 + 16u * e, make_uint4(e ? of1.x : of0.x, e ? of1.y : of0.y, rs, 0u));
             }
             if (e == 0) { sq0 = w; len0 = ln; } else { sq1 = w; len1 = ln; }
         }
@@ -586,12 +657,12 @@ k_reads(const __grid_constant__ GenParams p) {
                 uint32_t asc = __byte_perm(0x47414354u, 0u, ct0 | (ct1 << 4));
                 if (rare0 || rare1 || (c0 | c1) > 3u) {
                     if (rare0 || c0 > 3u) {
-                        uint32_t r = base_rare(p, e, j, pos, c0, w.w0, w.w1);
+                        uint32_t r = base_rare<SMEM>(p, meta_a, ent_a, e, j, pos, c0, w.w0, w.w1);
                         asc = (asc & 0xff00u) | (r & 0xffu);
                         qq = (qq & 0xff00u) | (r >> 8);
                     }
                     if (two && (rare1 || c1 > 3u)) {
-                        uint32_t r = base_rare(p, e, j, pos1, c1, w.w2, w.w3);
+                        uint32_t r = base_rare<SMEM>(p, meta_a, ent_a, e, j, pos1, c1, w.w2, w.w3);
                         asc = (asc & 0xffu) | ((r & 0xffu) << 8);
                         qq = (qq & 0xffu) | (r & 0xff00u);
                     }
@@ -612,27 +683,31 @@ k_reads(const __grid_constant__ GenParams p) {
 #pragma unroll
         for (uint32_t e = 0; e < 2; e++) {
             if (e >= n_ends) break;
-            const uint32_t r = i * n_ends + e;
-            const uint64_t o = p.block_base[(size_t)e * p.n_scan_blocks + i / kScanBlock] + p.rec_local[r];
-            const uint32_t rs = lds32(W0 + 4u * e) & 0xffffffu;
+            const uint4 sc = lds128(W0 + 16u * e);
+            const uint64_t o = ((uint64_t)sc.y << 32) | sc.x;
+            const uint32_t rs = sc.z;
             const uint32_t ln = e ? len1 : len0;
             const uint32_t idlen = (e ? sq1 : sq0) - rs;
             const uint32_t a = (uint32_t)o & 15u, total = a + idlen + 2u * ln + 4u;
             uint8_t* dst = p.out[e] + (o - a);
             const uint32_t src = rs - a;                       // shared address of the byte that lands on dst[0]
             const uint32_t sh = (src & 3u) * 8u, srcw = src & ~3u;
-            for (uint32_t lo = lane * 16u; lo < total; lo += 512u) {
-                const uint32_t hi = lo + 16u;
-                if (lo >= a && hi <= total) {
-                    const uint32_t x0 = lds32(srcw + lo), x1 = lds32(srcw + lo + 4u), x2 = lds32(srcw + lo + 8u),
-                                   x3 = lds32(srcw + lo + 12u), x4 = lds32(srcw + lo + 16u);
-                    *reinterpret_cast<uint4*>(dst + lo) =
-                        make_uint4(__funnelshift_r(x0, x1, sh), __funnelshift_r(x1, x2, sh), __funnelshift_r(x2, x3, sh),
-                                   __funnelshift_r(x3, x4, sh));
-                } else {
-                    const uint32_t k0 = lo > a ? lo : a, k1 = hi < total ? hi : total;
-                    for (uint32_t k = k0; k < k1; k++) dst[k] = (uint8_t)lds8(src + k);
-                }
+            // whole 16-byte chunks of the file that lie inside the record
+            const uint32_t first = a ? 16u : 0u, last = total & ~15u;
+            for (uint32_t lo = first + lane * 16u; lo < last; lo += 512u) {
+                const uint32_t x0 = lds32(srcw + lo), x1 = lds32(srcw + lo + 4u), x2 = lds32(srcw + lo + 8u),
+                               x3 = lds32(srcw + lo + 12u), x4 = lds32(srcw + lo + 16u);
+                *reinterpret_cast<uint4*>(dst + lo) =
+                    make_uint4(__funnelshift_r(x0, x1, sh), __funnelshift_r(x1, x2, sh), __funnelshift_r(x2, x3, sh),
+                               __funnelshift_r(x3, x4, sh));
+            }
+            // the record's share of its first and last chunk, one byte per lane
+            if (lane < 16u) {
+                const uint32_t k = a + lane;
+                if (a && k < 16u && k < total) dst[k] = (uint8_t)lds8(src + k);
+            } else {
+                const uint32_t k = last + (lane - 16u);
+                if (k < total && (last >= 16u || !a)) dst[k] = (uint8_t)lds8(src + k);
             }
         }
         __syncwarp();

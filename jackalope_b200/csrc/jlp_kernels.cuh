@@ -28,7 +28,7 @@ struct EndPlan {
     uint8_t idlen;         // bytes of the ID line, '\n' included (when inlined)
     uint32_t rec_len;      // FASTQ bytes of the record
     uint32_t group;
-    uint64_t start;        // leftmost template coordinate (fill_fq_lines `start`)
+    uint64_t off;          // byte offset of the record in its output file's batch buffer (k_offsets)
     uint8_t idline[64];    // "@<genome>-<chrom>-<start>-<F|R>[/<1|2>]\n"
 };
 static_assert(sizeof(EndPlan) == 96, "EndPlan layout");
@@ -93,6 +93,9 @@ cudaError_t launch_place(const GenParams& p, cudaStream_t s);
 cudaError_t launch_scan(const uint32_t* rec_len, uint32_t n_records, uint32_t n_ends,
                         uint32_t* rec_local, uint64_t* block_tot, uint64_t* block_base,
                         uint64_t* totals_out, cudaStream_t s);
+
+// absolute record offsets into the plan: block_base + rec_local
+cudaError_t launch_offsets(const GenParams& p, cudaStream_t s);
 
 // template gather + quality/error model + FASTQ record assembly, one warp per pair;
 // n_sm sizes the persistent grid
