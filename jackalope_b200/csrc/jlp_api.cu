@@ -376,7 +376,8 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
     uint32_t max_prefix = 0;
     for (const GroupDev& g : groups) max_prefix = std::max(max_prefix, g.prefix_len);
     const uint64_t max_rec = (uint64_t)max_prefix + 20 + 5 + 2ull * L + 4;
-    gp.rec_buf = (uint32_t)((max_rec + 64 + 15) & ~15ull);   // + alignment pad, gather overrun, copy-out over-read
+    gp.rec_buf = (uint32_t)((max_rec + 64 + 15) & ~15ull);
+    gp.tpl_buf = (L + 34u + 15u) & ~15u;        // the template, its slack to 16-byte alignment, the word over-read   // + alignment pad, gather overrun, copy-out over-read
     const uint64_t n_rec_max = B * n_ends;
     const uint32_t nsb_max = (uint32_t)((B + kScanBlock - 1) / kScanBlock);
     const bool need_host = sink.kind != SINK_NONE;

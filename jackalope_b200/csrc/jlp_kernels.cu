@@ -291,6 +291,18 @@ __device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile
 __device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts128(uint32_t a, uint4 v) { asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
 
+__device__ __forceinline__ uint2 lds64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// bytes of shared memory one warp of k_reads owns (host and device agree through this)
+__host__ __device__ inline uint32_t reads_warp_bytes(uint32_t n_ends, uint32_t rec_buf, uint32_t tpl_buf) {
+    return 32u + 3u * 192u + 4u * tpl_buf + n_ends * rec_buf;
+}
+
 __device__ __forceinline__ U4 qual_block(const GenParams& p, uint64_t j, uint32_t blk, uint32_t e) {
     return philox4x32_10_rk((uint32_t)j, (uint32_t)(j >> 32), blk, PL_QUAL | (e << 8), p.rk);
 }
@@ -519,75 +531,80 @@ k_reads(const __grid_constant__ GenParams p) {
     }
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     const uint32_t n_ends = p.n_ends;
-    // this warp's shared memory: 32 bytes of scratch, then one record buffer per end
-    const uint32_t W0 = sbase + tab_bytes + warp * (32u + n_ends * p.rec_buf);
-    const uint32_t R0 = W0 + 32u;
-
+    // this warp's shared memory: 32 bytes of scratch, a ring of three plan slots (both ends'
+    // EndPlan records of one pair), a ring of two template slots (the bytes around each end's
+    // template, copied as 16-byte chunks), then one record buffer per end
+    const uint32_t tplw = p.tpl_buf;
+    const uint32_t W0 = sbase + tab_bytes + warp * reads_warp_bytes(n_ends, p.rec_buf, tplw);
+    const uint32_t PL0 = W0 + 32u, TP0 = PL0 + 3u * 192u, R0 = TP0 + 4u * tplw;
     const uint32_t stride = gridDim.x * wpc;
-    for (uint32_t i = blockIdx.x * wpc + warp; i < p.batch_pairs; i += stride) {
-        const uint64_t j = p.batch_lo + i;
-        // ---- software prefetch, so that the loads of later iterations find their lines on chip:
-        //      the plan records of the pair after next, and -- through the next pair's plan, which
-        //      was prefetched an iteration ago -- the next pair's template bases
-        if (i + 2u * stride < p.batch_pairs) {
-            const uint8_t* pn = reinterpret_cast<const uint8_t*>(p.plan + (size_t)(i + 2u * stride) * n_ends);
-            if (lane < 3u * n_ends) asm volatile("prefetch.global.L1 [%0];" :: "l"(pn + 32u * lane));
-        }
-        if (i + stride < p.batch_pairs) {
-            const uint4 pn = __ldg(reinterpret_cast<const uint4*>(p.plan + (size_t)(i + stride) * n_ends + ((lane >> 3) & (n_ends - 1u))));
-            const uint64_t sa = ((uint64_t)pn.y << 32) | pn.x;
-            const uint64_t pa = (sa & ~(uint64_t)31) + 32u * (lane & 7u);
-            if (lane < 8u * n_ends && pa < sa + pn.z) asm volatile("prefetch.global.L1 [%0];" :: "l"(pa));
-        }
+    const uint32_t i0 = blockIdx.x * wpc + warp;
 
-        // ---- phase A: everything both ends need from global memory is requested before any
-        //      of it is used: plan heads, ID-line bytes, then the template words of both ends
-        const uint4* pp0 = reinterpret_cast<const uint4*>(p.plan + (size_t)i * n_ends);
-        const uint4* pp1 = reinterpret_cast<const uint4*>(p.plan + (size_t)i * n_ends + (n_ends - 1u));
-        const uint4 pa0 = __ldg(pp0), pa1 = __ldg(pp1);
-        const uint2 of0 = __ldg(reinterpret_cast<const uint2*>(pp0 + 1) + 1), of1 = __ldg(reinterpret_cast<const uint2*>(pp1 + 1) + 1);
-        const uint32_t idA0 = __ldg(reinterpret_cast<const uint8_t*>(pp0 + 2) + lane);
-        const uint32_t idA1 = __ldg(reinterpret_cast<const uint8_t*>(pp1 + 2) + lane);
-        uint32_t sq0 = 0, sq1 = 0, len0 = 0, len1 = 0;
-        uint32_t gw[2][3] = {{0, 0, 0}, {0, 0, 0}}, gsh[2] = {0, 0};
-        bool fast[2];
-#pragma unroll
-        for (uint32_t e = 0; e < 2; e++) {
-            fast[e] = false;
-            if (e >= n_ends) break;
-            const uint4 pa = e ? pa1 : pa0;
-            const uint32_t S = pa.z, ln = pa.w & 0xffffu, flags = (pa.w >> 16) & 0xffu;
+    // Asynchronous staging (cp.async, 16 bytes per lane): the plan of pair k+2 and the template
+    // bytes of pair k+1 are on their way while pair k is processed, so no load of the main loop
+    // waits on HBM.
+    auto stage_plan = [&](uint32_t slot, uint32_t pair) {
+        if (lane < 6u * n_ends)
+            cp_async16(PL0 + slot * 192u + 16u * lane, reinterpret_cast<const uint8_t*>(p.plan + (size_t)pair * n_ends) + 16u * lane);
+    };
+    auto stage_tpl = [&](uint32_t tslot, uint32_t pslot) {
+        const uint32_t e = lane >> 4;
+        if (e < n_ends) {
+            const uint4 pa = lds128(PL0 + pslot * 192u + e * 96u);
             const uint64_t sa = ((uint64_t)pa.y << 32) | pa.x;
-            fast[e] = !(flags & (kPlanIndels | kPlanBarcode));
-            const uint32_t tb = 8u * lane;
-            if (fast[e] && tb < ln) {
-                // 8 template bytes from three aligned words; forward: seg[tb .. tb+8),
-                // reverse: seg[S-1-tb-7 .. S-1-tb] (may reach below seg: allocations carry front padding)
-                const uint64_t u = (flags & kPlanReverse) ? sa + (S - 1u - tb) - 7u : sa + tb;
-                const uint32_t* wp = reinterpret_cast<const uint32_t*>(u & ~(uint64_t)3);
-                gsh[e] = ((uint32_t)u & 3u) * 8u;
-                gw[e][0] = __ldg(wp); gw[e][1] = __ldg(wp + 1); gw[e][2] = __ldg(wp + 2);
-            }
+            const uint64_t ws = (sa - 8u) & ~(uint64_t)15;
+            const uint64_t need = sa + pa.z + 12u;                 // last byte the fast gather can touch, plus one
+            for (uint32_t l = lane & 15u; 16u * l < tplw; l += 16u)
+                if (ws + 16u * l < need) cp_async16(TP0 + (tslot * 2u + e) * tplw + 16u * l, reinterpret_cast<const uint8_t*>(ws + 16u * l));
         }
+    };
+    if (i0 < p.batch_pairs) {
+        stage_plan(0, i0);
+        if (i0 + stride < p.batch_pairs) stage_plan(1, i0 + stride);
+        cp_async_commit();
+        cp_async_wait_all();
+        __syncwarp();
+        stage_tpl(0, 0);
+        cp_async_commit();
+    }
+
+    uint32_t k = 0;
+    for (uint32_t i = i0; i < p.batch_pairs; i += stride, k++) {
+        const uint64_t j = p.batch_lo + i;
+        cp_async_wait_all();
+        __syncwarp();
+        if (i + 2u * stride < p.batch_pairs) stage_plan((k + 2u) % 3u, i + 2u * stride);
+        if (i + stride < p.batch_pairs) stage_tpl((k + 1u) & 1u, (k + 1u) % 3u);
+        cp_async_commit();
+        const uint32_t PL = PL0 + (k % 3u) * 192u, TP = TP0 + (k & 1u) * 2u * tplw;
+
+        // ---- phase A: ID line and template base codes into the record buffers, all from shared memory
+        uint32_t sq0 = 0, sq1 = 0, len0 = 0, len1 = 0;
 #pragma unroll
         for (uint32_t e = 0; e < 2; e++) {
             if (e >= n_ends) break;
-            const uint4 pa = e ? pa1 : pa0;
-            const uint4* pp = e ? pp1 : pp0;
+            const uint4 pa = lds128(PL + e * 96u);
             const uint32_t S = pa.z, ln = pa.w & 0xffffu, flags = (pa.w >> 16) & 0xffu;
             uint32_t idlen = pa.w >> 24;
             const bool reverse = flags & kPlanReverse;
-            const uint8_t* seg = reinterpret_cast<const uint8_t*>(((uint64_t)pa.y << 32) | pa.x);
+            const uint64_t sa = ((uint64_t)pa.y << 32) | pa.x;
+            const uint8_t* seg = reinterpret_cast<const uint8_t*>(sa);
             const uint32_t R = R0 + e * p.rec_buf;
-            if (flags & kPlanLongId) idlen = __ldg(&pp[1].x) - 2u * ln - 4u;
+            if (flags & kPlanLongId) idlen = lds32(PL + e * 96u + 16u) - 2u * ln - 4u;
             // the record starts at rs so that the sequence line (rs + idlen) is 8-byte aligned
             const uint32_t rs = R + ((8u - (idlen & 7u)) & 7u);
             const uint32_t w = rs + idlen;
             // template codes first: the last lane's 8-byte store may run past the line's end
-            if (fast[e]) {
+            if (!(flags & (kPlanIndels | kPlanBarcode))) {
+                const uint32_t d0 = (uint32_t)(sa - ((sa - 8u) & ~(uint64_t)15));      // seg's place in the staged window
                 const uint32_t tb0 = 8u * lane;
                 if (tb0 < ln) {
-                    uint32_t x0 = __funnelshift_r(gw[e][0], gw[e][1], gsh[e]), x1 = __funnelshift_r(gw[e][1], gw[e][2], gsh[e]);
+                    // 8 template bytes from three aligned words; forward: seg[tb .. tb+8),
+                    // reverse: seg[S-1-tb-7 .. S-1-tb] read backwards and complemented
+                    const uint32_t bo = reverse ? d0 + S - 8u - tb0 : d0 + tb0;
+                    const uint32_t wa = TP + e * tplw + (bo & ~3u), sh = (bo & 3u) * 8u;
+                    const uint32_t g0 = lds32(wa), g1 = lds32(wa + 4u), g2 = lds32(wa + 8u);
+                    uint32_t x0 = __funnelshift_r(g0, g1, sh), x1 = __funnelshift_r(g1, g2, sh);
                     if (reverse) {
                         const uint32_t t = __byte_perm(x1, 0u, 0x0123u);
                         x1 = __byte_perm(x0, 0u, 0x0123u);
@@ -595,7 +612,7 @@ k_reads(const __grid_constant__ GenParams p) {
                     }
                     sts64(w + tb0, codes4(x0, reverse), codes4(x1, reverse));
                 }
-                for (uint32_t tb = tb0 + 256u; tb < ln; tb += 256u) {          // reads longer than 256
+                for (uint32_t tb = tb0 + 256u; tb < ln; tb += 256u) {          // reads longer than 256: straight from HBM
                     uint32_t x0, x1;
                     if (!reverse) load8(seg + tb, x0, x1);
                     else {
@@ -607,7 +624,7 @@ k_reads(const __grid_constant__ GenParams p) {
                     sts64(w + tb, codes4(x0, reverse), codes4(x1, reverse));
                 }
             } else {
-                const GroupDev* Gp = p.groups + __ldg(&pp[1].y);
+                const GroupDev* Gp = p.groups + lds32(PL + e * 96u + 20u);
                 const uint8_t* bc = p.strpool + Gp->bc_off;
                 if (flags & kPlanIndels) gather_indels(p, e, j, w, seg, bc, S, Gp->bc_len, ln, reverse);
                 else gather_barcode(w, seg, bc, S, Gp->bc_len, ln, reverse);
@@ -615,15 +632,14 @@ k_reads(const __grid_constant__ GenParams p) {
             __syncwarp();
             // ID line, separators
             if (!(flags & kPlanLongId)) {
-                if (lane < idlen) sts8(rs + lane, e ? idA1 : idA0);
-                if (lane + 32u < idlen) sts8(rs + 32u + lane, __ldg(reinterpret_cast<const uint8_t*>(pp + 2) + 32u + lane));
+                for (uint32_t t = lane; t < idlen; t += 32u) sts8(rs + t, lds8(PL + e * 96u + 32u + t));
             } else if (lane == 0) {
-                long_idline(p, rs, p.groups + __ldg(&pp[1].y), seg, reverse, e);
+                long_idline(p, rs, p.groups + lds32(PL + e * 96u + 20u), seg, reverse, e);
             }
             if (lane == 0) {
                 sts8(w + ln, '\n'); sts8(w + ln + 1, '+'); sts8(w + ln + 2, '\n');
                 sts8(w + 2 * ln + 3, '\n');
-                sts128(W0 + 16u * e, make_uint4(e ? of1.x : of0.x, e ? of1.y : of0.y, rs, 0u));
+                sts32(W0 + 4u * e, rs);
             }
             if (e == 0) { sq0 = w; len0 = ln; } else { sq1 = w; len1 = ln; }
         }
@@ -683,9 +699,9 @@ k_reads(const __grid_constant__ GenParams p) {
 #pragma unroll
         for (uint32_t e = 0; e < 2; e++) {
             if (e >= n_ends) break;
-            const uint4 sc = lds128(W0 + 16u * e);
-            const uint64_t o = ((uint64_t)sc.y << 32) | sc.x;
-            const uint32_t rs = sc.z;
+            const uint2 ov = lds64(PL + e * 96u + 24u);
+            const uint64_t o = ((uint64_t)ov.y << 32) | ov.x;
+            const uint32_t rs = lds32(W0 + 4u * e);
             const uint32_t ln = e ? len1 : len0;
             const uint32_t idlen = (e ? sq1 : sq0) - rs;
             const uint32_t a = (uint32_t)o & 15u, total = a + idlen + 2u * ln + 4u;
@@ -728,7 +744,7 @@ static size_t reads_table_bytes(const GenParams& p) {
 cudaError_t launch_reads(const GenParams& p, int n_sm, cudaStream_t s) {
     if (p.batch_pairs == 0) return cudaSuccess;
     const int threads = kReadsThreads, wpc = threads / 32;
-    const size_t rec_bytes = (size_t)wpc * (32 + (size_t)p.n_ends * p.rec_buf);
+    const size_t rec_bytes = (size_t)wpc * reads_warp_bytes(p.n_ends, p.rec_buf, p.tpl_buf);
     const size_t tab = reads_table_bytes(p);
     const bool use_smem = tab + rec_bytes <= 200 * 1024;
     const size_t smem_bytes = rec_bytes + (use_smem ? tab : 0);

@@ -58,6 +58,7 @@ struct GenParams {
     uint32_t matepair;
     uint32_t dup_never;      // prob_dup threshold is 0
     uint32_t rec_buf;        // bytes of shared memory per (warp, end) record buffer
+    uint32_t tpl_buf;        // bytes of shared memory per staged template window (multiple of 16)
     uint64_t c_dup;          // x < c_dup: duplicate of the previous fragment
     uint64_t c_rev;          // x < c_rev: reverse strand first
     EndDev end[2];
