@@ -27,6 +27,7 @@ def build(force=False, verbose=False):
            "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "-shared", "-o", LIB]
     if verbose:
         cmd += ["-Xptxas", "-v"]
+    cmd += os.environ.get("JLP_NVCC_EXTRA", "").split()
     cmd += [os.path.join(CSRC, f) for f in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

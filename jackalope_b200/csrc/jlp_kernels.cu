@@ -495,7 +495,11 @@ __device__ __noinline__ void gather_barcode(uint32_t w, const uint8_t* seg, cons
     for (uint32_t t = lane; t < ln; t += 32) sts8(w + t, template_code(seg, bc, t, b, S - b, reverse));
 }
 
-constexpr int kReadsThreads = 384;
+#ifndef JLP_READS_THREADS
+#define JLP_READS_THREADS 896   // 28 warps, one CTA per SM sharing one copy of the tables: measured best
+#define JLP_READS_CTAS 1
+#endif
+constexpr int kReadsThreads = JLP_READS_THREADS;
 
 // One warp per read pair.
 //   phase A (per end): the ID line (prepared by k_place) and the template's base codes go
@@ -508,7 +512,7 @@ constexpr int kReadsThreads = 384;
 //     with 128-bit stores; the shift between the record's place in shared memory and its
 //     place in the file is taken out with funnel shifts.
 template <bool SMEM>
-__global__ void __launch_bounds__(kReadsThreads, 2)
+__global__ void __launch_bounds__(kReadsThreads, JLP_READS_CTAS)
 k_reads(const __grid_constant__ GenParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
