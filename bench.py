@@ -80,50 +80,76 @@ def make_genome_into(buf, lens, seed):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region, polled through NVML every ~2 ms
+    (nvidia-smi -lms cannot sample a region of a few tens of milliseconds); falls back to one
+    nvidia-smi query if NVML is unavailable."""
 
     def __init__(self, index):
-        self.index, self.proc, self.path = index, None, None
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        self._h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            uuid = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+            except Exception:
+                pass
+            if uuid:
+                try:
+                    self._h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode() if not uuid.startswith("GPU-") else uuid.encode())
+                except Exception:
+                    self._h = None
+            if self._h is None:
+                self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nv = None
+
+    def _poll(self):
+        nv = self._nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            fd, self.path = tempfile.mkstemp(suffix=".csv")
-            os.close(fd)
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
+        if self._nv is None:
+            return
+        self._stop.clear()
+        self._thr = threading.Thread(target=self._poll, daemon=True)
+        self._thr.start()
 
     def stop(self):
-        if not self.proc:
-            return None
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in open(self.path):
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 7:
-                continue
+        if self._nv is None:
             try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        os.unlink(self.path)
-        if not sm:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm",
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=20).stdout
+                f = [float(x) for x in o.strip().split(",")]
+                return {"sm_mhz": f[0], "sm_max_mhz": f[1], "samples": 1, "reasons": [], "how": "nvidia-smi after the region"}
+            except Exception:
+                return None
+        self._stop.set()
+        if self._thr:
+            self._thr.join(timeout=2)
+        if not self.samples:
             return None
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "samples": len(sm),
-                "reasons": sorted(reasons)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "samples": len(self.samples),
+                "reasons": sorted(self.reasons), "how": "NVML polled every 2 ms during the timed region"}
 
 
 def dist_env():
@@ -311,9 +337,34 @@ def main():
                "note": "wall clock around jlp_set_genome (pinned H2D, once per call) + jlp_illumina_stream; "
                        "FASTQ lands in the library's double-buffered pinned host buffers"}
 
+    # ---- the same through FILES (the reference-facing default sink): tmpfs, all host threads writing
+    e2e_files = None
+    if not a.no_e2e and rank == 0 and world == 1 and os.path.isdir("/dev/shm"):
+        import shutil
+        need = int(sum(st["bytes_out"]) * 1.1)
+        if shutil.disk_usage("/dev/shm").free > 2 * need:
+            d = tempfile.mkdtemp(dir="/dev/shm")
+            try:
+                nthr = min(host_threads(), 32)
+                J.illumina(genome, os.path.join(d, "w"), 2 * B, L, True, seed=a.seed + 300, ctx=ctx, batch_pairs=B,
+                           n_threads=nthr, overwrite=True, **kw)
+                ctx._genome = None
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                J.illumina(genome, os.path.join(d, "r"), 2 * a.steps * B, L, True, seed=a.seed, ctx=ctx, batch_pairs=B,
+                           n_threads=nthr, overwrite=True, **kw)
+                t_files = time.perf_counter() - t0
+                sz = os.path.getsize(os.path.join(d, "r_R1.fq")) + os.path.getsize(os.path.join(d, "r_R2.fq"))
+                assert sz == sum(st["bytes_out"]), (sz, st["bytes_out"])
+                e2e_files = {"value": a.steps * B / t_files, "unit": UNIT, "ms_per_step": t_files / a.steps * 1e3,
+                             "writer_threads": nthr, "bytes_written": sz,
+                             "note": "illumina(obj, out_prefix, ...) writing <prefix>_R{1,2}.fq on tmpfs; genome H2D inside"}
+            finally:
+                shutil.rmtree(d, ignore_errors=True)
+
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
            "ms_per_step": run_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "u8", "data": "synthetic", "config": config, "clocks": clk, "e2e": e2e,
+           "dtype": "u8", "data": "synthetic", "config": config, "clocks": clk, "e2e": e2e, "e2e_files": e2e_files,
            "gpu_launches": int(st["kernel_launches"])}
 
     if rank == 0:

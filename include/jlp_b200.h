@@ -51,6 +51,15 @@ const char* jlp_last_error(const jlp_ctx* ctx);
 int jlp_set_genome(jlp_ctx* ctx, const char* bases, const uint64_t* chrom_off, uint64_t n_chroms,
                    const char* const* chrom_names, const char* genome_name);
 
+/* The same upload without waiting for it: one H2D copy per chromosome on its own
+ * stream.  A following jlp_illumina_* call on the reference genome starts generating
+ * as soon as the chromosomes its first batch reads are resident and waits for the
+ * whole upload before it returns; `bases` must stay valid until then (or until
+ * jlp_genome_sync).  Haplotype calls wait for the whole genome first. */
+int jlp_set_genome_async(jlp_ctx* ctx, const char* bases, const uint64_t* chrom_off, uint64_t n_chroms,
+                         const char* const* chrom_names, const char* genome_name);
+int jlp_genome_sync(jlp_ctx* ctx);
+
 /* Drop all haplotypes previously added. */
 int jlp_clear_haplotypes(jlp_ctx* ctx);
 
@@ -93,7 +102,7 @@ typedef struct jlp_illumina_params {
     const char* comp_method;     /* "gzip" | "bgzip" (validated, src/hts.h:470) */
     uint64_t n_reads;
     double prob_dup;
-    uint64_t n_threads;          /* advisory: host writer threads */
+    uint64_t n_threads;          /* host writer threads (pwrite of the pinned batch buffers), 1..64 */
     int show_progress;           /* unused by the library; see progress callback */
     uint64_t read_pool_size;     /* duplicate chains stop at pool boundaries, src/hts.h:266-267 */
     const double* haplotype_probs; /* [n_haps], haplotype runs only */

@@ -9,7 +9,12 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cerrno>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
 #include <cstdio>
 #include <cstring>
 #include <memory>
@@ -85,6 +90,71 @@ template <typename T> struct PinBuf {
     ~PinBuf() { if (p) cudaFreeHost(p); }
 };
 
+// Host writer threads: the FASTQ of a batch sits in a pinned buffer; its slices are written
+// with pwrite() at their final file offsets while the GPU generates and copies the next
+// batch (the reference's threads serialise on one omp critical per pool instead,
+// src/hts.h:401-416).
+class WriterPool {
+public:
+    struct Task { int fd; const uint8_t* p; uint64_t n; uint64_t off; std::atomic<int>* pending; };
+    ~WriterPool() { stop(); }
+    void start(size_t n_threads) {
+        if (th.size() == n_threads) return;
+        stop();
+        quit = false;
+        for (size_t i = 0; i < n_threads; i++) th.emplace_back([this]() { loop(); });
+    }
+    void stop() {
+        { std::lock_guard<std::mutex> l(m); quit = true; }
+        cv.notify_all();
+        for (std::thread& t : th) t.join();
+        th.clear();
+    }
+    void submit(const Task& t) {
+        t.pending->fetch_add(1);
+        { std::lock_guard<std::mutex> l(m); q.push_back(t); }
+        cv.notify_one();
+    }
+    // wait until every task counted by `pending` is done; returns the first error text (empty = none)
+    std::string wait(std::atomic<int>& pending) {
+        std::unique_lock<std::mutex> l(m);
+        cv_done.wait(l, [&]() { return pending.load() == 0; });
+        return err;
+    }
+    void clear_error() { std::lock_guard<std::mutex> l(m); err.clear(); }
+private:
+    void loop() {
+        for (;;) {
+            Task t;
+            {
+                std::unique_lock<std::mutex> l(m);
+                cv.wait(l, [&]() { return quit || !q.empty(); });
+                if (q.empty()) return;
+                t = q.front(); q.pop_front();
+            }
+            std::string e;
+            const uint8_t* p = t.p; uint64_t n = t.n, off = t.off;
+            while (n) {
+                ssize_t w = ::pwrite(t.fd, p, n > (1u << 30) ? (1u << 30) : n, (off_t)off);
+                if (w < 0) { if (errno == EINTR) continue; e = std::strerror(errno); break; }
+                p += w; n -= (uint64_t)w; off += (uint64_t)w;
+            }
+            {
+                std::lock_guard<std::mutex> l(m);
+                if (!e.empty() && err.empty()) err = e;
+                t.pending->fetch_sub(1);
+            }
+            cv_done.notify_all();
+        }
+    }
+    std::vector<std::thread> th;
+    std::mutex m;
+    std::condition_variable cv, cv_done;
+    std::deque<Task> q;
+    std::string err;
+    bool quit = false;
+};
+
 struct HapDev {
     std::string name;
     std::vector<const uint8_t*> seq;    // per chromosome; aliases the reference when unmutated
@@ -102,6 +172,7 @@ struct Slot {
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // start, placed, scanned, reads done, copied
     uint32_t pairs = 0;
     bool busy = false;
+    std::atomic<int> writes{0};   // slices of h_out still being written to the files
 };
 
 }  // namespace
@@ -129,6 +200,10 @@ struct jlp_ctx {
     DevBuf<uint8_t> d_strpool;
     DevBuf<uint32_t> d_status;
     Slot slot[2];
+    WriterPool writers;
+    cudaStream_t s_upload = nullptr;            // genome H2D, chromosome by chromosome
+    std::vector<cudaEvent_t> chrom_ev;          // chromosome c is resident once chrom_ev[c] has fired
+    bool upload_pending = false;
     cudaEvent_t ev_run[2] = {nullptr, nullptr};
     uint64_t h2d_bytes = 0;
 };
@@ -173,6 +248,7 @@ struct Sink {
     void* chunk_user = nullptr;
     // files
     int fd[2] = {-1, -1};
+    uint64_t pos[2] = {0, 0};
     std::string names[2];
     void close_files() {
         for (int e = 0; e < 2; e++) if (fd[e] >= 0) { ::close(fd[e]); fd[e] = -1; }
@@ -253,6 +329,7 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
     // --- argument checks the C++ layer of the reference performs
     if (c->chrom_off.size() < 2) throw ArgErr("no reference genome has been set");
     if (use_haps && c->haps.empty()) throw ArgErr("no haplotypes have been added");
+    if (use_haps && c->upload_pending) { CK(cudaStreamSynchronize(c->s_upload)); c->upload_pending = false; }
     if (!c->have_prof[0]) throw ArgErr("no quality profile for read 1");
     if (n_ends == 2) {
         if (!c->have_prof[1]) throw ArgErr("no quality profile for read 2");
@@ -400,6 +477,12 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
     jlp_run_stats st;
     std::memset(&st, 0, sizeof st);
 
+    auto wait_writes = [&](Slot& s) {
+        if (sink.kind != SINK_FILES) return;
+        std::string e = c->writers.wait(s.writes);
+        if (!e.empty()) { c->writers.clear_error(); throw IoErr("Error writing to file " + sink.names[0] + " / " + sink.names[1] + ": " + e); }
+    };
+    if (sink.kind == SINK_FILES) c->writers.start((size_t)std::min<uint64_t>(std::max<uint64_t>(P->n_threads, 1), 64));
     // finish a batch: wait for its totals, copy the FASTQ to the host, hand it to the sink
     uint64_t job_index = 0;
     auto finish = [&](Slot& s, const Job& job) {
@@ -414,6 +497,7 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
         st.pairs += s.pairs;
         st.batches++;
         if (need_host) {
+            wait_writes(s);                     // the pinned buffers of this slot are free again
             for (int e = 0; e < n_ends; e++) {
                 uint64_t n = s.h_totals.p[e];
                 CK(cudaMemcpyAsync(s.h_out[e].p, s.out[e].p, n, cudaMemcpyDeviceToHost, c->s_copy));
@@ -423,8 +507,13 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
             CK(cudaEventSynchronize(s.ev[4]));
             for (int e = 0; e < n_ends; e++) {
                 uint64_t n = s.h_totals.p[e];
-                if (sink.kind == SINK_FILES) write_all(sink.fd[e], s.h_out[e].p, n, sink.names[e]);
-                else if (sink.kind == SINK_STREAM) {
+                if (sink.kind == SINK_FILES) {
+                    // R1 and R2 stay record-aligned: both files receive the same batches in the same order
+                    const uint64_t slice = 8ull << 20;
+                    for (uint64_t o = 0; o < n; o += slice)
+                        c->writers.submit(WriterPool::Task{sink.fd[e], s.h_out[e].p + o, std::min(slice, n - o), sink.pos[e] + o, &s.writes});
+                    sink.pos[e] += n;
+                } else if (sink.kind == SINK_STREAM) {
                     if (sink.chunk_cb(sink.chunk_user, job_index, e, reinterpret_cast<const char*>(s.h_out[e].p), n))
                         throw IoErr("the chunk callback reported an error");
                 } else {
@@ -437,6 +526,7 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
         s.busy = false;
     };
 
+    size_t next_chrom_wait = 0;
     const uint32_t S = P->shard_count > 1 ? P->shard_count : 1;
     const uint32_t si = P->shard_count > 1 ? P->shard_index : 0;
     if (si >= S) throw ArgErr("shard_index >= shard_count");
@@ -444,7 +534,9 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
     for (const Job& job : jobs) {
         if (P->abort_cb && P->abort_cb(P->cb_user)) throw Aborted();   // src/hts.h:536
         if (sink.kind == SINK_FILES) {
+            for (Slot& s : c->slot) wait_writes(s);
             sink.close_files();
+            sink.pos[0] = sink.pos[1] = 0;
             for (int e = 0; e < n_ends; e++) {
                 sink.names[e] = job.file_prefix + "_R" + std::to_string(e + 1) + ".fq";   // src/hts.h:344
                 sink.fd[e] = ::open(sink.names[e].c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
@@ -459,6 +551,14 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
             Slot& s = c->slot[cur];
             if (s.busy) finish(s, job);
             const uint32_t np = (uint32_t)std::min<uint64_t>(B, hi - b0);
+            if (c->upload_pending && !use_haps) {
+                // the batch reads the chromosomes of its pairs (and of earlier ones, through duplicate
+                // leaders): wait for the upload of the last one it can touch
+                size_t g_hi = (size_t)(std::upper_bound(group_off.begin(), group_off.end(), b0 + np - 1) - group_off.begin()) - 1;
+                g_hi = std::min(g_hi, c->chrom_ev.size() - 1);
+                for (; next_chrom_wait <= g_hi; next_chrom_wait++)
+                    CK(cudaStreamWaitEvent(c->s_compute, c->chrom_ev[next_chrom_wait], 0));
+            }
             gp.job_lo = job.lo; gp.job_hi = job.hi; gp.batch_lo = b0; gp.batch_pairs = np;
             const uint32_t n_rec = np * n_ends;
             const uint32_t nsb = (np + kScanBlock - 1) / kScanBlock;
@@ -481,10 +581,12 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
             cur ^= 1;
             if (P->abort_cb && P->abort_cb(P->cb_user)) {
                 for (Slot& t : c->slot) if (t.busy) { cudaEventSynchronize(t.ev[3]); t.busy = false; }
+                for (Slot& t : c->slot) c->writers.wait(t.writes);
                 throw Aborted();
             }
         }
         for (Slot& s : c->slot) if (s.busy) finish(s, job);
+        for (Slot& s : c->slot) wait_writes(s);
         job_index++;
     }
     CK(cudaEventRecord(c->ev_run[1], c->s_compute));
@@ -495,6 +597,7 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
         st.run_ms = ms;
     }
     sink.close_files();
+    if (c->upload_pending) { CK(cudaStreamSynchronize(c->s_upload)); c->upload_pending = false; }
     uint32_t status = 0;
     CK(cudaMemcpy(&status, c->d_status.p, sizeof status, cudaMemcpyDeviceToHost));
     if (status & 1u) throw ArgErr("a barcode is at least as long as a read's template (fragment or chromosome too short)");
@@ -524,6 +627,7 @@ int jlp_ctx_create(int device, jlp_ctx** out) {
         CK(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device));
         CK(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&c->s_upload, cudaStreamNonBlocking));
     });
     if (rc != JLP_OK) { g_create_error = c->err; return rc; }
     *out = c.release();
@@ -539,29 +643,63 @@ void jlp_ctx_destroy(jlp_ctx* c) {
     for (cudaEvent_t ev : c->ev_run) if (ev) cudaEventDestroy(ev);
     if (c->s_compute) cudaStreamDestroy(c->s_compute);
     if (c->s_copy) cudaStreamDestroy(c->s_copy);
+    if (c->s_upload) cudaStreamDestroy(c->s_upload);
+    for (cudaEvent_t ev : c->chrom_ev) cudaEventDestroy(ev);
+    c->writers.stop();
     delete c;
 }
 
 const char* jlp_last_error(const jlp_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
 
-int jlp_set_genome(jlp_ctx* c, const char* bases, const uint64_t* chrom_off, uint64_t n_chroms,
-                   const char* const* chrom_names, const char* genome_name) {
+static int set_genome_impl(jlp_ctx* c, const char* bases, const uint64_t* chrom_off, uint64_t n_chroms,
+                           const char* const* chrom_names, const char* genome_name, bool wait) {
     if (!c) return JLP_ERR_ARG;
     return guarded(c, [&]() {
         if (!bases || !chrom_off || !chrom_names || n_chroms == 0) throw ArgErr("empty genome");
         for (uint64_t i = 0; i < n_chroms; i++)
             if (chrom_off[i + 1] < chrom_off[i]) throw ArgErr("chrom_off must be non-decreasing");
+        if (chrom_off[0] != 0) throw ArgErr("chrom_off[0] must be 0");
+        if (c->upload_pending) { CK(cudaStreamSynchronize(c->s_upload)); c->upload_pending = false; }
         free_haps(c);
         c->chrom_off.assign(chrom_off, chrom_off + n_chroms + 1);
         c->chrom_names.clear();
         for (uint64_t i = 0; i < n_chroms; i++) c->chrom_names.push_back(chrom_names[i] ? chrom_names[i] : "");
         c->genome_name = genome_name ? genome_name : "REF";
-        if (chrom_off[0] != 0) throw ArgErr("chrom_off[0] must be 0");
         uint64_t total = chrom_off[n_chroms];
         c->genome.ensure(total + 2 * kPad);
-        CK(cudaMemcpyAsync(c->genome.p + kPad, bases, total, cudaMemcpyHostToDevice, c->s_compute));
-        CK(cudaStreamSynchronize(c->s_compute));
+        while (c->chrom_ev.size() < n_chroms) {
+            cudaEvent_t ev;
+            CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            c->chrom_ev.push_back(ev);
+        }
+        // one copy and one event per chromosome: generation starts as soon as the chromosomes a batch
+        // reads are resident, the rest of the genome follows underneath (PCIe is full duplex, the
+        // FASTQ flows the other way)
+        for (uint64_t i = 0; i < n_chroms; i++) {
+            const uint64_t n = chrom_off[i + 1] - chrom_off[i];
+            if (n) CK(cudaMemcpyAsync(c->genome.p + kPad + chrom_off[i], bases + chrom_off[i], n, cudaMemcpyHostToDevice, c->s_upload));
+            CK(cudaEventRecord(c->chrom_ev[i], c->s_upload));
+        }
+        c->upload_pending = true;
         c->h2d_bytes += total;
+        if (wait) { CK(cudaStreamSynchronize(c->s_upload)); c->upload_pending = false; }
+    });
+}
+
+int jlp_set_genome(jlp_ctx* c, const char* bases, const uint64_t* chrom_off, uint64_t n_chroms,
+                   const char* const* chrom_names, const char* genome_name) {
+    return set_genome_impl(c, bases, chrom_off, n_chroms, chrom_names, genome_name, true);
+}
+
+int jlp_set_genome_async(jlp_ctx* c, const char* bases, const uint64_t* chrom_off, uint64_t n_chroms,
+                         const char* const* chrom_names, const char* genome_name) {
+    return set_genome_impl(c, bases, chrom_off, n_chroms, chrom_names, genome_name, false);
+}
+
+int jlp_genome_sync(jlp_ctx* c) {
+    if (!c) return JLP_ERR_ARG;
+    return guarded(c, [&]() {
+        if (c->upload_pending) { CK(cudaStreamSynchronize(c->s_upload)); c->upload_pending = false; }
     });
 }
 
@@ -578,6 +716,7 @@ int jlp_add_haplotype(jlp_ctx* c, const char* name, const uint64_t* n_muts, cons
     return guarded(c, [&]() {
         if (c->chrom_off.size() < 2) throw ArgErr("set the reference genome first");
         if (!n_muts || !chrom_sizes) throw ArgErr("n_muts / chrom_sizes is NULL");
+        if (c->upload_pending) { CK(cudaStreamSynchronize(c->s_upload)); c->upload_pending = false; }
         const uint64_t nc = c->chrom_off.size() - 1;
         HapDev H;
         H.name = name ? name : "";

@@ -139,13 +139,17 @@ class Context:
                 raise JackalopeError(msg)
             raise RuntimeError("%s failed (%d): %s" % (what, rc, msg))
 
-    def set_genome(self, g: RefGenome):
+    def set_genome(self, g: RefGenome, wait=True):
+        """Upload the reference.  With wait=False the copy runs chromosome by chromosome underneath
+        the next illumina() call on this genome, which waits for it before returning."""
         if self._genome is g:
             return
         bases, off = g.flat()
         names = (C.c_char_p * g.n_chroms())(*[n.encode() for n in g.names])
-        self._check(self.lib.jlp_set_genome(self.h, bases.ctypes.data_as(C.c_void_p), off.ctypes.data_as(u64p),
-                                            g.n_chroms(), names, g.name.encode()), "jlp_set_genome")
+        fn = self.lib.jlp_set_genome if wait else self.lib.jlp_set_genome_async
+        self._upload_keep = (bases, off)      # the library reads `bases` until the upload is done
+        self._check(fn(self.h, bases.ctypes.data_as(C.c_void_p), off.ctypes.data_as(u64p),
+                       g.n_chroms(), names, g.name.encode()), "jlp_set_genome")
         self._genome, self._haps = g, None
 
     def set_haplotypes(self, haps: Haplotypes):
@@ -299,7 +303,7 @@ def illumina(obj, out_prefix, n_reads, read_length, paired, frag_mean=400, frag_
     if is_haps:
         ctx.set_haplotypes(obj)
     else:
-        ctx.set_genome(obj)
+        ctx.set_genome(obj, wait=False)
     ctx.set_profile(0, prof1)
     if prof2 is not None:
         ctx.set_profile(1, prof2)

@@ -135,6 +135,15 @@ def test_pair_geometry_known_answers(ctx, tmp_path):
             assert all(len(r[3]) == 100 for r in recs)
 
 
+def test_writer_threads_and_many_batches(ctx, tmp_path):
+    g = small_genome(seed=31)
+    pre = str(tmp_path / "w")
+    r1, r2, _ = J.illumina(g, "", 6000, 100, True, seed=32, ctx=ctx, sink="memory")
+    for nthr in (1, 4):
+        J.illumina(g, pre, 6000, 100, True, seed=32, ctx=ctx, batch_pairs=500, n_threads=nthr, overwrite=True)
+        assert open(pre + "_R1.fq", "rb").read() == r1 and open(pre + "_R2.fq", "rb").read() == r2
+
+
 def test_stream_sink_hands_out_the_same_bytes(ctx):
     g = small_genome(seed=21)
     r1, r2, _ = J.illumina(g, "", 3000, 100, True, seed=22, ctx=ctx, sink="memory")
