@@ -239,6 +239,11 @@ def main():
     rank, local_rank, world = dist_env()
     if a.impl == "reference" and rank != 0:
         return 0
+    # stdout carries exactly one JSON line: everything else a library prints there (NCCL's version
+    # banner, ...) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     lens, L, kw, full_pairs = workload(a.workload, int(a.genome_bases))
     total = int(lens.sum())
     config = {"workload": a.workload, "genome_bases": total, "n_chroms": len(lens), "read_length": L, "paired": True,
@@ -252,7 +257,7 @@ def main():
     import jackalope_b200 as J
 
     if a.impl == "reference":
-        return reference_arm(a, lens, L, kw, config, J)
+        return reference_arm(a, lens, L, kw, config, J, real_stdout)
 
     import torch
     if not torch.cuda.is_available():
@@ -392,7 +397,7 @@ def main():
             t0 = time.perf_counter()
             out["cpu_baseline"] = cpu_baseline(genome, lens, flat, L, kw, prof1, prof2)
             log("[bench] cpu baseline took %.1f s" % (time.perf_counter() - t0))
-        print(json.dumps(out), flush=True)
+        print(json.dumps(out), file=real_stdout, flush=True)
     ctx.close()
     if world > 1:
         dist.barrier()
@@ -400,7 +405,7 @@ def main():
     return 0
 
 
-def reference_arm(a, lens, L, kw, config, J):
+def reference_arm(a, lens, L, kw, config, J, real_stdout):
     """The reference's own CPU implementation on bounded samples of the workload."""
     total = int(lens.sum())
     flat = np.empty(total, dtype=np.uint8)
@@ -437,7 +442,7 @@ def reference_arm(a, lens, L, kw, config, J):
                       "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
                       "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
                       "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                      "gpu_launches": 0}), flush=True)
+                      "gpu_launches": 0}), file=real_stdout, flush=True)
     return 0
 
 

@@ -582,31 +582,32 @@ k_reads(const __grid_constant__ GenParams p) {
         cp_async_commit();
         const uint32_t PL = PL0 + (k % 3u) * 192u, TP = TP0 + (k & 1u) * 2u * tplw;
 
-        // ---- phase A: ID line and template base codes into the record buffers, all from shared memory
-        uint32_t sq0 = 0, sq1 = 0, len0 = 0, len1 = 0;
-#pragma unroll
-        for (uint32_t e = 0; e < 2; e++) {
-            if (e >= n_ends) break;
-            const uint4 pa = lds128(PL + e * 96u);
+        // ---- phase A: ID line and template base codes into the record buffers, all from shared
+        //      memory.  The two ends are handled side by side, one half-warp each (lane >> 4 is the
+        //      end, lane & 15 the worker), so the per-end bookkeeping is paid once per pair.
+        const uint32_t he = lane >> 4, hl = lane & 15u;
+        const bool mine = he < n_ends;
+        const uint32_t PLe = PL + he * 96u;
+        uint32_t my_w = 0, my_ln = 0, my_flags = 0, my_rs = 0;
+        if (mine) {
+            const uint4 pa = lds128(PLe);
             const uint32_t S = pa.z, ln = pa.w & 0xffffu, flags = (pa.w >> 16) & 0xffu;
             uint32_t idlen = pa.w >> 24;
             const bool reverse = flags & kPlanReverse;
-            const uint64_t sa = ((uint64_t)pa.y << 32) | pa.x;
-            const uint8_t* seg = reinterpret_cast<const uint8_t*>(sa);
-            const uint32_t R = R0 + e * p.rec_buf;
-            if (flags & kPlanLongId) idlen = lds32(PL + e * 96u + 16u) - 2u * ln - 4u;
+            if (flags & kPlanLongId) idlen = lds32(PLe + 16u) - 2u * ln - 4u;
             // the record starts at rs so that the sequence line (rs + idlen) is 8-byte aligned
-            const uint32_t rs = R + ((8u - (idlen & 7u)) & 7u);
+            const uint32_t rs = R0 + he * p.rec_buf + ((8u - (idlen & 7u)) & 7u);
             const uint32_t w = rs + idlen;
-            // template codes first: the last lane's 8-byte store may run past the line's end
+            my_w = w; my_ln = ln; my_flags = flags; my_rs = rs;
             if (!(flags & (kPlanIndels | kPlanBarcode))) {
-                const uint32_t d0 = (uint32_t)(sa - ((sa - 8u) & ~(uint64_t)15));      // seg's place in the staged window
-                const uint32_t tb0 = 8u * lane;
-                if (tb0 < ln) {
-                    // 8 template bytes from three aligned words; forward: seg[tb .. tb+8),
-                    // reverse: seg[S-1-tb-7 .. S-1-tb] read backwards and complemented
-                    const uint32_t bo = reverse ? d0 + S - 8u - tb0 : d0 + tb0;
-                    const uint32_t wa = TP + e * tplw + (bo & ~3u), sh = (bo & 3u) * 8u;
+                // 8 template bytes per step from three aligned words of the staged window; forward:
+                // seg[tb .. tb+8), reverse: seg[S-1-tb-7 .. S-1-tb] read backwards and complemented.
+                // The last store of a line may run up to 7 bytes past its end (separators come later).
+                const uint32_t d0 = (pa.x - ((pa.x - 8u) & ~15u));                     // seg's place in the window
+                const uint32_t TPe = TP + he * tplw;
+                for (uint32_t tb = 8u * hl; tb < ln; tb += 128u) {
+                    const uint32_t bo = reverse ? d0 + S - 8u - tb : d0 + tb;
+                    const uint32_t wa = TPe + (bo & ~3u), sh = (bo & 3u) * 8u;
                     const uint32_t g0 = lds32(wa), g1 = lds32(wa + 4u), g2 = lds32(wa + 8u);
                     uint32_t x0 = __funnelshift_r(g0, g1, sh), x1 = __funnelshift_r(g1, g2, sh);
                     if (reverse) {
@@ -614,39 +615,46 @@ k_reads(const __grid_constant__ GenParams p) {
                         x1 = __byte_perm(x0, 0u, 0x0123u);
                         x0 = t;
                     }
-                    sts64(w + tb0, codes4(x0, reverse), codes4(x1, reverse));
-                }
-                for (uint32_t tb = tb0 + 256u; tb < ln; tb += 256u) {          // reads longer than 256: straight from HBM
-                    uint32_t x0, x1;
-                    if (!reverse) load8(seg + tb, x0, x1);
-                    else {
-                        uint32_t y0, y1;
-                        load8(seg + (S - 1u - tb) - 7, y0, y1);
-                        x0 = __byte_perm(y1, 0u, 0x0123u);
-                        x1 = __byte_perm(y0, 0u, 0x0123u);
-                    }
                     sts64(w + tb, codes4(x0, reverse), codes4(x1, reverse));
                 }
-            } else {
-                const GroupDev* Gp = p.groups + lds32(PL + e * 96u + 20u);
-                const uint8_t* bc = p.strpool + Gp->bc_off;
-                if (flags & kPlanIndels) gather_indels(p, e, j, w, seg, bc, S, Gp->bc_len, ln, reverse);
-                else gather_barcode(w, seg, bc, S, Gp->bc_len, ln, reverse);
             }
-            __syncwarp();
-            // ID line, separators
-            if (!(flags & kPlanLongId)) {
-                for (uint32_t t = lane; t < idlen; t += 32u) sts8(rs + t, lds8(PL + e * 96u + 32u + t));
-            } else if (lane == 0) {
-                long_idline(p, rs, p.groups + lds32(PL + e * 96u + 20u), seg, reverse, e);
-            }
-            if (lane == 0) {
-                sts8(w + ln, '\n'); sts8(w + ln + 1, '+'); sts8(w + ln + 2, '\n');
-                sts8(w + 2 * ln + 3, '\n');
-                sts32(W0 + 4u * e, rs);
-            }
-            if (e == 0) { sq0 = w; len0 = ln; } else { sq1 = w; len1 = ln; }
         }
+        // ends with indels or a barcode take the whole warp, one end after the other
+        {
+            const uint32_t f0 = __shfl_sync(0xffffffffu, my_flags, 0), f1 = __shfl_sync(0xffffffffu, my_flags, 16);
+            if ((f0 | f1) & (kPlanIndels | kPlanBarcode)) {
+#pragma unroll 1
+                for (uint32_t e = 0; e < n_ends; e++) {
+                    const uint32_t fe = e ? f1 : f0;
+                    if (!(fe & (kPlanIndels | kPlanBarcode))) continue;
+                    const uint4 pa = lds128(PL + e * 96u);
+                    const uint8_t* seg = reinterpret_cast<const uint8_t*>(((uint64_t)pa.y << 32) | pa.x);
+                    const uint32_t w = __shfl_sync(0xffffffffu, my_w, 16 * e), ln = pa.w & 0xffffu;
+                    const GroupDev* Gp = p.groups + lds32(PL + e * 96u + 20u);
+                    const uint8_t* bc = p.strpool + Gp->bc_off;
+                    if (fe & kPlanIndels) gather_indels(p, e, j, w, seg, bc, pa.z, Gp->bc_len, ln, fe & kPlanReverse);
+                    else gather_barcode(w, seg, bc, pa.z, Gp->bc_len, ln, fe & kPlanReverse);
+                }
+            }
+        }
+        __syncwarp();
+        // ID line, separators
+        if (mine) {
+            const uint32_t idlen = my_w - my_rs;
+            if (!(my_flags & kPlanLongId)) {
+                for (uint32_t t = hl; t < idlen; t += 16u) sts8(my_rs + t, lds8(PLe + 32u + t));
+            } else if (hl == 0) {
+                const uint2 sp = lds64(PLe);
+                long_idline(p, my_rs, p.groups + lds32(PLe + 20u), reinterpret_cast<const uint8_t*>(((uint64_t)sp.y << 32) | sp.x),
+                            my_flags & kPlanReverse, he);
+            }
+            if (hl == 0) {
+                sts8(my_w + my_ln, '\n'); sts8(my_w + my_ln + 1, '+'); sts8(my_w + my_ln + 2, '\n');
+                sts8(my_w + 2 * my_ln + 3, '\n');
+            }
+        }
+        const uint32_t sq0 = __shfl_sync(0xffffffffu, my_w, 0), sq1 = __shfl_sync(0xffffffffu, my_w, 16);
+        const uint32_t len0 = __shfl_sync(0xffffffffu, my_ln, 0), len1 = n_ends == 2 ? __shfl_sync(0xffffffffu, my_ln, 16) : 0u;
         __syncwarp();
 
         // ---- phase B
@@ -699,22 +707,18 @@ k_reads(const __grid_constant__ GenParams p) {
         }
         __syncwarp();
 
-        // ---- phase C
-#pragma unroll
-        for (uint32_t e = 0; e < 2; e++) {
-            if (e >= n_ends) break;
-            const uint2 ov = lds64(PL + e * 96u + 24u);
+        // ---- phase C: each half-warp moves its end's record to its final offset
+        if (mine) {
+            const uint2 ov = lds64(PLe + 24u);
             const uint64_t o = ((uint64_t)ov.y << 32) | ov.x;
-            const uint32_t rs = lds32(W0 + 4u * e);
-            const uint32_t ln = e ? len1 : len0;
-            const uint32_t idlen = (e ? sq1 : sq0) - rs;
-            const uint32_t a = (uint32_t)o & 15u, total = a + idlen + 2u * ln + 4u;
-            uint8_t* dst = p.out[e] + (o - a);
-            const uint32_t src = rs - a;                       // shared address of the byte that lands on dst[0]
+            const uint32_t idlen = my_w - my_rs;
+            const uint32_t a = ov.x & 15u, total = a + idlen + 2u * my_ln + 4u;
+            uint8_t* dst = p.out[he] + (o - a);
+            const uint32_t src = my_rs - a;                    // shared address of the byte that lands on dst[0]
             const uint32_t sh = (src & 3u) * 8u, srcw = src & ~3u;
             // whole 16-byte chunks of the file that lie inside the record
             const uint32_t first = a ? 16u : 0u, last = total & ~15u;
-            for (uint32_t lo = first + lane * 16u; lo < last; lo += 512u) {
+            for (uint32_t lo = first + hl * 16u; lo < last; lo += 256u) {
                 const uint32_t x0 = lds32(srcw + lo), x1 = lds32(srcw + lo + 4u), x2 = lds32(srcw + lo + 8u),
                                x3 = lds32(srcw + lo + 12u), x4 = lds32(srcw + lo + 16u);
                 *reinterpret_cast<uint4*>(dst + lo) =
@@ -722,12 +726,11 @@ k_reads(const __grid_constant__ GenParams p) {
                                __funnelshift_r(x3, x4, sh));
             }
             // the record's share of its first and last chunk, one byte per lane
-            if (lane < 16u) {
-                const uint32_t k = a + lane;
+            {
+                const uint32_t k = a + hl;
                 if (a && k < 16u && k < total) dst[k] = (uint8_t)lds8(src + k);
-            } else {
-                const uint32_t k = last + (lane - 16u);
-                if (k < total && (last >= 16u || !a)) dst[k] = (uint8_t)lds8(src + k);
+                const uint32_t k2 = last + hl;
+                if (k2 < total && (last >= 16u || !a)) dst[k2] = (uint8_t)lds8(src + k2);
             }
         }
         __syncwarp();
