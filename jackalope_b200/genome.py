@@ -102,52 +102,64 @@ def random_genome(n_chroms, chrom_len, seed=0, pi_tcag=(0.25, 0.25, 0.25, 0.25))
     return RefGenome(["chrom%d" % i for i in range(n_chroms)], seqs)
 
 
-def random_mutations(ref_seq: np.ndarray, rng, sub_rate, indel_rate, max_indel=10):
+def random_mutations(ref_seq: np.ndarray, rng, sub_rate, indel_rate, max_indel=10, want_edits=True):
     """Sorted, non-overlapping substitutions / insertions / deletions on one
-    chromosome, written directly in AllMutations form.  Indel sizes 1..max_indel
-    with weights exp(-size) (the relative rates `indels()` uses, R/mevo.R:660-699).
-    Returns (HapChromMuts, list of (kind, hap_pos, payload)) where the list replays
-    the same edits through HapChrom::add_* in ascending order."""
+    chromosome, written directly in AllMutations form (vectorised: usable at 500 Mb).
+    Indel sizes 1..max_indel with weights exp(-size) (the relative rates `indels()`
+    uses, R/mevo.R:660-699).  Returns (HapChromMuts, edits) where `edits` (only if
+    want_edits) is the list of (kind, hap_pos, payload) that replays the same edits
+    through HapChrom::add_* in ascending order."""
     n = ref_seq.size
-    n_sub = rng.binomial(n, sub_rate)
-    n_ind = rng.binomial(n, indel_rate)
-    m = min(n_sub + n_ind, max(0, n // (max_indel + 2)))
+    n_sub = int(rng.binomial(n, sub_rate))
+    n_ind = int(rng.binomial(n, indel_rate))
+    n_slots = n // (max_indel + 2)
+    m = min(n_sub + n_ind, max(0, n_slots))
     if m == 0:
         return HapChromMuts.empty(n), []
     # sites spaced so that a deletion never reaches the next site
-    slots = np.sort(rng.choice(n // (max_indel + 2), size=m, replace=False)) * (max_indel + 2)
+    if m * 4 < n_slots:
+        slots = np.unique(rng.integers(0, n_slots, size=int(m * 1.05) + 16))
+        if slots.size > m:
+            slots = np.sort(rng.choice(slots, size=m, replace=False))
+        m = slots.size
+    else:
+        slots = np.sort(rng.choice(n_slots, size=m, replace=False))
+    old_pos = slots.astype(np.int64) * (max_indel + 2)
     kinds = np.zeros(m, dtype=np.int8)
     ind_idx = rng.choice(m, size=min(n_ind, m), replace=False)
     kinds[ind_idx] = rng.integers(1, 3, size=ind_idx.size)      # 1 insertion, 2 deletion
     w = np.exp(-np.arange(1, max_indel + 1, dtype=np.float64))
-    sizes = rng.choice(np.arange(1, max_indel + 1), size=m, p=w / w.sum())
+    sizes = rng.choice(np.arange(1, max_indel + 1), size=m, p=w / w.sum()).astype(np.int64)
+    is_ins, is_del, is_sub = kinds == 1, kinds == 2, kinds == 0
+    sizes[is_del] = np.minimum(sizes[is_del], n - old_pos[is_del])
+    delta = np.where(is_ins, sizes, np.where(is_del, -sizes, 0))
+    shift_before = np.concatenate(([0], np.cumsum(delta)[:-1]))
+    new_pos = old_pos + shift_before
+    nuc_len = np.where(is_sub, 1, np.where(is_ins, 1 + sizes, 0)).astype(np.int64)
+    nuc_off = np.concatenate(([0], np.cumsum(nuc_len)[:-1]))
     bases = np.frombuffer(b"TCAG", dtype=np.uint8)
-    old_pos, new_pos, nuc_off, nuc_len, edits = [], [], [], [], []
-    pool = bytearray()
-    shift = 0
-    for o, kind, sz in zip(slots.tolist(), kinds.tolist(), sizes.tolist()):
-        old_pos.append(o)
-        new_pos.append(o + shift)
-        nuc_off.append(len(pool))
-        if kind == 0:
-            cur = b"TCAG".find(bytes([int(ref_seq[o])]))
-            alt = bases[(cur + 1 + rng.integers(0, 3)) % 4] if cur >= 0 else bases[rng.integers(0, 4)]
-            pool.append(int(alt))
-            nuc_len.append(1)
-            edits.append(("sub", o + shift, bytes([int(alt)])))
-        elif kind == 1:
-            ins = bases[rng.integers(0, 4, size=sz)].tobytes()
-            pool.append(int(ref_seq[o]))
-            pool += ins
-            nuc_len.append(1 + sz)
-            edits.append(("ins", o + shift, ins))
-            shift += sz
-        else:
-            sz = min(sz, n - o)
-            nuc_len.append(0)
-            edits.append(("del", o + shift, sz))
-            shift -= sz
-    return HapChromMuts(old_pos, new_pos, nuc_off, nuc_len, bytes(pool), n + shift), edits
+    pool = bases[rng.integers(0, 4, size=int(nuc_len.sum()), dtype=np.uint8)]
+    # substitutions: a base different from the reference's (any base where the reference is not T/C/A/G)
+    ref_at = ref_seq[old_pos]
+    lut = np.full(256, 255, dtype=np.uint8)
+    lut[bases] = np.arange(4, dtype=np.uint8)
+    cur = lut[ref_at[is_sub]]
+    alt_idx = np.where(cur < 4, (cur.astype(np.int64) + 1 + rng.integers(0, 3, size=cur.size)) % 4,
+                       rng.integers(0, 4, size=cur.size))
+    pool[nuc_off[is_sub]] = bases[alt_idx]
+    pool[nuc_off[is_ins]] = ref_at[is_ins]                      # the anchor base of an insertion
+    muts = HapChromMuts(old_pos, new_pos, nuc_off, nuc_len, pool, n + int(delta.sum()))
+    edits = []
+    if want_edits:
+        pb = pool.tobytes()
+        for o, np_, k, sz, no in zip(old_pos.tolist(), new_pos.tolist(), kinds.tolist(), sizes.tolist(), nuc_off.tolist()):
+            if k == 0:
+                edits.append(("sub", np_, pb[no:no + 1]))
+            elif k == 1:
+                edits.append(("ins", np_, pb[no + 1:no + 1 + sz]))
+            else:
+                edits.append(("del", np_, sz))
+    return muts, edits
 
 
 def random_haplotypes(reference: RefGenome, n_haps, sub_rate=0.01, indel_rate=0.001, seed=0, names=None,
@@ -157,7 +169,7 @@ def random_haplotypes(reference: RefGenome, n_haps, sub_rate=0.01, indel_rate=0.
     for _ in range(n_haps):
         mh, eh = [], []
         for seq in reference.seqs:
-            mm, ee = random_mutations(seq, rng, sub_rate, indel_rate)
+            mm, ee = random_mutations(seq, rng, sub_rate, indel_rate, want_edits=return_edits)
             mh.append(mm)
             eh.append(ee)
         muts.append(mh)

@@ -56,8 +56,13 @@ def group_counts(p, obj, is_haps):
     return counts
 
 
+def oracle_jobs(obj, n_reads, read_length, paired, seed, **kw):
+    """Pair-index ranges [(lo, hi)] of the run's jobs (one per haplotype with sep_files, else one)."""
+    return oracle_run(obj, n_reads, read_length, paired, seed, _jobs_only=True, **kw)
+
+
 def oracle_run(obj, n_reads, read_length, paired, seed, lo=None, hi=None, want_ledger=False, hap_seqs=None,
-               **kw):
+               only_job=None, _jobs_only=False, **kw):
     """Oracle output for the run illumina(obj, ..., seed=seed) performs.
     Returns dict(r1, r2[, plan, ledger, ledger_cnt, groups]); with sep_files the
     jobs' outputs are concatenated in haplotype order (as sink="memory" does)."""
@@ -76,6 +81,11 @@ def oracle_run(obj, n_reads, read_length, paired, seed, lo=None, hi=None, want_l
     nc = ref.n_chroms()
     nh = obj.n_haps() if is_haps else 1
     counts = group_counts(p, obj, is_haps)
+    if _jobs_only:
+        off = np.concatenate(([0], np.cumsum(counts))).astype(np.uint64)
+        if is_haps and p.sep_files:
+            return [(int(off[h * nc]), int(off[(h + 1) * nc])) for h in range(nh)]
+        return [(0, int(off[-1]))]
     if is_haps:
         hap_seqs = hap_seqs or hap_sequences(obj)
         seqs = [hap_seqs[h][c] for h in range(nh) for c in range(nc)]
@@ -96,6 +106,8 @@ def oracle_run(obj, n_reads, read_length, paired, seed, lo=None, hi=None, want_l
         jobs = [(0, int(groups.off[-1]))]
     res = dict(r1=b"", r2=b"", groups=groups, jobs=jobs, params=p, profiles=(prof1, prof2), n_chroms=nc)
     for (jl, jh) in jobs:
+        if only_job is not None and (jl, jh) != tuple(only_job):
+            continue
         a_lo = jl if lo is None else max(jl, lo)
         a_hi = jh if hi is None else min(jh, hi)
         if a_hi <= a_lo:
