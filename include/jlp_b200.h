@@ -32,7 +32,7 @@ enum jlp_status {
     JLP_ERR_CUDA = -3,       /* CUDA runtime error */
     JLP_ERR_IO = -4,         /* cannot open / write an output file (src/io.h:288-290) */
     JLP_ERR_ABORTED = -5,    /* abort callback asked to stop (Progress::check_abort, src/hts.h:396-399) */
-    JLP_ERR_UNSUPPORTED = -6 /* a feature of the reference not built yet (see jlp_illumina_params.compress) */
+    JLP_ERR_UNSUPPORTED = -6 /* a feature of the reference not built yet (none on this path at present) */
 };
 
 /* ---- context: one per GPU (one process per GPU under torchrun) -------------- */
@@ -98,8 +98,8 @@ typedef struct jlp_illumina_params {
     int matepair;
     const char* out_prefix;      /* files <prefix>[_<hap>]_R{1,2}.fq, src/hts.h:344,541 */
     int sep_files;               /* haplotype runs only */
-    int compress;                /* 0 = plain FASTQ; >0: JLP_ERR_UNSUPPORTED in this round */
-    const char* comp_method;     /* "gzip" | "bgzip" (validated, src/hts.h:470) */
+    int compress;                /* 0 = plain FASTQ; 1..9 = zlib level, files get ".gz" appended (src/io.h:126,217) */
+    const char* comp_method;     /* "gzip" | "bgzip" (src/hts.h:470); with n_threads > 1 always bgzip (src/hts.h:478-490) */
     uint64_t n_reads;
     double prob_dup;
     uint64_t n_threads;          /* host writer threads (pwrite of the pinned batch buffers), 1..64 */
@@ -177,6 +177,10 @@ int jlp_illumina_group_counts(jlp_ctx* ctx, int use_haplotypes, const jlp_illumi
  * sizes[n_chroms]); otherwise sizes is [n_haps][n_chroms].  counts has the same shape. */
 int jlp_apportion(uint64_t seed, uint64_t n_pairs, uint64_t n_haps, uint64_t n_chroms,
                   const double* hap_probs, const uint64_t* sizes, uint64_t* counts);
+/* The compressed form the files sink writes for `n` bytes of FASTQ: BGZF blocks + EOF block
+ * (bgzf != 0; FileBGZF, src/io.h:58-135) or concatenated gzip members (FileGZ, src/io.h:140-236).
+ * *len receives the size; JLP_ERR_ARG if `cap` is too small. */
+int jlp_deflate(int bgzf, int level, const void* in, uint64_t n, void* out, uint64_t cap, uint64_t* len);
 /* Pair-index range [lo, hi) of job [job_lo, job_hi) that shard `shard_index` of
  * `shard_count` generates (jlp_illumina_params.shard_index / shard_count): contiguous
  * and near-equal, as split_int (src/util.h:245-258) splits reads over threads. */

@@ -50,7 +50,7 @@ class RunStats(C.Structure):
 SYMBOLS = [
     "jlp_ctx_create", "jlp_ctx_destroy", "jlp_last_error", "jlp_set_genome", "jlp_set_genome_async", "jlp_genome_sync", "jlp_clear_haplotypes",
     "jlp_add_haplotype", "jlp_get_haplotype_chrom", "jlp_set_profile", "jlp_illumina_ref", "jlp_illumina_hap",
-    "jlp_illumina_to_memory", "jlp_illumina_stream", "jlp_illumina_device_only", "jlp_illumina_group_counts", "jlp_apportion", "jlp_shard_range", "jlp_reads_per_group", "jlp_alias_build",
+    "jlp_illumina_to_memory", "jlp_illumina_stream", "jlp_illumina_device_only", "jlp_illumina_group_counts", "jlp_apportion", "jlp_shard_range", "jlp_deflate", "jlp_reads_per_group", "jlp_alias_build",
     "jlp_threshold", "jlp_unif_expr", "jlp_frag_table", "jlp_philox4x32_10", "jlp_draw_pos", "jlp_draw_pair",
     "jlp_version",
 ]
@@ -90,6 +90,7 @@ def lib():
     L.jlp_illumina_group_counts.argtypes = [C.c_void_p, C.c_int, C.POINTER(Params), u64p, C.c_uint64, u64p]
     L.jlp_apportion.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, f64p, u64p, u64p]
     L.jlp_shard_range.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, u64p, u64p]
+    L.jlp_deflate.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, u64p]
     L.jlp_reads_per_group.argtypes = [C.c_uint64, f64p, C.c_uint64, C.c_uint64, u64p]
     L.jlp_alias_build.argtypes = [f64p, C.c_uint64, f64p, u64p]
     L.jlp_threshold.argtypes = [C.c_int, C.c_double, u64p, C.POINTER(C.c_int)]

@@ -8,8 +8,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libjlp_b200.so")
-SOURCES = ["jlp_api.cu", "jlp_kernels.cu", "jlp_host.cpp"]
-HEADERS = ["jlp_draws.h", "jlp_host.h", "jlp_kernels.cuh", os.path.join("..", "..", "include", "jlp_b200.h")]
+SOURCES = ["jlp_api.cu", "jlp_kernels.cu", "jlp_host.cpp", "jlp_deflate.cpp"]
+HEADERS = ["jlp_draws.h", "jlp_host.h", "jlp_kernels.cuh", "jlp_deflate.h", os.path.join("..", "..", "include", "jlp_b200.h")]
 
 
 def _stale():
@@ -28,7 +28,7 @@ def build(force=False, verbose=False):
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += os.environ.get("JLP_NVCC_EXTRA", "").split()
-    cmd += [os.path.join(CSRC, f) for f in SOURCES]
+    cmd += [os.path.join(CSRC, f) for f in SOURCES] + ["-lz"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

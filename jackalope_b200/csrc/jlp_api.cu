@@ -13,6 +13,7 @@
 #include <cerrno>
 #include <condition_variable>
 #include <deque>
+#include <functional>
 #include <mutex>
 #include <thread>
 #include <cstdio>
@@ -22,6 +23,7 @@
 #include <string>
 #include <vector>
 
+#include "jlp_deflate.h"
 #include "jlp_draws.h"
 #include "jlp_host.h"
 #include "jlp_kernels.cuh"
@@ -96,7 +98,8 @@ template <typename T> struct PinBuf {
 // src/hts.h:401-416).
 class WriterPool {
 public:
-    struct Task { int fd; const uint8_t* p; uint64_t n; uint64_t off; std::atomic<int>* pending; };
+    // a task returns an error text (empty = fine); `pending` counts the tasks of one batch slot
+    struct Task { std::function<std::string()> run; std::atomic<int>* pending; };
     ~WriterPool() { stop(); }
     void start(size_t n_threads) {
         if (th.size() == n_threads) return;
@@ -110,9 +113,9 @@ public:
         for (std::thread& t : th) t.join();
         th.clear();
     }
-    void submit(const Task& t) {
-        t.pending->fetch_add(1);
-        { std::lock_guard<std::mutex> l(m); q.push_back(t); }
+    void submit(std::atomic<int>* pending, std::function<std::string()> f) {
+        pending->fetch_add(1);
+        { std::lock_guard<std::mutex> l(m); q.push_back(Task{std::move(f), pending}); }
         cv.notify_one();
     }
     // wait until every task counted by `pending` is done; returns the first error text (empty = none)
@@ -130,15 +133,9 @@ private:
                 std::unique_lock<std::mutex> l(m);
                 cv.wait(l, [&]() { return quit || !q.empty(); });
                 if (q.empty()) return;
-                t = q.front(); q.pop_front();
+                t = std::move(q.front()); q.pop_front();
             }
-            std::string e;
-            const uint8_t* p = t.p; uint64_t n = t.n, off = t.off;
-            while (n) {
-                ssize_t w = ::pwrite(t.fd, p, n > (1u << 30) ? (1u << 30) : n, (off_t)off);
-                if (w < 0) { if (errno == EINTR) continue; e = std::strerror(errno); break; }
-                p += w; n -= (uint64_t)w; off += (uint64_t)w;
-            }
+            std::string e = t.run();
             {
                 std::lock_guard<std::mutex> l(m);
                 if (!e.empty() && err.empty()) err = e;
@@ -154,6 +151,15 @@ private:
     std::string err;
     bool quit = false;
 };
+
+std::string pwrite_all(int fd, const uint8_t* p, uint64_t n, uint64_t off) {
+    while (n) {
+        ssize_t w = ::pwrite(fd, p, n > (1u << 30) ? (1u << 30) : n, (off_t)off);
+        if (w < 0) { if (errno == EINTR) continue; return std::strerror(errno); }
+        p += w; n -= (uint64_t)w; off += (uint64_t)w;
+    }
+    return std::string();
+}
 
 struct HapDev {
     std::string name;
@@ -172,7 +178,8 @@ struct Slot {
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // start, placed, scanned, reads done, copied
     uint32_t pairs = 0;
     bool busy = false;
-    std::atomic<int> writes{0};   // slices of h_out still being written to the files
+    std::atomic<int> writes{0};   // slices of h_out still being written to / compressed for the files
+    std::vector<std::vector<uint8_t>> zout[2];   // compressed slices of the batch, in file order
 };
 
 }  // namespace
@@ -339,8 +346,15 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
     if (P->compress > 0) {
         std::string m = P->comp_method ? P->comp_method : "";
         if (m != "gzip" && m != "bgzip") throw ArgErr("\nUnrecognized compression method.");  // src/hts.h:470
-        throw Unsupported("compressed output (compress > 0) is not built yet; write plain FASTQ");
+        if (P->compress > 9) throw ArgErr("\nInvalid bgzip compress level of " + std::to_string(P->compress) +
+                                          ". It must be in range [0,9].");                   // src/io.h:113-117
     }
+    // write_reads_cpp_ (src/hts.h:441-500): compressed + one thread -> the method asked for;
+    // compressed + several threads -> always bgzip (the reference writes plain files first and
+    // bgzips them afterwards; here the batches are compressed on their way to the file)
+    const int zmethod = P->compress <= 0 ? -1
+                        : (P->n_threads > 1 || std::string(P->comp_method ? P->comp_method : "") == "bgzip") ? DEFLATE_BGZF
+                                                                                                            : DEFLATE_GZIP;
     if (!(P->prob_dup >= 0 && P->prob_dup <= 1)) throw ArgErr("prob_dup must be in [0,1]");
     const double insp[2] = {P->ins_prob1, P->ins_prob2}, delp[2] = {P->del_prob1, P->del_prob2};
     for (int e = 0; e < n_ends; e++)
@@ -481,6 +495,15 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
         if (sink.kind != SINK_FILES) return;
         std::string e = c->writers.wait(s.writes);
         if (!e.empty()) { c->writers.clear_error(); throw IoErr("Error writing to file " + sink.names[0] + " / " + sink.names[1] + ": " + e); }
+        // compressed slices of the slot's batch go to the files in order
+        for (int k = 0; k < n_ends; k++) {
+            for (std::vector<uint8_t>& v : s.zout[k]) {
+                std::string w = pwrite_all(sink.fd[k], v.data(), v.size(), sink.pos[k]);
+                if (!w.empty()) throw IoErr("Error writing to file " + sink.names[k] + ": " + w);
+                sink.pos[k] += v.size();
+            }
+            s.zout[k].clear();
+        }
     };
     if (sink.kind == SINK_FILES) c->writers.start((size_t)std::min<uint64_t>(std::max<uint64_t>(P->n_threads, 1), 64));
     // finish a batch: wait for its totals, copy the FASTQ to the host, hand it to the sink
@@ -498,6 +521,7 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
         st.batches++;
         if (need_host) {
             wait_writes(s);                     // the pinned buffers of this slot are free again
+            if (zmethod >= 0) for (Slot& t : c->slot) if (&t != &s) wait_writes(t);   // keep the files in batch order
             for (int e = 0; e < n_ends; e++) {
                 uint64_t n = s.h_totals.p[e];
                 CK(cudaMemcpyAsync(s.h_out[e].p, s.out[e].p, n, cudaMemcpyDeviceToHost, c->s_copy));
@@ -507,12 +531,30 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
             CK(cudaEventSynchronize(s.ev[4]));
             for (int e = 0; e < n_ends; e++) {
                 uint64_t n = s.h_totals.p[e];
-                if (sink.kind == SINK_FILES) {
+                if (sink.kind == SINK_FILES && zmethod < 0) {
                     // R1 and R2 stay record-aligned: both files receive the same batches in the same order
                     const uint64_t slice = 8ull << 20;
-                    for (uint64_t o = 0; o < n; o += slice)
-                        c->writers.submit(WriterPool::Task{sink.fd[e], s.h_out[e].p + o, std::min(slice, n - o), sink.pos[e] + o, &s.writes});
+                    for (uint64_t o = 0; o < n; o += slice) {
+                        const int fd = sink.fd[e];
+                        const uint8_t* src = s.h_out[e].p + o;
+                        const uint64_t len = std::min(slice, n - o), off = sink.pos[e] + o;
+                        c->writers.submit(&s.writes, [fd, src, len, off]() { return pwrite_all(fd, src, len, off); });
+                    }
                     sink.pos[e] += n;
+                } else if (sink.kind == SINK_FILES) {
+                    // compressed: the writer threads deflate slices of whole members; their output is
+                    // written in order once the batch is done (flush_compressed)
+                    const uint64_t unit = zmethod == DEFLATE_BGZF ? 0xff00ull : (1ull << 20);
+                    const uint64_t slice = unit * (zmethod == DEFLATE_BGZF ? 64 : 4);
+                    const size_t n_slices = (size_t)((n + slice - 1) / slice);
+                    s.zout[e].assign(n_slices, std::vector<uint8_t>());
+                    for (size_t k = 0; k < n_slices; k++) {
+                        const uint8_t* src = s.h_out[e].p + k * slice;
+                        const uint64_t len = std::min<uint64_t>(slice, n - k * slice);
+                        std::vector<uint8_t>* dst = &s.zout[e][k];
+                        const int lvl = P->compress;
+                        c->writers.submit(&s.writes, [zmethod, lvl, src, len, dst]() { return deflate_members(zmethod, lvl, src, len, *dst); });
+                    }
                 } else if (sink.kind == SINK_STREAM) {
                     if (sink.chunk_cb(sink.chunk_user, job_index, e, reinterpret_cast<const char*>(s.h_out[e].p), n))
                         throw IoErr("the chunk callback reported an error");
@@ -539,6 +581,7 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
             sink.pos[0] = sink.pos[1] = 0;
             for (int e = 0; e < n_ends; e++) {
                 sink.names[e] = job.file_prefix + "_R" + std::to_string(e + 1) + ".fq";   // src/hts.h:344
+                if (zmethod >= 0) sink.names[e] += ".gz";                                 // src/io.h:126,217
                 sink.fd[e] = ::open(sink.names[e].c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
                 if (sink.fd[e] < 0) throw IoErr("Unable to open file " + sink.names[e] + ".\n");  // src/io.h:288-290
             }
@@ -587,6 +630,12 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
         }
         for (Slot& s : c->slot) if (s.busy) finish(s, job);
         for (Slot& s : c->slot) wait_writes(s);
+        if (sink.kind == SINK_FILES && zmethod == DEFLATE_BGZF)
+            for (int e = 0; e < n_ends; e++) {   // bgzf_close appends the empty end-of-file block
+                std::string w = pwrite_all(sink.fd[e], kBgzfEof, sizeof kBgzfEof, sink.pos[e]);
+                if (!w.empty()) throw IoErr("Error writing to file " + sink.names[e] + ": " + w);
+                sink.pos[e] += sizeof kBgzfEof;
+            }
         job_index++;
     }
     CK(cudaEventRecord(c->ev_run[1], c->s_compute));
@@ -854,6 +903,18 @@ int jlp_illumina_group_counts(jlp_ctx* c, int use_haplotypes, const jlp_illumina
 }
 
 // ---- host-side pieces (no device) ----
+
+int jlp_deflate(int bgzf, int level, const void* in, uint64_t n, void* out, uint64_t cap, uint64_t* len) {
+    if ((!in && n) || !len) return JLP_ERR_ARG;
+    std::vector<uint8_t> v;
+    std::string e = deflate_members(bgzf ? DEFLATE_BGZF : DEFLATE_GZIP, level, static_cast<const uint8_t*>(in), n, v);
+    if (!e.empty()) return JLP_ERR_ARG;
+    if (bgzf) v.insert(v.end(), kBgzfEof, kBgzfEof + sizeof kBgzfEof);
+    *len = v.size();
+    if (v.size() > cap || !out) return v.size() > cap ? JLP_ERR_ARG : JLP_OK;
+    std::memcpy(out, v.data(), v.size());
+    return JLP_OK;
+}
 
 int jlp_shard_range(uint64_t job_lo, uint64_t job_hi, uint32_t shard_index, uint32_t shard_count, uint64_t* lo,
                     uint64_t* hi) {

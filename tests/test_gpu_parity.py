@@ -165,5 +165,44 @@ def test_errors_surface_like_the_reference(ctx, tmp_path):
     blocker.write_text("a file where a directory is needed")
     with pytest.raises((RuntimeError, OSError)):   # unopenable output file (src/io.h:288-290)
         J.illumina(g, str(blocker / "reads"), 100, 100, True, seed=1, ctx=ctx, overwrite=True)
-    with pytest.raises(RuntimeError, match="not built"):
-        J.illumina(g, str(tmp_path / "z"), 100, 100, True, seed=1, ctx=ctx, compress=True)
+    with pytest.raises(J.JackalopeError, match="gzip cannot be performed using multiple threads"):
+        J.illumina(g, str(tmp_path / "z"), 100, 100, True, seed=1, ctx=ctx, compress=True, comp_method="gzip", n_threads=2)
+
+
+def bgzf_blocks(z: bytes):
+    """Walk the BGZF blocks of a file: (compressed size, uncompressed size) per block."""
+    import struct
+    out, p = [], 0
+    while p < len(z):
+        assert z[p:p + 4] == b"\x1f\x8b\x08\x04" and z[p + 10:p + 16] == b"\x06\x00BC\x02\x00"
+        bsize = struct.unpack_from("<H", z, p + 16)[0] + 1
+        isize = struct.unpack_from("<I", z, p + bsize - 4)[0]
+        out.append((bsize, isize))
+        p += bsize
+    assert p == len(z)
+    return out
+
+
+def test_compressed_output(ctx, tmp_path):
+    """compress > 0 (write_reads_cpp_, src/hts.h:441-500): <prefix>_R{1,2}.fq.gz, bgzip or gzip; the
+    decompressed bytes are the uncompressed run's."""
+    import gzip
+    g = small_genome(seed=41)
+    r1, r2, _ = J.illumina(g, "", 8000, 100, True, seed=42, ctx=ctx, sink="memory")
+    for method, nthr, level in (("bgzip", 1, True), ("bgzip", 4, 3), ("gzip", 1, 9)):
+        pre = str(tmp_path / ("z_%s_%d" % (method, nthr)))
+        J.illumina(g, pre, 8000, 100, True, seed=42, ctx=ctx, compress=level, comp_method=method, n_threads=nthr,
+                   batch_pairs=1500)
+        z1, z2 = open(pre + "_R1.fq.gz", "rb").read(), open(pre + "_R2.fq.gz", "rb").read()
+        assert gzip.decompress(z1) == r1 and gzip.decompress(z2) == r2
+        if method == "bgzip":
+            for z in (z1, z2):
+                blocks = bgzf_blocks(z)
+                assert blocks[-1] == (28, 0) and all(b <= 65536 and 0 < i <= 0xff00 for b, i in blocks[:-1])
+        with pytest.raises(J.JackalopeError, match="already exists"):
+            J.illumina(g, pre, 8000, 100, True, seed=42, ctx=ctx, compress=level, comp_method=method, n_threads=nthr)
+    haps = J.random_haplotypes(g, 2, seed=43)
+    pre = str(tmp_path / "zh")
+    J.illumina(haps, pre, 3000, 100, True, seed=44, ctx=ctx, compress=True, sep_files=True, n_threads=2)
+    m1, _, _ = J.illumina(haps, "", 3000, 100, True, seed=44, ctx=ctx, sep_files=True, sink="memory")
+    assert b"".join(gzip.decompress(open("%s_%s_R1.fq.gz" % (pre, h), "rb").read()) for h in haps.hap_names) == m1

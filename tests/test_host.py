@@ -188,6 +188,33 @@ def test_shard_ranges_partition_a_job():
     assert lib.jlp_shard_range(0, 10, 3, 3, C.byref(a), C.byref(b)) != 0
 
 
+def test_deflate_members_are_valid_gzip_and_bgzf():
+    import gzip
+    import struct
+    lib = _lib.lib()
+    rng = np.random.default_rng(9)
+    data = b"".join(b"@REF-chrom%d-%d-F/1\n%s\n+\n%s\n" % (i % 7, i * 31, bytes(rng.choice(np.frombuffer(b"TCAG", np.uint8), 100)),
+                                                             bytes(rng.integers(35, 74, 100, dtype=np.uint8))) for i in range(3000))
+    for bg in (0, 1):
+        for level in (1, 6, 9):
+            n = C.c_uint64()
+            buf = C.create_string_buffer(len(data) + 65536)
+            assert lib.jlp_deflate(bg, level, data, len(data), buf, len(buf), C.byref(n)) == 0
+            z = buf.raw[:n.value]
+            assert gzip.decompress(z) == data and len(z) < len(data)
+            if bg:
+                p, sizes = 0, []
+                while p < len(z):
+                    assert z[p:p + 4] == b"\x1f\x8b\x08\x04" and z[p + 12:p + 14] == b"BC"
+                    b = struct.unpack_from("<H", z, p + 16)[0] + 1
+                    sizes.append(struct.unpack_from("<I", z, p + b - 4)[0])
+                    p += b
+                assert p == len(z) and sizes[-1] == 0 and max(sizes) <= 0xff00 and sum(sizes) == len(data)
+    n = C.c_uint64()
+    assert lib.jlp_deflate(1, 6, b"", 0, None, 0, C.byref(n)) == 0 and n.value == 28     # an empty file is just the EOF block
+    assert lib.jlp_deflate(1, 11, data, len(data), None, 0, C.byref(n)) != 0
+
+
 # ------------------------------------------------------------- R-layer mirror ---
 
 def test_builtin_profiles_are_the_reference_files():
