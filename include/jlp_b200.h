@@ -179,7 +179,7 @@ int jlp_apportion(uint64_t seed, uint64_t n_pairs, uint64_t n_haps, uint64_t n_c
                   const double* hap_probs, const uint64_t* sizes, uint64_t* counts);
 /* The compressed form the files sink writes for `n` bytes of FASTQ: BGZF blocks + EOF block
  * (bgzf != 0; FileBGZF, src/io.h:58-135) or concatenated gzip members (FileGZ, src/io.h:140-236).
- * *len receives the size; JLP_ERR_ARG if `cap` is too small. */
+ * *len receives the size (out == NULL only asks for it); JLP_ERR_ARG if `cap` is too small. */
 int jlp_deflate(int bgzf, int level, const void* in, uint64_t n, void* out, uint64_t cap, uint64_t* len);
 /* Pair-index range [lo, hi) of job [job_lo, job_hi) that shard `shard_index` of
  * `shard_count` generates (jlp_illumina_params.shard_index / shard_count): contiguous

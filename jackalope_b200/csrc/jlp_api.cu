@@ -911,7 +911,8 @@ int jlp_deflate(int bgzf, int level, const void* in, uint64_t n, void* out, uint
     if (!e.empty()) return JLP_ERR_ARG;
     if (bgzf) v.insert(v.end(), kBgzfEof, kBgzfEof + sizeof kBgzfEof);
     *len = v.size();
-    if (v.size() > cap || !out) return v.size() > cap ? JLP_ERR_ARG : JLP_OK;
+    if (!out) return JLP_OK;                 // size query
+    if (v.size() > cap) return JLP_ERR_ARG;
     std::memcpy(out, v.data(), v.size());
     return JLP_OK;
 }
