@@ -273,6 +273,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
     def max_over_ranks(x):
         if world == 1:
             return x
@@ -311,6 +318,7 @@ def main():
     clk = clocks.stop() if rank == 0 else None
     assert st["pairs"] == a.steps * B and st["batches"] == a.steps, st
     run_ms = max_over_ranks(st["run_ms"])
+    launches = int(sum_over_ranks(st["kernel_launches"]))
     value = a.steps * B * world / (run_ms / 1e3)
     place_ms = st["place_ms"] / st["batches"]
     reads_ms = st["reads_ms"] / st["batches"]
@@ -370,7 +378,7 @@ def main():
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
            "ms_per_step": run_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "u8", "data": "synthetic", "config": config, "clocks": clk, "e2e": e2e, "e2e_files": e2e_files,
-           "gpu_launches": int(st["kernel_launches"])}
+           "gpu_launches": launches}
 
     if rank == 0:
         peaks, which = None, "fallback"

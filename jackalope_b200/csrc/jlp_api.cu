@@ -177,6 +177,7 @@ struct Slot {
     PinBuf<uint64_t> h_totals;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // start, placed, scanned, reads done, copied
     uint32_t pairs = 0;
+    uint64_t tot[2] = {0, 0};     // FASTQ bytes of the batch per file (read back from the device)
     bool busy = false;
     std::atomic<int> writes{0};   // slices of h_out still being written to / compressed for the files
     std::vector<std::vector<uint8_t>> zout[2];   // compressed slices of the batch, in file order
@@ -206,7 +207,7 @@ struct jlp_ctx {
     DevBuf<GroupDev> d_groups;
     DevBuf<uint8_t> d_strpool;
     DevBuf<uint32_t> d_status;
-    Slot slot[2];
+    Slot slot[3];                               // compute | D2H copy | delivery to the sink, one batch each
     WriterPool writers;
     cudaStream_t s_upload = nullptr;            // genome H2D, chromosome by chromosome
     std::vector<cudaEvent_t> chrom_ev;          // chromosome c is resident once chrom_ev[c] has fired
@@ -506,31 +507,36 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
         }
     };
     if (sink.kind == SINK_FILES) c->writers.start((size_t)std::min<uint64_t>(std::max<uint64_t>(P->n_threads, 1), 64));
-    // finish a batch: wait for its totals, copy the FASTQ to the host, hand it to the sink
     uint64_t job_index = 0;
-    auto finish = [&](Slot& s, const Job& job) {
-        (void)job;
+    Slot* z_pending = nullptr;      // the batch whose compressed slices are not in the files yet
+    // stage 2 of a batch: its kernels are done -> statistics, then its FASTQ starts its way to the host
+    // (queued right behind the previous batch's copy, so the bus never idles)
+    auto issue_copy = [&](Slot& s) {
         CK(cudaEventSynchronize(s.ev[3]));
         float ms_place = 0, ms_all = 0, ms_reads = 0;
         CK(cudaEventElapsedTime(&ms_place, s.ev[0], s.ev[1]));
         CK(cudaEventElapsedTime(&ms_reads, s.ev[2], s.ev[3]));
         CK(cudaEventElapsedTime(&ms_all, s.ev[0], s.ev[3]));
         st.place_ms += ms_place; st.reads_ms += ms_reads; st.device_ms += ms_all;
-        for (int e = 0; e < n_ends; e++) st.bytes_out[e] += s.h_totals.p[e];
+        for (int e = 0; e < n_ends; e++) { s.tot[e] = s.h_totals.p[e]; st.bytes_out[e] += s.tot[e]; }
         st.pairs += s.pairs;
         st.batches++;
+        if (!need_host) return;
+        if (z_pending == &s) { wait_writes(s); z_pending = nullptr; }
+        wait_writes(s);                         // the pinned buffers of this slot are free again
+        for (int e = 0; e < n_ends; e++) {
+            CK(cudaMemcpyAsync(s.h_out[e].p, s.out[e].p, s.tot[e], cudaMemcpyDeviceToHost, c->s_copy));
+            st.d2h_bytes += s.tot[e];
+        }
+        CK(cudaEventRecord(s.ev[4], c->s_copy));
+    };
+    // stage 3: the copy has landed -> hand the batch to the sink
+    auto deliver = [&](Slot& s) {
         if (need_host) {
-            wait_writes(s);                     // the pinned buffers of this slot are free again
-            if (zmethod >= 0) for (Slot& t : c->slot) if (&t != &s) wait_writes(t);   // keep the files in batch order
-            for (int e = 0; e < n_ends; e++) {
-                uint64_t n = s.h_totals.p[e];
-                CK(cudaMemcpyAsync(s.h_out[e].p, s.out[e].p, n, cudaMemcpyDeviceToHost, c->s_copy));
-                st.d2h_bytes += n;
-            }
-            CK(cudaEventRecord(s.ev[4], c->s_copy));
             CK(cudaEventSynchronize(s.ev[4]));
+            if (zmethod >= 0 && z_pending) { wait_writes(*z_pending); z_pending = nullptr; }   // files stay in batch order
             for (int e = 0; e < n_ends; e++) {
-                uint64_t n = s.h_totals.p[e];
+                const uint64_t n = s.tot[e];
                 if (sink.kind == SINK_FILES && zmethod < 0) {
                     // R1 and R2 stay record-aligned: both files receive the same batches in the same order
                     const uint64_t slice = 8ull << 20;
@@ -543,7 +549,7 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
                     sink.pos[e] += n;
                 } else if (sink.kind == SINK_FILES) {
                     // compressed: the writer threads deflate slices of whole members; their output is
-                    // written in order once the batch is done (flush_compressed)
+                    // written in order once the batch is done (wait_writes)
                     const uint64_t unit = zmethod == DEFLATE_BGZF ? 0xff00ull : (1ull << 20);
                     const uint64_t slice = unit * (zmethod == DEFLATE_BGZF ? 64 : 4);
                     const size_t n_slices = (size_t)((n + slice - 1) / slice);
@@ -555,6 +561,7 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
                         const int lvl = P->compress;
                         c->writers.submit(&s.writes, [zmethod, lvl, src, len, dst]() { return deflate_members(zmethod, lvl, src, len, *dst); });
                     }
+                    z_pending = &s;
                 } else if (sink.kind == SINK_STREAM) {
                     if (sink.chunk_cb(sink.chunk_user, job_index, e, reinterpret_cast<const char*>(s.h_out[e].p), n))
                         throw IoErr("the chunk callback reported an error");
@@ -588,11 +595,16 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
         }
         uint64_t lo, hi;
         shard_range(job.lo, job.hi, si, S, lo, hi);
-        int cur = 0;
-        Slot* prev = nullptr;
-        for (uint64_t b0 = lo; b0 < hi; b0 += B) {
-            Slot& s = c->slot[cur];
-            if (s.busy) finish(s, job);
+        // three batches in flight: batch b computes while b-1 crosses PCIe and b-2 is handed to the sink
+        std::deque<Slot*> computing, copying;
+        auto drain_one = [&]() {
+            if (!copying.empty() && (computing.empty() || copying.size() >= 2)) { deliver(*copying.front()); copying.pop_front(); }
+            else if (!computing.empty()) { issue_copy(*computing.front()); copying.push_back(computing.front()); computing.pop_front(); }
+        };
+        uint64_t bi = 0;
+        for (uint64_t b0 = lo; b0 < hi; b0 += B, bi++) {
+            Slot& s = c->slot[bi % 3];
+            while (s.busy) drain_one();
             const uint32_t np = (uint32_t)std::min<uint64_t>(B, hi - b0);
             if (c->upload_pending && !use_haps) {
                 // the batch reads the chromosomes of its pairs (and of earlier ones, through duplicate
@@ -619,16 +631,18 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
             CK(cudaEventRecord(s.ev[3], c->s_compute));
             st.kernel_launches += 5;
             s.pairs = np; s.busy = true;
-            if (prev && prev->busy) finish(*prev, job);
-            prev = &s;
-            cur ^= 1;
+            computing.push_back(&s);
+            // the previous batch's copy is queued before the one in flight is waited for
+            if (computing.size() > 1) { issue_copy(*computing.front()); copying.push_back(computing.front()); computing.pop_front(); }
+            if (copying.size() > 1) { deliver(*copying.front()); copying.pop_front(); }
             if (P->abort_cb && P->abort_cb(P->cb_user)) {
-                for (Slot& t : c->slot) if (t.busy) { cudaEventSynchronize(t.ev[3]); t.busy = false; }
+                for (Slot& t : c->slot) if (t.busy) { cudaEventSynchronize(t.ev[3]); cudaStreamSynchronize(c->s_copy); t.busy = false; }
                 for (Slot& t : c->slot) c->writers.wait(t.writes);
                 throw Aborted();
             }
         }
-        for (Slot& s : c->slot) if (s.busy) finish(s, job);
+        while (!computing.empty() || !copying.empty()) drain_one();
+        if (z_pending) { wait_writes(*z_pending); z_pending = nullptr; }
         for (Slot& s : c->slot) wait_writes(s);
         if (sink.kind == SINK_FILES && zmethod == DEFLATE_BGZF)
             for (int e = 0; e < n_ends; e++) {   // bgzf_close appends the empty end-of-file block

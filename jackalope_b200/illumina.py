@@ -16,7 +16,7 @@ import numpy as np
 
 from . import _lib
 from .genome import Haplotypes, RefGenome
-from .profiles import JackalopeError, flatten_profile, read_profile
+from .profiles import JackalopeError, cached_flat_profile
 
 u8p, u32p, u64p, f64p = _lib.u8p, _lib.u32p, _lib.u64p, _lib.f64p
 
@@ -183,7 +183,7 @@ class Context:
     def set_profile(self, end, flat):
         L, nq, probs, quals = flat
         old = self._profiles[end]
-        if old is not None and old[0] == L and all(np.array_equal(a, b) for a, b in zip(old[1:], flat[1:])):
+        if old is not None and (old is flat or (old[0] == L and all(np.array_equal(a, b) for a, b in zip(old[1:], flat[1:])))):
             return
         self._check(self.lib.jlp_set_profile(self.h, end, L, nq.ctypes.data_as(u32p), probs.ctypes.data_as(f64p),
                                              quals.ctypes.data_as(u8p)), "jlp_set_profile")
@@ -249,8 +249,8 @@ def _prepare(obj, out_prefix, n_reads, read_length, paired, frag_mean, frag_sd, 
         haplotype_probs = [1.0] * obj.n_haps()
     if barcodes is None:
         barcodes = [""] * (obj.n_haps() if is_haps else 1)
-    prof1 = flatten_profile(read_profile(profile1, seq_sys, read_length, 1))
-    prof2 = flatten_profile(read_profile(profile2, seq_sys, read_length, 2)) if paired else None
+    prof1 = cached_flat_profile(profile1, seq_sys, read_length, 1)
+    prof2 = cached_flat_profile(profile2, seq_sys, read_length, 2) if paired else None
 
     keep = []
     p = _lib.Params()

@@ -237,3 +237,26 @@ def flatten_profile(prof):
             probs.append(p)
             quals.append((q & 0xFF).astype(np.uint8))
     return L, nq, np.ascontiguousarray(np.concatenate(probs)), np.ascontiguousarray(np.concatenate(quals))
+
+
+_flat_cache = {}
+
+
+def cached_flat_profile(profile_fn, seq_sys, read_length, read):
+    """flatten_profile(read_profile(...)), memoised: parsing an ART profile costs ~10 ms of
+    Python per call, which a multi-million-pairs-per-second run should pay once.  Files are keyed
+    by path, size and mtime."""
+    key = (profile_fn, seq_sys, int(read_length), int(read))
+    if profile_fn is not None and not str(profile_fn).startswith("builtin:"):
+        try:
+            st = os.stat(profile_fn)
+            key += (st.st_size, st.st_mtime_ns)
+        except OSError:
+            pass
+    hit = _flat_cache.get(key)
+    if hit is None:
+        hit = flatten_profile(read_profile(profile_fn, seq_sys, read_length, read))
+        if len(_flat_cache) > 64:
+            _flat_cache.clear()
+        _flat_cache[key] = hit
+    return hit
