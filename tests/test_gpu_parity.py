@@ -206,3 +206,33 @@ def test_compressed_output(ctx, tmp_path):
     J.illumina(haps, pre, 3000, 100, True, seed=44, ctx=ctx, compress=True, sep_files=True, n_threads=2)
     m1, _, _ = J.illumina(haps, "", 3000, 100, True, seed=44, ctx=ctx, sep_files=True, sink="memory")
     assert b"".join(gzip.decompress(open("%s_%s_R1.fq.gz" % (pre, h), "rb").read()) for h in haps.hap_names) == m1
+
+
+def test_long_names_take_the_long_id_path(ctx):
+    """ID lines longer than the 64 bytes the plan record inlines are written by the fallback path."""
+    base = J.random_genome(2, 3000, seed=51)
+    g = J.RefGenome(["chromosome_with_a_very_long_name_%d_" % i + "x" * 40 for i in range(2)], base.seqs)
+    check(ctx, g, 1200, 100, True, seed=52)
+    haps = J.random_haplotypes(g, 2, seed=53, names=["haplotype_" + "y" * 30, "h"])
+    check(ctx, haps, 1200, 100, True, seed=54, sep_files=True, barcodes=["ACGT", "TTGCA"])
+
+
+@pytest.mark.parametrize("L,seq_sys,paired", [(250, "MSv1", True), (250, "MSv3", False), (36, "GA1", True), (75, "NS50", True),
+                                              (50, "MinS", False), (125, "HS25", True), (150, "HSXt", True)])
+def test_other_profiles_and_read_lengths(ctx, L, seq_sys, paired):
+    g = small_genome(seed=55, n=2, length=6000)
+    check(ctx, g, 1500, L, paired, seed=56 + L, seq_sys=seq_sys, frag_mean=max(400, 2 * L), frag_sd=60,
+          ins_prob1=0.004, del_prob1=0.006, ins_prob2=0.005, del_prob2=0.003)
+
+
+def test_heavy_deletions_long_spans(ctx):
+    """deletion-heavy ends consume templates much longer than the read (span > 256 positions)"""
+    g = small_genome(seed=57, n=2, length=9000, with_n=False)
+    check(ctx, g, 1000, 100, True, seed=58, frag_mean=900, frag_sd=100, del_prob1=0.7, ins_prob1=0.05, del_prob2=0.5,
+          ins_prob2=0.3)
+
+
+def test_single_chromosome_shorter_than_read(ctx):
+    g = J.RefGenome(["tiny"], [J.random_genome(1, 40, seed=59).seqs[0]])
+    check(ctx, g, 400, 100, True, seed=60)
+    check(ctx, g, 200, 100, False, seed=61, barcodes=["ACG"])
