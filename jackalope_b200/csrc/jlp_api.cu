@@ -436,7 +436,7 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
     gp.c_rev = thr_ld_lt(0.5).thr;
     for (int e = 0; e < n_ends; e++) {
         EndDev& E = gp.end[e];
-        E.meta = c->d_meta[e].p; E.entry = c->d_entry[e].p; E.entry64 = c->d_entry64[e].p; E.coin = c->d_coin[e].p;
+        E.meta = c->d_meta[e].p; E.entry64 = c->d_entry64[e].p; E.coin = c->d_coin[e].p;
         E.mis = c->d_mis[e].p;
         E.entry_n = (uint32_t)c->tab[e].entry.size();
         Thr ta = thr_double_le(insp[e] + delp[e]);   // u > ins + del  <=>  x >= tA
@@ -996,19 +996,9 @@ void jlp_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
     out[0] = w.w0; out[1] = w.w1; out[2] = w.w2; out[3] = w.w3;
 }
 uint64_t jlp_draw_pos(uint64_t seed, uint64_t j, uint32_t end, uint32_t purpose, uint32_t pos) {
-    if (purpose == PU_INS) return slow64(seed, j, end, PU_INS, pos);
-    uint32_t H;
-    if (purpose == PU_INDEL) {
-        U4 w = draw_block(seed, j, pos >> 3, PL_INDEL, end);
-        uint32_t f = pos & 7u;
-        uint32_t v = (f >> 1) == 0 ? w.w0 : (f >> 1) == 1 ? w.w1 : (f >> 1) == 2 ? w.w2 : w.w3;
-        H = (f & 1) ? (v >> 16) : (v & 0xffffu);
-    } else {
-        U4 w = draw_block(seed, j, pos >> 1, PL_QUAL, end);
-        uint32_t a = (pos & 1) ? w.w2 : w.w0, b = (pos & 1) ? w.w3 : w.w1;
-        H = purpose == PU_DIE ? (a & 0xffffu) : purpose == PU_COIN ? (a >> 16) : purpose == PU_MIS ? (b & 0xffffu) : (b >> 16);
-    }
-    return full_draw(H, seed, j, end, purpose, pos);
+    if (high_bits(purpose) == 0) return slow64(seed, j, end, purpose, pos);
+    U4 w = purpose == PU_INDEL ? draw_block(seed, j, pos >> 3, PL_INDEL, end) : draw_block(seed, j, pos >> 1, PL_QUAL, end);
+    return full_draw(high_of(w, purpose, pos), seed, j, end, purpose, pos);
 }
 uint64_t jlp_draw_pair(uint64_t seed, uint64_t j, int which) {
     U4 w = draw_block(seed, j, (uint32_t)(which >> 1), PL_PAIR, 0);

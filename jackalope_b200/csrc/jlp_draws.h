@@ -12,13 +12,13 @@
 //                block 1 -> X_strand  = w1:w0, X_dup   = w3:w2
 //   plane INDEL: block t>>3, 16-bit field t&7      -> high 16 bits of X_indel(t)
 //   plane QUAL : block p>>1, base h = p&1:
-//                die = w[2h] & 0xffff, coin = w[2h] >> 16,
-//                mis = w[2h+1] & 0xffff, sub = w[2h+1] >> 16   (high 16 bits)
-//   plane SLOW : block pos<<3 | purpose, S = w1:w0 -> low 48 bits of X
-//                (the whole of X for purpose INS)
-//   X = H << 48 | (S & (2^48 - 1))
+//                die  = w[2h] >> 8  (high 24 bits of X_die), sub = w[2h] & 0xff (high 8 bits of X_sub)
+//                coin = w[2h+1] >> 16, mis = w[2h+1] & 0xffff   (high 16 bits)
+//   plane SLOW : block pos<<3 | purpose, S = w1:w0 -> the low bits of X: 48 (INDEL, COIN, MIS),
+//                40 (DIE), 56 (SUB); the whole of X for INS
+//   X = H << (64 - hbits) | (S & (2^(64 - hbits) - 1))
 //
-// A kernel decides on the 16 high bits alone whenever that is provably enough
+// A kernel decides on the high bits alone whenever that is provably enough
 // and fetches the SLOW plane only for the (rare) ambiguous cases, so the result
 // always equals the one a full 64-bit draw gives.
 //
@@ -105,8 +105,25 @@ JLP_HD uint64_t hi64(const U4& w) { return ((uint64_t)w.w3 << 32) | w.w2; }
 JLP_HD uint64_t slow64(uint64_t seed, uint64_t j, uint32_t end, uint32_t purpose, uint32_t pos) {
     return lo64(draw_block(seed, j, (pos << 3) | purpose, PL_SLOW, end));
 }
+// number of high bits of a draw that live outside the SLOW plane
+JLP_HD uint32_t high_bits(uint32_t purpose) {
+    return purpose == PU_DIE ? 24u : purpose == PU_SUB ? 8u : purpose == PU_INS ? 0u : 16u;
+}
 JLP_HD uint64_t full_draw(uint32_t H, uint64_t seed, uint64_t j, uint32_t end, uint32_t purpose, uint32_t pos) {
-    return ((uint64_t)H << 48) | (slow64(seed, j, end, purpose, pos) & 0xFFFFFFFFFFFFull);
+    const uint32_t hb = high_bits(purpose);
+    const uint64_t s = slow64(seed, j, end, purpose, pos);
+    if (hb == 0) return s;
+    return ((uint64_t)H << (64u - hb)) | (s & (~0ull >> hb));
+}
+// the high bits of draw (purpose, pos) out of its QUAL / INDEL block
+JLP_HD uint32_t high_of(const U4& w, uint32_t purpose, uint32_t pos) {
+    if (purpose == PU_INDEL) {
+        const uint32_t f = pos & 7u;
+        const uint32_t v = (f >> 1) == 0 ? w.w0 : (f >> 1) == 1 ? w.w1 : (f >> 1) == 2 ? w.w2 : w.w3;
+        return (f & 1u) ? (v >> 16) : (v & 0xffffu);
+    }
+    const uint32_t a = (pos & 1u) ? w.w2 : w.w0, b = (pos & 1u) ? w.w3 : w.w1;
+    return purpose == PU_DIE ? (a >> 8) : purpose == PU_SUB ? (a & 0xffu) : purpose == PU_COIN ? (b >> 16) : (b & 0xffffu);
 }
 
 // ---- exact restatements of the reference's uses of u = runif_01(x) ----

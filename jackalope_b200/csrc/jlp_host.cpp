@@ -119,7 +119,7 @@ void build_end_tables(uint64_t L, const uint32_t* nq, const double* probs, const
         uint32_t e = out.entry[k];
         uint32_t qs = (e >> 16) & 0xffu, qa = e >> 24;
         // the quality CHARACTERS (q + '!', modulo 256 as the reference's uint8 arithmetic gives)
-        uint32_t lo = (e & 0xffffu) | (((qs + 33u) & 0xffu) << 16) | (((qa + 33u) & 0xffu) << 24);
+        uint32_t lo = ((qa + 33u) & 0xffu) | (((qs + 33u) & 0xffu) << 8) | ((e & 0xffffu) << 16);
         out.entry64[k] = static_cast<uint64_t>(lo) | (static_cast<uint64_t>(out.mis16[qs]) << 32) |
                          (static_cast<uint64_t>(out.mis16[qa]) << 48);
     }

@@ -185,6 +185,9 @@ k_place(const __grid_constant__ GenParams p) {
     const uint32_t frag_cap = frag_len > 0xffffffffull ? 0xffffffffu : (uint32_t)frag_len;
     const uint32_t hA = p.end[e].hA;
     while (length_now < L && frag_pos < frag_cap) {
+        // 8 template positions per Philox block, 16 bits each: a field above the gate is a plain base.
+        // (An 8-bit gate would halve the Philox work but make a candidate -- and with it the slow path of
+        // the whole warp -- 256 times more likely; measured: 0.46 ms instead of 0.25 ms.)
         U4 w = draw_block(p.seed, j, frag_pos >> 3, PL_INDEL, e);
         bool plain = ((w.w0 & 0xffffu) > hA) & ((w.w0 >> 16) > hA) & ((w.w1 & 0xffffu) > hA) & ((w.w1 >> 16) > hA) &
                      ((w.w2 & 0xffffu) > hA) & ((w.w2 >> 16) > hA) & ((w.w3 & 0xffffu) > hA) & ((w.w3 >> 16) > hA);
@@ -312,41 +315,39 @@ __device__ __forceinline__ U4 qual_block(const GenParams& p, uint64_t j, uint32_
 // ambiguous high bits, mismatches.  Returns ascii | qualchar << 8.
 template <bool SMEM>
 __device__ __noinline__ uint32_t base_rare(const GenParams& p, uint32_t meta_a, uint32_t ent_a, uint32_t e, uint64_t j,
-                                           uint32_t pos, uint32_t code, uint32_t wa, uint32_t wb) {
+                                           uint32_t pos, uint32_t code, uint32_t die, uint32_t cm) {
     const EndDev& E = p.end[e];
-    const uint32_t Hdie = wa & 0xffffu, Hcoin = wa >> 16, Hmis = wb & 0xffffu, Hsub = wb >> 16;
+    const uint32_t Hcoin = cm >> 16, Hmis = cm & 0xffffu;
     if (code > 3) {
         // 'N' with a quality below 10 (src/hts_illumina.h:237-242)
-        uint32_t prod = Hdie * 10u;
-        uint32_t qc = (prod >> 16) + 33u;
-        if ((prod & 0xffffu) + 10u > 0xffffu) qc = nqual_x87(full_draw(Hdie, p.seed, j, e, PU_DIE, pos));
+        uint32_t qc = __umulhi(die, 10u) + 33u;
+        if (die * 10u + 2560u < 2560u) qc = nqual_x87(full_draw(die >> 8, p.seed, j, e, PU_DIE, pos));
         return 0x4Eu | ((qc & 0xffu) << 8);
     }
     uint32_t m;
     if (SMEM) m = lds32_ro(meta_a + (code * p.L + pos) * 4u);
     else m = __ldg(E.meta + code * p.L + pos);
     const uint32_t n = m & 0xffu, off = m >> 8;
-    uint32_t prod = Hdie * n;
-    uint32_t i = prod >> 16;
-    if ((prod & 0xffffu) + n > 0xffffu) {
-        uint64_t ii = mul_floor_x87(full_draw(Hdie, p.seed, j, e, PU_DIE, pos), n);
+    uint32_t i = __umulhi(die, n);
+    if (die * n + (n << 8) < (n << 8)) {     // the draw's low 40 bits can carry into the slot index
+        uint64_t ii = mul_floor_x87(full_draw(die >> 8, p.seed, j, e, PU_DIE, pos), n);
         i = ii >= n ? n - 1u : (uint32_t)ii;
     }
     uint2 ent;
     if (SMEM) ent = lds64_ro(ent_a + (off + i) * 8u);
     else ent = __ldg(reinterpret_cast<const uint2*>(E.entry64) + off + i);
-    const uint32_t thr = ent.x & 0xffffu;
+    const uint32_t thr = ent.x >> 16;
     bool self = Hcoin < thr;
     if (Hcoin == thr) self = full_draw(Hcoin, p.seed, j, e, PU_COIN, pos) < E.coin[off + i];
-    const uint32_t qc = self ? ((ent.x >> 16) & 0xffu) : (ent.x >> 24);          // quality character
+    const uint32_t qc = self ? ((ent.x >> 8) & 0xffu) : (ent.x & 0xffu);          // quality character
     const uint32_t mt = self ? (ent.y & 0xffffu) : (ent.y >> 16);
     bool mism = Hmis < mt;
     if (Hmis == mt) mism = full_draw(Hmis, p.seed, j, e, PU_MIS, pos) < E.mis[(qc - 33u) & 0xffu];
     if (mism) {
         // mm_nucleos[nt][(uint64)(u * 3)] (src/hts.h:46): the si-th code other than `code`
-        uint32_t p3 = Hsub * 3u;
-        uint32_t si = p3 >> 16;
-        if ((p3 & 0xffffu) + 3u > 0xffffu) {
+        const uint32_t Hsub = die & 0xffu, p3 = Hsub * 3u;
+        uint32_t si = p3 >> 8;
+        if ((p3 & 0xffu) + 3u > 0xffu) {
             uint64_t s3 = mul_floor_x87(full_draw(Hsub, p.seed, j, e, PU_SUB, pos), 3);
             si = s3 > 2 ? 2u : (uint32_t)s3;
         }
@@ -363,20 +364,23 @@ __device__ __noinline__ uint32_t base_rare(const GenParams& p, uint32_t meta_a, 
 // decide instead (ambiguous high bits or a mismatch).
 template <bool SMEM>
 __device__ __forceinline__ void base_fast(const GenParams& p, uint32_t meta_a, uint32_t ent_a, uint32_t e, uint32_t pos,
-                                          uint32_t ct, uint32_t wa, uint32_t wb, uint32_t& entx, bool& self, bool& rare) {
+                                          uint32_t ct, uint32_t die, uint32_t cm, uint32_t& entx, bool& self, bool& rare) {
     uint32_t m;
     if (SMEM) m = lds32_ro(meta_a + (ct * p.L + pos) * 4u);
     else m = __ldg(p.end[e].meta + ct * p.L + pos);
     const uint32_t n = m & 0xffu;
-    const uint32_t prod = (wa & 0xffffu) * n;
-    const uint32_t slot = (m >> 8) + (prod >> 16);
+    const uint32_t lo = die * n;                              // die * n / 2^32 is the alias slot (die: 24 bits of X_die, then 8 of X_sub) ...
+    const uint32_t slot = (m >> 8) + __umulhi(die, n);
     uint2 ent;
     if (SMEM) ent = lds64_ro(ent_a + slot * 8u);
     else ent = __ldg(reinterpret_cast<const uint2*>(p.end[e].entry64) + slot);
-    const uint32_t thr = ent.x & 0xffffu, Hcoin = wa >> 16;
-    self = Hcoin < thr;
+    // coin: high half of cm against the threshold in the high half of the entry, compared in place
+    const uint32_t thr_hi = ent.x & 0xffff0000u;
+    self = cm < thr_hi;
     const uint32_t mt = self ? (ent.y & 0xffffu) : (ent.y >> 16);    // high 16 bits of the quality's mismatch threshold
-    rare = ((((prod + n) ^ prod) & 0x10000u) != 0u) || (Hcoin == thr) || ((wb & 0xffffu) <= mt);
+    // ... unless the draw's low 40 bits could carry into it; coin and mismatch are undecided when their
+    // 16 high bits equal the threshold's; a mismatch itself is handled by the exact path too
+    rare = (lo + (n << 8) < (n << 8)) || (cm - thr_hi < 0x10000u) || ((cm & 0xffffu) <= mt);
     entx = ent.x;
 }
 
@@ -681,7 +685,7 @@ k_reads(const __grid_constant__ GenParams p) {
                 base_fast<SMEM>(p, meta_a, ent_a, e, pos, ct0, w.w0, w.w1, x0, self0, rare0);
                 base_fast<SMEM>(p, meta_a, ent_a, e, pos1, ct1, w.w2, w.w3, x1, self1, rare1);
                 // both quality characters with one byte permute, both letters with another
-                uint32_t qq = __byte_perm(x0, x1, (self0 ? 2u : 3u) | (self1 ? 0x60u : 0x70u));
+                uint32_t qq = __byte_perm(x0, x1, (self0 ? 1u : 0u) | (self1 ? 0x50u : 0x40u));
                 uint32_t asc = __byte_perm(0x47414354u, 0u, ct0 | (ct1 << 4));
                 if (rare0 || rare1 || (c0 | c1) > 3u) {
                     if (rare0 || c0 > 3u) {

@@ -36,12 +36,11 @@ constexpr uint32_t kPlanReverse = 1, kPlanIndels = 2, kPlanBarcode = 4, kPlanLon
 
 struct EndDev {
     const uint32_t* meta;    // [4*L] offset << 8 | n
-    const uint64_t* entry64; // coin16 | (q_self + 33) << 16 | (q_alias + 33) << 24 | mis16[q_self] << 32 | mis16[q_alias] << 48
-    const uint32_t* entry;   // low half of entry64 (slow path)
+    const uint64_t* entry64; // low word: (q_alias + 33) | (q_self + 33) << 8 | coin16 << 16; high word: mis16[q_self] | mis16[q_alias] << 16
     const uint64_t* coin;    // full thresholds (slow path)
     const uint64_t* mis;     // [256] full mismatch thresholds (slow path)
     uint32_t entry_n;
-    uint32_t hA;             // high-16 gate of the indel draw (0x10000 = always slow)
+    uint32_t hA;             // high-16 gate of the indel draw: a field > hA is a plain base (0x10000 = never)
     uint64_t tA, tI;         // x >= tA: plain base; else x >= tI: deletion; else insertion
     uint32_t tA_all, tI_all; // threshold is 2^64 (never reached)
 };

@@ -76,26 +76,26 @@ static uint64_t slow64(uint64_t seed, uint64_t j, uint32_t end, uint32_t purpose
     return ((uint64_t)w[1] << 32) | w[0];
 }
 
-/* per-end, per-position draws */
+/* per-end, per-position draws (layout: jackalope_b200/csrc/jlp_draws.h) */
 uint64_t orc_draw_pos(uint64_t seed, uint64_t j, uint32_t end, uint32_t purpose, uint32_t pos) {
     uint32_t w[4];
-    uint64_t H;
-    if (purpose == PU_INS) return slow64(seed, j, end, purpose, pos);
+    uint64_t H, s = slow64(seed, j, end, purpose, pos);
+    uint32_t hb;
+    if (purpose == PU_INS) return s;
     if (purpose == PU_INDEL) {
         call(seed, j, pos >> 3, PL_INDEL, end, w);
         uint32_t f = pos & 7;
         H = (w[f >> 1] >> (16 * (f & 1))) & 0xffffu;
+        hb = 16;
     } else {
         call(seed, j, pos >> 1, PL_QUAL, end, w);
         uint32_t h = pos & 1;
-        switch (purpose) {
-        case PU_DIE:  H = w[2 * h] & 0xffffu; break;
-        case PU_COIN: H = w[2 * h] >> 16; break;
-        case PU_MIS:  H = w[2 * h + 1] & 0xffffu; break;
-        default:      H = w[2 * h + 1] >> 16; break; /* PU_SUB */
-        }
+        if (purpose == PU_DIE) { H = w[2 * h] >> 8; hb = 24; }
+        else if (purpose == PU_SUB) { H = w[2 * h] & 0xffu; hb = 8; }
+        else if (purpose == PU_COIN) { H = w[2 * h + 1] >> 16; hb = 16; }
+        else { H = w[2 * h + 1] & 0xffffu; hb = 16; }   /* PU_MIS */
     }
-    return (H << 48) | (slow64(seed, j, end, purpose, pos) & 0xFFFFFFFFFFFFull);
+    return (H << (64 - hb)) | (s & (~0ull >> hb));
 }
 
 /* -------------------------------------------------- reference primitives */

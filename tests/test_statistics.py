@@ -59,7 +59,10 @@ def summarize(r1, r2, genome, L):
                 clean = False
                 continue
             d = x != y
-            if d.sum() > 12:                     # an indel shifted the read against its template
+            if d.sum() > 4:                      # an indel shifted the read against its template (true
+                                                 # substitutions average ~0.5 per read); a looser cut lets
+                                                 # shifted reads in, whose clustered mismatches break the
+                                                 # independence the chi-square tests assume
                 out["indel_reads"][e] += 1
                 clean = False
                 continue
