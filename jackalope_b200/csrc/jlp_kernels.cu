@@ -537,7 +537,9 @@ k_reads(const __grid_constant__ GenParams p) {
         }
         __syncthreads();
     }
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    uint32_t lane;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));      // kept in a register (the compiler would re-read SR_TID)
+    const uint32_t warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     const uint32_t n_ends = p.n_ends;
     // this warp's shared memory: 32 bytes of scratch, a ring of three plan slots (both ends'
     // EndPlan records of one pair), a ring of two template slots (the bytes around each end's
@@ -576,15 +578,17 @@ k_reads(const __grid_constant__ GenParams p) {
         cp_async_commit();
     }
 
-    uint32_t k = 0;
-    for (uint32_t i = i0; i < p.batch_pairs; i += stride, k++) {
+    uint32_t ps = 0, ts = 0;             // ring positions of the current pair's plan (mod 3) and templates (mod 2)
+    for (uint32_t i = i0; i < p.batch_pairs; i += stride) {
         const uint64_t j = p.batch_lo + i;
+        const uint32_t ps1 = ps == 2u ? 0u : ps + 1u, ps2 = ps1 == 2u ? 0u : ps1 + 1u;
         cp_async_wait_all();
         __syncwarp();
-        if (i + 2u * stride < p.batch_pairs) stage_plan((k + 2u) % 3u, i + 2u * stride);
-        if (i + stride < p.batch_pairs) stage_tpl((k + 1u) & 1u, (k + 1u) % 3u);
+        if (i + 2u * stride < p.batch_pairs) stage_plan(ps2, i + 2u * stride);
+        if (i + stride < p.batch_pairs) stage_tpl(ts ^ 1u, ps1);
         cp_async_commit();
-        const uint32_t PL = PL0 + (k % 3u) * 192u, TP = TP0 + (k & 1u) * 2u * tplw;
+        const uint32_t PL = PL0 + ps * 192u, TP = TP0 + ts * 2u * tplw;
+        ps = ps1; ts ^= 1u;
 
         // ---- phase A: ID line and template base codes into the record buffers, all from shared
         //      memory.  The two ends are handled side by side, one half-warp each (lane >> 4 is the
