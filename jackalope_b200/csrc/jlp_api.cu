@@ -211,7 +211,8 @@ struct jlp_ctx {
     WriterPool writers;
     cudaStream_t s_upload = nullptr;            // genome H2D, chromosome by chromosome
     std::vector<cudaEvent_t> chrom_ev;          // chromosome c is resident once chrom_ev[c] has fired
-    bool upload_pending = false;
+    bool upload_pending = false;                // copies issued (or still to be issued), not yet waited for
+    const char* upload_src = nullptr;           // host bases of a deferred upload (jlp_set_genome_async), else NULL
     cudaEvent_t ev_run[2] = {nullptr, nullptr};
     uint64_t h2d_bytes = 0;
 };
@@ -240,6 +241,26 @@ template <typename F> int guarded(jlp_ctx* c, F f) {
     } catch (const Unsupported& e) { return fail(c, JLP_ERR_UNSUPPORTED, e.what());
     } catch (const Aborted& e) { return fail(c, JLP_ERR_ABORTED, e.what());
     } catch (const std::exception& e) { return fail(c, JLP_ERR_ARG, e.what()); }
+}
+
+// Issue the per-chromosome H2D copies of a deferred genome upload, starting with chromosome
+// `first` (the first one the caller is going to read) and wrapping around.
+void issue_upload(jlp_ctx* c, size_t first) {
+    if (!c->upload_src) return;
+    const size_t n = c->chrom_off.size() - 1;
+    for (size_t k = 0; k < n; k++) {
+        const size_t i = (first + k) % n;
+        const uint64_t len = c->chrom_off[i + 1] - c->chrom_off[i];
+        if (len) CK(cudaMemcpyAsync(c->genome.p + kPad + c->chrom_off[i], c->upload_src + c->chrom_off[i], len, cudaMemcpyHostToDevice, c->s_upload));
+        CK(cudaEventRecord(c->chrom_ev[i], c->s_upload));
+    }
+    c->upload_src = nullptr;
+}
+void finish_upload(jlp_ctx* c) {
+    if (!c->upload_pending) return;
+    issue_upload(c, 0);
+    CK(cudaStreamSynchronize(c->s_upload));
+    c->upload_pending = false;
 }
 
 // ---------------------------------------------------------------- the run ---
@@ -337,7 +358,7 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
     // --- argument checks the C++ layer of the reference performs
     if (c->chrom_off.size() < 2) throw ArgErr("no reference genome has been set");
     if (use_haps && c->haps.empty()) throw ArgErr("no haplotypes have been added");
-    if (use_haps && c->upload_pending) { CK(cudaStreamSynchronize(c->s_upload)); c->upload_pending = false; }
+    if (use_haps) finish_upload(c);
     if (!c->have_prof[0]) throw ArgErr("no quality profile for read 1");
     if (n_ends == 2) {
         if (!c->have_prof[1]) throw ArgErr("no quality profile for read 2");
@@ -575,7 +596,7 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
         s.busy = false;
     };
 
-    size_t next_chrom_wait = 0;
+    std::vector<char> chrom_waited(c->chrom_ev.size(), 0);
     const uint32_t S = P->shard_count > 1 ? P->shard_count : 1;
     const uint32_t si = P->shard_count > 1 ? P->shard_index : 0;
     if (si >= S) throw ArgErr("shard_index >= shard_count");
@@ -607,12 +628,18 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
             while (s.busy) drain_one();
             const uint32_t np = (uint32_t)std::min<uint64_t>(B, hi - b0);
             if (c->upload_pending && !use_haps) {
-                // the batch reads the chromosomes of its pairs (and of earlier ones, through duplicate
-                // leaders): wait for the upload of the last one it can touch
+                // the batch reads the chromosomes of its pairs, and through a duplicate chain's leader
+                // possibly the one before: make the compute stream wait for exactly those uploads (a
+                // deferred upload is issued now, starting with the first chromosome this shard reads)
+                // (a leader lies at most pool_pairs - 1 pairs before its duplicate, never before the job's start)
+                const uint64_t first_pair = b0 - std::min<uint64_t>(b0 - job.lo, gp.pool_pairs - 1);
+                size_t g_lo = (size_t)(std::upper_bound(group_off.begin(), group_off.end(), first_pair) - group_off.begin()) - 1;
                 size_t g_hi = (size_t)(std::upper_bound(group_off.begin(), group_off.end(), b0 + np - 1) - group_off.begin()) - 1;
                 g_hi = std::min(g_hi, c->chrom_ev.size() - 1);
-                for (; next_chrom_wait <= g_hi; next_chrom_wait++)
-                    CK(cudaStreamWaitEvent(c->s_compute, c->chrom_ev[next_chrom_wait], 0));
+                g_lo = std::min(g_lo, g_hi);
+                issue_upload(c, g_lo);
+                for (size_t g = g_lo; g <= g_hi; g++)
+                    if (!chrom_waited[g]) { CK(cudaStreamWaitEvent(c->s_compute, c->chrom_ev[g], 0)); chrom_waited[g] = 1; }
             }
             gp.job_lo = job.lo; gp.job_hi = job.hi; gp.batch_lo = b0; gp.batch_pairs = np;
             const uint32_t n_rec = np * n_ends;
@@ -660,7 +687,7 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
         st.run_ms = ms;
     }
     sink.close_files();
-    if (c->upload_pending) { CK(cudaStreamSynchronize(c->s_upload)); c->upload_pending = false; }
+    finish_upload(c);
     uint32_t status = 0;
     CK(cudaMemcpy(&status, c->d_status.p, sizeof status, cudaMemcpyDeviceToHost));
     if (status & 1u) throw ArgErr("a barcode is at least as long as a read's template (fragment or chromosome too short)");
@@ -722,7 +749,11 @@ static int set_genome_impl(jlp_ctx* c, const char* bases, const uint64_t* chrom_
         for (uint64_t i = 0; i < n_chroms; i++)
             if (chrom_off[i + 1] < chrom_off[i]) throw ArgErr("chrom_off must be non-decreasing");
         if (chrom_off[0] != 0) throw ArgErr("chrom_off[0] must be 0");
-        if (c->upload_pending) { CK(cudaStreamSynchronize(c->s_upload)); c->upload_pending = false; }
+        if (c->upload_pending) {      // a deferred upload that never ran is simply dropped
+            c->upload_src = nullptr;
+            CK(cudaStreamSynchronize(c->s_upload));
+            c->upload_pending = false;
+        }
         free_haps(c);
         c->chrom_off.assign(chrom_off, chrom_off + n_chroms + 1);
         c->chrom_names.clear();
@@ -737,15 +768,12 @@ static int set_genome_impl(jlp_ctx* c, const char* bases, const uint64_t* chrom_
         }
         // one copy and one event per chromosome: generation starts as soon as the chromosomes a batch
         // reads are resident, the rest of the genome follows underneath (PCIe is full duplex, the
-        // FASTQ flows the other way)
-        for (uint64_t i = 0; i < n_chroms; i++) {
-            const uint64_t n = chrom_off[i + 1] - chrom_off[i];
-            if (n) CK(cudaMemcpyAsync(c->genome.p + kPad + chrom_off[i], bases + chrom_off[i], n, cudaMemcpyHostToDevice, c->s_upload));
-            CK(cudaEventRecord(c->chrom_ev[i], c->s_upload));
-        }
+        // FASTQ flows the other way).  The asynchronous form defers the copies to the next run, which
+        // starts them at the first chromosome its shard reads.
+        c->upload_src = bases;
         c->upload_pending = true;
         c->h2d_bytes += total;
-        if (wait) { CK(cudaStreamSynchronize(c->s_upload)); c->upload_pending = false; }
+        if (wait) finish_upload(c);
     });
 }
 
@@ -762,7 +790,7 @@ int jlp_set_genome_async(jlp_ctx* c, const char* bases, const uint64_t* chrom_of
 int jlp_genome_sync(jlp_ctx* c) {
     if (!c) return JLP_ERR_ARG;
     return guarded(c, [&]() {
-        if (c->upload_pending) { CK(cudaStreamSynchronize(c->s_upload)); c->upload_pending = false; }
+        finish_upload(c);
     });
 }
 
@@ -779,7 +807,7 @@ int jlp_add_haplotype(jlp_ctx* c, const char* name, const uint64_t* n_muts, cons
     return guarded(c, [&]() {
         if (c->chrom_off.size() < 2) throw ArgErr("set the reference genome first");
         if (!n_muts || !chrom_sizes) throw ArgErr("n_muts / chrom_sizes is NULL");
-        if (c->upload_pending) { CK(cudaStreamSynchronize(c->s_upload)); c->upload_pending = false; }
+        finish_upload(c);
         const uint64_t nc = c->chrom_off.size() - 1;
         HapDev H;
         H.name = name ? name : "";
