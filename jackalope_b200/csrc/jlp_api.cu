@@ -198,7 +198,7 @@ struct jlp_ctx {
     // profiles
     EndTables tab[2];
     bool have_prof[2] = {false, false};
-    DevBuf<uint32_t> d_meta[2], d_entry[2];
+    DevBuf<uint32_t> d_meta[2];
     DevBuf<uint64_t> d_coin[2], d_mis[2], d_entry64[2];
     int n_sm = 148;
     // run-scoped device data
@@ -290,16 +290,6 @@ struct Job {
     std::string file_prefix;  // <prefix> or <prefix>_<hap>
 };
 
-void write_all(int fd, const uint8_t* p, uint64_t n, const std::string& name) {
-    while (n) {
-        ssize_t w = ::write(fd, p, n > (1u << 30) ? (1u << 30) : n);
-        if (w < 0) {
-            if (errno == EINTR) continue;
-            throw IoErr("Error writing to file " + name + ": " + std::strerror(errno));
-        }
-        p += w; n -= (uint64_t)w;
-    }
-}
 
 // Contiguous, near-equal split of a job's pair-index range over shards (the even split of
 // split_int, src/util.h:245-258, applied to GPUs instead of threads).
@@ -459,7 +449,7 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
         EndDev& E = gp.end[e];
         E.meta = c->d_meta[e].p; E.entry64 = c->d_entry64[e].p; E.coin = c->d_coin[e].p;
         E.mis = c->d_mis[e].p;
-        E.entry_n = (uint32_t)c->tab[e].entry.size();
+        E.entry_n = (uint32_t)c->tab[e].entry64.size();
         Thr ta = thr_double_le(insp[e] + delp[e]);   // u > ins + del  <=>  x >= tA
         Thr ti = thr_double_le(insp[e]);             // u > ins        <=>  x >= tI
         E.tA = ta.thr; E.tA_all = ta.all; E.tI = ti.thr; E.tI_all = ti.all;
@@ -876,12 +866,11 @@ int jlp_set_profile(jlp_ctx* c, int end, uint64_t read_length, const uint32_t* n
         build_end_tables(read_length, nq, probs, quals, c->tab[end]);
         const EndTables& t = c->tab[end];
         c->d_meta[end].upload(t.meta, c->s_compute);
-        c->d_entry[end].upload(t.entry, c->s_compute);
         c->d_entry64[end].upload(t.entry64, c->s_compute);
         c->d_coin[end].upload(t.coin, c->s_compute);
         c->d_mis[end].upload(t.mis, c->s_compute);
         CK(cudaStreamSynchronize(c->s_compute));
-        c->h2d_bytes += t.meta.size() * 4 + t.entry.size() * 20 + 256 * 8;
+        c->h2d_bytes += t.meta.size() * 4 + t.entry64.size() * 16 + 256 * 8;
         c->have_prof[end] = true;
     });
 }

@@ -81,7 +81,7 @@ void build_end_tables(uint64_t L, const uint32_t* nq, const double* probs, const
         tot += nq[i];
     }
     if (tot >= (1ull << 24)) throw std::runtime_error("profile too large");
-    out.entry.resize(tot);
+    std::vector<uint32_t> entry(tot);          // coin16 | q_self << 16 | q_alias << 24
     out.coin.resize(tot);
     unsigned max_qual = 0;
     std::vector<double> Prob;
@@ -99,7 +99,7 @@ void build_end_tables(uint64_t L, const uint32_t* nq, const double* probs, const
             uint64_t c = t.thr;                          // never `all`: Prob <= 1 and u == 1 exists
             out.coin[off + k] = c;
             uint32_t q_self = quals[off + k], q_alias = quals[off + Alias[k]];
-            out.entry[off + k] = static_cast<uint32_t>(c >> 48) | (q_self << 16) | (q_alias << 24);
+            entry[off + k] = static_cast<uint32_t>(c >> 48) | (q_self << 16) | (q_alias << 24);
             if (q_self > max_qual) max_qual = q_self;
         }
         off += n;
@@ -107,21 +107,21 @@ void build_end_tables(uint64_t L, const uint32_t* nq, const double* probs, const
     // qual_prob_map, src/hts_illumina.h:182-187.  Entries above max_qual do not
     // exist in the reference; they are never indexed.
     out.mis.assign(256, 0);
-    out.mis16.assign(256, 0);
+    std::vector<uint16_t> mis16(256, 0);       // high 16 bits of the mismatch threshold per quality
     for (unsigned q = 0; q <= max_qual; q++) {
         double prob = q == 0 ? 1.0 : std::pow(10, static_cast<double>(q) / -10.0);
         Thr t = thr_double_lt(prob);
         out.mis[q] = t.thr;
-        out.mis16[q] = static_cast<uint16_t>(t.thr >> 48);
+        mis16[q] = static_cast<uint16_t>(t.thr >> 48);
     }
     out.entry64.resize(tot);
     for (uint64_t k = 0; k < tot; k++) {
-        uint32_t e = out.entry[k];
+        uint32_t e = entry[k];
         uint32_t qs = (e >> 16) & 0xffu, qa = e >> 24;
         // the quality CHARACTERS (q + '!', modulo 256 as the reference's uint8 arithmetic gives)
         uint32_t lo = ((qa + 33u) & 0xffu) | (((qs + 33u) & 0xffu) << 8) | ((e & 0xffffu) << 16);
-        out.entry64[k] = static_cast<uint64_t>(lo) | (static_cast<uint64_t>(out.mis16[qs]) << 32) |
-                         (static_cast<uint64_t>(out.mis16[qa]) << 48);
+        out.entry64[k] = static_cast<uint64_t>(lo) | (static_cast<uint64_t>(mis16[qs]) << 32) |
+                         (static_cast<uint64_t>(mis16[qa]) << 48);
     }
 }
 

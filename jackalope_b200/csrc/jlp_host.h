@@ -34,10 +34,8 @@ void alias_build(const double* probs, uint64_t n, double* Prob, uint64_t* Alias)
 struct EndTables {
     uint64_t L = 0;
     std::vector<uint32_t> meta;     // [4*L]  offset << 8 | n
-    std::vector<uint32_t> entry;    // per table slot: coin16 | q_self << 16 | q_alias << 24
     std::vector<uint64_t> entry64;  // (q_alias+33) | (q_self+33) << 8 | coin16 << 16 | mis16[q_self] << 32 | mis16[q_alias] << 48
     std::vector<uint64_t> coin;     // full coin threshold per slot (slow path)
-    std::vector<uint16_t> mis16;    // [256] high 16 bits of the mismatch threshold per quality
     std::vector<uint64_t> mis;      // [256] full mismatch threshold per quality
     uint32_t max_n = 0;
 };

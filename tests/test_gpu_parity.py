@@ -236,3 +236,21 @@ def test_single_chromosome_shorter_than_read(ctx):
     g = J.RefGenome(["tiny"], [J.random_genome(1, 40, seed=59).seqs[0]])
     check(ctx, g, 400, 100, True, seed=60)
     check(ctx, g, 200, 100, False, seed=61, barcodes=["ACG"])
+
+
+def test_degenerate_counts(ctx, tmp_path):
+    """an odd n_reads is floored to whole pairs (src/hts.h:334-336); zero pairs give empty files; a haplotype
+    with probability 0 gets empty files of its own with sep_files"""
+    g = small_genome(seed=71, with_n=False)
+    pre = str(tmp_path / "d")
+    J.illumina(g, pre, 1, 100, True, seed=72, ctx=ctx)
+    assert open(pre + "_R1.fq", "rb").read() == b"" and open(pre + "_R2.fq", "rb").read() == b""
+    r1, r2, st = J.illumina(g, "", 7, 100, True, seed=73, ctx=ctx, sink="memory")
+    assert len(fastq_records(r1)) == len(fastq_records(r2)) == 3 and st["pairs"] == 3
+    check(ctx, g, 7, 100, True, seed=73)
+    check(ctx, g, 1, 100, False, seed=74)
+    haps = J.random_haplotypes(g, 3, seed=75)
+    J.illumina(haps, pre, 600, 100, True, seed=76, ctx=ctx, sep_files=True, haplotype_probs=[1, 0, 1], overwrite=True)
+    assert open("%s_hap1_R1.fq" % pre, "rb").read() == b""
+    assert open("%s_hap0_R1.fq" % pre, "rb").read().count(b"\n") + open("%s_hap2_R1.fq" % pre, "rb").read().count(b"\n") == 4 * 300
+    check(ctx, haps, 600, 100, True, seed=76, sep_files=True, haplotype_probs=[1, 0, 1])
