@@ -51,11 +51,13 @@ const char* jlp_last_error(const jlp_ctx* ctx);
 int jlp_set_genome(jlp_ctx* ctx, const char* bases, const uint64_t* chrom_off, uint64_t n_chroms,
                    const char* const* chrom_names, const char* genome_name);
 
-/* The same upload without waiting for it: one H2D copy per chromosome on its own
- * stream.  A following jlp_illumina_* call on the reference genome starts generating
- * as soon as the chromosomes its first batch reads are resident and waits for the
- * whole upload before it returns; `bases` must stay valid until then (or until
- * jlp_genome_sync).  Haplotype calls wait for the whole genome first. */
+/* The same upload, deferred: nothing is copied yet.  A following jlp_illumina_* call on
+ * the reference genome copies, chromosome by chromosome on its own stream, the
+ * chromosomes its shard of the job reads (all of them for an unsharded job, about 1/N
+ * with N shards), starts generating as soon as the first batch's are resident and waits
+ * for its copies before it returns.  Chromosomes no run has read stay on the host, so
+ * `bases` must stay valid until jlp_genome_sync() (which uploads the rest) or until the
+ * genome is replaced.  Haplotype calls upload the whole genome first. */
 int jlp_set_genome_async(jlp_ctx* ctx, const char* bases, const uint64_t* chrom_off, uint64_t n_chroms,
                          const char* const* chrom_names, const char* genome_name);
 int jlp_genome_sync(jlp_ctx* ctx);

@@ -211,8 +211,9 @@ struct jlp_ctx {
     WriterPool writers;
     cudaStream_t s_upload = nullptr;            // genome H2D, chromosome by chromosome
     std::vector<cudaEvent_t> chrom_ev;          // chromosome c is resident once chrom_ev[c] has fired
-    bool upload_pending = false;                // copies issued (or still to be issued), not yet waited for
+    bool upload_pending = false;                // some chromosome is not resident yet (or its copy not waited for)
     const char* upload_src = nullptr;           // host bases of a deferred upload (jlp_set_genome_async), else NULL
+    std::vector<char> chrom_resident;           // 1: the chromosome's H2D copy has been issued
     cudaEvent_t ev_run[2] = {nullptr, nullptr};
     uint64_t h2d_bytes = 0;
 };
@@ -243,24 +244,26 @@ template <typename F> int guarded(jlp_ctx* c, F f) {
     } catch (const std::exception& e) { return fail(c, JLP_ERR_ARG, e.what()); }
 }
 
-// Issue the per-chromosome H2D copies of a deferred genome upload, starting with chromosome
-// `first` (the first one the caller is going to read) and wrapping around.
-void issue_upload(jlp_ctx* c, size_t first) {
+// Issue the H2D copies of chromosomes [first, last] of a deferred genome upload (those not
+// issued yet); every copy is followed by its chromosome's event.
+void issue_upload(jlp_ctx* c, size_t first, size_t last) {
     if (!c->upload_src) return;
-    const size_t n = c->chrom_off.size() - 1;
-    for (size_t k = 0; k < n; k++) {
-        const size_t i = (first + k) % n;
+    for (size_t i = first; i <= last && i < c->chrom_resident.size(); i++) {
+        if (c->chrom_resident[i]) continue;
         const uint64_t len = c->chrom_off[i + 1] - c->chrom_off[i];
         if (len) CK(cudaMemcpyAsync(c->genome.p + kPad + c->chrom_off[i], c->upload_src + c->chrom_off[i], len, cudaMemcpyHostToDevice, c->s_upload));
         CK(cudaEventRecord(c->chrom_ev[i], c->s_upload));
+        c->chrom_resident[i] = 1;
+        c->h2d_bytes += len;
     }
-    c->upload_src = nullptr;
 }
+// Make the whole genome resident and wait for it.
 void finish_upload(jlp_ctx* c) {
     if (!c->upload_pending) return;
-    issue_upload(c, 0);
+    if (!c->chrom_resident.empty()) issue_upload(c, 0, c->chrom_resident.size() - 1);
     CK(cudaStreamSynchronize(c->s_upload));
     c->upload_pending = false;
+    c->upload_src = nullptr;
 }
 
 // ---------------------------------------------------------------- the run ---
@@ -619,15 +622,21 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
             const uint32_t np = (uint32_t)std::min<uint64_t>(B, hi - b0);
             if (c->upload_pending && !use_haps) {
                 // the batch reads the chromosomes of its pairs, and through a duplicate chain's leader
-                // possibly the one before: make the compute stream wait for exactly those uploads (a
-                // deferred upload is issued now, starting with the first chromosome this shard reads)
+                // possibly the one before: make the compute stream wait for exactly those uploads
                 // (a leader lies at most pool_pairs - 1 pairs before its duplicate, never before the job's start)
                 const uint64_t first_pair = b0 - std::min<uint64_t>(b0 - job.lo, gp.pool_pairs - 1);
                 size_t g_lo = (size_t)(std::upper_bound(group_off.begin(), group_off.end(), first_pair) - group_off.begin()) - 1;
                 size_t g_hi = (size_t)(std::upper_bound(group_off.begin(), group_off.end(), b0 + np - 1) - group_off.begin()) - 1;
                 g_hi = std::min(g_hi, c->chrom_ev.size() - 1);
                 g_lo = std::min(g_lo, g_hi);
-                issue_upload(c, g_lo);
+                if (b0 == lo) {
+                    // first batch of this shard of the job: a deferred upload copies, in the order the shard
+                    // will read them, all the chromosomes the shard reads and nothing else (with N GPUs each
+                    // needs about 1/N of the genome); the rest stays on the host until some run asks for it
+                    size_t g_end = (size_t)(std::upper_bound(group_off.begin(), group_off.end(), hi - 1) - group_off.begin()) - 1;
+                    issue_upload(c, g_lo, std::min(g_end, c->chrom_ev.size() - 1));
+                }
+                issue_upload(c, g_lo, g_hi);
                 for (size_t g = g_lo; g <= g_hi; g++)
                     if (!chrom_waited[g]) { CK(cudaStreamWaitEvent(c->s_compute, c->chrom_ev[g], 0)); chrom_waited[g] = 1; }
             }
@@ -677,7 +686,15 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
         st.run_ms = ms;
     }
     sink.close_files();
-    finish_upload(c);
+    if (c->upload_pending) {
+        // the copies this run issued are done before the caller gets control back; chromosomes no
+        // shard of this run touched remain on the host (upload_src must stay valid, see the header)
+        CK(cudaStreamSynchronize(c->s_upload));
+        if (std::find(c->chrom_resident.begin(), c->chrom_resident.end(), 0) == c->chrom_resident.end()) {
+            c->upload_pending = false;
+            c->upload_src = nullptr;
+        }
+    }
     uint32_t status = 0;
     CK(cudaMemcpy(&status, c->d_status.p, sizeof status, cudaMemcpyDeviceToHost));
     if (status & 1u) throw ArgErr("a barcode is at least as long as a read's template (fragment or chromosome too short)");
@@ -762,7 +779,7 @@ static int set_genome_impl(jlp_ctx* c, const char* bases, const uint64_t* chrom_
         // starts them at the first chromosome its shard reads.
         c->upload_src = bases;
         c->upload_pending = true;
-        c->h2d_bytes += total;
+        c->chrom_resident.assign(n_chroms, 0);
         if (wait) finish_upload(c);
     });
 }
