@@ -6,7 +6,8 @@
 // include path.  The two exported signatures -- and therefore R/RcppExports.R:96-107,
 // src/RcppExports.cpp:111-175 and the R function illumina() -- stay exactly as they are.
 // R, Rcpp and the package's build chain are absent from the image this repository was
-// built in, so this file has not been compiled there; the same sequence of C-ABI calls is
+// built in, so this file has only been type-checked there (g++ -fsyntax-only against the package's own
+// ref_classes.h / hap_classes.h and the stub Rcpp headers of oracle/stubs); the same sequence of C-ABI calls is
 // what jackalope_b200/illumina.py performs through ctypes and what the test-suite runs.
 //
 // Only jackalope's own types are read, through const access, as the original code does
@@ -97,7 +98,7 @@ int abort_cb(void* prog) { return static_cast<Progress*>(prog)->check_abort() ? 
 void progress_cb(void* prog, uint64_t reads) { static_cast<Progress*>(prog)->increment(reads); }  // src/hts.h:414
 
 uint64_t seed_from_r() {           // as mt_seeds does: 32-bit values from R's RNG, so set.seed() governs the run (src/pcg.h:37-46)
-    NumericVector s = Rcpp::runif(2, 0, 4294967296.0);
+    std::vector<uint64> s = as<std::vector<uint64>>(Rcpp::runif(2, 0, 4294967296.0));
     return (static_cast<uint64_t>(s[0]) << 32) | static_cast<uint64_t>(s[1]);
 }
 

@@ -334,3 +334,17 @@ def test_oracle_pair_geometry_known_answers():
             assert {x[1] for x in recs} == want
             assert all(x[0].split(b"-")[2] in (b"0", b"100") for x in recs)
     assert g.n_chroms() == 1
+
+
+def test_rcpp_glue_type_checks_against_the_reference_headers():
+    """integration/hts_illumina_b200.cpp cannot be built without R, but it must at least compile
+    (syntax only) against jackalope's own ref_classes.h / hap_classes.h with the stub Rcpp headers."""
+    import shutil
+    import subprocess
+    if not os.path.isdir(REF) or shutil.which("g++") is None:
+        pytest.skip("/root/reference or g++ absent")
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-w", "-I" + os.path.join(ROOT, "oracle", "stubs"),
+                        "-I" + os.path.join(REF, "inst", "include"), "-I" + os.path.join(REF, "src"),
+                        "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "integration", "hts_illumina_b200.cpp")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[:2000]
