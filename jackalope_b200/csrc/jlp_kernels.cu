@@ -31,14 +31,26 @@ k_materialize(const uint8_t* __restrict__ ref, uint64_t ref_size, uint64_t n_mut
               const uint64_t* __restrict__ old_pos, const uint64_t* __restrict__ new_pos,
               const int64_t* __restrict__ size_mod, const uint64_t* __restrict__ nuc_off,
               const uint8_t* __restrict__ pool, uint64_t chrom_size, uint8_t* __restrict__ out) {
-    uint64_t p0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
-    if (p0 >= chrom_size) return;
-    int64_t lo = -1, hi = (int64_t)n_muts;
+    const uint64_t p0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    // The 32 lanes of a warp cover 512 consecutive output bases, so their records lie next to each
+    // other: one cooperative 32-ary search per warp (5 rounds of one probe per lane for 2^21 records,
+    // instead of 21 dependent loads per thread) finds the last record at or before the warp's first
+    // base; each lane then steps forward to its own.
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t pw = p0 - 16ull * lane;                 // the warp's first base
+    int64_t lo = -1, hi = (int64_t)n_muts;                 // new_pos[lo] <= pw < new_pos[hi]
     while (hi - lo > 1) {
-        int64_t mid = lo + (hi - lo) / 2;
-        if (new_pos[mid] <= p0) lo = mid; else hi = mid;
+        const int64_t step = (hi - lo - 1 + 31) / 32;
+        const int64_t idx = lo + (int64_t)(lane + 1u) * step;
+        const bool ok = idx < hi && new_pos[idx] <= pw;
+        const int c = __popc(__ballot_sync(0xffffffffu, ok)); // sorted: the lanes that answer yes form a prefix
+        const int64_t nlo = lo + (int64_t)c * step, nhi = lo + (int64_t)(c + 1) * step;
+        lo = c ? nlo : lo;
+        hi = nhi < hi ? nhi : hi;
     }
+    if (p0 >= chrom_size) return;
     int64_t i = lo;
+    while (i + 1 < (int64_t)n_muts && new_pos[i + 1] <= p0) i++;
     uint64_t next = (i + 1 < (int64_t)n_muts) ? new_pos[i + 1] : ~0ull;
     uint64_t np = 0, op = 0, no = 0;
     int64_t sm = 0;
