@@ -62,6 +62,15 @@ int jlp_set_genome_async(jlp_ctx* ctx, const char* bases, const uint64_t* chrom_
                          const char* const* chrom_names, const char* genome_name);
 int jlp_genome_sync(jlp_ctx* ctx);
 
+/* create_genome (create_genome_cpp, src/create_sequences.cpp:162-184): random
+ * chromosomes of the given lengths, nucleotides alias-sampled from pi_tcag (T, C, A, G), generated
+ * straight into device memory -- the genome is resident afterwards, no upload needed.  chrom_names may be
+ * NULL ("chrom<i>").  jlp_get_genome copies the bases (all chromosomes, concatenated) to the host;
+ * out == NULL only asks for the size. */
+int jlp_create_genome(jlp_ctx* ctx, uint64_t n_chroms, const uint64_t* lens, const double* pi_tcag, uint64_t seed,
+                      const char* const* chrom_names, const char* genome_name);
+int jlp_get_genome(jlp_ctx* ctx, char* out, uint64_t cap, uint64_t* len);
+
 /* Drop all haplotypes previously added. */
 int jlp_clear_haplotypes(jlp_ctx* ctx);
 
@@ -211,6 +220,8 @@ int jlp_frag_table(double shape, double scale, uint64_t frag_min, uint64_t frag_
 void jlp_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 uint64_t jlp_draw_pos(uint64_t seed, uint64_t j, uint32_t end, uint32_t purpose, uint32_t pos);
 uint64_t jlp_draw_pair(uint64_t seed, uint64_t j, int which);
+/* logical draw of the genome generator: which = 0 die roll, 1 alias coin, of base `pos` of chromosome `chrom` */
+uint64_t jlp_genome_draw(uint64_t seed, uint32_t chrom, uint64_t pos, int which);
 
 const char* jlp_version(void);
 

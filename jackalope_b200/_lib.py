@@ -48,7 +48,7 @@ class RunStats(C.Structure):
 
 # every symbol include/jlp_b200.h declares
 SYMBOLS = [
-    "jlp_ctx_create", "jlp_ctx_destroy", "jlp_last_error", "jlp_set_genome", "jlp_set_genome_async", "jlp_genome_sync", "jlp_clear_haplotypes",
+    "jlp_ctx_create", "jlp_ctx_destroy", "jlp_last_error", "jlp_set_genome", "jlp_set_genome_async", "jlp_genome_sync", "jlp_create_genome", "jlp_get_genome", "jlp_genome_draw", "jlp_clear_haplotypes",
     "jlp_add_haplotype", "jlp_get_haplotype_chrom", "jlp_set_profile", "jlp_illumina_ref", "jlp_illumina_hap",
     "jlp_illumina_to_memory", "jlp_illumina_stream", "jlp_illumina_device_only", "jlp_illumina_group_counts", "jlp_apportion", "jlp_shard_range", "jlp_deflate", "jlp_reads_per_group", "jlp_alias_build",
     "jlp_threshold", "jlp_unif_expr", "jlp_frag_table", "jlp_philox4x32_10", "jlp_draw_pos", "jlp_draw_pair",
@@ -76,6 +76,10 @@ def lib():
     L.jlp_set_genome.argtypes = [C.c_void_p, C.c_void_p, u64p, C.c_uint64, pp, C.c_char_p]
     L.jlp_set_genome_async.argtypes = L.jlp_set_genome.argtypes
     L.jlp_genome_sync.argtypes = [C.c_void_p]
+    L.jlp_create_genome.argtypes = [C.c_void_p, C.c_uint64, u64p, f64p, C.c_uint64, pp, C.c_char_p]
+    L.jlp_get_genome.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, u64p]
+    L.jlp_genome_draw.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_int]
+    L.jlp_genome_draw.restype = C.c_uint64
     L.jlp_clear_haplotypes.argtypes = [C.c_void_p]
     L.jlp_add_haplotype.argtypes = [C.c_void_p, C.c_char_p, u64p, C.POINTER(u64p), C.POINTER(u64p),
                                     C.POINTER(u64p), C.POINTER(C.c_void_p), u64p, u64p, u64p]

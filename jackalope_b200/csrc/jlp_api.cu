@@ -801,6 +801,54 @@ int jlp_genome_sync(jlp_ctx* c) {
     });
 }
 
+int jlp_create_genome(jlp_ctx* c, uint64_t n_chroms, const uint64_t* lens, const double* pi_tcag, uint64_t seed,
+                      const char* const* chrom_names, const char* genome_name) {
+    if (!c) return JLP_ERR_ARG;
+    return guarded(c, [&]() {
+        if (!lens || !pi_tcag || n_chroms == 0) throw ArgErr("empty genome");
+        double tot = 0;
+        for (int k = 0; k < 4; k++) { if (!(pi_tcag[k] >= 0)) throw ArgErr("pi_tcag must be >= 0"); tot += pi_tcag[k]; }
+        if (!(tot > 0)) throw ArgErr("pi_tcag must have at least one value > 0");
+        if (c->upload_pending) { c->upload_src = nullptr; CK(cudaStreamSynchronize(c->s_upload)); c->upload_pending = false; }
+        free_haps(c);
+        c->chrom_off.assign(1, 0);
+        c->chrom_names.clear();
+        for (uint64_t i = 0; i < n_chroms; i++) {
+            if (lens[i] == 0) throw ArgErr("chromosome lengths must be >= 1");       // "never returns empty chromosomes"
+            c->chrom_off.push_back(c->chrom_off.back() + lens[i]);
+            c->chrom_names.push_back(chrom_names && chrom_names[i] ? chrom_names[i] : "chrom" + std::to_string(i));   // src/create_sequences.cpp:178-181
+        }
+        c->genome_name = genome_name ? genome_name : "REF";
+        c->chrom_resident.assign(n_chroms, 1);
+        c->genome.ensure(c->chrom_off.back() + 2 * kPad);
+        // AliasSampler(pi_tcag), src/alias_sampler.h:68-106
+        double Prob[4];
+        uint64_t Alias[4];
+        alias_build(pi_tcag, 4, Prob, Alias);
+        GenomeTables t;
+        for (int k = 0; k < 4; k++) {
+            Thr th = thr_double_lt(Prob[k]);
+            t.thr[k] = th.thr; t.thr16[k] = (uint32_t)(th.thr >> 48); t.alias[k] = (uint32_t)Alias[k];
+        }
+        for (uint64_t i = 0; i < n_chroms; i++)
+            CK(launch_create_chrom(c->genome.p + kPad + c->chrom_off[i], lens[i], (uint32_t)i, seed, t, c->s_compute));
+        CK(cudaStreamSynchronize(c->s_compute));
+    });
+}
+
+int jlp_get_genome(jlp_ctx* c, char* out, uint64_t cap, uint64_t* len) {
+    if (!c) return JLP_ERR_ARG;
+    return guarded(c, [&]() {
+        if (c->chrom_off.size() < 2) throw ArgErr("no reference genome has been set");
+        finish_upload(c);
+        const uint64_t n = c->chrom_off.back();
+        if (len) *len = n;
+        if (!out) return;
+        if (n > cap) throw ArgErr("output buffer too small");
+        CK(cudaMemcpy(out, c->genome.p + kPad, n, cudaMemcpyDeviceToHost));
+    });
+}
+
 int jlp_clear_haplotypes(jlp_ctx* c) {
     if (!c) return JLP_ERR_ARG;
     return guarded(c, [&]() { free_haps(c); });
@@ -1033,6 +1081,9 @@ uint64_t jlp_draw_pos(uint64_t seed, uint64_t j, uint32_t end, uint32_t purpose,
     if (high_bits(purpose) == 0) return slow64(seed, j, end, purpose, pos);
     U4 w = purpose == PU_INDEL ? draw_block(seed, j, pos >> 3, PL_INDEL, end) : draw_block(seed, j, pos >> 1, PL_QUAL, end);
     return full_draw(high_of(w, purpose, pos), seed, j, end, purpose, pos);
+}
+uint64_t jlp_genome_draw(uint64_t seed, uint32_t chrom, uint64_t pos, int which) {
+    return genome_draw(seed, chrom, pos, (uint32_t)which);
 }
 uint64_t jlp_draw_pair(uint64_t seed, uint64_t j, int which) {
     U4 w = draw_block(seed, j, (uint32_t)(which >> 1), PL_PAIR, 0);

@@ -38,7 +38,7 @@
 
 namespace jlp {
 
-enum Plane : uint32_t { PL_PAIR = 0, PL_INDEL = 1, PL_QUAL = 2, PL_SLOW = 3 };
+enum Plane : uint32_t { PL_PAIR = 0, PL_INDEL = 1, PL_QUAL = 2, PL_SLOW = 3, PL_GENOME = 4, PL_GSLOW = 5 };
 enum Purpose : uint32_t { PU_INDEL = 0, PU_DIE = 1, PU_COIN = 2, PU_MIS = 3, PU_SUB = 4, PU_INS = 5 };
 
 struct U4 { uint32_t w0, w1, w2, w3; };
@@ -124,6 +124,25 @@ JLP_HD uint32_t high_of(const U4& w, uint32_t purpose, uint32_t pos) {
     }
     const uint32_t a = (pos & 1u) ? w.w2 : w.w0, b = (pos & 1u) ? w.w3 : w.w1;
     return purpose == PU_DIE ? (a >> 8) : purpose == PU_SUB ? (a & 0xffu) : purpose == PU_COIN ? (b >> 16) : (b & 0xffffu);
+}
+
+// ---- draws of the genome generator (create_genome): chromosome c, base b ----
+//   plane GENOME: counter (b>>2 lo, b>>2 hi, c, PL_GENOME), word b&3:
+//                 bits 31..30 = high 2 bits of X_die(b), bits 29..14 = high 16 bits of X_coin(b)
+//   plane GSLOW : counter (b lo, b hi, c, PL_GSLOW | which<<8), S = w1:w0 -> the low 62 (die, which 0)
+//                 or 48 (coin, which 1) bits
+JLP_HD U4 genome_block(uint64_t seed, uint32_t chrom, uint64_t block) {
+    return philox4x32_10((uint32_t)block, (uint32_t)(block >> 32), chrom, PL_GENOME, (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+JLP_HD uint64_t genome_slow(uint64_t seed, uint32_t chrom, uint64_t b, uint32_t which) {
+    return lo64(philox4x32_10((uint32_t)b, (uint32_t)(b >> 32), chrom, PL_GSLOW | (which << 8), (uint32_t)seed, (uint32_t)(seed >> 32)));
+}
+JLP_HD uint32_t genome_word(const U4& w, uint32_t k) { return k == 0 ? w.w0 : k == 1 ? w.w1 : k == 2 ? w.w2 : w.w3; }
+JLP_HD uint64_t genome_draw(uint64_t seed, uint32_t chrom, uint64_t b, uint32_t which) {
+    const uint32_t w = genome_word(genome_block(seed, chrom, b >> 2), (uint32_t)b & 3u);
+    const uint64_t s = genome_slow(seed, chrom, b, which);
+    if (which == 0) return ((uint64_t)(w >> 30) << 62) | (s & (~0ull >> 2));
+    return ((uint64_t)((w >> 14) & 0xffffu) << 48) | (s & (~0ull >> 16));
 }
 
 // ---- exact restatements of the reference's uses of u = runif_01(x) ----

@@ -93,6 +93,55 @@ cudaError_t launch_materialize(const uint8_t* ref, uint64_t ref_size, uint64_t n
     return cudaGetLastError();
 }
 
+// --------------------------------------------------------- create_genome ---
+
+// One thread per 16 bases = 4 Philox blocks.  Per base the reference's AliasSampler::sample
+// (src/alias_sampler.h:53-60, called from create_chromosomes_, src/create_sequences.cpp:129-132):
+// slot i = (uint64)(u1 * 4), then i or Alias[i] depending on u2 < Prob[i].  With four slots the die
+// roll is the top two bits of its draw; the coin is decided on 16 bits; the rare ties fetch the rest.
+__global__ void __launch_bounds__(256)
+k_create_chrom(uint8_t* __restrict__ out, uint64_t len, uint32_t chrom, uint64_t seed, const __grid_constant__ GenomeTables t) {
+    // each thread owns one 16-byte-aligned chunk of the OUTPUT (chromosomes start at arbitrary byte offsets of
+    // the genome buffer), i.e. bases [16 t - sh, 16 t - sh + 16) of the chromosome
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(out) & 15u);
+    const int64_t bs = (int64_t)(((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16) - (int64_t)sh;
+    if (bs >= (int64_t)len) return;
+    uint32_t o[4] = {0, 0, 0, 0};
+    U4 w4 = {0, 0, 0, 0};
+    uint64_t have = ~0ull;
+#pragma unroll
+    for (uint32_t k = 0; k < 16; k++) {
+        const int64_t bb = bs + (int64_t)k;
+        if (bb < 0 || bb >= (int64_t)len) continue;
+        const uint64_t b = (uint64_t)bb;
+        if ((b >> 2) != have) { have = b >> 2; w4 = genome_block(seed, chrom, have); }
+        const uint32_t w = genome_word(w4, (uint32_t)b & 3u);
+        uint32_t i = w >> 30;
+        if ((w & 0x3fffffffu) == 0x3fffffffu) {                // the low bits could carry: (x + 1) >> 62 on the full draw
+            const uint64_t x = genome_draw(seed, chrom, b, 0);
+            i = x == ~0ull ? 3u : (uint32_t)((x + 1) >> 62);
+        }
+        const uint32_t H = (w >> 14) & 0xffffu, th = t.thr16[i];
+        bool self = H < th;
+        if (H == th) self = genome_draw(seed, chrom, b, 1) < t.thr[i];
+        const uint32_t kk = self ? i : t.alias[i];
+        o[k >> 2] |= (__byte_perm(0x47414354u, 0u, kk) & 0xffu) << (8u * (k & 3u));
+    }
+    uint8_t* dst = out + bs;                                   // 16-byte aligned
+    if (bs >= 0 && bs + 16 <= (int64_t)len) *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+    else
+        for (uint32_t k = 0; k < 16; k++)
+            if (bs + (int64_t)k >= 0 && bs + (int64_t)k < (int64_t)len) dst[k] = (uint8_t)(o[k >> 2] >> (8u * (k & 3u)));
+}
+
+cudaError_t launch_create_chrom(uint8_t* out, uint64_t len, uint32_t chrom, uint64_t seed, const GenomeTables& t,
+                                cudaStream_t s) {
+    if (len == 0) return cudaSuccess;
+    const uint64_t n16 = (len + 15 + 15) / 16;                 // + the shift of the first chunk
+    k_create_chrom<<<(unsigned)((n16 + 255) / 256), 256, 0, s>>>(out, len, chrom, seed, t);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------ primitives ---
 
 // nt_map (src/hts.h:36-44) as codes: T,C,A,G -> 0..3, anything else 4.

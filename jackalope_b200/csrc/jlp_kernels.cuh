@@ -85,6 +85,15 @@ cudaError_t launch_materialize(const uint8_t* ref, uint64_t ref_size, uint64_t n
                                const uint8_t* pool, uint64_t chrom_size, uint8_t* out,
                                cudaStream_t s);
 
+// create_genome: alias-sampled nucleotides of one chromosome, written straight into HBM
+struct GenomeTables {
+    uint32_t thr16[4];      // high 16 bits of the alias coin threshold per slot
+    uint64_t thr[4];        // full thresholds
+    uint32_t alias[4];
+};
+cudaError_t launch_create_chrom(uint8_t* out, uint64_t len, uint32_t chrom, uint64_t seed, const GenomeTables& t,
+                                cudaStream_t s);
+
 // fragment placement + indel summary + record lengths, one thread per read end
 cudaError_t launch_place(const GenParams& p, cudaStream_t s);
 

@@ -176,3 +176,52 @@ def random_haplotypes(reference: RefGenome, n_haps, sub_rate=0.01, indel_rate=0.
         edits.append(eh)
     haps = Haplotypes(reference, names or ["hap%d" % i for i in range(n_haps)], muts)
     return (haps, edits) if return_edits else haps
+
+
+def create_genome(n_chroms, len_mean, len_sd=0, pi_tcag=(0.25, 0.25, 0.25, 0.25), n_threads=1, *, seed=None, ctx=None, device=0):
+    """``create_genome()`` of the reference (R/create_genome.R:24-58, create_genome_cpp,
+    src/create_sequences.cpp:162-184) with the chromosomes generated on the GPU: lengths from
+    Gamma(mean, sd) truncated to integers >= 1 (or all ``len_mean`` when ``len_sd`` is 0), nucleotides
+    alias-sampled from ``pi_tcag`` (T, C, A, G), names ``chrom0..``.  The genome stays resident in the
+    context's HBM, so a following ``illumina()`` on the returned object uploads nothing.
+    ``n_threads`` is accepted for compatibility.  There is no CPU path."""
+    import ctypes as C
+    import numbers
+
+    from . import _lib
+    from .illumina import default_context
+
+    def bad(par, what):
+        raise JackalopeError("\nFor the `create_genome` function in jackalope, argument `%s` must be %s." % (par, what))
+    if not (isinstance(n_chroms, numbers.Real) and float(n_chroms) == int(n_chroms) and n_chroms >= 1):
+        bad("n_chroms", "a single integer >= 1")
+    if not (isinstance(len_mean, numbers.Real) and len_mean >= 1):
+        bad("len_mean", "a single number >= 1")
+    if not (isinstance(len_sd, numbers.Real) and len_sd >= 0):
+        bad("len_sd", "a single number >= 0")
+    pi = np.asarray(pi_tcag, dtype=np.float64)
+    if pi.shape != (4,) or np.any(pi < 0) or np.all(pi == 0) or np.any(np.isnan(pi)):
+        bad("pi_tcag", "a numeric vector of length 4, where no number can be < 0 and at least one must be > 0")
+    if not (isinstance(n_threads, numbers.Real) and float(n_threads) == int(n_threads) and n_threads >= 1):
+        bad("n_threads", "a single integer >= 1")
+    if seed is None:
+        seed = int(np.random.randint(0, 2 ** 63 - 1, dtype=np.int64))
+    n_chroms = int(n_chroms)
+    if len_sd > 0:
+        rng = np.random.default_rng(seed)
+        shape, scale = (len_mean / len_sd) ** 2, len_sd ** 2 / len_mean      # src/create_sequences.cpp:78-79
+        lens = np.maximum(rng.gamma(shape, scale, size=n_chroms).astype(np.uint64), 1)
+    else:
+        lens = np.full(n_chroms, int(len_mean), dtype=np.uint64)
+    ctx = ctx or default_context(device)
+    ctx._check(ctx.lib.jlp_create_genome(ctx.h, n_chroms, lens.ctypes.data_as(_lib.u64p), pi.ctypes.data_as(_lib.f64p),
+                                         int(seed) & (2 ** 64 - 1), None, b"REF"), "jlp_create_genome")
+    total = int(lens.sum())
+    flat = np.empty(total, dtype=np.uint8)
+    n = C.c_uint64()
+    ctx._check(ctx.lib.jlp_get_genome(ctx.h, flat.ctypes.data_as(C.c_void_p), total, C.byref(n)), "jlp_get_genome")
+    off = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
+    g = RefGenome(["chrom%d" % i for i in range(n_chroms)], [flat[off[i]:off[i + 1]] for i in range(n_chroms)])
+    g.flat = lambda: (flat, off.astype(np.uint64))
+    ctx._genome, ctx._haps = g, None           # already resident
+    return g

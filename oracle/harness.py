@@ -74,6 +74,9 @@ def oracle():
         lib.orc_qual_prob_map.argtypes = [C.c_uint64, u32p, f64p, u8p, f64p]
         lib.orc_materialize.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64, u64p, u64p, u64p,
                                         C.c_char_p, C.c_uint64, C.c_char_p]
+        lib.orc_genome_draw.restype = C.c_uint64
+        lib.orc_genome_draw.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_int]
+        lib.orc_create_chrom.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, f64p, C.c_char_p, u64p]
         lib.orc_generate.argtypes = [C.POINTER(OrcJob), C.c_uint64, C.c_uint64,
                                      C.c_char_p, C.c_uint64, u64p, C.c_char_p, C.c_uint64, u64p,
                                      u64p, u64p, C.c_uint64, u64p, u64p]
@@ -102,6 +105,27 @@ def qual_prob_map(flat):
     out = np.zeros(256, dtype=np.float64)
     assert oracle().orc_qual_prob_map(L, _ptr(nq, u32p), _ptr(probs, f64p), _ptr(quals, u8p), _ptr(out, f64p)) == 0
     return out
+
+
+def create_chrom(seed, chrom, length, pi_tcag, want_ledger=False):
+    """One chromosome of create_genome from the oracle (bytes[, ledger of draws])."""
+    pi = np.ascontiguousarray(pi_tcag, dtype=np.float64)
+    out = C.create_string_buffer(max(1, length))
+    led = np.zeros(max(1, 2 * length), dtype=np.uint64) if want_ledger else None
+    assert oracle().orc_create_chrom(seed, chrom, length, _ptr(pi, f64p), out, _ptr(led, u64p)) == 0
+    return (out.raw[:length], led[:2 * length]) if want_ledger else out.raw[:length]
+
+
+def ref_create_chrom_replay(pi_tcag, length, script):
+    """The reference's own sampling loop (create_chromosomes_) fed with `script`."""
+    lib = ref_lib(True)
+    pi = np.ascontiguousarray(pi_tcag, dtype=np.float64)
+    sc = np.ascontiguousarray(script, dtype=np.uint64)
+    out = C.create_string_buffer(max(1, length))
+    used = C.c_uint64()
+    rc = lib.jref_create_chrom_replay(_ptr(pi, f64p), length, _ptr(sc, u64p), sc.size, out, C.byref(used))
+    assert rc == 0
+    return out.raw[:length], used.value
 
 
 def materialize(ref: bytes, old_pos, new_pos, nuc_off, pool: bytes, chrom_size: int) -> bytes:
@@ -221,6 +245,7 @@ def ref_lib(replay=False):
                                               C.c_uint64, C.c_uint64] + prof + [C.POINTER(C.c_char_p), C.c_char_p,
                                                                                C.c_uint64]
         else:
+            lib.jref_create_chrom_replay.argtypes = [f64p, C.c_uint64, u64p, C.c_uint64, C.c_char_p, u64p]
             lib.jref_replay.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + prof + [
                 C.POINTER(C.c_char_p), C.c_uint64, u64p, u64p, u64p, u64p, u64p, C.c_uint64, u64p,
                 C.c_char_p, C.c_uint64, u64p, C.c_char_p, C.c_uint64, u64p, C.c_char_p, C.c_uint64]

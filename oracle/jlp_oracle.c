@@ -501,6 +501,39 @@ done:
     return rc;
 }
 
+/* ----------------------------------------------------------- create_genome */
+
+/* draws of the genome generator (layout: jackalope_b200/csrc/jlp_draws.h): which 0 = die, 1 = coin */
+uint64_t orc_genome_draw(uint64_t seed, uint32_t chrom, uint64_t b, int which) {
+    uint32_t ctr[4] = {(uint32_t)(b >> 2), (uint32_t)((b >> 2) >> 32), chrom, 4u}, key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, w[4], v[4];
+    orc_philox4x32_10(ctr, key, w);
+    uint32_t word = w[b & 3];
+    uint32_t c2[4] = {(uint32_t)b, (uint32_t)(b >> 32), chrom, 5u | ((uint32_t)which << 8)};
+    orc_philox4x32_10(c2, key, v);
+    uint64_t s = ((uint64_t)v[1] << 32) | v[0];
+    if (which == 0) return ((uint64_t)(word >> 30) << 62) | (s & (~0ull >> 2));
+    return ((uint64_t)((word >> 14) & 0xffffu) << 48) | (s & (~0ull >> 16));
+}
+
+/* One chromosome of create_chromosomes_ (src/create_sequences.cpp:129-132): per base
+ * k = sampler.sample(engine) (AliasSampler::sample, src/alias_sampler.h:53-60), base = jlp::bases[k].
+ * ledger (optional, 2 * len): the draws in the order the reference consumes them. */
+int orc_create_chrom(uint64_t seed, uint32_t chrom, uint64_t len, const double* pi_tcag, char* out, uint64_t* ledger) {
+    double Prob[4];
+    uint64_t Alias[4];
+    if (orc_alias_build(pi_tcag, 4, Prob, Alias)) return -1;
+    for (uint64_t b = 0; b < len; b++) {
+        uint64_t xd = orc_genome_draw(seed, chrom, b, 0), xc = orc_genome_draw(seed, chrom, b, 1);
+        if (ledger) { ledger[2 * b] = xd; ledger[2 * b + 1] = xc; }
+        uint64_t i = (uint64_t)(runif_01(xd) * 4);
+        if (i > 3) i = 3;                       /* u == 1.0 (x = 2^64-1) indexes past the table in the reference: clamp */
+        double u = (double)runif_01(xc);
+        uint64_t k = (u < Prob[i]) ? i : Alias[i];
+        out[b] = BASES[k];
+    }
+    return 0;
+}
+
 /* literal uniform expressions, same numbering as jref_unif_expr in ref_driver.cpp */
 uint64_t orc_unif_expr(int kind, uint64_t x, double p, uint64_t n) {
     long double ul = runif_01(x);

@@ -349,6 +349,26 @@ int jref_replay(void* obj, int is_hap, int paired, int matepair,
     return 0;
 }
 
+// The inner loop of create_chromosomes_ (src/create_sequences.cpp:129-132) on a scripted engine:
+// chrom.push_back(bases_[sampler.sample(engine)]) with the reference's own AliasSampler.
+int jref_create_chrom_replay(const double* pi_tcag, uint64_t len, const uint64_t* script, uint64_t script_len,
+                             char* out, uint64_t* consumed) {
+    jlp_replay::Script& sc = jlp_replay::script();
+    sc.data = script; sc.len = script_len; sc.pos = 0; sc.underruns = 0;
+    pcg64 engine;
+    const AliasSampler sampler(std::vector<double>(pi_tcag, pi_tcag + 4));
+    std::string bases_ = jlp::bases;
+    std::string chrom;
+    chrom.reserve(len);
+    for (uint64_t j = 0; j < len; j++) {
+        uint64 k = sampler.sample(engine);
+        chrom.push_back(bases_[k]);
+    }
+    std::memcpy(out, chrom.data(), len);
+    if (consumed) *consumed = sc.pos;
+    return sc.underruns ? -1 : 0;
+}
+
 int jref_is_replay() { return 1; }
 #endif
 

@@ -254,3 +254,26 @@ def test_degenerate_counts(ctx, tmp_path):
     assert open("%s_hap1_R1.fq" % pre, "rb").read() == b""
     assert open("%s_hap0_R1.fq" % pre, "rb").read().count(b"\n") + open("%s_hap2_R1.fq" % pre, "rb").read().count(b"\n") == 4 * 300
     check(ctx, haps, 600, 100, True, seed=76, sep_files=True, haplotype_probs=[1, 0, 1])
+
+
+def test_create_genome_on_device(ctx):
+    """create_genome (SURVEY.md section 8f rank 4): chromosomes generated in HBM are the oracle's byte for byte;
+    the genome is resident, so illumina() on it uploads nothing and still matches the oracle."""
+    from scipy import stats
+    from oracle import harness as H
+    for pi in ([0.25, 0.25, 0.25, 0.25], [0.1, 0.2, 0.3, 0.4], [0, 1, 0, 3]):
+        g = J.create_genome(3, 7001, pi_tcag=pi, seed=81, ctx=ctx)
+        assert g.names == ["chrom0", "chrom1", "chrom2"]
+        for c in range(3):
+            assert g.chrom(c) == H.create_chrom(81, c, 7001, pi)
+    g = J.create_genome(5, 40000, len_sd=8000, pi_tcag=[0.1, 0.2, 0.3, 0.4], seed=82, ctx=ctx)
+    assert len(set(int(s) for s in g.sizes())) == 5 and min(g.sizes()) >= 1
+    cnt = np.bincount(np.concatenate(g.seqs), minlength=256)[np.frombuffer(b"TCAG", np.uint8)]
+    assert stats.chisquare(cnt, np.array([0.1, 0.2, 0.3, 0.4]) * cnt.sum()).pvalue > 1e-4
+    before = J.illumina(g, "", 2, 100, True, seed=1, ctx=ctx, sink="device")["h2d_bytes"]
+    r1, r2, st = check(ctx, g, 3000, 100, True, seed=83)
+    assert st["h2d_bytes"] - before < 1_000_000          # tables only: the genome was never uploaded
+    with pytest.raises(J.JackalopeError):
+        J.create_genome(0, 100, ctx=ctx)
+    with pytest.raises(J.JackalopeError):
+        J.create_genome(2, 100, pi_tcag=[0, 0, 0, 0], ctx=ctx)

@@ -250,3 +250,17 @@ def test_pair_geometry_known_answers_through_the_reference():
             for k in (1, 2):
                 lines = open("%s_R%d.fq" % (pre, k), "rb").read().split(b"\n")
                 assert set(lines[1::4]) - {b""} == want
+
+
+@needs_ref
+@pytest.mark.parametrize("pi", [[0.25, 0.25, 0.25, 0.25], [0.1, 0.2, 0.3, 0.4], [0, 1, 0, 3], [5, 1, 1, 1]])
+def test_create_genome_replay(pi):
+    """create_genome: the reference's sampling loop (AliasSampler::sample per base,
+    src/create_sequences.cpp:129-132) fed with the oracle's draw ledger gives the oracle's chromosome."""
+    for chrom, n in ((0, 1), (3, 4097), (7, 20000)):
+        seq, led = H.create_chrom(99, chrom, n, pi, want_ledger=True)
+        ref_seq, used = H.ref_create_chrom_replay(pi, n, led)
+        assert used == 2 * n and ref_seq == seq
+    lib = _lib.lib()
+    assert all(lib.jlp_genome_draw(99, 3, p, w) == H.oracle().orc_genome_draw(99, 3, p, w)
+               for p in list(range(0, 200)) + [2 ** 33 + 5] for w in (0, 1))
