@@ -300,9 +300,9 @@ def main():
     ctx = J.Context(local_rank)
     B = a.batch_pairs
 
-    def run(n_steps, sink, seed):
+    def run(n_steps, sink, seed, **more):
         return J.illumina(genome, "", 2 * n_steps * B * world, L, True, seed=seed, ctx=ctx, sink=sink,
-                          batch_pairs=B, shard=(rank, world), **kw)
+                          batch_pairs=B, shard=(rank, world), **kw, **more)
 
     # ---- device-resident leg
     for i in range(a.warmup):
@@ -351,6 +351,41 @@ def main():
                        "are copied from pinned host memory inside the region, every batch's FASTQ lands in the library's "
                        "pinned host buffers"}
 
+    # ---- compress = TRUE on the device (BGZF members written by k_bgzf): kernel time with the output left in HBM,
+    #      and end to end with only the compressed bytes crossing PCIe
+    bgzf = None
+    if not a.no_e2e:
+        zkw = dict(compress=True, comp_engine="device")
+        run(1, "device", a.seed + 400, **zkw)
+        barrier()
+        stz = run(a.steps, "device", a.seed, **zkw)
+        barrier()
+        z_ms = max_over_ranks(stz["bgzf_ms"] / stz["batches"])
+        zrun_ms = max_over_ranks(stz["run_ms"])
+        zseen = [0, 0]
+
+        def zsink(job, end, buf):
+            zseen[end] += len(buf)
+
+        run(1, zsink, a.seed + 401, **zkw)
+        zseen[0] = zseen[1] = 0
+        barrier()
+        ctx._genome = None
+        t0 = time.perf_counter()
+        stz2 = run(a.steps, zsink, a.seed, **zkw)
+        barrier()
+        t_z = max_over_ranks(time.perf_counter() - t0)
+        assert stz["bytes_out"] == st["bytes_out"] and zseen[0] == stz2["z_bytes"][0] + 28, (stz, zseen)
+        zin, zout = sum(stz["bytes_out"]) / stz["batches"], sum(stz["z_bytes"]) / stz["batches"]
+        bgzf = {"device_resident": {"value": a.steps * B * world / (zrun_ms / 1e3), "unit": UNIT, "ms_per_step": zrun_ms / a.steps},
+                "e2e": {"value": a.steps * B * world / t_z, "unit": UNIT, "ms_per_step": t_z / a.steps * 1e3,
+                        "d2h_bytes_per_step": stz2["d2h_bytes"] / a.steps},
+                "ratio": zout / zin, "k_bgzf_ms_per_step": z_ms,
+                "k_bgzf_GBps": (zin + zout) / (z_ms / 1e3) / 1e9,
+                "note": "compress=TRUE, comp_engine=device: k_bgzf + scan + gather after k_reads; e2e hands BGZF bytes to the caller "
+                        "from pinned host buffers (jlp_illumina_stream); GB/s counts FASTQ bytes read + BGZF bytes written"}
+        log("[bench] device BGZF: %.3f ms/step, ratio %.3f, e2e %.2f ms/step" % (z_ms, zout / zin, t_z / a.steps * 1e3))
+
     # ---- the same through FILES (the reference-facing default sink): tmpfs, all host threads writing
     e2e_files = None
     if not a.no_e2e and rank == 0 and world == 1 and os.path.isdir("/dev/shm"):
@@ -373,21 +408,29 @@ def main():
                 e2e_files = {"value": a.steps * B / t_files, "unit": UNIT, "ms_per_step": t_files / a.steps * 1e3,
                              "writer_threads": nthr, "bytes_written": sz,
                              "note": "illumina(obj, out_prefix, ...) writing <prefix>_R{1,2}.fq on tmpfs; genome H2D inside"}
-                # compress = TRUE (bgzip, level 6, the reference's default level): 2 steps, zlib on the writer threads
+                # compress = TRUE (the reference's default level 6 -> the device coder)
                 ctx._genome = None
                 t0 = time.perf_counter()
-                J.illumina(genome, os.path.join(d, "z"), 2 * 2 * B, L, True, seed=a.seed, ctx=ctx, batch_pairs=B,
+                J.illumina(genome, os.path.join(d, "z"), 2 * a.steps * B, L, True, seed=a.seed, ctx=ctx, batch_pairs=B,
                            n_threads=nthr, compress=True, overwrite=True, **kw)
                 t_z = time.perf_counter() - t0
                 zsz = os.path.getsize(os.path.join(d, "z_R1.fq.gz")) + os.path.getsize(os.path.join(d, "z_R2.fq.gz"))
-                e2e_files["bgzip"] = {"value": 2 * B / t_z, "unit": UNIT, "steps": 2, "compressed_bytes": zsz,
-                                      "ratio": zsz / (sz / a.steps * 2), "note": "compress=TRUE, comp_method=bgzip, level 6"}
+                e2e_files["bgzip_device"] = {"value": a.steps * B / t_z, "unit": UNIT, "steps": a.steps, "compressed_bytes": zsz,
+                                             "ratio": zsz / sz, "note": "compress=TRUE, comp_method=bgzip (BGZF written by the GPU)"}
+                # the same with zlib level 6 on the writer threads: 1 step
+                t0 = time.perf_counter()
+                J.illumina(genome, os.path.join(d, "y"), 2 * B, L, True, seed=a.seed, ctx=ctx, batch_pairs=B,
+                           n_threads=nthr, compress=True, comp_engine="host", overwrite=True, **kw)
+                t_z = time.perf_counter() - t0
+                zsz = os.path.getsize(os.path.join(d, "y_R1.fq.gz")) + os.path.getsize(os.path.join(d, "y_R2.fq.gz"))
+                e2e_files["bgzip_host_zlib6"] = {"value": B / t_z, "unit": UNIT, "steps": 1, "compressed_bytes": zsz,
+                                                 "ratio": zsz / (sz / a.steps), "note": "comp_engine=host: zlib level 6 on the writer threads"}
             finally:
                 shutil.rmtree(d, ignore_errors=True)
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
            "ms_per_step": run_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "u8", "data": "synthetic", "config": config, "clocks": clk, "e2e": e2e, "e2e_files": e2e_files,
+           "dtype": "u8", "data": "synthetic", "config": config, "clocks": clk, "e2e": e2e, "e2e_files": e2e_files, "bgzf": bgzf,
            "gpu_launches": launches}
 
     if rank == 0:

@@ -129,7 +129,16 @@ typedef struct jlp_illumina_params {
     jlp_abort_cb abort_cb;
     jlp_progress_cb progress_cb;
     void* cb_user;
+    int comp_engine;             /* who compresses when compress > 0: enum jlp_comp_engine */
 } jlp_illumina_params;
+
+/* Compressed output (write_reads_cpp_, src/hts.h:441-500).  The device coder writes BGZF members of one
+ * dynamic-Huffman block each (a literal-only code: on FASTQ the size zlib gives at level 1, about 18 % above
+ * level 6) on the GPU, so only compressed bytes cross PCIe; the level is not used.  The host coder is zlib at
+ * `compress` on the writer threads.  AUTO: device for levels 1..6 when writing files, host for 7..9.  Memory and
+ * stream sinks (jlp_illumina_to_memory / _stream) receive BGZF bytes, EOF block included, only with
+ * JLP_COMP_DEVICE; otherwise they always receive plain FASTQ. */
+enum jlp_comp_engine { JLP_COMP_AUTO = 0, JLP_COMP_HOST = 1, JLP_COMP_DEVICE = 2 };
 
 typedef struct jlp_run_stats {
     uint64_t pairs;              /* read pairs (or single reads) generated by this call */
@@ -143,6 +152,8 @@ typedef struct jlp_run_stats {
     uint64_t h2d_bytes;
     double run_ms;               /* CUDA-event time on the compute stream from the start of the call's device
                                     work to the end of its last kernel (includes waits on the D2H double buffer) */
+    uint64_t z_bytes[2];         /* compressed bytes produced per end by the device coder (0 otherwise) */
+    double bgzf_ms;              /* ... of device_ms, the BGZF kernels (k_bgzf, k_bgzf_scan, k_bgzf_gather) */
 } jlp_run_stats;
 
 /* Reads from the reference genome (illumina_ref_cpp). */
@@ -192,6 +203,9 @@ int jlp_apportion(uint64_t seed, uint64_t n_pairs, uint64_t n_haps, uint64_t n_c
  * (bgzf != 0; FileBGZF, src/io.h:58-135) or concatenated gzip members (FileGZ, src/io.h:140-236).
  * *len receives the size (out == NULL only asks for it); JLP_ERR_ARG if `cap` is too small. */
 int jlp_deflate(int bgzf, int level, const void* in, uint64_t n, void* out, uint64_t cap, uint64_t* len);
+/* The same for the device coder: `n` host bytes are uploaded, compressed by the BGZF kernels and brought back,
+ * EOF block appended (parity tests of the coder on arbitrary bytes; needs a device). */
+int jlp_bgzf_device(jlp_ctx* ctx, const void* in, uint64_t n, void* out, uint64_t cap, uint64_t* len);
 /* Pair-index range [lo, hi) of job [job_lo, job_hi) that shard `shard_index` of
  * `shard_count` generates (jlp_illumina_params.shard_index / shard_count): contiguous
  * and near-equal, as split_int (src/util.h:245-258) splits reads over threads. */

@@ -29,6 +29,7 @@ class Params(C.Structure):
         ("barcodes", C.POINTER(C.c_char_p)), ("seed", C.c_uint64), ("batch_pairs", C.c_uint64),
         ("shard_index", C.c_uint32), ("shard_count", C.c_uint32),
         ("abort_cb", ABORT_CB), ("progress_cb", PROGRESS_CB), ("cb_user", C.c_void_p),
+        ("comp_engine", C.c_int),
     ]
 
 
@@ -37,20 +38,21 @@ class RunStats(C.Structure):
         ("pairs", C.c_uint64), ("bytes_out", C.c_uint64 * 2), ("batches", C.c_uint64),
         ("kernel_launches", C.c_uint64), ("device_ms", C.c_double), ("place_ms", C.c_double),
         ("reads_ms", C.c_double), ("d2h_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64),
-        ("run_ms", C.c_double),
+        ("run_ms", C.c_double), ("z_bytes", C.c_uint64 * 2), ("bgzf_ms", C.c_double),
     ]
 
     def as_dict(self):
         return dict(pairs=self.pairs, bytes_out=list(self.bytes_out), batches=self.batches,
                     kernel_launches=self.kernel_launches, device_ms=self.device_ms, place_ms=self.place_ms,
-                    reads_ms=self.reads_ms, d2h_bytes=self.d2h_bytes, h2d_bytes=self.h2d_bytes, run_ms=self.run_ms)
+                    reads_ms=self.reads_ms, d2h_bytes=self.d2h_bytes, h2d_bytes=self.h2d_bytes, run_ms=self.run_ms,
+                    z_bytes=list(self.z_bytes), bgzf_ms=self.bgzf_ms)
 
 
 # every symbol include/jlp_b200.h declares
 SYMBOLS = [
     "jlp_ctx_create", "jlp_ctx_destroy", "jlp_last_error", "jlp_set_genome", "jlp_set_genome_async", "jlp_genome_sync", "jlp_create_genome", "jlp_get_genome", "jlp_genome_draw", "jlp_clear_haplotypes",
     "jlp_add_haplotype", "jlp_get_haplotype_chrom", "jlp_set_profile", "jlp_illumina_ref", "jlp_illumina_hap",
-    "jlp_illumina_to_memory", "jlp_illumina_stream", "jlp_illumina_device_only", "jlp_illumina_group_counts", "jlp_apportion", "jlp_shard_range", "jlp_deflate", "jlp_reads_per_group", "jlp_alias_build",
+    "jlp_illumina_to_memory", "jlp_illumina_stream", "jlp_illumina_device_only", "jlp_illumina_group_counts", "jlp_apportion", "jlp_shard_range", "jlp_deflate", "jlp_bgzf_device", "jlp_reads_per_group", "jlp_alias_build",
     "jlp_threshold", "jlp_unif_expr", "jlp_frag_table", "jlp_philox4x32_10", "jlp_draw_pos", "jlp_draw_pair",
     "jlp_version",
 ]
@@ -95,6 +97,7 @@ def lib():
     L.jlp_apportion.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, f64p, u64p, u64p]
     L.jlp_shard_range.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, u64p, u64p]
     L.jlp_deflate.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, u64p]
+    L.jlp_bgzf_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, u64p]
     L.jlp_reads_per_group.argtypes = [C.c_uint64, f64p, C.c_uint64, C.c_uint64, u64p]
     L.jlp_alias_build.argtypes = [f64p, C.c_uint64, f64p, u64p]
     L.jlp_threshold.argtypes = [C.c_int, C.c_double, u64p, C.POINTER(C.c_int)]

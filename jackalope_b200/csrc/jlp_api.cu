@@ -175,9 +175,14 @@ struct Slot {
     DevBuf<uint64_t> block_tot, block_base, totals;
     PinBuf<uint8_t> h_out[2];
     PinBuf<uint64_t> h_totals;
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // start, placed, scanned, reads done, copied
+    // device BGZF: one 64 KiB slot per block, the members' sizes and offsets, the contiguous compressed batch
+    DevBuf<uint8_t> zslots[2], zdev[2];
+    DevBuf<uint32_t> zlen[2];
+    DevBuf<uint64_t> zoff[2];
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // start, placed, scanned, reads done, copied, all kernels done
     uint32_t pairs = 0;
     uint64_t tot[2] = {0, 0};     // FASTQ bytes of the batch per file (read back from the device)
+    uint64_t ztot[2] = {0, 0};    // compressed bytes of the batch per file (device BGZF)
     bool busy = false;
     std::atomic<int> writes{0};   // slices of h_out still being written to / compressed for the files
     std::vector<std::vector<uint8_t>> zout[2];   // compressed slices of the batch, in file order
@@ -367,7 +372,14 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
     // write_reads_cpp_ (src/hts.h:441-500): compressed + one thread -> the method asked for;
     // compressed + several threads -> always bgzip (the reference writes plain files first and
     // bgzips them afterwards; here the batches are compressed on their way to the file)
-    const int zmethod = P->compress <= 0 ? -1
+    // comp_engine picks who compresses: the device coder (BGZF members of one dynamic-Huffman block each, jlp_bgzf.cu;
+    // only compressed bytes cross PCIe) or zlib on the writer threads at the level asked for.  Memory and stream
+    // sinks receive compressed bytes only when the device coder is asked for explicitly.
+    if (P->comp_engine < JLP_COMP_AUTO || P->comp_engine > JLP_COMP_DEVICE) throw ArgErr("comp_engine must be 0 (auto), 1 (host) or 2 (device)");
+    const bool dev_z = P->compress > 0 && (P->comp_engine == JLP_COMP_DEVICE ||
+                                           (P->comp_engine == JLP_COMP_AUTO && P->compress <= 6 && sink.kind == SINK_FILES));
+    const bool want_gz = P->compress > 0;
+    const int zmethod = P->compress <= 0 || dev_z ? -1
                         : (P->n_threads > 1 || std::string(P->comp_method ? P->comp_method : "") == "bgzip") ? DEFLATE_BGZF
                                                                                                             : DEFLATE_GZIP;
     if (!(P->prob_dup >= 0 && P->prob_dup <= 1)) throw ArgErr("prob_dup must be in [0,1]");
@@ -487,18 +499,27 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
     const uint64_t n_rec_max = B * n_ends;
     const uint32_t nsb_max = (uint32_t)((B + kScanBlock - 1) / kScanBlock);
     const bool need_host = sink.kind != SINK_NONE;
+    const uint32_t nblk_max = dev_z ? (uint32_t)((B * max_rec + kBgzfIn - 1) / kBgzfIn) + 1 : 0;
     for (Slot& s : c->slot) {
         s.plan.ensure(n_rec_max);
         s.rec_len.ensure(n_rec_max);
         s.rec_local.ensure(n_rec_max);
         s.block_tot.ensure((size_t)nsb_max * 2);
         s.block_base.ensure((size_t)nsb_max * 2);
-        s.totals.ensure(2);
-        s.h_totals.ensure(2);
+        s.totals.ensure(4);
+        s.h_totals.ensure(4);
+        CK(cudaMemsetAsync(s.totals.p, 0, 4 * sizeof(uint64_t), c->s_compute));
         for (int e = 0; e < n_ends; e++) {
-            s.out[e].ensure(B * max_rec);
-            if (need_host) s.h_out[e].ensure(B * max_rec);
+            s.out[e].ensure(B * max_rec + 64);
+            if (need_host) s.h_out[e].ensure(dev_z ? (size_t)nblk_max * kBgzfSlot : B * max_rec);
         }
+        if (dev_z)
+            for (int e = 0; e < 2; e++) {
+                s.zslots[e].ensure((size_t)nblk_max * kBgzfSlot);
+                s.zdev[e].ensure((size_t)nblk_max * kBgzfSlot);
+                s.zlen[e].ensure(nblk_max);
+                s.zoff[e].ensure(nblk_max);
+            }
         for (cudaEvent_t& ev : s.ev) if (!ev) CK(cudaEventCreate(&ev));
         s.busy = false;
     }
@@ -526,21 +547,27 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
     // stage 2 of a batch: its kernels are done -> statistics, then its FASTQ starts its way to the host
     // (queued right behind the previous batch's copy, so the bus never idles)
     auto issue_copy = [&](Slot& s) {
-        CK(cudaEventSynchronize(s.ev[3]));
-        float ms_place = 0, ms_all = 0, ms_reads = 0;
+        CK(cudaEventSynchronize(s.ev[5]));
+        float ms_place = 0, ms_all = 0, ms_reads = 0, ms_z = 0;
         CK(cudaEventElapsedTime(&ms_place, s.ev[0], s.ev[1]));
         CK(cudaEventElapsedTime(&ms_reads, s.ev[2], s.ev[3]));
-        CK(cudaEventElapsedTime(&ms_all, s.ev[0], s.ev[3]));
+        CK(cudaEventElapsedTime(&ms_z, s.ev[3], s.ev[5]));
+        CK(cudaEventElapsedTime(&ms_all, s.ev[0], s.ev[5]));
         st.place_ms += ms_place; st.reads_ms += ms_reads; st.device_ms += ms_all;
-        for (int e = 0; e < n_ends; e++) { s.tot[e] = s.h_totals.p[e]; st.bytes_out[e] += s.tot[e]; }
+        if (dev_z) st.bgzf_ms += ms_z;
+        for (int e = 0; e < n_ends; e++) {
+            s.tot[e] = s.h_totals.p[e]; st.bytes_out[e] += s.tot[e];
+            s.ztot[e] = dev_z ? s.h_totals.p[2 + e] : 0; st.z_bytes[e] += s.ztot[e];
+        }
         st.pairs += s.pairs;
         st.batches++;
         if (!need_host) return;
         if (z_pending == &s) { wait_writes(s); z_pending = nullptr; }
         wait_writes(s);                         // the pinned buffers of this slot are free again
         for (int e = 0; e < n_ends; e++) {
-            CK(cudaMemcpyAsync(s.h_out[e].p, s.out[e].p, s.tot[e], cudaMemcpyDeviceToHost, c->s_copy));
-            st.d2h_bytes += s.tot[e];
+            const uint64_t nb = dev_z ? s.ztot[e] : s.tot[e];
+            CK(cudaMemcpyAsync(s.h_out[e].p, dev_z ? s.zdev[e].p : s.out[e].p, nb, cudaMemcpyDeviceToHost, c->s_copy));
+            st.d2h_bytes += nb;
         }
         CK(cudaEventRecord(s.ev[4], c->s_copy));
     };
@@ -550,7 +577,7 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
             CK(cudaEventSynchronize(s.ev[4]));
             if (zmethod >= 0 && z_pending) { wait_writes(*z_pending); z_pending = nullptr; }   // files stay in batch order
             for (int e = 0; e < n_ends; e++) {
-                const uint64_t n = s.tot[e];
+                const uint64_t n = dev_z ? s.ztot[e] : s.tot[e];
                 if (sink.kind == SINK_FILES && zmethod < 0) {
                     // R1 and R2 stay record-aligned: both files receive the same batches in the same order
                     const uint64_t slice = 8ull << 20;
@@ -602,7 +629,7 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
             sink.pos[0] = sink.pos[1] = 0;
             for (int e = 0; e < n_ends; e++) {
                 sink.names[e] = job.file_prefix + "_R" + std::to_string(e + 1) + ".fq";   // src/hts.h:344
-                if (zmethod >= 0) sink.names[e] += ".gz";                                 // src/io.h:126,217
+                if (want_gz) sink.names[e] += ".gz";                                      // src/io.h:126,217
                 sink.fd[e] = ::open(sink.names[e].c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
                 if (sink.fd[e] < 0) throw IoErr("Unable to open file " + sink.names[e] + ".\n");  // src/io.h:288-290
             }
@@ -653,8 +680,14 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
             CK(launch_offsets(gp, c->s_compute));
             CK(cudaEventRecord(s.ev[2], c->s_compute));
             CK(launch_reads(gp, c->n_sm, c->s_compute));
-            CK(cudaMemcpyAsync(s.h_totals.p, s.totals.p, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->s_compute));
             CK(cudaEventRecord(s.ev[3], c->s_compute));
+            if (dev_z) {
+                CK(launch_bgzf(s.out[0].p, s.out[1].p, s.totals.p, nblk_max, s.zslots[0].p, s.zslots[1].p, s.zlen[0].p,
+                               s.zlen[1].p, s.zoff[0].p, s.zoff[1].p, s.zdev[0].p, s.zdev[1].p, c->s_compute));
+                st.kernel_launches += 3;
+            }
+            CK(cudaMemcpyAsync(s.h_totals.p, s.totals.p, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->s_compute));
+            CK(cudaEventRecord(s.ev[5], c->s_compute));
             st.kernel_launches += 5;
             s.pairs = np; s.busy = true;
             computing.push_back(&s);
@@ -662,7 +695,7 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
             if (computing.size() > 1) { issue_copy(*computing.front()); copying.push_back(computing.front()); computing.pop_front(); }
             if (copying.size() > 1) { deliver(*copying.front()); copying.pop_front(); }
             if (P->abort_cb && P->abort_cb(P->cb_user)) {
-                for (Slot& t : c->slot) if (t.busy) { cudaEventSynchronize(t.ev[3]); cudaStreamSynchronize(c->s_copy); t.busy = false; }
+                for (Slot& t : c->slot) if (t.busy) { cudaEventSynchronize(t.ev[5]); cudaStreamSynchronize(c->s_copy); t.busy = false; }
                 for (Slot& t : c->slot) c->writers.wait(t.writes);
                 throw Aborted();
             }
@@ -670,11 +703,20 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
         while (!computing.empty() || !copying.empty()) drain_one();
         if (z_pending) { wait_writes(*z_pending); z_pending = nullptr; }
         for (Slot& s : c->slot) wait_writes(s);
-        if (sink.kind == SINK_FILES && zmethod == DEFLATE_BGZF)
+        if (sink.kind == SINK_FILES && (zmethod == DEFLATE_BGZF || dev_z))
             for (int e = 0; e < n_ends; e++) {   // bgzf_close appends the empty end-of-file block
                 std::string w = pwrite_all(sink.fd[e], kBgzfEof, sizeof kBgzfEof, sink.pos[e]);
                 if (!w.empty()) throw IoErr("Error writing to file " + sink.names[e] + ": " + w);
                 sink.pos[e] += sizeof kBgzfEof;
+            }
+        if (dev_z && sink.kind == SINK_STREAM)
+            for (int e = 0; e < n_ends; e++)
+                if (sink.chunk_cb(sink.chunk_user, job_index, e, reinterpret_cast<const char*>(kBgzfEof), sizeof kBgzfEof))
+                    throw IoErr("the chunk callback reported an error");
+        if (dev_z && sink.kind == SINK_MEMORY)
+            for (int e = 0; e < n_ends; e++) {
+                if (sink.len[e] + sizeof kBgzfEof <= sink.cap[e]) std::memcpy(sink.mem[e] + sink.len[e], kBgzfEof, sizeof kBgzfEof);
+                sink.len[e] += sizeof kBgzfEof;
             }
         job_index++;
     }
@@ -725,6 +767,7 @@ int jlp_ctx_create(int device, jlp_ctx** out) {
         CK(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&c->s_upload, cudaStreamNonBlocking));
+        CK(bgzf_init());
     });
     if (rc != JLP_OK) { g_create_error = c->err; return rc; }
     *out = c.release();
@@ -1011,6 +1054,32 @@ int jlp_deflate(int bgzf, int level, const void* in, uint64_t n, void* out, uint
     if (v.size() > cap) return JLP_ERR_ARG;
     std::memcpy(out, v.data(), v.size());
     return JLP_OK;
+}
+
+int jlp_bgzf_device(jlp_ctx* c, const void* in, uint64_t n, void* out, uint64_t cap, uint64_t* len) {
+    if (!c) return JLP_ERR_ARG;
+    return guarded(c, [&]() {
+        if ((n && !in) || !len) throw ArgErr("NULL argument");
+        const uint32_t nblk = (uint32_t)((n + kBgzfIn - 1) / kBgzfIn);
+        DevBuf<uint8_t> d_in, d_slots, d_out;
+        DevBuf<uint32_t> d_zlen;
+        DevBuf<uint64_t> d_zoff, d_tot;
+        d_in.ensure(n + 64); d_slots.ensure((size_t)nblk * kBgzfSlot); d_out.ensure((size_t)nblk * kBgzfSlot);
+        d_zlen.ensure(nblk); d_zoff.ensure(nblk); d_tot.ensure(4);
+        const uint64_t tot[4] = {n, 0, 0, 0};
+        if (n) CK(cudaMemcpyAsync(d_in.p, in, n, cudaMemcpyHostToDevice, c->s_compute));
+        CK(cudaMemcpyAsync(d_tot.p, tot, sizeof tot, cudaMemcpyHostToDevice, c->s_compute));
+        CK(launch_bgzf(d_in.p, d_in.p, d_tot.p, nblk, d_slots.p, d_slots.p, d_zlen.p, d_zlen.p, d_zoff.p, d_zoff.p, d_out.p,
+                       d_out.p, c->s_compute));
+        uint64_t back[4];
+        CK(cudaMemcpyAsync(back, d_tot.p, sizeof back, cudaMemcpyDeviceToHost, c->s_compute));
+        CK(cudaStreamSynchronize(c->s_compute));
+        *len = back[2] + sizeof kBgzfEof;
+        if (!out) return;
+        if (cap < *len) throw ArgErr("output buffer too small");
+        if (back[2]) CK(cudaMemcpy(out, d_out.p, back[2], cudaMemcpyDeviceToHost));
+        std::memcpy(static_cast<uint8_t*>(out) + back[2], kBgzfEof, sizeof kBgzfEof);
+    });
 }
 
 int jlp_shard_range(uint64_t job_lo, uint64_t job_hi, uint32_t shard_index, uint32_t shard_count, uint64_t* lo,

@@ -202,7 +202,7 @@ def default_context(device=0):
 def _prepare(obj, out_prefix, n_reads, read_length, paired, frag_mean, frag_sd, matepair, seq_sys, profile1,
              profile2, ins_prob1, del_prob1, ins_prob2, del_prob2, frag_len_min, frag_len_max, haplotype_probs,
              barcodes, prob_dup, sep_files, compress, comp_method, n_threads, read_pool_size, show_progress,
-             overwrite, seed, batch_pairs, shard, check_files):
+             overwrite, seed, batch_pairs, shard, check_files, comp_engine="auto"):
     """Everything illumina() does before calling into C++ (R/hts_illumina.R:621-731).
     Returns (params struct, keep-alive list, flattened profiles)."""
     if matepair:
@@ -272,6 +272,9 @@ def _prepare(obj, out_prefix, n_reads, read_length, paired, frag_mean, frag_sd, 
     p.seed = int(seed) & (2 ** 64 - 1)
     p.batch_pairs = int(batch_pairs or 0)
     p.shard_index, p.shard_count = (int(shard[0]), int(shard[1])) if shard else (0, 1)
+    if comp_engine not in ("auto", "host", "device"):
+        raise JackalopeError("comp_engine must be \"auto\", \"host\" or \"device\"")
+    p.comp_engine = {"auto": 0, "host": 1, "device": 2}[comp_engine]
     return p, keep, (prof1, prof2), is_haps, fns
 
 
@@ -280,14 +283,16 @@ def illumina(obj, out_prefix, n_reads, read_length, paired, frag_mean=400, frag_
              ins_prob2=0.00015, del_prob2=0.00023, frag_len_min=None, frag_len_max=None, haplotype_probs=None,
              barcodes=None, prob_dup=0.02, sep_files=False, compress=False, comp_method="bgzip", n_threads=1,
              read_pool_size=1000, show_progress=False, overwrite=False, *, seed=None, device=0, ctx=None,
-             batch_pairs=None, shard=None, sink="files"):
+             batch_pairs=None, shard=None, sink="files", comp_engine="auto"):
     """Create and write Illumina reads to FASTQ file(s).
 
     Positional and keyword arguments up to ``overwrite`` are the reference's.
     Keyword-only additions: ``seed`` (the reference draws its seeds from R's RNG;
     here ``None`` draws one from numpy's global RNG, so ``np.random.seed`` plays
     the part of ``set.seed``), ``device``/``ctx`` (which GPU), ``batch_pairs``,
-    ``shard=(index, count)``, and ``sink``: "files" (default, returns ``None``
+    ``shard=(index, count)``, ``comp_engine`` ("auto": files compressed at levels 1-6 come from the device
+    BGZF coder, levels 7-9 from zlib on the writer threads; "host"; "device": also memory and callable sinks
+    receive BGZF bytes), and ``sink``: "files" (default, returns ``None``
     like the reference), "memory" (returns ``(r1_bytes, r2_bytes, stats)``) or
     "device" (generate and discard on the GPU; returns ``stats``), or a callable
     ``sink(job, end, buffer)`` that receives every batch's FASTQ bytes from the library's
@@ -298,7 +303,7 @@ def illumina(obj, out_prefix, n_reads, read_length, paired, frag_mean=400, frag_
         obj, out_prefix, n_reads, read_length, paired, frag_mean, frag_sd, matepair, seq_sys, profile1, profile2,
         ins_prob1, del_prob1, ins_prob2, del_prob2, frag_len_min, frag_len_max, haplotype_probs, barcodes, prob_dup,
         sep_files, compress, comp_method, n_threads, read_pool_size, show_progress, overwrite, seed, batch_pairs,
-        shard, check_files=(isinstance(sink, str) and sink == "files"))
+        shard, check_files=(isinstance(sink, str) and sink == "files"), comp_engine=comp_engine)
     ctx = ctx or default_context(device)
     if is_haps:
         ctx.set_haplotypes(obj)
