@@ -38,21 +38,24 @@ __constant__ uint32_t c_crc_adv[17][32];   // operator "advance the CRC register
 
 struct ZShared {
     uint32_t stage[kStageWords];          // the block image
-    uint32_t hist[kZW][288];              // per-warp literal counts
+    uint32_t hist[kZW][256];              // per-warp literal counts
     uint32_t cnt[288];                    // literal/length counts; [256] = end of block
     uint32_t crc_tab[256];
-    uint32_t crc[kZT];
     uint32_t ctab[256];                   // code (bit-reversed, LSB first) | length << 16 per literal
-    uint32_t warp_sum[kZW];
+    uint32_t sw[288];                     // Huffman: weights of the leaves in sorted order
+    uint32_t w_int[288];                  // ... of the internal nodes in creation order
+    uint32_t scan_tmp[kZW + 1];
+    uint32_t crc_w[kZW];
+    uint32_t bl[16];                      // codes per length
+    uint32_t cl_cnt[19];                  // counts of the code-length alphabet
     uint16_t sorted[288];                 // symbols with count > 0, ascending count
-    uint8_t len[320];                     // code lengths: [0, 286) literal/length, [286, 316) distance
+    uint16_t par_leaf[288], par_int[288]; // parent (internal node index) of leaves / internal nodes
     uint16_t code[288];
-    uint32_t w_int[288];                  // Huffman scratch: internal node weights
-    uint16_t par_leaf[288], par_int[288];
+    uint16_t cl_code[19];
+    alignas(16) uint8_t len[320];         // code lengths: [0, 257) literals and end of block, [257, 259) the two distance codes
     uint8_t d_int[288];
-    uint16_t tok[336];                    // run-length tokens of the code lengths: symbol | extra << 5
-    uint32_t next_code[16];
-    uint32_t n_active, n_tok, hdr_bits, eob, total_bits, stored, crc_out;
+    uint8_t cl_len[19];
+    uint32_t maxd, hdr_fixed_bits, hdr_bits, eob, total_bits, stored, crc_out;
 };
 
 __device__ __forceinline__ uint32_t crc_apply(const uint32_t* m, uint32_t v) {
@@ -68,36 +71,43 @@ __device__ uint32_t crc_advance(uint32_t v, uint32_t n) {
     return v;
 }
 
-// serial bit writer into the zeroed block image (one thread)
-struct BitW {
-    uint32_t* w; uint32_t pos;
-    __device__ void put(uint32_t v, uint32_t n) {
-        if (!n) return;
-        const uint32_t i = pos >> 5, s = pos & 31;
-        w[i] |= v << s;
-        if (s + n > 32) w[i + 1] |= v >> (32 - s);
-        pos += n;
-    }
-};
+// bits OR-ed into the zeroed block image at a bit position; threads write disjoint bits of shared words
+__device__ __forceinline__ void put_bits(uint32_t* w, uint32_t& pos, uint32_t v, uint32_t n) {
+    if (!n) return;
+    const uint32_t i = pos >> 5, s = pos & 31;
+    atomicOr(&w[i], v << s);
+    if (s + n > 32) atomicOr(&w[i + 1], v >> (32 - s));
+    pos += n;
+}
 
-// Code lengths (<= max_bits) of the symbols sorted[0 .. n) (ascending count) into len[sym].
-// Two-queue Huffman, then the count fix-up for over-long codes, then lengths handed out in
-// sorted order (longest code to the rarest symbol).  One thread.
-__device__ void huff_lengths(ZShared& S, const uint32_t* cnt, uint32_t n, uint32_t max_bits, uint8_t* len) {
-    if (n == 0) return;
-    if (n == 1) { len[S.sorted[0]] = 1; return; }
+// Two-queue Huffman over the leaves S.sw[0 .. n) (ascending): parents into par_leaf / par_int, the root is
+// internal node n - 2.  One thread; the heads of both queues are kept in registers.
+__device__ void huff_merge(ZShared& S, uint32_t n) {
     uint32_t i = 0, k = 0, m = 0;
+    uint32_t lw = S.sw[0], iw = 0xffffffffu;
     while (m + 1 < n) {
         uint32_t w = 0;
+#pragma unroll
         for (int q = 0; q < 2; q++) {
-            const bool leaf = i < n && (k >= m || cnt[S.sorted[i]] <= S.w_int[k]);
-            if (leaf) { w += cnt[S.sorted[i]]; S.par_leaf[i++] = (uint16_t)m; }
-            else { w += S.w_int[k]; S.par_int[k++] = (uint16_t)m; }
+            if (i < n && (k >= m || lw <= iw)) {
+                w += lw; S.par_leaf[i] = (uint16_t)m; i++;
+                lw = i < n ? S.sw[i] : 0xffffffffu;
+            } else {
+                w += iw; S.par_int[k] = (uint16_t)m; k++;
+                iw = k < m ? S.w_int[k] : 0xffffffffu;
+            }
         }
-        S.w_int[m++] = w;
+        S.w_int[m] = w;
+        if (k == m) iw = w;
+        m++;
     }
-    uint32_t bl[16];
-    for (uint32_t b = 0; b < 16; b++) bl[b] = 0;
+}
+
+// Code lengths limited to max_bits from the tree huff_merge left (one thread): depths top-down, clamped, then the
+// count fix-up for over-long codes, then lengths handed out in sorted order (longest code to the rarest symbol).
+// Leaves S.bl[] = codes per length.
+__device__ void huff_limit(ZShared& S, uint32_t n, uint32_t max_bits, uint8_t* len) {
+    for (uint32_t b = 0; b < 16; b++) S.bl[b] = 0;
     int overflow = 0;
     S.d_int[n - 2] = 0;
     for (int q = (int)n - 3; q >= 0; q--) {
@@ -108,40 +118,58 @@ __device__ void huff_lengths(ZShared& S, const uint32_t* cnt, uint32_t n, uint32
     for (uint32_t q = 0; q < n; q++) {
         uint32_t d = S.d_int[S.par_leaf[q]] + 1u;
         if (d > max_bits) { d = max_bits; overflow++; }
-        bl[d]++;
+        S.bl[d]++;
     }
     while (overflow > 0) {
         uint32_t b = max_bits - 1;
-        while (bl[b] == 0) b--;
-        bl[b]--; bl[b + 1] += 2; bl[max_bits]--;
+        while (S.bl[b] == 0) b--;
+        S.bl[b]--; S.bl[b + 1] += 2; S.bl[max_bits]--;
         overflow -= 2;
     }
     // Kraft check; a code that does not add up is replaced by a flat one (never seen, kept as a guard)
     uint32_t kraft = 0;
-    for (uint32_t b = 1; b <= max_bits; b++) kraft += bl[b] << (max_bits - b);
+    for (uint32_t b = 1; b <= max_bits; b++) kraft += S.bl[b] << (max_bits - b);
     if (kraft != (1u << max_bits)) {
         uint32_t flat = 1;
         while ((1u << flat) < n) flat++;
+        for (uint32_t b = 0; b < 16; b++) S.bl[b] = 0;
+        S.bl[flat] = n;
         for (uint32_t q = 0; q < n; q++) len[S.sorted[q]] = (uint8_t)flat;
         return;
     }
     uint32_t q = 0;
     for (uint32_t b = max_bits; b >= 1; b--)
-        for (uint32_t c = bl[b]; c; c--) len[S.sorted[q++]] = (uint8_t)b;
+        for (uint32_t c = S.bl[b]; c; c--) len[S.sorted[q++]] = (uint8_t)b;
 }
 
 __device__ __forceinline__ uint32_t rev_bits(uint32_t code, uint32_t n) { return __brev(code) >> (32 - n); }
 
-// canonical codes of a small alphabet (one thread); code[] bit-reversed for LSB-first packing
-__device__ void small_codes(const uint8_t* len, uint32_t n_sym, uint32_t max_bits, uint16_t* code) {
-    uint32_t bl[16], next[16];
-    for (uint32_t b = 0; b < 16; b++) bl[b] = 0;
-    for (uint32_t s = 0; s < n_sym; s++) bl[len[s]]++;
-    bl[0] = 0;
+// first canonical code of length l, from the codes per length
+__device__ __forceinline__ uint32_t first_code(const uint32_t* bl, uint32_t l) {
     uint32_t c = 0;
-    for (uint32_t b = 1; b <= max_bits; b++) { c = (c + bl[b - 1]) << 1; next[b] = c; }
-    for (uint32_t s = 0; s < n_sym; s++)
-        if (len[s]) code[s] = (uint16_t)rev_bits(next[len[s]]++, len[s]);
+    for (uint32_t q = 1; q <= l; q++) c = (c + (q > 1 ? bl[q - 1] : 0u)) << 1;
+    return c;
+}
+
+// exclusive prefix of v over the CTA and the total (two barriers)
+__device__ __forceinline__ uint32_t block_scan(uint32_t v, uint32_t* tmp, uint32_t& total) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += x; }
+    if (lane == 31) tmp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t x = lane < kZW ? tmp[lane] : 0u;
+        uint32_t xi = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, xi, o); if (lane >= (uint32_t)o) xi += y; }
+        if (lane < kZW) tmp[lane] = xi - x;
+        if (lane == kZW - 1) tmp[kZW] = xi;
+    }
+    __syncthreads();
+    total = tmp[kZW];
+    return tmp[warp] + incl - v;
 }
 
 template <bool FULL, typename F>
@@ -187,6 +215,28 @@ __device__ __forceinline__ void pack(const uint4 (&d)[8], uint32_t my_len, const
     if (nb) atomicOr(&stage[wi], (uint32_t)acc);
 }
 
+// The run of equal code lengths starting at a position, as the tokens of RFC 1951 section 3.2.7:
+// zeros: 18 (11..138 zeros, 7 extra bits), 17 (3..10, 3 bits), else literal 0s; a length v: v once, then
+// 16 (repeat 3..6 times, 2 bits), else literal v's.
+struct RunTok {
+    uint32_t v, n_big, big_extra_last, n_mid, mid_extra, n_lit;   // zeros: big = 18, mid = 17; else big = 16, mid unused
+};
+__device__ __forceinline__ RunTok run_tokens(uint32_t v, uint32_t run) {
+    RunTok r{v, 0, 0, 0, 0, 0};
+    if (v == 0) {
+        r.n_big = run / 138; uint32_t rem = run % 138;
+        if (rem >= 11) { r.n_big++; r.big_extra_last = rem - 11; rem = 0; } else r.big_extra_last = 127;
+        if (rem >= 3) { r.n_mid = 1; r.mid_extra = rem - 3; rem = 0; }
+        r.n_lit = rem;
+    } else {
+        uint32_t rem = run - 1;
+        r.n_big = rem / 6; rem %= 6;
+        if (rem >= 3) { r.n_big++; r.big_extra_last = rem - 3; rem = 0; } else r.big_extra_last = 3;
+        r.n_lit = 1 + rem;
+    }
+    return r;
+}
+
 __global__ void __launch_bounds__(kZT, 1)
 k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const uint64_t* __restrict__ totals, uint32_t nblk_max,
        uint8_t* __restrict__ slots0, uint8_t* __restrict__ slots1, uint32_t* __restrict__ zlen0, uint32_t* __restrict__ zlen1) {
@@ -216,9 +266,12 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
         uint4* s4 = reinterpret_cast<uint4*>(S.stage);
         for (uint32_t i = t; i < kStageWords / 4; i += kZT) s4[i] = make_uint4(0, 0, 0, 0);
         uint32_t* h = &S.hist[0][0];
-        for (uint32_t i = t; i < kZW * 288; i += kZT) h[i] = 0;
+        for (uint32_t i = t; i < kZW * 256; i += kZT) h[i] = 0;
         if (t < 256) S.crc_tab[t] = c_crc_tab[t];
-        if (t < 320) S.len[t] = 0;
+        if (t < 320) S.len[t] = (t == 257 || t == 258) ? 1 : 0;   // two unused distance codes of one bit, as zlib sends for a block of literals
+        if (t < 16) S.bl[t] = 0;
+        if (t < 19) { S.cl_cnt[t] = 0; S.cl_len[t] = 0; }
+        if (t == 0) S.maxd = 0;
     }
     __syncthreads();
 
@@ -226,22 +279,34 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
     uint32_t crc;
     if (my_len == kChunk) pass1<true>(d, my_len, S.hist[warp], S.crc_tab, crc);
     else pass1<false>(d, my_len, S.hist[warp], S.crc_tab, crc);
-    S.crc[t] = crc;
+    // CRC tree inside the warp: the node at lane covers chunks [t, t + 2s); its right half has right_len bytes
+#pragma unroll
+    for (uint32_t s = 1; s < 32; s <<= 1) {
+        const uint32_t other = __shfl_down_sync(0xffffffffu, crc, s);
+        if ((lane & (2 * s - 1)) == 0) {
+            const uint32_t r0 = (t + s) * kChunk;
+            crc = crc_advance(crc, r0 >= len ? 0u : min(s * kChunk, len - r0)) ^ other;
+        }
+    }
+    if (lane == 0) S.crc_w[warp] = crc;
     __syncthreads();
     uint32_t my_cnt = 0;
-    if (t < 288) {
+    if (t <= 256) {
         if (t < 256) for (int w = 0; w < kZW; w++) my_cnt += S.hist[w][t];
-        if (t == 256) my_cnt = 1;     // end of block
+        else my_cnt = 1;     // end of block
         S.cnt[t] = my_cnt;
     }
-    // CRC tree: the node at t covers chunks [t, t + 2s); the right half has right_len bytes
-    for (uint32_t s = 1; s < kZT; s <<= 1) {
-        __syncthreads();
-        if ((t & (2 * s - 1)) == 0) {
-            const uint32_t r0 = (t + s) * kChunk;
-            const uint32_t right_len = r0 >= len ? 0u : min(s * kChunk, len - r0);
-            S.crc[t] = crc_advance(S.crc[t], right_len) ^ S.crc[t + s];
+    if (warp == kZW - 1) {   // the last warp finishes the CRC over the warps' results
+        crc = lane < kZW ? S.crc_w[lane] : 0u;
+#pragma unroll
+        for (uint32_t s = 1; s < kZW; s <<= 1) {
+            const uint32_t other = __shfl_down_sync(0xffffffffu, crc, s);
+            if ((lane & (2 * s - 1)) == 0 && lane < kZW) {
+                const uint32_t r0 = (lane + s) * 32u * kChunk;
+                crc = crc_advance(crc, r0 >= len ? 0u : min(s * 32u * kChunk, len - r0)) ^ other;
+            }
         }
+        if (lane == 0) S.crc_out = crc ^ crc_advance(0xffffffffu, len) ^ 0xffffffffu;
     }
     const uint32_t n_active = __syncthreads_count(my_cnt != 0);
     // rank sort of the active symbols (ascending count, ties by symbol)
@@ -252,152 +317,171 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
             rank += (c != 0 && (c < my_cnt || (c == my_cnt && s < t))) ? 1u : 0u;
         }
         S.sorted[rank] = (uint16_t)t;
+        S.sw[rank] = my_cnt;
     }
-    if (t == 32) S.crc_out = S.crc[0] ^ crc_advance(0xffffffffu, len) ^ 0xffffffffu;
     __syncthreads();
 
-    // ---- literal code lengths (one thread), canonical codes (all)
-    if (t == 0) {
-        huff_lengths(S, S.cnt, n_active, 15, S.len);
-        uint32_t bl[16];
-        for (int q = 0; q < 16; q++) bl[q] = 0;
-        for (uint32_t s = 0; s <= 256; s++) bl[S.len[s]]++;
-        bl[0] = 0;
-        uint32_t c = 0;
-        for (uint32_t q = 1; q < 16; q++) { c = (c + bl[q - 1]) << 1; S.next_code[q] = c; }
+    // ---- literal code lengths: the tree by one thread, the depths by one thread per leaf
+    if (t == 0) huff_merge(S, n_active);       // n_active >= 2: a literal and the end of block
+    __syncthreads();
+    if (t < n_active) {
+        uint32_t p = S.par_leaf[t], dep = 1;
+        const uint32_t root = n_active - 2;
+        while (p != root) { p = S.par_int[p]; dep++; }
+        S.len[S.sorted[t]] = (uint8_t)min(dep, 15u);
+        atomicAdd(&S.bl[min(dep, 15u)], 1u);
+        if (dep > 15) atomicMax(&S.maxd, dep);
     }
     __syncthreads();
-    if (t < 288) {
-        const uint32_t l = t < kNLit ? S.len[t] : 0;
+    if (S.maxd > 15) {                         // rare: the 15-bit limit has to act
+        if (t == 0) huff_limit(S, n_active, 15, S.len);
+        __syncthreads();
+    }
+    // canonical codes: first code of the length + the symbols of the same length before this one
+    if (t <= 256) {
+        const uint32_t l = S.len[t];
         if (l) {
-            // canonical order inside a length is by symbol
+            const uint32_t pat = l * 0x01010101u;
+            const uint32_t* lw = reinterpret_cast<const uint32_t*>(S.len);
             uint32_t same = 0;
-            for (uint32_t s = 0; s < t; s++) same += S.len[s] == l ? 1u : 0u;
-            S.code[t] = (uint16_t)rev_bits(S.next_code[l] + same, l);
+            for (uint32_t j = 0; j < t / 4; j++) same += __popc(__vcmpeq4(lw[j], pat));
+            same += __popc(__vcmpeq4(lw[t / 4], pat) & ((1u << (8 * (t & 3))) - 1u));
+            S.code[t] = (uint16_t)rev_bits(first_code(S.bl, l) + same / 8, l);
+        }
+    }
+    // the runs of the code-length sequence [0, 259): one thread per run counts its tokens
+    RunTok rt{0, 0, 0, 0, 0, 0};
+    bool run_start = false;
+    if (t < 259) {
+        const uint32_t v = S.len[t];
+        run_start = t == 0 || S.len[t - 1] != v;
+        if (run_start) {
+            uint32_t run = 1;
+            while (t + run < 259 && S.len[t + run] == v) run++;
+            rt = run_tokens(v, run);
+            if (v == 0) {
+                if (rt.n_big) atomicAdd(&S.cl_cnt[18], rt.n_big);
+                if (rt.n_mid) atomicAdd(&S.cl_cnt[17], 1u);
+                if (rt.n_lit) atomicAdd(&S.cl_cnt[0], rt.n_lit);
+            } else {
+                if (rt.n_big) atomicAdd(&S.cl_cnt[16], rt.n_big);
+                atomicAdd(&S.cl_cnt[v], rt.n_lit);
+            }
         }
     }
     __syncthreads();
     if (t < 256) S.ctab[t] = S.len[t] ? (uint32_t)S.code[t] | (uint32_t)S.len[t] << 16 : 0u;
 
-    // ---- header of the dynamic block: run-length coded code lengths and their own code (one thread)
+    // ---- the code-length code and the fixed part of the block header (one thread) while the others size their chunks
+    uint32_t bits = 0;
     if (t == 0) {
-        // no length symbols; two unused distance codes of one bit each, as zlib sends for a block of
-        // literals ("at least one distance code exists and at least one bit is sent", trees.c)
-        const uint32_t hlit = 257, hdist = 2;
-        const uint32_t N = hlit + hdist;
-        uint8_t* L = S.len;                            // [0, 257) literal/length lengths, then the distance code lengths
-        L[257] = 1; L[258] = 1;
-        uint32_t nt = 0;
-        uint32_t clc[19];
-        for (int q = 0; q < 19; q++) clc[q] = 0;
-        auto tok = [&](uint32_t sym, uint32_t extra) { S.tok[nt++] = (uint16_t)(sym | extra << 5); clc[sym]++; };
-        for (uint32_t i = 0; i < N;) {
-            const uint32_t v = L[i];
-            uint32_t run = 1;
-            while (i + run < N && L[i + run] == v) run++;
-            uint32_t r = run;
-            if (v == 0) {
-                while (r >= 11) { const uint32_t k = r < 138 ? r : 138; tok(18, k - 11); r -= k; }
-                if (r >= 3) { tok(17, r - 3); r = 0; }
-                while (r) { tok(0, 0); r--; }
-            } else {
-                tok(v, 0); r--;
-                while (r >= 3) { const uint32_t k = r < 6 ? r : 6; tok(16, k - 3); r -= k; }
-                while (r) { tok(v, 0); r--; }
-            }
-            i += run;
-        }
-        L[257] = 0; L[258] = 0;
-        S.n_tok = nt;
-        // code-length code: sort its used symbols, lengths <= 7, codes
         uint32_t n_cl = 0;
-        for (uint32_t s = 0; s < 19; s++)
-            if (clc[s]) {
+        for (uint32_t s = 0; s < 19; s++) {
+            const uint32_t c = S.cl_cnt[s];
+            if (c) {
                 uint32_t p = n_cl++;
-                while (p > 0 && (clc[S.sorted[p - 1]] > clc[s])) { S.sorted[p] = S.sorted[p - 1]; p--; }
-                S.sorted[p] = (uint16_t)s;
+                while (p > 0 && S.sw[p - 1] > c) { S.sw[p] = S.sw[p - 1]; S.sorted[p] = S.sorted[p - 1]; p--; }
+                S.sw[p] = c; S.sorted[p] = (uint16_t)s;
             }
-        uint8_t cl_len[19];
-        uint16_t cl_code[19];
-        for (int q = 0; q < 19; q++) { cl_len[q] = 0; cl_code[q] = 0; }
-        huff_lengths(S, clc, n_cl, 7, cl_len);
-        small_codes(cl_len, 19, 7, cl_code);
+        }
+        if (n_cl == 1) {                       // a complete code needs two symbols
+            S.cl_len[S.sorted[0]] = 1; S.cl_len[S.sorted[0] ? 0 : 1] = 1;
+            for (uint32_t q = 0; q < 16; q++) S.bl[q] = 0;
+            S.bl[1] = 2;
+        } else {
+            huff_merge(S, n_cl);
+            huff_limit(S, n_cl, 7, S.cl_len);
+        }
+        uint32_t next[8];
+        uint32_t c = 0;
+        next[0] = 0;
+#pragma unroll
+        for (uint32_t q = 1; q < 8; q++) { c = (c + (q > 1 ? S.bl[q - 1] : 0u)) << 1; next[q] = c; }
+        for (uint32_t s = 0; s < 19; s++) {
+            const uint32_t l = S.cl_len[s];
+            uint32_t code = 0;
+#pragma unroll
+            for (uint32_t q = 1; q < 8; q++) if (l == q) code = next[q]++;
+            S.cl_code[s] = (uint16_t)(l ? rev_bits(code, l) : 0u);
+        }
         const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
         uint32_t hclen = 19;
-        while (hclen > 4 && cl_len[order[hclen - 1]] == 0) hclen--;
-        BitW bw{S.stage, kHdr * 8};
-        bw.put(1, 1); bw.put(2, 2);                   // BFINAL, BTYPE = dynamic Huffman
-        bw.put(hlit - 257, 5); bw.put(hdist - 1, 5); bw.put(hclen - 4, 4);
-        for (uint32_t q = 0; q < hclen; q++) bw.put(cl_len[order[q]], 3);
-        for (uint32_t q = 0; q < nt; q++) {
-            const uint32_t sym = S.tok[q] & 31u, extra = S.tok[q] >> 5;
-            bw.put(cl_code[sym], cl_len[sym]);
-            if (sym == 16) bw.put(extra, 2);
-            else if (sym == 17) bw.put(extra, 3);
-            else if (sym == 18) bw.put(extra, 7);
-        }
-        S.hdr_bits = bw.pos;
+        while (hclen > 4 && S.cl_len[order[hclen - 1]] == 0) hclen--;
+        uint32_t pos = kHdr * 8;
+        put_bits(S.stage, pos, 1, 1); put_bits(S.stage, pos, 2, 2);                   // BFINAL, BTYPE = dynamic Huffman
+        put_bits(S.stage, pos, 0, 5); put_bits(S.stage, pos, 1, 5); put_bits(S.stage, pos, hclen - 4, 4);   // HLIT = 257, HDIST = 2
+        for (uint32_t q = 0; q < hclen; q++) put_bits(S.stage, pos, S.cl_len[order[q]], 3);
+        S.hdr_fixed_bits = pos;
         S.eob = (uint32_t)S.code[256] | (uint32_t)S.len[256] << 16;
     }
+    bits = my_len == kChunk ? size_bits<true>(d, my_len, S.ctab) : size_bits<false>(d, my_len, S.ctab);
     __syncthreads();
 
-    // ---- pass 2: size, scan, pack
-    uint32_t bits = my_len == kChunk ? size_bits<true>(d, my_len, S.ctab) : size_bits<false>(d, my_len, S.ctab);
-    uint32_t incl = bits;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += v; }
-    if (lane == 31) S.warp_sum[warp] = incl;
-    __syncthreads();
-    if (t == 0) {
-        uint32_t run = S.hdr_bits;
-        for (int w = 0; w < kZW; w++) { const uint32_t v = S.warp_sum[w]; S.warp_sum[w] = run; run += v; }
-        const uint32_t end_bits = run + (S.eob >> 16);
-        S.total_bits = end_bits;
-        S.stored = ((end_bits + 7) / 8 - kHdr) >= len + 5 ? 1u : 0u;
+    // ---- one scan for both the header tokens of the runs and the chunks: header bits << 20 | chunk bits
+    uint32_t hb = 0;
+    uint32_t l_big = 0, c_big = 0, l_mid = 0, c_mid = 0, l_lit = 0, c_lit = 0;
+    if (run_start) {
+        const uint32_t big = rt.v == 0 ? 18u : 16u, xb = rt.v == 0 ? 7u : 2u;
+        l_big = S.cl_len[big]; c_big = S.cl_code[big];
+        l_mid = S.cl_len[17]; c_mid = S.cl_code[17];
+        l_lit = S.cl_len[rt.v]; c_lit = S.cl_code[rt.v];
+        hb = rt.n_big * (l_big + xb) + rt.n_mid * (l_mid + 3u) + rt.n_lit * l_lit;
     }
-    __syncthreads();
-    uint32_t bitpos = S.warp_sum[warp] + incl - bits;
-    const bool stored = S.stored != 0;
-    if (stored) {
+    uint32_t total;
+    const uint32_t excl = block_scan(hb << 20 | bits, S.scan_tmp, total);
+    const uint32_t hdr_bits = S.hdr_fixed_bits + (total >> 20);
+    const uint32_t eob = S.eob;
+    const uint32_t end_bits = hdr_bits + (total & 0xfffffu) + (eob >> 16);
+    const bool stored = ((end_bits + 7) / 8 - kHdr) >= len + 5;     // uniform
+    uint32_t bitpos, total_bits;
+    if (!stored) {
+        if (run_start) {
+            uint32_t pos = S.hdr_fixed_bits + (excl >> 20);
+            if (rt.v == 0) {
+                for (uint32_t q = 0; q < rt.n_big; q++) { put_bits(S.stage, pos, c_big, l_big); put_bits(S.stage, pos, q + 1 == rt.n_big ? rt.big_extra_last : 127u, 7); }
+                if (rt.n_mid) { put_bits(S.stage, pos, c_mid, l_mid); put_bits(S.stage, pos, rt.mid_extra, 3); }
+                for (uint32_t q = 0; q < rt.n_lit; q++) put_bits(S.stage, pos, c_lit, l_lit);
+            } else {
+                put_bits(S.stage, pos, c_lit, l_lit);
+                for (uint32_t q = 0; q < rt.n_big; q++) { put_bits(S.stage, pos, c_big, l_big); put_bits(S.stage, pos, q + 1 == rt.n_big ? rt.big_extra_last : 3u, 2); }
+                for (uint32_t q = 1; q < rt.n_lit; q++) put_bits(S.stage, pos, c_lit, l_lit);
+            }
+        }
+        bitpos = hdr_bits + (excl & 0xfffffu);
+        total_bits = end_bits;
+    } else {
         // does not shrink: stored block (BTYPE 00) through the same packing code with the identity table
-        const uint32_t clear_words = (S.hdr_bits + 31) / 32 + 1;
+        const uint32_t clear_words = (S.hdr_fixed_bits + 31) / 32 + 1;
         __syncthreads();
-        for (uint32_t i = t; i < clear_words; i += kZT) S.stage[i] = 0;
+        for (uint32_t i = kHdr / 4 + t; i < clear_words; i += kZT) S.stage[i] = 0;
         if (t < 256) S.ctab[t] = t | 8u << 16;
         __syncthreads();
         if (t == 0) {
-            BitW bw{S.stage, kHdr * 8};
-            bw.put(1, 8);                              // BFINAL = 1, BTYPE = 00, padding to the byte
-            bw.put(len, 16); bw.put(len ^ 0xffffu, 16);
-            S.total_bits = bw.pos + len * 8;
+            uint32_t pos = kHdr * 8;
+            put_bits(S.stage, pos, 1, 8);                              // BFINAL = 1, BTYPE = 00, padding to the byte
+            put_bits(S.stage, pos, len, 16); put_bits(S.stage, pos, len ^ 0xffffu, 16);
         }
         bitpos = (kHdr + 5 + my_off) * 8;
-        __syncthreads();
+        total_bits = (kHdr + 5 + len) * 8;
     }
     if (my_len == kChunk) pack<true>(d, my_len, S.ctab, S.stage, bitpos);
     else if (my_len) pack<false>(d, my_len, S.ctab, S.stage, bitpos);
-    __syncthreads();
+    const uint32_t body_end = (total_bits + 7) / 8;
+    const uint32_t total_bytes = body_end + 8;
     if (t == 0) {
-        uint32_t pos = S.total_bits;
-        if (!stored) {
-            BitW bw{S.stage, pos - (S.eob >> 16)};
-            bw.put(S.eob & 0xffffu, S.eob >> 16);
-        }
-        const uint32_t body_end = (pos + 7) / 8;       // bytes so far
-        const uint32_t total = body_end + 8;
-        BitW bw{S.stage, body_end * 8};
-        bw.put(S.crc_out, 32); bw.put(len, 32);
+        uint32_t pos = total_bits - (eob >> 16);
+        if (!stored) put_bits(S.stage, pos, eob & 0xffffu, eob >> 16);
+        pos = body_end * 8;
+        put_bits(S.stage, pos, S.crc_out, 32); put_bits(S.stage, pos, len, 32);
         // member header: ID1 ID2 CM FLG(FEXTRA) MTIME XFL OS(255) XLEN=6 'B' 'C' SLEN=2 BSIZE = total - 1
         S.stage[0] = 0x04088b1fu; S.stage[1] = 0; S.stage[2] = 0x0006ff00u; S.stage[3] = 0x00024342u;
-        S.stage[4] |= (total - 1) & 0xffffu;
-        S.total_bits = total;
-        *zlen = total;
+        atomicOr(&S.stage[4], (total_bytes - 1) & 0xffffu);
+        *zlen = total_bytes;
     }
     __syncthreads();
-    const uint32_t total = S.total_bits;
     const uint4* s4 = reinterpret_cast<const uint4*>(S.stage);
     uint4* o4 = reinterpret_cast<uint4*>(slot);
-    for (uint32_t i = t; i < (total + 15) / 16; i += kZT) o4[i] = s4[i];
+    for (uint32_t i = t; i < (total_bytes + 15) / 16; i += kZT) o4[i] = s4[i];
 }
 
 // exclusive prefix of the member sizes of one file (one CTA per file); the file's compressed size into totals[2 + file]
