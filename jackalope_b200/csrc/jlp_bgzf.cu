@@ -35,6 +35,7 @@ constexpr uint32_t kStageWords = kBgzfSlot / 4;
 
 __constant__ uint32_t c_crc_tab[256];
 __constant__ uint32_t c_crc_adv[17][32];   // operator "advance the CRC register over 2^j zero bytes", by bit image
+__constant__ uint32_t c_crc_init_full;     // the initial register 0xffffffff advanced over a full block
 
 struct ZShared {
     uint32_t stage[kStageWords];          // the block image
@@ -172,8 +173,14 @@ __device__ __forceinline__ uint32_t block_scan(uint32_t v, uint32_t* tmp, uint32
     return tmp[warp] + incl - v;
 }
 
-template <bool FULL, typename F>
-__device__ __forceinline__ void for_bytes(const uint4 (&d)[8], uint32_t my_len, F f) {
+// pass 1 of a thread: its 128 contiguous bytes, 16 at a time from global memory -> warp histogram, chunk CRC
+template <bool FULL>
+__device__ __forceinline__ uint32_t pass1(const uint8_t* chunk, uint32_t my_len, uint32_t* hist, const uint32_t* tab) {
+    uint32_t reg = 0;
+    uint4 d[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+        d[k] = (FULL || 16u * k < my_len) ? __ldg(reinterpret_cast<const uint4*>(chunk) + k) : make_uint4(0, 0, 0, 0);
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         const uint32_t w[4] = {d[k].x, d[k].y, d[k].z, d[k].w};
@@ -181,38 +188,51 @@ __device__ __forceinline__ void for_bytes(const uint4 (&d)[8], uint32_t my_len, 
         for (int q = 0; q < 4; q++)
 #pragma unroll
             for (int r = 0; r < 4; r++)
-                if (FULL || (uint32_t)(k * 16 + q * 4 + r) < my_len) f((w[q] >> (8 * r)) & 0xffu);
+                if (FULL || (uint32_t)(k * 16 + q * 4 + r) < my_len) {
+                    const uint32_t b = (w[q] >> (8 * r)) & 0xffu;
+                    atomicAdd(&hist[b], 1u);
+                    reg = tab[(reg ^ b) & 0xffu] ^ (reg >> 8);
+                }
     }
+    return reg;
 }
 
+// pass 2 of a warp: its segment (4096 bytes, fewer at the end of the file) again, this time 4 bytes per lane and
+// 128 contiguous bytes per round; the codes of a lane's 4 bytes are joined (<= 60 bits), a warp scan of the
+// lengths places them, and they are OR-ed into the block image.
 template <bool FULL>
-__device__ __forceinline__ void pass1(const uint4 (&d)[8], uint32_t my_len, uint32_t* hist, const uint32_t* tab, uint32_t& crc) {
-    uint32_t reg = 0;
-    for_bytes<FULL>(d, my_len, [&](uint32_t b) {
-        atomicAdd(&hist[b], 1u);
-        reg = tab[(reg ^ b) & 0xffu] ^ (reg >> 8);
-    });
-    crc = reg;
-}
-
-template <bool FULL>
-__device__ __forceinline__ uint32_t size_bits(const uint4 (&d)[8], uint32_t my_len, const uint32_t* ctab) {
-    uint32_t n = 0;
-    for_bytes<FULL>(d, my_len, [&](uint32_t b) { n += ctab[b] >> 16; });
-    return n;
-}
-
-template <bool FULL>
-__device__ __forceinline__ void pack(const uint4 (&d)[8], uint32_t my_len, const uint32_t* ctab, uint32_t* stage, uint32_t bitpos) {
-    uint32_t wi = bitpos >> 5, nb = bitpos & 31;
-    uint64_t acc = 0;
-    for_bytes<FULL>(d, my_len, [&](uint32_t b) {
-        const uint32_t e = ctab[b];
-        acc |= (uint64_t)(e & 0xffffu) << nb;
-        nb += e >> 16;
-        if (nb >= 32) { atomicOr(&stage[wi++], (uint32_t)acc); acc >>= 32; nb -= 32; }
-    });
-    if (nb) atomicOr(&stage[wi], (uint32_t)acc);
+__device__ __forceinline__ void pack_warp(const uint8_t* seg, uint32_t seg_len, const uint32_t* ctab, uint32_t* stage,
+                                          uint32_t base, uint32_t lane) {
+    const uint32_t* g = reinterpret_cast<const uint32_t*>(seg) + lane;
+    for (uint32_t r0 = 0; r0 < 32; r0 += 4) {
+        if (!FULL && r0 * 128u >= seg_len) break;
+        uint32_t w[4];
+#pragma unroll
+        for (uint32_t u = 0; u < 4; u++)
+            w[u] = (FULL || (r0 + u) * 128u + lane * 4u < seg_len) ? __ldg(g + (r0 + u) * 32u) : 0u;
+#pragma unroll
+        for (uint32_t u = 0; u < 4; u++) {
+            const uint32_t off = (r0 + u) * 128u + lane * 4u;
+            const uint32_t nv = FULL ? 4u : (off >= seg_len ? 0u : min(4u, seg_len - off));
+            uint32_t e0 = ctab[w[u] & 0xffu], e1 = ctab[(w[u] >> 8) & 0xffu], e2 = ctab[(w[u] >> 16) & 0xffu], e3 = ctab[w[u] >> 24];
+            if (!FULL) { if (nv < 1) e0 = 0; if (nv < 2) e1 = 0; if (nv < 3) e2 = 0; if (nv < 4) e3 = 0; }
+            const uint32_t l0 = e0 >> 16, l1 = e1 >> 16, l2 = e2 >> 16, l3 = e3 >> 16;
+            const uint32_t c01 = (e0 & 0xffffu) | (e1 & 0xffffu) << l0, l01 = l0 + l1;
+            const uint32_t c23 = (e2 & 0xffffu) | (e3 & 0xffffu) << l2, l23 = l2 + l3;
+            const uint64_t c = (uint64_t)c01 | (uint64_t)c23 << l01;
+            const uint32_t l = l01 + l23;
+            uint32_t incl = l;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += x; }
+            const uint32_t pos = base + incl - l;
+            base += __shfl_sync(0xffffffffu, incl, 31);
+            const uint32_t i = pos >> 5, sh = pos & 31;
+            const uint32_t lo = (uint32_t)c, hi = (uint32_t)(c >> 32);
+            if (l) atomicOr(&stage[i], lo << sh);
+            if (sh + l > 32) atomicOr(&stage[i + 1], __funnelshift_l(lo, hi, sh));
+            if (sh + l > 64) atomicOr(&stage[i + 2], __funnelshift_l(hi, 0u, sh));
+        }
+    }
 }
 
 // The run of equal code lengths starting at a position, as the tokens of RFC 1951 section 3.2.7:
@@ -237,7 +257,7 @@ __device__ __forceinline__ RunTok run_tokens(uint32_t v, uint32_t run) {
     return r;
 }
 
-__global__ void __launch_bounds__(kZT, 1)
+__global__ void __launch_bounds__(kZT, 2)
 k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const uint64_t* __restrict__ totals, uint32_t nblk_max,
        uint8_t* __restrict__ slots0, uint8_t* __restrict__ slots1, uint32_t* __restrict__ zlen0, uint32_t* __restrict__ zlen1) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -253,13 +273,8 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
     uint8_t* slot = (second ? slots1 : slots0) + (uint64_t)b * kBgzfSlot;
     uint32_t* zlen = (second ? zlen1 : zlen0) + b;
 
-    // ---- the chunk of this thread, once from global memory
     const uint32_t my_off = t * kChunk;
     const uint32_t my_len = my_off >= len ? 0u : min(kChunk, len - my_off);
-    uint4 d[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++)
-        d[k] = (my_off + 16u * k < len) ? __ldg(reinterpret_cast<const uint4*>(in + my_off) + k) : make_uint4(0, 0, 0, 0);
 
     // ---- clear the image and the histograms
     {
@@ -276,9 +291,8 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
     __syncthreads();
 
     // ---- pass 1: histogram + chunk CRC
-    uint32_t crc;
-    if (my_len == kChunk) pass1<true>(d, my_len, S.hist[warp], S.crc_tab, crc);
-    else pass1<false>(d, my_len, S.hist[warp], S.crc_tab, crc);
+    uint32_t crc = my_len == kChunk ? pass1<true>(in + my_off, my_len, S.hist[warp], S.crc_tab)
+                                    : pass1<false>(in + my_off, my_len, S.hist[warp], S.crc_tab);
     // CRC tree inside the warp: the node at lane covers chunks [t, t + 2s); its right half has right_len bytes
 #pragma unroll
     for (uint32_t s = 1; s < 32; s <<= 1) {
@@ -306,7 +320,7 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
                 crc = crc_advance(crc, r0 >= len ? 0u : min(s * 32u * kChunk, len - r0)) ^ other;
             }
         }
-        if (lane == 0) S.crc_out = crc ^ crc_advance(0xffffffffu, len) ^ 0xffffffffu;
+        if (lane == 0) S.crc_out = crc ^ (len == kBgzfIn ? c_crc_init_full : crc_advance(0xffffffffu, len)) ^ 0xffffffffu;
     }
     const uint32_t n_active = __syncthreads_count(my_cnt != 0);
     // rank sort of the active symbols (ascending count, ties by symbol)
@@ -348,6 +362,7 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
             same += __popc(__vcmpeq4(lw[t / 4], pat) & ((1u << (8 * (t & 3))) - 1u));
             S.code[t] = (uint16_t)rev_bits(first_code(S.bl, l) + same / 8, l);
         }
+        if (t < 256) S.ctab[t] = l ? (uint32_t)S.code[t] | l << 16 : 0u;
     }
     // the runs of the code-length sequence [0, 259): one thread per run counts its tokens
     RunTok rt{0, 0, 0, 0, 0, 0};
@@ -370,10 +385,8 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
         }
     }
     __syncthreads();
-    if (t < 256) S.ctab[t] = S.len[t] ? (uint32_t)S.code[t] | (uint32_t)S.len[t] << 16 : 0u;
 
     // ---- the code-length code and the fixed part of the block header (one thread) while the others size their chunks
-    uint32_t bits = 0;
     if (t == 0) {
         uint32_t n_cl = 0;
         for (uint32_t s = 0; s < 19; s++) {
@@ -414,7 +427,13 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
         S.hdr_fixed_bits = pos;
         S.eob = (uint32_t)S.code[256] | (uint32_t)S.len[256] << 16;
     }
-    bits = my_len == kChunk ? size_bits<true>(d, my_len, S.ctab) : size_bits<false>(d, my_len, S.ctab);
+    // bits of this warp's segment: its histogram times the code lengths
+    uint32_t bits = 0;
+#pragma unroll
+    for (uint32_t q = 0; q < 8; q++) bits += S.hist[warp][lane + 32 * q] * (S.ctab[lane + 32 * q] >> 16);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) bits += __shfl_xor_sync(0xffffffffu, bits, o);
+    if (lane) bits = 0;
     __syncthreads();
 
     // ---- one scan for both the header tokens of the runs and the chunks: header bits << 20 | chunk bits
@@ -447,7 +466,7 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
                 for (uint32_t q = 1; q < rt.n_lit; q++) put_bits(S.stage, pos, c_lit, l_lit);
             }
         }
-        bitpos = hdr_bits + (excl & 0xfffffu);
+        bitpos = hdr_bits + (__shfl_sync(0xffffffffu, excl, 0) & 0xfffffu);
         total_bits = end_bits;
     } else {
         // does not shrink: stored block (BTYPE 00) through the same packing code with the identity table
@@ -461,11 +480,15 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
             put_bits(S.stage, pos, 1, 8);                              // BFINAL = 1, BTYPE = 00, padding to the byte
             put_bits(S.stage, pos, len, 16); put_bits(S.stage, pos, len ^ 0xffffu, 16);
         }
-        bitpos = (kHdr + 5 + my_off) * 8;
+        bitpos = (kHdr + 5 + warp * 32u * kChunk) * 8;
         total_bits = (kHdr + 5 + len) * 8;
     }
-    if (my_len == kChunk) pack<true>(d, my_len, S.ctab, S.stage, bitpos);
-    else if (my_len) pack<false>(d, my_len, S.ctab, S.stage, bitpos);
+    {
+        const uint32_t seg_off = warp * 32u * kChunk;
+        const uint32_t seg_len = seg_off >= len ? 0u : min(32u * kChunk, len - seg_off);
+        if (seg_len == 32u * kChunk) pack_warp<true>(in + seg_off, seg_len, S.ctab, S.stage, bitpos, lane);
+        else if (seg_len) pack_warp<false>(in + seg_off, seg_len, S.ctab, S.stage, bitpos, lane);
+    }
     const uint32_t body_end = (total_bits + 7) / 8;
     const uint32_t total_bytes = body_end + 8;
     if (t == 0) {
@@ -561,6 +584,15 @@ cudaError_t bgzf_init() {
     cudaError_t e = cudaMemcpyToSymbol(c_crc_tab, tab, sizeof tab);
     if (e != cudaSuccess) return e;
     e = cudaMemcpyToSymbol(c_crc_adv, adv, sizeof adv);
+    if (e != cudaSuccess) return e;
+    uint32_t init_full = 0xffffffffu;
+    for (int j = 0; j < 17; j++)
+        if ((kBgzfIn >> j) & 1u) {
+            uint32_t r = 0;
+            for (int q = 0; q < 32; q++) if ((init_full >> q) & 1u) r ^= adv[j][q];
+            init_full = r;
+        }
+    e = cudaMemcpyToSymbol(c_crc_init_full, &init_full, sizeof init_full);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_bgzf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZShared));
 }
