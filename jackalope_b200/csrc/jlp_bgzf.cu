@@ -36,6 +36,9 @@ constexpr uint32_t kStageWords = kBgzfSlot / 4;
 __constant__ uint32_t c_crc_tab[256];
 __constant__ uint32_t c_crc_adv[17][32];   // operator "advance the CRC register over 2^j zero bytes", by bit image
 __constant__ uint32_t c_crc_init_full;     // the initial register 0xffffffff advanced over a full block
+// the same operators for 2^7 .. 2^15 zero bytes (the sizes a full block's CRC tree combines) as 4 x 256-entry tables:
+// advance(v) = T[0][v & 255] ^ T[1][v >> 8 & 255] ^ T[2][v >> 16 & 255] ^ T[3][v >> 24]
+__device__ uint32_t g_crc_lvl[9][4][256];
 
 struct ZShared {
     uint32_t stage[kStageWords];          // the block image
@@ -64,6 +67,10 @@ __device__ __forceinline__ uint32_t crc_apply(const uint32_t* m, uint32_t v) {
 #pragma unroll
     for (int i = 0; i < 32; i++) r ^= ((v >> i) & 1u) ? m[i] : 0u;
     return r;
+}
+__device__ __forceinline__ uint32_t crc_advance_lvl(uint32_t j, uint32_t v) {
+    const uint32_t (*T)[256] = g_crc_lvl[j];
+    return __ldg(&T[0][v & 0xffu]) ^ __ldg(&T[1][(v >> 8) & 0xffu]) ^ __ldg(&T[2][(v >> 16) & 0xffu]) ^ __ldg(&T[3][v >> 24]);
 }
 // CRC register advanced over n zero bytes
 __device__ uint32_t crc_advance(uint32_t v, uint32_t n) {
@@ -295,11 +302,13 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
                                     : pass1<false>(in + my_off, my_len, S.hist[warp], S.crc_tab);
     // CRC tree inside the warp: the node at lane covers chunks [t, t + 2s); its right half has right_len bytes
 #pragma unroll
-    for (uint32_t s = 1; s < 32; s <<= 1) {
+    for (uint32_t j = 0; j < 5; j++) {
+        const uint32_t s = 1u << j;
         const uint32_t other = __shfl_down_sync(0xffffffffu, crc, s);
         if ((lane & (2 * s - 1)) == 0) {
             const uint32_t r0 = (t + s) * kChunk;
-            crc = crc_advance(crc, r0 >= len ? 0u : min(s * kChunk, len - r0)) ^ other;
+            const uint32_t right_len = r0 >= len ? 0u : min(s * kChunk, len - r0);
+            crc = (right_len == s * kChunk ? crc_advance_lvl(j, crc) : crc_advance(crc, right_len)) ^ other;
         }
     }
     if (lane == 0) S.crc_w[warp] = crc;
@@ -310,28 +319,36 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
         else my_cnt = 1;     // end of block
         S.cnt[t] = my_cnt;
     }
-    if (warp == kZW - 1) {   // the last warp finishes the CRC over the warps' results
+    // the active symbols, compacted in symbol order: count << 9 | symbol orders them by (count, symbol)
+    const uint32_t act = __ballot_sync(0xffffffffu, my_cnt != 0);
+    if (lane == 0) S.scan_tmp[warp] = __popc(act);
+    __syncthreads();
+    uint32_t n_active = 0, before = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < 9; w++) { const uint32_t c = S.scan_tmp[w]; n_active += c; before += w < warp ? c : 0u; }
+    if (my_cnt) S.w_int[before + __popc(act & ((1u << lane) - 1u))] = my_cnt << 9 | t;
+    __syncthreads();
+    // rank sort (ascending count, ties by symbol)
+    if (my_cnt) {
+        const uint32_t key = my_cnt << 9 | t;
+        uint32_t rank = 0;
+        for (uint32_t q = 0; q < n_active; q++) rank += S.w_int[q] < key ? 1u : 0u;
+        S.sorted[rank] = (uint16_t)t;
+        S.sw[rank] = my_cnt;
+    }
+    if (warp == kZW - 1) {   // meanwhile the last warp (no symbols of its own) finishes the CRC over the warps' results
         crc = lane < kZW ? S.crc_w[lane] : 0u;
 #pragma unroll
-        for (uint32_t s = 1; s < kZW; s <<= 1) {
+        for (uint32_t j = 0; j < 4; j++) {
+            const uint32_t s = 1u << j;
             const uint32_t other = __shfl_down_sync(0xffffffffu, crc, s);
             if ((lane & (2 * s - 1)) == 0 && lane < kZW) {
                 const uint32_t r0 = (lane + s) * 32u * kChunk;
-                crc = crc_advance(crc, r0 >= len ? 0u : min(s * 32u * kChunk, len - r0)) ^ other;
+                const uint32_t right_len = r0 >= len ? 0u : min(s * 32u * kChunk, len - r0);
+                crc = (right_len == s * 32u * kChunk ? crc_advance_lvl(5 + j, crc) : crc_advance(crc, right_len)) ^ other;
             }
         }
         if (lane == 0) S.crc_out = crc ^ (len == kBgzfIn ? c_crc_init_full : crc_advance(0xffffffffu, len)) ^ 0xffffffffu;
-    }
-    const uint32_t n_active = __syncthreads_count(my_cnt != 0);
-    // rank sort of the active symbols (ascending count, ties by symbol)
-    if (my_cnt) {
-        uint32_t rank = 0;
-        for (uint32_t s = 0; s <= 256; s++) {
-            const uint32_t c = S.cnt[s];
-            rank += (c != 0 && (c < my_cnt || (c == my_cnt && s < t))) ? 1u : 0u;
-        }
-        S.sorted[rank] = (uint16_t)t;
-        S.sw[rank] = my_cnt;
     }
     __syncthreads();
 
@@ -386,46 +403,60 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
     }
     __syncthreads();
 
-    // ---- the code-length code and the fixed part of the block header (one thread) while the others size their chunks
-    if (t == 0) {
-        uint32_t n_cl = 0;
-        for (uint32_t s = 0; s < 19; s++) {
-            const uint32_t c = S.cl_cnt[s];
-            if (c) {
-                uint32_t p = n_cl++;
-                while (p > 0 && S.sw[p - 1] > c) { S.sw[p] = S.sw[p - 1]; S.sorted[p] = S.sorted[p - 1]; p--; }
-                S.sw[p] = c; S.sorted[p] = (uint16_t)s;
+    // ---- the code-length code and the fixed part of the block header (warp 0) while the others size their segments
+    if (warp == 0) {
+        const uint32_t c = lane < 19 ? S.cl_cnt[lane] : 0u;
+        const uint32_t n_cl = __popc(__ballot_sync(0xffffffffu, c != 0));
+        const uint32_t key = c << 5 | lane;
+        uint32_t rank = 0;
+#pragma unroll
+        for (uint32_t q = 0; q < 19; q++) {
+            const uint32_t k2 = __shfl_sync(0xffffffffu, key, q);
+            rank += (k2 >> 5) != 0 && k2 < key ? 1u : 0u;
+        }
+        if (c) { S.sorted[rank] = (uint16_t)lane; S.sw[rank] = c; }
+        if (lane < 16) S.bl[lane] = 0;
+        __syncwarp();
+        if (n_cl == 1) {                       // a complete code needs two symbols
+            if (lane == 0) { S.cl_len[S.sorted[0]] = 1; S.cl_len[S.sorted[0] ? 0 : 1] = 1; S.bl[1] = 2; }
+        } else {
+            if (lane == 0) huff_merge(S, n_cl);
+            __syncwarp();
+            uint32_t dep = 0;
+            if (lane < n_cl) {
+                uint32_t p = S.par_leaf[lane];
+                dep = 1;
+                while (p != n_cl - 2) { p = S.par_int[p]; dep++; }
+                S.cl_len[S.sorted[lane]] = (uint8_t)min(dep, 7u);
+                atomicAdd(&S.bl[min(dep, 7u)], 1u);
+            }
+            if (__any_sync(0xffffffffu, dep > 7)) {   // the 7-bit limit has to act
+                __syncwarp();
+                if (lane == 0) huff_limit(S, n_cl, 7, S.cl_len);
             }
         }
-        if (n_cl == 1) {                       // a complete code needs two symbols
-            S.cl_len[S.sorted[0]] = 1; S.cl_len[S.sorted[0] ? 0 : 1] = 1;
-            for (uint32_t q = 0; q < 16; q++) S.bl[q] = 0;
-            S.bl[1] = 2;
-        } else {
-            huff_merge(S, n_cl);
-            huff_limit(S, n_cl, 7, S.cl_len);
-        }
-        uint32_t next[8];
-        uint32_t c = 0;
-        next[0] = 0;
+        __syncwarp();
+        const uint32_t l = lane < 19 ? S.cl_len[lane] : 0u;
+        uint32_t same = 0;
 #pragma unroll
-        for (uint32_t q = 1; q < 8; q++) { c = (c + (q > 1 ? S.bl[q - 1] : 0u)) << 1; next[q] = c; }
-        for (uint32_t s = 0; s < 19; s++) {
-            const uint32_t l = S.cl_len[s];
-            uint32_t code = 0;
-#pragma unroll
-            for (uint32_t q = 1; q < 8; q++) if (l == q) code = next[q]++;
-            S.cl_code[s] = (uint16_t)(l ? rev_bits(code, l) : 0u);
+        for (uint32_t q = 0; q < 19; q++) {
+            const uint32_t l2 = __shfl_sync(0xffffffffu, l, q);
+            same += (l2 == l && q < lane) ? 1u : 0u;
         }
-        const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
-        uint32_t hclen = 19;
-        while (hclen > 4 && S.cl_len[order[hclen - 1]] == 0) hclen--;
-        uint32_t pos = kHdr * 8;
-        put_bits(S.stage, pos, 1, 1); put_bits(S.stage, pos, 2, 2);                   // BFINAL, BTYPE = dynamic Huffman
-        put_bits(S.stage, pos, 0, 5); put_bits(S.stage, pos, 1, 5); put_bits(S.stage, pos, hclen - 4, 4);   // HLIT = 257, HDIST = 2
-        for (uint32_t q = 0; q < hclen; q++) put_bits(S.stage, pos, S.cl_len[order[q]], 3);
-        S.hdr_fixed_bits = pos;
-        S.eob = (uint32_t)S.code[256] | (uint32_t)S.len[256] << 16;
+        if (lane < 19) S.cl_code[lane] = (uint16_t)(l ? rev_bits(first_code(S.bl, l) + same, l) : 0u);
+        const uint32_t order_lane = lane < 19 ? (uint32_t)"\x10\x11\x12\x00\x08\x07\x09\x06\x0a\x05\x0b\x04\x0c\x03\x0d\x02\x0e\x01\x0f"[lane] : 0u;
+        // HCLEN: the lengths are sent in the order 16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15 up to the last one used
+        const uint32_t l_ord = __shfl_sync(0xffffffffu, l, order_lane);
+        const uint32_t used = __ballot_sync(0xffffffffu, lane < 19 && l_ord != 0);
+        const uint32_t hclen = max(4u, 32u - (uint32_t)__clz(used));
+        if (lane == 0) {
+            uint32_t pos = kHdr * 8;
+            put_bits(S.stage, pos, 1, 1); put_bits(S.stage, pos, 2, 2);                   // BFINAL, BTYPE = dynamic Huffman
+            put_bits(S.stage, pos, 0, 5); put_bits(S.stage, pos, 1, 5); put_bits(S.stage, pos, hclen - 4, 4);   // HLIT = 257, HDIST = 2
+            S.hdr_fixed_bits = pos + 3 * hclen;
+            S.eob = (uint32_t)S.code[256] | (uint32_t)S.len[256] << 16;
+        }
+        if (lane < hclen) { uint32_t pos = kHdr * 8 + 17 + 3 * lane; put_bits(S.stage, pos, l_ord, 3); }
     }
     // bits of this warp's segment: its histogram times the code lengths
     uint32_t bits = 0;
@@ -593,6 +624,17 @@ cudaError_t bgzf_init() {
             init_full = r;
         }
     e = cudaMemcpyToSymbol(c_crc_init_full, &init_full, sizeof init_full);
+    if (e != cudaSuccess) return e;
+    static uint32_t lvl[9][4][256];
+    for (int j = 0; j < 9; j++)
+        for (int k = 0; k < 4; k++)
+            for (uint32_t x = 0; x < 256; x++) {
+                const uint32_t v = x << (8 * k);
+                uint32_t r = 0;
+                for (int q = 0; q < 32; q++) if ((v >> q) & 1u) r ^= adv[7 + j][q];
+                lvl[j][k][x] = r;
+            }
+    e = cudaMemcpyToSymbol(g_crc_lvl, lvl, sizeof lvl);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_bgzf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZShared));
 }
