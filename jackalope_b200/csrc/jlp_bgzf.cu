@@ -32,6 +32,7 @@ constexpr uint32_t kChunk = 128;         // input bytes per thread
 constexpr uint32_t kNLit = 286;          // literal/length alphabet
 constexpr uint32_t kHdr = 18;            // BGZF member header bytes
 constexpr uint32_t kStageWords = kBgzfSlot / 4;
+constexpr uint32_t kHistWord0 = kStageWords - kZW * 256;   // the histograms alias the end of the image
 
 __constant__ uint32_t c_crc_tab[256];
 __constant__ uint32_t c_crc_adv[17][32];   // operator "advance the CRC register over 2^j zero bytes", by bit image
@@ -41,8 +42,7 @@ __constant__ uint32_t c_crc_init_full;     // the initial register 0xffffffff ad
 __device__ uint32_t g_crc_lvl[9][4][256];
 
 struct ZShared {
-    uint32_t stage[kStageWords];          // the block image
-    uint32_t hist[kZW][256];              // per-warp literal counts
+    uint32_t stage[kStageWords];          // the block image; its last 16 KiB hold the per-warp literal counts until the packing starts
     uint32_t cnt[288];                    // literal/length counts; [256] = end of block
     uint32_t crc_tab[256];
     uint32_t ctab[256];                   // code (bit-reversed, LSB first) | length << 16 per literal
@@ -264,7 +264,7 @@ __device__ __forceinline__ RunTok run_tokens(uint32_t v, uint32_t run) {
     return r;
 }
 
-__global__ void __launch_bounds__(kZT, 2)
+__global__ void __launch_bounds__(kZT, 3)
 k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const uint64_t* __restrict__ totals, uint32_t nblk_max,
        uint8_t* __restrict__ slots0, uint8_t* __restrict__ slots1, uint32_t* __restrict__ zlen0, uint32_t* __restrict__ zlen1) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -287,8 +287,6 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
     {
         uint4* s4 = reinterpret_cast<uint4*>(S.stage);
         for (uint32_t i = t; i < kStageWords / 4; i += kZT) s4[i] = make_uint4(0, 0, 0, 0);
-        uint32_t* h = &S.hist[0][0];
-        for (uint32_t i = t; i < kZW * 256; i += kZT) h[i] = 0;
         if (t < 256) S.crc_tab[t] = c_crc_tab[t];
         if (t < 320) S.len[t] = (t == 257 || t == 258) ? 1 : 0;   // two unused distance codes of one bit, as zlib sends for a block of literals
         if (t < 16) S.bl[t] = 0;
@@ -298,8 +296,8 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
     __syncthreads();
 
     // ---- pass 1: histogram + chunk CRC
-    uint32_t crc = my_len == kChunk ? pass1<true>(in + my_off, my_len, S.hist[warp], S.crc_tab)
-                                    : pass1<false>(in + my_off, my_len, S.hist[warp], S.crc_tab);
+    uint32_t* hist = S.stage + kHistWord0 + warp * 256;
+    uint32_t crc = my_len == kChunk ? pass1<true>(in + my_off, my_len, hist, S.crc_tab) : pass1<false>(in + my_off, my_len, hist, S.crc_tab);
     // CRC tree inside the warp: the node at lane covers chunks [t, t + 2s); its right half has right_len bytes
 #pragma unroll
     for (uint32_t j = 0; j < 5; j++) {
@@ -315,7 +313,7 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
     __syncthreads();
     uint32_t my_cnt = 0;
     if (t <= 256) {
-        if (t < 256) for (int w = 0; w < kZW; w++) my_cnt += S.hist[w][t];
+        if (t < 256) for (int w = 0; w < kZW; w++) my_cnt += S.stage[kHistWord0 + w * 256 + t];
         else my_cnt = 1;     // end of block
         S.cnt[t] = my_cnt;
     }
@@ -461,7 +459,7 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
     // bits of this warp's segment: its histogram times the code lengths
     uint32_t bits = 0;
 #pragma unroll
-    for (uint32_t q = 0; q < 8; q++) bits += S.hist[warp][lane + 32 * q] * (S.ctab[lane + 32 * q] >> 16);
+    for (uint32_t q = 0; q < 8; q++) bits += hist[lane + 32 * q] * (S.ctab[lane + 32 * q] >> 16);
 #pragma unroll
     for (int o = 16; o; o >>= 1) bits += __shfl_xor_sync(0xffffffffu, bits, o);
     if (lane) bits = 0;
@@ -484,6 +482,11 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
     const uint32_t end_bits = hdr_bits + (total & 0xfffffu) + (eob >> 16);
     const bool stored = ((end_bits + 7) / 8 - kHdr) >= len + 5;     // uniform
     uint32_t bitpos, total_bits;
+    if ((stored ? kHdr + 5 + len : (end_bits + 7) / 8) + 8 > kHistWord0 * 4) {
+        // the image reaches into the histograms (every warp has read its own before the scan's barriers)
+        for (uint32_t i = kHistWord0 + t; i < kStageWords; i += kZT) S.stage[i] = 0;
+        __syncthreads();
+    }
     if (!stored) {
         if (run_start) {
             uint32_t pos = S.hdr_fixed_bits + (excl >> 20);
