@@ -5,7 +5,9 @@
 
 #include <cuda_runtime.h>
 #include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
+#include <sys/statvfs.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -158,6 +160,21 @@ std::string pwrite_all(int fd, const uint8_t* p, uint64_t n, uint64_t off) {
         if (w < 0) { if (errno == EINTR) continue; return std::strerror(errno); }
         p += w; n -= (uint64_t)w; off += (uint64_t)w;
     }
+    return std::string();
+}
+
+// The same slice through a shared mapping of the file (already extended to its new size): page-cache pages are
+// allocated and filled by the calling thread, so the writer threads do not queue on the inode lock that
+// serialises write() calls on one file (measured on the B200 box's tmpfs: 7.4 GB/s with pwrite from any number
+// of threads, 14 GB/s with 16 threads copying into mappings; tools/write_probe.cpp).  Falls back to pwrite when
+// the file cannot be mapped.
+std::string mmap_write_all(int fd, const uint8_t* p, uint64_t n, uint64_t off) {
+    static const uint64_t page = (uint64_t)sysconf(_SC_PAGESIZE);
+    const uint64_t a0 = off / page * page;
+    void* m = ::mmap(nullptr, (size_t)(off + n - a0), PROT_READ | PROT_WRITE, MAP_SHARED, fd, (off_t)a0);
+    if (m == MAP_FAILED) return pwrite_all(fd, p, n, off);
+    std::memcpy(static_cast<uint8_t*>(m) + (off - a0), p, n);
+    ::munmap(m, (size_t)(off + n - a0));
     return std::string();
 }
 
@@ -580,12 +597,22 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
                 const uint64_t n = dev_z ? s.ztot[e] : s.tot[e];
                 if (sink.kind == SINK_FILES && zmethod < 0) {
                     // R1 and R2 stay record-aligned: both files receive the same batches in the same order
+                    // with several writer threads the file is extended first and the slices are copied into
+                    // mappings of it; with one thread, when the file system is nearly full (a write() reports
+                    // ENOSPC, a mapping would fault) or when the file cannot be extended, plain pwrite
+                    bool mapped = P->n_threads > 1 && n > 0;
+                    if (mapped) {
+                        struct statvfs vfs;
+                        mapped = ::fstatvfs(sink.fd[e], &vfs) == 0 && (uint64_t)vfs.f_bavail * vfs.f_frsize > 2 * n + (64ull << 20) &&
+                                 ::ftruncate(sink.fd[e], (off_t)(sink.pos[e] + n)) == 0;
+                    }
                     const uint64_t slice = 8ull << 20;
                     for (uint64_t o = 0; o < n; o += slice) {
                         const int fd = sink.fd[e];
                         const uint8_t* src = s.h_out[e].p + o;
                         const uint64_t len = std::min(slice, n - o), off = sink.pos[e] + o;
-                        c->writers.submit(&s.writes, [fd, src, len, off]() { return pwrite_all(fd, src, len, off); });
+                        if (mapped) c->writers.submit(&s.writes, [fd, src, len, off]() { return mmap_write_all(fd, src, len, off); });
+                        else c->writers.submit(&s.writes, [fd, src, len, off]() { return pwrite_all(fd, src, len, off); });
                     }
                     sink.pos[e] += n;
                 } else if (sink.kind == SINK_FILES) {
@@ -630,7 +657,7 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
             for (int e = 0; e < n_ends; e++) {
                 sink.names[e] = job.file_prefix + "_R" + std::to_string(e + 1) + ".fq";   // src/hts.h:344
                 if (want_gz) sink.names[e] += ".gz";                                      // src/io.h:126,217
-                sink.fd[e] = ::open(sink.names[e].c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+                sink.fd[e] = ::open(sink.names[e].c_str(), O_RDWR | O_CREAT | O_TRUNC, 0644);
                 if (sink.fd[e] < 0) throw IoErr("Unable to open file " + sink.names[e] + ".\n");  // src/io.h:288-290
             }
         }
