@@ -125,6 +125,7 @@ void illumina_ref_cpp(SEXP ref_genome_ptr, const bool& paired, const bool& matep
     jlp_illumina_params P = {};
     P.paired = paired; P.matepair = matepair; P.out_prefix = out_prefix.c_str();   // expand_path: do it in R (path.expand)
     P.compress = compress; P.comp_method = comp_method.c_str();
+    P.comp_engine = JLP_COMP_AUTO;   // levels 1-6: BGZF written by the GPU; 7-9: zlib on the writer threads
     P.n_reads = n_reads; P.prob_dup = prob_dup; P.n_threads = n_threads; P.read_pool_size = read_pool_size;
     P.frag_len_shape = frag_len_shape; P.frag_len_scale = frag_len_scale;
     P.frag_len_min = frag_len_min; P.frag_len_max = frag_len_max;
@@ -160,6 +161,7 @@ void illumina_hap_cpp(SEXP hap_set_ptr, const bool& paired, const bool& matepair
     jlp_illumina_params P = {};
     P.paired = paired; P.matepair = matepair; P.out_prefix = out_prefix.c_str(); P.sep_files = sep_files;
     P.compress = compress; P.comp_method = comp_method.c_str();
+    P.comp_engine = JLP_COMP_AUTO;   // levels 1-6: BGZF written by the GPU; 7-9: zlib on the writer threads
     P.n_reads = n_reads; P.prob_dup = prob_dup; P.n_threads = n_threads; P.read_pool_size = read_pool_size;
     P.haplotype_probs = haplotype_probs.data();
     P.frag_len_shape = frag_len_shape; P.frag_len_scale = frag_len_scale;

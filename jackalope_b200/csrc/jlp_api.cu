@@ -544,6 +544,24 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
     jlp_run_stats st;
     std::memset(&st, 0, sizeof st);
 
+    // If the run ends by an exception, nothing of it may stay in flight: kernels and copies still use the
+    // slots, writer tasks still hold the file descriptors the caller's Sink is about to close.
+    struct Quiesce {
+        jlp_ctx* c;
+        bool armed = true;
+        ~Quiesce() {
+            if (!armed) return;
+            cudaStreamSynchronize(c->s_compute);
+            cudaStreamSynchronize(c->s_copy);
+            for (Slot& s : c->slot) {
+                c->writers.wait(s.writes);
+                s.busy = false;
+                s.zout[0].clear(); s.zout[1].clear();
+            }
+            c->writers.clear_error();
+        }
+    } quiesce{c};
+
     auto wait_writes = [&](Slot& s) {
         if (sink.kind != SINK_FILES) return;
         std::string e = c->writers.wait(s.writes);
@@ -709,7 +727,7 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
             CK(launch_reads(gp, c->n_sm, c->s_compute));
             CK(cudaEventRecord(s.ev[3], c->s_compute));
             if (dev_z) {
-                CK(launch_bgzf(s.out[0].p, s.out[1].p, s.totals.p, nblk_max, s.zslots[0].p, s.zslots[1].p, s.zlen[0].p,
+                CK(launch_bgzf(s.out[0].p, s.out[1].p, s.totals.p, nblk_max, P->compress >= 4, s.zslots[0].p, s.zslots[1].p, s.zlen[0].p,
                                s.zlen[1].p, s.zoff[0].p, s.zoff[1].p, s.zdev[0].p, s.zdev[1].p, c->s_compute));
                 st.kernel_launches += 3;
             }
@@ -769,6 +787,7 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
     if (status & 1u) throw ArgErr("a barcode is at least as long as a read's template (fragment or chromosome too short)");
     st.h2d_bytes = c->h2d_bytes;
     if (stats) *stats = st;
+    quiesce.armed = false;
 }
 
 }  // namespace
@@ -1083,7 +1102,7 @@ int jlp_deflate(int bgzf, int level, const void* in, uint64_t n, void* out, uint
     return JLP_OK;
 }
 
-int jlp_bgzf_device(jlp_ctx* c, const void* in, uint64_t n, void* out, uint64_t cap, uint64_t* len) {
+int jlp_bgzf_device(jlp_ctx* c, int level, const void* in, uint64_t n, void* out, uint64_t cap, uint64_t* len) {
     if (!c) return JLP_ERR_ARG;
     return guarded(c, [&]() {
         if ((n && !in) || !len) throw ArgErr("NULL argument");
@@ -1096,7 +1115,7 @@ int jlp_bgzf_device(jlp_ctx* c, const void* in, uint64_t n, void* out, uint64_t 
         const uint64_t tot[4] = {n, 0, 0, 0};
         if (n) CK(cudaMemcpyAsync(d_in.p, in, n, cudaMemcpyHostToDevice, c->s_compute));
         CK(cudaMemcpyAsync(d_tot.p, tot, sizeof tot, cudaMemcpyHostToDevice, c->s_compute));
-        CK(launch_bgzf(d_in.p, d_in.p, d_tot.p, nblk, d_slots.p, d_slots.p, d_zlen.p, d_zlen.p, d_zoff.p, d_zoff.p, d_out.p,
+        CK(launch_bgzf(d_in.p, d_in.p, d_tot.p, nblk, level >= 4, d_slots.p, d_slots.p, d_zlen.p, d_zlen.p, d_zoff.p, d_zoff.p, d_out.p,
                        d_out.p, c->s_compute));
         uint64_t back[4];
         CK(cudaMemcpyAsync(back, d_tot.p, sizeof back, cudaMemcpyDeviceToHost, c->s_compute));

@@ -115,11 +115,12 @@ constexpr uint32_t kScanBlock = 1024;
 // BGZF on the device (jlp_bgzf.cu).  totals[0..1] hold the FASTQ bytes of the two files of a batch (device
 // memory, as launch_scan leaves them); the compressed sizes come back in totals[2..3].  Block b of a file is
 // compressed into slots + b * kBgzfSlot, then gathered to out + (sum of the sizes before it).  nblk_max sizes
-// the grids: an upper bound of the blocks of either file.
+// the grids: an upper bound of the blocks of either file.  `matches`: also look for length/distance pairs (a line's
+// common prefix with the line four lines earlier); smaller output, about twice the kernel time.
 constexpr uint32_t kBgzfIn = 0xff00;     // input bytes per block, htslib's BGZF_BLOCK_SIZE
 constexpr uint32_t kBgzfSlot = 65536;    // a BGZF block never exceeds 64 KiB
 cudaError_t bgzf_init();
-cudaError_t launch_bgzf(const uint8_t* in0, const uint8_t* in1, uint64_t* totals, uint32_t nblk_max, uint8_t* slots0,
+cudaError_t launch_bgzf(const uint8_t* in0, const uint8_t* in1, uint64_t* totals, uint32_t nblk_max, bool matches, uint8_t* slots0,
                         uint8_t* slots1, uint32_t* zlen0, uint32_t* zlen1, uint64_t* zoff0, uint64_t* zoff1, uint8_t* out0,
                         uint8_t* out1, cudaStream_t s);
 

@@ -31,12 +31,12 @@ def bgzf_blocks(z: bytes):
     return out
 
 
-def device_bgzf(ctx, data: bytes) -> bytes:
+def device_bgzf(ctx, data: bytes, level: int = 6) -> bytes:
     lib = ctx.lib
     n = C.c_uint64()
     cap = len(data) + (len(data) // 0xff00 + 2) * 64 + 64
     buf = C.create_string_buffer(cap)
-    rc = lib.jlp_bgzf_device(ctx.h, data, len(data), buf, cap, C.byref(n))
+    rc = lib.jlp_bgzf_device(ctx.h, level, data, len(data), buf, cap, C.byref(n))
     assert rc == 0, lib.jlp_last_error(ctx.h)
     return buf.raw[:n.value]
 
@@ -55,7 +55,8 @@ def huffman_only_size(data: bytes) -> int:
             a, b = heapq.heappop(h), heapq.heappop(h)
             bits += a + b
             heapq.heappush(h, a + b)
-        tot += (bits + 7) // 8 + 26
+        # the coder keeps at most 44 KiB of block image: what does not get below that is stored (5 + 26 bytes of framing)
+        tot += (bits + 7) // 8 + 26 if (bits + 7) // 8 + 200 < 44 * 1024 else len(data[i:i + 0xff00]) + 31
     return tot
 
 
@@ -89,15 +90,23 @@ CASES = {
     # the 15-bit limit has to act
     "fibonacci_depth": b"".join(bytes([65 + k]) * f for k, f in enumerate(
         [1, 2, 3, 5, 8, 13, 21, 34, 55, 89, 144, 233, 377, 610, 987, 1597, 2584, 4181, 6765, 10946, 17711])),
+    # identical and nearly identical lines: matches up to the line's last byte, lengths up to 258, short distances
+    "repeated_lines": b"".join(b"%s\n" % (b"ACGT" * (1 + i % 70)) for i in range(2400)),
+    "short_lines": b"".join(b"ab%d\n" % (i % 7) for i in range(30000)),             # more line starts than the coder keeps
+    "empty_lines": b"\n" * 5000 + b"x\n\n" * 3000,
+    # many distinct rare bytes before each line start: literal codes of 12+ bits next to a match (the lane's bits pass 64)
+    "long_codes_before_matches": b"".join(bytes(np.random.default_rng(i).integers(128, 256, 45, dtype=np.uint8)) + b"\n" + b"PREFIX-%06d" % (i * 7919 % 10**6) + b"A" * (i % 5) + b"\n" + b"qq\n" + b"rr\n" for i in range(1500)),
     "chunk_tail_127": fastq_like(0xff00 + 127, 6),
     "chunk_tail_129": fastq_like(2 * 0xff00 + 129, 7),
 }
 
 
+@pytest.mark.parametrize("level", [1, 6])
 @pytest.mark.parametrize("name", list(CASES))
-def test_device_bgzf_round_trip(ctx, name):
+def test_device_bgzf_round_trip(ctx, name, level):
+    """level 1: literals only; level 6: also the matches of line prefixes."""
     data = CASES[name]
-    z = device_bgzf(ctx, data)
+    z = device_bgzf(ctx, data, level)
     blocks = bgzf_blocks(z)
     assert blocks[-1] == (28, 0)
     assert [i for _, i in blocks[:-1]] == [min(0xff00, len(data) - o) for o in range(0, len(data), 0xff00)]
@@ -108,6 +117,8 @@ def test_device_bgzf_round_trip(ctx, name):
         assert len(z) <= 1.01 * huffman_only_size(data) + 150 * len(blocks), (len(z), huffman_only_size(data))
     if name == "random_bytes_stored":
         assert len(z) <= len(data) + (len(data) // 0xff00 + 1) * 31 + 28    # stored blocks: 5 + 26 bytes each
+    if level == 6 and name in ("exact_block", "three_blocks_ragged", "repeated_lines", "long_codes_before_matches"):
+        assert len(z) < len(device_bgzf(ctx, data, 1))                      # the matches pay
 
 
 def small_genome(seed):
