@@ -322,8 +322,9 @@ def main():
     value = a.steps * B * world / (run_ms / 1e3)
     place_ms = st["place_ms"] / st["batches"]
     reads_ms = st["reads_ms"] / st["batches"]
-    log("[bench] device leg: %.3f ms/step (events), wall %.3f s, k_place %.3f ms, k_reads %.3f ms, bytes/pair %.1f"
-        % (run_ms / a.steps, wall, place_ms, reads_ms, sum(st["bytes_out"]) / st["pairs"]))
+    if rank == 0:
+        log("[bench] device leg: %.3f ms/step (events), wall %.3f s, k_place %.3f ms, k_reads %.3f ms, bytes/pair %.1f"
+            % (run_ms / a.steps, wall, place_ms, reads_ms, sum(st["bytes_out"]) / st["pairs"]))
 
     # ---- end-to-end leg: genome H2D + every batch's FASTQ D2H into pinned host buffers
     e2e = None
@@ -352,39 +353,42 @@ def main():
                        "pinned host buffers"}
 
     # ---- compress = TRUE on the device (BGZF members written by k_bgzf): kernel time with the output left in HBM,
-    #      and end to end with only the compressed bytes crossing PCIe
+    #      and end to end with only the compressed bytes crossing PCIe; level 6 (the reference's default: literals +
+    #      line-prefix matches) and level 1 (literals only)
     bgzf = None
     if not a.no_e2e:
-        zkw = dict(compress=True, comp_engine="device")
-        run(1, "device", a.seed + 400, **zkw)
-        barrier()
-        stz = run(a.steps, "device", a.seed, **zkw)
-        barrier()
-        z_ms = max_over_ranks(stz["bgzf_ms"] / stz["batches"])
-        zrun_ms = max_over_ranks(stz["run_ms"])
-        zseen = [0, 0]
+        bgzf = {"note": "compress=<level>, comp_engine=device: k_bgzf + scan + gather after k_reads; e2e hands BGZF bytes to the "
+                        "caller from pinned host buffers (jlp_illumina_stream); GB/s counts FASTQ bytes read + BGZF bytes written"}
+        for level in (6, 1):
+            zkw = dict(compress=level, comp_engine="device")
+            run(1, "device", a.seed + 400, **zkw)
+            barrier()
+            stz = run(a.steps, "device", a.seed, **zkw)
+            barrier()
+            z_ms = max_over_ranks(stz["bgzf_ms"] / stz["batches"])
+            zrun_ms = max_over_ranks(stz["run_ms"])
+            zseen = [0, 0]
 
-        def zsink(job, end, buf):
-            zseen[end] += len(buf)
+            def zsink(job, end, buf):
+                zseen[end] += len(buf)
 
-        run(1, zsink, a.seed + 401, **zkw)
-        zseen[0] = zseen[1] = 0
-        barrier()
-        ctx._genome = None
-        t0 = time.perf_counter()
-        stz2 = run(a.steps, zsink, a.seed, **zkw)
-        barrier()
-        t_z = max_over_ranks(time.perf_counter() - t0)
-        assert stz["bytes_out"] == st["bytes_out"] and zseen[0] == stz2["z_bytes"][0] + 28, (stz, zseen)
-        zin, zout = sum(stz["bytes_out"]) / stz["batches"], sum(stz["z_bytes"]) / stz["batches"]
-        bgzf = {"device_resident": {"value": a.steps * B * world / (zrun_ms / 1e3), "unit": UNIT, "ms_per_step": zrun_ms / a.steps},
+            run(1, zsink, a.seed + 401, **zkw)
+            zseen[0] = zseen[1] = 0
+            barrier()
+            ctx._genome = None
+            t0 = time.perf_counter()
+            stz2 = run(a.steps, zsink, a.seed, **zkw)
+            barrier()
+            t_z = max_over_ranks(time.perf_counter() - t0)
+            assert stz["bytes_out"] == st["bytes_out"] and zseen[0] == stz2["z_bytes"][0] + 28, (stz, zseen)
+            zin, zout = sum(stz["bytes_out"]) / stz["batches"], sum(stz["z_bytes"]) / stz["batches"]
+            bgzf["level%d" % level] = {
+                "device_resident": {"value": a.steps * B * world / (zrun_ms / 1e3), "unit": UNIT, "ms_per_step": zrun_ms / a.steps},
                 "e2e": {"value": a.steps * B * world / t_z, "unit": UNIT, "ms_per_step": t_z / a.steps * 1e3,
                         "d2h_bytes_per_step": stz2["d2h_bytes"] / a.steps},
-                "ratio": zout / zin, "k_bgzf_ms_per_step": z_ms,
-                "k_bgzf_GBps": (zin + zout) / (z_ms / 1e3) / 1e9,
-                "note": "compress=TRUE, comp_engine=device: k_bgzf + scan + gather after k_reads; e2e hands BGZF bytes to the caller "
-                        "from pinned host buffers (jlp_illumina_stream); GB/s counts FASTQ bytes read + BGZF bytes written"}
-        log("[bench] device BGZF: %.3f ms/step, ratio %.3f, e2e %.2f ms/step" % (z_ms, zout / zin, t_z / a.steps * 1e3))
+                "ratio": zout / zin, "k_bgzf_ms_per_step": z_ms, "k_bgzf_GBps": (zin + zout) / (z_ms / 1e3) / 1e9}
+            if rank == 0:
+                log("[bench] device BGZF level %d: %.3f ms/step, ratio %.3f, e2e %.2f ms/step" % (level, z_ms, zout / zin, t_z / a.steps * 1e3))
 
     # ---- the same through FILES (the reference-facing default sink): tmpfs, all host threads writing
     e2e_files = None
