@@ -163,19 +163,25 @@ std::string pwrite_all(int fd, const uint8_t* p, uint64_t n, uint64_t off) {
     return std::string();
 }
 
-// The same slice through a shared mapping of the file (already extended to its new size): page-cache pages are
-// allocated and filled by the calling thread, so the writer threads do not queue on the inode lock that
-// serialises write() calls on one file (measured on the B200 box's tmpfs: 7.4 GB/s with pwrite from any number
-// of threads, 14 GB/s with 16 threads copying into mappings; tools/write_probe.cpp).  Falls back to pwrite when
-// the file cannot be mapped.
-std::string mmap_write_all(int fd, const uint8_t* p, uint64_t n, uint64_t off) {
+// Files are also written through shared mappings: the main thread extends the file by a batch and maps the new
+// range once, the writer threads copy their slices into the mapping (page-cache pages are allocated and filled by
+// the copying thread, so the threads do not queue on the inode lock that serialises write() calls on one file;
+// measured on the B200 box's tmpfs: 7.4 GB/s with pwrite from any number of threads, 14 GB/s with 16 threads
+// copying into mappings, tools/write_probe.cpp), and the range is unmapped when the batch's slices are done --
+// one munmap per batch and file, not one TLB shoot-down per slice.
+struct Mapping {
+    void* base = nullptr;
+    size_t len = 0;
+    uint8_t* at = nullptr;      // where the batch's first byte goes
+    void unmap() { if (base) ::munmap(base, len); base = nullptr; len = 0; at = nullptr; }
+};
+bool map_range(int fd, uint64_t off, uint64_t n, Mapping& m) {
     static const uint64_t page = (uint64_t)sysconf(_SC_PAGESIZE);
     const uint64_t a0 = off / page * page;
-    void* m = ::mmap(nullptr, (size_t)(off + n - a0), PROT_READ | PROT_WRITE, MAP_SHARED, fd, (off_t)a0);
-    if (m == MAP_FAILED) return pwrite_all(fd, p, n, off);
-    std::memcpy(static_cast<uint8_t*>(m) + (off - a0), p, n);
-    ::munmap(m, (size_t)(off + n - a0));
-    return std::string();
+    void* p = ::mmap(nullptr, (size_t)(off + n - a0), PROT_READ | PROT_WRITE, MAP_SHARED, fd, (off_t)a0);
+    if (p == MAP_FAILED) return false;
+    m.base = p; m.len = (size_t)(off + n - a0); m.at = static_cast<uint8_t*>(p) + (off - a0);
+    return true;
 }
 
 struct HapDev {
@@ -203,6 +209,7 @@ struct Slot {
     bool busy = false;
     std::atomic<int> writes{0};   // slices of h_out still being written to / compressed for the files
     std::vector<std::vector<uint8_t>> zout[2];   // compressed slices of the batch, in file order
+    Mapping map[2];               // the file ranges this batch is being copied into
 };
 
 }  // namespace
@@ -555,6 +562,7 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
             cudaStreamSynchronize(c->s_copy);
             for (Slot& s : c->slot) {
                 c->writers.wait(s.writes);
+                for (Mapping& m : s.map) m.unmap();
                 s.busy = false;
                 s.zout[0].clear(); s.zout[1].clear();
             }
@@ -565,6 +573,7 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
     auto wait_writes = [&](Slot& s) {
         if (sink.kind != SINK_FILES) return;
         std::string e = c->writers.wait(s.writes);
+        for (Mapping& m : s.map) m.unmap();
         if (!e.empty()) { c->writers.clear_error(); throw IoErr("Error writing to file " + sink.names[0] + " / " + sink.names[1] + ": " + e); }
         // compressed slices of the slot's batch go to the files in order
         for (int k = 0; k < n_ends; k++) {
@@ -622,14 +631,15 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
                     if (mapped) {
                         struct statvfs vfs;
                         mapped = ::fstatvfs(sink.fd[e], &vfs) == 0 && (uint64_t)vfs.f_bavail * vfs.f_frsize > 2 * n + (64ull << 20) &&
-                                 ::ftruncate(sink.fd[e], (off_t)(sink.pos[e] + n)) == 0;
+                                 ::ftruncate(sink.fd[e], (off_t)(sink.pos[e] + n)) == 0 && map_range(sink.fd[e], sink.pos[e], n, s.map[e]);
                     }
                     const uint64_t slice = 8ull << 20;
                     for (uint64_t o = 0; o < n; o += slice) {
                         const int fd = sink.fd[e];
                         const uint8_t* src = s.h_out[e].p + o;
                         const uint64_t len = std::min(slice, n - o), off = sink.pos[e] + o;
-                        if (mapped) c->writers.submit(&s.writes, [fd, src, len, off]() { return mmap_write_all(fd, src, len, off); });
+                        uint8_t* dst = mapped ? s.map[e].at + o : nullptr;
+                        if (mapped) c->writers.submit(&s.writes, [dst, src, len]() { std::memcpy(dst, src, len); return std::string(); });
                         else c->writers.submit(&s.writes, [fd, src, len, off]() { return pwrite_all(fd, src, len, off); });
                     }
                     sink.pos[e] += n;

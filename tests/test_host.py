@@ -301,6 +301,28 @@ def test_check_illumina_args_rejects_what_the_reference_rejects():
             call(**bad)
 
 
+def test_params_struct_matches_the_header():
+    """The ctypes mirrors of jlp_illumina_params / jlp_run_stats have the fields of include/jlp_b200.h, in order
+    (comp_engine and the device-BGZF statistics included), and comp_engine is validated before anything runs."""
+    import re
+    hdr = open(os.path.join(ROOT, "include", "jlp_b200.h")).read()
+
+    def fields(struct):
+        body = hdr[hdr.index("typedef struct " + struct):hdr.index("} " + struct + ";")]
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        out = []
+        for decl in body.split("{", 1)[1].split(";"):
+            names = re.findall(r"([A-Za-z_][A-Za-z_0-9]*)\s*(?:\[[0-9]+\])?\s*(?:,|$)", decl.strip())
+            out += [n for n in names if n]
+        return out
+
+    assert fields("jlp_illumina_params") == [f[0] for f in _lib.Params._fields_]
+    assert fields("jlp_run_stats") == [f[0] for f in _lib.RunStats._fields_]
+    g = J.random_genome(1, 500, seed=1)
+    with pytest.raises(J.JackalopeError, match="comp_engine"):
+        J.illumina(g, "", 10, 100, True, seed=1, sink="memory", comp_engine="gpu")
+
+
 # ------------------------------------------------------------- golden vectors ---
 
 @pytest.mark.parametrize("name", sorted(CASES))
