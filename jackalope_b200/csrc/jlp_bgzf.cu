@@ -53,6 +53,17 @@ __constant__ uint32_t c_crc_init_full;     // the initial register 0xffffffff ad
 // advance(v) = T[0][v & 255] ^ T[1][v >> 8 & 255] ^ T[2][v >> 16 & 255] ^ T[3][v >> 24]
 __device__ uint32_t g_crc_lvl[9][4][256];
 
+// scratch of one Huffman construction
+struct HuffScratch {
+    uint32_t* sw;        // weights of the leaves in sorted order
+    uint32_t* w_int;     // ... of the internal nodes in creation order
+    uint16_t* sorted;    // symbols with count > 0, ascending count
+    uint16_t* par_leaf;  // parent (internal node index) of leaves
+    uint16_t* par_int;   // ... of internal nodes
+    uint8_t* d_int;
+    uint32_t* bl;        // codes per length
+};
+
 struct ZShared {
     uint32_t stage[kStageWords];          // the block image; its last 16 KiB hold the per-warp literal counts until the packing starts
     uint32_t mask[kMaskWords];            // bit q + 1: byte q of the block is covered by a match
@@ -78,6 +89,10 @@ struct ZShared {
     uint8_t dlen[32];
     uint8_t d_int[288];
     uint8_t cl_len[19];
+    // a second, small scratch: the distance code is built by warp 1 while thread 0 builds the literal/length tree
+    uint32_t sw2[32], w_int2[32], bl2[16];
+    uint16_t sorted2[32], par_leaf2[32], par_int2[32];
+    uint8_t d_int2[32];
     uint32_t maxd, hlit, hdist, hdr_fixed_bits, eob, crc_out;
 };
 
@@ -112,7 +127,7 @@ __device__ __forceinline__ void put_bits(uint32_t* w, uint32_t& pos, uint32_t v,
 
 // Two-queue Huffman over the leaves S.sw[0 .. n) (ascending): parents into par_leaf / par_int, the root is
 // internal node n - 2.  One thread; the heads of both queues are kept in registers.
-__device__ void huff_merge(ZShared& S, uint32_t n) {
+__device__ void huff_merge(const HuffScratch& S, uint32_t n) {
     uint32_t i = 0, k = 0, m = 0;
     uint32_t lw = S.sw[0], iw = 0xffffffffu;
     while (m + 1 < n) {
@@ -136,7 +151,7 @@ __device__ void huff_merge(ZShared& S, uint32_t n) {
 // Code lengths limited to max_bits from the tree huff_merge left (one thread): depths top-down, clamped, then the
 // count fix-up for over-long codes, then lengths handed out in sorted order (longest code to the rarest symbol).
 // Leaves S.bl[] = codes per length.
-__device__ void huff_limit(ZShared& S, uint32_t n, uint32_t max_bits, uint8_t* len) {
+__device__ void huff_limit(const HuffScratch& S, uint32_t n, uint32_t max_bits, uint8_t* len) {
     for (uint32_t b = 0; b < 16; b++) S.bl[b] = 0;
     int overflow = 0;
     S.d_int[n - 2] = 0;
@@ -185,7 +200,7 @@ __device__ __forceinline__ uint32_t first_code(const uint32_t* bl, uint32_t l) {
 // Lengths (<= max_bits) into len[], bit-reversed canonical codes into code[]; an alphabet with fewer than two
 // used symbols gets a second, unused one-bit code (a complete code, as zlib sends).  Returns the number of
 // used symbols, dummies included, through the highest one + 1.  Uses the CTA's Huffman scratch.
-__device__ uint32_t warp_huffman(ZShared& S, uint32_t c, uint32_t n_sym, uint32_t max_bits, uint8_t* len, uint16_t* code,
+__device__ uint32_t warp_huffman(const HuffScratch& S, uint32_t c, uint32_t n_sym, uint32_t max_bits, uint8_t* len, uint16_t* code,
                                  uint32_t lane) {
     const uint32_t n = __popc(__ballot_sync(0xffffffffu, c != 0));
     const uint32_t key = c << 5 | lane;
@@ -431,6 +446,8 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
 
     const uint32_t my_off = t * kChunk;
     const uint32_t my_len = my_off >= len ? 0u : min(kChunk, len - my_off);
+    const HuffScratch H1{S.sw, S.w_int, S.sorted, S.par_leaf, S.par_int, S.d_int, S.bl};
+    const HuffScratch H2{S.sw2, S.w_int2, S.sorted2, S.par_leaf2, S.par_int2, S.d_int2, S.bl2};
 
     // ---- clear the image (and with it the histograms), the match mask and the counters
     {
@@ -586,7 +603,11 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
     __syncthreads();
 
     // ---- literal/length code lengths: the tree by one thread, the depths by one thread per leaf
-    if (t == 0) huff_merge(S, n_active);       // n_active >= 2: a literal or a match, and the end of block
+    if (t == 0) huff_merge(H1, n_active);      // n_active >= 2: a literal or a match, and the end of block
+    if (warp == 1) {                           // meanwhile the distance code
+        const uint32_t hd = warp_huffman(H2, lane < kNDist ? S.dcnt[lane] : 0u, kNDist, 15, S.dlen, S.dcode, lane);
+        if (lane == 0) S.hdist = hd;
+    }
     __syncthreads();
     if (t < n_active) {
         uint32_t p = S.par_leaf[t], dep = 1;
@@ -598,7 +619,7 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
     }
     __syncthreads();
     if (S.maxd > 15) {                         // rare: the 15-bit limit has to act
-        if (t == 0) huff_limit(S, n_active, 15, S.len);
+        if (t == 0) huff_limit(H1, n_active, 15, S.len);
         __syncthreads();
     }
     // canonical codes: first code of the length + the symbols of the same length before this one
@@ -613,12 +634,6 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
             S.code[t] = (uint16_t)rev_bits(first_code(S.bl, l) + same / 8, l);
         }
         if (t < 256) S.ctab[t] = l ? (uint32_t)S.code[t] | l << 16 : 0u;
-    }
-    __syncthreads();
-    // ---- the distance code (warp 0; S.bl is free again)
-    if (warp == 0) {
-        const uint32_t hd = warp_huffman(S, lane < kNDist ? S.dcnt[lane] : 0u, kNDist, 15, S.dlen, S.dcode, lane);
-        if (lane == 0) S.hdist = hd;
     }
     __syncthreads();
     // the runs of the code-length sequence (HLIT literal/length lengths, then HDIST distance lengths): one thread
@@ -654,7 +669,7 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
 
     // ---- the code-length code and the fixed part of the block header (warp 0) while the others size their segments
     if (warp == 0) {
-        warp_huffman(S, lane < 19 ? S.cl_cnt[lane] : 0u, 19, 7, S.cl_len, S.cl_code, lane);
+        warp_huffman(H2, lane < 19 ? S.cl_cnt[lane] : 0u, 19, 7, S.cl_len, S.cl_code, lane);
         const uint32_t l = lane < 19 ? S.cl_len[lane] : 0u;
         const uint32_t order_lane = lane < 19 ? (uint32_t)"\x10\x11\x12\x00\x08\x07\x09\x06\x0a\x05\x0b\x04\x0c\x03\x0d\x02\x0e\x01\x0f"[lane] : 0u;
         // HCLEN: the lengths are sent in the order 16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15 up to the last one used
