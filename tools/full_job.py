@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """The whole BASELINE.json configs[4] job on one B200: 3.1 Gb genome, 30x coverage, PE150 HS25 =
-3.1e8 read pairs (~204 GB of FASTQ).  Two legs: FASTQ left in HBM, and FASTQ streamed into the
-library's pinned host buffers (nothing is written to disk: no file system here takes 200 GB).
+3.1e8 read pairs (~204 GB of FASTQ).  Legs: FASTQ left in HBM, FASTQ streamed into the
+library's pinned host buffers (nothing is written to disk: no file system here takes 200 GB), and the same
+stream compressed on the device (compress = 6 and 1: BGZF bytes reach the host).
 Prints one JSON line; run under gpurun, output kept in profiles/."""
 import json
 import os
@@ -45,7 +46,21 @@ st2 = J.illumina(g, "", 2 * full_pairs, L, True, seed=2, ctx=ctx, sink=sink, **k
 torch.cuda.synchronize()
 t_e2e = time.perf_counter() - t0
 assert seen == st2["bytes_out"] == st["bytes_out"]
-print(json.dumps({"workload": "3.1 Gb genome, 30x, PE150 HS25", "pairs": full_pairs, "fastq_bytes": sum(seen),
+bg = {}
+for level in (6, 1):
+    zk = dict(compress=level, comp_engine="device")
+    J.illumina(g, "", 2 * (1 << 21), L, True, seed=1, ctx=ctx, sink=sink, **kw, **zk)
+    seen[0] = seen[1] = 0
+    ctx._genome = None
+    t0 = time.perf_counter()
+    st3 = J.illumina(g, "", 2 * full_pairs, L, True, seed=2, ctx=ctx, sink=sink, **kw, **zk)
+    torch.cuda.synchronize()
+    t_z = time.perf_counter() - t0
+    assert st3["bytes_out"] == st["bytes_out"] and seen[0] == st3["z_bytes"][0] + 28
+    bg["level%d" % level] = {"end_to_end_s": t_z, "end_to_end_pairs_per_s": full_pairs / t_z, "bgzf_bytes": sum(seen),
+                             "ratio": sum(st3["z_bytes"]) / sum(st3["bytes_out"]), "k_bgzf_ms_per_batch": st3["bgzf_ms"] / st3["batches"]}
+seen[0], seen[1] = st2["bytes_out"]
+print(json.dumps({"bgzf": bg, "workload": "3.1 Gb genome, 30x, PE150 HS25", "pairs": full_pairs, "fastq_bytes": sum(seen),
                   "device_resident_s": t_dev, "device_resident_pairs_per_s": full_pairs / t_dev,
                   "device_event_ms": st["run_ms"], "batches": st["batches"],
                   "end_to_end_s": t_e2e, "end_to_end_pairs_per_s": full_pairs / t_e2e,
