@@ -125,6 +125,62 @@ def test_config4_96_haplotypes_uneven_sep_files(ctx, tmp_path):
     check_slices(ctx, haps, n_reads, 150, True, 10, 40, [0, 39], hap_seqs=hs, **kw)
 
 
+def test_config4_compressed_sep_files(ctx, tmp_path):
+    """The same multiplexed run with compress = TRUE: 192 BGZF files written by the GPU; every one inflates to
+    the plain run's file."""
+    import gzip
+    g = J.random_genome(12, 2_000_000, seed=105)
+    haps = J.random_haplotypes(g, 96, sub_rate=0.005, indel_rate=0.0005, seed=106)
+    probs = (1.0 / np.arange(1, 97)).tolist()
+    n_reads = 600_000
+    kw = dict(haplotype_probs=probs, sep_files=True, seq_sys="HS25")
+    pre, zpre = str(tmp_path / "mx"), str(tmp_path / "mz")
+    J.illumina(haps, pre, n_reads, 150, True, seed=10, ctx=ctx, n_threads=4, **kw)
+    J.illumina(haps, zpre, n_reads, 150, True, seed=10, ctx=ctx, n_threads=4, compress=True, **kw)
+    plain = comp = 0
+    for h in haps.hap_names:
+        for r in (1, 2):
+            a = open("%s_%s_R%d.fq" % (pre, h, r), "rb").read()
+            z = open("%s_%s_R%d.fq.gz" % (zpre, h, r), "rb").read()
+            assert z[-28:-24] == b"\x1f\x8b\x08\x04" and gzip.decompress(z) == a     # ends with the BGZF EOF block
+            plain += len(a)
+            comp += len(z)
+    assert comp < 0.37 * plain
+
+
+def test_config5_slice_compressed_stream(ctx):
+    """A 1e6-pair slice of the human-scale workload shape (24 chromosomes, PE150 HS25) streamed as BGZF at both
+    device levels: the inflated stream has the plain stream's digest.  Every chunk the sink receives is a whole
+    number of BGZF members, walked by their BSIZE fields."""
+    import struct
+    import zlib
+    g = J.random_genome(24, 500_000, seed=107)
+    n_reads = 2_000_000
+    a1, a2, lines, st = digest_run(ctx, g, n_reads, 150, True, 11, seq_sys="HS25", batch_pairs=300_000)
+    for level in (1, 6):
+        h = [hashlib.sha256(), hashlib.sha256()]
+        nz = [0, 0]
+
+        def sink(job, end, buf):
+            mv = memoryview(bytes(buf))
+            nz[end] += len(mv)
+            p = 0
+            while p < len(mv):
+                bsize = struct.unpack_from("<H", mv, p + 16)[0] + 1
+                body = zlib.decompress(mv[p + 18:p + bsize - 8], -15)
+                crc, isize = struct.unpack_from("<II", mv, p + bsize - 8)
+                assert isize == len(body) and crc == zlib.crc32(body)
+                h[end].update(body)
+                p += bsize
+            assert p == len(mv)
+
+        stz = J.illumina(g, "", n_reads, 150, True, seed=11, ctx=ctx, sink=sink, seq_sys="HS25", compress=level,
+                         comp_engine="device", batch_pairs=300_000)
+        assert (h[0].hexdigest(), h[1].hexdigest()) == (a1, a2)
+        assert stz["d2h_bytes"] == sum(stz["z_bytes"]) and nz[0] == stz["z_bytes"][0] + 28
+        assert sum(stz["z_bytes"]) < (0.36 if level == 6 else 0.40) * sum(st["bytes_out"])
+
+
 def test_model_statistics_at_scale(ctx):
     """4e5 PE150 HS25 pairs: per-position quality histograms against the profile, mismatch rate per
     position against sum_q P(q) 10^(-q/10), strand balance, fragment lengths against the Gamma law."""
