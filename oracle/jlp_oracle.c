@@ -547,3 +547,278 @@ uint64_t orc_unif_expr(int kind, uint64_t x, double p, uint64_t n) {
     }
     return 0;
 }
+
+/* ==================================================================== PacBio ===
+ * C restatement of the PacBio read model (/root/reference/src/hts_pacbio.{h,cpp}):
+ * what PacBioOneGenome::one_read does once the two stateful samplers have spoken.  Read length and
+ * (split_pos, passes_left, passes_right) are INJECTED per read (std::lognormal_distribution and
+ * std::chi_squared_distribution keep cached normals, so their draw counts depend on the history; they are
+ * compared statistically), everything after them is restated draw for draw:
+ *   PacBioQualityError::calc_min_exp      src/hts_pacbio.cpp
+ *   PacBioQualityError::update_probs      src/hts_pacbio.cpp      (trunc_norm: src/hts_pacbio.h:340-370)
+ *   PacBioQualityError::fill_quals        src/hts_pacbio.h:383-391
+ *   PacBioQualityError::sample (the walk) src/hts_pacbio.h:282-318
+ *   read_chrom_space, read_start          src/hts_pacbio.cpp, one_read
+ *   PacBioOneGenome::append_pool          src/hts_pacbio.cpp
+ * R::pnorm5 / R::qnorm5 are the stand-ins of rmath_standin.h on both sides of the comparison.
+ *
+ * Draw addressing: counter = (j_lo, j_hi, block, PL_PB | sub << 8), two 64-bit draws per Philox block.
+ *   sub 0 (read):  block 0: truncated normal left, right (its usual branch: one draw each);
+ *                  block 1: read_start, strand;
+ *                  blocks 16 + 2 it / 17 + 2 it: draws (u, v) of iteration `it` of the tail branch's rejection
+ *                  loop, left (lo halves) and right (hi halves)
+ *   sub 1 (walk):  template position p -> block p >> 1, half p & 1
+ *   sub 2 (edit):  the inserted / substituted base drawn at read position p -> block p >> 1, half p & 1 */
+#include "rmath_standin.h"
+
+enum { PL_PB = 4 };
+
+static uint64_t pb_draw(uint64_t seed, uint64_t j, uint32_t sub, uint32_t block, uint32_t half) {
+    uint32_t w[4];
+    call(seed, j, block, PL_PB, sub, w);
+    return half ? (((uint64_t)w[3] << 32) | w[2]) : (((uint64_t)w[1] << 32) | w[0]);
+}
+uint64_t orc_pb_draw(uint64_t seed, uint64_t j, uint32_t sub, uint32_t block, uint32_t half) { return pb_draw(seed, j, sub, block, half); }
+
+typedef struct {
+    double sqrt_params[2], norm_params[2];
+    double prob_thresh, prob_ins, prob_del, prob_subst;
+    double min_exp;
+} PbModel;
+
+static double pb_total(const PbModel* m, double e) { return pow(m->prob_ins, e) + pow(m->prob_del, e) + pow(m->prob_subst, e); }
+
+/* PacBioQualityError::calc_min_exp */
+static double pb_calc_min_exp(const PbModel* m) {
+    double min_exp = 1, total = pb_total(m, min_exp), left, right;
+    if (total < m->prob_thresh) {
+        while (total < m->prob_thresh) { min_exp /= 2; total = pb_total(m, min_exp); }
+        left = min_exp; right = min_exp * 2;
+    } else {
+        while (total > m->prob_thresh) { min_exp *= 2; total = pb_total(m, min_exp); }
+        left = min_exp / 2; right = min_exp;
+    }
+    for (int i = 0; i < 15; i++) {
+        double mid = (left + right) / 2;
+        total = pb_total(m, mid);
+        if (total == m->prob_thresh) { min_exp = mid; break; }
+        else if (total > m->prob_thresh) { left = mid; min_exp = (mid + right) / 2; }
+        else { right = mid; min_exp = (left + mid) / 2; }
+    }
+    return min_exp;
+}
+double orc_pb_min_exp(const double* sqrt_params, const double* norm_params, double prob_thresh, double prob_ins,
+                      double prob_del, double prob_subst) {
+    PbModel m = {{sqrt_params[0], sqrt_params[1]}, {norm_params[0], norm_params[1]}, prob_thresh, prob_ins, prob_del, prob_subst, 0};
+    return pb_calc_min_exp(&m);
+}
+
+static double pb_sigmoid(double x) { return 1 / (1 + pow(2, (-2.5 / 3 * x + 6.5 / 3))); }
+
+/* PacBioQualityError::trunc_norm; side 0 = left, 1 = right */
+static double pb_trunc_norm(const PbModel* m, double lower_thresh, uint64_t seed, uint64_t j, int side, Ledger* lg) {
+    double rnd;
+    const double a_bar = (lower_thresh - m->norm_params[0]) / m->norm_params[1];
+    if (lower_thresh < (m->norm_params[0] + 5 * m->norm_params[1])) {
+        const double p = jlp_pnorm(a_bar);
+        const uint64_t x = pb_draw(seed, j, 0, 0, (uint32_t)side);
+        led(lg, x);
+        /* runif_ab(eng, p, 1), src/pcg.h:103-105, in long double; R::qnorm5 takes a double */
+        const long double u = (long double)p + runif_01(x) * ((long double)1 - (long double)p);
+        const double q = jlp_qnorm((double)u);
+        rnd = q * m->norm_params[1] + m->norm_params[0];
+    } else {
+        double u, x_bar, v;
+        for (uint32_t it = 0;; it++) {
+            const uint64_t xu = pb_draw(seed, j, 0, 16 + 2 * it, (uint32_t)side), xv = pb_draw(seed, j, 0, 17 + 2 * it, (uint32_t)side);
+            led(lg, xu);
+            u = (double)runif_01(xu);
+            x_bar = sqrt(a_bar * a_bar - 2 * log(1 - u));
+            led(lg, xv);
+            v = (double)runif_01(xv);
+            if (!(v > (x_bar / a_bar))) break;
+        }
+        rnd = m->norm_params[1] * x_bar + m->norm_params[0];
+    }
+    return rnd;
+}
+
+typedef struct {
+    uint64_t seed;
+    uint64_t job_lo, job_hi;
+    double sqrt_params[2], norm_params[2];
+    double prob_thresh, prob_ins, prob_del, prob_subst;
+    uint64_t n_groups;
+    const uint64_t* group_off;
+    const char* const* group_seq;
+    const uint64_t* group_len;
+    const char* const* group_genome_name;
+    const char* const* group_chrom_name;
+    /* injected, indexed by j - job_lo */
+    const uint64_t* read_len;
+    const uint64_t* split_pos;
+    const double* passes_left;
+    const double* passes_right;
+} OrcPbJob;
+
+/* Reads [lo, hi) of the job.  plan (optional): [4 * (hi - lo)] group, read_length, read_start, read_chrom_space. */
+int orc_pacbio_generate(const OrcPbJob* J, uint64_t lo, uint64_t hi, char* out, uint64_t cap, uint64_t* len,
+                        uint64_t* plan, uint64_t* ledger, uint64_t ledger_cap, uint64_t* ledger_n, uint64_t* ledger_cnt) {
+    PbModel m = {{J->sqrt_params[0], J->sqrt_params[1]}, {J->norm_params[0], J->norm_params[1]},
+                 J->prob_thresh, J->prob_ins, J->prob_del, J->prob_subst, 0};
+    m.min_exp = pb_calc_min_exp(&m);
+    Sink S = {out, 0, cap};
+    Ledger lg = {ledger, 0, ledger_cap, ledger != NULL};
+    char* read = NULL;
+    uint64_t read_cap = 0;
+    uint64_t *ins = NULL, *del = NULL, *sub = NULL;
+    uint64_t ev_cap = 0;
+    int rc = 0;
+    for (uint64_t j = lo; j < hi; j++) {
+        const uint64_t led0 = lg.n;
+        /* the group: first (haplotype, chromosome) with reads left, one_read */
+        uint64_t g, glo = 0, ghi = J->n_groups;
+        while (ghi - glo > 1) { uint64_t mid = (glo + ghi) / 2; if (J->group_off[mid] <= j) glo = mid; else ghi = mid; }
+        g = glo;
+        const char* chrom = J->group_seq[g];
+        const uint64_t chrom_len = J->group_len[g];
+        uint64_t read_length = J->read_len[j - J->job_lo];
+        if (read_length >= chrom_len) read_length = chrom_len;
+        const uint64_t split_pos = J->split_pos[j - J->job_lo];
+        const double passes_left = J->passes_left[j - J->job_lo], passes_right = J->passes_right[j - J->job_lo];
+
+        /* ---- update_probs */
+        double cum_left[3], cum_right[3];
+        {
+            const double left_thresh = (m.min_exp - (sqrt(passes_left + m.sqrt_params[0]) - m.sqrt_params[1])) / pb_sigmoid(passes_left);
+            const double right_thresh = (m.min_exp - (sqrt(passes_right + m.sqrt_params[0]) - m.sqrt_params[1])) / pb_sigmoid(passes_right);
+            const double incr_l = pb_trunc_norm(&m, left_thresh, J->seed, j, 0, &lg);
+            const double incr_r = pb_trunc_norm(&m, right_thresh, J->seed, j, 1, &lg);
+            double exp_l = incr_l * pb_sigmoid(passes_left) + sqrt(passes_left + m.sqrt_params[0]) - m.sqrt_params[1];
+            double exp_r = incr_r * pb_sigmoid(passes_right) + sqrt(passes_right + m.sqrt_params[0]) - m.sqrt_params[1];
+            if (exp_l < 0.6) exp_l = 0.6;
+            if (exp_r < 0.6) exp_r = 0.6;
+            cum_left[0] = pow(m.prob_ins, exp_l);
+            cum_left[1] = pow(m.prob_del, exp_l) + cum_left[0];
+            cum_left[2] = pow(m.prob_subst, exp_l) + cum_left[1];
+            cum_right[0] = pow(m.prob_ins, exp_r);
+            cum_right[1] = pow(m.prob_del, exp_r) + cum_right[0];
+            cum_right[2] = pow(m.prob_subst, exp_r) + cum_right[1];
+        }
+        /* ---- fill_quals */
+        char qual_left, qual_right;
+        {
+            uint64_t tl = (uint64_t)round(-10.0 * log10(cum_left[2])), tr = (uint64_t)round(-10.0 * log10(cum_right[2]));
+            if (tl > 93) tl = 93;
+            if (tr > 93) tr = 93;
+            qual_left = (char)(tl + '!');
+            qual_right = (char)(tr + '!');
+        }
+        /* ---- the walk (PacBioQualityError::sample) */
+        if (2 * read_length + 16 > ev_cap) {
+            ev_cap = 2 * read_length + 16;
+            ins = (uint64_t*)realloc(ins, ev_cap * 8); del = (uint64_t*)realloc(del, ev_cap * 8); sub = (uint64_t*)realloc(sub, ev_cap * 8);
+            if (!ins || !del || !sub) { rc = -2; break; }
+        }
+        uint64_t n_ins = 0, n_del = 0, n_sub = 0;
+        {
+            uint64_t current_length = 0, chrom_pos = 0, extra_space = chrom_len - read_length;
+            const double* cum = cum_left;
+            while (current_length < read_length) {
+                if (current_length == split_pos) cum = cum_right;
+                const uint64_t x = pb_draw(J->seed, j, 1, (uint32_t)(chrom_pos >> 1), (uint32_t)(chrom_pos & 1));
+                led(&lg, x);
+                const double u = (double)runif_01(x);     /* `double u` in the reference */
+                if (u > cum[2]) {
+                    current_length++;
+                } else if (u < cum[0]) {
+                    if (current_length < (read_length - 1)) {
+                        if (n_ins < ev_cap) ins[n_ins] = chrom_pos;
+                        n_ins++;
+                        current_length++;
+                        extra_space++;
+                        if (current_length == split_pos) cum = cum_right;
+                    }
+                    current_length++;
+                } else if (u < cum[1]) {
+                    if (extra_space > 0) {
+                        if (n_del < ev_cap) del[n_del] = chrom_pos;
+                        n_del++;
+                        extra_space--;
+                    }
+                } else {
+                    if (n_sub < ev_cap) sub[n_sub] = chrom_pos;
+                    n_sub++;
+                    current_length++;
+                }
+                chrom_pos++;
+                if (chrom_pos >= ev_cap + 4 * read_length + (1u << 20)) { rc = -3; break; }   /* cannot happen: guards the loop */
+            }
+            if (rc) break;
+        }
+        /* ---- read_chrom_space, read_start */
+        const uint64_t space = read_length + n_del - n_ins;
+        uint64_t read_start = 0;
+        if (space < chrom_len) {
+            const uint64_t x = pb_draw(J->seed, j, 0, 1, 0);
+            led(&lg, x);
+            const double u = (double)runif_01(x);
+            read_start = (uint64_t)(u * (double)(chrom_len - space + 1));
+        } else if (space > chrom_len) { rc = -4; break; }
+        /* ---- append_pool */
+        {
+            const uint64_t x = pb_draw(J->seed, j, 0, 1, 1);
+            led(&lg, x);
+            const int reverse = runif_01(x) < 0.5;
+            char num[24];
+            putc_(&S, '@');
+            put(&S, J->group_genome_name[g], strlen(J->group_genome_name[g]));
+            putc_(&S, '-');
+            put(&S, J->group_chrom_name[g], strlen(J->group_chrom_name[g]));
+            putc_(&S, '-');
+            int nd = snprintf(num, sizeof num, "%llu", (unsigned long long)read_start);
+            put(&S, num, (uint64_t)nd);
+            putc_(&S, '-');
+            putc_(&S, reverse ? 'R' : 'F');
+            putc_(&S, '\n');
+            if (space + 1 > read_cap) { read_cap = space + 1; read = (char*)realloc(read, read_cap); if (!read) { rc = -2; break; } }
+            memcpy(read, chrom + read_start, space);
+            if (reverse) orc_rev_comp(read, space);
+            uint64_t read_pos = 0, current_length = 0, ii = 0, di = 0, si = 0;
+            while (current_length < read_length) {
+                if (ii < n_ins && read_pos == ins[ii]) {
+                    const uint64_t xe = pb_draw(J->seed, j, 2, (uint32_t)(read_pos >> 1), (uint32_t)(read_pos & 1));
+                    led(&lg, xe);
+                    const uint64_t rndi = (uint64_t)(runif_01(xe) * 4);
+                    putc_(&S, read[read_pos]);
+                    putc_(&S, BASES[rndi]);
+                    ii++;
+                    current_length += 2;
+                } else if (di < n_del && read_pos == del[di]) {
+                    di++;
+                } else if (si < n_sub && read_pos == sub[si]) {
+                    const uint64_t xe = pb_draw(J->seed, j, 2, (uint32_t)(read_pos >> 1), (uint32_t)(read_pos & 1));
+                    led(&lg, xe);
+                    const uint64_t rndi = (uint64_t)(runif_01(xe) * 3);
+                    putc_(&S, MM[nt_map((unsigned char)read[read_pos])][rndi]);
+                    si++;
+                    current_length++;
+                } else {
+                    putc_(&S, read[read_pos]);
+                    current_length++;
+                }
+                read_pos++;
+            }
+            putc_(&S, '\n'); putc_(&S, '+'); putc_(&S, '\n');
+            for (uint64_t i = 0; i < split_pos; i++) putc_(&S, qual_left);
+            for (uint64_t i = split_pos; i < read_length; i++) putc_(&S, qual_right);
+            putc_(&S, '\n');
+        }
+        if (plan) { uint64_t* p = plan + 4 * (j - lo); p[0] = g; p[1] = read_length; p[2] = read_start; p[3] = space; }
+        if (ledger_cnt) ledger_cnt[j - lo] = lg.n - led0;
+    }
+    free(read); free(ins); free(del); free(sub);
+    *len = S.n;
+    if (ledger_n) *ledger_n = lg.n;
+    return rc;
+}

@@ -42,6 +42,24 @@ inline uint64_t r_rng_next() {
 }
 }  // namespace jlp_stub
 
+// Rmath: the three functions the PacBio path calls (src/hts_pacbio.h:178,349,352); see rmath_standin.h
+#include "../rmath_standin.h"
+namespace R {
+inline double pnorm5(double x, double mu, double sigma, int lower, int log_p) {
+    (void)log_p;
+    const double p = jlp_pnorm((x - mu) / sigma);
+    return lower ? p : 1.0 - p;
+}
+inline double qnorm5(double p, double mu, double sigma, int lower, int log_p) {
+    (void)log_p;
+    return mu + sigma * jlp_qnorm(lower ? p : 1.0 - p);
+}
+inline double qchisq(double p, double df, int lower, int log_p) {
+    (void)log_p;
+    return jlp_qchisq(lower ? p : 1.0 - p, df);
+}
+}  // namespace R
+
 namespace Rcpp {
 
 struct exception : public std::runtime_error {
