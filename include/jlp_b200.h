@@ -192,6 +192,53 @@ int jlp_illumina_device_only(jlp_ctx* ctx, int use_haplotypes, const jlp_illumin
 int jlp_illumina_group_counts(jlp_ctx* ctx, int use_haplotypes, const jlp_illumina_params* p,
                               uint64_t* counts, uint64_t cap, uint64_t* n_groups);
 
+/* ---- PacBio reads: pacbio_ref_cpp / pacbio_hap_cpp,
+ *      /root/reference/src/hts_pacbio.cpp; arguments of pacbio(), R/hts_pacbio.R -------------------------------- */
+
+typedef struct jlp_pacbio_params {
+    /* the arguments of pacbio_{ref,hap}_cpp, same meaning */
+    const char* out_prefix;      /* files <prefix>[_<hap>]_R1.fq */
+    int sep_files;               /* haplotype runs only */
+    int compress;                /* as for Illumina; the device coder serves levels 1..6 */
+    const char* comp_method;
+    uint64_t n_reads;
+    uint64_t n_threads;          /* accepted for compatibility; the files are written by the calling thread */
+    uint64_t read_pool_size;
+    const double* haplotype_probs;
+    double prob_dup;             /* must be 0 (the default of pacbio()): duplicates are not built yet */
+    double scale, sigma, loc;    /* lognorm_read_length[3], [1], [2] */
+    double min_read_len;
+    const double* read_probs;    /* custom_read_lengths: n_custom probabilities and lengths, or NULL / 0 */
+    const uint64_t* read_lens;
+    uint64_t n_custom;
+    uint64_t max_passes;
+    double chi2_params_n[3];
+    double chi2_params_s[5];
+    double sqrt_params[2];
+    double norm_params[2];
+    double prob_thresh, prob_ins, prob_del, prob_subst;
+    /* additions of this implementation */
+    uint64_t seed;
+    uint64_t batch_reads;        /* reads per device batch; 0 = default */
+    int comp_engine;             /* enum jlp_comp_engine */
+} jlp_pacbio_params;
+
+/* Reads into files (use_haplotypes: the haplotypes added so far, else the reference genome). */
+int jlp_pacbio(jlp_ctx* ctx, int use_haplotypes, const jlp_pacbio_params* p, jlp_run_stats* stats);
+/* The same into a caller-provided host buffer (with sep_files the haplotypes' outputs are concatenated); out == NULL
+ * generates and drops the reads on the device.  *len receives the bytes needed. */
+int jlp_pacbio_to_memory(jlp_ctx* ctx, int use_haplotypes, const jlp_pacbio_params* p, char* out, uint64_t cap,
+                         uint64_t* len, jlp_run_stats* stats);
+/* What the run `p` describes draws for each of its reads before the per-base work: the (haplotype, chromosome) group,
+ * the read length (already limited to the chromosome), split_pos, passes_left, passes_right -- the quantities the
+ * reference's stateful samplers produce, which the parity tests inject into the oracle.  Arrays of n_reads entries. */
+int jlp_pacbio_read_plan(jlp_ctx* ctx, int use_haplotypes, const jlp_pacbio_params* p, uint64_t* group, uint64_t* read_len,
+                         uint64_t* split_pos, double* passes_left, double* passes_right);
+/* The samplers alone, no device needed: n reads of a chromosome of chrom_len bases (statistical tests against
+ * PacBioReadLenSampler::sample / PacBioPassSampler::sample). */
+int jlp_pacbio_sample(const jlp_pacbio_params* p, uint64_t n, uint64_t chrom_len, uint64_t* read_len, uint64_t* split_pos,
+                      double* passes_left, double* passes_right);
+
 /* ---- host-side pieces exposed for CPU tests (no device needed) --------------- */
 
 /* The apportioning jlp_illumina_group_counts reports, from sizes alone: pairs ->

@@ -33,6 +33,19 @@ class Params(C.Structure):
     ]
 
 
+class PacbioParams(C.Structure):
+    _fields_ = [
+        ("out_prefix", C.c_char_p), ("sep_files", C.c_int), ("compress", C.c_int), ("comp_method", C.c_char_p),
+        ("n_reads", C.c_uint64), ("n_threads", C.c_uint64), ("read_pool_size", C.c_uint64), ("haplotype_probs", f64p),
+        ("prob_dup", C.c_double), ("scale", C.c_double), ("sigma", C.c_double), ("loc", C.c_double),
+        ("min_read_len", C.c_double), ("read_probs", f64p), ("read_lens", u64p), ("n_custom", C.c_uint64),
+        ("max_passes", C.c_uint64), ("chi2_params_n", C.c_double * 3), ("chi2_params_s", C.c_double * 5),
+        ("sqrt_params", C.c_double * 2), ("norm_params", C.c_double * 2), ("prob_thresh", C.c_double),
+        ("prob_ins", C.c_double), ("prob_del", C.c_double), ("prob_subst", C.c_double), ("seed", C.c_uint64),
+        ("batch_reads", C.c_uint64), ("comp_engine", C.c_int),
+    ]
+
+
 class RunStats(C.Structure):
     _fields_ = [
         ("pairs", C.c_uint64), ("bytes_out", C.c_uint64 * 2), ("batches", C.c_uint64),
@@ -52,7 +65,7 @@ class RunStats(C.Structure):
 SYMBOLS = [
     "jlp_ctx_create", "jlp_ctx_destroy", "jlp_last_error", "jlp_set_genome", "jlp_set_genome_async", "jlp_genome_sync", "jlp_create_genome", "jlp_get_genome", "jlp_genome_draw", "jlp_clear_haplotypes",
     "jlp_add_haplotype", "jlp_get_haplotype_chrom", "jlp_set_profile", "jlp_illumina_ref", "jlp_illumina_hap",
-    "jlp_illumina_to_memory", "jlp_illumina_stream", "jlp_illumina_device_only", "jlp_illumina_group_counts", "jlp_apportion", "jlp_shard_range", "jlp_deflate", "jlp_bgzf_device", "jlp_reads_per_group", "jlp_alias_build",
+    "jlp_illumina_to_memory", "jlp_illumina_stream", "jlp_illumina_device_only", "jlp_illumina_group_counts", "jlp_apportion", "jlp_shard_range", "jlp_deflate", "jlp_bgzf_device", "jlp_pacbio", "jlp_pacbio_to_memory", "jlp_pacbio_read_plan", "jlp_pacbio_sample", "jlp_reads_per_group", "jlp_alias_build",
     "jlp_threshold", "jlp_unif_expr", "jlp_frag_table", "jlp_philox4x32_10", "jlp_draw_pos", "jlp_draw_pair",
     "jlp_version",
 ]
@@ -98,6 +111,10 @@ def lib():
     L.jlp_shard_range.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, u64p, u64p]
     L.jlp_deflate.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, u64p]
     L.jlp_bgzf_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, u64p]
+    L.jlp_pacbio.argtypes = [C.c_void_p, C.c_int, C.POINTER(PacbioParams), C.POINTER(RunStats)]
+    L.jlp_pacbio_to_memory.argtypes = [C.c_void_p, C.c_int, C.POINTER(PacbioParams), C.c_void_p, C.c_uint64, u64p, C.POINTER(RunStats)]
+    L.jlp_pacbio_read_plan.argtypes = [C.c_void_p, C.c_int, C.POINTER(PacbioParams), u64p, u64p, u64p, f64p, f64p]
+    L.jlp_pacbio_sample.argtypes = [C.POINTER(PacbioParams), C.c_uint64, C.c_uint64, u64p, u64p, f64p, f64p]
     L.jlp_reads_per_group.argtypes = [C.c_uint64, f64p, C.c_uint64, C.c_uint64, u64p]
     L.jlp_alias_build.argtypes = [f64p, C.c_uint64, f64p, u64p]
     L.jlp_threshold.argtypes = [C.c_int, C.c_double, u64p, C.POINTER(C.c_int)]

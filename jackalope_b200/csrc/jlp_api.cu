@@ -29,6 +29,7 @@
 #include "jlp_draws.h"
 #include "jlp_host.h"
 #include "jlp_kernels.cuh"
+#include "jlp_pacbio.h"
 
 using namespace jlp;
 
@@ -1095,6 +1096,267 @@ int jlp_illumina_group_counts(jlp_ctx* c, int use_haplotypes, const jlp_illumina
         uint64_t k = 0;
         for (const auto& v : cnt) for (uint64_t x : v) counts[k++] = x;
     });
+}
+
+// ---- PacBio ----
+
+namespace {
+
+void pb_model_from(const jlp_pacbio_params* P, PbModel& m) {
+    if (!P) throw ArgErr("params is NULL");
+    m.scale = P->scale; m.sigma = P->sigma; m.loc = P->loc; m.min_read_len = P->min_read_len;
+    if (P->n_custom) {
+        if (!P->read_probs || !P->read_lens) throw ArgErr("custom read lengths are NULL");
+        m.read_probs.assign(P->read_probs, P->read_probs + P->n_custom);
+        m.read_lens.assign(P->read_lens, P->read_lens + P->n_custom);
+    }
+    m.max_passes = P->max_passes;
+    std::copy(P->chi2_params_n, P->chi2_params_n + 3, m.chi2_n);
+    std::copy(P->chi2_params_s, P->chi2_params_s + 5, m.chi2_s);
+    std::copy(P->sqrt_params, P->sqrt_params + 2, m.sqrt_params);
+    std::copy(P->norm_params, P->norm_params + 2, m.norm_params);
+    m.prob_thresh = P->prob_thresh; m.prob_ins = P->prob_ins; m.prob_del = P->prob_del; m.prob_subst = P->prob_subst;
+    if (!(m.sigma > 0) || !(m.scale > 0) || m.max_passes < 1 || !(m.norm_params[1] > 0)) throw ArgErr("invalid PacBio model parameters");
+    try { pb_prepare(m); } catch (const std::exception& e) { throw ArgErr(e.what()); }
+}
+
+struct PbGroups {
+    std::vector<uint64_t> group_off;      // read-index prefix offsets
+    std::vector<GroupDev> groups;
+    std::vector<uint8_t> strpool;
+    std::vector<Job> jobs;
+};
+
+// reads -> haplotypes -> chromosomes, as for Illumina with one "end" (PacBioOneGenome::add_n_reads, src/hts_pacbio.h)
+PbGroups pb_groups(jlp_ctx* c, bool use_haps, const jlp_pacbio_params* P) {
+    if (c->chrom_off.size() < 2) throw ArgErr("no reference genome has been set");
+    if (use_haps && c->haps.empty()) throw ArgErr("no haplotypes have been added");
+    if (use_haps) finish_upload(c);
+    const uint64_t n_chroms = c->chrom_off.size() - 1, n_haps = c->haps.size();
+    std::vector<uint64_t> sizes;
+    std::vector<std::vector<uint64_t>> counts;
+    if (!use_haps) {
+        for (uint64_t i = 0; i < n_chroms; i++) sizes.push_back(c->chrom_off[i + 1] - c->chrom_off[i]);
+        counts = apportion_sizes(P->seed, P->n_reads, 1, n_chroms, nullptr, sizes.data());
+    } else {
+        if (!P->haplotype_probs) throw ArgErr("haplotype_probs is NULL");
+        for (const HapDev& h : c->haps) sizes.insert(sizes.end(), h.len.begin(), h.len.end());
+        counts = apportion_sizes(P->seed, P->n_reads, n_haps, n_chroms, P->haplotype_probs, sizes.data());
+    }
+    PbGroups G;
+    G.group_off.push_back(0);
+    const std::string prefix = P->out_prefix ? P->out_prefix : "";
+    auto add = [&](const std::string& gname, uint64_t chrom, const uint8_t* seq, uint64_t len, uint64_t count) {
+        GroupDev g;
+        const std::string pre = "@" + gname + "-" + c->chrom_names[chrom] + "-";
+        g.seq = seq; g.len = len;
+        g.prefix_off = (uint32_t)G.strpool.size(); g.prefix_len = (uint32_t)pre.size();
+        G.strpool.insert(G.strpool.end(), pre.begin(), pre.end());
+        g.bc_off = 0; g.bc_len = 0;
+        G.groups.push_back(g);
+        G.group_off.push_back(G.group_off.back() + count);
+        if (count > 0 && len == 0) throw ArgErr("a chromosome of length 0 was given reads");
+    };
+    if (!use_haps) {
+        for (uint64_t i = 0; i < n_chroms; i++) add(c->genome_name, i, c->genome.p + kPad + c->chrom_off[i], sizes[i], counts[0][i]);
+        G.jobs.push_back(Job{0, P->n_reads, prefix});
+    } else {
+        for (uint64_t h = 0; h < n_haps; h++) {
+            const uint64_t lo = G.group_off.back();
+            for (uint64_t i = 0; i < n_chroms; i++) add(c->haps[h].name, i, c->haps[h].seq[i], c->haps[h].len[i], counts[h][i]);
+            if (P->sep_files) G.jobs.push_back(Job{lo, G.group_off.back(), prefix + "_" + c->haps[h].name});
+        }
+        if (!P->sep_files) G.jobs.push_back(Job{0, G.group_off.back(), prefix});
+    }
+    return G;
+}
+
+// First version of the driver: one batch at a time (plan upload, k_pb_plan, scan, k_pb_reads, optional BGZF, copy,
+// write), no overlap between the stages yet.
+void run_pacbio(jlp_ctx* c, bool use_haps, const jlp_pacbio_params* P, int sink_kind, char* mem, uint64_t cap, uint64_t* mem_len,
+                jlp_run_stats* stats) {
+    PbModel model;
+    pb_model_from(P, model);
+    if (!(P->prob_dup == 0)) throw Unsupported("PacBio duplicates (prob_dup > 0) are not built yet");
+    if (P->compress < 0 || P->compress > 9) throw ArgErr("\nInvalid bgzip compress level. It must be in range [0,9].");
+    if (P->compress > 0) {
+        const std::string m = P->comp_method ? P->comp_method : "";
+        if (m != "gzip" && m != "bgzip") throw ArgErr("\nUnrecognized compression method.");
+    }
+    finish_upload(c);
+    const PbGroups G = pb_groups(c, use_haps, P);
+    const bool dev_z = P->compress > 0 && sink_kind == SINK_FILES &&
+                       (P->comp_engine == JLP_COMP_DEVICE || (P->comp_engine == JLP_COMP_AUTO && P->compress <= 6));
+    const int zmethod = P->compress <= 0 || dev_z || sink_kind != SINK_FILES ? -1
+                        : (P->n_threads > 1 || std::string(P->comp_method) == "bgzip") ? DEFLATE_BGZF : DEFLATE_GZIP;
+    DevBuf<GroupDev> d_groups;
+    DevBuf<uint8_t> d_strpool, d_out, d_zslots, d_zout;
+    DevBuf<PbRead> d_reads;
+    DevBuf<uint32_t> d_rec_len, d_rec_local, d_zlen;
+    DevBuf<uint64_t> d_block_tot, d_block_base, d_totals, d_zoff;
+    PinBuf<uint8_t> h_out;
+    d_groups.upload(G.groups, c->s_compute);
+    d_strpool.upload(G.strpool, c->s_compute);
+    d_totals.ensure(4);
+    CK(cudaMemsetAsync(d_totals.p, 0, 4 * sizeof(uint64_t), c->s_compute));
+    const uint64_t B = P->batch_reads ? P->batch_reads : 16384;
+    uint32_t max_prefix = 0;
+    for (const GroupDev& g : G.groups) max_prefix = std::max(max_prefix, g.prefix_len);
+    const uint64_t c_rev = thr_ld_lt(0.5).thr;
+    jlp_run_stats st;
+    std::memset(&st, 0, sizeof st);
+    uint64_t mem_used = 0;
+    std::vector<PbRead> plan;
+    cudaEvent_t ev[3];
+    for (cudaEvent_t& e : ev) CK(cudaEventCreate(&e));
+    for (const Job& job : G.jobs) {
+        int fd = -1;
+        uint64_t fpos = 0;
+        std::string fname;
+        if (sink_kind == SINK_FILES) {
+            fname = job.file_prefix + "_R1.fq" + (P->compress > 0 ? ".gz" : "");        // write_reads_one_filetype_, src/hts.h:344
+            fd = ::open(fname.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+            if (fd < 0) throw IoErr("Unable to open file " + fname + ".\n");
+        }
+        try {
+            for (uint64_t b0 = job.lo; b0 < job.hi; b0 += B) {
+                const uint32_t n = (uint32_t)std::min<uint64_t>(B, job.hi - b0);
+                // ---- per-read quantities on the host
+                plan.resize(n);
+                uint64_t bound = 0;
+                for (uint32_t i = 0; i < n; i++) {
+                    const uint64_t j = b0 + i;
+                    const size_t g = (size_t)(std::upper_bound(G.group_off.begin(), G.group_off.end(), j) - G.group_off.begin()) - 1;
+                    const PbSample smp = pb_sample(model, P->seed, j, G.groups[g].len);
+                    std::memset(&plan[i], 0, sizeof(PbRead));
+                    pb_read_model(model, P->seed, j, smp, plan[i]);
+                    plan[i].group = (uint32_t)g;
+                    bound += max_prefix + 24 + 2 * smp.read_length + 5;
+                }
+                d_reads.ensure(n);
+                d_rec_len.ensure(n); d_rec_local.ensure(n);
+                const uint32_t nsb = (n + kScanBlock - 1) / kScanBlock;
+                d_block_tot.ensure(nsb); d_block_base.ensure(nsb);
+                d_out.ensure(bound + 64);
+                CK(cudaMemcpyAsync(d_reads.p, plan.data(), n * sizeof(PbRead), cudaMemcpyHostToDevice, c->s_compute));
+                st.h2d_bytes += n * sizeof(PbRead);
+                CK(cudaEventRecord(ev[0], c->s_compute));
+                CK(launch_pb_plan(d_reads.p, n, b0, P->seed, d_groups.p, c_rev, d_rec_len.p, c->s_compute));
+                CK(launch_scan(d_rec_len.p, n, 1, d_rec_local.p, d_block_tot.p, d_block_base.p, d_totals.p, c->s_compute));
+                CK(launch_pb_reads(d_reads.p, n, b0, P->seed, d_groups.p, d_strpool.p, d_rec_local.p, d_block_base.p, d_out.p,
+                                   c->s_compute));
+                CK(cudaEventRecord(ev[1], c->s_compute));
+                st.kernel_launches += 4;
+                const uint32_t nblk = (uint32_t)((bound + kBgzfIn - 1) / kBgzfIn) + 1;
+                if (dev_z) {
+                    d_zslots.ensure((size_t)nblk * kBgzfSlot); d_zout.ensure((size_t)nblk * kBgzfSlot);
+                    d_zlen.ensure(2 * nblk); d_zoff.ensure(2 * nblk);
+                    CK(launch_bgzf(d_out.p, d_out.p, d_totals.p, nblk, P->compress >= 4, d_zslots.p, d_zslots.p, d_zlen.p, d_zlen.p + nblk,
+                                   d_zoff.p, d_zoff.p + nblk, d_zout.p, d_zout.p, c->s_compute));
+                    st.kernel_launches += 3;
+                }
+                CK(cudaEventRecord(ev[2], c->s_compute));
+                uint64_t tot[4];
+                CK(cudaMemcpyAsync(tot, d_totals.p, sizeof tot, cudaMemcpyDeviceToHost, c->s_compute));
+                CK(cudaStreamSynchronize(c->s_compute));
+                if (tot[0] > bound) throw std::runtime_error("internal: PacBio batch larger than its bound");
+                float ms = 0;
+                CK(cudaEventElapsedTime(&ms, ev[0], ev[1])); st.reads_ms += ms; st.device_ms += ms;
+                CK(cudaEventElapsedTime(&ms, ev[1], ev[2])); if (dev_z) { st.bgzf_ms += ms; st.device_ms += ms; }
+                st.pairs += n; st.batches++; st.bytes_out[0] += tot[0];
+                if (dev_z) st.z_bytes[0] += tot[2];
+                if (sink_kind == SINK_NONE) continue;
+                const uint64_t nb = dev_z ? tot[2] : tot[0];
+                h_out.ensure(nb + 64);
+                CK(cudaMemcpy(h_out.p, dev_z ? d_zout.p : d_out.p, nb, cudaMemcpyDeviceToHost));
+                st.d2h_bytes += nb;
+                if (sink_kind == SINK_MEMORY) {
+                    if (mem && mem_used + nb <= cap) std::memcpy(mem + mem_used, h_out.p, nb);
+                    mem_used += nb;
+                } else {
+                    const uint8_t* src = h_out.p;
+                    uint64_t len = nb;
+                    std::vector<uint8_t> z;
+                    if (zmethod >= 0) {
+                        const std::string e = deflate_members(zmethod, P->compress, h_out.p, nb, z);
+                        if (!e.empty()) throw IoErr(e);
+                        src = z.data(); len = z.size();
+                    }
+                    const std::string w = pwrite_all(fd, src, len, fpos);
+                    if (!w.empty()) throw IoErr("Error writing to file " + fname + ": " + w);
+                    fpos += len;
+                }
+            }
+            if (fd >= 0 && (dev_z || zmethod == DEFLATE_BGZF)) {
+                const std::string w = pwrite_all(fd, kBgzfEof, sizeof kBgzfEof, fpos);
+                if (!w.empty()) throw IoErr("Error writing to file " + fname + ": " + w);
+            }
+        } catch (...) {
+            if (fd >= 0) ::close(fd);
+            for (cudaEvent_t& e : ev) cudaEventDestroy(e);
+            throw;
+        }
+        if (fd >= 0) ::close(fd);
+    }
+    for (cudaEvent_t& e : ev) cudaEventDestroy(e);
+    if (mem_len) *mem_len = mem_used;
+    if (stats) *stats = st;
+}
+
+}  // namespace
+
+int jlp_pacbio(jlp_ctx* c, int use_haplotypes, const jlp_pacbio_params* p, jlp_run_stats* stats) {
+    if (!c) return JLP_ERR_ARG;
+    return guarded(c, [&]() {
+        if (!p || !p->out_prefix || !*p->out_prefix) throw ArgErr("out_prefix is empty");
+        run_pacbio(c, use_haplotypes != 0, p, SINK_FILES, nullptr, 0, nullptr, stats);
+    });
+}
+
+int jlp_pacbio_to_memory(jlp_ctx* c, int use_haplotypes, const jlp_pacbio_params* p, char* out, uint64_t cap, uint64_t* len,
+                         jlp_run_stats* stats) {
+    if (!c) return JLP_ERR_ARG;
+    return guarded(c, [&]() {
+        uint64_t need = 0;
+        run_pacbio(c, use_haplotypes != 0, p, out ? SINK_MEMORY : SINK_NONE, out, cap, &need, stats);
+        if (len) *len = need;
+        if (out && need > cap) throw ArgErr("output buffer too small");
+    });
+}
+
+int jlp_pacbio_read_plan(jlp_ctx* c, int use_haplotypes, const jlp_pacbio_params* p, uint64_t* group, uint64_t* read_len,
+                         uint64_t* split_pos, double* passes_left, double* passes_right) {
+    if (!c) return JLP_ERR_ARG;
+    return guarded(c, [&]() {
+        PbModel model;
+        pb_model_from(p, model);
+        const PbGroups G = pb_groups(c, use_haplotypes != 0, p);
+        for (uint64_t j = 0; j < p->n_reads; j++) {
+            const size_t g = (size_t)(std::upper_bound(G.group_off.begin(), G.group_off.end(), j) - G.group_off.begin()) - 1;
+            const PbSample s = pb_sample(model, p->seed, j, G.groups[g].len);
+            if (group) group[j] = g;
+            if (read_len) read_len[j] = s.read_length;
+            if (split_pos) split_pos[j] = s.split_pos;
+            if (passes_left) passes_left[j] = s.passes_left;
+            if (passes_right) passes_right[j] = s.passes_right;
+        }
+    });
+}
+
+int jlp_pacbio_sample(const jlp_pacbio_params* p, uint64_t n, uint64_t chrom_len, uint64_t* read_len, uint64_t* split_pos,
+                      double* passes_left, double* passes_right) {
+    try {
+        PbModel model;
+        pb_model_from(p, model);
+        for (uint64_t j = 0; j < n; j++) {
+            const PbSample s = pb_sample(model, p->seed, j, chrom_len);
+            if (read_len) read_len[j] = s.read_length;
+            if (split_pos) split_pos[j] = s.split_pos;
+            if (passes_left) passes_left[j] = s.passes_left;
+            if (passes_right) passes_right[j] = s.passes_right;
+        }
+    } catch (const std::exception& e) { return fail(nullptr, JLP_ERR_ARG, e.what()); }
+    return JLP_OK;
 }
 
 // ---- host-side pieces (no device) ----

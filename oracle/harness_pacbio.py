@@ -23,6 +23,7 @@ class OrcPbJob(C.Structure):
         ("n_groups", C.c_uint64), ("group_off", u64p), ("group_seq", C.POINTER(C.c_char_p)), ("group_len", u64p),
         ("group_genome_name", C.POINTER(C.c_char_p)), ("group_chrom_name", C.POINTER(C.c_char_p)),
         ("read_len", u64p), ("split_pos", u64p), ("passes_left", f64p), ("passes_right", f64p),
+        ("beyond_template_is_n", C.c_int32),
     ]
 
 
@@ -62,7 +63,7 @@ def split_passes(passes, read_length):
 
 
 def generate(names, seqs, genome_name, counts, read_len, split_pos, passes_left, passes_right, seed, want_ledger=True,
-             **model):
+             beyond_template_is_n=False, **model):
     """Oracle output for sum(counts) reads, counts[c] of them from chromosome c in order."""
     m = dict(DEFAULTS)
     m.update(model)
@@ -76,7 +77,7 @@ def generate(names, seqs, genome_name, counts, read_len, split_pos, passes_left,
     J.prob_thresh, J.prob_ins, J.prob_del, J.prob_subst = m["prob_thresh"], m["ins_prob"], m["del_prob"], m["sub_prob"]
     J.n_groups = len(seqs)
     J.group_off = off.ctypes.data_as(u64p)
-    keep = [H._strs([bytes(s) for s in seqs]), H._strs([genome_name] * len(seqs)), H._strs(names)]
+    keep = [H._strs([bytes(s) for s in seqs]), H._strs(genome_name if isinstance(genome_name, (list, tuple)) else [genome_name] * len(seqs)), H._strs(names)]
     J.group_seq, J.group_genome_name, J.group_chrom_name = keep
     lens = _arr([len(s) for s in seqs], np.uint64)
     J.group_len = lens.ctypes.data_as(u64p)
@@ -84,6 +85,7 @@ def generate(names, seqs, genome_name, counts, read_len, split_pos, passes_left,
     pl, pr = _arr(passes_left, np.float64), _arr(passes_right, np.float64)
     J.read_len, J.split_pos = rl.ctypes.data_as(u64p), sp.ctypes.data_as(u64p)
     J.passes_left, J.passes_right = pl.ctypes.data_as(f64p), pr.ctypes.data_as(f64p)
+    J.beyond_template_is_n = int(beyond_template_is_n)
     cap = int(np.sum(np.minimum(rl, lens.max())) * 2 + 200 * n + 64)
     out = C.create_string_buffer(cap)
     ln, led_n = C.c_uint64(), C.c_uint64()

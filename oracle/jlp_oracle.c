@@ -571,7 +571,7 @@ uint64_t orc_unif_expr(int kind, uint64_t x, double p, uint64_t n) {
  *   sub 2 (edit):  the inserted / substituted base drawn at read position p -> block p >> 1, half p & 1 */
 #include "rmath_standin.h"
 
-enum { PL_PB = 4 };
+enum { PL_PB = 6 };   /* planes 4 and 5 address the genome generator */
 
 static uint64_t pb_draw(uint64_t seed, uint64_t j, uint32_t sub, uint32_t block, uint32_t half) {
     uint32_t w[4];
@@ -659,6 +659,11 @@ typedef struct {
     const uint64_t* split_pos;
     const double* passes_left;
     const double* passes_right;
+    /* append_pool can step past the template it copied when a deletion the walk drew could not be recorded (no spare
+     * chromosome left: reads about as long as their chromosome); the reference then reads whatever an earlier read
+     * left in its buffer.  0: the same here (sequential, for the replay against the reference); 1: such a position
+     * reads 'N' (the defined behaviour the CUDA path is compared with). */
+    int32_t beyond_template_is_n;
 } OrcPbJob;
 
 /* Reads [lo, hi) of the job.  plan (optional): [4 * (hi - lo)] group, read_length, read_start, read_chrom_space. */
@@ -781,11 +786,18 @@ int orc_pacbio_generate(const OrcPbJob* J, uint64_t lo, uint64_t hi, char* out, 
             putc_(&S, '-');
             putc_(&S, reverse ? 'R' : 'F');
             putc_(&S, '\n');
-            if (space + 1 > read_cap) { read_cap = space + 1; read = (char*)realloc(read, read_cap); if (!read) { rc = -2; break; } }
+            if (space + read_length + 16 > read_cap) {
+                const uint64_t old = read_cap;
+                read_cap = space + read_length + 16;
+                read = (char*)realloc(read, read_cap);
+                if (!read) { rc = -2; break; }
+                memset(read + old, old ? 0 : 'N', read_cap - old);      /* std::string(1000, 'N'), then resize() appends '\0' */
+            }
             memcpy(read, chrom + read_start, space);
             if (reverse) orc_rev_comp(read, space);
             uint64_t read_pos = 0, current_length = 0, ii = 0, di = 0, si = 0;
             while (current_length < read_length) {
+                if (J->beyond_template_is_n && read_pos >= space) read[read_pos] = 'N';
                 if (ii < n_ins && read_pos == ins[ii]) {
                     const uint64_t xe = pb_draw(J->seed, j, 2, (uint32_t)(read_pos >> 1), (uint32_t)(read_pos & 1));
                     led(&lg, xe);

@@ -1,0 +1,93 @@
+"""PacBio reads on the GPU through the C ABI, byte-compared with the oracle.
+
+The library reports what it drew per read before the per-base work (jlp_pacbio_read_plan: group, read length, pass
+split -- the statistical tier, tests/test_pacbio_samplers.py); those values are injected into the oracle, which the
+unmodified reference replays byte for byte (tests/test_pacbio_oracle.py), and everything after them -- error
+probabilities and qualities, the insertion / deletion / substitution walk, template start, strand, extraction,
+reverse complement, the edits, the FASTQ record -- must then be identical."""
+import gzip
+
+import numpy as np
+import pytest
+
+import jackalope_b200 as J
+from common import first_diff, hap_sequences
+from oracle import harness_pacbio as P
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_for(obj, plan, seed, **model):
+    if isinstance(obj, J.Haplotypes):
+        hs = hap_sequences(obj)
+        seqs = [hs[h][c] for h in range(obj.n_haps()) for c in range(len(obj.reference.names))]
+        names = [n for _ in range(obj.n_haps()) for n in obj.reference.names]
+        gnames = [h for h in obj.hap_names for _ in obj.reference.names]
+    else:
+        seqs, names, gnames = [bytes(s) for s in obj.seqs], list(obj.names), "REF"
+    counts = np.bincount(plan["group"].astype(np.int64), minlength=len(seqs))
+    assert (np.diff(plan["group"].astype(np.int64)) >= 0).all()
+    return P.generate(names, seqs, gnames, counts, plan["read_len"], plan["split_pos"], plan["passes_left"],
+                      plan["passes_right"], seed, want_ledger=False, beyond_template_is_n=True, **model)["fastq"]
+
+
+def check(ctx, obj, n_reads, seed, **kw):
+    fq, st, plan = J.pacbio(obj, "", n_reads, seed=seed, ctx=ctx, sink="memory", want_plan=True, **kw)
+    model = {k: kw[k] for k in ("sqrt_params", "norm_params", "prob_thresh", "ins_prob", "del_prob", "sub_prob") if k in kw}
+    want = oracle_for(obj, plan, seed, **model)
+    d = first_diff(fq, want)
+    assert d is None, "differs at byte %d: gpu=%r oracle=%r" % (d, fq[max(0, d - 60):d + 40], want[max(0, d - 60):d + 40])
+    assert st["pairs"] == n_reads and fq.count(b"\n") == 4 * n_reads
+    return fq, st, plan
+
+
+def genome(seed, n, length, with_n=True):
+    g = J.random_genome(n, length, seed=seed)
+    if with_n:
+        s = g.seqs[0].copy()
+        s[100:160] = ord("N")
+        s[1000] = ord("x")
+        g.seqs[0] = s
+    return g
+
+
+def test_pacbio_ref_defaults(ctx):
+    fq, st, plan = check(ctx, genome(1, 3, 60000), 300, seed=11)
+    assert 3000 < plan["read_len"].mean() < 15000
+
+
+def test_pacbio_several_batches_and_custom_lengths(ctx):
+    g = genome(2, 4, 30000)
+    a, _, _ = check(ctx, g, 500, seed=12, custom_read_lengths=[[200, 1], [1500, 2], [4000, 1]], batch_reads=64)
+    b, _, _ = check(ctx, g, 500, seed=12, custom_read_lengths=[[200, 1], [1500, 2], [4000, 1]])
+    assert a == b                                      # output does not depend on the batch size
+
+
+def test_pacbio_reads_as_long_as_chromosomes(ctx):
+    # reads limited by short chromosomes: no spare template for deletions, read_chrom_space == chrom_len, start 0
+    g = J.RefGenome(["a", "b", "c"], [J.random_genome(1, n, seed=5 + n).seqs[0] for n in (300, 1200, 5000)])
+    check(ctx, g, 400, seed=13, custom_read_lengths=[[250, 1], [1300, 1], [6000, 1]])
+
+
+def test_pacbio_high_error_rates_and_tail_branch(ctx):
+    g = genome(3, 2, 20000)
+    check(ctx, g, 200, seed=14, ins_prob=0.3, del_prob=0.25, sub_prob=0.2, custom_read_lengths=[900, 2500])
+    check(ctx, g, 200, seed=15, norm_params=(-10.0, 0.1), custom_read_lengths=[900, 2500])
+
+
+def test_pacbio_haplotypes_pooled_and_sep_files(ctx, tmp_path):
+    g = genome(4, 3, 40000, with_n=False)
+    haps = J.random_haplotypes(g, 3, sub_rate=0.01, indel_rate=0.002, seed=6)
+    kw = dict(haplotype_probs=[1, 2, 3], custom_read_lengths=[[800, 1], [3000, 1]])
+    fq, _, _ = check(ctx, haps, 300, seed=16, **kw)
+    pre = str(tmp_path / "pb")
+    J.pacbio(haps, pre, 300, seed=16, ctx=ctx, sep_files=True, **kw)
+    assert b"".join(open("%s_%s_R1.fq" % (pre, h), "rb").read() for h in haps.hap_names) == fq
+    J.pacbio(haps, pre + "z", 300, seed=16, ctx=ctx, compress=True, **kw)                # BGZF written by the GPU
+    assert gzip.decompress(open(pre + "z_R1.fq.gz", "rb").read()) == fq
+    J.pacbio(haps, pre + "h", 300, seed=16, ctx=ctx, compress=9, **kw)                   # zlib on the host
+    assert gzip.decompress(open(pre + "h_R1.fq.gz", "rb").read()) == fq
+    with pytest.raises(J.JackalopeError, match="already exists"):
+        J.pacbio(haps, pre, 300, seed=16, ctx=ctx, sep_files=True, **kw)
+    with pytest.raises(RuntimeError, match="not built yet"):
+        J.pacbio(haps, "", 10, seed=1, ctx=ctx, sink="memory", prob_dup=0.1, **kw)
