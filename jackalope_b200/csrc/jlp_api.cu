@@ -1215,7 +1215,7 @@ void run_pacbio(jlp_ctx* c, bool use_haps, const jlp_pacbio_params* P, int sink_
         std::string fname;
         if (sink_kind == SINK_FILES) {
             fname = job.file_prefix + "_R1.fq" + (P->compress > 0 ? ".gz" : "");        // write_reads_one_filetype_, src/hts.h:344
-            fd = ::open(fname.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+            fd = ::open(fname.c_str(), O_RDWR | O_CREAT | O_TRUNC, 0644);
             if (fd < 0) throw IoErr("Unable to open file " + fname + ".\n");
         }
         try {
@@ -1224,14 +1224,26 @@ void run_pacbio(jlp_ctx* c, bool use_haps, const jlp_pacbio_params* P, int sink_
                 // ---- per-read quantities on the host
                 plan.resize(n);
                 uint64_t bound = 0;
-                for (uint32_t i = 0; i < n; i++) {
-                    const uint64_t j = b0 + i;
-                    const size_t g = (size_t)(std::upper_bound(G.group_off.begin(), G.group_off.end(), j) - G.group_off.begin()) - 1;
-                    const PbSample smp = pb_sample(model, P->seed, j, G.groups[g].len);
-                    std::memset(&plan[i], 0, sizeof(PbRead));
-                    pb_read_model(model, P->seed, j, smp, plan[i]);
-                    plan[i].group = (uint32_t)g;
-                    bound += max_prefix + 24 + 2 * smp.read_length + 5;
+                {
+                    // the reads are independent: split over the host threads (n_threads, at most 64)
+                    const uint32_t nt = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(P->n_threads, 1), 64);
+                    std::vector<uint64_t> part(nt, 0);
+                    auto work = [&](uint32_t k) {
+                        for (uint32_t i = k; i < n; i += nt) {
+                            const uint64_t j = b0 + i;
+                            const size_t g = (size_t)(std::upper_bound(G.group_off.begin(), G.group_off.end(), j) - G.group_off.begin()) - 1;
+                            const PbSample smp = pb_sample(model, P->seed, j, G.groups[g].len);
+                            std::memset(&plan[i], 0, sizeof(PbRead));
+                            pb_read_model(model, P->seed, j, smp, plan[i]);
+                            plan[i].group = (uint32_t)g;
+                            part[k] += max_prefix + 24 + 2 * smp.read_length + 5;
+                        }
+                    };
+                    std::vector<std::thread> th;
+                    for (uint32_t k = 1; k < nt; k++) th.emplace_back(work, k);
+                    work(0);
+                    for (std::thread& t : th) t.join();
+                    for (uint64_t v : part) bound += v;
                 }
                 d_reads.ensure(n);
                 d_rec_len.ensure(n); d_rec_local.ensure(n);
@@ -1282,8 +1294,28 @@ void run_pacbio(jlp_ctx* c, bool use_haps, const jlp_pacbio_params* P, int sink_
                         if (!e.empty()) throw IoErr(e);
                         src = z.data(); len = z.size();
                     }
-                    const std::string w = pwrite_all(fd, src, len, fpos);
-                    if (!w.empty()) throw IoErr("Error writing to file " + fname + ": " + w);
+                    // several writer threads: the file is extended and the batch copied into a mapping of the new range
+                    // in parallel (see Mapping); otherwise one pwrite
+                    Mapping map;
+                    struct statvfs vfs;
+                    if (P->n_threads > 1 && len > (8u << 20) && ::fstatvfs(fd, &vfs) == 0 &&
+                        (uint64_t)vfs.f_bavail * vfs.f_frsize > 2 * len + (64ull << 20) && ::ftruncate(fd, (off_t)(fpos + len)) == 0 &&
+                        map_range(fd, fpos, len, map)) {
+                        c->writers.start((size_t)std::min<uint64_t>(P->n_threads, 64));
+                        std::atomic<int> pending{0};
+                        const uint64_t slice = 8ull << 20;
+                        for (uint64_t o = 0; o < len; o += slice) {
+                            uint8_t* dst = map.at + o;
+                            const uint8_t* from = src + o;
+                            const uint64_t nb2 = std::min(slice, len - o);
+                            c->writers.submit(&pending, [dst, from, nb2]() { std::memcpy(dst, from, nb2); return std::string(); });
+                        }
+                        c->writers.wait(pending);
+                        map.unmap();
+                    } else {
+                        const std::string w = pwrite_all(fd, src, len, fpos);
+                        if (!w.empty()) throw IoErr("Error writing to file " + fname + ": " + w);
+                    }
                     fpos += len;
                 }
             }

@@ -1,6 +1,7 @@
 // Host side of the PacBio read generator: see jlp_pacbio.h.
 #include "jlp_pacbio.h"
 
+#include <atomic>
 #include <cmath>
 #include <stdexcept>
 
@@ -48,12 +49,28 @@ double qnorm(double p) {
     return x;
 }
 
+// The same quantile for the samplers of this file (statistical tier: any accurate quantile will do): Abramowitz and
+// Stegun 26.2.23 as the starting point, four Newton steps on pnorm.
+double qnorm_fast(double p) {
+    if (!(p > 0.0)) return -INFINITY;
+    if (!(p < 1.0)) return INFINITY;
+    if (p > 0.5) return -qnorm_fast(1.0 - p);
+    const double t = std::sqrt(-2.0 * std::log(p));
+    double x = -(t - (2.515517 + 0.802853 * t + 0.010328 * t * t) / (1.0 + 1.432788 * t + 0.189269 * t * t + 0.001308 * t * t * t));
+    for (int i = 0; i < 4; i++) {
+        const double d = 0.39894228040143267794 * std::exp(-0.5 * x * x);
+        if (!(d > 1e-300)) break;
+        x -= (pnorm(x) - p) / d;
+    }
+    return x;
+}
+
 // quantile of the chi-squared distribution (R::qchisq, src/hts_pacbio.h:178) by bisection on gamma_p
 double qchisq(double p, double df) {
     const long double a = 0.5L * df;
     double lo = 0.0, hi = df + 10.0 * std::sqrt(2.0 * df) + 50.0;
     while ((double)gamma_p(a, 0.5L * hi) < p) hi *= 2.0;
-    for (int i = 0; i < 100; i++) {
+    for (int i = 0; i < 60; i++) {
         const double mid = 0.5 * (lo + hi);
         if ((double)gamma_p(a, 0.5L * mid) < p) lo = mid; else hi = mid;
     }
@@ -80,7 +97,7 @@ double sample_gamma(double a, SampleStream& S) {
     if (a < 1.0) return sample_gamma(a + 1.0, S) * std::pow(S.next(), 1.0 / a);
     const double d = a - 1.0 / 3.0, c = 1.0 / std::sqrt(9.0 * d);
     for (;;) {
-        const double z = qnorm(S.next());
+        const double z = qnorm_fast(S.next());
         const double v0 = 1.0 + c * z;
         if (v0 <= 0) continue;
         const double v = v0 * v0 * v0, u = S.next();
@@ -113,7 +130,9 @@ void pb_prepare(PbModel& m) {
         else { right = mid; min_exp = (left + mid) / 2; }
     }
     m.min_exp = min_exp;
-    m.qchisq_cache.assign((size_t)std::max(1.0, std::floor(m.chi2_n[2])) + 2, -1.0);
+    m.qchisq_n = (size_t)std::max(1.0, std::floor(m.chi2_n[2])) + 2;
+    m.qchisq_cache.reset(new std::atomic<double>[m.qchisq_n]);
+    for (size_t i = 0; i < m.qchisq_n; i++) m.qchisq_cache[i].store(-1.0, std::memory_order_relaxed);
     if (!m.read_probs.empty()) {
         m.len_prob.resize(m.read_probs.size());
         m.len_alias.resize(m.read_probs.size());
@@ -129,8 +148,8 @@ PbSample pb_sample(const PbModel& m, uint64_t seed, uint64_t j, uint64_t chrom_l
         const double mu = std::log(m.scale);
         double min_len = std::ceil(m.min_read_len);
         if (min_len < 1) min_len = 1;
-        double rnd = std::exp(mu + m.sigma * qnorm(S.next())) + m.loc;
-        for (int it = 0; rnd < min_len && it < 10; it++) rnd = std::exp(mu + m.sigma * qnorm(S.next())) + m.loc;
+        double rnd = std::exp(mu + m.sigma * qnorm_fast(S.next())) + m.loc;
+        for (int it = 0; rnd < min_len && it < 10; it++) rnd = std::exp(mu + m.sigma * qnorm_fast(S.next())) + m.loc;
         if (rnd < min_len) rnd = min_len;
         r.read_length = (uint64_t)rnd;
     } else {
@@ -153,8 +172,11 @@ PbSample pb_sample(const PbModel& m, uint64_t seed, uint64_t j, uint64_t chrom_l
     } else {
         s = m.chi2_s[3] / std::pow(read_length, m.chi2_s[4]);
     }
-    double& thr = const_cast<PbModel&>(m).qchisq_cache[(size_t)std::floor(lcap)];      // a pure function of lcap (an integer)
-    if (thr < 0) thr = qchisq(0.9925, n);
+    // the outlier threshold is a pure function of lcap (an integer): filled on first use; concurrent callers may compute
+    // the same value twice
+    std::atomic<double>& slot = m.qchisq_cache[(size_t)std::floor(lcap)];
+    double thr = slot.load(std::memory_order_relaxed);
+    if (thr < 0) { thr = qchisq(0.9925, n); slot.store(thr, std::memory_order_relaxed); }
     double passes = 2.0 * sample_gamma(0.5 * n, S);
     while (passes > thr) passes = 2.0 * sample_gamma(0.5 * n, S);
     passes *= s;

@@ -7,7 +7,9 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
+#include <memory>
 #include <vector>
 
 #include "jlp_kernels.cuh"
@@ -25,7 +27,8 @@ struct PbModel {
     double norm_params[2] = {0, 0.2};
     double prob_thresh = 0.2, prob_ins = 0.11, prob_del = 0.04, prob_subst = 0.01;
     double min_exp = 0;                       // calc_min_exp(), set by pb_prepare
-    std::vector<double> qchisq_cache;         // outlier threshold per min(read_length, chi2_n[2])
+    mutable std::unique_ptr<std::atomic<double>[]> qchisq_cache;   // outlier threshold per min(read_length, chi2_n[2]), filled on first use
+    size_t qchisq_n = 0;
     std::vector<double> len_prob;             // alias tables of the custom read lengths
     std::vector<uint64_t> len_alias;
 };
