@@ -1249,7 +1249,7 @@ void run_pacbio(jlp_ctx* c, bool use_haps, const jlp_pacbio_params* P, int sink_
                 d_rec_len.ensure(n); d_rec_local.ensure(n);
                 const uint32_t nsb = (n + kScanBlock - 1) / kScanBlock;
                 d_block_tot.ensure(nsb); d_block_base.ensure(nsb);
-                d_out.ensure(bound + 64);
+                if (bound + 64 > d_out.n) d_out.ensure(bound + bound / 4 + 64);       // batches differ in size: grow with slack
                 CK(cudaMemcpyAsync(d_reads.p, plan.data(), n * sizeof(PbRead), cudaMemcpyHostToDevice, c->s_compute));
                 st.h2d_bytes += n * sizeof(PbRead);
                 CK(cudaEventRecord(ev[0], c->s_compute));
@@ -1279,7 +1279,7 @@ void run_pacbio(jlp_ctx* c, bool use_haps, const jlp_pacbio_params* P, int sink_
                 if (dev_z) st.z_bytes[0] += tot[2];
                 if (sink_kind == SINK_NONE) continue;
                 const uint64_t nb = dev_z ? tot[2] : tot[0];
-                h_out.ensure(nb + 64);
+                if (nb + 64 > h_out.n) h_out.ensure(nb + nb / 4 + 64);
                 CK(cudaMemcpy(h_out.p, dev_z ? d_zout.p : d_out.p, nb, cudaMemcpyDeviceToHost));
                 st.d2h_bytes += nb;
                 if (sink_kind == SINK_MEMORY) {

@@ -1,10 +1,10 @@
-// PacBio read generator, device side.  First version: one thread per read, the
-// reference's loops restated literally (PacBioQualityError::sample's walk, src/hts_pacbio.h:296-318;
-// PacBioOneGenome::append_pool, src/hts_pacbio.cpp), every draw addressed by (seed, read index, position), so a read
-// does not depend on batch size, thread mapping or GPU count.
-//   k_pb_plan   walks the template once to count insertions and deletions -> read_chrom_space, read_start, strand,
-//               record length
-//   k_pb_reads  walks it again and writes the FASTQ record
+// PacBio read generator, device side: PacBioQualityError::sample's walk
+// (src/hts_pacbio.h:296-318) and PacBioOneGenome::append_pool (src/hts_pacbio.cpp), every draw addressed by
+// (seed, read index, position), so a read does not depend on batch size, thread mapping or GPU count.  One warp per
+// read, one kernel template in two roles:
+//   k_pb_warp<false>  walks the template once to count insertions and deletions -> read_chrom_space, read_start,
+//                     strand, record length
+//   k_pb_warp<true>   walks it again and writes the FASTQ record
 #include "jlp_pacbio.h"
 
 #include "jlp_draws.h"
@@ -69,126 +69,178 @@ struct WalkDraws {
     }
 };
 
-__global__ void __launch_bounds__(128)
-k_pb_plan(PbRead* __restrict__ reads, uint32_t n, uint64_t first_read, uint64_t seed, const GroupDev* __restrict__ groups,
-          uint64_t c_rev, uint32_t* __restrict__ rec_len) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    PbRead R = reads[i];
-    const uint64_t j = first_read + i;
-    const GroupDev G = groups[R.group];
-    const uint64_t chrom_len = G.len;
-    const uint32_t read_length = R.read_length;
-    // ---- PacBioQualityError::sample: the counts, and how many bases append_pool will emit
-    uint32_t chrom_pos = 0, n_ins = 0, n_del = 0, seq_len = 0;
-    Walk W;
-    W.extra_space = chrom_len - read_length;
-    WalkDraws D{seed, j};
-    while (W.len < read_length) {
-        const uint32_t rec = W.step(R, D.at(chrom_pos));
-        n_ins += rec == 1;
-        n_del += rec == 2;
-        if (seq_len < read_length) seq_len += pb_emitted(rec);
-        chrom_pos++;
-    }
-    // ---- read_chrom_space, read_start (one_read, src/hts_pacbio.cpp), strand (append_pool)
-    const uint32_t space = read_length + n_del - n_ins;
-    const U4 w = draw_block(seed, j, 1, PL_PB, 0);
-    uint64_t start = 0;
-    if (space < chrom_len) {
-        // double u = runif_01(eng); read_start = u * (chrom_len - read_chrom_space + 1)
-        const uint64_t xs = lo64(w);
-        const double u = (xs == ~0ull) ? 1.0 : __ull2double_rn(xs + 1) * 5.421010862427522170037e-20;
-        start = __double2ull_rz(__dmul_rn(u, __ull2double_rn(chrom_len - space + 1)));
-    }
-    const bool reverse = hi64(w) < c_rev;
-    uint32_t nd = 1;
-    for (uint64_t v = start; v >= 10; v /= 10) nd++;
-    R.seg = G.seq + start;
-    R.space = space;
-    R.start = start;
-    R.reverse = reverse ? 1u : 0u;
-    R.rec_len = G.prefix_len + nd + 3u + seq_len + read_length + 4u;   // "@<genome>-<chrom>-" start "-F\n" | read '\n' '+' '\n' qual '\n'
-    reads[i] = R;
-    rec_len[i] = R.rec_len;
-}
-
 // cmp_map (src/str_manip.h:58-72): A<->T, C<->G, N->N, anything else -> 0
 __device__ __forceinline__ uint8_t pb_complement(uint8_t c) {
     return c == 'A' ? 'T' : c == 'T' ? 'A' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'N' ? 'N' : 0;
 }
 
-__global__ void __launch_bounds__(128)
-k_pb_reads(const PbRead* __restrict__ reads, uint32_t n, uint64_t first_read, uint64_t seed, const GroupDev* __restrict__ groups,
-           const uint8_t* __restrict__ strpool, const uint32_t* __restrict__ rec_local, const uint64_t* __restrict__ block_base,
-           uint8_t* __restrict__ out) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+// ---- one warp per read ---------------------------------------------------------------------------------------
+// The template is walked 64 positions at a time, two per lane (one Philox block).  Away from the three places where
+// the walk's rules couple neighbouring positions -- the switch from the left to the right error probabilities at
+// split_pos, the end of the read (an insertion needs room for two bases, the loop stops), and a chromosome with no
+// spare bases left for deletions -- every position's event is a function of its own draw, and a warp prefix sum of
+// the emitted bases places them.  A chunk that may touch one of those places is walked by lane 0 with the serial code
+// above; a read whose emitted count has ever run ahead of the walk's (an unrecordable deletion) stays there.
+template <bool EMIT>
+__global__ void __launch_bounds__(256)
+k_pb_warp(PbRead* __restrict__ reads, uint32_t n, uint64_t first_read, uint64_t seed, const GroupDev* __restrict__ groups,
+          uint64_t c_rev, uint32_t* __restrict__ rec_len, const uint8_t* __restrict__ strpool,
+          const uint32_t* __restrict__ rec_local, const uint64_t* __restrict__ block_base, uint8_t* __restrict__ out) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= n) return;
-    const PbRead R = reads[i];
+    PbRead R = reads[i];
     const uint64_t j = first_read + i;
     const GroupDev G = groups[R.group];
-    uint8_t* o = out + block_base[i / kScanBlock] + rec_local[i];
-    // ---- ID line
-    {
-        const uint8_t* pre = strpool + G.prefix_off;
-        for (uint32_t t = 0; t < G.prefix_len; t++) *o++ = pre[t];
-        uint8_t dg[20];
-        uint32_t nd = 0;
-        uint64_t v = R.start;
-        do { dg[nd++] = (uint8_t)('0' + (uint32_t)(v % 10)); v /= 10; } while (v);
-        for (uint32_t t = 0; t < nd; t++) *o++ = dg[nd - 1u - t];
-        *o++ = '-'; *o++ = R.reverse ? 'R' : 'F'; *o++ = '\n';
-    }
-    // ---- the walk again, this time with the bases; append_pool stops when IT has emitted read_length bases
-    const uint32_t read_length = R.read_length;
-    uint32_t emitted = 0, pos = 0;
-    Walk W;
-    W.extra_space = G.len - read_length;
-    WalkDraws D{seed, j};
-    while (emitted < read_length) {
-        const uint32_t rec = W.step(R, D.at(pos));
-        // the template base at this position: fill_read + rev_comp over read_chrom_space bases
-        // (append_pool can step past the template when a deletion the walk drew could not be recorded; the reference
-        //  then reads what an earlier read left in its buffer -- here such a position is an 'N')
-        const uint8_t base = pos >= R.space ? (uint8_t)'N' : R.reverse ? pb_complement(R.seg[R.space - 1u - pos]) : R.seg[pos];
-        if (rec == 1) {
-            const uint64_t xe = pb_draw(seed, j, 2, pos >> 1, pos & 1u);
-            *o++ = base;
-            const uint32_t r4 = ins_base_index(xe);
-            *o++ = r4 == 0 ? 'T' : r4 == 1 ? 'C' : r4 == 2 ? 'A' : r4 == 3 ? 'G' : 0;
-        } else if (rec == 3) {
-            const uint64_t xe = pb_draw(seed, j, 2, pos >> 1, pos & 1u);
-            uint64_t r3 = mul_floor_x87(xe, 3);
-            if (r3 > 2) r3 = 2;
-            // mm_nucleos[nt_map[base]][r3] (src/hts.h:36-46): the r3-th of T, C, A, G other than the base; NNN otherwise
-            const uint32_t code = base == 'T' ? 0u : base == 'C' ? 1u : base == 'A' ? 2u : base == 'G' ? 3u : 4u;
-            uint8_t sub = 'N';
-            if (code < 4u) { const uint32_t k = (uint32_t)r3 + ((uint32_t)r3 >= code ? 1u : 0u); sub = k == 0 ? 'T' : k == 1 ? 'C' : k == 2 ? 'A' : 'G'; }
-            *o++ = sub;
-        } else if (rec == 0) {
-            *o++ = base;
+    const uint32_t RL = R.read_length;
+    uint8_t* o = nullptr;
+    if (EMIT) {
+        o = out + block_base[i / kScanBlock] + rec_local[i];
+        const uint32_t idlen = R.rec_len - (RL + 4u) - (R.pad /* seq_len, kept by the plan */);
+        if (lane == 0) {
+            uint8_t* q = o;
+            const uint8_t* pre = strpool + G.prefix_off;
+            for (uint32_t t = 0; t < G.prefix_len; t++) *q++ = pre[t];
+            uint8_t dg[20];
+            uint32_t nd = 0;
+            uint64_t v = R.start;
+            do { dg[nd++] = (uint8_t)('0' + (uint32_t)(v % 10)); v /= 10; } while (v);
+            for (uint32_t t = 0; t < nd; t++) *q++ = dg[nd - 1u - t];
+            *q++ = '-'; *q++ = R.reverse ? 'R' : 'F'; *q++ = '\n';
         }
-        emitted += pb_emitted(rec);
-        pos++;
+        o += idlen;
     }
-    *o++ = '\n'; *o++ = '+'; *o++ = '\n';
-    const uint8_t ql = (uint8_t)(R.flags >> 8), qr = (uint8_t)(R.flags >> 16);
-    for (uint32_t t = 0; t < read_length; t++) *o++ = t < R.split_pos ? ql : qr;
-    *o++ = '\n';
+    Walk W;
+    W.extra_space = G.len - RL;
+    uint32_t emitted = 0, pos = 0, n_ins = 0, n_del = 0;        // emitted: append_pool's count (capped bookkeeping in the plan)
+    for (;;) {
+        if (EMIT ? emitted >= RL : W.len >= RL) break;
+        if (W.side == 0 && W.len == R.split_pos) W.side = 1;
+        const bool fast = emitted == W.len && (W.side == 1 || W.len + 130u < R.split_pos) && W.len + 130u < RL && W.extra_space >= 64;
+        if (fast) {
+            const U4 w = draw_block(seed, j, (pos >> 1) + lane, PL_PB, 1);
+            const uint32_t ev0 = pb_event(R, W.side, lo64(w)), ev1 = pb_event(R, W.side, hi64(w));
+            const uint32_t e0 = pb_emitted(ev0), e1 = pb_emitted(ev1);
+            uint32_t incl = e0 + e1;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += x; }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            const uint32_t ins = __popc(__ballot_sync(0xffffffffu, ev0 == 1)) + __popc(__ballot_sync(0xffffffffu, ev1 == 1));
+            const uint32_t del = __popc(__ballot_sync(0xffffffffu, ev0 == 2)) + __popc(__ballot_sync(0xffffffffu, ev1 == 2));
+            if (EMIT) {
+                uint8_t* q = o + emitted + (incl - e0 - e1);
+#pragma unroll
+                for (uint32_t h = 0; h < 2; h++) {
+                    const uint32_t ev = h ? ev1 : ev0, p = pos + 2u * lane + h;
+                    if (ev == 2) continue;
+                    const uint8_t base = R.reverse ? pb_complement(R.seg[R.space - 1u - p]) : R.seg[p];
+                    if (ev == 0) *q++ = base;
+                    else {
+                        const uint64_t xe = pb_draw(seed, j, 2, p >> 1, p & 1u);
+                        if (ev == 1) {
+                            *q++ = base;
+                            const uint32_t r4 = ins_base_index(xe);
+                            *q++ = r4 == 0 ? 'T' : r4 == 1 ? 'C' : r4 == 2 ? 'A' : r4 == 3 ? 'G' : 0;
+                        } else {
+                            uint64_t r3 = mul_floor_x87(xe, 3);
+                            if (r3 > 2) r3 = 2;
+                            const uint32_t code = base == 'T' ? 0u : base == 'C' ? 1u : base == 'A' ? 2u : base == 'G' ? 3u : 4u;
+                            uint8_t sub = 'N';
+                            if (code < 4u) { const uint32_t k = (uint32_t)r3 + ((uint32_t)r3 >= code ? 1u : 0u); sub = k == 0 ? 'T' : k == 1 ? 'C' : k == 2 ? 'A' : 'G'; }
+                            *q++ = sub;
+                        }
+                    }
+                }
+            }
+            W.len += total; emitted += total;
+            W.extra_space += ins; W.extra_space -= del;
+            n_ins += ins; n_del += del;
+            pos += 64;
+        } else {
+            // serial: lane 0 walks to the next multiple of 64 positions (or to the end of the read)
+            if (lane == 0) {
+                WalkDraws D{seed, j};
+                const uint32_t stop = (pos & ~63u) + 64u;
+                while (pos < stop && (EMIT ? emitted < RL : W.len < RL)) {
+                    const uint32_t rec = W.step(R, D.at(pos));
+                    n_ins += rec == 1; n_del += rec == 2;
+                    if (EMIT) {
+                        const uint8_t base = pos >= R.space ? (uint8_t)'N' : R.reverse ? pb_complement(R.seg[R.space - 1u - pos]) : R.seg[pos];
+                        uint8_t* q = o + emitted;
+                        if (rec == 1) {
+                            const uint64_t xe = pb_draw(seed, j, 2, pos >> 1, pos & 1u);
+                            *q++ = base;
+                            const uint32_t r4 = ins_base_index(xe);
+                            *q++ = r4 == 0 ? 'T' : r4 == 1 ? 'C' : r4 == 2 ? 'A' : r4 == 3 ? 'G' : 0;
+                        } else if (rec == 3) {
+                            const uint64_t xe = pb_draw(seed, j, 2, pos >> 1, pos & 1u);
+                            uint64_t r3 = mul_floor_x87(xe, 3);
+                            if (r3 > 2) r3 = 2;
+                            const uint32_t code = base == 'T' ? 0u : base == 'C' ? 1u : base == 'A' ? 2u : base == 'G' ? 3u : 4u;
+                            uint8_t sub = 'N';
+                            if (code < 4u) { const uint32_t k = (uint32_t)r3 + ((uint32_t)r3 >= code ? 1u : 0u); sub = k == 0 ? 'T' : k == 1 ? 'C' : k == 2 ? 'A' : 'G'; }
+                            *q++ = sub;
+                        } else if (rec == 0) {
+                            *q++ = base;
+                        }
+                        emitted += pb_emitted(rec);
+                    } else if (emitted < RL) {
+                        emitted += pb_emitted(rec);
+                    }
+                    pos++;
+                }
+            }
+            W.len = __shfl_sync(0xffffffffu, W.len, 0);
+            W.side = __shfl_sync(0xffffffffu, W.side, 0);
+            W.extra_space = __shfl_sync(0xffffffffu, W.extra_space, 0);
+            emitted = __shfl_sync(0xffffffffu, emitted, 0);
+            pos = __shfl_sync(0xffffffffu, pos, 0);
+            n_ins = __shfl_sync(0xffffffffu, n_ins, 0);
+            n_del = __shfl_sync(0xffffffffu, n_del, 0);
+        }
+    }
+    if (!EMIT) {
+        if (lane == 0) {
+            // ---- read_chrom_space, read_start (one_read, src/hts_pacbio.cpp), strand (append_pool)
+            const uint32_t space = RL + n_del - n_ins;
+            const U4 w = draw_block(seed, j, 1, PL_PB, 0);
+            uint64_t start = 0;
+            if (space < G.len) {
+                const uint64_t xs = lo64(w);
+                const double u = (xs == ~0ull) ? 1.0 : __ull2double_rn(xs + 1) * 5.421010862427522170037e-20;
+                start = __double2ull_rz(__dmul_rn(u, __ull2double_rn(G.len - space + 1)));
+            }
+            uint32_t nd = 1;
+            for (uint64_t v = start; v >= 10; v /= 10) nd++;
+            R.seg = G.seq + start;
+            R.space = space;
+            R.start = start;
+            R.reverse = hi64(w) < c_rev ? 1u : 0u;
+            R.pad = emitted;                                                   // bases of the sequence line (read_length, or one more)
+            R.rec_len = G.prefix_len + nd + 3u + emitted + RL + 4u;
+            reads[i] = R;
+            rec_len[i] = R.rec_len;
+        }
+    } else {
+        uint8_t* q = o + emitted;
+        if (lane == 0) { q[0] = '\n'; q[1] = '+'; q[2] = '\n'; q[3 + RL] = '\n'; }
+        const uint8_t ql = (uint8_t)(R.flags >> 8), qr = (uint8_t)(R.flags >> 16);
+        for (uint32_t t = lane; t < RL; t += 32) q[3 + t] = t < R.split_pos ? ql : qr;
+    }
 }
 
 }  // namespace
 
 cudaError_t launch_pb_plan(PbRead* reads, uint32_t n, uint64_t first_read, uint64_t seed, const GroupDev* groups,
                            uint64_t c_rev, uint32_t* rec_len, cudaStream_t s) {
-    if (n) k_pb_plan<<<(n + 127) / 128, 128, 0, s>>>(reads, n, first_read, seed, groups, c_rev, rec_len);
+    if (n) k_pb_warp<false><<<(n + 7) / 8, 256, 0, s>>>(reads, n, first_read, seed, groups, c_rev, rec_len, nullptr, nullptr, nullptr, nullptr);
     return cudaGetLastError();
 }
 
 cudaError_t launch_pb_reads(const PbRead* reads, uint32_t n, uint64_t first_read, uint64_t seed, const GroupDev* groups,
                             const uint8_t* strpool, const uint32_t* rec_local, const uint64_t* block_base, uint8_t* out,
                             cudaStream_t s) {
-    if (n) k_pb_reads<<<(n + 127) / 128, 128, 0, s>>>(reads, n, first_read, seed, groups, strpool, rec_local, block_base, out);
+    if (n) k_pb_warp<true><<<(n + 7) / 8, 256, 0, s>>>(const_cast<PbRead*>(reads), n, first_read, seed, groups, 0, nullptr, strpool, rec_local, block_base, out);
     return cudaGetLastError();
 }
 

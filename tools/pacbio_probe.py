@@ -31,6 +31,8 @@ out = {"workload": "10 x 10 Mb genome, pacbio() defaults", "reads": n, "bases": 
                   "host_threads": threads}}
 d = tempfile.mkdtemp(dir="/dev/shm")
 try:
+    J.pacbio(g, os.path.join(d, "w"), 1 << 15, seed=1, ctx=ctx, n_threads=threads, overwrite=True)      # buffers
+    J.pacbio(g, os.path.join(d, "w"), 1 << 15, seed=1, ctx=ctx, n_threads=threads, compress=True, overwrite=True)
     t0 = time.perf_counter()
     J.pacbio(g, os.path.join(d, "p"), n, seed=2, ctx=ctx, n_threads=threads)
     t_f = time.perf_counter() - t0
