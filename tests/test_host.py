@@ -359,14 +359,15 @@ def test_oracle_pair_geometry_known_answers():
 
 
 def test_rcpp_glue_type_checks_against_the_reference_headers():
-    """integration/hts_illumina_b200.cpp cannot be built without R, but it must at least compile
+    """integration/hts_illumina_b200.cpp and hts_pacbio_b200.cpp cannot be built without R, but they must at least compile
     (syntax only) against jackalope's own ref_classes.h / hap_classes.h with the stub Rcpp headers."""
     import shutil
     import subprocess
     if not os.path.isdir(REF) or shutil.which("g++") is None:
         pytest.skip("/root/reference or g++ absent")
-    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-w", "-I" + os.path.join(ROOT, "oracle", "stubs"),
-                        "-I" + os.path.join(REF, "inst", "include"), "-I" + os.path.join(REF, "src"),
-                        "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "integration", "hts_illumina_b200.cpp")],
-                       capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr[:2000]
+    for glue in ("hts_illumina_b200.cpp", "hts_pacbio_b200.cpp"):
+        r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-w", "-I" + os.path.join(ROOT, "oracle", "stubs"),
+                            "-I" + os.path.join(REF, "inst", "include"), "-I" + os.path.join(REF, "src"),
+                            "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "integration"),
+                            os.path.join(ROOT, "integration", glue)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[:2000]
