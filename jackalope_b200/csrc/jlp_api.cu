@@ -1194,7 +1194,14 @@ void run_pacbio(jlp_ctx* c, bool use_haps, const jlp_pacbio_params* P, int sink_
     DevBuf<PbRead> d_reads;
     DevBuf<uint32_t> d_rec_len, d_rec_local, d_zlen;
     DevBuf<uint64_t> d_block_tot, d_block_base, d_totals, d_zoff;
-    PinBuf<uint8_t> h_out;
+    // two host buffers: the writer threads copy batch k into the file while batch k + 1 is prepared, generated and copied
+    PinBuf<uint8_t> h_buf[2];
+    Mapping h_map[2];
+    std::atomic<int> h_pending[2];
+    h_pending[0] = 0; h_pending[1] = 0;
+    uint64_t n_batch = 0;
+    auto settle = [&](int k) { c->writers.wait(h_pending[k]); h_map[k].unmap(); };
+    struct Settle { decltype(settle)& f; ~Settle() { f(0); f(1); } } settle_all{settle};       // also on error paths, before fd closes
     d_groups.upload(G.groups, c->s_compute);
     d_strpool.upload(G.strpool, c->s_compute);
     d_totals.ensure(4);
@@ -1279,6 +1286,9 @@ void run_pacbio(jlp_ctx* c, bool use_haps, const jlp_pacbio_params* P, int sink_
                 if (dev_z) st.z_bytes[0] += tot[2];
                 if (sink_kind == SINK_NONE) continue;
                 const uint64_t nb = dev_z ? tot[2] : tot[0];
+                const int hk = (int)(n_batch++ & 1);
+                settle(hk);                                     // the slices of the batch before last are in the file
+                PinBuf<uint8_t>& h_out = h_buf[hk];
                 if (nb + 64 > h_out.n) h_out.ensure(nb + nb / 4 + 64);
                 CK(cudaMemcpy(h_out.p, dev_z ? d_zout.p : d_out.p, nb, cudaMemcpyDeviceToHost));
                 st.d2h_bytes += nb;
@@ -1295,23 +1305,19 @@ void run_pacbio(jlp_ctx* c, bool use_haps, const jlp_pacbio_params* P, int sink_
                         src = z.data(); len = z.size();
                     }
                     // several writer threads: the file is extended and the batch copied into a mapping of the new range
-                    // in parallel (see Mapping); otherwise one pwrite
-                    Mapping map;
+                    // in parallel (see Mapping) while the next batch is on its way; otherwise one pwrite
                     struct statvfs vfs;
-                    if (P->n_threads > 1 && len > (8u << 20) && ::fstatvfs(fd, &vfs) == 0 &&
+                    if (zmethod < 0 && P->n_threads > 1 && len > (8u << 20) && ::fstatvfs(fd, &vfs) == 0 &&
                         (uint64_t)vfs.f_bavail * vfs.f_frsize > 2 * len + (64ull << 20) && ::ftruncate(fd, (off_t)(fpos + len)) == 0 &&
-                        map_range(fd, fpos, len, map)) {
+                        map_range(fd, fpos, len, h_map[hk])) {
                         c->writers.start((size_t)std::min<uint64_t>(P->n_threads, 64));
-                        std::atomic<int> pending{0};
                         const uint64_t slice = 8ull << 20;
                         for (uint64_t o = 0; o < len; o += slice) {
-                            uint8_t* dst = map.at + o;
+                            uint8_t* dst = h_map[hk].at + o;
                             const uint8_t* from = src + o;
                             const uint64_t nb2 = std::min(slice, len - o);
-                            c->writers.submit(&pending, [dst, from, nb2]() { std::memcpy(dst, from, nb2); return std::string(); });
+                            c->writers.submit(&h_pending[hk], [dst, from, nb2]() { std::memcpy(dst, from, nb2); return std::string(); });
                         }
-                        c->writers.wait(pending);
-                        map.unmap();
                     } else {
                         const std::string w = pwrite_all(fd, src, len, fpos);
                         if (!w.empty()) throw IoErr("Error writing to file " + fname + ": " + w);
@@ -1319,11 +1325,13 @@ void run_pacbio(jlp_ctx* c, bool use_haps, const jlp_pacbio_params* P, int sink_
                     fpos += len;
                 }
             }
+            settle(0); settle(1);
             if (fd >= 0 && (dev_z || zmethod == DEFLATE_BGZF)) {
                 const std::string w = pwrite_all(fd, kBgzfEof, sizeof kBgzfEof, fpos);
                 if (!w.empty()) throw IoErr("Error writing to file " + fname + ": " + w);
             }
         } catch (...) {
+            settle(0); settle(1);
             if (fd >= 0) ::close(fd);
             for (cudaEvent_t& e : ev) cudaEventDestroy(e);
             throw;
