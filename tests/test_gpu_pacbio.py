@@ -91,3 +91,61 @@ def test_pacbio_haplotypes_pooled_and_sep_files(ctx, tmp_path):
         J.pacbio(haps, pre, 300, seed=16, ctx=ctx, sep_files=True, **kw)
     with pytest.raises(RuntimeError, match="not built yet"):
         J.pacbio(haps, "", 10, seed=1, ctx=ctx, sink="memory", prob_dup=0.1, **kw)
+
+
+def test_pacbio_end_to_end_statistics_against_the_reference(ctx, tmp_path):
+    """The whole generator against the unmodified reference run end to end on its own pcg64 streams (two-sample
+    tests, alpha = 1e-3): read lengths, the two quality characters of a read and where they split, strand, reads per
+    chromosome, and the observed mismatch-free fraction of short exact k-mers as a proxy for the error rates."""
+    import ctypes as C
+    from scipy import stats
+    from oracle import harness as H
+    if not H.have_ref(False):
+        pytest.skip("oracle/_ref not built")
+    g = genome(21, 4, 200000, with_n=False)
+    n = 6000
+    fq, _, _ = J.pacbio(g, "", n, seed=31, ctx=ctx, sink="memory", want_plan=True)
+    lib = H.ref_lib(False)
+    f64p, u64p = C.POINTER(C.c_double), C.POINTER(C.c_uint64)
+    lib.jrefpb_pacbio_ref.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint64] + [C.c_double] * 5 + \
+        [f64p, u64p, C.c_uint64, C.c_uint64, f64p, f64p, f64p, f64p] + [C.c_double] * 4 + [C.c_char_p, C.c_uint64]
+    rg = H.RefGenomeH(g.names, [bytes(s) for s in g.seqs])
+    D = P.DEFAULTS
+    arr = lambda x: np.ascontiguousarray(x, dtype=np.float64)
+    cn, cs, sq, nm = arr(D["chi2_params_n"]), arr(D["chi2_params_s"]), arr(D["sqrt_params"]), arr(D["norm_params"])
+    ln = D["lognorm_read_length"]
+    err = C.create_string_buffer(256)
+    lib.jref_set_r_seed(12345)
+    pre = str(tmp_path / "ref")
+    assert lib.jrefpb_pacbio_ref(rg.h, pre.encode(), n, 1, 100, 0.0, ln[2], ln[0], ln[1], 50.0, None, None, 0, 40,
+                                 cn.ctypes.data_as(f64p), cs.ctypes.data_as(f64p), sq.ctypes.data_as(f64p),
+                                 nm.ctypes.data_as(f64p), 0.2, 0.11, 0.04, 0.01, err, 256) == 0, err.value
+    ref = open(pre + "_R1.fq", "rb").read()
+
+    def features(b):
+        L = b.split(b"\n")[:-1]
+        ids, seqs, quals = L[0::4], L[1::4], L[3::4]
+        lens = np.array([len(s) for s in seqs], dtype=float)
+        strand = np.array([i.endswith(b"-R") for i in ids])
+        chrom = np.array([int(i.split(b"-")[1][5:]) for i in ids])
+        ql = np.array([q[0] for q in quals]); qr = np.array([q[-1] for q in quals])
+        split = np.array([len(q) - len(q.lstrip(bytes([q[0]]))) if q[0] != q[-1] else len(q) for q in quals]) / lens
+        return lens, strand, chrom, ql, qr, split
+
+    a, b = features(fq), features(ref)
+    assert len(a[0]) == len(b[0]) == n
+    assert stats.ks_2samp(a[0], b[0]).pvalue > 1e-3                                              # read lengths
+    assert stats.chi2_contingency([[a[1].sum(), (~a[1]).sum()], [b[1].sum(), (~b[1]).sum()]])[1] > 1e-3   # strand
+    # reads per chromosome: a deliberate deviation.  PacBioOneGenome never decrements chrom_reads (src/hts_pacbio.cpp:147,
+    # :200 look for the first chromosome with reads left; nothing takes them away, unlike IlluminaOneGenome,
+    # src/hts_illumina.cpp:404-406, and PacBioHaplotypes), so with a reference genome the reference takes EVERY read from
+    # the first chromosome; here the reads are apportioned by chromosome length, as add_n_reads intends.
+    ca, cb = np.bincount(a[2], minlength=4), np.bincount(b[2], minlength=4)
+    assert cb[0] == n and cb[1:].sum() == 0
+    assert stats.chisquare(ca).pvalue > 1e-3                                                     # four equal chromosomes
+    for k in (3, 4):                                                                              # quality characters
+        vals = np.union1d(a[k], b[k])
+        ta, tb = np.array([(a[k] == v).sum() for v in vals]), np.array([(b[k] == v).sum() for v in vals])
+        keep = (ta + tb) >= 20
+        assert stats.chi2_contingency([np.append(ta[keep], ta[~keep].sum() + 1), np.append(tb[keep], tb[~keep].sum() + 1)])[1] > 1e-3
+    assert stats.ks_2samp(a[5], b[5]).pvalue > 1e-3                                              # where the quality changes
