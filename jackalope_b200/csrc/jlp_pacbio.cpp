@@ -27,37 +27,15 @@ long double runif_01(uint64_t x) { return ((long double)x + 1) / ((long double)U
 
 // Standard normal distribution function and quantile.  The reference calls R::pnorm5 / R::qnorm5 here
 // (src/hts_pacbio.h:349-352); these agree with Rmath to a few ulp: the lower tail through erfc, the quantile by
-// bisection on it, polished by two Newton steps, the upper half by symmetry.
+// Newton steps on it from Abramowitz and Stegun 26.2.23, the upper half by symmetry.
 double pnorm(double x) { return 0.5 * std::erfc(-x * 0.70710678118654752440); }
 double qnorm(double p) {
     if (!(p > 0.0)) return -INFINITY;
     if (!(p < 1.0)) return INFINITY;
     if (p > 0.5) return -qnorm(1.0 - p);
-    double lo = -40.0, hi = 40.0;
-    for (int i = 0; i < 80; i++) {
-        const double mid = 0.5 * (lo + hi);
-        if (pnorm(mid) < p) lo = mid; else hi = mid;
-    }
-    double x = 0.5 * (lo + hi);
-    for (int i = 0; i < 2; i++) {
-        const double d = 0.39894228040143267794 * std::exp(-0.5 * x * x);
-        if (d > 1e-300) {
-            const double step = (pnorm(x) - p) / d;
-            if (std::fabs(step) < 1e-3) x -= step;
-        }
-    }
-    return x;
-}
-
-// The same quantile for the samplers of this file (statistical tier: any accurate quantile will do): Abramowitz and
-// Stegun 26.2.23 as the starting point, four Newton steps on pnorm.
-double qnorm_fast(double p) {
-    if (!(p > 0.0)) return -INFINITY;
-    if (!(p < 1.0)) return INFINITY;
-    if (p > 0.5) return -qnorm_fast(1.0 - p);
     const double t = std::sqrt(-2.0 * std::log(p));
     double x = -(t - (2.515517 + 0.802853 * t + 0.010328 * t * t) / (1.0 + 1.432788 * t + 0.189269 * t * t + 0.001308 * t * t * t));
-    for (int i = 0; i < 4; i++) {
+    for (int i = 0; i < 5; i++) {
         const double d = 0.39894228040143267794 * std::exp(-0.5 * x * x);
         if (!(d > 1e-300)) break;
         x -= (pnorm(x) - p) / d;
@@ -97,7 +75,7 @@ double sample_gamma(double a, SampleStream& S) {
     if (a < 1.0) return sample_gamma(a + 1.0, S) * std::pow(S.next(), 1.0 / a);
     const double d = a - 1.0 / 3.0, c = 1.0 / std::sqrt(9.0 * d);
     for (;;) {
-        const double z = qnorm_fast(S.next());
+        const double z = qnorm(S.next());
         const double v0 = 1.0 + c * z;
         if (v0 <= 0) continue;
         const double v = v0 * v0 * v0, u = S.next();
@@ -148,8 +126,8 @@ PbSample pb_sample(const PbModel& m, uint64_t seed, uint64_t j, uint64_t chrom_l
         const double mu = std::log(m.scale);
         double min_len = std::ceil(m.min_read_len);
         if (min_len < 1) min_len = 1;
-        double rnd = std::exp(mu + m.sigma * qnorm_fast(S.next())) + m.loc;
-        for (int it = 0; rnd < min_len && it < 10; it++) rnd = std::exp(mu + m.sigma * qnorm_fast(S.next())) + m.loc;
+        double rnd = std::exp(mu + m.sigma * qnorm(S.next())) + m.loc;
+        for (int it = 0; rnd < min_len && it < 10; it++) rnd = std::exp(mu + m.sigma * qnorm(S.next())) + m.loc;
         if (rnd < min_len) rnd = min_len;
         r.read_length = (uint64_t)rnd;
     } else {
