@@ -23,7 +23,7 @@ class OrcPbJob(C.Structure):
         ("n_groups", C.c_uint64), ("group_off", u64p), ("group_seq", C.POINTER(C.c_char_p)), ("group_len", u64p),
         ("group_genome_name", C.POINTER(C.c_char_p)), ("group_chrom_name", C.POINTER(C.c_char_p)),
         ("read_len", u64p), ("split_pos", u64p), ("passes_left", f64p), ("passes_right", f64p),
-        ("beyond_template_is_n", C.c_int32),
+        ("beyond_template_is_n", C.c_int32), ("prob_dup", C.c_double), ("pool_reads", C.c_uint64),
     ]
 
 
@@ -63,7 +63,7 @@ def split_passes(passes, read_length):
 
 
 def generate(names, seqs, genome_name, counts, read_len, split_pos, passes_left, passes_right, seed, want_ledger=True,
-             beyond_template_is_n=False, **model):
+             beyond_template_is_n=False, prob_dup=0.0, pool_reads=100, **model):
     """Oracle output for sum(counts) reads, counts[c] of them from chromosome c in order."""
     m = dict(DEFAULTS)
     m.update(model)
@@ -86,6 +86,7 @@ def generate(names, seqs, genome_name, counts, read_len, split_pos, passes_left,
     J.read_len, J.split_pos = rl.ctypes.data_as(u64p), sp.ctypes.data_as(u64p)
     J.passes_left, J.passes_right = pl.ctypes.data_as(f64p), pr.ctypes.data_as(f64p)
     J.beyond_template_is_n = int(beyond_template_is_n)
+    J.prob_dup, J.pool_reads = float(prob_dup), int(pool_reads)
     cap = int(np.sum(np.minimum(rl, lens.max())) * 2 + 200 * n + 64)
     out = C.create_string_buffer(cap)
     ln, led_n = C.c_uint64(), C.c_uint64()
@@ -100,12 +101,12 @@ def generate(names, seqs, genome_name, counts, read_len, split_pos, passes_left,
     return dict(fastq=out.raw[:ln.value], ledger=led[:led_n.value], ledger_cnt=led_cnt[:n], plan=plan[:4 * n].reshape(n, 4))
 
 
-def ref_replay(names, seqs, chrom_ind, read_len, split_pos, passes_left, passes_right, script, **model):
+def ref_replay(names, seqs, chrom_ind, read_len, split_pos, passes_left, passes_right, script, is_dup=None, **model):
     """The unmodified reference on the same reads, its pcg64 reading `script`."""
     m = dict(DEFAULTS)
     m.update(model)
     lib = H.ref_lib(True)
-    lib.jrefpb_replay.argtypes = [C.c_void_p, C.c_uint64, u64p, u64p, u64p, f64p, f64p, f64p, f64p, C.c_double, C.c_double,
+    lib.jrefpb_replay.argtypes = [C.c_void_p, C.c_uint64, u64p, u64p, u64p, f64p, f64p, C.POINTER(C.c_int32), f64p, f64p, C.c_double, C.c_double,
                                   C.c_double, C.c_double, u64p, C.c_uint64, u64p, C.c_char_p, C.c_uint64, u64p, C.c_char_p,
                                   C.c_uint64]
     g = H.RefGenomeH(names, [bytes(s) for s in seqs], replay=True)
@@ -114,13 +115,15 @@ def ref_replay(names, seqs, chrom_ind, read_len, split_pos, passes_left, passes_
     pl, pr = _arr(passes_left, np.float64), _arr(passes_right, np.float64)
     sq, nm = _arr(m["sqrt_params"], np.float64), _arr(m["norm_params"], np.float64)
     sc = _arr(script, np.uint64)
+    dup = _arr(is_dup, np.int32) if is_dup is not None else None
     consumed = np.zeros(max(1, n), dtype=np.uint64)
     cap = int(np.sum(rl) * 2 + 200 * n + 64)
     out = C.create_string_buffer(cap)
     ln = C.c_uint64()
     err = C.create_string_buffer(256)
     rc = lib.jrefpb_replay(g.h, n, ci.ctypes.data_as(u64p), rl.ctypes.data_as(u64p), sp.ctypes.data_as(u64p),
-                           pl.ctypes.data_as(f64p), pr.ctypes.data_as(f64p), sq.ctypes.data_as(f64p), nm.ctypes.data_as(f64p),
+                           pl.ctypes.data_as(f64p), pr.ctypes.data_as(f64p),
+                           dup.ctypes.data_as(C.POINTER(C.c_int32)) if dup is not None else None, sq.ctypes.data_as(f64p), nm.ctypes.data_as(f64p),
                            m["prob_thresh"], m["ins_prob"], m["del_prob"], m["sub_prob"], sc.ctypes.data_as(u64p), len(sc),
                            consumed.ctypes.data_as(u64p), out, cap, C.byref(ln), err, 256)
     assert rc == 0, err.value

@@ -664,7 +664,72 @@ typedef struct {
      * left in its buffer.  0: the same here (sequential, for the replay against the reference); 1: such a position
      * reads 'N' (the defined behaviour the CUDA path is compared with). */
     int32_t beyond_template_is_n;
+    /* duplicates (ReadWriterOneThread::create_reads, src/hts.h:254-280; PacBioOneGenome::re_read, src/hts_pacbio.cpp): read j
+     * re-reads the chromosome, read length and read_start of the first read of its chain iff the draw made after read
+     * j - 1 (sub 0, block 2, lo half) satisfies `dup < prob_dup` and j is not the first of its pool.  read_len of a
+     * duplicate is injected like any other (the caller passes its leader's) */
+    double prob_dup;
+    uint64_t pool_reads;
 } OrcPbJob;
+
+static uint64_t pb_group_of(const OrcPbJob* J, uint64_t j) {
+    uint64_t glo = 0, ghi = J->n_groups;
+    while (ghi - glo > 1) { uint64_t mid = (glo + ghi) / 2; if (J->group_off[mid] <= j) glo = mid; else ghi = mid; }
+    return glo;
+}
+static uint64_t pb_leader_of(const OrcPbJob* J, uint64_t j) {
+    uint64_t k = j;
+    if (!(J->prob_dup > 0) || J->pool_reads == 0) return k;
+    while (k > J->job_lo && ((k - J->job_lo) % J->pool_reads) != 0) {
+        const double dup = (double)runif_01(pb_draw(J->seed, k - 1, 0, 2, 0));
+        if (!(dup < J->prob_dup)) break;
+        k--;
+    }
+    return k;
+}
+static void pb_cum_probs(const PbModel* m, double passes_left, double passes_right, uint64_t seed, uint64_t j, Ledger* lg,
+                         double* cum_left, double* cum_right) {
+    const double left_thresh = (m->min_exp - (sqrt(passes_left + m->sqrt_params[0]) - m->sqrt_params[1])) / pb_sigmoid(passes_left);
+    const double right_thresh = (m->min_exp - (sqrt(passes_right + m->sqrt_params[0]) - m->sqrt_params[1])) / pb_sigmoid(passes_right);
+    const double incr_l = pb_trunc_norm(m, left_thresh, seed, j, 0, lg);
+    const double incr_r = pb_trunc_norm(m, right_thresh, seed, j, 1, lg);
+    double exp_l = incr_l * pb_sigmoid(passes_left) + sqrt(passes_left + m->sqrt_params[0]) - m->sqrt_params[1];
+    double exp_r = incr_r * pb_sigmoid(passes_right) + sqrt(passes_right + m->sqrt_params[0]) - m->sqrt_params[1];
+    if (exp_l < 0.6) exp_l = 0.6;
+    if (exp_r < 0.6) exp_r = 0.6;
+    cum_left[0] = pow(m->prob_ins, exp_l);
+    cum_left[1] = pow(m->prob_del, exp_l) + cum_left[0];
+    cum_left[2] = pow(m->prob_subst, exp_l) + cum_left[1];
+    cum_right[0] = pow(m->prob_ins, exp_r);
+    cum_right[1] = pow(m->prob_del, exp_r) + cum_right[0];
+    cum_right[2] = pow(m->prob_subst, exp_r) + cum_right[1];
+}
+/* read_start of a chain's first read k: its own model, walk (counts only) and start draw, nothing emitted */
+static uint64_t pb_leader_start(const OrcPbJob* J, const PbModel* m, uint64_t k, uint64_t chrom_len) {
+    uint64_t read_length = J->read_len[k - J->job_lo];
+    if (read_length >= chrom_len) read_length = chrom_len;
+    const uint64_t split_pos = J->split_pos[k - J->job_lo];
+    double cum_left[3], cum_right[3];
+    Ledger off = {NULL, 0, 0, 0};
+    pb_cum_probs(m, J->passes_left[k - J->job_lo], J->passes_right[k - J->job_lo], J->seed, k, &off, cum_left, cum_right);
+    uint64_t current_length = 0, chrom_pos = 0, extra_space = chrom_len - read_length, n_ins = 0, n_del = 0;
+    const double* cum = cum_left;
+    while (current_length < read_length) {
+        if (current_length == split_pos) cum = cum_right;
+        const double u = (double)runif_01(pb_draw(J->seed, k, 1, (uint32_t)(chrom_pos >> 1), (uint32_t)(chrom_pos & 1)));
+        if (u > cum[2]) current_length++;
+        else if (u < cum[0]) {
+            if (current_length < (read_length - 1)) { n_ins++; current_length++; extra_space++; if (current_length == split_pos) cum = cum_right; }
+            current_length++;
+        } else if (u < cum[1]) { if (extra_space > 0) { n_del++; extra_space--; } }
+        else current_length++;
+        chrom_pos++;
+    }
+    const uint64_t space = read_length + n_del - n_ins;
+    if (!(space < chrom_len)) return 0;
+    const double u = (double)runif_01(pb_draw(J->seed, k, 0, 1, 0));
+    return (uint64_t)(u * (double)(chrom_len - space + 1));
+}
 
 /* Reads [lo, hi) of the job.  plan (optional): [4 * (hi - lo)] group, read_length, read_start, read_chrom_space. */
 int orc_pacbio_generate(const OrcPbJob* J, uint64_t lo, uint64_t hi, char* out, uint64_t cap, uint64_t* len,
@@ -682,9 +747,9 @@ int orc_pacbio_generate(const OrcPbJob* J, uint64_t lo, uint64_t hi, char* out, 
     for (uint64_t j = lo; j < hi; j++) {
         const uint64_t led0 = lg.n;
         /* the group: first (haplotype, chromosome) with reads left, one_read */
-        uint64_t g, glo = 0, ghi = J->n_groups;
-        while (ghi - glo > 1) { uint64_t mid = (glo + ghi) / 2; if (J->group_off[mid] <= j) glo = mid; else ghi = mid; }
-        g = glo;
+        const uint64_t leader = pb_leader_of(J, j);
+        const int is_dup = leader != j;
+        const uint64_t g = pb_group_of(J, leader);
         const char* chrom = J->group_seq[g];
         const uint64_t chrom_len = J->group_len[g];
         uint64_t read_length = J->read_len[j - J->job_lo];
@@ -694,22 +759,7 @@ int orc_pacbio_generate(const OrcPbJob* J, uint64_t lo, uint64_t hi, char* out, 
 
         /* ---- update_probs */
         double cum_left[3], cum_right[3];
-        {
-            const double left_thresh = (m.min_exp - (sqrt(passes_left + m.sqrt_params[0]) - m.sqrt_params[1])) / pb_sigmoid(passes_left);
-            const double right_thresh = (m.min_exp - (sqrt(passes_right + m.sqrt_params[0]) - m.sqrt_params[1])) / pb_sigmoid(passes_right);
-            const double incr_l = pb_trunc_norm(&m, left_thresh, J->seed, j, 0, &lg);
-            const double incr_r = pb_trunc_norm(&m, right_thresh, J->seed, j, 1, &lg);
-            double exp_l = incr_l * pb_sigmoid(passes_left) + sqrt(passes_left + m.sqrt_params[0]) - m.sqrt_params[1];
-            double exp_r = incr_r * pb_sigmoid(passes_right) + sqrt(passes_right + m.sqrt_params[0]) - m.sqrt_params[1];
-            if (exp_l < 0.6) exp_l = 0.6;
-            if (exp_r < 0.6) exp_r = 0.6;
-            cum_left[0] = pow(m.prob_ins, exp_l);
-            cum_left[1] = pow(m.prob_del, exp_l) + cum_left[0];
-            cum_left[2] = pow(m.prob_subst, exp_l) + cum_left[1];
-            cum_right[0] = pow(m.prob_ins, exp_r);
-            cum_right[1] = pow(m.prob_del, exp_r) + cum_right[0];
-            cum_right[2] = pow(m.prob_subst, exp_r) + cum_right[1];
-        }
+        pb_cum_probs(&m, passes_left, passes_right, J->seed, j, &lg, cum_left, cum_right);
         /* ---- fill_quals */
         char qual_left, qual_right;
         {
@@ -762,9 +812,23 @@ int orc_pacbio_generate(const OrcPbJob* J, uint64_t lo, uint64_t hi, char* out, 
             if (rc) break;
         }
         /* ---- read_chrom_space, read_start */
-        const uint64_t space = read_length + n_del - n_ins;
+        uint64_t space = read_length + n_del - n_ins;
         uint64_t read_start = 0;
-        if (space < chrom_len) {
+        if (is_dup) {
+            /* re_read: the chain's read_start; deletions are given up from the back until the template fits, and a read
+             * that still does not fit is not written */
+            read_start = pb_leader_start(J, &m, leader, chrom_len);
+            while (space + read_start > chrom_len) {
+                if (n_del == 0) break;
+                n_del--;
+                space--;
+            }
+            if (space + read_start > chrom_len) {
+                if (plan) { uint64_t* p = plan + 4 * (j - lo); p[0] = g; p[1] = read_length; p[2] = read_start; p[3] = ~0ull; }
+                if (ledger_cnt) ledger_cnt[j - lo] = lg.n - led0;
+                continue;
+            }
+        } else if (space < chrom_len) {
             const uint64_t x = pb_draw(J->seed, j, 0, 1, 0);
             led(&lg, x);
             const double u = (double)runif_01(x);

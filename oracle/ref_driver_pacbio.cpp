@@ -82,11 +82,12 @@ int jrefpb_sample_lengths_passes(uint64_t n, uint64_t seed, double scale, double
 // history) and split_pos / passes_left / passes_right (PacBioPassSampler::sample: std::chi_squared_distribution, the
 // same) -- and then runs exactly what PacBioOneGenome::one_read does after them (src/hts_pacbio.cpp):
 //   qe_sampler.sample(...)   update_probs (two truncated normals), fill_quals, the insertion/deletion/substitution walk
-//   read_chrom_space, read_start
+//   read_chrom_space, read_start   (for a duplicate: re_read's rule instead, see below)
 //   append_pool(...)         strand, ID line, fill_read / rev_comp, the edits, the two-valued quality line
 // consumed[i] returns how many draws read i took from the script.
 int jrefpb_replay(void* ref, uint64_t n_reads, const uint64_t* chrom_ind, const uint64_t* read_len, const uint64_t* split_pos,
-                  const double* passes_left, const double* passes_right, const double* sqrt_params, const double* norm_params,
+                  const double* passes_left, const double* passes_right, const int32_t* is_dup, const double* sqrt_params,
+                  const double* norm_params,
                   double prob_thresh, double prob_ins, double prob_del, double prob_subst, const uint64_t* script,
                   uint64_t script_len, uint64_t* consumed, char* out, uint64_t cap, uint64_t* len, char* err, uint64_t errcap) {
     try {
@@ -110,7 +111,17 @@ int jrefpb_replay(void* ref, uint64_t n_reads, const uint64_t* chrom_ind, const 
             rd.qe_sampler.sample(eng, rd.qual_left, rd.qual_right, rd.insertions, rd.deletions, rd.substitutions, chrom_len,
                                  rd.read_length, rd.split_pos, rd.passes_left, rd.passes_right);
             rd.read_chrom_space = rd.read_length + rd.deletions.size() - rd.insertions.size();
-            if (rd.read_chrom_space < chrom_len) {
+            if (is_dup && is_dup[i]) {
+                // re_read (src/hts_pacbio.cpp): chrom_ind, read_length and read_start are the chain's (the harness passes the
+                // leader's chromosome and length; rd.read_start still holds the leader's); deletions are given up until the
+                // template fits, a read that does not fit is not written
+                while ((rd.read_chrom_space + rd.read_start) > chrom_len) {
+                    if (rd.deletions.empty()) break;
+                    rd.deletions.pop_back();
+                    rd.read_chrom_space--;
+                }
+                if ((rd.read_chrom_space + rd.read_start) > chrom_len) { consumed[i] = sc.pos - before; continue; }
+            } else if (rd.read_chrom_space < chrom_len) {
                 double u = runif_01(eng);
                 rd.read_start = static_cast<uint64>(u * (chrom_len - rd.read_chrom_space + 1));
             } else if (rd.read_chrom_space == chrom_len) {

@@ -80,3 +80,41 @@ def test_reference_replays_the_oracle_ledger(name):
         assert len(lines[4 * i + 1]) == eff == len(lines[4 * i + 3]) and lines[4 * i + 2] == b"+"
         q = lines[4 * i + 3]
         assert len(set(q[:sp[i]])) <= 1 and len(set(q[sp[i]:])) <= 1
+
+
+@needs_ref
+@pytest.mark.parametrize("lens,mean_len", [([6000, 3000, 9000], 1500), ([700, 400, 900], 800)])
+def test_duplicates_replay(lens, mean_len):
+    """prob_dup > 0: a duplicate (re_read) keeps its chain's chromosome, read length and read_start, draws a new pass
+    split, walk, strand and edits; with chromosome-long reads deletions are given up until the template fits and a
+    read that still does not fit is not written."""
+    names, seqs = genome(3, lens)
+    counts = [12, 12, 12]
+    chrom, rl, sp, pl, pr = reads(4, counts, lens, mean_len)
+    prob_dup, pool = 0.45, 7
+    # the chains: who duplicates whom is a function of the dup draws; a duplicate takes its leader's chromosome and length
+    from oracle.harness_pacbio import _orc
+    import ctypes as C
+    lib = _orc()
+    lib.orc_pb_draw.restype = C.c_uint64
+    lib.orc_pb_draw.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]
+    n = len(rl)
+    leader = np.arange(n)
+    for j in range(1, n):
+        if j % pool != 0 and (lib.orc_pb_draw(77, j - 1, 0, 2, 0) + 1) / 2.0 ** 64 < prob_dup:
+            leader[j] = leader[j - 1]
+    is_dup = (leader != np.arange(n)).astype(np.int32)
+    assert 5 < is_dup.sum() < n - 5
+    rl = rl[leader]
+    eff = np.minimum(rl, np.asarray(lens)[chrom[leader]])
+    sp = np.array([min(int(s), int(e)) for s, e in zip(sp, eff)])
+    o = P.generate(names, seqs, "REF", counts, rl, sp, pl, pr, seed=77, prob_dup=prob_dup, pool_reads=pool)
+    fq, consumed = P.ref_replay(names, seqs, chrom[leader], rl, sp, pl, pr, o["ledger"], is_dup=is_dup)
+    assert np.array_equal(consumed, o["ledger_cnt"])
+    assert fq == o["fastq"]
+    # duplicates share their leader's start
+    ids = [l for l in fq.split(b"\n")[0::4] if l]
+    written = o["plan"][:, 3] != np.uint64(2 ** 64 - 1)
+    assert len(ids) == written.sum()
+    starts = o["plan"][:, 2]
+    assert all(starts[j] == starts[leader[j]] for j in range(n))
