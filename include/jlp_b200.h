@@ -205,7 +205,7 @@ typedef struct jlp_pacbio_params {
     uint64_t n_threads;          /* accepted for compatibility; the files are written by the calling thread */
     uint64_t read_pool_size;
     const double* haplotype_probs;
-    double prob_dup;             /* must be 0 (the default of pacbio()): duplicates are not built yet */
+    double prob_dup;             /* duplicates re-read their chain's chromosome, length and start (re_read); read_pool_size <= 65536 then */
     double scale, sigma, loc;    /* lognorm_read_length[3], [1], [2] */
     double min_read_len;
     const double* read_probs;    /* custom_read_lengths: n_custom probabilities and lengths, or NULL / 0 */

@@ -2,7 +2,6 @@
 // (/root/reference/src/hts_pacbio.cpp) on the C ABI of include/jlp_b200.h; the exported signatures -- and with them
 // R/RcppExports.R, src/RcppExports.cpp and the R function pacbio() (R/hts_pacbio.R) -- stay as they are.  Build notes
 // as in hts_illumina_b200.cpp; type-checked only (no R in the image this repository was built in).
-// Not built yet in the library: duplicates (prob_dup > 0 returns JLP_ERR_UNSUPPORTED -> an R error).
 
 #include <RcppArmadillo.h>
 #include <progress.hpp>

@@ -1177,7 +1177,11 @@ void run_pacbio(jlp_ctx* c, bool use_haps, const jlp_pacbio_params* P, int sink_
                 jlp_run_stats* stats) {
     PbModel model;
     pb_model_from(P, model);
-    if (!(P->prob_dup == 0)) throw Unsupported("PacBio duplicates (prob_dup > 0) are not built yet");
+    if (!(P->prob_dup >= 0 && P->prob_dup <= 1)) throw ArgErr("prob_dup must be in [0,1]");
+    if (P->read_pool_size < 1) throw ArgErr("read_pool_size must be >= 1");
+    const Thr t_dup = thr_double_lt(P->prob_dup);
+    const bool dups = t_dup.thr != 0 || t_dup.all;
+    if (dups && P->read_pool_size > 65536) throw Unsupported("prob_dup > 0 with read_pool_size > 65536");
     if (P->compress < 0 || P->compress > 9) throw ArgErr("\nInvalid bgzip compress level. It must be in range [0,9].");
     if (P->compress > 0) {
         const std::string m = P->comp_method ? P->comp_method : "";
@@ -1206,7 +1210,10 @@ void run_pacbio(jlp_ctx* c, bool use_haps, const jlp_pacbio_params* P, int sink_
     d_strpool.upload(G.strpool, c->s_compute);
     d_totals.ensure(4);
     CK(cudaMemsetAsync(d_totals.p, 0, 4 * sizeof(uint64_t), c->s_compute));
-    const uint64_t B = P->batch_reads ? P->batch_reads : 16384;
+    uint64_t B = P->batch_reads ? P->batch_reads : 16384;
+    // a chain of duplicates never leaves its pool (src/hts.h:266-267): batches are whole pools, so a duplicate's leader is in
+    // its batch
+    if (dups) B = std::max<uint64_t>(P->read_pool_size, B / P->read_pool_size * P->read_pool_size);
     uint32_t max_prefix = 0;
     for (const GroupDev& g : G.groups) max_prefix = std::max(max_prefix, g.prefix_len);
     const uint64_t c_rev = thr_ld_lt(0.5).thr;
@@ -1232,24 +1239,42 @@ void run_pacbio(jlp_ctx* c, bool use_haps, const jlp_pacbio_params* P, int sink_
                 plan.resize(n);
                 uint64_t bound = 0;
                 {
-                    // the reads are independent: split over the host threads (n_threads, at most 64)
+                    // chains of duplicates: read i re-reads iff the draw made after read i - 1 says so and i does not open a pool
+                    std::vector<uint32_t> lead(n, kPbNoLeader);
+                    if (dups)
+                        for (uint32_t i = 1; i < n; i++)
+                            if ((b0 + i - job.lo) % P->read_pool_size != 0 && (t_dup.all || pb_dup_draw(P->seed, b0 + i - 1) < t_dup.thr))
+                                lead[i] = lead[i - 1] == kPbNoLeader ? i - 1 : lead[i - 1];
+                    // the reads are independent given their leaders: split over the host threads (n_threads, at most 64),
+                    // first the leaders, then the duplicates (which take their leader's chromosome and length)
                     const uint32_t nt = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(P->n_threads, 1), 64);
                     std::vector<uint64_t> part(nt, 0);
-                    auto work = [&](uint32_t k) {
-                        for (uint32_t i = k; i < n; i += nt) {
-                            const uint64_t j = b0 + i;
-                            const size_t g = (size_t)(std::upper_bound(G.group_off.begin(), G.group_off.end(), j) - G.group_off.begin()) - 1;
-                            const PbSample smp = pb_sample(model, P->seed, j, G.groups[g].len);
-                            std::memset(&plan[i], 0, sizeof(PbRead));
-                            pb_read_model(model, P->seed, j, smp, plan[i]);
-                            plan[i].group = (uint32_t)g;
-                            part[k] += max_prefix + 24 + 2 * smp.read_length + 5;
-                        }
-                    };
-                    std::vector<std::thread> th;
-                    for (uint32_t k = 1; k < nt; k++) th.emplace_back(work, k);
-                    work(0);
-                    for (std::thread& t : th) t.join();
+                    for (int pass = 0; pass < (dups ? 2 : 1); pass++) {
+                        auto work = [&](uint32_t k) {
+                            for (uint32_t i = k; i < n; i += nt) {
+                                if ((lead[i] != kPbNoLeader) != (pass == 1)) continue;
+                                const uint64_t j = b0 + i;
+                                PbSample smp;
+                                size_t g;
+                                if (pass == 0) {
+                                    g = (size_t)(std::upper_bound(G.group_off.begin(), G.group_off.end(), j) - G.group_off.begin()) - 1;
+                                    smp = pb_sample(model, P->seed, j, G.groups[g].len);
+                                } else {
+                                    g = plan[lead[i]].group;
+                                    smp = pb_sample_passes(model, P->seed, j, plan[lead[i]].read_length);
+                                }
+                                std::memset(&plan[i], 0, sizeof(PbRead));
+                                pb_read_model(model, P->seed, j, smp, plan[i]);
+                                plan[i].group = (uint32_t)g;
+                                plan[i].leader = lead[i];
+                                part[k] += max_prefix + 24 + 2 * smp.read_length + 5;
+                            }
+                        };
+                        std::vector<std::thread> th;
+                        for (uint32_t k = 1; k < nt; k++) th.emplace_back(work, k);
+                        work(0);
+                        for (std::thread& t : th) t.join();
+                    }
                     for (uint64_t v : part) bound += v;
                 }
                 d_reads.ensure(n);
@@ -1261,6 +1286,7 @@ void run_pacbio(jlp_ctx* c, bool use_haps, const jlp_pacbio_params* P, int sink_
                 st.h2d_bytes += n * sizeof(PbRead);
                 CK(cudaEventRecord(ev[0], c->s_compute));
                 CK(launch_pb_plan(d_reads.p, n, b0, P->seed, d_groups.p, c_rev, d_rec_len.p, c->s_compute));
+                if (dups) { CK(launch_pb_dups(d_reads.p, n, b0, P->seed, d_groups.p, d_rec_len.p, c->s_compute)); st.kernel_launches++; }
                 CK(launch_scan(d_rec_len.p, n, 1, d_rec_local.p, d_block_tot.p, d_block_base.p, d_totals.p, c->s_compute));
                 CK(launch_pb_reads(d_reads.p, n, b0, P->seed, d_groups.p, d_strpool.p, d_rec_local.p, d_block_base.p, d_out.p,
                                    c->s_compute));
@@ -1371,14 +1397,30 @@ int jlp_pacbio_read_plan(jlp_ctx* c, int use_haplotypes, const jlp_pacbio_params
         PbModel model;
         pb_model_from(p, model);
         const PbGroups G = pb_groups(c, use_haplotypes != 0, p);
-        for (uint64_t j = 0; j < p->n_reads; j++) {
-            const size_t g = (size_t)(std::upper_bound(G.group_off.begin(), G.group_off.end(), j) - G.group_off.begin()) - 1;
-            const PbSample s = pb_sample(model, p->seed, j, G.groups[g].len);
-            if (group) group[j] = g;
-            if (read_len) read_len[j] = s.read_length;
-            if (split_pos) split_pos[j] = s.split_pos;
-            if (passes_left) passes_left[j] = s.passes_left;
-            if (passes_right) passes_right[j] = s.passes_right;
+        const Thr t_dup = thr_double_lt(p->prob_dup);
+        const bool dups = t_dup.thr != 0 || t_dup.all;
+        for (const Job& job : G.jobs) {
+            uint64_t leader = job.lo;
+            PbSample ls{};
+            size_t lg = 0;
+            for (uint64_t j = job.lo; j < job.hi; j++) {
+                const bool dup = dups && j > job.lo && (j - job.lo) % std::max<uint64_t>(p->read_pool_size, 1) != 0 &&
+                                 (t_dup.all || pb_dup_draw(p->seed, j - 1) < t_dup.thr);
+                PbSample s;
+                if (!dup) {
+                    leader = j;
+                    lg = (size_t)(std::upper_bound(G.group_off.begin(), G.group_off.end(), j) - G.group_off.begin()) - 1;
+                    s = ls = pb_sample(model, p->seed, j, G.groups[lg].len);
+                } else {
+                    s = pb_sample_passes(model, p->seed, j, ls.read_length);
+                }
+                (void)leader;
+                if (group) group[j] = lg;
+                if (read_len) read_len[j] = s.read_length;
+                if (split_pos) split_pos[j] = s.split_pos;
+                if (passes_left) passes_left[j] = s.passes_left;
+                if (passes_right) passes_right[j] = s.passes_right;
+            }
         }
     });
 }

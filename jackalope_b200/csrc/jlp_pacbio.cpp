@@ -118,27 +118,9 @@ void pb_prepare(PbModel& m) {
     }
 }
 
-PbSample pb_sample(const PbModel& m, uint64_t seed, uint64_t j, uint64_t chrom_len) {
-    SampleStream S{seed, j};
-    PbSample r;
-    // ---- PacBioReadLenSampler::sample
-    if (m.read_probs.empty()) {
-        const double mu = std::log(m.scale);
-        double min_len = std::ceil(m.min_read_len);
-        if (min_len < 1) min_len = 1;
-        double rnd = std::exp(mu + m.sigma * qnorm(S.next())) + m.loc;
-        for (int it = 0; rnd < min_len && it < 10; it++) rnd = std::exp(mu + m.sigma * qnorm(S.next())) + m.loc;
-        if (rnd < min_len) rnd = min_len;
-        r.read_length = (uint64_t)rnd;
-    } else {
-        const uint64_t n = m.read_lens.size();
-        uint64_t i = (uint64_t)(S.next() * (double)n);
-        if (i >= n) i = n - 1;
-        if (!(S.next() < m.len_prob[i])) i = m.len_alias[i];
-        r.read_length = m.read_lens[i];
-    }
-    if (r.read_length >= chrom_len) r.read_length = chrom_len;          // one_read, src/hts_pacbio.cpp
-    // ---- PacBioPassSampler::sample
+namespace {
+// PacBioPassSampler::sample for r.read_length
+void pb_passes(const PbModel& m, SampleStream& S, PbSample& r) {
     const double read_length = (double)r.read_length;
     const double lcap = std::min(read_length, m.chi2_n[2]);
     double n = m.chi2_n[0] * lcap + m.chi2_n[1];
@@ -171,8 +153,42 @@ PbSample pb_sample(const PbModel& m, uint64_t seed, uint64_t j, uint64_t chrom_l
         r.passes_left = std::floor(passes);
         r.passes_right = std::ceil(passes);
     }
+}
+}  // namespace
+
+PbSample pb_sample(const PbModel& m, uint64_t seed, uint64_t j, uint64_t chrom_len) {
+    SampleStream S{seed, j};
+    PbSample r;
+    // ---- PacBioReadLenSampler::sample
+    if (m.read_probs.empty()) {
+        const double mu = std::log(m.scale);
+        double min_len = std::ceil(m.min_read_len);
+        if (min_len < 1) min_len = 1;
+        double rnd = std::exp(mu + m.sigma * qnorm(S.next())) + m.loc;
+        for (int it = 0; rnd < min_len && it < 10; it++) rnd = std::exp(mu + m.sigma * qnorm(S.next())) + m.loc;
+        if (rnd < min_len) rnd = min_len;
+        r.read_length = (uint64_t)rnd;
+    } else {
+        const uint64_t n = m.read_lens.size();
+        uint64_t i = (uint64_t)(S.next() * (double)n);
+        if (i >= n) i = n - 1;
+        if (!(S.next() < m.len_prob[i])) i = m.len_alias[i];
+        r.read_length = m.read_lens[i];
+    }
+    if (r.read_length >= chrom_len) r.read_length = chrom_len;          // one_read, src/hts_pacbio.cpp
+    pb_passes(m, S, r);
     return r;
 }
+
+PbSample pb_sample_passes(const PbModel& m, uint64_t seed, uint64_t j, uint64_t read_length) {
+    SampleStream S{seed, j};
+    PbSample r;
+    r.read_length = read_length;
+    pb_passes(m, S, r);
+    return r;
+}
+
+uint64_t pb_dup_draw(uint64_t seed, uint64_t j) { return pb_draw(seed, j, 0, 2, 0); }
 
 namespace {
 

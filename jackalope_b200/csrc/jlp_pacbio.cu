@@ -94,6 +94,7 @@ k_pb_warp(PbRead* __restrict__ reads, uint32_t n, uint64_t first_read, uint64_t 
     const GroupDev G = groups[R.group];
     const uint32_t RL = R.read_length;
     uint8_t* o = nullptr;
+    if (EMIT && R.rec_len == 0) return;          // a duplicate whose template does not fit is not written (re_read)
     if (EMIT) {
         o = out + block_base[i / kScanBlock] + rec_local[i];
         const uint32_t idlen = R.rec_len - (RL + 4u) - (R.pad /* seq_len, kept by the plan */);
@@ -116,7 +117,7 @@ k_pb_warp(PbRead* __restrict__ reads, uint32_t n, uint64_t first_read, uint64_t 
     for (;;) {
         if (EMIT ? emitted >= RL : W.len >= RL) break;
         if (W.side == 0 && W.len == R.split_pos) W.side = 1;
-        const bool fast = emitted == W.len && (W.side == 1 || W.len + 130u < R.split_pos) && W.len + 130u < RL && W.extra_space >= 64;
+        const bool fast = !(R.flags & kPbSerial) && emitted == W.len && (W.side == 1 || W.len + 130u < R.split_pos) && W.len + 130u < RL && W.extra_space >= 64;
         if (fast) {
             const U4 w = draw_block(seed, j, (pos >> 1) + lane, PL_PB, 1);
             const uint32_t ev0 = pb_event(R, W.side, lo64(w)), ev1 = pb_event(R, W.side, hi64(w));
@@ -162,8 +163,10 @@ k_pb_warp(PbRead* __restrict__ reads, uint32_t n, uint64_t first_read, uint64_t 
                 WalkDraws D{seed, j};
                 const uint32_t stop = (pos & ~63u) + 64u;
                 while (pos < stop && (EMIT ? emitted < RL : W.len < RL)) {
-                    const uint32_t rec = W.step(R, D.at(pos));
-                    n_ins += rec == 1; n_del += rec == 2;
+                    uint32_t rec = W.step(R, D.at(pos));
+                    n_ins += rec == 1;
+                    if (rec == 2 && EMIT && n_del >= R.del_keep) rec = 0;      // a deletion the duplicate gave up: a plain base
+                    n_del += rec == 2;
                     if (EMIT) {
                         const uint8_t base = pos >= R.space ? (uint8_t)'N' : R.reverse ? pb_complement(R.seg[R.space - 1u - pos]) : R.seg[pos];
                         uint8_t* q = o + emitted;
@@ -218,6 +221,8 @@ k_pb_warp(PbRead* __restrict__ reads, uint32_t n, uint64_t first_read, uint64_t 
             R.reverse = hi64(w) < c_rev ? 1u : 0u;
             R.pad = emitted;                                                   // bases of the sequence line (read_length, or one more)
             R.rec_len = G.prefix_len + nd + 3u + emitted + RL + 4u;
+            if (R.leader != kPbNoLeader) R.del_keep = n_del;                   // a duplicate: k_pb_dups settles start, span and record
+            else R.del_keep = 0xffffffffu;
             reads[i] = R;
             rec_len[i] = R.rec_len;
         }
@@ -229,11 +234,65 @@ k_pb_warp(PbRead* __restrict__ reads, uint32_t n, uint64_t first_read, uint64_t 
     }
 }
 
+// PacBioOneGenome::re_read (src/hts_pacbio.cpp): a duplicate keeps the read_start of the first read of its chain; the
+// deletions its own walk recorded are given up from the back until the template fits the chromosome, and if it still
+// does not fit the read is not written.  One thread per read, after k_pb_warp<false>.
+__global__ void __launch_bounds__(128)
+k_pb_dups(PbRead* __restrict__ reads, uint32_t n, uint64_t first_read, uint64_t seed, const GroupDev* __restrict__ groups,
+          uint32_t* __restrict__ rec_len) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PbRead R = reads[i];
+    if (R.leader == kPbNoLeader) return;
+    const GroupDev G = groups[R.group];
+    const uint64_t start = reads[R.leader].start;
+    const uint32_t RL = R.read_length;
+    uint64_t space = R.space;
+    uint32_t keep = R.del_keep, dropped = 0;
+    while (space + start > G.len && keep > 0) { keep--; space--; dropped++; }
+    if (space + start > G.len) {
+        R.rec_len = 0;
+    } else {
+        uint32_t seq_len = R.pad;
+        if (dropped) {
+            // append_pool now sees fewer deletions: what it emits is counted again, by the literal walk
+            Walk W;
+            W.extra_space = G.len - RL;
+            WalkDraws D{seed, first_read + i};
+            uint32_t emitted = 0, pos = 0, del_ord = 0;
+            while (W.len < RL) {
+                uint32_t rec = W.step(R, D.at(pos));
+                if (rec == 2) { if (del_ord >= keep) rec = 0; del_ord++; }
+                if (emitted < RL) emitted += pb_emitted(rec);
+                pos++;
+            }
+            seq_len = emitted;
+            R.flags |= kPbSerial;
+        }
+        uint32_t nd = 1;
+        for (uint64_t v = start; v >= 10; v /= 10) nd++;
+        R.seg = G.seq + start;
+        R.start = start;
+        R.space = (uint32_t)space;
+        R.del_keep = keep;
+        R.pad = seq_len;
+        R.rec_len = G.prefix_len + nd + 3u + seq_len + RL + 4u;
+    }
+    reads[i] = R;
+    rec_len[i] = R.rec_len;
+}
+
 }  // namespace
 
 cudaError_t launch_pb_plan(PbRead* reads, uint32_t n, uint64_t first_read, uint64_t seed, const GroupDev* groups,
                            uint64_t c_rev, uint32_t* rec_len, cudaStream_t s) {
     if (n) k_pb_warp<false><<<(n + 7) / 8, 256, 0, s>>>(reads, n, first_read, seed, groups, c_rev, rec_len, nullptr, nullptr, nullptr, nullptr);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pb_dups(PbRead* reads, uint32_t n, uint64_t first_read, uint64_t seed, const GroupDev* groups, uint32_t* rec_len,
+                           cudaStream_t s) {
+    if (n) k_pb_dups<<<(n + 127) / 128, 128, 0, s>>>(reads, n, first_read, seed, groups, rec_len);
     return cudaGetLastError();
 }
 

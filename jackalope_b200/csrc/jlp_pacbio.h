@@ -44,6 +44,10 @@ struct PbSample {
     double passes_left, passes_right;
 };
 PbSample pb_sample(const PbModel& m, uint64_t seed, uint64_t j, uint64_t chrom_len);
+// the same for a duplicate (PacBioOneGenome::re_read): the chain's read length, a new number of passes
+PbSample pb_sample_passes(const PbModel& m, uint64_t seed, uint64_t j, uint64_t read_length);
+// the draw ReadWriterOneThread::create_reads makes after read j (src/hts.h:264-277): the next read re-reads iff it is < prob_dup
+uint64_t pb_dup_draw(uint64_t seed, uint64_t j);
 
 // Per-read input of the kernels: the walk's comparisons as integer thresholds on the 64-bit draws
 // (update_probs + fill_quals, src/hts_pacbio.cpp / src/hts_pacbio.h:383-391; exact under replay).
@@ -59,14 +63,21 @@ struct PbRead {
     uint32_t rec_len;          // FASTQ bytes of the record
     uint64_t start;            // read_start
     uint32_t reverse;
-    uint32_t pad;
+    uint32_t pad;              // bases of the sequence line (k_pb_warp<false>)
+    uint32_t leader;           // a duplicate: index (in the batch) of the first read of its chain; kPbNoLeader otherwise
+    uint32_t del_keep;         // recorded deletions append_pool still sees (a duplicate may have to give some up)
 };
-static_assert(sizeof(PbRead) == 96, "PbRead layout");
+static_assert(sizeof(PbRead) == 104, "PbRead layout");
+constexpr uint32_t kPbNoLeader = 0xffffffffu;
+constexpr uint32_t kPbSerial = 1u << 24;      // PbRead::flags: the read is walked by one lane throughout
 void pb_read_model(const PbModel& m, uint64_t seed, uint64_t j, const PbSample& s, PbRead& out);
 
 // plan: walk -> counts -> template span, start, strand, record length; reads: the record itself
 cudaError_t launch_pb_plan(PbRead* reads, uint32_t n, uint64_t first_read, uint64_t seed, const GroupDev* groups,
                            uint64_t c_rev, uint32_t* rec_len, cudaStream_t s);
+// duplicates take their chain's start; deletions are given up until the template fits (re_read, src/hts_pacbio.cpp)
+cudaError_t launch_pb_dups(PbRead* reads, uint32_t n, uint64_t first_read, uint64_t seed, const GroupDev* groups, uint32_t* rec_len,
+                           cudaStream_t s);
 cudaError_t launch_pb_reads(const PbRead* reads, uint32_t n, uint64_t first_read, uint64_t seed, const GroupDev* groups,
                             const uint8_t* strpool, const uint32_t* rec_local, const uint64_t* block_base, uint8_t* out,
                             cudaStream_t s);

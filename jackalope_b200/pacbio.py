@@ -1,6 +1,5 @@
 """pacbio(): the PacBio read generator behind the reference's argument surface
-(/root/reference/R/hts_pacbio.R: pacbio(), check_pacbio_args()).  First version of SURVEY.md section 8f rank 3:
-no duplicates (prob_dup must be 0, the reference's default), one batch at a time."""
+(/root/reference/R/hts_pacbio.R: pacbio(), check_pacbio_args()); SURVEY.md section 8f rank 3."""
 from __future__ import annotations
 
 import ctypes as C

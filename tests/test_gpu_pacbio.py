@@ -17,7 +17,7 @@ from oracle import harness_pacbio as P
 pytestmark = pytest.mark.gpu
 
 
-def oracle_for(obj, plan, seed, **model):
+def oracle_for(obj, plan, seed, prob_dup=0.0, pool_reads=100, **model):
     if isinstance(obj, J.Haplotypes):
         hs = hap_sequences(obj)
         seqs = [hs[h][c] for h in range(obj.n_haps()) for c in range(len(obj.reference.names))]
@@ -28,16 +28,17 @@ def oracle_for(obj, plan, seed, **model):
     counts = np.bincount(plan["group"].astype(np.int64), minlength=len(seqs))
     assert (np.diff(plan["group"].astype(np.int64)) >= 0).all()
     return P.generate(names, seqs, gnames, counts, plan["read_len"], plan["split_pos"], plan["passes_left"],
-                      plan["passes_right"], seed, want_ledger=False, beyond_template_is_n=True, **model)["fastq"]
+                      plan["passes_right"], seed, want_ledger=False, beyond_template_is_n=True, prob_dup=prob_dup,
+                      pool_reads=pool_reads, **model)["fastq"]
 
 
 def check(ctx, obj, n_reads, seed, **kw):
     fq, st, plan = J.pacbio(obj, "", n_reads, seed=seed, ctx=ctx, sink="memory", want_plan=True, **kw)
     model = {k: kw[k] for k in ("sqrt_params", "norm_params", "prob_thresh", "ins_prob", "del_prob", "sub_prob") if k in kw}
-    want = oracle_for(obj, plan, seed, **model)
+    want = oracle_for(obj, plan, seed, prob_dup=kw.get("prob_dup", 0.0), pool_reads=kw.get("read_pool_size", 100), **model)
     d = first_diff(fq, want)
     assert d is None, "differs at byte %d: gpu=%r oracle=%r" % (d, fq[max(0, d - 60):d + 40], want[max(0, d - 60):d + 40])
-    assert st["pairs"] == n_reads and fq.count(b"\n") == 4 * n_reads
+    assert st["pairs"] == n_reads and (fq.count(b"\n") == 4 * n_reads or kw.get("prob_dup", 0) > 0)
     return fq, st, plan
 
 
@@ -89,8 +90,6 @@ def test_pacbio_haplotypes_pooled_and_sep_files(ctx, tmp_path):
     assert gzip.decompress(open(pre + "h_R1.fq.gz", "rb").read()) == fq
     with pytest.raises(J.JackalopeError, match="already exists"):
         J.pacbio(haps, pre, 300, seed=16, ctx=ctx, sep_files=True, **kw)
-    with pytest.raises(RuntimeError, match="not built yet"):
-        J.pacbio(haps, "", 10, seed=1, ctx=ctx, sink="memory", prob_dup=0.1, **kw)
 
 
 def test_pacbio_end_to_end_statistics_against_the_reference(ctx, tmp_path):
@@ -149,3 +148,28 @@ def test_pacbio_end_to_end_statistics_against_the_reference(ctx, tmp_path):
         keep = (ta + tb) >= 20
         assert stats.chi2_contingency([np.append(ta[keep], ta[~keep].sum() + 1), np.append(tb[keep], tb[~keep].sum() + 1)])[1] > 1e-3
     assert stats.ks_2samp(a[5], b[5]).pvalue > 1e-3                                              # where the quality changes
+
+
+def test_pacbio_duplicates(ctx):
+    """prob_dup > 0 (ReadWriterOneThread::create_reads + PacBioOneGenome::re_read): chains inside pools, the chain's
+    chromosome, read length and start, new passes / errors / strand; batches are whole pools."""
+    g = genome(7, 3, 30000)
+    kw = dict(prob_dup=0.4, read_pool_size=7, custom_read_lengths=[[300, 1], [1500, 2], [4000, 1]])
+    a, _, plan = check(ctx, g, 600, seed=41, batch_reads=64, **kw)
+    b, _, _ = check(ctx, g, 600, seed=41, **kw)
+    assert a == b
+    ids = a.split(b"\n")[0::4][:-1]
+    starts = [i.rsplit(b"-", 2)[1] for i in ids]
+    same = sum(starts[k] == starts[k - 1] for k in range(1, len(starts)))
+    assert 0.25 * 600 < same < 0.5 * 600                       # about prob_dup * (1 - 1/pool) of the reads repeat a start
+    haps = J.random_haplotypes(genome(8, 2, 20000, with_n=False), 2, seed=9)
+    check(ctx, haps, 300, seed=42, prob_dup=0.3, read_pool_size=10, custom_read_lengths=[700, 2500])
+
+
+def test_pacbio_duplicates_of_chromosome_long_reads(ctx):
+    """Duplicates whose own walk needs more template than the chain's start leaves: deletions are given up from the
+    back until it fits, and a read that still does not fit is not written (fewer than n_reads records)."""
+    g = J.RefGenome(["a", "b"], [J.random_genome(1, n, seed=50 + n).seqs[0] for n in (400, 1500)])
+    fq, st, plan = check(ctx, g, 600, seed=43, prob_dup=0.5, read_pool_size=9, custom_read_lengths=[[350, 1], [1400, 1], [3000, 1]],
+                         ins_prob=0.05, del_prob=0.12, sub_prob=0.02)
+    assert fq.count(b"\n") <= 4 * 600
