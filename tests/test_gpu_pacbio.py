@@ -169,7 +169,9 @@ def test_pacbio_duplicates(ctx):
 def test_pacbio_duplicates_of_chromosome_long_reads(ctx):
     """Duplicates whose own walk needs more template than the chain's start leaves: deletions are given up from the
     back until it fits, and a read that still does not fit is not written (fewer than n_reads records)."""
-    g = J.RefGenome(["a", "b"], [J.random_genome(1, n, seed=50 + n).seqs[0] for n in (400, 1500)])
-    fq, st, plan = check(ctx, g, 600, seed=43, prob_dup=0.5, read_pool_size=9, custom_read_lengths=[[350, 1], [1400, 1], [3000, 1]],
-                         ins_prob=0.05, del_prob=0.12, sub_prob=0.02)
-    assert fq.count(b"\n") <= 4 * 600
+    g = J.RefGenome(["a", "b", "c"], [J.random_genome(1, n, seed=50 + n).seqs[0] for n in (700, 400, 900)])
+    fq, st, plan = check(ctx, g, 600, seed=43, prob_dup=0.6, read_pool_size=9, custom_read_lengths=[[1000, 3], [650, 1]])
+    n_rec = fq.count(b"\n") // 4
+    assert 400 < n_rec < 600                                   # some duplicates cannot be written
+    check(ctx, g, 300, seed=44, prob_dup=0.5, read_pool_size=5, custom_read_lengths=[[1000, 1]], ins_prob=0.05, del_prob=0.2,
+          sub_prob=0.02)                                       # many deletions to give up
