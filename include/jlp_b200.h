@@ -221,6 +221,8 @@ typedef struct jlp_pacbio_params {
     uint64_t seed;
     uint64_t batch_reads;        /* reads per device batch; 0 = default */
     int comp_engine;             /* enum jlp_comp_engine */
+    uint32_t shard_index;        /* this process generates its share of every job: whole pools of read_pool_size reads, */
+    uint32_t shard_count;        /* contiguous and near-equal over the shards (0 or 1 = everything) */
 } jlp_pacbio_params;
 
 /* Reads into files (use_haplotypes: the haplotypes added so far, else the reference genome). */

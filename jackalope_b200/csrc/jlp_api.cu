@@ -1233,8 +1233,18 @@ void run_pacbio(jlp_ctx* c, bool use_haps, const jlp_pacbio_params* P, int sink_
             if (fd < 0) throw IoErr("Unable to open file " + fname + ".\n");
         }
         try {
-            for (uint64_t b0 = job.lo; b0 < job.hi; b0 += B) {
-                const uint32_t n = (uint32_t)std::min<uint64_t>(B, job.hi - b0);
+            // this shard's part of the job: whole pools, so that chains of duplicates stay inside it
+            uint64_t s_lo = job.lo, s_hi = job.hi;
+            if (P->shard_count > 1) {
+                if (P->shard_index >= P->shard_count) throw ArgErr("shard_index >= shard_count");
+                const uint64_t pool = std::max<uint64_t>(P->read_pool_size, 1), n_pools = (job.hi - job.lo + pool - 1) / pool;
+                uint64_t p_lo, p_hi;
+                shard_range(0, n_pools, P->shard_index, P->shard_count, p_lo, p_hi);
+                s_lo = std::min(job.hi, job.lo + p_lo * pool);
+                s_hi = std::min(job.hi, job.lo + p_hi * pool);
+            }
+            for (uint64_t b0 = s_lo; b0 < s_hi; b0 += B) {
+                const uint32_t n = (uint32_t)std::min<uint64_t>(B, s_hi - b0);
                 // ---- per-read quantities on the host
                 plan.resize(n);
                 uint64_t bound = 0;

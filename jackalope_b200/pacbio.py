@@ -74,7 +74,8 @@ def check_pacbio_args(obj, n_reads, haplotype_probs, sep_files, compress, comp_m
 
 def _params(obj, out_prefix, n_reads, chi2_params_s, chi2_params_n, max_passes, sqrt_params, norm_params, prob_thresh,
             ins_prob, del_prob, sub_prob, min_read_length, lognorm_read_length, custom_read_lengths, prob_dup,
-            haplotype_probs, sep_files, compress, comp_method, n_threads, read_pool_size, seed, batch_reads, comp_engine):
+            haplotype_probs, sep_files, compress, comp_method, n_threads, read_pool_size, seed, batch_reads, comp_engine,
+            shard=None):
     keep = []
     p = _lib.PacbioParams()
     p.out_prefix = (out_prefix or "").encode()
@@ -102,6 +103,7 @@ def _params(obj, out_prefix, n_reads, chi2_params_s, chi2_params_n, max_passes, 
     p.seed = int(seed) & (2 ** 64 - 1)
     p.batch_reads = int(batch_reads or 0)
     p.comp_engine = {"auto": 0, "host": 1, "device": 2}[comp_engine]
+    p.shard_index, p.shard_count = (int(shard[0]), int(shard[1])) if shard else (0, 1)
     return p, keep
 
 
@@ -112,9 +114,10 @@ def pacbio(obj, out_prefix, n_reads,
            lognorm_read_length=(0.200110276521, -10075.4363813, 17922.611306), custom_read_lengths=None, prob_dup=0.0,
            haplotype_probs=None, sep_files=False, compress=False, comp_method="bgzip", n_threads=1, read_pool_size=100,
            show_progress=False, overwrite=False, *, seed=None, device=0, ctx=None, batch_reads=None, sink="files",
-           comp_engine="auto", want_plan=False):
+           comp_engine="auto", want_plan=False, shard=None):
     """Create and write PacBio reads to FASTQ file(s); positional and keyword arguments up to ``overwrite`` are the
-    reference's.  ``sink``: "files" (returns None), "memory" (returns (fastq_bytes, stats)), "device" (generate and
+    reference's.  ``shard=(index, count)``: this call generates its share of every job (whole pools of
+    ``read_pool_size`` reads; the shards' outputs concatenate to the unsharded run).  ``sink``: "files" (returns None), "memory" (returns (fastq_bytes, stats)), "device" (generate and
     drop on the GPU; returns stats).  ``want_plan=True`` (with sink="memory") also returns what was drawn per read
     before the per-base work: dict(group, read_len, split_pos, passes_left, passes_right)."""
     check_pacbio_args(obj, n_reads, haplotype_probs, sep_files, compress, comp_method, n_threads, read_pool_size,
@@ -146,7 +149,7 @@ def pacbio(obj, out_prefix, n_reads,
     p, keep = _params(obj, out_prefix, n_reads, chi2_params_s, chi2_params_n, max_passes, sqrt_params, norm_params,
                       prob_thresh, ins_prob, del_prob, sub_prob, min_read_length, lognorm_read_length, custom_read_lengths,
                       prob_dup, haplotype_probs, sep_files, compress, comp_method, n_threads, read_pool_size, seed,
-                      batch_reads, comp_engine)
+                      batch_reads, comp_engine, shard)
     ctx = ctx or default_context(device)
     if is_haps:
         ctx.set_haplotypes(obj)

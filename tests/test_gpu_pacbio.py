@@ -175,3 +175,19 @@ def test_pacbio_duplicates_of_chromosome_long_reads(ctx):
     assert 400 < n_rec < 600                                   # some duplicates cannot be written
     check(ctx, g, 300, seed=44, prob_dup=0.5, read_pool_size=5, custom_read_lengths=[[1000, 1]], ins_prob=0.05, del_prob=0.2,
           sub_prob=0.02)                                       # many deletions to give up
+
+
+def test_pacbio_shards_concatenate(ctx):
+    """One process per GPU takes shard (k, n) of every job: whole pools, so chains of duplicates stay inside a shard; the
+    shards' outputs concatenate to the unsharded run."""
+    g = genome(9, 3, 30000)
+    kw = dict(prob_dup=0.3, read_pool_size=11, custom_read_lengths=[[300, 1], [2000, 2]])
+    whole, _ = J.pacbio(g, "", 500, seed=45, ctx=ctx, sink="memory", **kw)
+    parts = [J.pacbio(g, "", 500, seed=45, ctx=ctx, sink="memory", shard=(k, 3), **kw)[0] for k in range(3)]
+    assert all(len(p) > 0 for p in parts) and b"".join(parts) == whole
+    haps = J.random_haplotypes(genome(10, 2, 20000, with_n=False), 3, seed=11)
+    hk = dict(sep_files=True, haplotype_probs=[3, 2, 1], custom_read_lengths=[900, 2500])
+    whole, _ = J.pacbio(haps, "", 400, seed=46, ctx=ctx, sink="memory", **hk)
+    parts = [J.pacbio(haps, "", 400, seed=46, ctx=ctx, sink="memory", shard=(k, 2), **hk)[0] for k in range(2)]
+    # with sep_files every job (haplotype) is split: shard 0 holds the first halves, in haplotype order
+    assert sum(len(p) for p in parts) == len(whole) and sorted(b"".join(parts).split(b"@")) == sorted(whole.split(b"@"))

@@ -318,6 +318,7 @@ def test_params_struct_matches_the_header():
 
     assert fields("jlp_illumina_params") == [f[0] for f in _lib.Params._fields_]
     assert fields("jlp_run_stats") == [f[0] for f in _lib.RunStats._fields_]
+    assert fields("jlp_pacbio_params") == [f[0] for f in _lib.PacbioParams._fields_]
     g = J.random_genome(1, 500, seed=1)
     with pytest.raises(J.JackalopeError, match="comp_engine"):
         J.illumina(g, "", 10, 100, True, seed=1, sink="memory", comp_engine="gpu")
