@@ -65,3 +65,33 @@ def test_samplers_are_addressed_by_read_index_and_clamp_to_the_chromosome():
     assert set(np.unique(d[0])) == {100, 2000} and 0.70 < (d[0] == 2000).mean() < 0.80
     with pytest.raises(J.JackalopeError):
         J.sample_read_plan(10, 1000, ins_prob=0.6, del_prob=0.5)
+
+
+def test_check_pacbio_args_mirrors_the_reference():
+    """R/hts_pacbio.R:8-110: the argument checks of pacbio()."""
+    g = J.random_genome(2, 500, seed=1)
+    haps = J.random_haplotypes(g, 2, seed=2)
+    D = dict(n_reads=10, haplotype_probs=None, sep_files=False, compress=False, comp_method="bgzip", n_threads=1,
+             read_pool_size=100, chi2_params_s=DEFAULTS["chi2_params_s"], chi2_params_n=DEFAULTS["chi2_params_n"], max_passes=40,
+             sqrt_params=DEFAULTS["sqrt_params"], norm_params=DEFAULTS["norm_params"], prob_thresh=0.2, ins_prob=0.11,
+             del_prob=0.04, sub_prob=0.01, min_read_length=50, lognorm_read_length=DEFAULTS["lognorm_read_length"],
+             custom_read_lengths=None, prob_dup=0.0, show_progress=False)
+
+    def call(obj=g, **kw):
+        a = dict(D)
+        a.update(kw)
+        J.check_pacbio_args(obj, **a)
+
+    call()
+    call(haps, haplotype_probs=[1, 2], sep_files=True, custom_read_lengths=[[100, 1], [200, 0]])
+    call(custom_read_lengths=[100, 200, 300])
+    for bad in (dict(obj="x"), dict(n_reads=0), dict(n_threads=0), dict(read_pool_size=0), dict(max_passes=0),
+                dict(min_read_length=0), dict(prob_thresh=1.5), dict(ins_prob=-0.1), dict(prob_dup=2),
+                dict(ins_prob=0.5, del_prob=0.4, sub_prob=0.2), dict(chi2_params_s=(1, 2, 3)), dict(chi2_params_n=(1, 2)),
+                dict(lognorm_read_length=(1, 2)), dict(sqrt_params=(1,)), dict(norm_params=(0, 0.2, 1)),
+                dict(custom_read_lengths=[[1, 2, 3]]), dict(custom_read_lengths=[[100, -1], [200, 1]]),
+                dict(custom_read_lengths=[[100, 0], [200, 0]]), dict(haplotype_probs=[1, 2]), dict(obj=haps, haplotype_probs=[1]),
+                dict(obj=haps, haplotype_probs=[0, 0]), dict(sep_files=1), dict(compress=10), dict(comp_method="xz"),
+                dict(show_progress=1)):
+        with pytest.raises(J.JackalopeError):
+            call(**bad)
