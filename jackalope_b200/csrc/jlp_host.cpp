@@ -36,13 +36,44 @@ template <typename F> Thr prefix_count(F pred) {
     return Thr{hi, false};
 }
 
+// The same with a guess of where the prefix ends (for thresholds on u = runif_01(x) against p that is p * 2^64 up to
+// rounding): a bracket is grown around the guess and bisected, about 25 evaluations instead of 64.
+template <typename F> Thr prefix_count_near(F pred, long double guess) {
+    if (pred(UINT64_MAX)) return Thr{UINT64_MAX, true};
+    if (!pred(0)) return Thr{0, false};
+    uint64_t g = guess <= 0 ? 0 : guess >= 18446744073709551615.0L ? UINT64_MAX : static_cast<uint64_t>(guess);
+    uint64_t lo = 0, hi = UINT64_MAX;  // pred(lo) true, pred(hi) false
+    if (pred(g)) {
+        lo = g;
+        for (uint64_t step = 1024; ; step *= 16) {
+            const uint64_t c = g > UINT64_MAX - step ? UINT64_MAX : g + step;
+            if (!pred(c)) { hi = c; break; }
+            lo = c;
+            if (c == UINT64_MAX) break;
+        }
+    } else {
+        hi = g;
+        for (uint64_t step = 1024; ; step *= 16) {
+            const uint64_t c = g < step ? 0 : g - step;
+            if (pred(c)) { lo = c; break; }
+            hi = c;
+            if (c == 0) break;
+        }
+    }
+    while (hi - lo > 1) {
+        uint64_t mid = lo + (hi - lo) / 2;
+        if (pred(mid)) lo = mid; else hi = mid;
+    }
+    return Thr{hi, false};
+}
+
 }  // namespace
 
 Thr thr_double_lt(double p) {
-    return prefix_count([p](uint64_t x) { double u = runif_01(x); return u < p; });
+    return prefix_count_near([p](uint64_t x) { double u = runif_01(x); return u < p; }, (long double)p * 18446744073709551616.0L);
 }
 Thr thr_double_le(double p) {
-    return prefix_count([p](uint64_t x) { double u = runif_01(x); return !(u > p); });
+    return prefix_count_near([p](uint64_t x) { double u = runif_01(x); return !(u > p); }, (long double)p * 18446744073709551616.0L);
 }
 Thr thr_ld_lt(double p) {
     return prefix_count([p](uint64_t x) { return runif_01(x) < p; });
