@@ -117,43 +117,72 @@ k_pb_warp(PbRead* __restrict__ reads, uint32_t n, uint64_t first_read, uint64_t 
     for (;;) {
         if (EMIT ? emitted >= RL : W.len >= RL) break;
         if (W.side == 0 && W.len == R.split_pos) W.side = 1;
-        const bool fast = !(R.flags & kPbSerial) && emitted == W.len && (W.side == 1 || W.len + 130u < R.split_pos) && W.len + 130u < RL && W.extra_space >= 64;
+        // A chunk is decided in parallel and kept only if no rule coupled its positions: the read must not come within
+        // two bases of its end inside the chunk (an insertion needs room, the loop stops there), deletions must always be
+        // recordable, and append_pool's count must not have run ahead of the walk's.  The switch to the right-hand error
+        // probabilities is resolved in place: a position uses them iff the length before it has reached split_pos, which
+        // the prefix sum over the left-hand events tells up to the first such position.
+        bool fast = !(R.flags & kPbSerial) && emitted == W.len && W.extra_space >= 64 && W.len + 4u < RL;
+        uint32_t ev0 = 0, ev1 = 0, e0 = 0, e1 = 0, incl = 0, total = 0;
         if (fast) {
             const U4 w = draw_block(seed, j, (pos >> 1) + lane, PL_PB, 1);
-            const uint32_t ev0 = pb_event(R, W.side, lo64(w)), ev1 = pb_event(R, W.side, hi64(w));
-            const uint32_t e0 = pb_emitted(ev0), e1 = pb_emitted(ev1);
-            uint32_t incl = e0 + e1;
+            const uint64_t x0 = lo64(w), x1 = hi64(w);
+            ev0 = pb_event(R, W.side, x0); ev1 = pb_event(R, W.side, x1);
+            e0 = pb_emitted(ev0); e1 = pb_emitted(ev1);
+            incl = e0 + e1;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += x; }
-            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            total = __shfl_sync(0xffffffffu, incl, 31);
+            if (W.side == 0 && W.len + total >= R.split_pos) {
+                const uint32_t pre0 = W.len + incl - e0 - e1, pre1 = pre0 + e0;
+                const bool r0 = pre0 >= R.split_pos, r1 = pre1 >= R.split_pos;
+                const uint32_t any = __ballot_sync(0xffffffffu, r0 || r1);
+                if (any) {
+                    const uint32_t fl = (uint32_t)__ffs(any) - 1u;
+                    const bool s0 = lane > fl || (lane == fl && r0), s1 = lane > fl || (lane == fl && (r0 || r1));
+                    if (s0) ev0 = pb_event(R, 1, x0);
+                    if (s1) ev1 = pb_event(R, 1, x1);
+                    e0 = pb_emitted(ev0); e1 = pb_emitted(ev1);
+                    incl = e0 + e1;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += x; }
+                    total = __shfl_sync(0xffffffffu, incl, 31);
+                }
+            }
+            fast = W.len + total + 3u < RL;            // every position saw a length below read_length - 1, and the walk goes on
+        }
+        if (fast) {
             const uint32_t ins = __popc(__ballot_sync(0xffffffffu, ev0 == 1)) + __popc(__ballot_sync(0xffffffffu, ev1 == 1));
             const uint32_t del = __popc(__ballot_sync(0xffffffffu, ev0 == 2)) + __popc(__ballot_sync(0xffffffffu, ev1 == 2));
             if (EMIT) {
                 uint8_t* q = o + emitted + (incl - e0 - e1);
+                // the inserted / substituted bases of both positions come from one Philox block (positions 2k and 2k + 1
+                // share block k of the edit plane)
+                U4 we = {0, 0, 0, 0};
+                if (((ev0 | ev1) & 1u) != 0) we = draw_block(seed, j, (pos >> 1) + lane, PL_PB, 2);     // events 1 and 3 are odd
 #pragma unroll
                 for (uint32_t h = 0; h < 2; h++) {
                     const uint32_t ev = h ? ev1 : ev0, p = pos + 2u * lane + h;
                     if (ev == 2) continue;
                     const uint8_t base = R.reverse ? pb_complement(R.seg[R.space - 1u - p]) : R.seg[p];
-                    if (ev == 0) *q++ = base;
-                    else {
-                        const uint64_t xe = pb_draw(seed, j, 2, p >> 1, p & 1u);
-                        if (ev == 1) {
-                            *q++ = base;
-                            const uint32_t r4 = ins_base_index(xe);
-                            *q++ = r4 == 0 ? 'T' : r4 == 1 ? 'C' : r4 == 2 ? 'A' : r4 == 3 ? 'G' : 0;
-                        } else {
-                            uint64_t r3 = mul_floor_x87(xe, 3);
-                            if (r3 > 2) r3 = 2;
-                            const uint32_t code = base == 'T' ? 0u : base == 'C' ? 1u : base == 'A' ? 2u : base == 'G' ? 3u : 4u;
-                            uint8_t sub = 'N';
-                            if (code < 4u) { const uint32_t k = (uint32_t)r3 + ((uint32_t)r3 >= code ? 1u : 0u); sub = k == 0 ? 'T' : k == 1 ? 'C' : k == 2 ? 'A' : 'G'; }
-                            *q++ = sub;
-                        }
+                    const uint64_t xe = h ? hi64(we) : lo64(we);
+                    uint8_t first = base;
+                    if (ev == 3) {
+                        uint64_t r3 = mul_floor_x87(xe, 3);
+                        if (r3 > 2) r3 = 2;
+                        const uint32_t code = base == 'T' ? 0u : base == 'C' ? 1u : base == 'A' ? 2u : base == 'G' ? 3u : 4u;
+                        first = 'N';
+                        if (code < 4u) { const uint32_t k = (uint32_t)r3 + ((uint32_t)r3 >= code ? 1u : 0u); first = k == 0 ? 'T' : k == 1 ? 'C' : k == 2 ? 'A' : 'G'; }
+                    }
+                    *q++ = first;
+                    if (ev == 1) {
+                        const uint32_t r4 = ins_base_index(xe);
+                        *q++ = r4 == 0 ? 'T' : r4 == 1 ? 'C' : r4 == 2 ? 'A' : r4 == 3 ? 'G' : 0;
                     }
                 }
             }
             W.len += total; emitted += total;
+            if (W.side == 0 && W.len > R.split_pos) W.side = 1;         // (reaching it exactly is seen at the next position)
             W.extra_space += ins; W.extra_space -= del;
             n_ins += ins; n_del += del;
             pos += 64;
