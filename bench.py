@@ -189,6 +189,33 @@ def cpu_reference_run(ref, n_pairs, L, prof1, prof2, threads, seed):
         return time.perf_counter() - t0
 
 
+def cpu_reference_pacbio(ref, n_reads, threads):
+    """pacbio_ref_cpp (defaults of pacbio()) of the unmodified reference on `threads` host threads; returns seconds."""
+    from oracle import harness as H
+    from oracle.harness_pacbio import DEFAULTS as D
+    import shutil
+    lib = H.ref_lib(False)
+    f64p, u64p = C.POINTER(C.c_double), C.POINTER(C.c_uint64)
+    lib.jrefpb_pacbio_ref.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint64] + [C.c_double] * 5 + \
+        [f64p, u64p, C.c_uint64, C.c_uint64, f64p, f64p, f64p, f64p] + [C.c_double] * 4 + [C.c_char_p, C.c_uint64]
+    arr = lambda x: np.ascontiguousarray(x, dtype=np.float64)
+    cn, cs, sq, nm = arr(D["chi2_params_n"]), arr(D["chi2_params_s"]), arr(D["sqrt_params"]), arr(D["norm_params"])
+    ln = D["lognorm_read_length"]
+    need = n_reads * 20000
+    shm = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > 2 * need else None
+    err = C.create_string_buffer(256)
+    with tempfile.TemporaryDirectory(dir=shm) as d:
+        if shm is None:
+            os.symlink("/dev/null", os.path.join(d, "p_R1.fq"))
+        t0 = time.perf_counter()
+        rc = lib.jrefpb_pacbio_ref(ref.h, os.path.join(d, "p").encode(), n_reads, threads, 100, 0.0, ln[2], ln[0], ln[1], 50.0, None, None,
+                                   0, 40, cn.ctypes.data_as(f64p), cs.ctypes.data_as(f64p), sq.ctypes.data_as(f64p), nm.ctypes.data_as(f64p),
+                                   0.2, 0.11, 0.04, 0.01, err, 256)
+        if rc != 0:
+            raise RuntimeError(err.value.decode())
+        return time.perf_counter() - t0
+
+
 def cpu_port_run(genome, n_pairs, L, kw, seed):
     """The oracle port (1 thread) on the same workload; returns seconds."""
     from oracle.compare import oracle_run
@@ -204,7 +231,7 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-def cpu_baseline(genome, lens, flat_bases, L, kw, prof1, prof2, target_s=12.0):
+def cpu_baseline(genome, lens, flat_bases, L, kw, prof1, prof2, target_s=12.0, pacbio_out=None):
     threads = host_threads()
     ref = cpu_reference_setup(lens, flat_bases)
     if ref is not None:
@@ -212,6 +239,15 @@ def cpu_baseline(genome, lens, flat_bases, L, kw, prof1, prof2, target_s=12.0):
         t = cpu_reference_run(ref, n0, L, prof1, prof2, threads, 1)
         n1 = int(max(n0, min(1e7, n0 / t * target_s)))
         t1 = cpu_reference_run(ref, n1, L, prof1, prof2, threads, 2)
+        if pacbio_out is not None:
+            try:        # the PacBio generator of the unmodified reference on the same genome and threads: about 3 s
+                tp = cpu_reference_pacbio(ref, 2000 * threads, threads)
+                npb = int(max(2000 * threads, min(4e5, 2000 * threads / tp * 3.0)))
+                tp = cpu_reference_pacbio(ref, npb, threads)
+                pacbio_out["cpu_baseline"] = {"value": npb / tp, "unit": "reads/s", "cores": threads, "kind": "reference",
+                                              "sample": "%d reads through pacbio_ref_cpp, n_threads=%d, %.1f s" % (npb, threads, tp)}
+            except Exception as e:
+                pacbio_out["cpu_baseline"] = {"error": str(e)[:200]}
         return {"value": n1 / t1, "unit": UNIT, "cores": threads, "kind": "reference",
                 "sample": "%d pairs of the same workload (3.1 Gb genome, PE150 HS25) through illumina_ref_cpp, "
                           "n_threads=%d, read_pool_size=1000, output to tmpfs (or /dev/null when tmpfs is too small), %.1f s" % (n1, threads, t1)}
@@ -479,7 +515,8 @@ def main():
         if not a.no_cpu_baseline and world == 1:
             prof1, prof2 = (J.flatten_profile(J.read_profile(None, "HS25", L, r)) for r in (1, 2))
             t0 = time.perf_counter()
-            out["cpu_baseline"] = cpu_baseline(genome, lens, flat, L, kw, prof1, prof2)
+            out["cpu_baseline"] = cpu_baseline(genome, lens, flat, L, kw, prof1, prof2,
+                                               pacbio_out=pacbio if isinstance(pacbio, dict) and "error" not in pacbio else None)
             log("[bench] cpu baseline took %.1f s" % (time.perf_counter() - t0))
         print(json.dumps(out), file=real_stdout, flush=True)
     ctx.close()
