@@ -477,10 +477,13 @@ def main():
         try:
             nthr = min(host_threads(), 32)
             J.pacbio(genome, "", 1 << 13, seed=a.seed, ctx=ctx, sink="device", n_threads=nthr)
-            t0 = time.perf_counter()
-            stp = J.pacbio(genome, "", 1 << 16, seed=a.seed + 1, ctx=ctx, sink="device", n_threads=nthr)
-            t_pb = time.perf_counter() - t0
-            pacbio = {"reads": stp["pairs"], "bases": stp["bytes_out"][0] / 2, "reads_per_s": stp["pairs"] / t_pb,
+            runs = []
+            for rep in range(3):        # three runs, the median reported (the host preparation shares the cores with whatever else runs)
+                t0 = time.perf_counter()
+                stp = J.pacbio(genome, "", 1 << 16, seed=a.seed + 1 + rep, ctx=ctx, sink="device", n_threads=nthr)
+                runs.append(time.perf_counter() - t0)
+            t_pb = sorted(runs)[1]
+            pacbio = {"reads": stp["pairs"], "bases": stp["bytes_out"][0] / 2, "reads_per_s": stp["pairs"] / t_pb, "wall_s_runs": runs,
                       "kernel_ms": stp["reads_ms"], "kernel_reads_per_s": stp["pairs"] / (stp["reads_ms"] / 1e3),
                       "kernel_fastq_GBps": stp["bytes_out"][0] / (stp["reads_ms"] / 1e3) / 1e9, "host_threads": nthr,
                       "note": "pacbio() defaults, reads left on the device; reads_per_s includes the per-read host preparation"}
