@@ -6,9 +6,11 @@
 // include path.  The two exported signatures -- and therefore R/RcppExports.R:96-107,
 // src/RcppExports.cpp:111-175 and the R function illumina() -- stay exactly as they are.
 // R, Rcpp and the package's build chain are absent from the image this repository was
-// built in, so this file has only been type-checked there (g++ -fsyntax-only against the package's own
-// ref_classes.h / hap_classes.h and the stub Rcpp headers of oracle/stubs); the same sequence of C-ABI calls is
-// what jackalope_b200/illumina.py performs through ctypes and what the test-suite runs.
+// built in.  What is checked there: this file is compiled TOGETHER with the stock wrappers of
+// src/RcppExports.cpp:109-243 (extracted at build time, never copied into the repository), the package's own
+// ref_classes.h / hap_classes.h and stub Rcpp headers into oracle/_ref/libjlp_glue.so, linked with
+// libjlp_b200.so (oracle/Makefile, oracle/glue_driver.cpp); tests/test_gpu_glue.py then calls
+// _jackalope_illumina_{ref,hap}_cpp the way .Call does and byte-compares the files with the oracle.
 //
 // Only jackalope's own types are read, through const access, as the original code does
 // (XPtr<RefGenome> / XPtr<HapSet> are borrowed, never freed: src/hts_illumina.h:307,513).
@@ -57,7 +59,7 @@ void illumina_ref_cpp(SEXP ref_genome_ptr, const bool& paired, const bool& matep
                       const double& frag_len_shape, const double& frag_len_scale, const uint64& frag_len_min,
                       const uint64& frag_len_max, const QualProbs& qual_probs1, const Quals& quals1,
                       const double& ins_prob1, const double& del_prob1, const QualProbs& qual_probs2, const Quals& quals2,
-                      const double& ins_prob2, const double& del_prob2, std::vector<std::string> barcodes) {
+                      const double& ins_prob2, const double& del_prob2, const std::vector<std::string>& barcodes) {
     XPtr<RefGenome> ref_genome(ref_genome_ptr);
     Ctx ctx;
     set_genome(ctx, *ref_genome);
@@ -91,7 +93,7 @@ void illumina_hap_cpp(SEXP hap_set_ptr, const bool& paired, const bool& matepair
                       const double& frag_len_shape, const double& frag_len_scale, const uint64& frag_len_min,
                       const uint64& frag_len_max, const QualProbs& qual_probs1, const Quals& quals1,
                       const double& ins_prob1, const double& del_prob1, const QualProbs& qual_probs2, const Quals& quals2,
-                      const double& ins_prob2, const double& del_prob2, std::vector<std::string> barcodes) {
+                      const double& ins_prob2, const double& del_prob2, const std::vector<std::string>& barcodes) {
     XPtr<HapSet> hap_set(hap_set_ptr);
     Ctx ctx;
     set_genome(ctx, *(hap_set->reference));

@@ -383,3 +383,127 @@ def ref_illumina_hap(hs: HapSetH, *, paired, matepair, out_prefix, sep_files, n_
                                *_prof_args(paired, prof1, prof2, ins_prob, del_prob), bcs, err, 512)
     if rc != 0:
         raise RuntimeError("illumina_hap_cpp: " + err.value.decode())
+
+
+# ------------------------------------------------- Rcpp glue link harness ---
+# oracle/_ref/libjlp_glue.so = integration/*.cpp + the stock RcppExports wrappers + oracle/glue_driver.cpp,
+# linked with jackalope_b200/libjlp_b200.so (oracle/Makefile).  Calls go wrapper -> glue -> C ABI -> CUDA.
+
+GLUE_SYMBOLS = ["_jackalope_illumina_ref_cpp", "_jackalope_illumina_hap_cpp", "_jackalope_pacbio_ref_cpp",
+                "_jackalope_pacbio_hap_cpp"]
+
+
+def have_glue():
+    return os.path.exists(os.path.join(HERE, "_ref", "libjlp_glue.so"))
+
+
+_glue = None
+
+
+def glue_lib():
+    global _glue
+    if _glue is None:
+        lib = C.CDLL(os.path.join(HERE, "_ref", "libjlp_glue.so"))
+        lib.jglue_genome_new.restype = C.c_void_p
+        lib.jglue_genome_new.argtypes = [C.c_uint64, C.POINTER(C.c_char_p), u64p, C.POINTER(C.c_char_p)]
+        lib.jglue_genome_free.argtypes = [C.c_void_p]
+        lib.jglue_hapset_new.restype = C.c_void_p
+        lib.jglue_hapset_new.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_char_p)]
+        lib.jglue_hapset_free.argtypes = [C.c_void_p]
+        lib.jglue_add_edits.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, u8p, u64p, u64p, u64p, C.c_char_p]
+        lib.jglue_hap_chrom_size.restype = C.c_uint64
+        lib.jglue_hap_chrom_size.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
+        lib.jglue_set_r_seed.argtypes = [C.c_uint64]
+        lib.jglue_seed_after.restype = C.c_uint64
+        lib.jglue_seed_after.argtypes = [C.c_uint64]
+        prof = [C.c_uint64, u32p, f64p, u8p, C.c_double, C.c_double, u32p, f64p, u8p, C.c_double, C.c_double]
+        lib.jglue_illumina_ref.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_uint64, C.c_double,
+                                           C.c_uint64, C.c_uint64, C.c_double, C.c_double, C.c_uint64, C.c_uint64] + prof + \
+            [C.c_char_p, C.c_char_p, C.c_uint64]
+        lib.jglue_illumina_hap.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_uint64,
+                                           C.c_double, C.c_uint64, C.c_uint64, f64p, C.c_double, C.c_double, C.c_uint64,
+                                           C.c_uint64] + prof + [C.POINTER(C.c_char_p), C.c_char_p, C.c_uint64]
+        lib.jglue_pacbio_ref.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint64] + [C.c_double] * 5 + \
+            [C.c_uint64, f64p, f64p, f64p, f64p] + [C.c_double] * 4 + [C.c_char_p, C.c_uint64]
+        _glue = lib
+    return _glue
+
+
+class GlueGenome:
+    """A jackalope RefGenome living inside libjlp_glue.so (what R holds behind the ref_genome XPtr)."""
+
+    def __init__(self, names, seqs):
+        self.lib = glue_lib()
+        self.seqs = [bytes(s) for s in seqs]
+        lens = np.array([len(s) for s in self.seqs], dtype=np.uint64)
+        self.h = self.lib.jglue_genome_new(len(self.seqs), _strs(self.seqs), _ptr(lens, u64p), _strs(list(names)))
+
+    def __del__(self):
+        try:
+            self.lib.jglue_genome_free(self.h)
+        except Exception:
+            pass
+
+
+def edits_arrays(edits):
+    """[(kind, pos, payload)] -> (kind u8[], pos u64[], size u64[], pay_off u64[], payload bytes)"""
+    n = len(edits)
+    kind, pos, size, off = np.zeros(n, np.uint8), np.zeros(n, np.uint64), np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+    pay = bytearray()
+    for i, (k, p, x) in enumerate(edits):
+        pos[i] = p
+        if k == "del":
+            kind[i], size[i] = 2, x
+        else:
+            kind[i] = 0 if k == "sub" else 1
+            off[i], size[i] = len(pay), len(x)
+            pay += x
+    return kind, pos, size, off, bytes(pay)
+
+
+class GlueHapSet:
+    """A jackalope HapSet inside libjlp_glue.so, edited through the reference's own HapChrom::add_*."""
+
+    def __init__(self, ref: GlueGenome, hap_names, edits):
+        self.lib, self.ref = ref.lib, ref
+        self.h = self.lib.jglue_hapset_new(ref.h, len(hap_names), _strs(list(hap_names)))
+        for h, eh in enumerate(edits):
+            for c, ec in enumerate(eh):
+                if ec:
+                    kind, pos, size, off, pay = edits_arrays(ec)
+                    assert self.lib.jglue_add_edits(self.h, h, c, len(ec), _ptr(kind, u8p), _ptr(pos, u64p), _ptr(size, u64p),
+                                                    _ptr(off, u64p), pay) == 0
+
+    def __del__(self):
+        try:
+            self.lib.jglue_hapset_free(self.h)
+        except Exception:
+            pass
+
+
+def glue_illumina(obj, *, paired, matepair, out_prefix, n_reads, prof1, prof2, r_seed, sep_files=False, compress=0,
+                  comp_method="bgzip", prob_dup=0.02, n_threads=1, read_pool_size=1000, hap_probs=None, shape=16.0, scale=25.0,
+                  frag_len_min=None, frag_len_max=2 ** 32 - 1, ins_prob=(0.00009, 0.00015), del_prob=(0.00011, 0.00023),
+                  barcodes=None):
+    """.Call("_jackalope_illumina_{ref,hap}_cpp", ...) through the stock wrappers and the glue.  Returns the run seed
+    the glue drew from the (stub) R RNG seeded with `r_seed`; raises RuntimeError with R's error text."""
+    lib = glue_lib()
+    seed = lib.jglue_seed_after(r_seed)
+    lib.jglue_set_r_seed(r_seed)
+    err = C.create_string_buffer(1024)
+    L = prof1[0]
+    fmin = L if frag_len_min is None else frag_len_min
+    pa = _prof_args(paired, prof1, prof2, ins_prob, del_prob)
+    if isinstance(obj, GlueHapSet):
+        hp = np.ascontiguousarray(hap_probs, dtype=np.float64)
+        bcs = _strs(barcodes) if barcodes is not None else None
+        rc = lib.jglue_illumina_hap(obj.h, int(paired), int(matepair), out_prefix.encode(), int(sep_files), compress,
+                                    comp_method.encode(), n_reads, prob_dup, n_threads, read_pool_size, _ptr(hp, f64p), shape,
+                                    scale, fmin, frag_len_max, *pa, bcs, err, 1024)
+    else:
+        rc = lib.jglue_illumina_ref(obj.h, int(paired), int(matepair), out_prefix.encode(), compress, comp_method.encode(),
+                                    n_reads, prob_dup, n_threads, read_pool_size, shape, scale, fmin, frag_len_max, *pa,
+                                    (barcodes[0] if barcodes else "").encode(), err, 1024)
+    if rc != 0:
+        raise RuntimeError(err.value.decode(errors="replace"))
+    return seed

@@ -15,10 +15,10 @@ def pytest_configure(config):
 @pytest.fixture(scope="session", autouse=True)
 def _built():
     """Build the checker (oracle, and oracle/_ref where /root/reference exists) and the product library."""
-    from oracle import harness
-    harness.build()
     from jackalope_b200 import build as jbuild
     jbuild.build()
+    from oracle import harness
+    harness.build()           # after the product: oracle/_ref/libjlp_glue.so links against it
     yield
 
 

@@ -372,3 +372,27 @@ def test_rcpp_glue_type_checks_against_the_reference_headers():
                             "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "integration"),
                             os.path.join(ROOT, "integration", glue)], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr[:2000]
+
+
+def test_rcpp_glue_links_against_the_stock_wrappers():
+    """oracle/_ref/libjlp_glue.so = integration/*.cpp + the generated wrappers of /root/reference/src/RcppExports.cpp
+    :109-243 (extracted at build time) + libjlp_b200.so under -Wl,-z,defs: the four exports resolve against the
+    prototypes the stock wrappers declare (a by-value `barcodes`, as in round 1, is an undefined symbol here).
+    No compute call: the GPU tests (tests/test_gpu_glue.py) go through it."""
+    import subprocess
+    if not os.path.isdir(REF):
+        pytest.skip("/root/reference absent")
+    assert H.have_glue(), "oracle/Makefile did not build _ref/libjlp_glue.so"
+    so = os.path.join(ROOT, "oracle", "_ref", "libjlp_glue.so")
+    syms = subprocess.run(["nm", "-D", "--defined-only", so], capture_output=True, text=True, check=True).stdout
+    for s in H.GLUE_SYMBOLS:
+        assert (" T " + s) in syms, s
+    for export in ("illumina_ref_cpp", "illumina_hap_cpp", "pacbio_ref_cpp", "pacbio_hap_cpp"):
+        assert any(("_Z%d%s" % (len(export), export)) in line for line in syms.splitlines()), export
+    undef = subprocess.run(["nm", "-D", "--undefined-only", so], capture_output=True, text=True, check=True).stdout
+    assert "jlp_illumina_ref" in undef and "jlp_pacbio" in undef            # bound to libjlp_b200.so, not restated
+    # the wrappers in the build are the reference's, verbatim
+    ext = open(os.path.join(ROOT, "oracle", "_ref", "rcpp_exports_extract.cpp")).read()
+    stock = open(os.path.join(REF, "src", "RcppExports.cpp")).read()
+    body = ext[ext.index("// illumina_ref_cpp"):]
+    assert body in stock and "const std::vector<std::string>& barcodes);" in body
