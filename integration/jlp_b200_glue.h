@@ -21,22 +21,31 @@ using namespace Rcpp;
 
 struct Ctx {                       // destroys the context on every exit path, Rcpp::stop included
     jlp_ctx* p = nullptr;
-    Ctx() { if (jlp_ctx_create(0, &p) != JLP_OK) stop(jlp_last_error(nullptr)); }   // no CPU fallback
+    std::string bases;             // the flattened genome: the library reads it during the run (deferred upload)
+    // every GPU the process can see (CUDA_VISIBLE_DEVICES selects them): one call, one ordered set of files,
+    // as the reference's n_threads share one set (src/hts.h:334-353); no CPU fallback
+    Ctx() {
+        int rc = jlp_ctx_create_multi(0, nullptr, &p);
+        if (rc == JLP_OK && jlp_ctx_n_devices(p) == 1) { jlp_ctx_destroy(p); p = nullptr; rc = jlp_ctx_create(0, &p); }
+        if (rc != JLP_OK) stop(jlp_last_error(nullptr));
+    }
     ~Ctx() { jlp_ctx_destroy(p); }
     void check(int rc) { if (rc != JLP_OK) stop(std::string(jlp_last_error(p))); }
 };
 
+// RefGenome -> one contiguous byte array + offsets.  The upload is deferred: the run copies, chromosome by
+// chromosome underneath the first batches, what each device's piece of the run reads (haplotype runs: everything).
 inline void set_genome(Ctx& ctx, const RefGenome& ref) {
-    std::string bases;
-    bases.reserve(ref.total_size);
+    ctx.bases.clear();
+    ctx.bases.reserve(ref.total_size);
     std::vector<uint64_t> off(1, 0);
     std::vector<const char*> names;
     for (uint64 i = 0; i < ref.size(); i++) {
-        bases += ref[i].nucleos;
-        off.push_back(bases.size());
+        ctx.bases += ref[i].nucleos;
+        off.push_back(ctx.bases.size());
         names.push_back(ref[i].name.c_str());
     }
-    ctx.check(jlp_set_genome(ctx.p, bases.data(), off.data(), names.size(), names.data(), ref.name.c_str()));
+    ctx.check(jlp_set_genome_async(ctx.p, ctx.bases.data(), off.data(), names.size(), names.data(), ref.name.c_str()));
 }
 
 // one haplotype: AllMutations of every chromosome as flat arrays

@@ -63,7 +63,7 @@ class RunStats(C.Structure):
 
 # every symbol include/jlp_b200.h declares
 SYMBOLS = [
-    "jlp_ctx_create", "jlp_ctx_destroy", "jlp_last_error", "jlp_set_genome", "jlp_set_genome_async", "jlp_genome_sync", "jlp_create_genome", "jlp_get_genome", "jlp_genome_draw", "jlp_clear_haplotypes",
+    "jlp_ctx_create", "jlp_ctx_create_multi", "jlp_ctx_n_devices", "jlp_materialize_haplotypes", "jlp_ctx_destroy", "jlp_last_error", "jlp_set_genome", "jlp_set_genome_async", "jlp_genome_sync", "jlp_create_genome", "jlp_get_genome", "jlp_genome_draw", "jlp_clear_haplotypes",
     "jlp_add_haplotype", "jlp_get_haplotype_chrom", "jlp_set_profile", "jlp_illumina_ref", "jlp_illumina_hap",
     "jlp_illumina_to_memory", "jlp_illumina_stream", "jlp_illumina_device_only", "jlp_illumina_group_counts", "jlp_apportion", "jlp_shard_range", "jlp_deflate", "jlp_bgzf_device", "jlp_pacbio", "jlp_pacbio_to_memory", "jlp_pacbio_read_plan", "jlp_pacbio_sample", "jlp_reads_per_group", "jlp_alias_build",
     "jlp_threshold", "jlp_unif_expr", "jlp_frag_table", "jlp_philox4x32_10", "jlp_draw_pos", "jlp_draw_pair",
@@ -84,6 +84,9 @@ def lib():
     L = C.CDLL(LIB_PATH)
     pp = C.POINTER(C.c_char_p)
     L.jlp_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    L.jlp_ctx_create_multi.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p)]
+    L.jlp_ctx_n_devices.argtypes = [C.c_void_p]
+    L.jlp_materialize_haplotypes.argtypes = [C.c_void_p]
     L.jlp_ctx_destroy.argtypes = [C.c_void_p]
     L.jlp_ctx_destroy.restype = None
     L.jlp_last_error.argtypes = [C.c_void_p]

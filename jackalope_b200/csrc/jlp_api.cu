@@ -11,8 +11,10 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <cerrno>
+#include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <functional>
@@ -185,11 +187,25 @@ bool map_range(int fd, uint64_t off, uint64_t n, Mapping& m) {
     return true;
 }
 
-struct HapDev {
+// AllMutations of one haplotype chromosome (src/hap_classes.h:100-104) as the library keeps them on the host:
+// a haplotype chromosome is materialised on a device only when a run's pair range touches it (SURVEY.md 8e:
+// "each GPU needs only the haplotypes its range touches"), so the records outlive jlp_add_haplotype.
+struct HapChromHost {
+    uint64_t size = 0;                                   // mutated chromosome size
+    std::vector<uint64_t> old_pos, new_pos, nuc_off;
+    std::vector<int64_t> size_mod;                       // size_modifier per record, src/hap_classes.h:314-333
+    std::vector<uint8_t> pool;
+};
+struct HapStore {
     std::string name;
-    std::vector<const uint8_t*> seq;    // per chromosome; aliases the reference when unmutated
+    std::vector<HapChromHost> chrom;
+};
+struct HapDev {
+    std::shared_ptr<HapStore> store;    // shared by the devices of a multi-GPU context
+    std::vector<const uint8_t*> seq;    // per chromosome; aliases the reference when unmutated; NULL = not materialised yet
     std::vector<uint64_t> len;
     std::vector<uint8_t*> owned;        // device allocations to free
+    const std::string& name() const { return store->name; }
 };
 
 struct Slot {
@@ -211,12 +227,16 @@ struct Slot {
     std::atomic<int> writes{0};   // slices of h_out still being written to / compressed for the files
     std::vector<std::vector<uint8_t>> zout[2];   // compressed slices of the batch, in file order
     Mapping map[2];               // the file ranges this batch is being copied into
+    uint64_t file_end[2] = {0, 0};  // where this batch ends in the files (plain FASTQ)
 };
 
 }  // namespace
 
 struct jlp_ctx {
     int device = 0;
+    // a multi-GPU context (jlp_ctx_create_multi) owns one child context per device and no device state of its own:
+    // it keeps the genome / haplotype metadata (names, sizes) and fans every call out to its children
+    std::vector<jlp_ctx*> kids;
     std::string err;
     cudaStream_t s_compute = nullptr, s_copy = nullptr;
     // genome
@@ -246,6 +266,10 @@ struct jlp_ctx {
     std::vector<char> chrom_resident;           // 1: the chromosome's H2D copy has been issued
     cudaEvent_t ev_run[2] = {nullptr, nullptr};
     uint64_t h2d_bytes = 0;
+    // scratch of the haplotype materialisation (mutation records of one chromosome)
+    DevBuf<uint64_t> m_old, m_new, m_off;
+    DevBuf<int64_t> m_sm;
+    DevBuf<uint8_t> m_pool;
 };
 
 namespace {
@@ -263,7 +287,7 @@ int fail(jlp_ctx* c, int code, const std::string& msg) {
 
 template <typename F> int guarded(jlp_ctx* c, F f) {
     try {
-        if (c) CK(cudaSetDevice(c->device));
+        if (c && c->kids.empty()) CK(cudaSetDevice(c->device));
         f();
         return JLP_OK;
     } catch (const ArgErr& e) { return fail(c, JLP_ERR_ARG, e.what());
@@ -272,6 +296,30 @@ template <typename F> int guarded(jlp_ctx* c, F f) {
     } catch (const Unsupported& e) { return fail(c, JLP_ERR_UNSUPPORTED, e.what());
     } catch (const Aborted& e) { return fail(c, JLP_ERR_ABORTED, e.what());
     } catch (const std::exception& e) { return fail(c, JLP_ERR_ARG, e.what()); }
+}
+
+// the context itself, or the first child of a multi-GPU context (made current): calls that do not spread over devices
+jlp_ctx* first_device(jlp_ctx* c) {
+    if (c->kids.empty()) return c;
+    CK(cudaSetDevice(c->kids[0]->device));
+    return c->kids[0];
+}
+// f(device context) for the context itself, or for every child of a multi-GPU context (current device set)
+template <typename F> void for_each_device(jlp_ctx* c, F f) {
+    if (c->kids.empty()) { f(c); return; }
+    for (jlp_ctx* k : c->kids) { CK(cudaSetDevice(k->device)); f(k); }
+}
+// the same, one host thread per device; the first error (if any) is rethrown as a runtime_error of its text
+template <typename F> void for_each_device_parallel(jlp_ctx* c, F f) {
+    if (c->kids.size() <= 1) { for_each_device(c, f); return; }
+    std::vector<std::string> errs(c->kids.size());
+    std::vector<std::thread> th;
+    for (size_t r = 0; r < c->kids.size(); r++)
+        th.emplace_back([&, r]() {
+            try { CK(cudaSetDevice(c->kids[r]->device)); f(c->kids[r]); } catch (const std::exception& e) { errs[r] = e.what(); if (errs[r].empty()) errs[r] = "error"; }
+        });
+    for (std::thread& t : th) t.join();
+    for (const std::string& e : errs) if (!e.empty()) throw CudaErr(e);
 }
 
 // Issue the H2D copies of chromosomes [first, last] of a deferred genome upload (those not
@@ -310,7 +358,9 @@ struct Sink {
     void* chunk_user = nullptr;
     // files
     int fd[2] = {-1, -1};
-    uint64_t pos[2] = {0, 0};
+    uint64_t pos[2] = {0, 0};        // where the next batch goes
+    uint64_t done[2] = {0, 0};       // end of the last batch known to be completely written (error paths truncate back to it)
+    bool own_size[2] = {false, false};   // this call extends the file itself (not a pre-sized file shared with other devices)
     std::string names[2];
     void close_files() {
         for (int e = 0; e < 2; e++) if (fd[e] >= 0) { ::close(fd[e]); fd[e] = -1; }
@@ -362,7 +412,8 @@ std::vector<std::vector<uint64_t>> apportion_sizes(uint64_t seed, uint64_t n_pai
     return out;
 }
 
-std::vector<std::vector<uint64_t>> apportion(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, uint64_t n_pairs) {
+// needs only the sizes: works on a multi-GPU parent context (metadata, no device state) as well
+std::vector<std::vector<uint64_t>> apportion(const jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, uint64_t n_pairs) {
     const uint64_t n_chroms = c->chrom_off.size() - 1;
     std::vector<uint64_t> sizes;
     if (!use_haps) {
@@ -374,14 +425,36 @@ std::vector<std::vector<uint64_t>> apportion(jlp_ctx* c, bool use_haps, const jl
     return apportion_sizes(P->seed, n_pairs, c->haps.size(), n_chroms, P->haplotype_probs, sizes.data());
 }
 
-void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jlp_run_stats* stats) {
+// How a run's compressed output is produced (write_reads_cpp_, src/hts.h:441-500): compressed + one thread -> the
+// method asked for; compressed + several threads -> always bgzip (the reference writes plain files first and bgzips
+// them afterwards; here the batches are compressed on their way to the file).  comp_engine picks who compresses:
+// the device coder (BGZF members of one dynamic-Huffman block each, jlp_bgzf.cu; only compressed bytes cross PCIe)
+// or zlib on the writer threads at the level asked for.  AUTO uses the device coder only where the reference itself
+// would write BGZF (comp_method "bgzip", or several threads) at levels 1..6; a gzip request with one thread is a
+// gzip stream from zlib (FileGZ, src/io.h:140-236).  Memory and stream sinks receive compressed bytes only when the
+// device coder is asked for explicitly.
+struct Compression {
+    bool dev_z = false;       // BGZF on the device
+    int zmethod = -1;         // host zlib: DEFLATE_BGZF / DEFLATE_GZIP; -1 = none
+    bool want_gz = false;     // file names get ".gz"
+};
+Compression compression_of(const jlp_illumina_params* P, SinkKind kind) {
+    Compression z;
+    if (P->compress <= 0) return z;
+    const std::string m = P->comp_method ? P->comp_method : "";
+    const bool bgzip = P->n_threads > 1 || m == "bgzip";
+    z.want_gz = true;
+    z.dev_z = P->comp_engine == JLP_COMP_DEVICE || (P->comp_engine == JLP_COMP_AUTO && P->compress <= 6 && kind == SINK_FILES && bgzip);
+    if (!z.dev_z) z.zmethod = bgzip ? DEFLATE_BGZF : DEFLATE_GZIP;
+    return z;
+}
+
+// the argument checks the C++ layer of the reference performs, plus the ranges of the additions
+void check_params(const jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, SinkKind kind) {
     if (!P) throw ArgErr("params is NULL");
     const int n_ends = P->paired || P->matepair ? 2 : 1;
-    const bool matepair = P->matepair != 0;
-    // --- argument checks the C++ layer of the reference performs
     if (c->chrom_off.size() < 2) throw ArgErr("no reference genome has been set");
     if (use_haps && c->haps.empty()) throw ArgErr("no haplotypes have been added");
-    if (use_haps) finish_upload(c);
     if (!c->have_prof[0]) throw ArgErr("no quality profile for read 1");
     if (n_ends == 2) {
         if (!c->have_prof[1]) throw ArgErr("no quality profile for read 2");
@@ -394,19 +467,7 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
         if (P->compress > 9) throw ArgErr("\nInvalid bgzip compress level of " + std::to_string(P->compress) +
                                           ". It must be in range [0,9].");                   // src/io.h:113-117
     }
-    // write_reads_cpp_ (src/hts.h:441-500): compressed + one thread -> the method asked for;
-    // compressed + several threads -> always bgzip (the reference writes plain files first and
-    // bgzips them afterwards; here the batches are compressed on their way to the file)
-    // comp_engine picks who compresses: the device coder (BGZF members of one dynamic-Huffman block each, jlp_bgzf.cu;
-    // only compressed bytes cross PCIe) or zlib on the writer threads at the level asked for.  Memory and stream
-    // sinks receive compressed bytes only when the device coder is asked for explicitly.
     if (P->comp_engine < JLP_COMP_AUTO || P->comp_engine > JLP_COMP_DEVICE) throw ArgErr("comp_engine must be 0 (auto), 1 (host) or 2 (device)");
-    const bool dev_z = P->compress > 0 && (P->comp_engine == JLP_COMP_DEVICE ||
-                                           (P->comp_engine == JLP_COMP_AUTO && P->compress <= 6 && sink.kind == SINK_FILES));
-    const bool want_gz = P->compress > 0;
-    const int zmethod = P->compress <= 0 || dev_z ? -1
-                        : (P->n_threads > 1 || std::string(P->comp_method ? P->comp_method : "") == "bgzip") ? DEFLATE_BGZF
-                                                                                                            : DEFLATE_GZIP;
     if (!(P->prob_dup >= 0 && P->prob_dup <= 1)) throw ArgErr("prob_dup must be in [0,1]");
     const double insp[2] = {P->ins_prob1, P->ins_prob2}, delp[2] = {P->del_prob1, P->del_prob2};
     for (int e = 0; e < n_ends; e++)
@@ -416,13 +477,31 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
         throw ArgErr("frag_len_min must be >= 1 and <= frag_len_max");
     if (!(P->frag_len_shape > 0 && P->frag_len_scale > 0)) throw ArgErr("fragment Gamma shape and scale must be > 0");
     if (P->read_pool_size < 1) throw ArgErr("read_pool_size must be >= 1");
-    if (sink.kind == SINK_FILES && (!P->out_prefix || !*P->out_prefix)) throw ArgErr("out_prefix is empty");
-    const uint32_t L = (uint32_t)c->tab[0].L;
-    const uint64_t n_haps = c->haps.size();
-    const uint64_t n_chroms = c->chrom_off.size() - 1;
-    const bool sep = use_haps && P->sep_files;
+    if (kind == SINK_FILES && (!P->out_prefix || !*P->out_prefix)) throw ArgErr("out_prefix is empty");
     if (use_haps && !P->haplotype_probs) throw ArgErr("haplotype_probs is NULL");
+    if (P->shard_count > 1 && P->shard_index >= P->shard_count) throw ArgErr("shard_index >= shard_count");
+}
 
+// The (haplotype, chromosome) groups of a run in the order the reference exhausts them (hap-major, chrom-major:
+// src/hts_illumina.cpp:199-201, :505-528), their pair-index prefix offsets, ID-line prefixes and barcodes, and the
+// jobs (= sets of output files).  A pure function of the parameters and of the sizes the context knows, so every
+// device of a multi-GPU run builds the same one.
+struct Layout {
+    int n_ends = 1;
+    uint64_t n_pairs = 0;
+    std::vector<uint64_t> group_off;      // [n_groups + 1]
+    std::vector<GroupDev> groups;         // seq is filled in per device
+    std::vector<uint32_t> group_hap, group_chrom;
+    std::vector<uint8_t> strpool;
+    std::vector<Job> jobs;
+};
+
+Layout make_layout(const jlp_ctx* c, bool use_haps, const jlp_illumina_params* P) {
+    Layout Y;
+    Y.n_ends = P->paired || P->matepair ? 2 : 1;
+    const uint32_t L = (uint32_t)c->tab[0].L;
+    const uint64_t n_haps = c->haps.size(), n_chroms = c->chrom_off.size() - 1;
+    const bool sep = use_haps && P->sep_files;
     // --- barcodes (T/C/A/G only, R/hts_illumina.R:385-391)
     std::vector<std::string> barcodes(use_haps ? n_haps : 1);
     if (P->barcodes)
@@ -432,48 +511,133 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
             if (ch != 'T' && ch != 'C' && ch != 'A' && ch != 'G') throw ArgErr("barcodes may only contain T, C, A, G");
         if (bcs.size() >= L) throw ArgErr("a barcode is as long as the read");
     }
-
     // --- apportion pairs: threads -> haplotypes -> chromosomes
     //     (write_reads_one_filetype_ src/hts.h:334-353, add_n_reads src/hts_illumina.h:410-418, :620-644,
     //      write_reads_cpp_sep_files_ src/hts.h:527-529); one "thread", n_pairs = floor(n_reads / n_ends)
-    const uint64_t n_pairs = P->n_reads / n_ends;
-    const std::vector<std::vector<uint64_t>> counts = apportion(c, use_haps, P, n_pairs);
-
-    std::vector<uint64_t> group_off(1, 0);
-    std::vector<GroupDev> groups;
-    std::vector<uint8_t> strpool;
-    std::vector<Job> jobs;
-    uint64_t min_len_with_reads = ~0ull;
-    auto add_group = [&](const std::string& gname, uint64_t chrom, const uint8_t* seq, uint64_t len,
-                         const std::string& bc, uint64_t count) {
+    Y.n_pairs = P->n_reads / Y.n_ends;
+    const std::vector<std::vector<uint64_t>> counts = apportion(c, use_haps, P, Y.n_pairs);
+    Y.group_off.assign(1, 0);
+    auto add_group = [&](const std::string& gname, uint32_t hap, uint64_t chrom, uint64_t len, const std::string& bc, uint64_t count) {
         GroupDev g;
         std::string pre = "@" + gname + "-" + c->chrom_names[chrom] + "-";
-        g.seq = seq; g.len = len;
-        g.prefix_off = (uint32_t)strpool.size(); g.prefix_len = (uint32_t)pre.size();
-        strpool.insert(strpool.end(), pre.begin(), pre.end());
-        g.bc_off = (uint32_t)strpool.size(); g.bc_len = (uint32_t)bc.size();
-        strpool.insert(strpool.end(), bc.begin(), bc.end());
-        groups.push_back(g);
-        group_off.push_back(group_off.back() + count);
-        if (count > 0 && len < min_len_with_reads) min_len_with_reads = len;
+        g.seq = nullptr; g.len = len;
+        g.prefix_off = (uint32_t)Y.strpool.size(); g.prefix_len = (uint32_t)pre.size();
+        Y.strpool.insert(Y.strpool.end(), pre.begin(), pre.end());
+        g.bc_off = (uint32_t)Y.strpool.size(); g.bc_len = (uint32_t)bc.size();
+        Y.strpool.insert(Y.strpool.end(), bc.begin(), bc.end());
+        Y.groups.push_back(g);
+        Y.group_hap.push_back(hap); Y.group_chrom.push_back((uint32_t)chrom);
+        Y.group_off.push_back(Y.group_off.back() + count);
         if (count > 0 && len == 0) throw ArgErr("a chromosome of length 0 was given reads");
     };
     const std::string prefix = P->out_prefix ? P->out_prefix : "";
     if (!use_haps) {
         for (uint64_t i = 0; i < n_chroms; i++)
-            add_group(c->genome_name, i, c->genome.p + kPad + c->chrom_off[i], c->chrom_off[i + 1] - c->chrom_off[i],
-                      barcodes[0], counts[0][i]);
-        jobs.push_back(Job{0, n_pairs, prefix});
+            add_group(c->genome_name, 0, i, c->chrom_off[i + 1] - c->chrom_off[i], barcodes[0], counts[0][i]);
+        Y.jobs.push_back(Job{0, Y.n_pairs, prefix});
     } else {
         for (uint64_t h = 0; h < n_haps; h++) {
             const HapDev& H = c->haps[h];
-            uint64_t lo = group_off.back();
-            for (uint64_t i = 0; i < n_chroms; i++) add_group(H.name, i, H.seq[i], H.len[i], barcodes[h], counts[h][i]);
-            if (sep) jobs.push_back(Job{lo, group_off.back(), prefix + "_" + H.name});
+            uint64_t lo = Y.group_off.back();
+            for (uint64_t i = 0; i < n_chroms; i++) add_group(H.name(), (uint32_t)h, i, H.len[i], barcodes[h], counts[h][i]);
+            if (sep) Y.jobs.push_back(Job{lo, Y.group_off.back(), prefix + "_" + H.name()});
         }
-        if (!sep) jobs.push_back(Job{0, group_off.back(), prefix});
+        if (!sep) Y.jobs.push_back(Job{0, Y.group_off.back(), prefix});
     }
-    if (group_off.back() != n_pairs) throw std::runtime_error("internal: apportioning does not add up");
+    if (Y.group_off.back() != Y.n_pairs) throw std::runtime_error("internal: apportioning does not add up");
+    return Y;
+}
+
+// name of output file `e` of a job (src/hts.h:344; ".gz" appended by FileGZ / FileBGZF, src/io.h:126,217).
+// A process that generates one shard of a run (shard_count > 1, one process per GPU) writes its own files,
+// <prefix>[_<hap>]_R<k>.fq[.gz].shard<i>of<n>: concatenated in shard order they are the unsharded run's file.
+std::string file_name(const Job& job, int e, bool gz, const jlp_illumina_params* P) {
+    std::string n = job.file_prefix + "_R" + std::to_string(e + 1) + ".fq";
+    if (gz) n += ".gz";
+    if (P->shard_count > 1) n += ".shard" + std::to_string(P->shard_index) + "of" + std::to_string(P->shard_count);
+    return n;
+}
+
+// Materialise haplotype chromosome (h, ci) on this context's device if it is not resident yet
+// (HapChrom::get_chrom_full, src/hap_classes.cpp:80-116).
+void ensure_hap_chrom(jlp_ctx* c, size_t h, size_t ci) {
+    HapDev& H = c->haps[h];
+    if (H.seq[ci]) return;
+    const HapChromHost& M = H.store->chrom[ci];
+    const uint64_t ref_size = c->chrom_off[ci + 1] - c->chrom_off[ci];
+    const uint8_t* ref = c->genome.p + kPad + c->chrom_off[ci];
+    c->m_old.upload(M.old_pos, c->s_compute); c->m_new.upload(M.new_pos, c->s_compute); c->m_off.upload(M.nuc_off, c->s_compute);
+    c->m_sm.upload(M.size_mod, c->s_compute); c->m_pool.upload(M.pool, c->s_compute);
+    c->h2d_bytes += M.old_pos.size() * 32 + M.pool.size();
+    uint8_t* out = nullptr;
+    CK(cudaMalloc(reinterpret_cast<void**>(&out), M.size + 2 * kPad));
+    H.owned.push_back(out);
+    CK(launch_materialize(ref, ref_size, M.old_pos.size(), c->m_old.p, c->m_new.p, c->m_sm.p, c->m_off.p, c->m_pool.p, M.size,
+                          out + kPad, c->s_compute));
+    CK(cudaStreamSynchronize(c->s_compute));      // the scratch buffers are reused by the next chromosome
+    H.seq[ci] = out + kPad;
+}
+
+typedef std::vector<std::pair<uint64_t, uint64_t>> Ranges;
+typedef std::vector<std::array<uint64_t, 2>> PerJobBytes;
+
+// What a multi-GPU run tells each of its devices (jlp_ctx_create_multi); a plain call leaves everything empty.
+struct RunExtras {
+    const Ranges* ranges = nullptr;       // [jobs] the pair range of every job this call generates (else: the shard of P)
+    PerJobBytes* sizes_out = nullptr;     // size pass: only count the FASTQ bytes per job and end of those ranges
+    const PerJobBytes* base = nullptr;    // [jobs] where this call's bytes start in each job's files / in the memory sink
+    bool shared_files = false;            // the files exist, created and sized by the caller: open without truncating, no EOF block
+    std::string part_suffix;              // compressed multi-GPU runs: this call writes <name><suffix>, joined by the caller
+};
+
+void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jlp_run_stats* stats, const RunExtras& X = RunExtras()) {
+    check_params(c, use_haps, P, sink.kind);
+    const int n_ends = P->paired || P->matepair ? 2 : 1;
+    const bool matepair = P->matepair != 0;
+    if (use_haps) finish_upload(c);
+    const uint64_t h2d_before = c->h2d_bytes;
+    const Compression Z = compression_of(P, sink.kind);
+    const bool dev_z = Z.dev_z, want_gz = Z.want_gz;
+    const int zmethod = Z.zmethod;
+    const bool sizes_only = X.sizes_out != nullptr;
+    const double insp[2] = {P->ins_prob1, P->ins_prob2}, delp[2] = {P->del_prob1, P->del_prob2};
+    const uint32_t L = (uint32_t)c->tab[0].L;
+
+    Layout Y = make_layout(c, use_haps, P);
+    const std::vector<uint64_t>& group_off = Y.group_off;
+    std::vector<GroupDev>& groups = Y.groups;
+    const std::vector<Job>& jobs = Y.jobs;
+
+    // --- the pair range of every job this call generates
+    Ranges ranges;
+    if (X.ranges) ranges = *X.ranges;
+    else {
+        const uint32_t S = P->shard_count > 1 ? P->shard_count : 1, si = P->shard_count > 1 ? P->shard_index : 0;
+        for (const Job& j : jobs) { uint64_t lo, hi; shard_range(j.lo, j.hi, si, S, lo, hi); ranges.emplace_back(lo, hi); }
+    }
+    if (ranges.size() != jobs.size()) throw std::runtime_error("internal: one range per job");
+    const uint64_t pool_pairs = (P->read_pool_size + n_ends - 1) / n_ends;   // pool closes at >= read_pool_size reads
+    // groups a range reads: those of its pairs, and through a duplicate chain's leader possibly the one before
+    // (a leader lies at most pool_pairs - 1 pairs before its duplicate, never before the job's start)
+    auto groups_of = [&](const Job& job, uint64_t lo, uint64_t hi, size_t& g_lo, size_t& g_hi) {
+        const uint64_t first_pair = lo - std::min<uint64_t>(lo - job.lo, pool_pairs - 1);
+        g_lo = (size_t)(std::upper_bound(group_off.begin(), group_off.end(), first_pair) - group_off.begin()) - 1;
+        g_hi = (size_t)(std::upper_bound(group_off.begin(), group_off.end(), hi - 1) - group_off.begin()) - 1;
+        g_hi = std::min(g_hi, groups.size() - 1);
+        g_lo = std::min(g_lo, g_hi);
+    };
+    // --- sequences: the reference's chromosomes, or the haplotype chromosomes the ranges touch (materialised now)
+    if (!use_haps) {
+        for (size_t g = 0; g < groups.size(); g++) groups[g].seq = c->genome.p + kPad + c->chrom_off[g];
+    } else {
+        for (size_t k = 0; k < jobs.size(); k++) {
+            if (ranges[k].second <= ranges[k].first) continue;
+            size_t g_lo, g_hi;
+            groups_of(jobs[k], ranges[k].first, ranges[k].second, g_lo, g_hi);
+            for (size_t g = g_lo; g <= g_hi; g++) ensure_hap_chrom(c, Y.group_hap[g], Y.group_chrom[g]);
+        }
+        for (size_t g = 0; g < groups.size(); g++) groups[g].seq = c->haps[Y.group_hap[g]].seq[Y.group_chrom[g]];
+    }
 
     // --- thresholds
     GenParams gp;
@@ -481,7 +645,7 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
     gp.seed = P->seed;
     philox_round_keys(P->seed, gp.rk);
     gp.n_ends = n_ends; gp.L = L; gp.matepair = matepair;
-    gp.pool_pairs = (P->read_pool_size + n_ends - 1) / n_ends;   // pool closes at >= read_pool_size reads
+    gp.pool_pairs = pool_pairs;
     Thr td = thr_double_lt(P->prob_dup);
     gp.c_dup = td.thr; gp.dup_never = td.thr == 0;
     gp.c_rev = thr_ld_lt(0.5).thr;
@@ -503,28 +667,30 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
     c->d_frag_guide.upload(guide, c->s_compute);
     c->d_group_off.upload(group_off, c->s_compute);
     c->d_groups.upload(groups, c->s_compute);
-    c->d_strpool.upload(strpool, c->s_compute);
+    c->d_strpool.upload(Y.strpool, c->s_compute);
     c->d_status.ensure(1);
     CK(cudaMemsetAsync(c->d_status.p, 0, sizeof(uint32_t), c->s_compute));
-    c->h2d_bytes += frag.size() * 8 + group_off.size() * 8 + groups.size() * sizeof(GroupDev) + strpool.size();
+    c->h2d_bytes += frag.size() * 8 + group_off.size() * 8 + groups.size() * sizeof(GroupDev) + Y.strpool.size();
     gp.frag_cdf = c->d_frag.p; gp.frag_guide = c->d_frag_guide.p; gp.frag_n = (uint32_t)frag.size(); gp.frag_min = P->frag_len_min;
     gp.group_off = c->d_group_off.p; gp.n_groups = (uint32_t)groups.size();
     gp.groups = c->d_groups.p; gp.strpool = c->d_strpool.p; gp.status = c->d_status.p;
 
     // --- batch buffers
-    uint64_t max_job = 0;
-    for (const Job& j : jobs) max_job = std::max(max_job, j.hi - j.lo);
+    uint64_t max_range = 0;
+    for (const auto& r : ranges) max_range = std::max(max_range, r.second - r.first);
     uint64_t B = P->batch_pairs ? P->batch_pairs : (1ull << 20);
-    B = std::max<uint64_t>(1, std::min(B, max_job));
+    B = std::max<uint64_t>(1, std::min(B, max_range));
     uint32_t max_prefix = 0;
     for (const GroupDev& g : groups) max_prefix = std::max(max_prefix, g.prefix_len);
     const uint64_t max_rec = (uint64_t)max_prefix + 20 + 5 + 2ull * L + 4;
     gp.rec_buf = (uint32_t)((max_rec + 64 + 15) & ~15ull);
-    gp.tpl_buf = (L + 34u + 15u) & ~15u;        // the template, its slack to 16-byte alignment, the word over-read   // + alignment pad, gather overrun, copy-out over-read
+    gp.tpl_buf = (L + 34u + 15u) & ~15u;        // the template, its slack to 16-byte alignment, the word over-read
+    if (!sizes_only && !reads_fits(gp)) throw Unsupported("read_length " + std::to_string(L) + " (with these chromosome names) needs more shared memory per "
+                                                          "read pair than one SM has: the read kernel cannot hold such a record");
     const uint64_t n_rec_max = B * n_ends;
     const uint32_t nsb_max = (uint32_t)((B + kScanBlock - 1) / kScanBlock);
-    const bool need_host = sink.kind != SINK_NONE;
-    const uint32_t nblk_max = dev_z ? (uint32_t)((B * max_rec + kBgzfIn - 1) / kBgzfIn) + 1 : 0;
+    const bool need_host = sink.kind != SINK_NONE && !sizes_only;
+    const uint32_t nblk_max = dev_z && !sizes_only ? (uint32_t)((B * max_rec + kBgzfIn - 1) / kBgzfIn) + 1 : 0;
     for (Slot& s : c->slot) {
         s.plan.ensure(n_rec_max);
         s.rec_len.ensure(n_rec_max);
@@ -534,11 +700,11 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
         s.totals.ensure(4);
         s.h_totals.ensure(4);
         CK(cudaMemsetAsync(s.totals.p, 0, 4 * sizeof(uint64_t), c->s_compute));
-        for (int e = 0; e < n_ends; e++) {
+        for (int e = 0; e < n_ends && !sizes_only; e++) {
             s.out[e].ensure(B * max_rec + 64);
             if (need_host) s.h_out[e].ensure(dev_z ? (size_t)nblk_max * kBgzfSlot : B * max_rec);
         }
-        if (dev_z)
+        if (dev_z && !sizes_only)
             for (int e = 0; e < 2; e++) {
                 s.zslots[e].ensure((size_t)nblk_max * kBgzfSlot);
                 s.zdev[e].ensure((size_t)nblk_max * kBgzfSlot);
@@ -553,9 +719,12 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
     std::memset(&st, 0, sizeof st);
 
     // If the run ends by an exception, nothing of it may stay in flight: kernels and copies still use the
-    // slots, writer tasks still hold the file descriptors the caller's Sink is about to close.
+    // slots, writer tasks still hold the file descriptors the caller's Sink is about to close.  Files this call
+    // extends itself are cut back to the last completely written batch (an extended, never filled tail would
+    // otherwise stay behind as zero bytes).
     struct Quiesce {
         jlp_ctx* c;
+        Sink* sink;
         bool armed = true;
         ~Quiesce() {
             if (!armed) return;
@@ -568,8 +737,11 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
                 s.zout[0].clear(); s.zout[1].clear();
             }
             c->writers.clear_error();
+            if (sink->kind == SINK_FILES)
+                for (int e = 0; e < 2; e++)
+                    if (sink->fd[e] >= 0 && sink->own_size[e] && ::ftruncate(sink->fd[e], (off_t)sink->done[e]) != 0) { /* best effort */ }
         }
-    } quiesce{c};
+    } quiesce{c, &sink};
 
     auto wait_writes = [&](Slot& s) {
         if (sink.kind != SINK_FILES) return;
@@ -584,9 +756,11 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
                 sink.pos[k] += v.size();
             }
             s.zout[k].clear();
+            if (s.file_end[k] > sink.done[k]) sink.done[k] = s.file_end[k];
+            if (zmethod >= 0) sink.done[k] = sink.pos[k];
         }
     };
-    if (sink.kind == SINK_FILES) c->writers.start((size_t)std::min<uint64_t>(std::max<uint64_t>(P->n_threads, 1), 64));
+    if (sink.kind == SINK_FILES && !sizes_only) c->writers.start((size_t)std::min<uint64_t>(std::max<uint64_t>(P->n_threads, 1), 64));
     uint64_t job_index = 0;
     Slot* z_pending = nullptr;      // the batch whose compressed slices are not in the files yet
     // stage 2 of a batch: its kernels are done -> statistics, then its FASTQ starts its way to the host
@@ -623,16 +797,16 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
             if (zmethod >= 0 && z_pending) { wait_writes(*z_pending); z_pending = nullptr; }   // files stay in batch order
             for (int e = 0; e < n_ends; e++) {
                 const uint64_t n = dev_z ? s.ztot[e] : s.tot[e];
+                s.file_end[e] = 0;
                 if (sink.kind == SINK_FILES && zmethod < 0) {
-                    // R1 and R2 stay record-aligned: both files receive the same batches in the same order
-                    // with several writer threads the file is extended first and the slices are copied into
-                    // mappings of it; with one thread, when the file system is nearly full (a write() reports
-                    // ENOSPC, a mapping would fault) or when the file cannot be extended, plain pwrite
+                    // R1 and R2 stay record-aligned: both files receive the same batches in the same order.
+                    // With several writer threads the file's new range is reserved (posix_fallocate: a full file
+                    // system is an error here, not a SIGBUS in a writer thread later) and the slices are copied into
+                    // a mapping of it; with one thread, or when the range cannot be reserved or mapped, plain pwrite.
                     bool mapped = P->n_threads > 1 && n > 0;
                     if (mapped) {
-                        struct statvfs vfs;
-                        mapped = ::fstatvfs(sink.fd[e], &vfs) == 0 && (uint64_t)vfs.f_bavail * vfs.f_frsize > 2 * n + (64ull << 20) &&
-                                 ::ftruncate(sink.fd[e], (off_t)(sink.pos[e] + n)) == 0 && map_range(sink.fd[e], sink.pos[e], n, s.map[e]);
+                        if (sink.own_size[e]) mapped = ::posix_fallocate(sink.fd[e], (off_t)sink.pos[e], (off_t)n) == 0;
+                        mapped = mapped && map_range(sink.fd[e], sink.pos[e], n, s.map[e]);
                     }
                     const uint64_t slice = 8ull << 20;
                     for (uint64_t o = 0; o < n; o += slice) {
@@ -644,6 +818,7 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
                         else c->writers.submit(&s.writes, [fd, src, len, off]() { return pwrite_all(fd, src, len, off); });
                     }
                     sink.pos[e] += n;
+                    s.file_end[e] = sink.pos[e];
                 } else if (sink.kind == SINK_FILES) {
                     // compressed: the writer threads deflate slices of whole members; their output is
                     // written in order once the batch is done (wait_writes)
@@ -673,25 +848,43 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
     };
 
     std::vector<char> chrom_waited(c->chrom_ev.size(), 0);
-    const uint32_t S = P->shard_count > 1 ? P->shard_count : 1;
-    const uint32_t si = P->shard_count > 1 ? P->shard_index : 0;
-    if (si >= S) throw ArgErr("shard_index >= shard_count");
+    if (sizes_only) X.sizes_out->assign(jobs.size(), std::array<uint64_t, 2>{0, 0});
 
-    for (const Job& job : jobs) {
+    for (size_t jk = 0; jk < jobs.size(); jk++) {
+        const Job& job = jobs[jk];
+        const uint64_t lo = ranges[jk].first, hi = ranges[jk].second;
         if (P->abort_cb && P->abort_cb(P->cb_user)) throw Aborted();   // src/hts.h:536
-        if (sink.kind == SINK_FILES) {
+        if (X.ranges && hi <= lo) { job_index++; continue; }             // a multi-GPU device with no part in this job's files
+        if (sink.kind == SINK_FILES && !sizes_only) {
             for (Slot& s : c->slot) wait_writes(s);
             sink.close_files();
-            sink.pos[0] = sink.pos[1] = 0;
             for (int e = 0; e < n_ends; e++) {
-                sink.names[e] = job.file_prefix + "_R" + std::to_string(e + 1) + ".fq";   // src/hts.h:344
-                if (want_gz) sink.names[e] += ".gz";                                      // src/io.h:126,217
-                sink.fd[e] = ::open(sink.names[e].c_str(), O_RDWR | O_CREAT | O_TRUNC, 0644);
+                sink.names[e] = file_name(job, e, want_gz, P) + X.part_suffix;
+                sink.pos[e] = sink.done[e] = X.base ? (*X.base)[jk][e] : 0;
+                sink.own_size[e] = !X.shared_files;
+                sink.fd[e] = ::open(sink.names[e].c_str(), X.shared_files ? O_RDWR : (O_RDWR | O_CREAT | O_TRUNC), 0644);
                 if (sink.fd[e] < 0) throw IoErr("Unable to open file " + sink.names[e] + ".\n");  // src/io.h:288-290
             }
         }
-        uint64_t lo, hi;
-        shard_range(job.lo, job.hi, si, S, lo, hi);
+        if (sink.kind == SINK_MEMORY && X.base) for (int e = 0; e < n_ends; e++) sink.len[e] = (*X.base)[jk][e];
+        if (sizes_only) {
+            // size pass: placement and scan only; the totals come back batch by batch (a few hundred microseconds each)
+            for (uint64_t b0 = lo; b0 < hi; b0 += B) {
+                Slot& s = c->slot[0];
+                const uint32_t np = (uint32_t)std::min<uint64_t>(B, hi - b0);
+                gp.job_lo = job.lo; gp.job_hi = job.hi; gp.batch_lo = b0; gp.batch_pairs = np;
+                gp.plan = s.plan.p; gp.rec_len = s.rec_len.p; gp.rec_local = s.rec_local.p; gp.block_base = s.block_base.p;
+                gp.n_scan_blocks = (np + kScanBlock - 1) / kScanBlock;
+                CK(launch_place(gp, c->s_compute));
+                CK(launch_scan(s.rec_len.p, np * n_ends, n_ends, s.rec_local.p, s.block_tot.p, s.block_base.p, s.totals.p, c->s_compute));
+                CK(cudaMemcpyAsync(s.h_totals.p, s.totals.p, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->s_compute));
+                CK(cudaStreamSynchronize(c->s_compute));
+                for (int e = 0; e < n_ends; e++) (*X.sizes_out)[jk][e] += s.h_totals.p[e];
+                st.kernel_launches += 3; st.pairs += np; st.batches++;
+            }
+            job_index++;
+            continue;
+        }
         // three batches in flight: batch b computes while b-1 crosses PCIe and b-2 is handed to the sink
         std::deque<Slot*> computing, copying;
         auto drain_one = [&]() {
@@ -704,18 +897,15 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
             while (s.busy) drain_one();
             const uint32_t np = (uint32_t)std::min<uint64_t>(B, hi - b0);
             if (c->upload_pending && !use_haps) {
-                // the batch reads the chromosomes of its pairs, and through a duplicate chain's leader
-                // possibly the one before: make the compute stream wait for exactly those uploads
-                // (a leader lies at most pool_pairs - 1 pairs before its duplicate, never before the job's start)
-                const uint64_t first_pair = b0 - std::min<uint64_t>(b0 - job.lo, gp.pool_pairs - 1);
-                size_t g_lo = (size_t)(std::upper_bound(group_off.begin(), group_off.end(), first_pair) - group_off.begin()) - 1;
-                size_t g_hi = (size_t)(std::upper_bound(group_off.begin(), group_off.end(), b0 + np - 1) - group_off.begin()) - 1;
+                // make the compute stream wait for exactly the uploads of the chromosomes this batch reads
+                size_t g_lo, g_hi;
+                groups_of(job, b0, b0 + np, g_lo, g_hi);
                 g_hi = std::min(g_hi, c->chrom_ev.size() - 1);
                 g_lo = std::min(g_lo, g_hi);
                 if (b0 == lo) {
-                    // first batch of this shard of the job: a deferred upload copies, in the order the shard
-                    // will read them, all the chromosomes the shard reads and nothing else (with N GPUs each
-                    // needs about 1/N of the genome); the rest stays on the host until some run asks for it
+                    // first batch of this call's part of the job: a deferred upload copies, in the order the part
+                    // will read them, all the chromosomes it reads and nothing else (with N GPUs each needs about
+                    // 1/N of the genome); the rest stays on the host until some run asks for it
                     size_t g_end = (size_t)(std::upper_bound(group_off.begin(), group_off.end(), hi - 1) - group_off.begin()) - 1;
                     issue_upload(c, g_lo, std::min(g_end, c->chrom_ev.size() - 1));
                 }
@@ -750,20 +940,18 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
             // the previous batch's copy is queued before the one in flight is waited for
             if (computing.size() > 1) { issue_copy(*computing.front()); copying.push_back(computing.front()); computing.pop_front(); }
             if (copying.size() > 1) { deliver(*copying.front()); copying.pop_front(); }
-            if (P->abort_cb && P->abort_cb(P->cb_user)) {
-                for (Slot& t : c->slot) if (t.busy) { cudaEventSynchronize(t.ev[5]); cudaStreamSynchronize(c->s_copy); t.busy = false; }
-                for (Slot& t : c->slot) c->writers.wait(t.writes);
-                throw Aborted();
-            }
+            if (P->abort_cb && P->abort_cb(P->cb_user)) throw Aborted();   // Quiesce settles what is in flight
         }
         while (!computing.empty() || !copying.empty()) drain_one();
         if (z_pending) { wait_writes(*z_pending); z_pending = nullptr; }
         for (Slot& s : c->slot) wait_writes(s);
-        if (sink.kind == SINK_FILES && (zmethod == DEFLATE_BGZF || dev_z))
+        const bool eof_block = !X.shared_files && X.part_suffix.empty();      // a multi-GPU run appends it once, after joining the parts
+        if (sink.kind == SINK_FILES && (zmethod == DEFLATE_BGZF || dev_z) && eof_block)
             for (int e = 0; e < n_ends; e++) {   // bgzf_close appends the empty end-of-file block
                 std::string w = pwrite_all(sink.fd[e], kBgzfEof, sizeof kBgzfEof, sink.pos[e]);
                 if (!w.empty()) throw IoErr("Error writing to file " + sink.names[e] + ": " + w);
                 sink.pos[e] += sizeof kBgzfEof;
+                sink.done[e] = sink.pos[e];
             }
         if (dev_z && sink.kind == SINK_STREAM)
             for (int e = 0; e < n_ends; e++)
@@ -796,9 +984,222 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
     uint32_t status = 0;
     CK(cudaMemcpy(&status, c->d_status.p, sizeof status, cudaMemcpyDeviceToHost));
     if (status & 1u) throw ArgErr("a barcode is at least as long as a read's template (fragment or chromosome too short)");
-    st.h2d_bytes = c->h2d_bytes;
+    st.h2d_bytes = c->h2d_bytes - h2d_before;      // of this call (a deferred genome upload it performed included)
     if (stats) *stats = st;
     quiesce.armed = false;
+}
+
+// ------------------------------------------------- one call, several GPUs ---
+//
+// The reference splits a run over its threads and keeps ONE ordered set of files inside one call
+// (write_reads_one_filetype_, src/hts.h:334-353 split, :401-416 both pools written together;
+// write_reads_cpp_sep_files_, :512-552).  A multi-GPU context does the same over devices: the run's pair-index
+// space [0, n_pairs) is cut into near-equal contiguous pieces, one per device (a piece may cover several
+// haplotypes' jobs with sep_files, and a job may have several writers); every device runs the three-stage batch
+// pipeline of run() on its piece from its own host thread.  No data moves between the devices (no collective):
+//   plain FASTQ   a size pass (placement + scan only, a few hundred microseconds per batch) tells every device how
+//                 many bytes it will write per job and file, so the devices write into disjoint ranges of the
+//                 same, pre-sized R1 / R2 files (or of the caller's memory buffers) -- R1 and R2 stay aligned;
+//   compressed    sizes are not known beforehand: device r writes whole BGZF members into <file>.part<r>, the
+//                 parts are joined in device order (copy_file_range) and the EOF block is appended once.
+// Only the haplotype chromosomes a device's piece touches are materialised there (ensure_hap_chrom).
+// Callbacks run on the calling thread only (R is single-threaded): the device threads count progress in an atomic
+// and poll an abort flag; the calling thread polls both while it waits.
+
+struct MultiShared {
+    std::atomic<uint64_t> progress{0};
+    std::atomic<int> abort{0};
+};
+int multi_abort_cb(void* u) { return static_cast<MultiShared*>(u)->abort.load(std::memory_order_relaxed); }
+void multi_progress_cb(void* u, uint64_t reads) { static_cast<MultiShared*>(u)->progress.fetch_add(reads, std::memory_order_relaxed); }
+
+std::string copy_range(int out_fd, int in_fd, uint64_t n) {
+    std::vector<uint8_t> buf;
+    while (n) {
+        ssize_t w = ::copy_file_range(in_fd, nullptr, out_fd, nullptr, (size_t)std::min<uint64_t>(n, 1ull << 30), 0);
+        if (w < 0 && (errno == EXDEV || errno == EINVAL || errno == ENOSYS || errno == EOPNOTSUPP)) {
+            // file systems without copy_file_range: read + write
+            buf.resize(8u << 20);
+            ssize_t r = ::read(in_fd, buf.data(), (size_t)std::min<uint64_t>(n, buf.size()));
+            if (r < 0) { if (errno == EINTR) continue; return std::strerror(errno); }
+            if (r == 0) return "unexpected end of a part file";
+            for (ssize_t o = 0; o < r;) {
+                ssize_t x = ::write(out_fd, buf.data() + o, (size_t)(r - o));
+                if (x < 0) { if (errno == EINTR) continue; return std::strerror(errno); }
+                o += x;
+            }
+            n -= (uint64_t)r;
+            continue;
+        }
+        if (w < 0) { if (errno == EINTR) continue; return std::strerror(errno); }
+        if (w == 0) return "unexpected end of a part file";
+        n -= (uint64_t)w;
+    }
+    return std::string();
+}
+
+void run_multi(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jlp_run_stats* stats) {
+    check_params(c, use_haps, P, sink.kind);
+    if (sink.kind == SINK_STREAM)
+        throw Unsupported("jlp_illumina_stream on a multi-GPU context: batches of several devices have no single order; "
+                          "use files / memory, or one context per device with shard_index / shard_count");
+    if (P->shard_count > 1) throw ArgErr("shard_index / shard_count do not combine with a multi-GPU context");
+    const size_t N = c->kids.size();
+    const Layout Y = make_layout(c, use_haps, P);
+    const size_t nj = Y.jobs.size();
+    const int n_ends = Y.n_ends;
+    const Compression Z = compression_of(P, sink.kind);
+    if (Z.want_gz && Z.dev_z && sink.kind == SINK_MEMORY)
+        throw Unsupported("compressed output into memory on a multi-GPU context");
+    const bool sized = sink.kind == SINK_MEMORY || (sink.kind == SINK_FILES && !Z.want_gz);   // plain bytes at known offsets
+    const bool parts = sink.kind == SINK_FILES && Z.want_gz;
+
+    // --- the devices' pieces of the pair-index space, per job
+    std::vector<Ranges> ranges(N, Ranges(nj));
+    for (size_t r = 0; r < N; r++) {
+        uint64_t glo, ghi;
+        shard_range(0, Y.n_pairs, (uint32_t)r, (uint32_t)N, glo, ghi);
+        for (size_t k = 0; k < nj; k++) {
+            const uint64_t lo = std::min(std::max(glo, Y.jobs[k].lo), Y.jobs[k].hi), hi = std::min(std::max(ghi, Y.jobs[k].lo), Y.jobs[k].hi);
+            ranges[r][k] = {lo, std::max(lo, hi)};
+        }
+    }
+
+    MultiShared shared;
+    jlp_illumina_params Pk = *P;
+    Pk.shard_index = 0; Pk.shard_count = 0;
+    Pk.abort_cb = multi_abort_cb; Pk.progress_cb = multi_progress_cb; Pk.cb_user = &shared;
+    Pk.n_threads = P->n_threads <= 1 ? 1 : std::max<uint64_t>(2, (P->n_threads + N - 1) / N);   // host writer threads per device
+
+    std::vector<std::string> errs(N);
+    std::vector<int> codes(N, JLP_OK);
+    std::vector<jlp_run_stats> st(N);
+    // run f(r) for every device on its own thread; the calling thread serves the callbacks meanwhile
+    auto on_devices = [&](const std::function<void(size_t)>& f, bool with_callbacks) {
+        std::atomic<size_t> left{N};
+        std::vector<std::thread> th;
+        for (size_t r = 0; r < N; r++)
+            th.emplace_back([&, r]() {
+                codes[r] = guarded(c->kids[r], [&]() { f(r); });
+                if (codes[r] != JLP_OK) { errs[r] = c->kids[r]->err; shared.abort.store(1); }    // the others stop at their next batch
+                left.fetch_sub(1);
+            });
+        while (left.load() != 0) {
+            std::this_thread::sleep_for(std::chrono::milliseconds(with_callbacks ? 20 : 2));
+            if (!with_callbacks) continue;
+            const uint64_t d = shared.progress.exchange(0);
+            if (d && P->progress_cb) P->progress_cb(P->cb_user, d);
+            if (P->abort_cb && !shared.abort.load() && P->abort_cb(P->cb_user)) shared.abort.store(2);
+        }
+        for (std::thread& t : th) t.join();
+        const uint64_t d = shared.progress.exchange(0);
+        if (d && P->progress_cb && with_callbacks) P->progress_cb(P->cb_user, d);
+        if (shared.abort.load() == 2) throw Aborted();
+        for (size_t r = 0; r < N; r++) {
+            if (codes[r] == JLP_OK || codes[r] == JLP_ERR_ABORTED) continue;      // a device aborted because another failed
+            const std::string m = "device " + std::to_string(c->kids[r]->device) + ": " + errs[r];
+            switch (codes[r]) {
+            case JLP_ERR_ARG: throw ArgErr(errs[r]);
+            case JLP_ERR_IO: throw IoErr(errs[r]);
+            case JLP_ERR_UNSUPPORTED: throw Unsupported(errs[r]);
+            default: throw CudaErr(m);
+            }
+        }
+    };
+
+    // --- size pass
+    std::vector<PerJobBytes> sizes(N), base(N, PerJobBytes(nj, std::array<uint64_t, 2>{0, 0}));
+    std::vector<std::array<uint64_t, 2>> job_total(nj, std::array<uint64_t, 2>{0, 0});
+    uint64_t launches = 0;
+    if (sized) {
+        on_devices([&](size_t r) {
+            Sink none;
+            RunExtras X;
+            X.ranges = &ranges[r]; X.sizes_out = &sizes[r];
+            run(c->kids[r], use_haps, &Pk, none, &st[r], X);
+        }, false);
+        uint64_t mem_off[2] = {0, 0};
+        for (size_t k = 0; k < nj; k++)
+            for (int e = 0; e < n_ends; e++) {
+                uint64_t o = sink.kind == SINK_MEMORY ? mem_off[e] : 0;      // memory: the jobs' outputs are concatenated
+                for (size_t r = 0; r < N; r++) { base[r][k][e] = o; o += sizes[r][k][e]; }
+                job_total[k][e] = o - (sink.kind == SINK_MEMORY ? mem_off[e] : 0);
+                mem_off[e] += job_total[k][e];
+            }
+        for (size_t r = 0; r < N; r++) launches += st[r].kernel_launches;
+        if (sink.kind == SINK_FILES)
+            for (size_t k = 0; k < nj; k++)
+                for (int e = 0; e < n_ends; e++) {
+                    const std::string name = file_name(Y.jobs[k], e, false, P);
+                    const int fd = ::open(name.c_str(), O_RDWR | O_CREAT | O_TRUNC, 0644);
+                    if (fd < 0) throw IoErr("Unable to open file " + name + ".\n");      // src/io.h:288-290
+                    int rc = job_total[k][e] ? ::posix_fallocate(fd, 0, (off_t)job_total[k][e]) : 0;
+                    if (rc == EOPNOTSUPP || rc == EINVAL) rc = ::ftruncate(fd, (off_t)job_total[k][e]) == 0 ? 0 : errno;
+                    ::close(fd);
+                    if (rc != 0) throw IoErr("Error writing to file " + name + ": " + std::strerror(rc));
+                }
+        if (sink.kind == SINK_MEMORY) { sink.len[0] = mem_off[0]; sink.len[1] = mem_off[1]; }
+    }
+
+    // --- the run proper
+    struct Cleanup {       // part files never outlive the call
+        std::vector<std::string> names;
+        ~Cleanup() { for (const std::string& n : names) ::unlink(n.c_str()); }
+    } cleanup;
+    if (parts)
+        for (size_t r = 0; r < N; r++)
+            for (size_t k = 0; k < nj; k++)
+                if (ranges[r][k].second > ranges[r][k].first)
+                    for (int e = 0; e < n_ends; e++) cleanup.names.push_back(file_name(Y.jobs[k], e, true, P) + ".part" + std::to_string(r));
+    on_devices([&](size_t r) {
+        Sink sk;
+        sk.kind = sink.kind;
+        for (int e = 0; e < 2; e++) { sk.mem[e] = sink.mem[e]; sk.cap[e] = sink.cap[e]; }
+        RunExtras X;
+        X.ranges = &ranges[r];
+        if (sized) { X.base = &base[r]; X.shared_files = sink.kind == SINK_FILES; }
+        if (parts) X.part_suffix = ".part" + std::to_string(r);
+        run(c->kids[r], use_haps, &Pk, sk, &st[r], X);
+    }, true);
+
+    // --- compressed: join the parts in device order, one end-of-file block per file
+    if (parts)
+        for (size_t k = 0; k < nj; k++)
+            for (int e = 0; e < n_ends; e++) {
+                const std::string name = file_name(Y.jobs[k], e, true, P);
+                const int fd = ::open(name.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+                if (fd < 0) throw IoErr("Unable to open file " + name + ".\n");
+                std::string w;
+                for (size_t r = 0; r < N && w.empty(); r++) {
+                    if (ranges[r][k].second <= ranges[r][k].first) continue;
+                    const std::string part = name + ".part" + std::to_string(r);
+                    const int in = ::open(part.c_str(), O_RDONLY);
+                    struct stat sb;
+                    if (in < 0 || ::fstat(in, &sb) != 0) { w = "cannot read " + part; if (in >= 0) ::close(in); break; }
+                    w = copy_range(fd, in, (uint64_t)sb.st_size);
+                    ::close(in);
+                }
+                if (w.empty() && (Z.dev_z || Z.zmethod == DEFLATE_BGZF)) {
+                    const off_t end = ::lseek(fd, 0, SEEK_END);
+                    w = end < 0 ? std::string(std::strerror(errno)) : pwrite_all(fd, kBgzfEof, sizeof kBgzfEof, (uint64_t)end);
+                }
+                ::close(fd);
+                if (!w.empty()) throw IoErr("Error writing to file " + name + ": " + w);
+            }
+
+    jlp_run_stats tot;
+    std::memset(&tot, 0, sizeof tot);
+    for (size_t r = 0; r < N; r++) {
+        tot.pairs += st[r].pairs; tot.batches += st[r].batches; tot.kernel_launches += st[r].kernel_launches;
+        for (int e = 0; e < 2; e++) { tot.bytes_out[e] += st[r].bytes_out[e]; tot.z_bytes[e] += st[r].z_bytes[e]; }
+        tot.d2h_bytes += st[r].d2h_bytes; tot.h2d_bytes += st[r].h2d_bytes;
+        // device time: the slowest device's (they work side by side)
+        tot.device_ms = std::max(tot.device_ms, st[r].device_ms); tot.place_ms = std::max(tot.place_ms, st[r].place_ms);
+        tot.reads_ms = std::max(tot.reads_ms, st[r].reads_ms); tot.bgzf_ms = std::max(tot.bgzf_ms, st[r].bgzf_ms);
+        tot.run_ms = std::max(tot.run_ms, st[r].run_ms);
+    }
+    tot.kernel_launches += launches;
+    if (stats) *stats = tot;
 }
 
 }  // namespace
@@ -831,8 +1232,38 @@ int jlp_ctx_create(int device, jlp_ctx** out) {
     return JLP_OK;
 }
 
+int jlp_ctx_create_multi(int n_devices, const int* devices, jlp_ctx** out) {
+    if (!out) return fail(nullptr, JLP_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, JLP_ERR_NO_DEVICE, std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                                                    "); this library has no CPU fallback");
+    if (n_devices < 0 || n_devices > n) return fail(nullptr, JLP_ERR_ARG, "more devices asked for than are visible");
+    if (n_devices == 0) { n_devices = n; devices = nullptr; }
+    std::unique_ptr<jlp_ctx> c(new jlp_ctx);
+    c->device = -1;
+    for (int i = 0; i < n_devices; i++) {
+        const int d = devices ? devices[i] : i;
+        jlp_ctx* k = nullptr;
+        const int rc = jlp_ctx_create(d, &k);
+        if (rc != JLP_OK) { for (jlp_ctx* q : c->kids) jlp_ctx_destroy(q); return rc; }
+        c->kids.push_back(k);
+    }
+    *out = c.release();
+    return JLP_OK;
+}
+
+int jlp_ctx_n_devices(const jlp_ctx* c) { return c ? (c->kids.empty() ? 1 : (int)c->kids.size()) : 0; }
+
 void jlp_ctx_destroy(jlp_ctx* c) {
     if (!c) return;
+    if (!c->kids.empty()) {
+        for (jlp_ctx* k : c->kids) jlp_ctx_destroy(k);
+        delete c;
+        return;
+    }
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     free_haps(c);
@@ -851,6 +1282,19 @@ const char* jlp_last_error(const jlp_ctx* c) { return c ? c->err.c_str() : g_cre
 static int set_genome_impl(jlp_ctx* c, const char* bases, const uint64_t* chrom_off, uint64_t n_chroms,
                            const char* const* chrom_names, const char* genome_name, bool wait) {
     if (!c) return JLP_ERR_ARG;
+    if (!c->kids.empty()) {
+        // every device gets a deferred upload (a run copies only the chromosomes the device's piece reads); the
+        // synchronous form then makes the whole genome resident everywhere, one host thread per device
+        return guarded(c, [&]() {
+            for (jlp_ctx* k : c->kids) {
+                const int rc = set_genome_impl(k, bases, chrom_off, n_chroms, chrom_names, genome_name, false);
+                if (rc != JLP_OK) throw ArgErr(k->err);
+            }
+            c->haps.clear();
+            c->chrom_off = c->kids[0]->chrom_off; c->chrom_names = c->kids[0]->chrom_names; c->genome_name = c->kids[0]->genome_name;
+            if (wait) for_each_device_parallel(c, [](jlp_ctx* d) { finish_upload(d); });
+        });
+    }
     return guarded(c, [&]() {
         if (!bases || !chrom_off || !chrom_names || n_chroms == 0) throw ArgErr("empty genome");
         for (uint64_t i = 0; i < n_chroms; i++)
@@ -897,13 +1341,22 @@ int jlp_set_genome_async(jlp_ctx* c, const char* bases, const uint64_t* chrom_of
 int jlp_genome_sync(jlp_ctx* c) {
     if (!c) return JLP_ERR_ARG;
     return guarded(c, [&]() {
-        finish_upload(c);
+        for_each_device_parallel(c, [](jlp_ctx* d) { finish_upload(d); });
     });
 }
 
 int jlp_create_genome(jlp_ctx* c, uint64_t n_chroms, const uint64_t* lens, const double* pi_tcag, uint64_t seed,
                       const char* const* chrom_names, const char* genome_name) {
     if (!c) return JLP_ERR_ARG;
+    if (!c->kids.empty())        // the same seed gives every device the same genome: generated in place everywhere, nothing copied
+        return guarded(c, [&]() {
+            for (jlp_ctx* k : c->kids) {
+                const int rc = jlp_create_genome(k, n_chroms, lens, pi_tcag, seed, chrom_names, genome_name);
+                if (rc != JLP_OK) throw ArgErr(k->err);
+            }
+            c->haps.clear();
+            c->chrom_off = c->kids[0]->chrom_off; c->chrom_names = c->kids[0]->chrom_names; c->genome_name = c->kids[0]->genome_name;
+        });
     return guarded(c, [&]() {
         if (!lens || !pi_tcag || n_chroms == 0) throw ArgErr("empty genome");
         double tot = 0;
@@ -938,6 +1391,11 @@ int jlp_create_genome(jlp_ctx* c, uint64_t n_chroms, const uint64_t* lens, const
 
 int jlp_get_genome(jlp_ctx* c, char* out, uint64_t cap, uint64_t* len) {
     if (!c) return JLP_ERR_ARG;
+    if (!c->kids.empty()) {
+        const int rc = jlp_get_genome(c->kids[0], out, cap, len);
+        if (rc != JLP_OK) c->err = c->kids[0]->err;
+        return rc;
+    }
     return guarded(c, [&]() {
         if (c->chrom_off.size() < 2) throw ArgErr("no reference genome has been set");
         finish_upload(c);
@@ -951,7 +1409,59 @@ int jlp_get_genome(jlp_ctx* c, char* out, uint64_t cap, uint64_t* len) {
 
 int jlp_clear_haplotypes(jlp_ctx* c) {
     if (!c) return JLP_ERR_ARG;
-    return guarded(c, [&]() { free_haps(c); });
+    return guarded(c, [&]() {
+        for_each_device(c, [](jlp_ctx* d) { free_haps(d); });
+        c->haps.clear();
+    });
+}
+
+// the host-side store of one haplotype: a copy of the caller's AllMutations arrays + size_modifier per record
+static std::shared_ptr<HapStore> make_hap_store(const jlp_ctx* c, const char* name, const uint64_t* n_muts, const uint64_t* const* old_pos,
+                                                const uint64_t* const* new_pos, const uint64_t* const* nuc_off,
+                                                const char* const* nuc_pool, const uint64_t* nuc_pool_len, const uint64_t* chrom_sizes) {
+    if (c->chrom_off.size() < 2) throw ArgErr("set the reference genome first");
+    if (!n_muts || !chrom_sizes) throw ArgErr("n_muts / chrom_sizes is NULL");
+    const uint64_t nc = c->chrom_off.size() - 1;
+    auto S = std::make_shared<HapStore>();
+    S->name = name ? name : "";
+    S->chrom.resize(nc);
+    for (uint64_t ci = 0; ci < nc; ci++) {
+        const uint64_t M = n_muts[ci];
+        const uint64_t ref_size = c->chrom_off[ci + 1] - c->chrom_off[ci];
+        HapChromHost& H = S->chrom[ci];
+        H.size = chrom_sizes[ci];
+        if (M == 0) {   // get_chrom_full returns the reference string (src/hap_classes.cpp:82)
+            if (chrom_sizes[ci] != ref_size) throw ArgErr("chromosome without mutations must keep the reference size");
+            continue;
+        }
+        if (!old_pos || !new_pos || !nuc_off || !nuc_pool || !nuc_pool_len || !old_pos[ci] || !new_pos[ci] || !nuc_off[ci])
+            throw ArgErr("mutation arrays are NULL");
+        // size_modifier per record, src/hap_classes.h:314-333
+        H.size_mod.resize(M);
+        for (uint64_t i = 0; i < M; i++) {
+            if (i && new_pos[ci][i] < new_pos[ci][i - 1]) throw ArgErr("mutations must be sorted by new_pos");
+            int64_t s = (i + 1 < M) ? (int64_t)(new_pos[ci][i + 1] - old_pos[ci][i + 1]) : (int64_t)(chrom_sizes[ci] - ref_size);
+            H.size_mod[i] = s + (int64_t)(old_pos[ci][i] - new_pos[ci][i]);
+        }
+        H.old_pos.assign(old_pos[ci], old_pos[ci] + M);
+        H.new_pos.assign(new_pos[ci], new_pos[ci] + M);
+        H.nuc_off.assign(nuc_off[ci], nuc_off[ci] + M);
+        H.pool.assign(nuc_pool[ci], nuc_pool[ci] + nuc_pool_len[ci]);
+    }
+    return S;
+}
+
+// attach a haplotype to a context: unmutated chromosomes alias the reference, the others wait for a run to touch them
+static void attach_hap(jlp_ctx* c, const std::shared_ptr<HapStore>& S) {
+    HapDev H;
+    H.store = S;
+    const bool device = c->kids.empty();
+    for (size_t ci = 0; ci < S->chrom.size(); ci++) {
+        const HapChromHost& M = S->chrom[ci];
+        H.len.push_back(M.size);
+        H.seq.push_back(device && M.old_pos.empty() ? c->genome.p + kPad + c->chrom_off[ci] : nullptr);
+    }
+    c->haps.push_back(std::move(H));
 }
 
 int jlp_add_haplotype(jlp_ctx* c, const char* name, const uint64_t* n_muts, const uint64_t* const* old_pos,
@@ -960,64 +1470,36 @@ int jlp_add_haplotype(jlp_ctx* c, const char* name, const uint64_t* n_muts, cons
                       const uint64_t* chrom_sizes, uint64_t* hap_index) {
     if (!c) return JLP_ERR_ARG;
     return guarded(c, [&]() {
-        if (c->chrom_off.size() < 2) throw ArgErr("set the reference genome first");
-        if (!n_muts || !chrom_sizes) throw ArgErr("n_muts / chrom_sizes is NULL");
-        finish_upload(c);
-        const uint64_t nc = c->chrom_off.size() - 1;
-        HapDev H;
-        H.name = name ? name : "";
-        DevBuf<uint64_t> d_old, d_new, d_off;
-        DevBuf<int64_t> d_sm;
-        DevBuf<uint8_t> d_pool;
-        try {
-            for (uint64_t ci = 0; ci < nc; ci++) {
-                const uint64_t M = n_muts[ci];
-                const uint64_t ref_size = c->chrom_off[ci + 1] - c->chrom_off[ci];
-                const uint8_t* ref = c->genome.p + kPad + c->chrom_off[ci];
-                if (M == 0) {   // get_chrom_full returns the reference string (src/hap_classes.cpp:82)
-                    if (chrom_sizes[ci] != ref_size) throw ArgErr("chromosome without mutations must keep the reference size");
-                    H.seq.push_back(ref); H.len.push_back(ref_size);
-                    continue;
-                }
-                // size_modifier per record, src/hap_classes.h:314-333
-                std::vector<int64_t> sm(M);
-                for (uint64_t i = 0; i < M; i++) {
-                    if (i && new_pos[ci][i] < new_pos[ci][i - 1]) throw ArgErr("mutations must be sorted by new_pos");
-                    int64_t s = (i + 1 < M) ? (int64_t)(new_pos[ci][i + 1] - old_pos[ci][i + 1])
-                                            : (int64_t)(chrom_sizes[ci] - ref_size);
-                    sm[i] = s + (int64_t)(old_pos[ci][i] - new_pos[ci][i]);
-                }
-                std::vector<uint64_t> vo(old_pos[ci], old_pos[ci] + M), vn(new_pos[ci], new_pos[ci] + M),
-                    vf(nuc_off[ci], nuc_off[ci] + M);
-                std::vector<uint8_t> vp(nuc_pool[ci], nuc_pool[ci] + nuc_pool_len[ci]);
-                d_old.upload(vo, c->s_compute); d_new.upload(vn, c->s_compute); d_off.upload(vf, c->s_compute);
-                d_sm.upload(sm, c->s_compute); d_pool.upload(vp, c->s_compute);
-                c->h2d_bytes += M * 32 + vp.size();
-                uint8_t* out = nullptr;
-                CK(cudaMalloc(reinterpret_cast<void**>(&out), chrom_sizes[ci] + 2 * kPad));
-                H.owned.push_back(out);
-                CK(launch_materialize(ref, ref_size, M, d_old.p, d_new.p, d_sm.p, d_off.p, d_pool.p, chrom_sizes[ci],
-                                      out + kPad, c->s_compute));
-                CK(cudaStreamSynchronize(c->s_compute));
-                H.seq.push_back(out + kPad); H.len.push_back(chrom_sizes[ci]);
-            }
-        } catch (...) {
-            for (uint8_t* p : H.owned) cudaFree(p);
-            throw;
-        }
+        std::shared_ptr<HapStore> S = make_hap_store(c, name, n_muts, old_pos, new_pos, nuc_off, nuc_pool, nuc_pool_len, chrom_sizes);
         if (hap_index) *hap_index = c->haps.size();
-        c->haps.push_back(std::move(H));
+        attach_hap(c, S);
+        for (jlp_ctx* k : c->kids) attach_hap(k, S);
+    });
+}
+
+int jlp_materialize_haplotypes(jlp_ctx* c) {
+    if (!c) return JLP_ERR_ARG;
+    return guarded(c, [&]() {
+        for_each_device(c, [&](jlp_ctx* d) {
+            finish_upload(d);
+            for (size_t h = 0; h < d->haps.size(); h++)
+                for (size_t ci = 0; ci < d->haps[h].seq.size(); ci++) ensure_hap_chrom(d, h, ci);
+        });
     });
 }
 
 int jlp_get_haplotype_chrom(jlp_ctx* c, uint64_t hap, uint64_t chrom, char* out, uint64_t cap, uint64_t* len) {
     if (!c) return JLP_ERR_ARG;
     return guarded(c, [&]() {
-        if (hap >= c->haps.size() || chrom >= c->haps[hap].seq.size()) throw ArgErr("haplotype / chromosome index out of range");
-        uint64_t n = c->haps[hap].len[chrom];
+        jlp_ctx* d = c->kids.empty() ? c : c->kids[0];
+        if (!c->kids.empty()) CK(cudaSetDevice(d->device));
+        if (hap >= d->haps.size() || chrom >= d->haps[hap].seq.size()) throw ArgErr("haplotype / chromosome index out of range");
+        uint64_t n = d->haps[hap].len[chrom];
         if (len) *len = n;
         if (n > cap) throw ArgErr("output buffer too small");
-        if (n) CK(cudaMemcpy(out, c->haps[hap].seq[chrom], n, cudaMemcpyDeviceToHost));
+        finish_upload(d);
+        ensure_hap_chrom(d, hap, chrom);
+        if (n) CK(cudaMemcpy(out, d->haps[hap].seq[chrom], n, cudaMemcpyDeviceToHost));
     });
 }
 
@@ -1029,6 +1511,14 @@ int jlp_set_profile(jlp_ctx* c, int end, uint64_t read_length, const uint32_t* n
         if (!nq || !probs || !quals) throw ArgErr("profile arrays are NULL");
         if (read_length >= 65536) throw ArgErr("read_length too large");
         build_end_tables(read_length, nq, probs, quals, c->tab[end]);
+        if (!c->kids.empty()) {        // the parent keeps the host tables (read length, checks); every device gets its copy
+            for (jlp_ctx* k : c->kids) {
+                const int rc = jlp_set_profile(k, end, read_length, nq, probs, quals);
+                if (rc != JLP_OK) throw ArgErr(k->err);
+            }
+            c->have_prof[end] = true;
+            return;
+        }
         const EndTables& t = c->tab[end];
         c->d_meta[end].upload(t.meta, c->s_compute);
         c->d_entry64[end].upload(t.entry64, c->s_compute);
@@ -1040,13 +1530,18 @@ int jlp_set_profile(jlp_ctx* c, int end, uint64_t read_length, const uint32_t* n
     });
 }
 
+static void run_any(jlp_ctx* c, bool use_haps, const jlp_illumina_params* p, Sink& s, jlp_run_stats* stats) {
+    if (c->kids.empty()) run(c, use_haps, p, s, stats);
+    else run_multi(c, use_haps, p, s, stats);
+}
+
 int jlp_illumina_ref(jlp_ctx* c, const jlp_illumina_params* p, jlp_run_stats* stats) {
     if (!c) return JLP_ERR_ARG;
-    return guarded(c, [&]() { Sink s; s.kind = SINK_FILES; run(c, false, p, s, stats); });
+    return guarded(c, [&]() { Sink s; s.kind = SINK_FILES; run_any(c, false, p, s, stats); });
 }
 int jlp_illumina_hap(jlp_ctx* c, const jlp_illumina_params* p, jlp_run_stats* stats) {
     if (!c) return JLP_ERR_ARG;
-    return guarded(c, [&]() { Sink s; s.kind = SINK_FILES; run(c, true, p, s, stats); });
+    return guarded(c, [&]() { Sink s; s.kind = SINK_FILES; run_any(c, true, p, s, stats); });
 }
 
 int jlp_illumina_to_memory(jlp_ctx* c, int use_haplotypes, const jlp_illumina_params* p, char* out1, uint64_t cap1,
@@ -1057,7 +1552,7 @@ int jlp_illumina_to_memory(jlp_ctx* c, int use_haplotypes, const jlp_illumina_pa
         s.kind = SINK_MEMORY;
         s.mem[0] = out1; s.cap[0] = out1 ? cap1 : 0;
         s.mem[1] = out2; s.cap[1] = out2 ? cap2 : 0;
-        run(c, use_haplotypes != 0, p, s, stats);
+        run_any(c, use_haplotypes != 0, p, s, stats);
         if (len1) *len1 = s.len[0];
         if (len2) *len2 = s.len[1];
         if (s.len[0] > s.cap[0] || s.len[1] > s.cap[1]) throw ArgErr("output buffer too small");
@@ -1071,13 +1566,13 @@ int jlp_illumina_stream(jlp_ctx* c, int use_haplotypes, const jlp_illumina_param
         if (!cb) throw ArgErr("chunk callback is NULL");
         Sink s;
         s.kind = SINK_STREAM; s.chunk_cb = cb; s.chunk_user = user;
-        run(c, use_haplotypes != 0, p, s, stats);
+        run_any(c, use_haplotypes != 0, p, s, stats);
     });
 }
 
 int jlp_illumina_device_only(jlp_ctx* c, int use_haplotypes, const jlp_illumina_params* p, jlp_run_stats* stats) {
     if (!c) return JLP_ERR_ARG;
-    return guarded(c, [&]() { Sink s; s.kind = SINK_NONE; run(c, use_haplotypes != 0, p, s, stats); });
+    return guarded(c, [&]() { Sink s; s.kind = SINK_NONE; run_any(c, use_haplotypes != 0, p, s, stats); });
 }
 
 int jlp_illumina_group_counts(jlp_ctx* c, int use_haplotypes, const jlp_illumina_params* p, uint64_t* counts,
@@ -1163,8 +1658,11 @@ PbGroups pb_groups(jlp_ctx* c, bool use_haps, const jlp_pacbio_params* P) {
     } else {
         for (uint64_t h = 0; h < n_haps; h++) {
             const uint64_t lo = G.group_off.back();
-            for (uint64_t i = 0; i < n_chroms; i++) add(c->haps[h].name, i, c->haps[h].seq[i], c->haps[h].len[i], counts[h][i]);
-            if (P->sep_files) G.jobs.push_back(Job{lo, G.group_off.back(), prefix + "_" + c->haps[h].name});
+            for (uint64_t i = 0; i < n_chroms; i++) {
+                if (counts[h][i]) ensure_hap_chrom(c, h, i);        // materialised when first read from
+                add(c->haps[h].name(), i, c->haps[h].seq[i], c->haps[h].len[i], counts[h][i]);
+            }
+            if (P->sep_files) G.jobs.push_back(Job{lo, G.group_off.back(), prefix + "_" + c->haps[h].name()});
         }
         if (!P->sep_files) G.jobs.push_back(Job{0, G.group_off.back(), prefix});
     }
@@ -1385,7 +1883,8 @@ int jlp_pacbio(jlp_ctx* c, int use_haplotypes, const jlp_pacbio_params* p, jlp_r
     if (!c) return JLP_ERR_ARG;
     return guarded(c, [&]() {
         if (!p || !p->out_prefix || !*p->out_prefix) throw ArgErr("out_prefix is empty");
-        run_pacbio(c, use_haplotypes != 0, p, SINK_FILES, nullptr, 0, nullptr, stats);
+        jlp_ctx* d = first_device(c);
+        run_pacbio(d, use_haplotypes != 0, p, SINK_FILES, nullptr, 0, nullptr, stats);
     });
 }
 
@@ -1394,7 +1893,8 @@ int jlp_pacbio_to_memory(jlp_ctx* c, int use_haplotypes, const jlp_pacbio_params
     if (!c) return JLP_ERR_ARG;
     return guarded(c, [&]() {
         uint64_t need = 0;
-        run_pacbio(c, use_haplotypes != 0, p, out ? SINK_MEMORY : SINK_NONE, out, cap, &need, stats);
+        jlp_ctx* d = first_device(c);
+        run_pacbio(d, use_haplotypes != 0, p, out ? SINK_MEMORY : SINK_NONE, out, cap, &need, stats);
         if (len) *len = need;
         if (out && need > cap) throw ArgErr("output buffer too small");
     });
@@ -1406,7 +1906,7 @@ int jlp_pacbio_read_plan(jlp_ctx* c, int use_haplotypes, const jlp_pacbio_params
     return guarded(c, [&]() {
         PbModel model;
         pb_model_from(p, model);
-        const PbGroups G = pb_groups(c, use_haplotypes != 0, p);
+        const PbGroups G = pb_groups(first_device(c), use_haplotypes != 0, p);
         const Thr t_dup = thr_double_lt(p->prob_dup);
         const bool dups = t_dup.thr != 0 || t_dup.all;
         for (const Job& job : G.jobs) {
@@ -1470,6 +1970,7 @@ int jlp_bgzf_device(jlp_ctx* c, int level, const void* in, uint64_t n, void* out
     if (!c) return JLP_ERR_ARG;
     return guarded(c, [&]() {
         if ((n && !in) || !len) throw ArgErr("NULL argument");
+        c = first_device(c);
         const uint32_t nblk = (uint32_t)((n + kBgzfIn - 1) / kBgzfIn);
         DevBuf<uint8_t> d_in, d_slots, d_out;
         DevBuf<uint32_t> d_zlen;

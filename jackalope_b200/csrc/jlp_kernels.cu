@@ -18,6 +18,8 @@
 #include "jlp_kernels.cuh"
 #include "jlp_draws.h"
 
+#include <algorithm>
+
 namespace jlp {
 
 // ------------------------------------------------------------ materialise ---
@@ -817,13 +819,32 @@ static size_t reads_table_bytes(const GenParams& p) {
     return b;
 }
 
+// Threads per CTA of k_reads for this run: the most warps (at most kReadsThreads / 32) whose record and staging
+// buffers fit the shared memory of one SM -- together with the profile tables when those fit too (at least 8 warps
+// then), else with the tables read from global memory.  0: not even one warp's buffers fit (a custom profile with
+// a read length of several thousand).
+static int reads_threads(const GenParams& p, bool& use_smem) {
+    const size_t per_warp = reads_warp_bytes(p.n_ends, p.rec_buf, p.tpl_buf), tab = reads_table_bytes(p);
+    const size_t with_tab = 200 * 1024, without = 226 * 1024;
+    const int max_w = kReadsThreads / 32;
+    int w = (int)std::min<size_t>(max_w, tab < with_tab ? (with_tab - tab) / per_warp : 0);
+    if (w >= 8) { use_smem = true; return 32 * w; }
+    use_smem = false;
+    w = (int)std::min<size_t>(max_w, without / per_warp);
+    return 32 * w;
+}
+bool reads_fits(const GenParams& p) {
+    bool u;
+    return reads_threads(p, u) > 0;
+}
+
 cudaError_t launch_reads(const GenParams& p, int n_sm, cudaStream_t s) {
     if (p.batch_pairs == 0) return cudaSuccess;
-    const int threads = kReadsThreads, wpc = threads / 32;
+    bool use_smem = false;
+    const int threads = reads_threads(p, use_smem), wpc = threads / 32;
+    if (threads <= 0) return cudaErrorInvalidConfiguration;
     const size_t rec_bytes = (size_t)wpc * reads_warp_bytes(p.n_ends, p.rec_buf, p.tpl_buf);
-    const size_t tab = reads_table_bytes(p);
-    const bool use_smem = tab + rec_bytes <= 200 * 1024;
-    const size_t smem_bytes = rec_bytes + (use_smem ? tab : 0);
+    const size_t smem_bytes = rec_bytes + (use_smem ? reads_table_bytes(p) : 0);
     cudaError_t err;
     int per_sm = 0;
     if (use_smem) {

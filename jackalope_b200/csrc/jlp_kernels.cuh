@@ -109,6 +109,8 @@ cudaError_t launch_offsets(const GenParams& p, cudaStream_t s);
 // template gather + quality/error model + FASTQ record assembly, one warp per pair;
 // n_sm sizes the persistent grid
 cudaError_t launch_reads(const GenParams& p, int n_sm, cudaStream_t s);
+// false: the records of this read length do not fit the shared memory of an SM (rec_buf / tpl_buf must be set)
+bool reads_fits(const GenParams& p);
 
 constexpr uint32_t kScanBlock = 1024;
 

@@ -108,15 +108,24 @@ def check_illumina_args(obj, n_reads, read_length, paired, frag_mean, frag_sd, m
 
 
 class Context:
-    """One GPU's library context with a genome (and haplotypes) resident in HBM."""
+    """A library context with a genome (and haplotypes) resident in HBM: one GPU (``device``), or several GPUs of
+    this host driven by one call (``devices``: a list of device indices, or "all") -- illumina() then cuts the run
+    into one contiguous piece per GPU and still writes ONE ordered set of files (jlp_ctx_create_multi)."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, devices=None):
         self.lib = _lib.lib()
         h = C.c_void_p()
-        rc = self.lib.jlp_ctx_create(int(device), C.byref(h))
+        if devices is None:
+            rc = self.lib.jlp_ctx_create(int(device), C.byref(h))
+        elif isinstance(devices, str) and devices == "all":
+            rc = self.lib.jlp_ctx_create_multi(0, None, C.byref(h))
+        else:
+            arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+            rc = self.lib.jlp_ctx_create_multi(len(devices), arr, C.byref(h))
         if rc != 0:
             raise RuntimeError("jlp_ctx_create: " + self.lib.jlp_last_error(None).decode())
         self.h = h
+        self.n_devices = int(self.lib.jlp_ctx_n_devices(h))
         self._genome = None
         self._haps = None
         self._profiles = [None, None]
@@ -338,6 +347,9 @@ def illumina(obj, out_prefix, n_reads, read_length, paired, frag_mean=400, frag_
         raise JackalopeError("sink must be \"files\", \"memory\" or \"device\"")
     n_ends = 2 if p.paired else 1
     n_rec = int(n_reads) // n_ends
+    if p.shard_count > 1:        # a shard holds about 1/count of every job (one job per haplotype with sep_files)
+        n_jobs = obj.n_haps() if (is_haps and p.sep_files) else 1
+        n_rec = n_rec // p.shard_count + n_jobs
     max_name = max(len(n) for n in (obj.reference.names if is_haps else obj.names))
     max_gn = max(len(n) for n in obj.hap_names) if is_haps else 3
     cap = n_rec * (max_name + max_gn + 32 + 2 * int(read_length) + 8) + 64

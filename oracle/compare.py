@@ -41,6 +41,19 @@ def hap_sequences(haps: J.Haplotypes):
     return out
 
 
+def lazy_hap_sequences(haps: J.Haplotypes):
+    """(h, c) -> bytes: one haplotype chromosome materialised with the oracle on demand (cached)."""
+    cache = {}
+
+    def get(h, c):
+        if (h, c) not in cache:
+            m = haps.muts[h][c]
+            cache[(h, c)] = H.materialize(haps.reference.chrom(c), m.old_pos, m.new_pos, m.nuc_off, m.pool.tobytes(), m.chrom_size)
+        return cache[(h, c)]
+    get.cache = cache
+    return get
+
+
 def group_counts(p, obj, is_haps):
     """Pairs per (haplotype, chromosome) of the run `p` describes (jlp_apportion)."""
     ref = obj.reference if is_haps else obj
@@ -65,7 +78,9 @@ def oracle_run(obj, n_reads, read_length, paired, seed, lo=None, hi=None, want_l
                only_job=None, _jobs_only=False, **kw):
     """Oracle output for the run illumina(obj, ..., seed=seed) performs.
     Returns dict(r1, r2[, plan, ledger, ledger_cnt, groups]); with sep_files the
-    jobs' outputs are concatenated in haplotype order (as sink="memory" does)."""
+    jobs' outputs are concatenated in haplotype order (as sink="memory" does).
+    hap_seqs: materialised haplotype chromosomes [h][c], or a callable (h, c) -> bytes asked only for the groups
+    the pair range [lo, hi) can touch (runs at sizes where materialising everything on the CPU is out of reach)."""
     a = dict(DEFAULTS)
     a.update(kw)
     p, keep, (prof1, prof2), is_haps, _ = _prepare(obj, "x", n_reads, read_length, paired, a["frag_mean"],
@@ -86,7 +101,33 @@ def oracle_run(obj, n_reads, read_length, paired, seed, lo=None, hi=None, want_l
         if is_haps and p.sep_files:
             return [(int(off[h * nc]), int(off[(h + 1) * nc])) for h in range(nh)]
         return [(0, int(off[-1]))]
-    if is_haps:
+    off_all = np.concatenate(([0], np.cumsum(counts))).astype(np.uint64)
+    pool_pairs = (p.read_pool_size + n_ends - 1) // n_ends
+    if is_haps and p.sep_files:
+        jobs = [(int(off_all[h * nc]), int(off_all[(h + 1) * nc])) for h in range(nh)]
+    else:
+        jobs = [(0, int(off_all[-1]))]
+    lens = None
+    if is_haps and callable(hap_seqs):
+        # lazy: materialise only the (haplotype, chromosome) groups the requested pairs -- and the leaders of
+        # their duplicate chains, at most pool_pairs - 1 pairs earlier in the same job -- can touch
+        touched = set()
+        for (jl, jh) in jobs:
+            if only_job is not None and (jl, jh) != tuple(only_job):
+                continue
+            a_lo, a_hi = (jl if lo is None else max(jl, lo)), (jh if hi is None else min(jh, hi))
+            if a_hi <= a_lo:
+                continue
+            first = max(jl, a_lo - min(a_lo - jl, pool_pairs - 1))
+            g0 = int(np.searchsorted(off_all, first, side="right")) - 1
+            g1 = int(np.searchsorted(off_all, a_hi - 1, side="right")) - 1
+            touched.update(range(g0, g1 + 1))
+        seqs = [hap_seqs(g // nc, g % nc) if g in touched else b"" for g in range(nh * nc)]
+        lens = [obj.muts[h][c].chrom_size for h in range(nh) for c in range(nc)]
+        gnames = [obj.hap_names[h] for h in range(nh) for c in range(nc)]
+        cnames = [ref.names[c] for h in range(nh) for c in range(nc)]
+        bcs = [p.barcodes[h].decode() for h in range(nh) for c in range(nc)]
+    elif is_haps:
         hap_seqs = hap_seqs or hap_sequences(obj)
         seqs = [hap_seqs[h][c] for h in range(nh) for c in range(nc)]
         gnames = [obj.hap_names[h] for h in range(nh) for c in range(nc)]
@@ -97,13 +138,8 @@ def oracle_run(obj, n_reads, read_length, paired, seed, lo=None, hi=None, want_l
         gnames = [ref.name] * nc
         cnames = list(ref.names)
         bcs = [p.barcodes[0].decode()] * nc
-    groups = H.Groups(counts, seqs, gnames, cnames, bcs)
+    groups = H.Groups(counts, seqs, gnames, cnames, bcs, lens=lens)
     cdf = frag_table(p.frag_len_shape, p.frag_len_scale, p.frag_len_min, p.frag_len_max)
-    pool_pairs = (p.read_pool_size + n_ends - 1) // n_ends
-    if is_haps and p.sep_files:
-        jobs = [(int(groups.off[h * nc]), int(groups.off[(h + 1) * nc])) for h in range(nh)]
-    else:
-        jobs = [(0, int(groups.off[-1]))]
     res = dict(r1=b"", r2=b"", groups=groups, jobs=jobs, params=p, profiles=(prof1, prof2), n_chroms=nc)
     for (jl, jh) in jobs:
         if only_job is not None and (jl, jh) != tuple(only_job):

@@ -141,10 +141,13 @@ def materialize(ref: bytes, old_pos, new_pos, nuc_off, pool: bytes, chrom_size: 
 class Groups:
     """(haplotype, chromosome) groups in the order the reference exhausts them."""
 
-    def __init__(self, counts, seqs, genome_names, chrom_names, barcodes):
+    def __init__(self, counts, seqs, genome_names, chrom_names, barcodes, lens=None):
+        """`lens`: the chromosomes' sizes when some of `seqs` are placeholders (b"": a group the requested
+        pair range cannot touch -- the oracle reads a group's bases only when it places a read there)."""
         self.counts = np.asarray(counts, dtype=np.uint64)
         self.off = np.concatenate(([0], np.cumsum(self.counts))).astype(np.uint64)
         self.seqs = [bytes(s) for s in seqs]
+        self.lens = np.array([len(s) for s in self.seqs] if lens is None else lens, dtype=np.uint64)
         self.genome_names = list(genome_names)
         self.chrom_names = list(chrom_names)
         self.barcodes = list(barcodes)
@@ -175,7 +178,7 @@ def generate(*, seed, paired, matepair, groups: Groups, prof1, prof2, ins_prob, 
     ng = len(groups.seqs)
     J.n_groups, J.group_off = ng, _ptr(groups.off, u64p)
     seqs = _strs(groups.seqs)
-    glen = np.array([len(s) for s in groups.seqs], dtype=np.uint64)
+    glen = groups.lens
     gn, cn, bc = _strs(groups.genome_names), _strs(groups.chrom_names), _strs(groups.barcodes)
     J.group_seq, J.group_len = seqs, _ptr(glen, u64p)
     J.group_genome_name, J.group_chrom_name, J.group_barcode = gn, cn, bc

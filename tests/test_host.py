@@ -396,3 +396,22 @@ def test_rcpp_glue_links_against_the_stock_wrappers():
     stock = open(os.path.join(REF, "src", "RcppExports.cpp")).read()
     body = ext[ext.index("// illumina_ref_cpp"):]
     assert body in stock and "const std::vector<std::string>& barcodes);" in body
+
+
+def test_oracle_lazy_haplotype_groups_match_the_full_materialisation():
+    """oracle_run with a callable hap_seqs materialises only the groups a pair range can touch (used by the
+    full-size GPU parity tests); the bytes must equal the run that materialises everything."""
+    from common import hap_sequences, lazy_hap_sequences, oracle_jobs
+    g = J.random_genome(4, 6_000, seed=71)
+    haps = J.random_haplotypes(g, 5, sub_rate=0.01, indel_rate=0.003, seed=72)
+    kw = dict(haplotype_probs=[1, 2, 3, 4, 5], sep_files=True, prob_dup=0.4, read_pool_size=20, seq_sys="HS25")
+    full = hap_sequences(haps)
+    lazy = lazy_hap_sequences(haps)
+    jobs = oracle_jobs(haps, 4000, 100, True, 5, **kw)
+    assert len(jobs) == 5
+    jl, jh = jobs[3]
+    for lo, hi in ((jl, jl + 40), (jl + (jh - jl) // 2, jl + (jh - jl) // 2 + 60), (jh - 30, jh)):
+        a = oracle_run(haps, 4000, 100, True, 5, lo=lo, hi=hi, hap_seqs=full, only_job=(jl, jh), **kw)
+        b = oracle_run(haps, 4000, 100, True, 5, lo=lo, hi=hi, hap_seqs=lazy, only_job=(jl, jh), **kw)
+        assert a["r1"] == b["r1"] and a["r2"] == b["r2"] and len(a["r1"]) > 0
+    assert 0 < len(lazy.cache) < 20 and all(h == 3 for h, _ in lazy.cache)
