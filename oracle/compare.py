@@ -175,3 +175,25 @@ def first_diff(a: bytes, b: bytes):
     if d.size == 0:
         return None if len(a) == len(b) else n
     return int(d[0])
+
+
+def explain_diff(a: bytes, b: bytes, what=("got", "want")):
+    """Text describing the first difference of two FASTQ byte strings: the record (4 lines) around it from both."""
+    d = first_diff(a, b)
+    if d is None:
+        return "identical"
+
+    def record(x):
+        lo = x.rfind(b"\n@", 0, d) + 1
+        hi = lo
+        for _ in range(4):
+            k = x.find(b"\n", hi)
+            if k < 0:
+                hi = len(x)
+                break
+            hi = k + 1
+        return lo, x[lo:hi].decode(errors="replace")
+
+    (la, ra), (lb, rb) = record(a), record(b)
+    return "first difference at byte %d (record %d of %s, offset %d in it)\n%s:\n%s%s:\n%s" % (
+        d, a[:la].count(b"\n") // 4, what[0], d - la, what[0], ra, what[1], rb)

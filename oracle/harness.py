@@ -226,6 +226,7 @@ def ref_lib(replay=False):
         lib.jref_add_sub.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_char, C.c_uint64]
         lib.jref_add_ins.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_char_p, C.c_uint64]
         lib.jref_add_del.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]
+        lib.jref_add_edits.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, u8p, u64p, u64p, u64p, C.c_char_p]
         for f in ("jref_hap_chrom_size", "jref_hap_n_muts", "jref_hap_nuc_bytes"):
             getattr(lib, f).restype = C.c_uint64
             getattr(lib, f).argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
@@ -297,6 +298,11 @@ class HapSetH:
     def add_del(self, hap, chrom, size, pos):
         assert self.lib.jref_add_del(self.h, hap, chrom, size, pos) == 0
 
+    def add_edit_arrays(self, hap, chrom, kind, pos, size, off, payload):
+        """many edits in one call (see muts_edit_arrays)"""
+        assert self.lib.jref_add_edits(self.h, hap, chrom, len(kind), _ptr(kind, u8p), _ptr(pos, u64p), _ptr(size, u64p),
+                                       _ptr(off, u64p), payload) == 0
+
     def chrom_size(self, hap, chrom):
         return int(self.lib.jref_hap_chrom_size(self.h, hap, chrom))
 
@@ -316,6 +322,31 @@ class HapSetH:
         self.lib.jref_hap_get_muts(self.h, hap, chrom, _ptr(op, u64p), _ptr(npos, u64p), _ptr(no, u64p),
                                    _ptr(nl, u32p), pool)
         return op[:m], npos[:m], no[:m], nl[:m], pool.raw[:nb]
+
+
+def muts_edit_arrays(m, ref_size):
+    """AllMutations arrays of one haplotype chromosome (jackalope_b200.genome.HapChromMuts: sorted, non-overlapping
+    records) -> the edits that rebuild them through HapChrom::add_* in ascending order, as flat arrays
+    (kind u8[], pos u64[], size u64[], pay_off u64[], payload bytes).  Vectorised: usable at 500 Mb."""
+    n = m.old_pos.size
+    kind = np.where(m.nuc_len == 1, 0, np.where(m.nuc_len > 1, 1, 2)).astype(np.uint8)
+    shift = m.new_pos.astype(np.int64) - m.old_pos.astype(np.int64)
+    nxt = np.concatenate((shift[1:], [int(m.chrom_size) - int(ref_size)])) if n else shift
+    size_mod = nxt - shift                                           # src/hap_classes.h:314-333
+    size = np.where(kind == 0, 1, np.where(kind == 1, m.nuc_len.astype(np.int64) - 1, -size_mod)).astype(np.uint64)
+    off = (m.nuc_off + (kind == 1)).astype(np.uint64)                # an insertion's payload follows its anchor base
+    return kind, np.ascontiguousarray(m.new_pos, dtype=np.uint64), size, off, m.pool.tobytes()
+
+
+def hapset_from_muts(ref: "RefGenomeH", haps, which=None):
+    """A reference HapSet holding haplotypes `which` (default: all) of a jackalope_b200 Haplotypes object."""
+    which = list(range(haps.n_haps())) if which is None else list(which)
+    hs = HapSetH(ref, [haps.hap_names[h] for h in which])
+    for k, h in enumerate(which):
+        for c, m in enumerate(haps.muts[h]):
+            if m.old_pos.size:
+                hs.add_edit_arrays(k, c, *muts_edit_arrays(m, len(ref.seqs[c])))
+    return hs
 
 
 def ref_alias_build(probs, replay=False):

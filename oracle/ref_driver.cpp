@@ -96,6 +96,20 @@ int jref_add_del(void* hs, uint64_t hap, uint64_t chrom, uint64_t size, uint64_t
     catch (...) { return -1; }
     return 0;
 }
+// n edits of one haplotype chromosome in one call, in the order given (kind 0 substitution: payload 1 base;
+// 1 insertion: payload the inserted bases; 2 deletion of `size`); pos = 0-based haplotype coordinate at edit time
+int jref_add_edits(void* hs, uint64_t hap, uint64_t chrom, uint64_t n, const uint8_t* kind, const uint64_t* pos,
+                   const uint64_t* size, const uint64_t* pay_off, const char* payload) {
+    try {
+        HapChrom& hc = (*static_cast<HapSet*>(hs))[hap][chrom];
+        for (uint64_t i = 0; i < n; i++) {
+            if (kind[i] == 0) hc.add_substitution(payload[pay_off[i]], pos[i]);
+            else if (kind[i] == 1) hc.add_insertion(std::string(payload + pay_off[i], size[i]), pos[i]);
+            else hc.add_deletion(size[i], pos[i]);
+        }
+    } catch (...) { return -1; }
+    return 0;
+}
 uint64_t jref_hap_chrom_size(void* hs, uint64_t hap, uint64_t chrom) {
     return (*static_cast<HapSet*>(hs))[hap][chrom].size();
 }

@@ -13,7 +13,7 @@ import pytest
 
 import jackalope_b200 as J
 from jackalope_b200 import _lib
-from common import first_diff, lazy_hap_sequences, oracle_jobs, oracle_run
+from common import explain_diff, first_diff, lazy_hap_sequences, oracle_jobs, oracle_run
 
 pytestmark = pytest.mark.gpu
 
@@ -90,7 +90,7 @@ def test_config5_human_scale_slices_of_the_full_job():
             lo, hi = shard_bounds(0, n_pairs, k, S)
             o = oracle_run(g, n_reads, L, True, seed, lo=lo, hi=hi, **kw)
             d1, d2 = first_diff(r1, o["r1"]), first_diff(r2, o["r2"])
-            assert d1 is None and d2 is None, "slice %d: R1 byte %r, R2 byte %r" % (k, d1, d2)
+            assert d1 is None and d2 is None, "slice %d (pairs %d..%d):\nR1 %s\nR2 %s" % (k, lo, hi, explain_diff(r1, o["r1"]), explain_diff(r2, o["r2"]))
             assert st["pairs"] == hi - lo and r1.count(b"\n") == 4 * (hi - lo)
             assert st["h2d_bytes"] < 0.6e9, "the deferred upload copied more than the touched chromosomes"
             if k == 0:       # chrom0 is 248 Mb: most of its start coordinates have 9 digits
@@ -139,7 +139,8 @@ def test_config4_96_haplotypes_500Mb_sep_files_full_size():
                 lo, hi = shard_bounds(jl, jh, k, S)
                 o = oracle_run(haps, n_reads, L, True, seed, lo=lo, hi=hi, hap_seqs=lazy, only_job=(jl, jh), **kw)
                 d1, d2 = first_diff(got[(h, 0)], o["r1"]), first_diff(got[(h, 1)], o["r2"])
-                assert d1 is None and d2 is None, "hap %d slice %d: R1 byte %r, R2 byte %r" % (h, k, d1, d2)
+                assert d1 is None and d2 is None, "hap %d slice %d (pairs %d..%d of job %d..%d):\nR1 %s\nR2 %s" % (
+                    h, k, lo, hi, jl, jh, explain_diff(got[(h, 0)], o["r1"]), explain_diff(got[(h, 1)], o["r2"]))
                 assert o["r1"].startswith(b"@hap%d-" % h) and hi > lo
     finally:
         ctx.close()
