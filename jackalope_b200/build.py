@@ -22,6 +22,8 @@ def _stale():
 def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB
+    if os.environ.get("JLP_NO_BUILD") and os.path.exists(LIB):      # use the library as shipped (measuring an older build)
+        return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
            "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "-shared", "-o", LIB]

@@ -204,8 +204,17 @@ struct HapDev {
     std::shared_ptr<HapStore> store;    // shared by the devices of a multi-GPU context
     std::vector<const uint8_t*> seq;    // per chromosome; aliases the reference when unmutated; NULL = not materialised yet
     std::vector<uint64_t> len;
-    std::vector<uint8_t*> owned;        // device allocations to free
     const std::string& name() const { return store->name; }
+};
+
+// Device memory of the materialised haplotype chromosomes: carved out of a few large slabs (one cudaMalloc per GiB,
+// not one per chromosome -- 96 haplotypes x 20 chromosomes would be 1920 allocations); freed together.
+struct HapArena {
+    std::vector<uint8_t*> slabs;
+    size_t used = 0, cap = 0;
+    uint8_t* alloc(size_t n);
+    void release() { for (uint8_t* p : slabs) cudaFree(p); slabs.clear(); used = cap = 0; }
+    ~HapArena() { release(); }
 };
 
 struct Slot {
@@ -267,6 +276,7 @@ struct jlp_ctx {
     cudaEvent_t ev_run[2] = {nullptr, nullptr};
     uint64_t h2d_bytes = 0;
     // scratch of the haplotype materialisation (mutation records of one chromosome)
+    HapArena hap_mem;
     DevBuf<uint64_t> m_old, m_new, m_off;
     DevBuf<int64_t> m_sm;
     DevBuf<uint8_t> m_pool;
@@ -274,10 +284,23 @@ struct jlp_ctx {
 
 namespace {
 
+uint8_t* HapArena::alloc(size_t n) {
+    n = (n + 255) & ~(size_t)255;
+    if (slabs.empty() || used + n > cap) {
+        const size_t want = std::max<size_t>(n, (size_t)1 << 30);
+        uint8_t* p = nullptr;
+        CK(cudaMalloc(reinterpret_cast<void**>(&p), want));
+        slabs.push_back(p);
+        used = 0; cap = want;
+    }
+    uint8_t* r = slabs.back() + used;
+    used += n;
+    return r;
+}
+
 void free_haps(jlp_ctx* c) {
-    for (HapDev& h : c->haps)
-        for (uint8_t* p : h.owned) cudaFree(p);
     c->haps.clear();
+    c->hap_mem.release();
 }
 
 int fail(jlp_ctx* c, int code, const std::string& msg) {
@@ -569,9 +592,7 @@ void ensure_hap_chrom(jlp_ctx* c, size_t h, size_t ci) {
     c->m_old.upload(M.old_pos, c->s_compute); c->m_new.upload(M.new_pos, c->s_compute); c->m_off.upload(M.nuc_off, c->s_compute);
     c->m_sm.upload(M.size_mod, c->s_compute); c->m_pool.upload(M.pool, c->s_compute);
     c->h2d_bytes += M.old_pos.size() * 32 + M.pool.size();
-    uint8_t* out = nullptr;
-    CK(cudaMalloc(reinterpret_cast<void**>(&out), M.size + 2 * kPad));
-    H.owned.push_back(out);
+    uint8_t* out = c->hap_mem.alloc(M.size + 2 * kPad);
     CK(launch_materialize(ref, ref_size, M.old_pos.size(), c->m_old.p, c->m_new.p, c->m_sm.p, c->m_off.p, c->m_pool.p, M.size,
                           out + kPad, c->s_compute));
     CK(cudaStreamSynchronize(c->s_compute));      // the scratch buffers are reused by the next chromosome
@@ -683,8 +704,9 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
     uint32_t max_prefix = 0;
     for (const GroupDev& g : groups) max_prefix = std::max(max_prefix, g.prefix_len);
     const uint64_t max_rec = (uint64_t)max_prefix + 20 + 5 + 2ull * L + 4;
-    gp.rec_buf = (uint32_t)((max_rec + 64 + 15) & ~15ull);
+    gp.rec_buf = (uint32_t)((max_rec + 32 + 15) & ~15ull);   // a record at any 16-byte phase, and the 16 bytes the carry copy reads behind it
     gp.tpl_buf = (L + 34u + 15u) & ~15u;        // the template, its slack to 16-byte alignment, the word over-read
+    gp.cod_buf = (L + 8u + 15u) & ~15u;         // base codes of a read; the last 8-byte store may run past its end
     if (!sizes_only && !reads_fits(gp)) throw Unsupported("read_length " + std::to_string(L) + " (with these chromosome names) needs more shared memory per "
                                                           "read pair than one SM has: the read kernel cannot hold such a record");
     const uint64_t n_rec_max = B * n_ends;
@@ -923,7 +945,6 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
             CK(cudaEventRecord(s.ev[1], c->s_compute));
             CK(launch_scan(s.rec_len.p, n_rec, n_ends, s.rec_local.p, s.block_tot.p, s.block_base.p, s.totals.p,
                            c->s_compute));
-            CK(launch_offsets(gp, c->s_compute));
             CK(cudaEventRecord(s.ev[2], c->s_compute));
             CK(launch_reads(gp, c->n_sm, c->s_compute));
             CK(cudaEventRecord(s.ev[3], c->s_compute));
@@ -934,7 +955,7 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
             }
             CK(cudaMemcpyAsync(s.h_totals.p, s.totals.p, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->s_compute));
             CK(cudaEventRecord(s.ev[5], c->s_compute));
-            st.kernel_launches += 5;
+            st.kernel_launches += 4;
             s.pairs = np; s.busy = true;
             computing.push_back(&s);
             // the previous batch's copy is queued before the one in flight is waited for
@@ -1081,7 +1102,11 @@ void run_multi(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& si
         for (size_t r = 0; r < N; r++)
             th.emplace_back([&, r]() {
                 codes[r] = guarded(c->kids[r], [&]() { f(r); });
-                if (codes[r] != JLP_OK) { errs[r] = c->kids[r]->err; shared.abort.store(1); }    // the others stop at their next batch
+                if (codes[r] != JLP_OK) {                     // the others stop at their next batch
+                    errs[r] = c->kids[r]->err;
+                    int none = 0;
+                    shared.abort.compare_exchange_strong(none, 1);
+                }
                 left.fetch_sub(1);
             });
         while (left.load() != 0) {
@@ -1240,7 +1265,7 @@ int jlp_ctx_create_multi(int n_devices, const int* devices, jlp_ctx** out) {
     if (e != cudaSuccess || n == 0)
         return fail(nullptr, JLP_ERR_NO_DEVICE, std::string("no CUDA device available (") + cudaGetErrorString(e) +
                                                     "); this library has no CPU fallback");
-    if (n_devices < 0 || n_devices > n) return fail(nullptr, JLP_ERR_ARG, "more devices asked for than are visible");
+    if (n_devices < 0 || n_devices > 64) return fail(nullptr, JLP_ERR_ARG, "n_devices must be 0 (all visible devices) .. 64");
     if (n_devices == 0) { n_devices = n; devices = nullptr; }
     std::unique_ptr<jlp_ctx> c(new jlp_ctx);
     c->device = -1;

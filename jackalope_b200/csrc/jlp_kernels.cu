@@ -276,37 +276,18 @@ k_place(const __grid_constant__ GenParams p) {
     const uint32_t space = S - b;
     const uint64_t start = (p.matepair != 0) == reverse ? frag_start : frag_start + frag_len - space;
 
-    // ---- the ID line "@<genome>-<chrom>-<start>-<F|R>[/<1|2>]\n" (fill_fq_lines, src/hts_illumina.cpp:296-312)
-    uint8_t digits[20];
-    uint32_t nd = 0;
-    {
-        uint64_t v = start;
-        do { digits[nd++] = (uint8_t)('0' + (uint32_t)(v % 10)); v /= 10; } while (v);
-    }
+    // ---- length of the ID line "@<genome>-<chrom>-<start>-<F|R>[/<1|2>]\n" (fill_fq_lines, src/hts_illumina.cpp:296-312);
+    //      its text is written by the read kernel
+    uint32_t nd = 1;
+    for (uint64_t v = start; v >= 10; v /= 10) nd++;
     const uint32_t idlen = G.prefix_len + nd + 3u + (p.n_ends == 2 ? 2u : 0u);
     uint32_t flags = (reverse ? kPlanReverse : 0u) | (n_ev ? kPlanIndels : 0u) | (b ? kPlanBarcode : 0u);
-    uint4* dst = reinterpret_cast<uint4*>(p.plan + r);
-    if (idlen <= 64u) {
-        __align__(16) uint8_t line[64];
-#pragma unroll
-        for (uint32_t t = 0; t < 16; t++) reinterpret_cast<uint32_t*>(line)[t] = 0;
-        uint32_t w = 0;
-        const uint8_t* pre = p.strpool + G.prefix_off;
-        for (; w < G.prefix_len; w++) line[w] = pre[w];
-        for (uint32_t t = 0; t < nd; t++) line[w++] = digits[nd - 1u - t];
-        line[w++] = '-';
-        line[w++] = reverse ? 'R' : 'F';
-        if (p.n_ends == 2) { line[w++] = '/'; line[w++] = (uint8_t)('1' + e); }
-        line[w++] = '\n';
-#pragma unroll
-        for (uint32_t t = 0; t < 4; t++) dst[2 + t] = reinterpret_cast<const uint4*>(line)[t];
-    } else {
-        flags |= kPlanLongId;
-    }
+    if (idlen > 255u) flags |= kPlanLongId;
     const uint32_t rec_len = idlen + 2u * len + 4u;   // ID line | read '\n' '+' '\n' qual '\n'
     const uint64_t sega = reinterpret_cast<uint64_t>(G.seq + start);
+    uint4* dst = reinterpret_cast<uint4*>(p.plan + r);
     dst[0] = make_uint4((uint32_t)sega, (uint32_t)(sega >> 32), S, len | (flags << 16) | ((idlen & 0xffu) << 24));
-    dst[1] = make_uint4(rec_len, g, 0u, 0u);          // the offset is filled in by k_offsets after the scan
+    dst[1] = make_uint4(rec_len, g, (uint32_t)start, (uint32_t)(start >> 32));
     p.rec_len[r] = rec_len;
 }
 
@@ -314,22 +295,6 @@ cudaError_t launch_place(const GenParams& p, cudaStream_t s) {
     uint32_t n = p.batch_pairs * p.n_ends;
     if (n == 0) return cudaSuccess;
     k_place<<<(n + 255) / 256, 256, 0, s>>>(p);
-    return cudaGetLastError();
-}
-
-// One thread per record: its absolute offset in the batch's output buffer.
-__global__ void __launch_bounds__(256)
-k_offsets(const __grid_constant__ GenParams p) {
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= p.batch_pairs * p.n_ends) return;
-    const uint32_t e = (p.n_ends == 2) ? (r & 1u) : 0u, i = (p.n_ends == 2) ? (r >> 1) : r;
-    p.plan[r].off = p.block_base[(size_t)e * p.n_scan_blocks + i / kScanBlock] + p.rec_local[r];
-}
-
-cudaError_t launch_offsets(const GenParams& p, cudaStream_t s) {
-    uint32_t n = p.batch_pairs * p.n_ends;
-    if (n == 0) return cudaSuccess;
-    k_offsets<<<(n + 255) / 256, 256, 0, s>>>(p);
     return cudaGetLastError();
 }
 
@@ -364,11 +329,6 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// bytes of shared memory one warp of k_reads owns (host and device agree through this)
-__host__ __device__ inline uint32_t reads_warp_bytes(uint32_t n_ends, uint32_t rec_buf, uint32_t tpl_buf) {
-    return 32u + 3u * 192u + 4u * tpl_buf + n_ends * rec_buf;
-}
-
 __device__ __forceinline__ U4 qual_block(const GenParams& p, uint64_t j, uint32_t blk, uint32_t e) {
     return philox4x32_10_rk((uint32_t)j, (uint32_t)(j >> 32), blk, PL_QUAL | (e << 8), p.rk);
 }
@@ -384,7 +344,7 @@ __device__ __noinline__ uint32_t base_rare(const GenParams& p, uint32_t meta_a, 
     if (code > 3) {
         // 'N' with a quality below 10 (src/hts_illumina.h:237-242)
         uint32_t qc = __umulhi(die, 10u) + 33u;
-        if (die * 10u + 2560u < 2560u) qc = nqual_x87(full_draw(die >> 8, p.seed, j, e, PU_DIE, pos));
+        if (die * 10u + 2560u < 5120u) qc = nqual_x87(full_draw(die >> 8, p.seed, j, e, PU_DIE, pos));   // two-sided, as in base_fast
         return 0x4Eu | ((qc & 0xffu) << 8);
     }
     uint32_t m;
@@ -392,7 +352,7 @@ __device__ __noinline__ uint32_t base_rare(const GenParams& p, uint32_t meta_a, 
     else m = __ldg(E.meta + code * p.L + pos);
     const uint32_t n = m & 0xffu, off = m >> 8;
     uint32_t i = __umulhi(die, n);
-    if (die * n + (n << 8) < (n << 8)) {     // the draw's low 40 bits can carry into the slot index
+    if (die * n + (n << 8) < (n << 9)) {     // the draw's low 40 bits decide the slot index (see base_fast)
         uint64_t ii = mul_floor_x87(full_draw(die >> 8, p.seed, j, e, PU_DIE, pos), n);
         i = ii >= n ? n - 1u : (uint32_t)ii;
     }
@@ -441,9 +401,11 @@ __device__ __forceinline__ void base_fast(const GenParams& p, uint32_t meta_a, u
     const uint32_t thr_hi = ent.x & 0xffff0000u;
     self = cm < thr_hi;
     const uint32_t mt = self ? (ent.y & 0xffffu) : (ent.y >> 16);    // high 16 bits of the quality's mismatch threshold
-    // ... unless the draw's low 40 bits could carry into it; coin and mismatch are undecided when their
-    // 16 high bits equal the threshold's; a mismatch itself is handled by the exact path too
-    rare = (lo + (n << 8) < (n << 8)) || (cm - thr_hi < 0x10000u) || ((cm & 0xffffu) <= mt);
+    // ... unless the draw's low 40 bits decide: the word's low byte belongs to X_sub, not to X_die, so the product's
+    // fraction is off by up to n * 2^8 either way -- about to carry (true low bits larger) or just carried (the
+    // substitution byte alone pushed it over); coin and mismatch are undecided when their 16 high bits equal the
+    // threshold's; a mismatch itself is handled by the exact path too
+    rare = (lo + (n << 8) < (n << 9)) || (cm - thr_hi < 0x10000u) || ((cm & 0xffffu) <= mt);
     entx = ent.x;
 }
 
@@ -487,26 +449,6 @@ __device__ __forceinline__ void load8(const uint8_t* a, uint32_t& lo, uint32_t& 
     const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
     lo = __funnelshift_r(w0, w1, sh);
     hi = __funnelshift_r(w1, w2, sh);
-}
-
-// ID line of a record whose line did not fit the plan (very long genome / chromosome names):
-// lane 0 writes it byte by byte.
-__device__ __noinline__ void long_idline(const GenParams& p, uint32_t dst, const GroupDev* Gp, const uint8_t* seg,
-                                         bool reverse, uint32_t e) {
-    uint64_t start = (uint64_t)(seg - Gp->seq);
-    const uint8_t* pre = p.strpool + Gp->prefix_off;
-    const uint32_t n = Gp->prefix_len;
-    for (uint32_t t = 0; t < n; t++) sts8(dst + t, pre[t]);
-    dst += n;
-    uint8_t dg[20];
-    uint32_t nd = 0;
-    do { dg[nd++] = (uint8_t)('0' + (uint32_t)(start % 10)); start /= 10; } while (start);
-    for (uint32_t t = 0; t < nd; t++) sts8(dst + t, dg[nd - 1u - t]);
-    dst += nd;
-    sts8(dst++, '-');
-    sts8(dst++, reverse ? 'R' : 'F');
-    if (p.n_ends == 2) { sts8(dst++, '/'); sts8(dst++, '1' + e); }
-    sts8(dst, '\n');
 }
 
 // Template codes of an end WITH insertions / deletions: every template position gets its
@@ -563,21 +505,83 @@ __device__ __noinline__ void gather_barcode(uint32_t w, const uint8_t* seg, cons
 }
 
 #ifndef JLP_READS_THREADS
-#define JLP_READS_THREADS 896   // 28 warps, one CTA per SM sharing one copy of the tables: measured best
+#define JLP_READS_THREADS 896   // 28 warps, one CTA per SM sharing one copy of the tables
 #define JLP_READS_CTAS 1
 #endif
 constexpr int kReadsThreads = JLP_READS_THREADS;
+constexpr uint32_t kTplSlots = 3;       // staged template windows per warp: pair k is read while k+1 and k+2 are on their way
 
-// One warp per read pair.
-//   phase A (per end): the ID line (prepared by k_place) and the template's base codes go
-//     into the end's record buffer in shared memory, placed so that the sequence line
-//     starts 8-byte aligned: 8 template positions per lane from three aligned word loads,
-//     one 64-bit shared store;
-//   phase B (both ends in one index space, two bases per lane and Philox block): quality
-//     by the alias method, mismatch test, substitution; rare cases branch to base_rare();
-//   phase C (per end): the finished FASTQ record moves to its final offset in the output
-//     with 128-bit stores; the shift between the record's place in shared memory and its
-//     place in the file is taken out with funnel shifts.
+// bytes of shared memory one warp of k_reads owns (host and device agree through this):
+// 4 mbarriers | 64 bytes of scratch | 2 chunks of plans | kTplSlots template windows per end | one base-code line per end |
+// two output buffers per end
+__host__ __device__ inline uint32_t reads_warp_bytes(uint32_t n_ends, uint32_t rec_buf, uint32_t tpl_buf, uint32_t cod_buf) {
+    return 96u + 2u * kPlanChunk * n_ends * 32u + kTplSlots * n_ends * tpl_buf + n_ends * cod_buf + 2u * n_ends * rec_buf;
+}
+
+// ---- bulk asynchronous copies (cp.async.bulk: SASS UBLKCP) and their mbarriers
+__device__ __forceinline__ void mbar_init(uint32_t a, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(a), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t a, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" :: "r"(a), "r"(parity) : "memory");
+}
+// global -> shared, completion counted in bytes on an mbarrier; both addresses and the size are multiples of 16
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+// shared -> global, tracked by the issuing thread's bulk async-groups
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
+// generic-proxy accesses to shared memory before, asynchronous-proxy accesses after
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ID line of a record with a very long genome / chromosome name, or a coordinate >= 2^32: one lane writes it byte by byte.
+__device__ __noinline__ void slow_idline(const GenParams& p, uint32_t dst, const GroupDev* Gp, uint64_t start, bool reverse, uint32_t e) {
+    const uint8_t* pre = p.strpool + Gp->prefix_off;
+    const uint32_t n = Gp->prefix_len;
+    for (uint32_t t = 0; t < n; t++) sts8(dst + t, pre[t]);
+    dst += n;
+    uint8_t dg[20];
+    uint32_t nd = 0;
+    do { dg[nd++] = (uint8_t)('0' + (uint32_t)(start % 10)); start /= 10; } while (start);
+    for (uint32_t t = 0; t < nd; t++) sts8(dst + t, dg[nd - 1u - t]);
+    dst += nd;
+    sts8(dst++, '-');
+    sts8(dst++, reverse ? 'R' : 'F');
+    if (p.n_ends == 2) { sts8(dst++, '/'); sts8(dst++, '1' + e); }
+    sts8(dst, '\n');
+}
+
+// ceil(2^64 / 10^k), k = 1..9: floor(n / 10^k) = umul64hi(n, c_m10[k]) for every n < 2^32
+__constant__ uint64_t c_m10[10] = {0ull, 1844674407370955162ull, 184467440737095517ull, 18446744073709552ull, 1844674407370956ull,
+                                   184467440737096ull, 18446744073710ull, 1844674407371ull, 184467440738ull, 18446744074ull};
+
+// One warp per run of consecutive read pairs: the R1 records of a run are one contiguous span of file 1, its R2
+// records one of file 2, so a record is assembled in shared memory AT ITS FILE ALIGNMENT and leaves with one bulk
+// copy (cp.async.bulk shared -> global) of the 16-byte chunks it completes; the unfinished last chunk is carried
+// into the next record's buffer.  Only the two ragged ends of a run are written byte by byte.
+//   staging   the plans of 8 pairs per bulk copy (global -> shared, mbarrier); the bytes around both templates of
+//             pairs k+1 and k+2 as bulk copies while pair k is processed
+//   phase A   template bytes -> base codes (T0 C1 A2 G3, other 4), reverse-complemented on the reverse strand,
+//             8 positions per lane from aligned shared words; ends with indels / a barcode take the whole warp
+//   ID line   written in place: the group's prefix from a per-warp cache, one decimal digit per lane
+//   phase B   (both ends in one index space, two bases per lane and Philox block) quality by the alias method,
+//             mismatch test, substitution, straight into the record; undecided draws branch to base_rare()
+//   flush     lanes 0 and 16: bulk copy of the chunks their end's record completes, commit, carry
+// Per-warp state that changes once per pair is packed into one register (st): bits 0-3 where the next record starts
+// in its buffer, 4-7 the bytes of the run's first chunk that belong to the previous run, 8 the buffer in use,
+// 9-10 the template slot, 11-13 the slots' mbarrier parities.
 template <bool SMEM>
 __global__ void __launch_bounds__(kReadsThreads, JLP_READS_CTAS)
 k_reads(const __grid_constant__ GenParams p) {
@@ -604,79 +608,117 @@ k_reads(const __grid_constant__ GenParams p) {
     asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));      // kept in a register (the compiler would re-read SR_TID)
     const uint32_t warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     const uint32_t n_ends = p.n_ends;
-    // this warp's shared memory: 32 bytes of scratch, a ring of three plan slots (both ends'
-    // EndPlan records of one pair), a ring of two template slots (the bytes around each end's
-    // template, copied as 16-byte chunks), then one record buffer per end
-    const uint32_t tplw = p.tpl_buf;
-    const uint32_t W0 = sbase + tab_bytes + warp * reads_warp_bytes(n_ends, p.rec_buf, tplw);
-    const uint32_t PL0 = W0 + 32u, TP0 = PL0 + 3u * 192u, R0 = TP0 + 4u * tplw;
-    const uint32_t stride = gridDim.x * wpc;
-    const uint32_t i0 = blockIdx.x * wpc + warp;
+    const uint32_t tplw = p.tpl_buf, codw = p.cod_buf, obw = p.rec_buf;
+    // this warp's shared memory: 4 mbarriers (plan chunks; template slots 0, 1, 2) | 64 bytes of scratch (the current
+    // group's ID-line prefix, its index and length) | 2 plan chunks | template windows | code lines | output buffers
+    const uint32_t W0 = sbase + tab_bytes + warp * reads_warp_bytes(n_ends, obw, tplw, codw);
+    const uint32_t plan_pair = n_ends * 32u;                  // bytes of plan per pair
+#define MB0 (W0)
+#define SC0 (W0 + 32u)
+#define PL0 (W0 + 96u)
+#define TP0 (PL0 + 2u * kPlanChunk * plan_pair)
+#define CD0 (TP0 + kTplSlots * n_ends * tplw)
+#define OB0 (CD0 + n_ends * codw)
 
-    // Asynchronous staging (cp.async, 16 bytes per lane): the plan of pair k+2 and the template
-    // bytes of pair k+1 are on their way while pair k is processed, so no load of the main loop
-    // waits on HBM.
-    auto stage_plan = [&](uint32_t slot, uint32_t pair) {
-        if (lane < 6u * n_ends)
-            cp_async16(PL0 + slot * 192u + 16u * lane, reinterpret_cast<const uint8_t*>(p.plan + (size_t)pair * n_ends) + 16u * lane);
-    };
-    auto stage_tpl = [&](uint32_t tslot, uint32_t pslot) {
-        const uint32_t e = lane >> 4;
-        if (e < n_ends) {
-            const uint4 pa = lds128(PL0 + pslot * 192u + e * 96u);
-            const uint64_t sa = ((uint64_t)pa.y << 32) | pa.x;
-            const uint64_t ws = (sa - 8u) & ~(uint64_t)15;
-            const uint64_t need = sa + pa.z + 12u;                 // last byte the fast gather can touch, plus one
-            for (uint32_t l = lane & 15u; 16u * l < tplw; l += 16u)
-                if (ws + 16u * l < need) cp_async16(TP0 + (tslot * 2u + e) * tplw + 16u * l, reinterpret_cast<const uint8_t*>(ws + 16u * l));
+    // ---- this warp's run of pairs
+    const uint32_t n_warps = gridDim.x * wpc;
+    const uint32_t per = (p.batch_pairs + n_warps - 1u) / n_warps;
+    const uint32_t r0 = min((blockIdx.x * wpc + warp) * per, p.batch_pairs);
+    const uint32_t n_run = min(per, p.batch_pairs - r0);
+    if (n_run == 0) return;
+
+    const uint32_t he = lane >> 4, hl = lane & 15u;           // phase A, ID line and flush: one half-warp per end
+    const bool mine = he < n_ends;
+    // where the run's first record of this lane's end goes: its offset in the file's batch buffer
+    uint8_t* gbase = nullptr;                                 // global address of byte 0 of the output buffer in use (16-byte aligned)
+    uint32_t st = 0;
+    if (mine) {
+        const uint64_t fo = p.block_base[(size_t)he * p.n_scan_blocks + r0 / kScanBlock] + p.rec_local[r0 * n_ends + he];
+        st = ((uint32_t)fo & 15u) * 0x11u;                    // apos = hole = fo % 16
+        gbase = p.out[he] + (fo & ~(uint64_t)15);
+    }
+    if (lane == 0) {
+        mbar_init(MB0, 1); mbar_init(MB0 + 8u, 1); mbar_init(MB0 + 16u, 1); mbar_init(MB0 + 24u, 1);
+        sts32(SC0 + 32u, 0xffffffffu);                        // no group cached
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    // plans: chunk c (pairs 8c .. of the run) -> buffer c & 1; ONE mbarrier, whose phase c is chunk c: chunk c + 2 is
+    // issued (after pair 8c + 7) only when chunk c + 1 has been waited for (after pair 8c + 6)
+    const uint32_t n_chunks = (n_run + kPlanChunk - 1u) / kPlanChunk;
+    auto stage_chunk = [&](uint32_t c) {
+        if (lane == 0) {
+            const uint32_t np = min(kPlanChunk, n_run - c * kPlanChunk), bytes = np * plan_pair;
+            mbar_expect_tx(MB0, bytes);
+            bulk_g2s(PL0 + (c & 1u) * kPlanChunk * plan_pair, reinterpret_cast<const uint8_t*>(p.plan) + (size_t)(r0 + c * kPlanChunk) * plan_pair, bytes, MB0);
         }
     };
-    if (i0 < p.batch_pairs) {
-        stage_plan(0, i0);
-        if (i0 + stride < p.batch_pairs) stage_plan(1, i0 + stride);
-        cp_async_commit();
-        cp_async_wait_all();
+    auto plan_addr = [&](uint32_t k) { return PL0 + (((k >> 3) & 1u) * kPlanChunk + (k & 7u)) * plan_pair; };
+    // templates of pair k -> slot; both ends' windows complete on the slot's mbarrier
+    auto stage_tpl = [&](uint32_t k, uint32_t slot) {
+        const uint32_t mb = MB0 + 8u + 8u * slot;
+        uint32_t bytes = 0;
+        uint64_t ws = 0;
+        if (hl == 0 && mine) {
+            const uint4 pa = lds128(plan_addr(k) + he * 32u);
+            const uint64_t sa = ((uint64_t)pa.y << 32) | pa.x;
+            ws = (sa - 8u) & ~(uint64_t)15;
+            // up to the last byte the gather can touch, plus one
+            bytes = min((uint32_t)((sa + pa.z + 12u - ws + 15u) & ~(uint64_t)15), tplw);
+        }
+        const uint32_t b1 = __shfl_sync(0xffffffffu, bytes, 16);
+        if (lane == 0) mbar_expect_tx(mb, bytes + b1);
         __syncwarp();
-        stage_tpl(0, 0);
-        cp_async_commit();
-    }
+        if (bytes) bulk_g2s(TP0 + (slot * n_ends + he) * tplw, reinterpret_cast<const void*>(ws), bytes, mb);
+    };
+    stage_chunk(0);
+    mbar_wait(MB0, 0);
+    if (n_chunks > 1) stage_chunk(1);
+    stage_tpl(0, 0);
+    if (n_run > 1) stage_tpl(1, 1);
 
-    uint32_t ps = 0, ts = 0;             // ring positions of the current pair's plan (mod 3) and templates (mod 2)
-    for (uint32_t i = i0; i < p.batch_pairs; i += stride) {
-        const uint64_t j = p.batch_lo + i;
-        const uint32_t ps1 = ps == 2u ? 0u : ps + 1u, ps2 = ps1 == 2u ? 0u : ps1 + 1u;
-        cp_async_wait_all();
-        __syncwarp();
-        if (i + 2u * stride < p.batch_pairs) stage_plan(ps2, i + 2u * stride);
-        if (i + stride < p.batch_pairs) stage_tpl(ts ^ 1u, ps1);
-        cp_async_commit();
-        const uint32_t PL = PL0 + ps * 192u, TP = TP0 + ts * 2u * tplw;
-        ps = ps1; ts ^= 1u;
-
-        // ---- phase A: ID line and template base codes into the record buffers, all from shared
-        //      memory.  The two ends are handled side by side, one half-warp each (lane >> 4 is the
-        //      end, lane & 15 the worker), so the per-end bookkeeping is paid once per pair.
-        const uint32_t he = lane >> 4, hl = lane & 15u;
-        const bool mine = he < n_ends;
-        const uint32_t PLe = PL + he * 96u;
-        uint32_t my_w = 0, my_ln = 0, my_flags = 0, my_rs = 0;
-        if (mine) {
-            const uint4 pa = lds128(PLe);
+#pragma unroll 1
+    for (uint32_t k = 0; k < n_run; k++) {
+        const uint64_t j = p.batch_lo + r0 + k;
+        const uint32_t PLk = plan_addr(k);
+        {
+            const uint32_t slot = (st >> 9) & 3u;
+            mbar_wait(MB0 + 8u + 8u * slot, (st >> (11u + slot)) & 1u);
+            st ^= 0x800u << slot;
+        }
+        uint32_t sq, ln_e;                                    // this end's sequence line (shared address) and read length
+        {
+            // ---- this lane's end: plan fields
+            const uint32_t slot = (st >> 9) & 3u;
+            const uint32_t TPe = TP0 + (slot * n_ends + he) * tplw;
+            uint4 pa = make_uint4(0, 0, 0, 0);
+            uint32_t rec = 0, grp_e = 0;
+            if (mine) { pa = lds128(PLk + he * 32u); const uint2 pb = lds64(PLk + he * 32u + 16u); rec = pb.x; grp_e = pb.y; }
             const uint32_t S = pa.z, ln = pa.w & 0xffffu, flags = (pa.w >> 16) & 0xffu;
             uint32_t idlen = pa.w >> 24;
-            const bool reverse = flags & kPlanReverse;
-            if (flags & kPlanLongId) idlen = lds32(PLe + 16u) - 2u * ln - 4u;
-            // the record starts at rs so that the sequence line (rs + idlen) is 8-byte aligned
-            const uint32_t rs = R0 + he * p.rec_buf + ((8u - (idlen & 7u)) & 7u);
-            const uint32_t w = rs + idlen;
-            my_w = w; my_ln = ln; my_flags = flags; my_rs = rs;
-            if (!(flags & (kPlanIndels | kPlanBarcode))) {
-                // 8 template bytes per step from three aligned words of the staged window; forward:
-                // seg[tb .. tb+8), reverse: seg[S-1-tb-7 .. S-1-tb] read backwards and complemented.
-                // The last store of a line may run up to 7 bytes past its end (separators come later).
-                const uint32_t d0 = (pa.x - ((pa.x - 8u) & ~15u));                     // seg's place in the window
-                const uint32_t TPe = TP + he * tplw;
+            if (flags & kPlanLongId) idlen = rec - 2u * ln - 4u;
+            const uint32_t rs = OB0 + (he * 2u + ((st >> 8) & 1u)) * obw + (st & 15u);   // the record's first byte
+            sq = rs + idlen;
+            ln_e = ln;
+            const uint32_t f_any = __shfl_sync(0xffffffffu, flags, 0) | __shfl_sync(0xffffffffu, flags, 16);
+            const uint32_t grp = __shfl_sync(0xffffffffu, grp_e, 0);
+            if (grp != lds32(SC0 + 32u)) {                    // a new (haplotype, chromosome) group: its prefix into the cache
+                __syncwarp();
+                const GroupDev* Gp = p.groups + grp;
+                const uint32_t n = Gp->prefix_len;
+                if (lane < n) sts8(SC0 + lane, p.strpool[Gp->prefix_off + lane]);
+                if (lane == 0) { sts32(SC0 + 32u, grp); sts32(SC0 + 36u, n); }
+                __syncwarp();
+            }
+            // ---- phase A: template base codes into the end's code line (8-byte aligned), from the staged window
+            const uint32_t CDe = CD0 + he * codw;
+            if (mine && !(flags & (kPlanIndels | kPlanBarcode))) {
+                const bool reverse = flags & kPlanReverse;
+                const uint32_t d0 = (pa.x - ((pa.x - 8u) & ~15u));                       // seg's place in the window
                 for (uint32_t tb = 8u * hl; tb < ln; tb += 128u) {
+                    // 8 template bytes from three aligned words; forward: seg[tb .. tb+8), reverse: seg[S-1-tb-7 .. S-1-tb]
+                    // read backwards and complemented.  The last store of a line may run up to 7 bytes past its end.
                     const uint32_t bo = reverse ? d0 + S - 8u - tb : d0 + tb;
                     const uint32_t wa = TPe + (bo & ~3u), sh = (bo & 3u) * 8u;
                     const uint32_t g0 = lds32(wa), g1 = lds32(wa + 4u), g2 = lds32(wa + 8u);
@@ -686,46 +728,55 @@ k_reads(const __grid_constant__ GenParams p) {
                         x1 = __byte_perm(x0, 0u, 0x0123u);
                         x0 = t;
                     }
-                    sts64(w + tb, codes4(x0, reverse), codes4(x1, reverse));
+                    sts64(CDe + tb, codes4(x0, reverse), codes4(x1, reverse));
                 }
             }
-        }
-        // ends with indels or a barcode take the whole warp, one end after the other
-        {
-            const uint32_t f0 = __shfl_sync(0xffffffffu, my_flags, 0), f1 = __shfl_sync(0xffffffffu, my_flags, 16);
-            if ((f0 | f1) & (kPlanIndels | kPlanBarcode)) {
+            // ends with indels or a barcode take the whole warp, one end after the other
+            if (f_any & (kPlanIndels | kPlanBarcode)) {
 #pragma unroll 1
                 for (uint32_t e = 0; e < n_ends; e++) {
-                    const uint32_t fe = e ? f1 : f0;
+                    const uint4 px = lds128(PLk + e * 32u);
+                    const uint32_t fe = (px.w >> 16) & 0xffu;
                     if (!(fe & (kPlanIndels | kPlanBarcode))) continue;
-                    const uint4 pa = lds128(PL + e * 96u);
-                    const uint8_t* seg = reinterpret_cast<const uint8_t*>(((uint64_t)pa.y << 32) | pa.x);
-                    const uint32_t w = __shfl_sync(0xffffffffu, my_w, 16 * e), ln = pa.w & 0xffffu;
-                    const GroupDev* Gp = p.groups + lds32(PL + e * 96u + 20u);
+                    const uint8_t* seg = reinterpret_cast<const uint8_t*>(((uint64_t)px.y << 32) | px.x);
+                    const GroupDev* Gp = p.groups + grp;
                     const uint8_t* bc = p.strpool + Gp->bc_off;
-                    if (fe & kPlanIndels) gather_indels(p, e, j, w, seg, bc, pa.z, Gp->bc_len, ln, fe & kPlanReverse);
-                    else gather_barcode(w, seg, bc, pa.z, Gp->bc_len, ln, fe & kPlanReverse);
+                    if (fe & kPlanIndels) gather_indels(p, e, j, CD0 + e * codw, seg, bc, px.z, Gp->bc_len, px.w & 0xffffu, fe & kPlanReverse);
+                    else gather_barcode(CD0 + e * codw, seg, bc, px.z, Gp->bc_len, px.w & 0xffffu, fe & kPlanReverse);
+                }
+            }
+            // ---- ID line "@<genome>-<chrom>-<start>-<F|R>[/<1|2>]\n" (fill_fq_lines, src/hts_illumina.cpp:296-312) and the
+            //      separators, in place
+            if (mine) {
+                const uint32_t pfx_len = lds32(SC0 + 36u);
+                const uint2 sv = lds64(PLk + he * 32u + 24u);                          // start coordinate
+                if (pfx_len <= 32u && sv.y == 0u) {
+                    if (hl < pfx_len) sts8(rs + hl, lds8(SC0 + hl));
+                    if (hl + 16u < pfx_len) sts8(rs + hl + 16u, lds8(SC0 + hl + 16u));
+                    const uint32_t nd = idlen - pfx_len - 3u - (n_ends == 2 ? 2u : 0u);
+                    const uint32_t at = rs + pfx_len;
+                    if (hl < 10u) {
+                        const uint32_t q = hl == 0 ? sv.x : (uint32_t)__umul64hi((uint64_t)sv.x, c_m10[hl]);   // start / 10^hl
+                        const uint32_t dig = q - 10u * (__umulhi(q, 0xCCCCCCCDu) >> 3);
+                        if (hl < nd) sts8(at + nd - 1u - hl, '0' + dig);
+                    } else {
+                        // "-F/1\n" or "-F\n": lanes 10.. write one byte each
+                        const uint32_t fr = (flags & kPlanReverse) ? 'R' : 'F';
+                        const uint32_t t = hl - 10u;
+                        const uint32_t ch = t == 0 ? '-' : t == 1 ? fr : n_ends == 2 ? (t == 2 ? '/' : t == 3 ? '1' + he : '\n') : '\n';
+                        if (t < (n_ends == 2 ? 5u : 3u)) sts8(at + nd + t, ch);
+                    }
+                } else if (hl == 0) {
+                    slow_idline(p, rs, p.groups + grp, ((uint64_t)sv.y << 32) | sv.x, flags & kPlanReverse, he);
+                }
+                if (hl == 15u) {
+                    sts8(sq + ln, '\n'); sts8(sq + ln + 1, '+'); sts8(sq + ln + 2, '\n');
+                    sts8(sq + 2 * ln + 3, '\n');
                 }
             }
         }
-        __syncwarp();
-        // ID line, separators
-        if (mine) {
-            const uint32_t idlen = my_w - my_rs;
-            if (!(my_flags & kPlanLongId)) {
-                for (uint32_t t = hl; t < idlen; t += 16u) sts8(my_rs + t, lds8(PLe + 32u + t));
-            } else if (hl == 0) {
-                const uint2 sp = lds64(PLe);
-                long_idline(p, my_rs, p.groups + lds32(PLe + 20u), reinterpret_cast<const uint8_t*>(((uint64_t)sp.y << 32) | sp.x),
-                            my_flags & kPlanReverse, he);
-            }
-            if (hl == 0) {
-                sts8(my_w + my_ln, '\n'); sts8(my_w + my_ln + 1, '+'); sts8(my_w + my_ln + 2, '\n');
-                sts8(my_w + 2 * my_ln + 3, '\n');
-            }
-        }
-        const uint32_t sq0 = __shfl_sync(0xffffffffu, my_w, 0), sq1 = __shfl_sync(0xffffffffu, my_w, 16);
-        const uint32_t len0 = __shfl_sync(0xffffffffu, my_ln, 0), len1 = n_ends == 2 ? __shfl_sync(0xffffffffu, my_ln, 16) : 0u;
+        const uint32_t sq0 = __shfl_sync(0xffffffffu, sq, 0), sq1 = __shfl_sync(0xffffffffu, sq, 16);
+        const uint32_t len0 = __shfl_sync(0xffffffffu, ln_e, 0), len1 = n_ends == 2 ? __shfl_sync(0xffffffffu, ln_e, 16) : 0u;
         __syncwarp();
 
         // ---- phase B
@@ -744,7 +795,7 @@ k_reads(const __grid_constant__ GenParams p) {
                 const uint32_t meta_a = second ? mA1 : mA0, ent_a = second ? eA1 : eA0;
                 const bool two = pos + 1u < ln;
                 const U4 w = qual_block(p, j, blk, e);
-                const uint32_t cc = lds16(s0);
+                const uint32_t cc = lds16(CD0 + e * codw + pos);
                 const uint32_t c0 = cc & 0xffu, c1 = two ? cc >> 8 : 0u, pos1 = two ? pos + 1u : pos;
                 const uint32_t ct0 = min(c0, 3u), ct1 = min(c1, 3u);
                 uint32_t x0, x1;
@@ -766,46 +817,60 @@ k_reads(const __grid_constant__ GenParams p) {
                         qq = (qq & 0xffu) | (r & 0xff00u);
                     }
                 }
+                sts8(s0, asc);
+                sts8(q0, qq);
                 if (two) {
-                    sts16(s0, asc);
-                    sts8(q0, qq);
+                    sts8(s0 + 1u, asc >> 8);
                     sts8(q0 + 1u, qq >> 8);
-                } else {
-                    sts8(s0, asc);
-                    sts8(q0, qq);
                 }
             }
         }
+        // ---- flush: the 16-byte chunks this end's record completes leave as one bulk copy
+        fence_async_smem();
         __syncwarp();
-
-        // ---- phase C: each half-warp moves its end's record to its final offset
-        if (mine) {
-            const uint2 ov = lds64(PLe + 24u);
-            const uint64_t o = ((uint64_t)ov.y << 32) | ov.x;
-            const uint32_t idlen = my_w - my_rs;
-            const uint32_t a = ov.x & 15u, total = a + idlen + 2u * my_ln + 4u;
-            uint8_t* dst = p.out[he] + (o - a);
-            const uint32_t src = my_rs - a;                    // shared address of the byte that lands on dst[0]
-            const uint32_t sh = (src & 3u) * 8u, srcw = src & ~3u;
-            // whole 16-byte chunks of the file that lie inside the record
-            const uint32_t first = a ? 16u : 0u, last = total & ~15u;
-            for (uint32_t lo = first + hl * 16u; lo < last; lo += 256u) {
-                const uint32_t x0 = lds32(srcw + lo), x1 = lds32(srcw + lo + 4u), x2 = lds32(srcw + lo + 8u),
-                               x3 = lds32(srcw + lo + 12u), x4 = lds32(srcw + lo + 16u);
-                *reinterpret_cast<uint4*>(dst + lo) =
-                    make_uint4(__funnelshift_r(x0, x1, sh), __funnelshift_r(x1, x2, sh), __funnelshift_r(x2, x3, sh),
-                               __funnelshift_r(x3, x4, sh));
+        {
+            const uint32_t apos = st & 15u, hole = (st >> 4) & 15u, cur = (st >> 8) & 1u;
+            const uint32_t total = apos + (mine ? lds32(PLk + he * 32u + 16u) : 0u);   // bytes of the buffer in use
+            const uint32_t nfl = total & ~15u;                                       // ... of which whole chunks
+            const uint32_t buf = OB0 + (he * 2u + cur) * obw;
+            if (nfl) {
+                // first chunk of the run: only our bytes of it, one per lane
+                if (hole && hl >= hole) gbase[hl] = (uint8_t)lds8(buf + hl);
+                const uint32_t skip = hole ? 16u : 0u;
+                if (hl == 0 && nfl > skip) bulk_s2g(gbase + skip, buf + skip, nfl - skip);
             }
-            // the record's share of its first and last chunk, one byte per lane
-            {
-                const uint32_t k = a + hl;
-                if (a && k < 16u && k < total) dst[k] = (uint8_t)lds8(src + k);
-                const uint32_t k2 = last + hl;
-                if (k2 < total && (last >= 16u || !a)) dst[k2] = (uint8_t)lds8(src + k2);
-            }
+            if (hl == 0) { bulk_commit(); bulk_wait_read<1>(); }     // the copy out of the other buffer (previous pair) has been read
+            __syncwarp();
+            // carry the unfinished chunk into the other buffer; the next record continues right behind it
+            if (mine && hl == 0) sts128(OB0 + (he * 2u + (cur ^ 1u)) * obw, lds128(buf + nfl));
+            gbase += nfl;
+            // apos = total - nfl; hole stays only while nothing has been flushed; the other buffer; the next template slot
+            const uint32_t slot = (st >> 9) & 3u;
+            st = (st & 0x3800u) | (total & 15u) | (nfl ? 0u : hole << 4) | ((cur ^ 1u) << 8) | ((slot == kTplSlots - 1u ? 0u : slot + 1u) << 9);
         }
         __syncwarp();
+
+        // ---- staging for the pairs ahead
+        if (k + 2u < n_run) {
+            if (((k + 2u) & 7u) == 0u) mbar_wait(MB0, ((k + 2u) >> 3) & 1u);       // the chunk of pair k + 2 has landed
+            const uint32_t s2 = (st >> 9) & 3u;                                      // slot of pair k + 1 -> pair k + 2 goes one further
+            stage_tpl(k + 2u, s2 == kTplSlots - 1u ? 0u : s2 + 1u);
+        }
+        // chunk c's buffer is free once its last pair is done: chunk c + 2 takes it
+        if ((k & 7u) == 7u && (k >> 3) + 2u < n_chunks) stage_chunk((k >> 3) + 2u);
     }
+    // ---- the run's last, unfinished chunk: byte by byte
+    {
+        const uint32_t apos = st & 15u, hole = (st >> 4) & 15u, cur = (st >> 8) & 1u;
+        if (mine && hl >= hole && hl < apos) gbase[hl] = (uint8_t)lds8(OB0 + (he * 2u + cur) * obw + hl);
+    }
+    if (hl == 0) bulk_wait_read<0>();
+#undef MB0
+#undef SC0
+#undef PL0
+#undef TP0
+#undef CD0
+#undef OB0
 }
 
 static size_t reads_table_bytes(const GenParams& p) {
@@ -824,7 +889,7 @@ static size_t reads_table_bytes(const GenParams& p) {
 // then), else with the tables read from global memory.  0: not even one warp's buffers fit (a custom profile with
 // a read length of several thousand).
 static int reads_threads(const GenParams& p, bool& use_smem) {
-    const size_t per_warp = reads_warp_bytes(p.n_ends, p.rec_buf, p.tpl_buf), tab = reads_table_bytes(p);
+    const size_t per_warp = reads_warp_bytes(p.n_ends, p.rec_buf, p.tpl_buf, p.cod_buf), tab = reads_table_bytes(p);
     const size_t with_tab = 200 * 1024, without = 226 * 1024;
     const int max_w = kReadsThreads / 32;
     int w = (int)std::min<size_t>(max_w, tab < with_tab ? (with_tab - tab) / per_warp : 0);
@@ -843,7 +908,7 @@ cudaError_t launch_reads(const GenParams& p, int n_sm, cudaStream_t s) {
     bool use_smem = false;
     const int threads = reads_threads(p, use_smem), wpc = threads / 32;
     if (threads <= 0) return cudaErrorInvalidConfiguration;
-    const size_t rec_bytes = (size_t)wpc * reads_warp_bytes(p.n_ends, p.rec_buf, p.tpl_buf);
+    const size_t rec_bytes = (size_t)wpc * reads_warp_bytes(p.n_ends, p.rec_buf, p.tpl_buf, p.cod_buf);
     const size_t smem_bytes = rec_bytes + (use_smem ? reads_table_bytes(p) : 0);
     cudaError_t err;
     int per_sm = 0;

@@ -19,20 +19,20 @@ struct GroupDev {
 };
 
 // Everything scalar about one read end, written by the placement kernel (one
-// thread per end), read by the read kernel (one warp per pair).
+// thread per end), read by the read kernel (one warp per run of consecutive pairs).
 struct EndPlan {
     const uint8_t* seg;    // first template base in HBM (chromosome + start)
     uint32_t S;            // template positions consumed, barcode included (adjust_chrom_spaces)
     uint16_t len;          // final read length
-    uint8_t flags;         // bit 0 reverse strand, 1 insertions/deletions, 2 barcode, 3 ID line not inlined
-    uint8_t idlen;         // bytes of the ID line, '\n' included (when inlined)
+    uint8_t flags;         // bit 0 reverse strand, 1 insertions/deletions, 2 barcode, 3 ID line longer than 255 bytes
+    uint8_t idlen;         // bytes of the ID line, '\n' included (when <= 255)
     uint32_t rec_len;      // FASTQ bytes of the record
     uint32_t group;
-    uint64_t off;          // byte offset of the record in its output file's batch buffer (k_offsets)
-    uint8_t idline[64];    // "@<genome>-<chrom>-<start>-<F|R>[/<1|2>]\n"
+    uint64_t start;        // the coordinate the ID line prints (leftmost template base on the chromosome)
 };
-static_assert(sizeof(EndPlan) == 96, "EndPlan layout");
+static_assert(sizeof(EndPlan) == 32, "EndPlan layout");
 constexpr uint32_t kPlanReverse = 1, kPlanIndels = 2, kPlanBarcode = 4, kPlanLongId = 8;
+constexpr uint32_t kPlanChunk = 8;      // pairs whose plans one bulk copy stages into shared memory
 
 struct EndDev {
     const uint32_t* meta;    // [4*L] offset << 8 | n
@@ -56,8 +56,9 @@ struct GenParams {
     uint32_t L;
     uint32_t matepair;
     uint32_t dup_never;      // prob_dup threshold is 0
-    uint32_t rec_buf;        // bytes of shared memory per (warp, end) record buffer
+    uint32_t rec_buf;        // bytes of shared memory per (warp, end) output buffer: 16 + the longest record, rounded to 16
     uint32_t tpl_buf;        // bytes of shared memory per staged template window (multiple of 16)
+    uint32_t cod_buf;        // bytes of shared memory per (warp, end) base-code line (multiple of 16)
     uint64_t c_dup;          // x < c_dup: duplicate of the previous fragment
     uint64_t c_rev;          // x < c_rev: reverse strand first
     EndDev end[2];
@@ -102,9 +103,6 @@ cudaError_t launch_place(const GenParams& p, cudaStream_t s);
 cudaError_t launch_scan(const uint32_t* rec_len, uint32_t n_records, uint32_t n_ends,
                         uint32_t* rec_local, uint64_t* block_tot, uint64_t* block_base,
                         uint64_t* totals_out, cudaStream_t s);
-
-// absolute record offsets into the plan: block_base + rec_local
-cudaError_t launch_offsets(const GenParams& p, cudaStream_t s);
 
 // template gather + quality/error model + FASTQ record assembly, one warp per pair;
 // n_sm sizes the persistent grid

@@ -92,10 +92,10 @@ def test_errors_become_r_errors(tmp_path):
     """Rcpp::stop in the glue -> END_RCPP of the stock wrapper -> an R error with the reference's text."""
     g = J.random_genome(1, 5_000, seed=35)
     gg = H.GlueGenome(g.names, [g.chrom(0)])
-    p1, _ = profiles(100)
-    p2 = J.flatten_profile(J.read_profile(None, "HS25", 150, 2))
-    with pytest.raises(RuntimeError, match="read lengths for R1 and R2 don't match"):      # src/hts_illumina.h:348-352
-        H.glue_illumina(gg, paired=True, matepair=False, out_prefix=str(tmp_path / "e"), n_reads=100, prof1=p1, prof2=p2, r_seed=1)
+    p1, p2 = profiles(100)
+    with pytest.raises(RuntimeError, match="barcode"):
+        H.glue_illumina(gg, paired=True, matepair=False, out_prefix=str(tmp_path / "e"), n_reads=100, prof1=p1, prof2=p2, r_seed=1,
+                        barcodes=["ACGT" * 25])
     with pytest.raises(RuntimeError, match="Unable to open file"):                          # src/io.h:288-290
         H.glue_illumina(gg, paired=False, matepair=False, out_prefix=str(tmp_path / "no" / "such" / "dir" / "x"), n_reads=100,
                         prof1=p1, prof2=None, r_seed=1)
