@@ -509,14 +509,15 @@ __device__ __noinline__ void gather_barcode(uint32_t w, const uint8_t* seg, cons
 #define JLP_READS_CTAS 1
 #endif
 constexpr int kReadsThreads = JLP_READS_THREADS;
-constexpr uint32_t kTplSlots = 3;       // staged template windows per warp: pair k is read while k+1 and k+2 are on their way
+constexpr uint32_t kTplSlots = 2;       // staged template windows per warp: pair k is read while pair k+1 is on its way
 
 // bytes of shared memory one warp of k_reads owns (host and device agree through this):
-// 4 mbarriers | 64 bytes of scratch | 2 chunks of plans | kTplSlots template windows per end | one base-code line per end |
-// two output buffers per end
+// 1 mbarrier (16 bytes) | 64 bytes of scratch | 2 chunks of plans | kTplSlots template windows per end |
+// one base-code line per end | two output buffers per end
 __host__ __device__ inline uint32_t reads_warp_bytes(uint32_t n_ends, uint32_t rec_buf, uint32_t tpl_buf, uint32_t cod_buf) {
-    return 96u + 2u * kPlanChunk * n_ends * 32u + kTplSlots * n_ends * tpl_buf + n_ends * cod_buf + 2u * n_ends * rec_buf;
+    return 80u + 2u * kPlanChunk * n_ends * 32u + kTplSlots * n_ends * tpl_buf + n_ends * cod_buf + 2u * n_ends * rec_buf;
 }
+constexpr uint32_t kReadsCtaBytes = 80;  // per CTA, in front of everything: ceil(2^64 / 10^k), k = 0..9
 
 // ---- bulk asynchronous copies (cp.async.bulk: SASS UBLKCP) and their mbarriers
 __device__ __forceinline__ void mbar_init(uint32_t a, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(a), "r"(count) : "memory"); }
@@ -567,21 +568,33 @@ __device__ __noinline__ void slow_idline(const GenParams& p, uint32_t dst, const
 __constant__ uint64_t c_m10[10] = {0ull, 1844674407370955162ull, 184467440737095517ull, 18446744073709552ull, 1844674407370956ull,
                                    184467440737096ull, 18446744073710ull, 1844674407371ull, 184467440738ull, 18446744074ull};
 
+// Four ASCII bases in one word -> four base codes (T0 C1 A2 G3), complemented on the reverse strand; `bad` collects
+// the bytes that are not T/C/A/G (non-zero: codes4_fix sets those codes to 4).
+__device__ __forceinline__ uint32_t codes4_acc(uint32_t x, bool reverse, uint32_t& bad) {
+    uint32_t x1 = (x >> 1) & 0x03030303u;                       // A0 C1 T2 G3
+    uint32_t code = x1 ^ 0x02020202u ^ ((x1 << 1) & 0x02020202u);  // T0 C1 A2 G3
+    uint32_t t = code | (code >> 4);
+    uint32_t sel = __byte_perm(t, 0u, 0x4420u);                 // one selector nibble per base
+    bad = __byte_perm(0x47414354u, 0u, sel) ^ x;
+    return reverse ? code ^ 0x02020202u : code;
+}
+
 // One warp per run of consecutive read pairs: the R1 records of a run are one contiguous span of file 1, its R2
 // records one of file 2, so a record is assembled in shared memory AT ITS FILE ALIGNMENT and leaves with one bulk
-// copy (cp.async.bulk shared -> global) of the 16-byte chunks it completes; the unfinished last chunk is carried
-// into the next record's buffer.  Only the two ragged ends of a run are written byte by byte.
+// copy (cp.async.bulk shared -> global, SASS UBLKCP) of the 16-byte chunks it completes; the unfinished last chunk is
+// carried into the next record's buffer.  Only the two ragged ends of a run are written byte by byte.
 //   staging   the plans of 8 pairs per bulk copy (global -> shared, mbarrier); the bytes around both templates of
-//             pairs k+1 and k+2 as bulk copies while pair k is processed
+//             pair k+1 by cp.async (16 bytes per lane) while pair k is processed
 //   phase A   template bytes -> base codes (T0 C1 A2 G3, other 4), reverse-complemented on the reverse strand,
-//             8 positions per lane from aligned shared words; ends with indels / a barcode take the whole warp
-//   ID line   written in place: the group's prefix from a per-warp cache, one decimal digit per lane
+//             16 positions per lane from aligned shared words; ends with indels / a barcode take the whole warp
+//   ID line   written in place, one byte per lane: the group's prefix from a per-warp cache, one decimal digit per lane
 //   phase B   (both ends in one index space, two bases per lane and Philox block) quality by the alias method,
 //             mismatch test, substitution, straight into the record; undecided draws branch to base_rare()
-//   flush     lanes 0 and 16: bulk copy of the chunks their end's record completes, commit, carry
-// Per-warp state that changes once per pair is packed into one register (st): bits 0-3 where the next record starts
-// in its buffer, 4-7 the bytes of the run's first chunk that belong to the previous run, 8 the buffer in use,
-// 9-10 the template slot, 11-13 the slots' mbarrier parities.
+//   flush     lane e < n_ends: bulk copy of the chunks end e's record completes, commit, carry
+// What changes once per pair lives in the warp's scratch, not in registers: per end where the next record starts in
+// its buffer (apos), the bytes of the run's first chunk that belong to the previous run (hole), and the offset of
+// byte 0 of the buffer in the file's batch buffer (goff).  The buffer in use, the template slot and all mbarrier
+// parities follow from the pair's index in the run.
 template <bool SMEM>
 __global__ void __launch_bounds__(kReadsThreads, JLP_READS_CTAS)
 k_reads(const __grid_constant__ GenParams p) {
@@ -589,11 +602,12 @@ k_reads(const __grid_constant__ GenParams p) {
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
     const uint32_t L = p.L;
     // table placement is a function of the launch parameters only
-    const uint32_t ent0 = 0;
+    const uint32_t ent0 = kReadsCtaBytes;
     const uint32_t meta0 = ent0 + p.end[0].entry_n * 8u;
     const uint32_t ent1 = (meta0 + 16u * L + 15u) & ~15u;
     const uint32_t meta1 = ent1 + (p.n_ends == 2 ? p.end[1].entry_n * 8u : 0u);
-    const uint32_t tab_bytes = !SMEM ? 0u : p.n_ends == 2 ? ((meta1 + 16u * L + 15u) & ~15u) : ent1;
+    const uint32_t tab_bytes = !SMEM ? kReadsCtaBytes : p.n_ends == 2 ? ((meta1 + 16u * L + 15u) & ~15u) : ent1;
+    if (threadIdx.x < 10) reinterpret_cast<uint64_t*>(smem)[threadIdx.x] = c_m10[threadIdx.x];
     if (SMEM) {
         for (uint32_t e = 0; e < p.n_ends; e++) {
             const EndDev& E = p.end[e];
@@ -602,20 +616,19 @@ k_reads(const __grid_constant__ GenParams p) {
             uint32_t* m = reinterpret_cast<uint32_t*>(smem + (e ? meta1 : meta0));
             for (uint32_t i = threadIdx.x; i < 4 * L; i += blockDim.x) m[i] = E.meta[i];
         }
-        __syncthreads();
     }
+    __syncthreads();
     uint32_t lane;
-    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));      // kept in a register (the compiler would re-read SR_TID)
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
     const uint32_t warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     const uint32_t n_ends = p.n_ends;
     const uint32_t tplw = p.tpl_buf, codw = p.cod_buf, obw = p.rec_buf;
-    // this warp's shared memory: 4 mbarriers (plan chunks; template slots 0, 1, 2) | 64 bytes of scratch (the current
-    // group's ID-line prefix, its index and length) | 2 plan chunks | template windows | code lines | output buffers
     const uint32_t W0 = sbase + tab_bytes + warp * reads_warp_bytes(n_ends, obw, tplw, codw);
     const uint32_t plan_pair = n_ends * 32u;                  // bytes of plan per pair
 #define MB0 (W0)
-#define SC0 (W0 + 32u)
-#define PL0 (W0 + 96u)
+#define SC0 (W0 + 16u)
+#define ST0 (W0 + 56u)                                        /* per end 8 bytes: apos | hole << 8, goff */
+#define PL0 (W0 + 80u)
 #define TP0 (PL0 + 2u * kPlanChunk * plan_pair)
 #define CD0 (TP0 + kTplSlots * n_ends * tplw)
 #define OB0 (CD0 + n_ends * codw)
@@ -627,78 +640,79 @@ k_reads(const __grid_constant__ GenParams p) {
     const uint32_t n_run = min(per, p.batch_pairs - r0);
     if (n_run == 0) return;
 
-    const uint32_t he = lane >> 4, hl = lane & 15u;           // phase A, ID line and flush: one half-warp per end
+    const uint32_t he = lane >> 4, hl = lane & 15u;           // phase A and ID line: one half-warp per end
     const bool mine = he < n_ends;
-    // where the run's first record of this lane's end goes: its offset in the file's batch buffer
-    uint8_t* gbase = nullptr;                                 // global address of byte 0 of the output buffer in use (16-byte aligned)
-    uint32_t st = 0;
-    if (mine) {
-        const uint64_t fo = p.block_base[(size_t)he * p.n_scan_blocks + r0 / kScanBlock] + p.rec_local[r0 * n_ends + he];
-        st = ((uint32_t)fo & 15u) * 0x11u;                    // apos = hole = fo % 16
-        gbase = p.out[he] + (fo & ~(uint64_t)15);
+    if (lane < n_ends) {
+        // where the run's first record of end `lane` goes: its offset in the file's batch buffer
+        const uint64_t fo = p.block_base[(size_t)lane * p.n_scan_blocks + r0 / kScanBlock] + p.rec_local[r0 * n_ends + lane];
+        sts32(ST0 + 8u * lane, ((uint32_t)fo & 15u) * 0x101u);    // apos = hole = fo % 16
+        sts32(ST0 + 8u * lane + 4u, (uint32_t)fo & ~15u);
     }
     if (lane == 0) {
-        mbar_init(MB0, 1); mbar_init(MB0 + 8u, 1); mbar_init(MB0 + 16u, 1); mbar_init(MB0 + 24u, 1);
+        mbar_init(MB0, 1);
         sts32(SC0 + 32u, 0xffffffffu);                        // no group cached
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
 
     // plans: chunk c (pairs 8c .. of the run) -> buffer c & 1; ONE mbarrier, whose phase c is chunk c: chunk c + 2 is
-    // issued (after pair 8c + 7) only when chunk c + 1 has been waited for (after pair 8c + 6)
+    // issued (after pair 8c + 7) only when chunk c + 1 has been waited for (during pair 8c + 7 at the latest)
     const uint32_t n_chunks = (n_run + kPlanChunk - 1u) / kPlanChunk;
     auto stage_chunk = [&](uint32_t c) {
         if (lane == 0) {
             const uint32_t np = min(kPlanChunk, n_run - c * kPlanChunk), bytes = np * plan_pair;
+            fence_async_smem();                               // the buffer's last readers (generic proxy) came before this __syncwarp
             mbar_expect_tx(MB0, bytes);
             bulk_g2s(PL0 + (c & 1u) * kPlanChunk * plan_pair, reinterpret_cast<const uint8_t*>(p.plan) + (size_t)(r0 + c * kPlanChunk) * plan_pair, bytes, MB0);
         }
     };
     auto plan_addr = [&](uint32_t k) { return PL0 + (((k >> 3) & 1u) * kPlanChunk + (k & 7u)) * plan_pair; };
-    // templates of pair k -> slot; both ends' windows complete on the slot's mbarrier
-    auto stage_tpl = [&](uint32_t k, uint32_t slot) {
-        const uint32_t mb = MB0 + 8u + 8u * slot;
-        uint32_t bytes = 0;
-        uint64_t ws = 0;
-        if (hl == 0 && mine) {
+    // the bytes around the templates of pair k -> slot k & 1: lane (he, hl) copies 16-byte chunk hl (+ 16, ...) of end he's window
+    auto stage_tpl = [&](uint32_t k) {
+        if (mine) {
             const uint4 pa = lds128(plan_addr(k) + he * 32u);
             const uint64_t sa = ((uint64_t)pa.y << 32) | pa.x;
-            ws = (sa - 8u) & ~(uint64_t)15;
-            // up to the last byte the gather can touch, plus one
-            bytes = min((uint32_t)((sa + pa.z + 12u - ws + 15u) & ~(uint64_t)15), tplw);
+            const uint64_t ws = (sa - 16u) & ~(uint64_t)15;
+            const uint32_t need = (uint32_t)(sa - ws) + pa.z + 19u;       // bytes of the window the gather can touch
+            const uint32_t dst = TP0 + ((k & 1u) * n_ends + he) * tplw;
+            for (uint32_t o = 16u * hl; o < tplw; o += 256u)
+                if (o < need) cp_async16(dst + o, reinterpret_cast<const uint8_t*>(ws) + o);
         }
-        const uint32_t b1 = __shfl_sync(0xffffffffu, bytes, 16);
-        if (lane == 0) mbar_expect_tx(mb, bytes + b1);
-        __syncwarp();
-        if (bytes) bulk_g2s(TP0 + (slot * n_ends + he) * tplw, reinterpret_cast<const void*>(ws), bytes, mb);
+        cp_async_commit();
     };
     stage_chunk(0);
     mbar_wait(MB0, 0);
     if (n_chunks > 1) stage_chunk(1);
-    stage_tpl(0, 0);
-    if (n_run > 1) stage_tpl(1, 1);
+    stage_tpl(0);
 
 #pragma unroll 1
     for (uint32_t k = 0; k < n_run; k++) {
         const uint64_t j = p.batch_lo + r0 + k;
         const uint32_t PLk = plan_addr(k);
-        {
-            const uint32_t slot = (st >> 9) & 3u;
-            mbar_wait(MB0 + 8u + 8u * slot, (st >> (11u + slot)) & 1u);
-            st ^= 0x800u << slot;
+        // ---- staging: the next pair's templates start their way; this pair's have landed
+        if (k + 1u < n_run) {
+            if (((k + 1u) & 7u) == 0u) mbar_wait(MB0, ((k + 1u) >> 3) & 1u);       // the chunk of pair k + 1 has landed
+            stage_tpl(k + 1u);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            cp_async_wait_all();
         }
+        __syncwarp();
         uint32_t sq, ln_e;                                    // this end's sequence line (shared address) and read length
         {
             // ---- this lane's end: plan fields
-            const uint32_t slot = (st >> 9) & 3u;
-            const uint32_t TPe = TP0 + (slot * n_ends + he) * tplw;
             uint4 pa = make_uint4(0, 0, 0, 0);
-            uint32_t rec = 0, grp_e = 0;
-            if (mine) { pa = lds128(PLk + he * 32u); const uint2 pb = lds64(PLk + he * 32u + 16u); rec = pb.x; grp_e = pb.y; }
+            uint32_t rec = 0, grp_e = 0, apos = 0;
+            if (mine) {
+                pa = lds128(PLk + he * 32u);
+                const uint2 pb = lds64(PLk + he * 32u + 16u);
+                rec = pb.x; grp_e = pb.y;
+                apos = lds32(ST0 + 8u * he) & 0xffu;
+            }
             const uint32_t S = pa.z, ln = pa.w & 0xffffu, flags = (pa.w >> 16) & 0xffu;
             uint32_t idlen = pa.w >> 24;
             if (flags & kPlanLongId) idlen = rec - 2u * ln - 4u;
-            const uint32_t rs = OB0 + (he * 2u + ((st >> 8) & 1u)) * obw + (st & 15u);   // the record's first byte
+            const uint32_t rs = OB0 + (he * 2u + (k & 1u)) * obw + apos;   // the record's first byte
             sq = rs + idlen;
             ln_e = ln;
             const uint32_t f_any = __shfl_sync(0xffffffffu, flags, 0) | __shfl_sync(0xffffffffu, flags, 16);
@@ -711,25 +725,29 @@ k_reads(const __grid_constant__ GenParams p) {
                 if (lane == 0) { sts32(SC0 + 32u, grp); sts32(SC0 + 36u, n); }
                 __syncwarp();
             }
-            // ---- phase A: template base codes into the end's code line (8-byte aligned), from the staged window
+            // ---- phase A: template base codes into the end's code line, 16 positions per lane from the staged window
             const uint32_t CDe = CD0 + he * codw;
-            if (mine && !(flags & (kPlanIndels | kPlanBarcode))) {
+            if (mine && !(flags & (kPlanIndels | kPlanBarcode)) && 16u * hl < ln) {
                 const bool reverse = flags & kPlanReverse;
-                const uint32_t d0 = (pa.x - ((pa.x - 8u) & ~15u));                       // seg's place in the window
-                for (uint32_t tb = 8u * hl; tb < ln; tb += 128u) {
-                    // 8 template bytes from three aligned words; forward: seg[tb .. tb+8), reverse: seg[S-1-tb-7 .. S-1-tb]
-                    // read backwards and complemented.  The last store of a line may run up to 7 bytes past its end.
-                    const uint32_t bo = reverse ? d0 + S - 8u - tb : d0 + tb;
-                    const uint32_t wa = TPe + (bo & ~3u), sh = (bo & 3u) * 8u;
-                    const uint32_t g0 = lds32(wa), g1 = lds32(wa + 4u), g2 = lds32(wa + 8u);
-                    uint32_t x0 = __funnelshift_r(g0, g1, sh), x1 = __funnelshift_r(g1, g2, sh);
-                    if (reverse) {
-                        const uint32_t t = __byte_perm(x1, 0u, 0x0123u);
-                        x1 = __byte_perm(x0, 0u, 0x0123u);
-                        x0 = t;
-                    }
-                    sts64(CDe + tb, codes4(x0, reverse), codes4(x1, reverse));
+                const uint32_t tb = 16u * hl;
+                const uint32_t d0 = pa.x - ((pa.x - 16u) & ~15u);                      // seg's place in the window: 16 .. 31
+                // forward: seg[tb .. tb+16); reverse: seg[S-1-tb-15 .. S-1-tb] read backwards and complemented
+                // (positions past the read's end hold garbage nobody reads)
+                const uint32_t bo = reverse ? d0 + S - 16u - tb : d0 + tb;
+                const uint32_t wa = TP0 + ((k & 1u) * n_ends + he) * tplw + (bo & ~3u), sh = (bo & 3u) * 8u;
+                const uint32_t g0 = lds32(wa), g1 = lds32(wa + 4u), g2 = lds32(wa + 8u), g3 = lds32(wa + 12u), g4 = lds32(wa + 16u);
+                uint32_t x0 = __funnelshift_r(g0, g1, sh), x1 = __funnelshift_r(g1, g2, sh), x2 = __funnelshift_r(g2, g3, sh),
+                         x3 = __funnelshift_r(g3, g4, sh);
+                if (reverse) {
+                    const uint32_t t0 = __byte_perm(x3, 0u, 0x0123u), t1 = __byte_perm(x2, 0u, 0x0123u);
+                    x3 = __byte_perm(x0, 0u, 0x0123u); x2 = __byte_perm(x1, 0u, 0x0123u);
+                    x0 = t0; x1 = t1;
                 }
+                uint32_t b0, b1, b2, b3;
+                uint4 c = make_uint4(codes4_acc(x0, reverse, b0), codes4_acc(x1, reverse, b1), codes4_acc(x2, reverse, b2),
+                                     codes4_acc(x3, reverse, b3));
+                if (b0 | b1 | b2 | b3) { c.x = codes4_fix(c.x, b0); c.y = codes4_fix(c.y, b1); c.z = codes4_fix(c.z, b2); c.w = codes4_fix(c.w, b3); }
+                sts128(CDe + tb, c);
             }
             // ends with indels or a barcode take the whole warp, one end after the other
             if (f_any & (kPlanIndels | kPlanBarcode)) {
@@ -746,26 +764,27 @@ k_reads(const __grid_constant__ GenParams p) {
                 }
             }
             // ---- ID line "@<genome>-<chrom>-<start>-<F|R>[/<1|2>]\n" (fill_fq_lines, src/hts_illumina.cpp:296-312) and the
-            //      separators, in place
+            //      separators, in place: prefix bytes hl and hl + 16; lanes 0-9 one decimal digit each, lanes 10-14 the
+            //      tail "-F/1\n" ("-F\n" single-end), lane 15 the four separator bytes of the record
             if (mine) {
                 const uint32_t pfx_len = lds32(SC0 + 36u);
                 const uint2 sv = lds64(PLk + he * 32u + 24u);                          // start coordinate
                 if (pfx_len <= 32u && sv.y == 0u) {
                     if (hl < pfx_len) sts8(rs + hl, lds8(SC0 + hl));
                     if (hl + 16u < pfx_len) sts8(rs + hl + 16u, lds8(SC0 + hl + 16u));
-                    const uint32_t nd = idlen - pfx_len - 3u - (n_ends == 2 ? 2u : 0u);
-                    const uint32_t at = rs + pfx_len;
-                    if (hl < 10u) {
-                        const uint32_t q = hl == 0 ? sv.x : (uint32_t)__umul64hi((uint64_t)sv.x, c_m10[hl]);   // start / 10^hl
-                        const uint32_t dig = q - 10u * (__umulhi(q, 0xCCCCCCCDu) >> 3);
-                        if (hl < nd) sts8(at + nd - 1u - hl, '0' + dig);
-                    } else {
-                        // "-F/1\n" or "-F\n": lanes 10.. write one byte each
-                        const uint32_t fr = (flags & kPlanReverse) ? 'R' : 'F';
-                        const uint32_t t = hl - 10u;
-                        const uint32_t ch = t == 0 ? '-' : t == 1 ? fr : n_ends == 2 ? (t == 2 ? '/' : t == 3 ? '1' + he : '\n') : '\n';
-                        if (t < (n_ends == 2 ? 5u : 3u)) sts8(at + nd + t, ch);
-                    }
+                    const uint32_t nt = n_ends == 2 ? 5u : 3u;
+                    const uint32_t nd = idlen - pfx_len - nt;
+                    const uint2 mm = lds64(sbase + 8u * min(hl, 9u));
+                    const uint32_t q = hl == 0 ? sv.x : (uint32_t)__umul64hi((uint64_t)sv.x, ((uint64_t)mm.y << 32) | mm.x);   // start / 10^hl
+                    const uint32_t dig = q - 10u * (__umulhi(q, 0xCCCCCCCDu) >> 3);
+                    const uint32_t fr = (flags & kPlanReverse) ? 'R' : 'F';
+                    const uint32_t tw = n_ends == 2 ? ('-' | fr << 8 | '/' << 16 | ('1' + he) << 24) : ('-' | fr << 8 | '\n' << 16);
+                    const uint32_t t = hl - 10u;                                       // lanes 10..: byte t of the tail
+                    const uint32_t tc = t < 4u ? (tw >> (8u * t)) & 0xffu : '\n';
+                    const bool is_dig = hl < 10u;
+                    const uint32_t ch = is_dig ? '0' + dig : tc;
+                    const uint32_t at = rs + pfx_len + (is_dig ? nd - 1u - hl : nd + t);
+                    if (is_dig ? hl < nd : t < nt) sts8(at, ch);
                 } else if (hl == 0) {
                     slow_idline(p, rs, p.groups + grp, ((uint64_t)sv.y << 32) | sv.x, flags & kPlanReverse, he);
                 }
@@ -825,48 +844,47 @@ k_reads(const __grid_constant__ GenParams p) {
                 }
             }
         }
-        // ---- flush: the 16-byte chunks this end's record completes leave as one bulk copy
+        // ---- flush: the 16-byte chunks a record completes leave as one bulk copy
         fence_async_smem();
         __syncwarp();
-        {
-            const uint32_t apos = st & 15u, hole = (st >> 4) & 15u, cur = (st >> 8) & 1u;
-            const uint32_t total = apos + (mine ? lds32(PLk + he * 32u + 16u) : 0u);   // bytes of the buffer in use
-            const uint32_t nfl = total & ~15u;                                       // ... of which whole chunks
-            const uint32_t buf = OB0 + (he * 2u + cur) * obw;
-            if (nfl) {
-                // first chunk of the run: only our bytes of it, one per lane
-                if (hole && hl >= hole) gbase[hl] = (uint8_t)lds8(buf + hl);
-                const uint32_t skip = hole ? 16u : 0u;
-                if (hl == 0 && nfl > skip) bulk_s2g(gbase + skip, buf + skip, nfl - skip);
+        if (mine) {
+            // the run's first chunk holds bytes of the previous run: our bytes of it go out one per lane (first pair(s) only)
+            const uint32_t sh = lds32(ST0 + 8u * he), hole = sh >> 8;
+            if (hole) {
+                const uint32_t total = (sh & 0xffu) + lds32(PLk + he * 32u + 16u);
+                if (total >= 16u && hl >= hole)
+                    (he ? p.out[1] : p.out[0])[lds32(ST0 + 8u * he + 4u) + hl] = (uint8_t)lds8(OB0 + (he * 2u + (k & 1u)) * obw + hl);
             }
-            if (hl == 0) { bulk_commit(); bulk_wait_read<1>(); }     // the copy out of the other buffer (previous pair) has been read
-            __syncwarp();
-            // carry the unfinished chunk into the other buffer; the next record continues right behind it
-            if (mine && hl == 0) sts128(OB0 + (he * 2u + (cur ^ 1u)) * obw, lds128(buf + nfl));
-            gbase += nfl;
-            // apos = total - nfl; hole stays only while nothing has been flushed; the other buffer; the next template slot
-            const uint32_t slot = (st >> 9) & 3u;
-            st = (st & 0x3800u) | (total & 15u) | (nfl ? 0u : hole << 4) | ((cur ^ 1u) << 8) | ((slot == kTplSlots - 1u ? 0u : slot + 1u) << 9);
         }
         __syncwarp();
-
-        // ---- staging for the pairs ahead
-        if (k + 2u < n_run) {
-            if (((k + 2u) & 7u) == 0u) mbar_wait(MB0, ((k + 2u) >> 3) & 1u);       // the chunk of pair k + 2 has landed
-            const uint32_t s2 = (st >> 9) & 3u;                                      // slot of pair k + 1 -> pair k + 2 goes one further
-            stage_tpl(k + 2u, s2 == kTplSlots - 1u ? 0u : s2 + 1u);
+        if (lane < n_ends) {                                  // lane e serves end e
+            const uint32_t sh = lds32(ST0 + 8u * lane), hole = sh >> 8, goff = lds32(ST0 + 8u * lane + 4u);
+            const uint32_t total = (sh & 0xffu) + lds32(PLk + lane * 32u + 16u);       // bytes of the buffer in use
+            const uint32_t nfl = total & ~15u;                                       // ... of which whole chunks
+            const uint32_t buf = OB0 + (lane * 2u + (k & 1u)) * obw;
+            const uint32_t skip = hole ? 16u : 0u;
+            if (nfl > skip) bulk_s2g((lane ? p.out[1] : p.out[0]) + goff + skip, buf + skip, nfl - skip);
+            bulk_commit();
+            bulk_wait_read<1>();                              // the copy out of the other buffer (previous pair) has been read
+            // carry the unfinished chunk into the other buffer; the next record continues right behind it
+            sts128(OB0 + (lane * 2u + ((k & 1u) ^ 1u)) * obw, lds128(buf + nfl));
+            sts32(ST0 + 8u * lane, (total & 15u) | (nfl ? 0u : hole << 8));
+            sts32(ST0 + 8u * lane + 4u, goff + nfl);
         }
+        __syncwarp();
         // chunk c's buffer is free once its last pair is done: chunk c + 2 takes it
         if ((k & 7u) == 7u && (k >> 3) + 2u < n_chunks) stage_chunk((k >> 3) + 2u);
     }
     // ---- the run's last, unfinished chunk: byte by byte
-    {
-        const uint32_t apos = st & 15u, hole = (st >> 4) & 15u, cur = (st >> 8) & 1u;
-        if (mine && hl >= hole && hl < apos) gbase[hl] = (uint8_t)lds8(OB0 + (he * 2u + cur) * obw + hl);
+    if (mine) {
+        const uint32_t sh = lds32(ST0 + 8u * he), apos = sh & 0xffu, hole = sh >> 8;
+        if (hl >= hole && hl < apos)
+            (he ? p.out[1] : p.out[0])[lds32(ST0 + 8u * he + 4u) + hl] = (uint8_t)lds8(OB0 + (he * 2u + (n_run & 1u)) * obw + hl);
     }
-    if (hl == 0) bulk_wait_read<0>();
+    if (lane < n_ends) bulk_wait_read<0>();
 #undef MB0
 #undef SC0
+#undef ST0
 #undef PL0
 #undef TP0
 #undef CD0
@@ -875,7 +893,7 @@ k_reads(const __grid_constant__ GenParams p) {
 
 static size_t reads_table_bytes(const GenParams& p) {
     // same layout as in k_reads: entry64[0], meta[0], (entry64[1], meta[1]), each end 16-byte aligned
-    size_t b = (size_t)p.end[0].entry_n * 8 + 16 * (size_t)p.L;
+    size_t b = kReadsCtaBytes + (size_t)p.end[0].entry_n * 8 + 16 * (size_t)p.L;
     b = (b + 15) & ~(size_t)15;
     if (p.n_ends == 2) {
         b += (size_t)p.end[1].entry_n * 8 + 16 * (size_t)p.L;
@@ -909,7 +927,7 @@ cudaError_t launch_reads(const GenParams& p, int n_sm, cudaStream_t s) {
     const int threads = reads_threads(p, use_smem), wpc = threads / 32;
     if (threads <= 0) return cudaErrorInvalidConfiguration;
     const size_t rec_bytes = (size_t)wpc * reads_warp_bytes(p.n_ends, p.rec_buf, p.tpl_buf, p.cod_buf);
-    const size_t smem_bytes = rec_bytes + (use_smem ? reads_table_bytes(p) : 0);
+    const size_t smem_bytes = rec_bytes + (use_smem ? reads_table_bytes(p) : kReadsCtaBytes);
     cudaError_t err;
     int per_sm = 0;
     if (use_smem) {
