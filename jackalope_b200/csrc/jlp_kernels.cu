@@ -513,9 +513,9 @@ constexpr uint32_t kTplSlots = 2;       // staged template windows per warp: pai
 
 // bytes of shared memory one warp of k_reads owns (host and device agree through this):
 // 1 mbarrier (16 bytes) | 64 bytes of scratch | 2 chunks of plans | kTplSlots template windows per end |
-// one base-code line per end | two output buffers per end
+// one base-code line per end | one output buffer per end
 __host__ __device__ inline uint32_t reads_warp_bytes(uint32_t n_ends, uint32_t rec_buf, uint32_t tpl_buf, uint32_t cod_buf) {
-    return 80u + 2u * kPlanChunk * n_ends * 32u + kTplSlots * n_ends * tpl_buf + n_ends * cod_buf + 2u * n_ends * rec_buf;
+    return 80u + 2u * kPlanChunk * n_ends * 32u + kTplSlots * n_ends * tpl_buf + n_ends * cod_buf + n_ends * rec_buf;
 }
 constexpr uint32_t kReadsCtaBytes = 80;  // per CTA, in front of everything: ceil(2^64 / 10^k), k = 0..9
 
@@ -580,22 +580,25 @@ __device__ __forceinline__ uint32_t codes4_acc(uint32_t x, bool reverse, uint32_
 }
 
 // One warp per run of consecutive read pairs: the R1 records of a run are one contiguous span of file 1, its R2
-// records one of file 2, so a record is assembled in shared memory AT ITS FILE ALIGNMENT and leaves with one bulk
-// copy (cp.async.bulk shared -> global, SASS UBLKCP) of the 16-byte chunks it completes; the unfinished last chunk is
-// carried into the next record's buffer.  Only the two ragged ends of a run are written byte by byte.
-//   staging   the plans of 8 pairs per bulk copy (global -> shared, mbarrier); the bytes around both templates of
-//             pair k+1 by cp.async (16 bytes per lane) while pair k is processed
+// records one of file 2, so a record is assembled in shared memory AT ITS FILE ALIGNMENT: the 16-byte chunks it
+// completes go to the file with one 128-bit load and one 128-bit store per lane and chunk (no shifting), the
+// unfinished last chunk moves to the front of the buffer and the next record continues behind it.  Only the two
+// ragged ends of a run are written byte by byte.
+//   staging   the plans of 8 pairs per bulk copy (cp.async.bulk global -> shared on an mbarrier, SASS UBLKCP); the
+//             bytes around both templates of pair k+1 by cp.async (16 bytes per lane) while pair k is processed
 //   phase A   template bytes -> base codes (T0 C1 A2 G3, other 4), reverse-complemented on the reverse strand,
 //             16 positions per lane from aligned shared words; ends with indels / a barcode take the whole warp
 //   ID line   written in place, one byte per lane: the group's prefix from a per-warp cache, one decimal digit per lane
 //   phase B   (both ends in one index space, two bases per lane and Philox block) quality by the alias method,
 //             mismatch test, substitution, straight into the record; undecided draws branch to base_rare()
-//   flush     lane e < n_ends: bulk copy of the chunks end e's record completes, commit, carry
+//   flush     all lanes: chunk c of the two records' finished chunks, shared -> global
+// (Measured: the same flush as cp.async.bulk shared -> global copies, one per record, costs about twice the
+//  instructions -- operands through uniform registers, proxy fence, commit / wait, a second buffer -- DESIGN.md.)
 // What changes once per pair lives in the warp's scratch, not in registers: per end where the next record starts in
 // its buffer (apos), the bytes of the run's first chunk that belong to the previous run (hole), and the offset of
-// byte 0 of the buffer in the file's batch buffer (goff).  The buffer in use, the template slot and all mbarrier
-// parities follow from the pair's index in the run.
-template <bool SMEM>
+// byte 0 of the buffer in the file's batch buffer (goff).  The template slot and the mbarrier parity follow from the
+// pair's index in the run.  NE: read ends per fragment (compile-time: paired / single).
+template <bool SMEM, uint32_t NE>
 __global__ void __launch_bounds__(kReadsThreads, JLP_READS_CTAS)
 k_reads(const __grid_constant__ GenParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -605,11 +608,11 @@ k_reads(const __grid_constant__ GenParams p) {
     const uint32_t ent0 = kReadsCtaBytes;
     const uint32_t meta0 = ent0 + p.end[0].entry_n * 8u;
     const uint32_t ent1 = (meta0 + 16u * L + 15u) & ~15u;
-    const uint32_t meta1 = ent1 + (p.n_ends == 2 ? p.end[1].entry_n * 8u : 0u);
-    const uint32_t tab_bytes = !SMEM ? kReadsCtaBytes : p.n_ends == 2 ? ((meta1 + 16u * L + 15u) & ~15u) : ent1;
+    const uint32_t meta1 = ent1 + (NE == 2 ? p.end[1].entry_n * 8u : 0u);
+    const uint32_t tab_bytes = !SMEM ? kReadsCtaBytes : NE == 2 ? ((meta1 + 16u * L + 15u) & ~15u) : ent1;
     if (threadIdx.x < 10) reinterpret_cast<uint64_t*>(smem)[threadIdx.x] = c_m10[threadIdx.x];
     if (SMEM) {
-        for (uint32_t e = 0; e < p.n_ends; e++) {
+        for (uint32_t e = 0; e < NE; e++) {
             const EndDev& E = p.end[e];
             uint64_t* en = reinterpret_cast<uint64_t*>(smem + (e ? ent1 : ent0));
             for (uint32_t i = threadIdx.x; i < E.entry_n; i += blockDim.x) en[i] = E.entry64[i];
@@ -621,17 +624,16 @@ k_reads(const __grid_constant__ GenParams p) {
     uint32_t lane;
     asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
     const uint32_t warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
-    const uint32_t n_ends = p.n_ends;
     const uint32_t tplw = p.tpl_buf, codw = p.cod_buf, obw = p.rec_buf;
-    const uint32_t W0 = sbase + tab_bytes + warp * reads_warp_bytes(n_ends, obw, tplw, codw);
-    const uint32_t plan_pair = n_ends * 32u;                  // bytes of plan per pair
+    const uint32_t W0 = sbase + tab_bytes + warp * reads_warp_bytes(NE, obw, tplw, codw);
+    constexpr uint32_t plan_pair = NE * 32u;                  // bytes of plan per pair
 #define MB0 (W0)
 #define SC0 (W0 + 16u)
 #define ST0 (W0 + 56u)                                        /* per end 8 bytes: apos | hole << 8, goff */
 #define PL0 (W0 + 80u)
 #define TP0 (PL0 + 2u * kPlanChunk * plan_pair)
-#define CD0 (TP0 + kTplSlots * n_ends * tplw)
-#define OB0 (CD0 + n_ends * codw)
+#define CD0 (TP0 + kTplSlots * NE * tplw)
+#define OB0 (CD0 + NE * codw)
 
     // ---- this warp's run of pairs
     const uint32_t n_warps = gridDim.x * wpc;
@@ -641,10 +643,10 @@ k_reads(const __grid_constant__ GenParams p) {
     if (n_run == 0) return;
 
     const uint32_t he = lane >> 4, hl = lane & 15u;           // phase A and ID line: one half-warp per end
-    const bool mine = he < n_ends;
-    if (lane < n_ends) {
+    const bool mine = he < NE;
+    if (lane < NE) {
         // where the run's first record of end `lane` goes: its offset in the file's batch buffer
-        const uint64_t fo = p.block_base[(size_t)lane * p.n_scan_blocks + r0 / kScanBlock] + p.rec_local[r0 * n_ends + lane];
+        const uint64_t fo = p.block_base[(size_t)lane * p.n_scan_blocks + r0 / kScanBlock] + p.rec_local[r0 * NE + lane];
         sts32(ST0 + 8u * lane, ((uint32_t)fo & 15u) * 0x101u);    // apos = hole = fo % 16
         sts32(ST0 + 8u * lane + 4u, (uint32_t)fo & ~15u);
     }
@@ -666,17 +668,19 @@ k_reads(const __grid_constant__ GenParams p) {
             bulk_g2s(PL0 + (c & 1u) * kPlanChunk * plan_pair, reinterpret_cast<const uint8_t*>(p.plan) + (size_t)(r0 + c * kPlanChunk) * plan_pair, bytes, MB0);
         }
     };
-    auto plan_addr = [&](uint32_t k) { return PL0 + (((k >> 3) & 1u) * kPlanChunk + (k & 7u)) * plan_pair; };
+    auto plan_addr = [&](uint32_t k) { return PL0 + (k & 15u) * plan_pair; };      // buffer (k >> 3) & 1, entry k & 7
     // the bytes around the templates of pair k -> slot k & 1: lane (he, hl) copies 16-byte chunk hl (+ 16, ...) of end he's window
     auto stage_tpl = [&](uint32_t k) {
         if (mine) {
             const uint4 pa = lds128(plan_addr(k) + he * 32u);
             const uint64_t sa = ((uint64_t)pa.y << 32) | pa.x;
             const uint64_t ws = (sa - 16u) & ~(uint64_t)15;
-            const uint32_t need = (uint32_t)(sa - ws) + pa.z + 19u;       // bytes of the window the gather can touch
-            const uint32_t dst = TP0 + ((k & 1u) * n_ends + he) * tplw;
-            for (uint32_t o = 16u * hl; o < tplw; o += 256u)
-                if (o < need) cp_async16(dst + o, reinterpret_cast<const uint8_t*>(ws) + o);
+            const uint32_t need = (pa.x & 15u) + 16u + pa.z + 19u;          // bytes of the window the gather can touch
+            const uint32_t dst = TP0 + ((k & 1u) * NE + he) * tplw;
+            const uint32_t o = 16u * hl;
+            if (o < min(need, tplw)) cp_async16(dst + o, reinterpret_cast<const uint8_t*>(ws) + o);
+            if (tplw > 256u)                                              // read lengths above 190
+                for (uint32_t o2 = o + 256u; o2 < min(need, tplw); o2 += 256u) cp_async16(dst + o2, reinterpret_cast<const uint8_t*>(ws) + o2);
         }
         cp_async_commit();
     };
@@ -712,10 +716,10 @@ k_reads(const __grid_constant__ GenParams p) {
             const uint32_t S = pa.z, ln = pa.w & 0xffffu, flags = (pa.w >> 16) & 0xffu;
             uint32_t idlen = pa.w >> 24;
             if (flags & kPlanLongId) idlen = rec - 2u * ln - 4u;
-            const uint32_t rs = OB0 + (he * 2u + (k & 1u)) * obw + apos;   // the record's first byte
+            const uint32_t rs = OB0 + he * obw + apos;        // the record's first byte
             sq = rs + idlen;
             ln_e = ln;
-            const uint32_t f_any = __shfl_sync(0xffffffffu, flags, 0) | __shfl_sync(0xffffffffu, flags, 16);
+            const uint32_t f_any = NE == 2 ? __shfl_sync(0xffffffffu, flags, 0) | __shfl_sync(0xffffffffu, flags, 16) : __shfl_sync(0xffffffffu, flags, 0);
             const uint32_t grp = __shfl_sync(0xffffffffu, grp_e, 0);
             if (grp != lds32(SC0 + 32u)) {                    // a new (haplotype, chromosome) group: its prefix into the cache
                 __syncwarp();
@@ -726,15 +730,14 @@ k_reads(const __grid_constant__ GenParams p) {
                 __syncwarp();
             }
             // ---- phase A: template base codes into the end's code line, 16 positions per lane from the staged window
-            const uint32_t CDe = CD0 + he * codw;
             if (mine && !(flags & (kPlanIndels | kPlanBarcode)) && 16u * hl < ln) {
                 const bool reverse = flags & kPlanReverse;
                 const uint32_t tb = 16u * hl;
-                const uint32_t d0 = pa.x - ((pa.x - 16u) & ~15u);                      // seg's place in the window: 16 .. 31
+                const uint32_t d0 = (pa.x & 15u) + 16u;                               // seg's place in the window: 16 .. 31
                 // forward: seg[tb .. tb+16); reverse: seg[S-1-tb-15 .. S-1-tb] read backwards and complemented
                 // (positions past the read's end hold garbage nobody reads)
                 const uint32_t bo = reverse ? d0 + S - 16u - tb : d0 + tb;
-                const uint32_t wa = TP0 + ((k & 1u) * n_ends + he) * tplw + (bo & ~3u), sh = (bo & 3u) * 8u;
+                const uint32_t wa = TP0 + ((k & 1u) * NE + he) * tplw + (bo & ~3u), sh = (bo & 3u) * 8u;
                 const uint32_t g0 = lds32(wa), g1 = lds32(wa + 4u), g2 = lds32(wa + 8u), g3 = lds32(wa + 12u), g4 = lds32(wa + 16u);
                 uint32_t x0 = __funnelshift_r(g0, g1, sh), x1 = __funnelshift_r(g1, g2, sh), x2 = __funnelshift_r(g2, g3, sh),
                          x3 = __funnelshift_r(g3, g4, sh);
@@ -747,12 +750,12 @@ k_reads(const __grid_constant__ GenParams p) {
                 uint4 c = make_uint4(codes4_acc(x0, reverse, b0), codes4_acc(x1, reverse, b1), codes4_acc(x2, reverse, b2),
                                      codes4_acc(x3, reverse, b3));
                 if (b0 | b1 | b2 | b3) { c.x = codes4_fix(c.x, b0); c.y = codes4_fix(c.y, b1); c.z = codes4_fix(c.z, b2); c.w = codes4_fix(c.w, b3); }
-                sts128(CDe + tb, c);
+                sts128(CD0 + he * codw + tb, c);
             }
             // ends with indels or a barcode take the whole warp, one end after the other
             if (f_any & (kPlanIndels | kPlanBarcode)) {
 #pragma unroll 1
-                for (uint32_t e = 0; e < n_ends; e++) {
+                for (uint32_t e = 0; e < NE; e++) {
                     const uint4 px = lds128(PLk + e * 32u);
                     const uint32_t fe = (px.w >> 16) & 0xffu;
                     if (!(fe & (kPlanIndels | kPlanBarcode))) continue;
@@ -772,15 +775,15 @@ k_reads(const __grid_constant__ GenParams p) {
                 if (pfx_len <= 32u && sv.y == 0u) {
                     if (hl < pfx_len) sts8(rs + hl, lds8(SC0 + hl));
                     if (hl + 16u < pfx_len) sts8(rs + hl + 16u, lds8(SC0 + hl + 16u));
-                    const uint32_t nt = n_ends == 2 ? 5u : 3u;
+                    constexpr uint32_t nt = NE == 2 ? 5u : 3u;
                     const uint32_t nd = idlen - pfx_len - nt;
                     const uint2 mm = lds64(sbase + 8u * min(hl, 9u));
                     const uint32_t q = hl == 0 ? sv.x : (uint32_t)__umul64hi((uint64_t)sv.x, ((uint64_t)mm.y << 32) | mm.x);   // start / 10^hl
                     const uint32_t dig = q - 10u * (__umulhi(q, 0xCCCCCCCDu) >> 3);
                     const uint32_t fr = (flags & kPlanReverse) ? 'R' : 'F';
-                    const uint32_t tw = n_ends == 2 ? ('-' | fr << 8 | '/' << 16 | ('1' + he) << 24) : ('-' | fr << 8 | '\n' << 16);
+                    const uint32_t tw = NE == 2 ? ('-' | fr << 8 | '/' << 16 | ('1' + he) << 24) : ('-' | fr << 8 | '\n' << 16);
                     const uint32_t t = hl - 10u;                                       // lanes 10..: byte t of the tail
-                    const uint32_t tc = t < 4u ? (tw >> (8u * t)) & 0xffu : '\n';
+                    const uint32_t tc = t < 4u ? (tw >> (8u * (t & 3u))) & 0xffu : '\n';
                     const bool is_dig = hl < 10u;
                     const uint32_t ch = is_dig ? '0' + dig : tc;
                     const uint32_t at = rs + pfx_len + (is_dig ? nd - 1u - hl : nd + t);
@@ -794,8 +797,8 @@ k_reads(const __grid_constant__ GenParams p) {
                 }
             }
         }
-        const uint32_t sq0 = __shfl_sync(0xffffffffu, sq, 0), sq1 = __shfl_sync(0xffffffffu, sq, 16);
-        const uint32_t len0 = __shfl_sync(0xffffffffu, ln_e, 0), len1 = n_ends == 2 ? __shfl_sync(0xffffffffu, ln_e, 16) : 0u;
+        const uint32_t sq0 = __shfl_sync(0xffffffffu, sq, 0), sq1 = NE == 2 ? __shfl_sync(0xffffffffu, sq, 16) : 0u;
+        const uint32_t len0 = __shfl_sync(0xffffffffu, ln_e, 0), len1 = NE == 2 ? __shfl_sync(0xffffffffu, ln_e, 16) : 0u;
         __syncwarp();
 
         // ---- phase B
@@ -804,7 +807,7 @@ k_reads(const __grid_constant__ GenParams p) {
             const uint32_t mA0 = sbase + meta0, mA1 = sbase + meta1, eA0 = sbase + ent0, eA1 = sbase + ent1;
 #pragma unroll 1
             for (uint32_t q = lane; q < nbt; q += 32) {
-                const bool second = q >= nb0;
+                const bool second = NE == 2 && q >= nb0;
                 const uint32_t e = second ? 1u : 0u;
                 const uint32_t blk = q - (second ? nb0 : 0u);
                 const uint32_t pos = 2u * blk;
@@ -844,32 +847,32 @@ k_reads(const __grid_constant__ GenParams p) {
                 }
             }
         }
-        // ---- flush: the 16-byte chunks a record completes leave as one bulk copy
-        fence_async_smem();
         __syncwarp();
-        if (mine) {
-            // the run's first chunk holds bytes of the previous run: our bytes of it go out one per lane (first pair(s) only)
-            const uint32_t sh = lds32(ST0 + 8u * he), hole = sh >> 8;
-            if (hole) {
-                const uint32_t total = (sh & 0xffu) + lds32(PLk + he * 32u + 16u);
-                if (total >= 16u && hl >= hole)
-                    (he ? p.out[1] : p.out[0])[lds32(ST0 + 8u * he + 4u) + hl] = (uint8_t)lds8(OB0 + (he * 2u + (k & 1u)) * obw + hl);
+        // ---- flush: the 16-byte chunks the records complete, one 128-bit load and store per lane and chunk
+        {
+            const uint32_t sh0 = lds32(ST0), g0 = lds32(ST0 + 4u);
+            const uint32_t tot0 = (sh0 & 0xffu) + lds32(PLk + 16u), n0 = tot0 >> 4;        // chunks of end 0
+            uint32_t sh1 = 0, g1 = 0, tot1 = 0, n1 = 0;
+            if (NE == 2) { sh1 = lds32(ST0 + 8u); g1 = lds32(ST0 + 12u); tot1 = (sh1 & 0xffu) + lds32(PLk + 48u); n1 = tot1 >> 4; }
+            for (uint32_t c = lane; c < n0 + n1; c += 32u) {
+                const bool second = c >= n0;
+                const uint32_t i = second ? c - n0 : c, buf = OB0 + (second ? obw : 0u) + 16u * i;
+                uint8_t* dst = (second ? p.out[1] + g1 : p.out[0] + g0) + 16u * i;
+                const uint32_t hole = (second ? sh1 : sh0) >> 8;
+                if (i == 0 && hole) {                             // the run's first chunk: only our bytes of it
+                    for (uint32_t b = hole; b < 16u; b++) dst[b] = (uint8_t)lds8(buf + b);
+                } else {
+                    *reinterpret_cast<uint4*>(dst) = lds128(buf);
+                }
             }
-        }
-        __syncwarp();
-        if (lane < n_ends) {                                  // lane e serves end e
-            const uint32_t sh = lds32(ST0 + 8u * lane), hole = sh >> 8, goff = lds32(ST0 + 8u * lane + 4u);
-            const uint32_t total = (sh & 0xffu) + lds32(PLk + lane * 32u + 16u);       // bytes of the buffer in use
-            const uint32_t nfl = total & ~15u;                                       // ... of which whole chunks
-            const uint32_t buf = OB0 + (lane * 2u + (k & 1u)) * obw;
-            const uint32_t skip = hole ? 16u : 0u;
-            if (nfl > skip) bulk_s2g((lane ? p.out[1] : p.out[0]) + goff + skip, buf + skip, nfl - skip);
-            bulk_commit();
-            bulk_wait_read<1>();                              // the copy out of the other buffer (previous pair) has been read
-            // carry the unfinished chunk into the other buffer; the next record continues right behind it
-            sts128(OB0 + (lane * 2u + ((k & 1u) ^ 1u)) * obw, lds128(buf + nfl));
-            sts32(ST0 + 8u * lane, (total & 15u) | (nfl ? 0u : hole << 8));
-            sts32(ST0 + 8u * lane + 4u, goff + nfl);
+            __syncwarp();
+            // the unfinished chunk moves to the front of the buffer; the next record continues right behind it
+            if (lane < NE) {
+                const uint32_t tot = lane ? tot1 : tot0, sh = lane ? sh1 : sh0, nfl = tot & ~15u;
+                if (nfl) sts128(OB0 + lane * obw, lds128(OB0 + lane * obw + nfl));
+                sts32(ST0 + 8u * lane, (tot & 15u) | (nfl ? 0u : sh & 0xff00u));
+                sts32(ST0 + 8u * lane + 4u, (lane ? g1 : g0) + nfl);
+            }
         }
         __syncwarp();
         // chunk c's buffer is free once its last pair is done: chunk c + 2 takes it
@@ -878,10 +881,8 @@ k_reads(const __grid_constant__ GenParams p) {
     // ---- the run's last, unfinished chunk: byte by byte
     if (mine) {
         const uint32_t sh = lds32(ST0 + 8u * he), apos = sh & 0xffu, hole = sh >> 8;
-        if (hl >= hole && hl < apos)
-            (he ? p.out[1] : p.out[0])[lds32(ST0 + 8u * he + 4u) + hl] = (uint8_t)lds8(OB0 + (he * 2u + (n_run & 1u)) * obw + hl);
+        if (hl >= hole && hl < apos) (he ? p.out[1] : p.out[0])[lds32(ST0 + 8u * he + 4u) + hl] = (uint8_t)lds8(OB0 + he * obw + hl);
     }
-    if (lane < n_ends) bulk_wait_read<0>();
 #undef MB0
 #undef SC0
 #undef ST0
@@ -921,6 +922,19 @@ bool reads_fits(const GenParams& p) {
     return reads_threads(p, u) > 0;
 }
 
+template <bool SMEM, uint32_t NE>
+static cudaError_t launch_reads_as(const GenParams& p, int n_sm, int threads, size_t smem_bytes, cudaStream_t s) {
+    cudaError_t err = cudaFuncSetAttribute(k_reads<SMEM, NE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (err != cudaSuccess) return err;
+    // persistent: one CTA per SM, every warp takes one contiguous run of the batch's pairs
+    const int wpc = threads / 32;
+    uint32_t blocks = (p.batch_pairs + wpc - 1) / wpc;
+    const uint32_t cap = (uint32_t)(n_sm > 0 ? n_sm : 148);
+    if (blocks > cap) blocks = cap;
+    k_reads<SMEM, NE><<<blocks, threads, smem_bytes, s>>>(p);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_reads(const GenParams& p, int n_sm, cudaStream_t s) {
     if (p.batch_pairs == 0) return cudaSuccess;
     bool use_smem = false;
@@ -928,25 +942,8 @@ cudaError_t launch_reads(const GenParams& p, int n_sm, cudaStream_t s) {
     if (threads <= 0) return cudaErrorInvalidConfiguration;
     const size_t rec_bytes = (size_t)wpc * reads_warp_bytes(p.n_ends, p.rec_buf, p.tpl_buf, p.cod_buf);
     const size_t smem_bytes = rec_bytes + (use_smem ? reads_table_bytes(p) : kReadsCtaBytes);
-    cudaError_t err;
-    int per_sm = 0;
-    if (use_smem) {
-        err = cudaFuncSetAttribute(k_reads<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        if (err != cudaSuccess) return err;
-        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_reads<true>, threads, smem_bytes);
-    } else {
-        err = cudaFuncSetAttribute(k_reads<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        if (err != cudaSuccess) return err;
-        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_reads<false>, threads, smem_bytes);
-    }
-    if (err != cudaSuccess) return err;
-    if (per_sm < 1) per_sm = 1;
-    uint32_t blocks = (p.batch_pairs + wpc - 1) / wpc;
-    const uint32_t cap = (uint32_t)(n_sm > 0 ? n_sm : 148) * (uint32_t)per_sm;
-    if (blocks > cap) blocks = cap;
-    if (use_smem) k_reads<true><<<blocks, threads, smem_bytes, s>>>(p);
-    else k_reads<false><<<blocks, threads, smem_bytes, s>>>(p);
-    return cudaGetLastError();
+    if (p.n_ends == 2) return use_smem ? launch_reads_as<true, 2>(p, n_sm, threads, smem_bytes, s) : launch_reads_as<false, 2>(p, n_sm, threads, smem_bytes, s);
+    return use_smem ? launch_reads_as<true, 1>(p, n_sm, threads, smem_bytes, s) : launch_reads_as<false, 1>(p, n_sm, threads, smem_bytes, s);
 }
 
 // ------------------------------------------------------------------ scan ---
