@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libjlp_b200.so")
+LIB_PATH = os.environ.get("JLP_B200_LIB") or os.path.join(HERE, "libjlp_b200.so")     # the override serves build-variant experiments
 
 u8p, u32p, u64p, f64p = (C.POINTER(t) for t in (C.c_uint8, C.c_uint32, C.c_uint64, C.c_double))
 ABORT_CB = C.CFUNCTYPE(C.c_int, C.c_void_p)

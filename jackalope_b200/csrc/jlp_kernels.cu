@@ -244,7 +244,7 @@ k_place(const __grid_constant__ GenParams p) {
     bool reverse = lo64(draw_block(p.seed, j, 1, PL_PAIR, 0)) < p.c_rev;
     if (e) reverse = !reverse;
 
-    uint32_t frag_pos = 0, length_now = 0, n_ev = 0;
+    uint32_t frag_pos = 0, length_now = 0, n_ev = 0, ev0 = 0xffffffffu, ev1 = 0xffffffffu;
     const uint32_t frag_cap = frag_len > 0xffffffffull ? 0xffffffffu : (uint32_t)frag_len;
     const uint32_t hA = p.end[e].hA;
     while (length_now < L && frag_pos < frag_cap) {
@@ -261,10 +261,12 @@ k_place(const __grid_constant__ GenParams p) {
         uint32_t f = frag_pos & 7u;
         for (; f < 8 && length_now < L && frag_pos < frag_cap; f++, frag_pos++) {
             int cls = indel_class(p, e, j, frag_pos, field16(w, f));
-            if (cls == 0) length_now++;
-            else if (cls == 1) n_ev++;
-            else if (length_now == L - 1) length_now++;   // src/hts_illumina.cpp:138-139: treated as a plain base
-            else { length_now += 2; n_ev++; }
+            if (cls == 2 && length_now == L - 1) cls = 0;  // src/hts_illumina.cpp:138-139: treated as a plain base
+            if (cls == 0) { length_now++; continue; }
+            length_now += cls == 2 ? 2u : 0u;
+            const uint32_t ev = frag_pos | ((uint32_t)cls << 16);
+            if (n_ev == 0) ev0 = ev; else if (n_ev == 1) ev1 = ev;
+            n_ev++;
         }
     }
     uint32_t S = frag_pos, len = length_now;
@@ -281,13 +283,13 @@ k_place(const __grid_constant__ GenParams p) {
     uint32_t nd = 1;
     for (uint64_t v = start; v >= 10; v /= 10) nd++;
     const uint32_t idlen = G.prefix_len + nd + 3u + (p.n_ends == 2 ? 2u : 0u);
-    uint32_t flags = (reverse ? kPlanReverse : 0u) | (n_ev ? kPlanIndels : 0u) | (b ? kPlanBarcode : 0u);
+    uint32_t flags = (reverse ? kPlanReverse : 0u) | (n_ev ? kPlanIndels : 0u) | (b ? kPlanBarcode : 0u) | (n_ev > 2 ? kPlanManyEv : 0u);
     if (idlen > 255u) flags |= kPlanLongId;
     const uint32_t rec_len = idlen + 2u * len + 4u;   // ID line | read '\n' '+' '\n' qual '\n'
     const uint64_t sega = reinterpret_cast<uint64_t>(G.seq + start);
     uint4* dst = reinterpret_cast<uint4*>(p.plan + r);
     dst[0] = make_uint4((uint32_t)sega, (uint32_t)(sega >> 32), S, len | (flags << 16) | ((idlen & 0xffu) << 24));
-    dst[1] = make_uint4(rec_len, g, (uint32_t)start, (uint32_t)(start >> 32));
+    dst[1] = make_uint4(rec_len, g, ev0, ev1);
     p.rec_len[r] = rec_len;
 }
 
@@ -564,6 +566,41 @@ __device__ __noinline__ void slow_idline(const GenParams& p, uint32_t dst, const
     sts8(dst, '\n');
 }
 
+// The one or two insertions / deletions of a read applied to its line of template codes (code[t] = template position t,
+// S of them), last event first: a deletion at t drops code[t] (the tail moves one to the left), an insertion at t puts
+// bases[(uint64)(u * 4)] behind code[t] (the tail moves one to the right).  The whole warp works on one end.
+__device__ __noinline__ void apply_events(const GenParams& p, uint32_t e, uint64_t j, uint32_t C, uint32_t S, uint32_t ev0, uint32_t ev1) {
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t top = S;                                         // codes in the line
+#pragma unroll 1
+    for (int k = 1; k >= 0; k--) {
+        const uint32_t ev = k ? ev1 : ev0;
+        if (ev == 0xffffffffu) continue;
+        const uint32_t t = ev & 0xffffu;
+        if ((ev >> 16) == 1u) {                               // deletion: code[x] = code[x + 1] for x >= t, front to back
+            for (uint32_t x0 = t; x0 + 1u < top; x0 += 32u) {
+                const uint32_t x = x0 + lane;
+                const uint32_t v = x + 1u < top ? lds8(C + x + 1u) : 0u;
+                __syncwarp();
+                if (x + 1u < top) sts8(C + x, v);
+                __syncwarp();
+            }
+            top--;
+        } else {                                              // insertion: code[x + 1] = code[x] for x > t, back to front
+            for (uint32_t hi = top; hi > t + 1u; hi = hi > t + 33u ? hi - 32u : t + 1u) {
+                const uint32_t lo = hi > t + 33u ? hi - 32u : t + 1u, x = lo + lane;
+                const uint32_t v = x < hi ? lds8(C + x) : 0u;
+                __syncwarp();
+                if (x < hi) sts8(C + x + 1u, v);
+                __syncwarp();
+            }
+            if (lane == 0) sts8(C + t + 1u, ins_base_index(slow64(p.seed, j, e, PU_INS, t)));
+            __syncwarp();
+            top++;
+        }
+    }
+}
+
 // ceil(2^64 / 10^k), k = 1..9: floor(n / 10^k) = umul64hi(n, c_m10[k]) for every n < 2^32
 __constant__ uint64_t c_m10[10] = {0ull, 1844674407370955162ull, 184467440737095517ull, 18446744073709552ull, 1844674407370956ull,
                                    184467440737096ull, 18446744073710ull, 1844674407371ull, 184467440738ull, 18446744074ull};
@@ -628,8 +665,8 @@ k_reads(const __grid_constant__ GenParams p) {
     const uint32_t W0 = sbase + tab_bytes + warp * reads_warp_bytes(NE, obw, tplw, codw);
     constexpr uint32_t plan_pair = NE * 32u;                  // bytes of plan per pair
 #define MB0 (W0)
-#define SC0 (W0 + 16u)
-#define ST0 (W0 + 56u)                                        /* per end 8 bytes: apos | hole << 8, goff */
+#define SC0 (W0 + 16u)                                        /* 32 bytes of the group's ID-line prefix; +32 group, +36 prefix length, +40 its chromosome's address */
+#define ST0 (W0 + 64u)                                        /* per end 8 bytes: apos | hole << 8, goff */
 #define PL0 (W0 + 80u)
 #define TP0 (PL0 + 2u * kPlanChunk * plan_pair)
 #define CD0 (TP0 + kTplSlots * NE * tplw)
@@ -726,11 +763,14 @@ k_reads(const __grid_constant__ GenParams p) {
                 const GroupDev* Gp = p.groups + grp;
                 const uint32_t n = Gp->prefix_len;
                 if (lane < n) sts8(SC0 + lane, p.strpool[Gp->prefix_off + lane]);
-                if (lane == 0) { sts32(SC0 + 32u, grp); sts32(SC0 + 36u, n); }
+                if (lane == 0) {
+                    const uint64_t gs = reinterpret_cast<uint64_t>(Gp->seq);
+                    sts32(SC0 + 32u, grp); sts32(SC0 + 36u, n); sts64(SC0 + 40u, (uint32_t)gs, (uint32_t)(gs >> 32));
+                }
                 __syncwarp();
             }
             // ---- phase A: template base codes into the end's code line, 16 positions per lane from the staged window
-            if (mine && !(flags & (kPlanIndels | kPlanBarcode)) && 16u * hl < ln) {
+            if (mine && !(flags & (kPlanManyEv | kPlanBarcode)) && 16u * hl < max(ln, S)) {
                 const bool reverse = flags & kPlanReverse;
                 const uint32_t tb = 16u * hl;
                 const uint32_t d0 = (pa.x & 15u) + 16u;                               // seg's place in the window: 16 .. 31
@@ -754,16 +794,24 @@ k_reads(const __grid_constant__ GenParams p) {
             }
             // ends with indels or a barcode take the whole warp, one end after the other
             if (f_any & (kPlanIndels | kPlanBarcode)) {
+                __syncwarp();
 #pragma unroll 1
                 for (uint32_t e = 0; e < NE; e++) {
                     const uint4 px = lds128(PLk + e * 32u);
                     const uint32_t fe = (px.w >> 16) & 0xffu;
                     if (!(fe & (kPlanIndels | kPlanBarcode))) continue;
-                    const uint8_t* seg = reinterpret_cast<const uint8_t*>(((uint64_t)px.y << 32) | px.x);
-                    const GroupDev* Gp = p.groups + grp;
-                    const uint8_t* bc = p.strpool + Gp->bc_off;
-                    if (fe & kPlanIndels) gather_indels(p, e, j, CD0 + e * codw, seg, bc, px.z, Gp->bc_len, px.w & 0xffffu, fe & kPlanReverse);
-                    else gather_barcode(CD0 + e * codw, seg, bc, px.z, Gp->bc_len, px.w & 0xffffu, fe & kPlanReverse);
+                    if (fe & (kPlanManyEv | kPlanBarcode)) {
+                        const uint8_t* seg = reinterpret_cast<const uint8_t*>(((uint64_t)px.y << 32) | px.x);
+                        const GroupDev* Gp = p.groups + grp;
+                        const uint8_t* bc = p.strpool + Gp->bc_off;
+                        if (fe & kPlanIndels) gather_indels(p, e, j, CD0 + e * codw, seg, bc, px.z, Gp->bc_len, px.w & 0xffffu, fe & kPlanReverse);
+                        else gather_barcode(CD0 + e * codw, seg, bc, px.z, Gp->bc_len, px.w & 0xffffu, fe & kPlanReverse);
+                    } else {
+                        // one or two insertions / deletions: phase A has laid down the codes of all S template positions;
+                        // the edits shift the line's tail, from the back as fill_read_qual applies them (src/hts_illumina.h:213-225)
+                        const uint2 evs = lds64(PLk + e * 32u + 24u);
+                        apply_events(p, e, j, CD0 + e * codw, px.z, evs.x, evs.y);
+                    }
                 }
             }
             // ---- ID line "@<genome>-<chrom>-<start>-<F|R>[/<1|2>]\n" (fill_fq_lines, src/hts_illumina.cpp:296-312) and the
@@ -771,7 +819,9 @@ k_reads(const __grid_constant__ GenParams p) {
             //      tail "-F/1\n" ("-F\n" single-end), lane 15 the four separator bytes of the record
             if (mine) {
                 const uint32_t pfx_len = lds32(SC0 + 36u);
-                const uint2 sv = lds64(PLk + he * 32u + 24u);                          // start coordinate
+                uint2 sv = lds64(SC0 + 40u);                                           // start coordinate = template - chromosome
+                sv.y = pa.y - sv.y - (pa.x < sv.x ? 1u : 0u);
+                sv.x = pa.x - sv.x;
                 if (pfx_len <= 32u && sv.y == 0u) {
                     if (hl < pfx_len) sts8(rs + hl, lds8(SC0 + hl));
                     if (hl + 16u < pfx_len) sts8(rs + hl + 16u, lds8(SC0 + hl + 16u));

@@ -24,14 +24,15 @@ struct EndPlan {
     const uint8_t* seg;    // first template base in HBM (chromosome + start)
     uint32_t S;            // template positions consumed, barcode included (adjust_chrom_spaces)
     uint16_t len;          // final read length
-    uint8_t flags;         // bit 0 reverse strand, 1 insertions/deletions, 2 barcode, 3 ID line longer than 255 bytes
+    uint8_t flags;         // bit 0 reverse strand, 1 insertions/deletions, 2 barcode, 3 ID line longer than 255 bytes, 4 > 2 indels
     uint8_t idlen;         // bytes of the ID line, '\n' included (when <= 255)
     uint32_t rec_len;      // FASTQ bytes of the record
     uint32_t group;
-    uint64_t start;        // the coordinate the ID line prints (leftmost template base on the chromosome)
+    uint32_t ev[2];        // the first two insertions / deletions of the read: template position | type << 16 (1 deletion,
+                           // 2 insertion), ascending; 0xffffffff = none
 };
 static_assert(sizeof(EndPlan) == 32, "EndPlan layout");
-constexpr uint32_t kPlanReverse = 1, kPlanIndels = 2, kPlanBarcode = 4, kPlanLongId = 8;
+constexpr uint32_t kPlanReverse = 1, kPlanIndels = 2, kPlanBarcode = 4, kPlanLongId = 8, kPlanManyEv = 16;   // ManyEv: more than two
 constexpr uint32_t kPlanChunk = 8;      // pairs whose plans one bulk copy stages into shared memory
 
 struct EndDev {
