@@ -4,7 +4,7 @@
 // turns it into u = (x+1)/2^64 with x87 long-double arithmetic
 // (/root/reference/src/pcg.h:21,99-101).  Here every logical draw
 // X(pair instance j, end, purpose, position) is a pure function of a
-// Philox4x32-10 counter, so a read does not depend on which GPU, CTA or thread
+// Philox4x32 counter (10 rounds; 7 in the QUAL plane), so a read does not depend on which GPU, CTA or thread
 // produced it:
 //
 //   counter = (j_lo, j_hi, block, plane | end << 8),  key = (seed_lo, seed_hi)
@@ -54,10 +54,16 @@ JLP_HD void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
 #endif
 }
 
-// Philox4x32-10, Salmon et al. SC'11, standard multipliers and Weyl constants.
-JLP_HD U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+// Philox4x32-R, Salmon et al. SC'11, standard multipliers and Weyl constants.  R = 10 everywhere except the QUAL plane
+// (two thirds of all the blocks a run draws), which uses R = 7: the fewest rounds at which Philox4x32 passes
+// BigCrush in that paper (their "Crush-resistant" column; 10 is its safety margin).
+constexpr int kQualRounds = 7;
+template <int R>
+JLP_HD U4 philox4x32_r(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#if defined(__CUDA_ARCH__)
 #pragma unroll
-    for (int r = 0; r < 10; r++) {
+#endif
+    for (int r = 0; r < R; r++) {
         uint32_t h0, l0, h1, l1;
         mulhilo(0xD2511F53u, c0, h0, l0);
         mulhilo(0xCD9E8D57u, c2, h1, l1);
@@ -71,13 +77,19 @@ JLP_HD U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint
     U4 o = {c0, c1, c2, c3};
     return o;
 }
+JLP_HD U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+    return philox4x32_r<10>(c0, c1, c2, c3, k0, k1);
+}
 
-// The same block with the ten round keys precomputed (rk[2r] = k0 + r * 0x9E3779B9,
+// The same block with the round keys precomputed (rk[2r] = k0 + r * 0x9E3779B9,
 // rk[2r+1] = k1 + r * 0xBB67AE85): in a kernel they sit in the constant bank and feed the
 // XORs directly.
-JLP_HD U4 philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const uint32_t* rk) {
+template <int R>
+JLP_HD U4 philox4x32_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const uint32_t* rk) {
+#if defined(__CUDA_ARCH__)
 #pragma unroll
-    for (int r = 0; r < 10; r++) {
+#endif
+    for (int r = 0; r < R; r++) {
         uint32_t h0, l0, h1, l1;
         mulhilo(0xD2511F53u, c0, h0, l0);
         mulhilo(0xCD9E8D57u, c2, h1, l1);
@@ -95,6 +107,8 @@ inline void philox_round_keys(uint64_t seed, uint32_t rk[20]) {
 }
 
 JLP_HD U4 draw_block(uint64_t seed, uint64_t j, uint32_t block, uint32_t plane, uint32_t end) {
+    if (plane == PL_QUAL)
+        return philox4x32_r<kQualRounds>((uint32_t)j, (uint32_t)(j >> 32), block, plane | (end << 8), (uint32_t)seed, (uint32_t)(seed >> 32));
     return philox4x32_10((uint32_t)j, (uint32_t)(j >> 32), block, plane | (end << 8),
                          (uint32_t)seed, (uint32_t)(seed >> 32));
 }

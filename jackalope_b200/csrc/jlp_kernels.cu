@@ -332,7 +332,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ U4 qual_block(const GenParams& p, uint64_t j, uint32_t blk, uint32_t e) {
-    return philox4x32_10_rk((uint32_t)j, (uint32_t)(j >> 32), blk, PL_QUAL | (e << 8), p.rk);
+    return philox4x32_rk<kQualRounds>((uint32_t)j, (uint32_t)(j >> 32), blk, PL_QUAL | (e << 8), p.rk);
 }
 
 // One base evaluated exactly (full 64-bit draws wherever the 16 high bits do not decide);
@@ -345,16 +345,18 @@ __device__ __noinline__ uint32_t base_rare(const GenParams& p, uint32_t meta_a, 
     const uint32_t Hcoin = cm >> 16, Hmis = cm & 0xffffu;
     if (code > 3) {
         // 'N' with a quality below 10 (src/hts_illumina.h:237-242)
-        uint32_t qc = __umulhi(die, 10u) + 33u;
-        if (die * 10u + 2560u < 5120u) qc = nqual_x87(full_draw(die >> 8, p.seed, j, e, PU_DIE, pos));   // two-sided, as in base_fast
+        const uint32_t dn = die & 0xffffff00u;
+        uint32_t qc = __umulhi(dn, 10u) + 33u;
+        if (dn * 10u + 2560u < 2560u) qc = nqual_x87(full_draw(die >> 8, p.seed, j, e, PU_DIE, pos));
         return 0x4Eu | ((qc & 0xffu) << 8);
     }
     uint32_t m;
     if (SMEM) m = lds32_ro(meta_a + (code * p.L + pos) * 4u);
     else m = __ldg(E.meta + code * p.L + pos);
     const uint32_t n = m & 0xffu, off = m >> 8;
-    uint32_t i = __umulhi(die, n);
-    if (die * n + (n << 8) < (n << 9)) {     // the draw's low 40 bits decide the slot index (see base_fast)
+    const uint32_t dc = die & 0xffffff00u;      // the high 24 bits of X_die (the low byte of the word belongs to X_sub)
+    uint32_t i = __umulhi(dc, n);
+    if (dc * n + (n << 8) < (n << 8)) {         // the draw's low 40 bits can carry into the slot index
         uint64_t ii = mul_floor_x87(full_draw(die >> 8, p.seed, j, e, PU_DIE, pos), n);
         i = ii >= n ? n - 1u : (uint32_t)ii;
     }
@@ -393,21 +395,21 @@ __device__ __forceinline__ void base_fast(const GenParams& p, uint32_t meta_a, u
     uint32_t m;
     if (SMEM) m = lds32_ro(meta_a + (ct * p.L + pos) * 4u);
     else m = __ldg(p.end[e].meta + ct * p.L + pos);
-    const uint32_t n = m & 0xffu;
-    const uint32_t lo = die * n;                              // die * n / 2^32 is the alias slot (die: 24 bits of X_die, then 8 of X_sub) ...
-    const uint32_t slot = (m >> 8) + __umulhi(die, n);
+    const uint32_t n = m & 0xffu, nsh = __byte_perm(m, 0u, 0x4404u);   // n and n << 8
+    // die * n / 2^32 is the alias slot.  The word's low byte belongs to X_sub, not to X_die: it is masked off, so the
+    // product's fraction lacks at most n * 2^8 and the slot is decided unless adding that much carries.
+    const uint32_t dc = die & 0xffffff00u;
+    const uint32_t slot = (m >> 8) + __umulhi(dc, n);
     uint2 ent;
     if (SMEM) ent = lds64_ro(ent_a + slot * 8u);
     else ent = __ldg(reinterpret_cast<const uint2*>(p.end[e].entry64) + slot);
     // coin: high half of cm against the threshold in the high half of the entry, compared in place
     const uint32_t thr_hi = ent.x & 0xffff0000u;
     self = cm < thr_hi;
-    const uint32_t mt = self ? (ent.y & 0xffffu) : (ent.y >> 16);    // high 16 bits of the quality's mismatch threshold
-    // ... unless the draw's low 40 bits decide: the word's low byte belongs to X_sub, not to X_die, so the product's
-    // fraction is off by up to n * 2^8 either way -- about to carry (true low bits larger) or just carried (the
-    // substitution byte alone pushed it over); coin and mismatch are undecided when their 16 high bits equal the
-    // threshold's; a mismatch itself is handled by the exact path too
-    rare = (lo + (n << 8) < (n << 9)) || (cm - thr_hi < 0x10000u) || ((cm & 0xffffu) <= mt);
+    const uint32_t mt = __byte_perm(ent.y, 0u, self ? 0x4410u : 0x4432u);      // high 16 bits of the quality's mismatch threshold
+    // coin and mismatch are undecided when their 16 high bits equal the threshold's; a mismatch itself is handled by
+    // the exact path too
+    rare = (dc * n + nsh < nsh) || (cm - thr_hi < 0x10000u) || ((cm & 0xffffu) <= mt);
     entx = ent.x;
 }
 

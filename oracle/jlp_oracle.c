@@ -36,11 +36,11 @@
 
 /* ------------------------------------------------------------------ Philox */
 
-/* Philox4x32-10 (Salmon et al., SC'11), standard constants. */
-void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+/* Philox4x32-R (Salmon et al., SC'11), standard constants. */
+static void philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4], int rounds) {
     uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
     uint32_t k0 = key[0], k1 = key[1];
-    for (int r = 0; r < 10; r++) {
+    for (int r = 0; r < rounds; r++) {
         uint64_t p0 = (uint64_t)0xD2511F53u * c0;
         uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
         uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
@@ -52,6 +52,8 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { philox4x32(ctr, key, out, 10); }
+void orc_philox4x32_r(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4], int rounds) { philox4x32(ctr, key, out, rounds); }
 
 /* Draw addressing.  counter = (j_lo, j_hi, block, plane | end<<8) */
 enum { PL_PAIR = 0, PL_INDEL = 1, PL_QUAL = 2, PL_SLOW = 3 };
@@ -60,7 +62,7 @@ enum { PU_INDEL = 0, PU_DIE = 1, PU_COIN = 2, PU_MIS = 3, PU_SUB = 4, PU_INS = 5
 static void call(uint64_t seed, uint64_t j, uint32_t block, uint32_t plane, uint32_t end, uint32_t w[4]) {
     uint32_t ctr[4] = {(uint32_t)j, (uint32_t)(j >> 32), block, plane | (end << 8)};
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
-    orc_philox4x32_10(ctr, key, w);
+    philox4x32(ctr, key, w, plane == PL_QUAL ? 7 : 10);      /* the QUAL plane runs 7 rounds (jlp_draws.h, kQualRounds) */
 }
 
 /* pair-level draws: which = 0 fraglen, 1 start, 2 strand, 3 dup */
