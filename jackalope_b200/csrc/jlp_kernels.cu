@@ -509,7 +509,9 @@ __device__ __noinline__ void gather_barcode(uint32_t w, const uint8_t* seg, cons
 }
 
 #ifndef JLP_READS_THREADS
-#define JLP_READS_THREADS 896   // 28 warps, one CTA per SM sharing one copy of the tables
+// 20 warps, one CTA per SM sharing one copy of the tables: 96 registers per thread, nothing spilled.  Measured
+// (DESIGN.md section 5): 896 threads (72 registers, spills) 1.56 ms, 768 1.54, 640 1.46, 512 1.50.
+#define JLP_READS_THREADS 640
 #define JLP_READS_CTAS 1
 #endif
 constexpr int kReadsThreads = JLP_READS_THREADS;
@@ -618,6 +620,62 @@ __device__ __forceinline__ uint32_t codes4_acc(uint32_t x, bool reverse, uint32_
     return reverse ? code ^ 0x02020202u : code;
 }
 
+// Phase B of k_reads for one pair: both ends in one index space, two bases per lane and Philox block -- quality by the
+// alias method, mismatch test, substitution, written straight into the records (sq0 / sq1: shared addresses of the two
+// sequence lines; cd: the code lines, codw bytes apart).  Undecided draws branch to base_rare().
+// inlined: as a function of its own (registers allocated apart from the bookkeeping around it) it was slower, 1.63 ms against 1.46
+#ifdef JLP_PHASEB_NOINLINE
+#define JLP_PHASEB_ATTR __noinline__
+#else
+#define JLP_PHASEB_ATTR __forceinline__
+#endif
+template <bool SMEM, uint32_t NE>
+__device__ JLP_PHASEB_ATTR void phase_b(const GenParams& p, uint64_t j, uint32_t lane, uint32_t sq0, uint32_t sq1, uint32_t len0, uint32_t len1,
+                                     uint32_t cd, uint32_t codw, uint32_t mA0, uint32_t mA1, uint32_t eA0, uint32_t eA1) {
+    const uint32_t nb0 = (len0 + 1u) >> 1, nbt = nb0 + ((len1 + 1u) >> 1);
+#pragma unroll 1
+    for (uint32_t q = lane; q < nbt; q += 32) {
+        const bool second = NE == 2 && q >= nb0;
+        const uint32_t e = second ? 1u : 0u;
+        const uint32_t blk = q - (second ? nb0 : 0u);
+        const uint32_t pos = 2u * blk;
+        const uint32_t ln = second ? len1 : len0;
+        const uint32_t s0 = (second ? sq1 : sq0) + pos;
+        const uint32_t q0 = s0 + ln + 3u;
+        const uint32_t meta_a = second ? mA1 : mA0, ent_a = second ? eA1 : eA0;
+        const bool two = pos + 1u < ln;
+        const U4 w = qual_block(p, j, blk, e);
+        const uint32_t cc = lds16(cd + e * codw + pos);
+        const uint32_t c0 = cc & 0xffu, c1 = two ? cc >> 8 : 0u, pos1 = two ? pos + 1u : pos;
+        const uint32_t ct0 = min(c0, 3u), ct1 = min(c1, 3u);
+        uint32_t x0, x1;
+        bool self0, self1, rare0, rare1;
+        base_fast<SMEM>(p, meta_a, ent_a, e, pos, ct0, w.w0, w.w1, x0, self0, rare0);
+        base_fast<SMEM>(p, meta_a, ent_a, e, pos1, ct1, w.w2, w.w3, x1, self1, rare1);
+        // both quality characters with one byte permute, both letters with another
+        uint32_t qq = __byte_perm(x0, x1, (self0 ? 1u : 0u) | (self1 ? 0x50u : 0x40u));
+        uint32_t asc = __byte_perm(0x47414354u, 0u, ct0 | (ct1 << 4));
+        if (rare0 || rare1 || (c0 | c1) > 3u) {
+            if (rare0 || c0 > 3u) {
+                uint32_t r = base_rare<SMEM>(p, meta_a, ent_a, e, j, pos, c0, w.w0, w.w1);
+                asc = (asc & 0xff00u) | (r & 0xffu);
+                qq = (qq & 0xff00u) | (r >> 8);
+            }
+            if (two && (rare1 || c1 > 3u)) {
+                uint32_t r = base_rare<SMEM>(p, meta_a, ent_a, e, j, pos1, c1, w.w2, w.w3);
+                asc = (asc & 0xffu) | ((r & 0xffu) << 8);
+                qq = (qq & 0xffu) | (r & 0xff00u);
+            }
+        }
+        sts8(s0, asc);
+        sts8(q0, qq);
+        if (two) {
+            sts8(s0 + 1u, asc >> 8);
+            sts8(q0 + 1u, qq >> 8);
+        }
+    }
+}
+
 // One warp per run of consecutive read pairs: the R1 records of a run are one contiguous span of file 1, its R2
 // records one of file 2, so a record is assembled in shared memory AT ITS FILE ALIGNMENT: the 16-byte chunks it
 // completes go to the file with one 128-bit load and one 128-bit store per lane and chunk (no shifting), the
@@ -682,7 +740,7 @@ k_reads(const __grid_constant__ GenParams p) {
     if (n_run == 0) return;
 
     const uint32_t he = lane >> 4, hl = lane & 15u;           // phase A and ID line: one half-warp per end
-    const bool mine = he < NE;
+    const bool mine = NE == 2 || he == 0;
     if (lane < NE) {
         // where the run's first record of end `lane` goes: its offset in the file's batch buffer
         const uint64_t fo = p.block_base[(size_t)lane * p.n_scan_blocks + r0 / kScanBlock] + p.rec_local[r0 * NE + lane];
@@ -854,51 +912,7 @@ k_reads(const __grid_constant__ GenParams p) {
         __syncwarp();
 
         // ---- phase B
-        {
-            const uint32_t nb0 = (len0 + 1u) >> 1, nbt = nb0 + ((len1 + 1u) >> 1);
-            const uint32_t mA0 = sbase + meta0, mA1 = sbase + meta1, eA0 = sbase + ent0, eA1 = sbase + ent1;
-#pragma unroll 1
-            for (uint32_t q = lane; q < nbt; q += 32) {
-                const bool second = NE == 2 && q >= nb0;
-                const uint32_t e = second ? 1u : 0u;
-                const uint32_t blk = q - (second ? nb0 : 0u);
-                const uint32_t pos = 2u * blk;
-                const uint32_t ln = second ? len1 : len0;
-                const uint32_t s0 = (second ? sq1 : sq0) + pos;
-                const uint32_t q0 = s0 + ln + 3u;
-                const uint32_t meta_a = second ? mA1 : mA0, ent_a = second ? eA1 : eA0;
-                const bool two = pos + 1u < ln;
-                const U4 w = qual_block(p, j, blk, e);
-                const uint32_t cc = lds16(CD0 + e * codw + pos);
-                const uint32_t c0 = cc & 0xffu, c1 = two ? cc >> 8 : 0u, pos1 = two ? pos + 1u : pos;
-                const uint32_t ct0 = min(c0, 3u), ct1 = min(c1, 3u);
-                uint32_t x0, x1;
-                bool self0, self1, rare0, rare1;
-                base_fast<SMEM>(p, meta_a, ent_a, e, pos, ct0, w.w0, w.w1, x0, self0, rare0);
-                base_fast<SMEM>(p, meta_a, ent_a, e, pos1, ct1, w.w2, w.w3, x1, self1, rare1);
-                // both quality characters with one byte permute, both letters with another
-                uint32_t qq = __byte_perm(x0, x1, (self0 ? 1u : 0u) | (self1 ? 0x50u : 0x40u));
-                uint32_t asc = __byte_perm(0x47414354u, 0u, ct0 | (ct1 << 4));
-                if (rare0 || rare1 || (c0 | c1) > 3u) {
-                    if (rare0 || c0 > 3u) {
-                        uint32_t r = base_rare<SMEM>(p, meta_a, ent_a, e, j, pos, c0, w.w0, w.w1);
-                        asc = (asc & 0xff00u) | (r & 0xffu);
-                        qq = (qq & 0xff00u) | (r >> 8);
-                    }
-                    if (two && (rare1 || c1 > 3u)) {
-                        uint32_t r = base_rare<SMEM>(p, meta_a, ent_a, e, j, pos1, c1, w.w2, w.w3);
-                        asc = (asc & 0xffu) | ((r & 0xffu) << 8);
-                        qq = (qq & 0xffu) | (r & 0xff00u);
-                    }
-                }
-                sts8(s0, asc);
-                sts8(q0, qq);
-                if (two) {
-                    sts8(s0 + 1u, asc >> 8);
-                    sts8(q0 + 1u, qq >> 8);
-                }
-            }
-        }
+        phase_b<SMEM, NE>(p, j, lane, sq0, sq1, len0, len1, CD0, codw, sbase + meta0, sbase + meta1, sbase + ent0, sbase + ent1);
         __syncwarp();
         // ---- flush: the 16-byte chunks the records complete, one 128-bit load and store per lane and chunk
         {
