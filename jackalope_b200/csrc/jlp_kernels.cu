@@ -387,11 +387,11 @@ __device__ __noinline__ uint32_t base_rare(const GenParams& p, uint32_t meta_a, 
 // alias method (IllQualPos::sample, src/hts_illumina.h:128-132; AliasSampler::sample,
 // src/alias_sampler.h:53-60) and the mismatch test (src/hts_illumina.h:251-252).
 // ct: base code clamped to 0..3 (keeps the table walk in bounds for 'N').  Outputs the table
-// entry's low word, which of its two qualities was drawn, and whether base_rare() must
-// decide instead (ambiguous high bits or a mismatch).
+// entry's low word, which of its two qualities was drawn, whether the base is a mismatch, and
+// whether base_rare() must decide instead (ambiguous high bits).
 template <bool SMEM>
 __device__ __forceinline__ void base_fast(const GenParams& p, uint32_t meta_a, uint32_t ent_a, uint32_t e, uint32_t pos,
-                                          uint32_t ct, uint32_t die, uint32_t cm, uint32_t& entx, bool& self, bool& rare) {
+                                          uint32_t ct, uint32_t die, uint32_t cm, uint32_t& entx, bool& self, bool& rare, bool& mism) {
     uint32_t m;
     if (SMEM) m = lds32_ro(meta_a + (ct * p.L + pos) * 4u);
     else m = __ldg(p.end[e].meta + ct * p.L + pos);
@@ -407,9 +407,10 @@ __device__ __forceinline__ void base_fast(const GenParams& p, uint32_t meta_a, u
     const uint32_t thr_hi = ent.x & 0xffff0000u;
     self = cm < thr_hi;
     const uint32_t mt = __byte_perm(ent.y, 0u, self ? 0x4410u : 0x4432u);      // high 16 bits of the quality's mismatch threshold
-    // coin and mismatch are undecided when their 16 high bits equal the threshold's; a mismatch itself is handled by
-    // the exact path too
-    rare = (dc * n + nsh < nsh) || (cm - thr_hi < 0x10000u) || ((cm & 0xffffu) <= mt);
+    // coin and mismatch are undecided when their 16 high bits equal the threshold's
+    const uint32_t mh = cm & 0xffffu;
+    mism = mh < mt;
+    rare = (dc * n + nsh < nsh) || (cm - thr_hi < 0x10000u) || (mh == mt);
     entx = ent.x;
 }
 
@@ -649,12 +650,20 @@ __device__ JLP_PHASEB_ATTR void phase_b(const GenParams& p, uint64_t j, uint32_t
         const uint32_t c0 = cc & 0xffu, c1 = two ? cc >> 8 : 0u, pos1 = two ? pos + 1u : pos;
         const uint32_t ct0 = min(c0, 3u), ct1 = min(c1, 3u);
         uint32_t x0, x1;
-        bool self0, self1, rare0, rare1;
-        base_fast<SMEM>(p, meta_a, ent_a, e, pos, ct0, w.w0, w.w1, x0, self0, rare0);
-        base_fast<SMEM>(p, meta_a, ent_a, e, pos1, ct1, w.w2, w.w3, x1, self1, rare1);
+        bool self0, self1, rare0, rare1, mis0, mis1;
+        base_fast<SMEM>(p, meta_a, ent_a, e, pos, ct0, w.w0, w.w1, x0, self0, rare0, mis0);
+        base_fast<SMEM>(p, meta_a, ent_a, e, pos1, ct1, w.w2, w.w3, x1, self1, rare1, mis1);
         // both quality characters with one byte permute, both letters with another
         uint32_t qq = __byte_perm(x0, x1, (self0 ? 1u : 0u) | (self1 ? 0x50u : 0x40u));
-        uint32_t asc = __byte_perm(0x47414354u, 0u, ct0 | (ct1 << 4));
+        uint32_t k0 = ct0, k1 = ct1;
+        if (mis0 | mis1) {
+            // mm_nucleos[nt][(uint64)(u * 3)] (src/hts.h:46): the si-th code other than the base's, si from the 8 high
+            // bits of X_sub unless the low bits could change it (3 of 256 values: the exact path decides)
+            const uint32_t p0 = (w.w0 & 0xffu) * 3u, p1 = (w.w2 & 0xffu) * 3u;
+            if (mis0) { if ((p0 & 0xffu) >= 253u) rare0 = true; else { const uint32_t si = p0 >> 8; k0 = si + (si >= ct0 ? 1u : 0u); } }
+            if (mis1) { if ((p1 & 0xffu) >= 253u) rare1 = true; else { const uint32_t si = p1 >> 8; k1 = si + (si >= ct1 ? 1u : 0u); } }
+        }
+        uint32_t asc = __byte_perm(0x47414354u, 0u, k0 | (k1 << 4));
         if (rare0 || rare1 || (c0 | c1) > 3u) {
             if (rare0 || c0 > 3u) {
                 uint32_t r = base_rare<SMEM>(p, meta_a, ent_a, e, j, pos, c0, w.w0, w.w1);
@@ -774,10 +783,10 @@ k_reads(const __grid_constant__ GenParams p) {
             const uint64_t ws = (sa - 16u) & ~(uint64_t)15;
             const uint32_t need = (pa.x & 15u) + 16u + pa.z + 19u;          // bytes of the window the gather can touch
             const uint32_t dst = TP0 + ((k & 1u) * NE + he) * tplw;
-            const uint32_t o = 16u * hl;
-            if (o < min(need, tplw)) cp_async16(dst + o, reinterpret_cast<const uint8_t*>(ws) + o);
-            if (tplw > 256u)                                              // read lengths above 190
-                for (uint32_t o2 = o + 256u; o2 < min(need, tplw); o2 += 256u) cp_async16(dst + o2, reinterpret_cast<const uint8_t*>(ws) + o2);
+            const uint32_t o = 16u * hl, top = min(need, tplw);
+            if (o < top) cp_async16(dst + o, reinterpret_cast<const uint8_t*>(ws) + o);
+            if (top > 256u)                                               // read lengths above 190
+                for (uint32_t o2 = o + 256u; o2 < top; o2 += 256u) cp_async16(dst + o2, reinterpret_cast<const uint8_t*>(ws) + o2);
         }
         cp_async_commit();
     };
@@ -785,6 +794,11 @@ k_reads(const __grid_constant__ GenParams p) {
     mbar_wait(MB0, 0);
     if (n_chunks > 1) stage_chunk(1);
     stage_tpl(0);
+    // what a lane contributes to an ID line does not change: its power of ten (lanes 1-9), its byte of the tail
+    // "-F/1\n" / "-F\n" (lanes 10-14; the strand letter is filled in per read), and -- per group -- two bytes of the prefix
+    const uint64_t m10r = c_m10[min(hl, 9u)];
+    const uint32_t tail0 = NE == 2 ? (hl == 10u ? '-' : hl == 12u ? '/' : hl == 13u ? '1' + he : '\n') : (hl == 10u ? '-' : '\n');
+    uint32_t pfxa = 0, pfxb = 0;
 
 #pragma unroll 1
     for (uint32_t k = 0; k < n_run; k++) {
@@ -822,7 +836,8 @@ k_reads(const __grid_constant__ GenParams p) {
                 __syncwarp();
                 const GroupDev* Gp = p.groups + grp;
                 const uint32_t n = Gp->prefix_len;
-                if (lane < n) sts8(SC0 + lane, p.strpool[Gp->prefix_off + lane]);
+                pfxa = hl < n ? p.strpool[Gp->prefix_off + hl] : 0u;
+                pfxb = hl + 16u < n ? p.strpool[Gp->prefix_off + hl + 16u] : 0u;
                 if (lane == 0) {
                     const uint64_t gs = reinterpret_cast<uint64_t>(Gp->seq);
                     sts32(SC0 + 32u, grp); sts32(SC0 + 36u, n); sts64(SC0 + 40u, (uint32_t)gs, (uint32_t)(gs >> 32));
@@ -883,21 +898,16 @@ k_reads(const __grid_constant__ GenParams p) {
                 sv.y = pa.y - sv.y - (pa.x < sv.x ? 1u : 0u);
                 sv.x = pa.x - sv.x;
                 if (pfx_len <= 32u && sv.y == 0u) {
-                    if (hl < pfx_len) sts8(rs + hl, lds8(SC0 + hl));
-                    if (hl + 16u < pfx_len) sts8(rs + hl + 16u, lds8(SC0 + hl + 16u));
+                    if (hl < pfx_len) sts8(rs + hl, pfxa);
+                    if (hl + 16u < pfx_len) sts8(rs + hl + 16u, pfxb);
                     constexpr uint32_t nt = NE == 2 ? 5u : 3u;
                     const uint32_t nd = idlen - pfx_len - nt;
-                    const uint2 mm = lds64(sbase + 8u * min(hl, 9u));
-                    const uint32_t q = hl == 0 ? sv.x : (uint32_t)__umul64hi((uint64_t)sv.x, ((uint64_t)mm.y << 32) | mm.x);   // start / 10^hl
+                    const uint32_t q = hl == 0 ? sv.x : (uint32_t)__umul64hi((uint64_t)sv.x, m10r);   // start / 10^hl
                     const uint32_t dig = q - 10u * (__umulhi(q, 0xCCCCCCCDu) >> 3);
-                    const uint32_t fr = (flags & kPlanReverse) ? 'R' : 'F';
-                    const uint32_t tw = NE == 2 ? ('-' | fr << 8 | '/' << 16 | ('1' + he) << 24) : ('-' | fr << 8 | '\n' << 16);
-                    const uint32_t t = hl - 10u;                                       // lanes 10..: byte t of the tail
-                    const uint32_t tc = t < 4u ? (tw >> (8u * (t & 3u))) & 0xffu : '\n';
                     const bool is_dig = hl < 10u;
-                    const uint32_t ch = is_dig ? '0' + dig : tc;
-                    const uint32_t at = rs + pfx_len + (is_dig ? nd - 1u - hl : nd + t);
-                    if (is_dig ? hl < nd : t < nt) sts8(at, ch);
+                    const uint32_t ch = is_dig ? '0' + dig : hl == 11u ? ((flags & kPlanReverse) ? 'R' : 'F') : tail0;
+                    const uint32_t at = rs + pfx_len + (is_dig ? nd - 1u - hl : nd + hl - 10u);
+                    if (is_dig ? hl < nd : hl < 10u + nt) sts8(at, ch);
                 } else if (hl == 0) {
                     slow_idline(p, rs, p.groups + grp, ((uint64_t)sv.y << 32) | sv.x, flags & kPlanReverse, he);
                 }
@@ -914,30 +924,27 @@ k_reads(const __grid_constant__ GenParams p) {
         // ---- phase B
         phase_b<SMEM, NE>(p, j, lane, sq0, sq1, len0, len1, CD0, codw, sbase + meta0, sbase + meta1, sbase + ent0, sbase + ent1);
         __syncwarp();
-        // ---- flush: the 16-byte chunks the records complete, one 128-bit load and store per lane and chunk
-        {
-            const uint32_t sh0 = lds32(ST0), g0 = lds32(ST0 + 4u);
-            const uint32_t tot0 = (sh0 & 0xffu) + lds32(PLk + 16u), n0 = tot0 >> 4;        // chunks of end 0
-            uint32_t sh1 = 0, g1 = 0, tot1 = 0, n1 = 0;
-            if (NE == 2) { sh1 = lds32(ST0 + 8u); g1 = lds32(ST0 + 12u); tot1 = (sh1 & 0xffu) + lds32(PLk + 48u); n1 = tot1 >> 4; }
-            for (uint32_t c = lane; c < n0 + n1; c += 32u) {
-                const bool second = c >= n0;
-                const uint32_t i = second ? c - n0 : c, buf = OB0 + (second ? obw : 0u) + 16u * i;
-                uint8_t* dst = (second ? p.out[1] + g1 : p.out[0] + g0) + 16u * i;
-                const uint32_t hole = (second ? sh1 : sh0) >> 8;
-                if (i == 0 && hole) {                             // the run's first chunk: only our bytes of it
-                    for (uint32_t b = hole; b < 16u; b++) dst[b] = (uint8_t)lds8(buf + b);
+        // ---- flush: the 16-byte chunks a record completes, one 128-bit load and store per lane and chunk; one half-warp per end
+        if (mine) {
+            const uint32_t sh = lds32(ST0 + 8u * he), goff = lds32(ST0 + 8u * he + 4u);
+            const uint32_t tot = (sh & 0xffu) + lds32(PLk + he * 32u + 16u), nfl = tot & ~15u;   // bytes of the buffer in use, whole chunks of them
+            const uint32_t buf = OB0 + he * obw;
+            uint8_t* dst = (he ? p.out[1] : p.out[0]) + goff;
+            for (uint32_t o = 16u * hl; o < nfl; o += 256u) {
+                if (o == 0 && sh >= 0x100u) {                     // the run's first chunk: only our bytes of it
+                    for (uint32_t b = sh >> 8; b < 16u; b++) dst[b] = (uint8_t)lds8(buf + b);
                 } else {
-                    *reinterpret_cast<uint4*>(dst) = lds128(buf);
+                    *reinterpret_cast<uint4*>(dst + o) = lds128(buf + o);
                 }
             }
-            __syncwarp();
+            uint4 carry = make_uint4(0, 0, 0, 0);
+            if (hl == 0 && nfl) carry = lds128(buf + nfl);
+            __syncwarp(NE == 2 ? 0xffffffffu : 0x0000ffffu);
             // the unfinished chunk moves to the front of the buffer; the next record continues right behind it
-            if (lane < NE) {
-                const uint32_t tot = lane ? tot1 : tot0, sh = lane ? sh1 : sh0, nfl = tot & ~15u;
-                if (nfl) sts128(OB0 + lane * obw, lds128(OB0 + lane * obw + nfl));
-                sts32(ST0 + 8u * lane, (tot & 15u) | (nfl ? 0u : sh & 0xff00u));
-                sts32(ST0 + 8u * lane + 4u, (lane ? g1 : g0) + nfl);
+            if (hl == 0) {
+                if (nfl) sts128(buf, carry);
+                sts32(ST0 + 8u * he, (tot & 15u) | (nfl ? 0u : sh & 0xff00u));
+                sts32(ST0 + 8u * he + 4u, goff + nfl);
             }
         }
         __syncwarp();
