@@ -4,7 +4,7 @@
 // turns it into u = (x+1)/2^64 with x87 long-double arithmetic
 // (/root/reference/src/pcg.h:21,99-101).  Here every logical draw
 // X(pair instance j, end, purpose, position) is a pure function of a
-// Philox4x32 counter (10 rounds; 7 in the QUAL plane), so a read does not depend on which GPU, CTA or thread
+// Philox4x32 counter (10 rounds; 7 in the per-base QUAL and INDEL planes), so a read does not depend on which GPU, CTA or thread
 // produced it:
 //
 //   counter = (j_lo, j_hi, block, plane | end << 8),  key = (seed_lo, seed_hi)
@@ -54,8 +54,8 @@ JLP_HD void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
 #endif
 }
 
-// Philox4x32-R, Salmon et al. SC'11, standard multipliers and Weyl constants.  R = 10 everywhere except the QUAL plane
-// (two thirds of all the blocks a run draws), which uses R = 7: the fewest rounds at which Philox4x32 passes
+// Philox4x32-R, Salmon et al. SC'11, standard multipliers and Weyl constants.  R = 10 everywhere except the QUAL and INDEL
+// planes (the per-base draws: nine tenths of all the blocks a run draws), which use R = 7: the fewest rounds at which Philox4x32 passes
 // BigCrush in that paper (their "Crush-resistant" column; 10 is its safety margin).
 constexpr int kQualRounds = 7;
 template <int R>
@@ -107,7 +107,7 @@ inline void philox_round_keys(uint64_t seed, uint32_t rk[20]) {
 }
 
 JLP_HD U4 draw_block(uint64_t seed, uint64_t j, uint32_t block, uint32_t plane, uint32_t end) {
-    if (plane == PL_QUAL)
+    if (plane == PL_QUAL || plane == PL_INDEL)
         return philox4x32_r<kQualRounds>((uint32_t)j, (uint32_t)(j >> 32), block, plane | (end << 8), (uint32_t)seed, (uint32_t)(seed >> 32));
     return philox4x32_10((uint32_t)j, (uint32_t)(j >> 32), block, plane | (end << 8),
                          (uint32_t)seed, (uint32_t)(seed >> 32));

@@ -62,7 +62,7 @@ enum { PU_INDEL = 0, PU_DIE = 1, PU_COIN = 2, PU_MIS = 3, PU_SUB = 4, PU_INS = 5
 static void call(uint64_t seed, uint64_t j, uint32_t block, uint32_t plane, uint32_t end, uint32_t w[4]) {
     uint32_t ctr[4] = {(uint32_t)j, (uint32_t)(j >> 32), block, plane | (end << 8)};
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
-    philox4x32(ctr, key, w, plane == PL_QUAL ? 7 : 10);      /* the QUAL plane runs 7 rounds (jlp_draws.h, kQualRounds) */
+    philox4x32(ctr, key, w, plane == PL_QUAL || plane == PL_INDEL ? 7 : 10);      /* the per-base planes run 7 rounds (jlp_draws.h, kQualRounds) */
 }
 
 /* pair-level draws: which = 0 fraglen, 1 start, 2 strand, 3 dup */
