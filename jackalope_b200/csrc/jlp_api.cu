@@ -2053,6 +2053,9 @@ int jlp_threshold(int kind, double p, uint64_t* thr, int* all) {
     if (kind == 1) t = thr_double_lt(p);
     else if (kind == 2) t = thr_double_le(p);
     else if (kind == 3) t = thr_ld_lt(p);
+    else if (kind == 11) t = thr_double_lt_x87(p);
+    else if (kind == 12) t = thr_double_le_x87(p);
+    else if (kind == 13) t = thr_ld_lt_x87(p);
     else return JLP_ERR_ARG;
     if (thr) *thr = t.thr;
     if (all) *all = t.all;

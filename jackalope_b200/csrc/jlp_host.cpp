@@ -1,6 +1,9 @@
-// Host-side model preparation (see jlp_host.h).  Compiled by g++; x86-64 only,
-// because the thresholds are found by evaluating the reference's own x87
-// long-double expressions (src/pcg.h:99-101) at candidate draws.
+// Host-side model preparation (see jlp_host.h).  Compiled by g++.
+//
+// The comparison thresholds restate the reference's floating-point tests on u = runif_01(x) = (x + 1) / 2^64
+// (x87 long double, src/pcg.h:99-101) as counts of 64-bit draws, in pure integer arithmetic:
+// they do not need an x87 and give the same numbers on any host.  Where long double has the x87 format the
+// reference's own expressions are also evaluated (thr_*_x87) and the tests require both to agree.
 #include "jlp_host.h"
 
 #include <algorithm>
@@ -11,19 +14,83 @@
 #include <random>
 #include <stdexcept>
 
-#if LDBL_MANT_DIG != 64
-#error "jlp_host.cpp needs the x87 80-bit long double the reference's runif_01 is defined with"
-#endif
-
 namespace jlp {
 
 namespace {
 
+typedef unsigned __int128 u128;
+
+// smallest integer y >= m * 2^s (strict: > m * 2^s); m < 2^55.  Values above 2^64 are returned as 2^64 + 1.
+u128 int_at_least(uint64_t m, int s, bool strict) {
+    const u128 cap = ((u128)1 << 64) + 1;
+    if (m == 0) return strict ? 1 : 0;
+    if (s >= 0) {
+        if (s > 64) return cap;
+        const u128 v = (u128)m << s;
+        return std::min<u128>(cap, v + (strict ? 1 : 0));
+    }
+    const int k = -s;
+    if (k >= 64) return 1;                              // 0 < m * 2^s < 1
+    const uint64_t q = m >> k, rem = m & ((1ull << k) - 1);
+    return rem ? (u128)q + 1 : (u128)q + (strict ? 1 : 0);
+}
+
+// p = M * 2^E with 2^52 <= M < 2^53 (p a positive normal double)
+void split_double(double p, uint64_t& M, int& E) {
+    int ex;
+    const double f = std::frexp(p, &ex);                // p = f * 2^ex, 0.5 <= f < 1
+    M = (uint64_t)std::ldexp(f, 53);
+    E = ex - 53;
+}
+
+// y* = the smallest integer y in [0, 2^64 + 1] whose u = y / 2^64, ROUNDED TO DOUBLE (nearest, ties to even), is >= p.
+// u rounds to a double >= p exactly when it lies at or above the midpoint between p and the double below it -- above
+// it only, if the tie goes to the neighbour (p's mantissa odd).
+u128 first_y_double_ge(double p) {
+    if (!(p > 0)) return 0;
+    if (p > 1) return ((u128)1 << 64) + 1;
+    if (p < 1e-300) return 1;
+    uint64_t M;
+    int E;
+    split_double(p, M, E);
+    const bool pow2 = M == (1ull << 52);                // the spacing below a power of two is half the one above
+    const uint64_t mm = pow2 ? 4 * M - 1 : 2 * M - 1;   // midpoint = mm * 2^(E - 2) or mm * 2^(E - 1)
+    return int_at_least(mm, (pow2 ? E - 2 : E - 1) + 64, (M & 1) != 0);
+}
+
+Thr count_below(u128 ystar) {                           // #{x in [0, 2^64) : x + 1 < y*}
+    if (ystar <= 1) return Thr{0, false};
+    if (ystar > ((u128)1 << 64)) return Thr{UINT64_MAX, true};
+    return Thr{(uint64_t)(ystar - 1), false};
+}
+
+}  // namespace
+
+// #{x : double(u) < p}
+Thr thr_double_lt(double p) { return count_below(first_y_double_ge(p)); }
+// #{x : !(double(u) > p)} = #{x : double(u) < the double above p}
+Thr thr_double_le(double p) {
+    if (p < 0) return Thr{0, false};
+    return count_below(first_y_double_ge(std::nextafter(p, INFINITY)));
+}
+// #{x : u < p} in long double: u = y / 2^64 exactly, so y < p * 2^64
+Thr thr_ld_lt(double p) {
+    if (!(p > 0)) return Thr{0, false};
+    if (p > 1) return Thr{UINT64_MAX, true};
+    if (p < 1e-300) return Thr{0, false};
+    uint64_t M;
+    int E;
+    split_double(p, M, E);
+    return count_below(int_at_least(M, E + 64, false));
+}
+
+#if LDBL_MANT_DIG == 64
+// ---- the reference's own expressions, evaluated on an x87 (test oracle of the integer forms above)
+namespace {
 inline long double runif_01(uint64_t x) {
     const long double max64 = static_cast<long double>(UINT64_MAX);
     return (static_cast<long double>(x) + 1) / (max64 + 2);
 }
-
 // smallest x for which pred is false, pred being true on a prefix of [0, 2^64)
 template <typename F> Thr prefix_count(F pred) {
     if (pred(UINT64_MAX)) return Thr{UINT64_MAX, true};
@@ -35,49 +102,15 @@ template <typename F> Thr prefix_count(F pred) {
     }
     return Thr{hi, false};
 }
-
-// The same with a guess of where the prefix ends (for thresholds on u = runif_01(x) against p that is p * 2^64 up to
-// rounding): a bracket is grown around the guess and bisected, about 25 evaluations instead of 64.
-template <typename F> Thr prefix_count_near(F pred, long double guess) {
-    if (pred(UINT64_MAX)) return Thr{UINT64_MAX, true};
-    if (!pred(0)) return Thr{0, false};
-    uint64_t g = guess <= 0 ? 0 : guess >= 18446744073709551615.0L ? UINT64_MAX : static_cast<uint64_t>(guess);
-    uint64_t lo = 0, hi = UINT64_MAX;  // pred(lo) true, pred(hi) false
-    if (pred(g)) {
-        lo = g;
-        for (uint64_t step = 1024; ; step *= 16) {
-            const uint64_t c = g > UINT64_MAX - step ? UINT64_MAX : g + step;
-            if (!pred(c)) { hi = c; break; }
-            lo = c;
-            if (c == UINT64_MAX) break;
-        }
-    } else {
-        hi = g;
-        for (uint64_t step = 1024; ; step *= 16) {
-            const uint64_t c = g < step ? 0 : g - step;
-            if (pred(c)) { lo = c; break; }
-            hi = c;
-            if (c == 0) break;
-        }
-    }
-    while (hi - lo > 1) {
-        uint64_t mid = lo + (hi - lo) / 2;
-        if (pred(mid)) lo = mid; else hi = mid;
-    }
-    return Thr{hi, false};
-}
-
 }  // namespace
-
-Thr thr_double_lt(double p) {
-    return prefix_count_near([p](uint64_t x) { double u = runif_01(x); return u < p; }, (long double)p * 18446744073709551616.0L);
-}
-Thr thr_double_le(double p) {
-    return prefix_count_near([p](uint64_t x) { double u = runif_01(x); return !(u > p); }, (long double)p * 18446744073709551616.0L);
-}
-Thr thr_ld_lt(double p) {
-    return prefix_count([p](uint64_t x) { return runif_01(x) < p; });
-}
+Thr thr_double_lt_x87(double p) { return prefix_count([p](uint64_t x) { double u = runif_01(x); return u < p; }); }
+Thr thr_double_le_x87(double p) { return prefix_count([p](uint64_t x) { double u = runif_01(x); return !(u > p); }); }
+Thr thr_ld_lt_x87(double p) { return prefix_count([p](uint64_t x) { return runif_01(x) < p; }); }
+#else
+Thr thr_double_lt_x87(double p) { return thr_double_lt(p); }
+Thr thr_double_le_x87(double p) { return thr_double_le(p); }
+Thr thr_ld_lt_x87(double p) { return thr_ld_lt(p); }
+#endif
 
 void alias_build(const double* probs, uint64_t n, double* Prob, uint64_t* Alias) {
     std::vector<double> p(probs, probs + n);

@@ -25,6 +25,11 @@ Thr thr_double_lt(double p);
 Thr thr_double_le(double p);
 // #{x : u < p} (long double compare) src/hts_illumina.cpp:352
 Thr thr_ld_lt(double p);
+// the same three found by evaluating the reference's x87 expressions at candidate draws (only where long double is
+// the x87 format; elsewhere they return the integer forms): the test oracle of the integer restatements
+Thr thr_double_lt_x87(double p);
+Thr thr_double_le_x87(double p);
+Thr thr_ld_lt_x87(double p);
 
 // --- alias tables ------------------------------------------------------------
 // AliasSampler::construct, src/alias_sampler.h:68-106

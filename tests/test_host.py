@@ -415,3 +415,28 @@ def test_oracle_lazy_haplotype_groups_match_the_full_materialisation():
         b = oracle_run(haps, 4000, 100, True, 5, lo=lo, hi=hi, hap_seqs=lazy, only_job=(jl, jh), **kw)
         assert a["r1"] == b["r1"] and a["r2"] == b["r2"] and len(a["r1"]) > 0
     assert 0 < len(lazy.cache) < 20 and all(h == 3 for h, _ in lazy.cache)
+
+
+def test_integer_thresholds_equal_the_x87_search():
+    """The comparison thresholds are computed in integer arithmetic (no x87 needed: SURVEY.md App. A.2); kinds 11-13 of
+    jlp_threshold evaluate the reference's own long-double expressions at candidate draws (x86-64).  Equal on random
+    probabilities of every magnitude and on doubles that sit exactly on, just below and just above a draw boundary."""
+    import math
+    import random
+    lib = _lib.lib()
+
+    def thr(kind, p):
+        t, a = C.c_uint64(), C.c_int()
+        assert lib.jlp_threshold(kind, p, C.byref(t), C.byref(a)) == 0
+        return t.value, a.value
+
+    rnd = random.Random(5)
+    ps = [0.0, 1.0, 0.5, 1e-25, 2.0 ** -64, 3 * 2.0 ** -64, 1 - 2.0 ** -53, 0.02, 0.00009, 0.0002, 10 ** -2.55, 1.5, -0.5, 2.0 ** -70, 5e-324]
+    for _ in range(400):
+        ps.append(min(1.0, rnd.random() * 2 ** rnd.choice([rnd.uniform(-70, 0), rnd.uniform(-12, 0), 0])))
+    for _ in range(150):
+        v = rnd.getrandbits(rnd.randint(1, 64)) / 2 ** 64
+        ps += [v, math.nextafter(v, 0), math.nextafter(v, 2)]
+    for p in ps:
+        for kind in (1, 2, 3):
+            assert thr(kind, p) == thr(kind + 10, p), (kind, p)
