@@ -16,6 +16,9 @@ using namespace jlp_glue;
 
 namespace {
 
+int abort_cb(void* prog) { return static_cast<Progress*>(prog)->check_abort() ? 1 : 0; }      // src/hts.h:396-399
+void progress_cb(void* prog, uint64_t reads) { static_cast<Progress*>(prog)->increment(reads); }  // src/hts.h:414
+
 void fill_params(jlp_pacbio_params& P, const std::string& out_prefix, const int& compress, const std::string& comp_method,
                  const uint64& n_reads, const uint64& n_threads, const uint64& read_pool_size, const double& prob_dup,
                  const double& scale, const double& sigma, const double& loc, const double& min_read_len,
@@ -59,8 +62,9 @@ void pacbio_ref_cpp(SEXP ref_genome_ptr, const std::string& out_prefix, const in
     fill_params(P, out_prefix, compress, comp_method, n_reads, n_threads, read_pool_size, prob_dup, scale, sigma, loc,
                 min_read_len, read_probs, lens, max_passes, chi2_params_n, chi2_params_s, sqrt_params, norm_params, prob_thresh,
                 prob_ins, prob_del, prob_subst);
-    ctx.check(jlp_pacbio(ctx.p, 0, &P, nullptr));
-    prog_bar.increment(n_reads);
+    P.abort_cb = abort_cb; P.progress_cb = progress_cb; P.cb_user = &prog_bar;
+    const int rc = jlp_pacbio(ctx.p, 0, &P, nullptr);
+    if (rc != JLP_OK && rc != JLP_ERR_ABORTED) ctx.check(rc);       // an interrupt just ends the run (src/hts.h:396-399)
 }
 
 //[[Rcpp::export]]
@@ -84,6 +88,7 @@ void pacbio_hap_cpp(SEXP hap_set_ptr, const std::string& out_prefix, const bool&
                 prob_ins, prob_del, prob_subst);
     P.sep_files = sep_files;
     P.haplotype_probs = haplotype_probs.data();
-    ctx.check(jlp_pacbio(ctx.p, 1, &P, nullptr));
-    prog_bar.increment(n_reads);
+    P.abort_cb = abort_cb; P.progress_cb = progress_cb; P.cb_user = &prog_bar;
+    const int rc = jlp_pacbio(ctx.p, 1, &P, nullptr);
+    if (rc != JLP_OK && rc != JLP_ERR_ABORTED) ctx.check(rc);
 }

@@ -43,6 +43,7 @@ class PacbioParams(C.Structure):
         ("sqrt_params", C.c_double * 2), ("norm_params", C.c_double * 2), ("prob_thresh", C.c_double),
         ("prob_ins", C.c_double), ("prob_del", C.c_double), ("prob_subst", C.c_double), ("seed", C.c_uint64),
         ("batch_reads", C.c_uint64), ("comp_engine", C.c_int), ("shard_index", C.c_uint32), ("shard_count", C.c_uint32),
+        ("abort_cb", ABORT_CB), ("progress_cb", PROGRESS_CB), ("cb_user", C.c_void_p),
     ]
 
 

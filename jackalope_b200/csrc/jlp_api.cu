@@ -1695,8 +1695,9 @@ PbGroups pb_groups(jlp_ctx* c, bool use_haps, const jlp_pacbio_params* P) {
     return G;
 }
 
-// First version of the driver: one batch at a time (plan upload, k_pb_plan, scan, k_pb_reads, optional BGZF, copy,
-// write), no overlap between the stages yet.
+// The driver: per batch the per-read quantities are prepared on the host (batch k + 1 on a helper thread while batch k
+// is on the device), then plan upload, k_pb_plan, scan, k_pb_reads, optional BGZF, copy, and the write of batch k
+// overlaps the next batch.  Callbacks are called on the calling thread between batches.
 void run_pacbio(jlp_ctx* c, bool use_haps, const jlp_pacbio_params* P, int sink_kind, char* mem, uint64_t cap, uint64_t* mem_len,
                 jlp_run_stats* stats) {
     PbModel model;
@@ -1734,7 +1735,7 @@ void run_pacbio(jlp_ctx* c, bool use_haps, const jlp_pacbio_params* P, int sink_
     d_strpool.upload(G.strpool, c->s_compute);
     d_totals.ensure(4);
     CK(cudaMemsetAsync(d_totals.p, 0, 4 * sizeof(uint64_t), c->s_compute));
-    uint64_t B = P->batch_reads ? P->batch_reads : 16384;
+    uint64_t B = P->batch_reads ? P->batch_reads : 65536;
     // a chain of duplicates never leaves its pool (src/hts.h:266-267): batches are whole pools, so a duplicate's leader is in
     // its batch
     if (dups) B = std::max<uint64_t>(P->read_pool_size, B / P->read_pool_size * P->read_pool_size);
@@ -1744,7 +1745,6 @@ void run_pacbio(jlp_ctx* c, bool use_haps, const jlp_pacbio_params* P, int sink_
     jlp_run_stats st;
     std::memset(&st, 0, sizeof st);
     uint64_t mem_used = 0;
-    std::vector<PbRead> plan;
     cudaEvent_t ev[3];
     for (cudaEvent_t& e : ev) CK(cudaEventCreate(&e));
     for (const Job& job : G.jobs) {
@@ -1767,12 +1767,14 @@ void run_pacbio(jlp_ctx* c, bool use_haps, const jlp_pacbio_params* P, int sink_
                 s_lo = std::min(job.hi, job.lo + p_lo * pool);
                 s_hi = std::min(job.hi, job.lo + p_hi * pool);
             }
-            for (uint64_t b0 = s_lo; b0 < s_hi; b0 += B) {
-                const uint32_t n = (uint32_t)std::min<uint64_t>(B, s_hi - b0);
-                // ---- per-read quantities on the host
-                plan.resize(n);
-                uint64_t bound = 0;
-                {
+            // ---- per-read quantities on the host (read length, passes, error probabilities, thresholds): batch k + 1 is
+            //      prepared by a helper thread (which spreads the reads over n_threads workers) while the device
+            //      generates batch k and the sink takes it
+            struct Prepared { std::vector<PbRead> plan; uint64_t bound = 0; std::string err; };
+            auto prepare = [&](uint64_t b0, uint32_t n, Prepared& out) {
+                try {
+                    std::vector<PbRead>& plan = out.plan;
+                    plan.resize(n);
                     // chains of duplicates: read i re-reads iff the draw made after read i - 1 says so and i does not open a pool
                     std::vector<uint32_t> lead(n, kPbNoLeader);
                     if (dups)
@@ -1783,34 +1785,59 @@ void run_pacbio(jlp_ctx* c, bool use_haps, const jlp_pacbio_params* P, int sink_
                     // first the leaders, then the duplicates (which take their leader's chromosome and length)
                     const uint32_t nt = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(P->n_threads, 1), 64);
                     std::vector<uint64_t> part(nt, 0);
+                    std::vector<std::string> errs(nt);
                     for (int pass = 0; pass < (dups ? 2 : 1); pass++) {
                         auto work = [&](uint32_t k) {
-                            for (uint32_t i = k; i < n; i += nt) {
-                                if ((lead[i] != kPbNoLeader) != (pass == 1)) continue;
-                                const uint64_t j = b0 + i;
-                                PbSample smp;
-                                size_t g;
-                                if (pass == 0) {
-                                    g = (size_t)(std::upper_bound(G.group_off.begin(), G.group_off.end(), j) - G.group_off.begin()) - 1;
-                                    smp = pb_sample(model, P->seed, j, G.groups[g].len);
-                                } else {
-                                    g = plan[lead[i]].group;
-                                    smp = pb_sample_passes(model, P->seed, j, plan[lead[i]].read_length);
+                            try {
+                                for (uint32_t i = k; i < n; i += nt) {
+                                    if ((lead[i] != kPbNoLeader) != (pass == 1)) continue;
+                                    const uint64_t j = b0 + i;
+                                    PbSample smp;
+                                    size_t g;
+                                    if (pass == 0) {
+                                        g = (size_t)(std::upper_bound(G.group_off.begin(), G.group_off.end(), j) - G.group_off.begin()) - 1;
+                                        smp = pb_sample(model, P->seed, j, G.groups[g].len);
+                                    } else {
+                                        g = plan[lead[i]].group;
+                                        smp = pb_sample_passes(model, P->seed, j, plan[lead[i]].read_length);
+                                    }
+                                    std::memset(&plan[i], 0, sizeof(PbRead));
+                                    pb_read_model(model, P->seed, j, smp, plan[i]);
+                                    plan[i].group = (uint32_t)g;
+                                    plan[i].leader = lead[i];
+                                    part[k] += max_prefix + 24 + 2 * smp.read_length + 5;
                                 }
-                                std::memset(&plan[i], 0, sizeof(PbRead));
-                                pb_read_model(model, P->seed, j, smp, plan[i]);
-                                plan[i].group = (uint32_t)g;
-                                plan[i].leader = lead[i];
-                                part[k] += max_prefix + 24 + 2 * smp.read_length + 5;
-                            }
+                            } catch (const std::exception& e) { errs[k] = e.what(); }
                         };
                         std::vector<std::thread> th;
                         for (uint32_t k = 1; k < nt; k++) th.emplace_back(work, k);
                         work(0);
                         for (std::thread& t : th) t.join();
                     }
-                    for (uint64_t v : part) bound += v;
+                    for (const std::string& e : errs) if (!e.empty()) { out.err = e; return; }
+                    out.bound = 0;
+                    for (uint64_t v : part) out.bound += v;
+                } catch (const std::exception& e) { out.err = e.what(); }
+            };
+            Prepared prep[2];
+            std::thread prep_thread;
+            struct JoinPrep { std::thread& t; ~JoinPrep() { if (t.joinable()) t.join(); } } join_prep{prep_thread};
+            if (s_lo < s_hi) prepare(s_lo, (uint32_t)std::min<uint64_t>(B, s_hi - s_lo), prep[0]);
+            uint64_t bk = 0;
+            for (uint64_t b0 = s_lo; b0 < s_hi; b0 += B, bk++) {
+                const uint32_t n = (uint32_t)std::min<uint64_t>(B, s_hi - b0);
+                if (prep_thread.joinable()) prep_thread.join();
+                Prepared& cur = prep[bk & 1];
+                if (!cur.err.empty()) throw ArgErr(cur.err);
+                if (P->abort_cb && P->abort_cb(P->cb_user)) throw Aborted();      // Progress::check_abort, src/hts.h:396-399
+                if (b0 + B < s_hi) {
+                    Prepared* nxt = &prep[(bk + 1) & 1];
+                    const uint64_t nb0 = b0 + B;
+                    const uint32_t nn = (uint32_t)std::min<uint64_t>(B, s_hi - nb0);
+                    prep_thread = std::thread([&prepare, nb0, nn, nxt]() { prepare(nb0, nn, *nxt); });
                 }
+                std::vector<PbRead>& plan = cur.plan;
+                const uint64_t bound = cur.bound;
                 d_reads.ensure(n);
                 d_rec_len.ensure(n); d_rec_local.ensure(n);
                 const uint32_t nsb = (n + kScanBlock - 1) / kScanBlock;
@@ -1844,7 +1871,7 @@ void run_pacbio(jlp_ctx* c, bool use_haps, const jlp_pacbio_params* P, int sink_
                 CK(cudaEventElapsedTime(&ms, ev[1], ev[2])); if (dev_z) { st.bgzf_ms += ms; st.device_ms += ms; }
                 st.pairs += n; st.batches++; st.bytes_out[0] += tot[0];
                 if (dev_z) st.z_bytes[0] += tot[2];
-                if (sink_kind == SINK_NONE) continue;
+                if (sink_kind == SINK_NONE) { if (P->progress_cb) P->progress_cb(P->cb_user, n); continue; }
                 const uint64_t nb = dev_z ? tot[2] : tot[0];
                 const int hk = (int)(n_batch++ & 1);
                 settle(hk);                                     // the slices of the batch before last are in the file
@@ -1884,7 +1911,9 @@ void run_pacbio(jlp_ctx* c, bool use_haps, const jlp_pacbio_params* P, int sink_
                     }
                     fpos += len;
                 }
+                if (P->progress_cb) P->progress_cb(P->cb_user, n);                  // Progress::increment, src/hts.h:414
             }
+            if (prep_thread.joinable()) prep_thread.join();
             settle(0); settle(1);
             if (fd >= 0 && (dev_z || zmethod == DEFLATE_BGZF)) {
                 const std::string w = pwrite_all(fd, kBgzfEof, sizeof kBgzfEof, fpos);

@@ -191,3 +191,38 @@ def test_pacbio_shards_concatenate(ctx):
     parts = [J.pacbio(haps, "", 400, seed=46, ctx=ctx, sink="memory", shard=(k, 2), **hk)[0] for k in range(2)]
     # with sep_files every job (haplotype) is split: shard 0 holds the first halves, in haplotype order
     assert sum(len(p) for p in parts) == len(whole) and sorted(b"".join(parts).split(b"@")) == sorted(whole.split(b"@"))
+
+
+def test_pacbio_callbacks(ctx):
+    """jlp_pacbio_params.progress_cb / abort_cb (Progress::increment / check_abort of the shared driver,
+    /root/reference/src/hts.h:396-399,414): progress adds up to n_reads over the batches; an abort request ends the
+    run with JLP_ERR_ABORTED."""
+    import ctypes as C
+    from jackalope_b200 import _lib
+    from jackalope_b200.pacbio import _params
+    from oracle.harness_pacbio import DEFAULTS as D
+    g = J.random_genome(2, 40_000, seed=51)
+    ctx.set_genome(g)
+    p, keep = _params(g, "", 900, D["chi2_params_s"], D["chi2_params_n"], D["max_passes"], D["sqrt_params"], D["norm_params"],
+                      D["prob_thresh"], D["ins_prob"], D["del_prob"], D["sub_prob"], D["min_read_length"], D["lognorm_read_length"],
+                      None, 0.0, None, False, 0, "bgzip", 2, 100, 77, 200, "auto")
+    seen = [0, 0]
+
+    def progress(_u, n):
+        seen[0] += n
+        seen[1] += 1
+
+    p.progress_cb = _lib.PROGRESS_CB(progress)
+    p.abort_cb = _lib.ABORT_CB(lambda _u: 0)
+    st, n = _lib.RunStats(), C.c_uint64()
+    assert ctx.lib.jlp_pacbio_to_memory(ctx.h, 0, C.byref(p), None, 0, C.byref(n), C.byref(st)) == 0
+    assert seen == [900, 5]
+    calls = [0]
+
+    def abort(_u):
+        calls[0] += 1
+        return 1 if calls[0] > 2 else 0
+
+    p.abort_cb = _lib.ABORT_CB(abort)
+    assert ctx.lib.jlp_pacbio_to_memory(ctx.h, 0, C.byref(p), None, 0, C.byref(n), C.byref(st)) == _lib.JLP_ERR_ABORTED
+    assert seen[0] == 900 + 2 * 200
