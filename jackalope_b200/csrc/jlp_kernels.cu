@@ -634,16 +634,18 @@ template <bool SMEM, uint32_t NE>
 __device__ JLP_PHASEB_ATTR void phase_b(const GenParams& p, uint64_t j, uint32_t lane, uint32_t sq0, uint32_t sq1, uint32_t len0, uint32_t len1,
                                      uint32_t cd, uint32_t codw, uint32_t mA0, uint32_t mA1, uint32_t eA0, uint32_t eA1) {
     const uint32_t nb0 = (len0 + 1u) >> 1, nbt = nb0 + ((len1 + 1u) >> 1);
+    // what differs between the two ends enters as base + e * difference: multiply-adds (the FMA pipe has room, the ALU
+    // pipe, which selects would use, is the kernel's bound)
+    const uint32_t d_len = len1 - len0, d_sq = sq1 - sq0, d_m = mA1 - mA0, d_e = eA1 - eA0;
 #pragma unroll 1
     for (uint32_t q = lane; q < nbt; q += 32) {
-        const bool second = NE == 2 && q >= nb0;
-        const uint32_t e = second ? 1u : 0u;
-        const uint32_t blk = q - (second ? nb0 : 0u);
+        const uint32_t e = NE == 2 && q >= nb0 ? 1u : 0u;
+        const uint32_t blk = q - e * nb0;
         const uint32_t pos = 2u * blk;
-        const uint32_t ln = second ? len1 : len0;
-        const uint32_t s0 = (second ? sq1 : sq0) + pos;
+        const uint32_t ln = len0 + e * d_len;
+        const uint32_t s0 = sq0 + e * d_sq + pos;
         const uint32_t q0 = s0 + ln + 3u;
-        const uint32_t meta_a = second ? mA1 : mA0, ent_a = second ? eA1 : eA0;
+        const uint32_t meta_a = mA0 + e * d_m, ent_a = eA0 + e * d_e;
         const bool two = pos + 1u < ln;
         const U4 w = qual_block(p, j, blk, e);
         const uint32_t cc = lds16(cd + e * codw + pos);
