@@ -277,6 +277,9 @@ struct jlp_ctx {
     uint64_t h2d_bytes = 0;
     // scratch of the haplotype materialisation (mutation records of one chromosome)
     HapArena hap_mem;
+    // PacBio driver: FASTQ of a batch on the device, its compressed form, and the two pinned host buffers batches alternate between
+    DevBuf<uint8_t> pb_out, pb_zslots, pb_zout;
+    PinBuf<uint8_t> pb_h_buf[2];
     DevBuf<uint64_t> m_old, m_new, m_off;
     DevBuf<int64_t> m_sm;
     DevBuf<uint8_t> m_pool;
@@ -1719,12 +1722,15 @@ void run_pacbio(jlp_ctx* c, bool use_haps, const jlp_pacbio_params* P, int sink_
     const int zmethod = P->compress <= 0 || dev_z || sink_kind != SINK_FILES ? -1
                         : (P->n_threads > 1 || std::string(P->comp_method) == "bgzip") ? DEFLATE_BGZF : DEFLATE_GZIP;
     DevBuf<GroupDev> d_groups;
-    DevBuf<uint8_t> d_strpool, d_out, d_zslots, d_zout;
+    DevBuf<uint8_t> d_strpool;
+    // the big buffers belong to the context: pinning (and unpinning) a gigabyte of host memory on every call cost
+    // more than generating the reads
+    DevBuf<uint8_t>&d_out = c->pb_out, &d_zslots = c->pb_zslots, &d_zout = c->pb_zout;
     DevBuf<PbRead> d_reads;
     DevBuf<uint32_t> d_rec_len, d_rec_local, d_zlen;
     DevBuf<uint64_t> d_block_tot, d_block_base, d_totals, d_zoff;
     // two host buffers: the writer threads copy batch k into the file while batch k + 1 is prepared, generated and copied
-    PinBuf<uint8_t> h_buf[2];
+    PinBuf<uint8_t>* h_buf = c->pb_h_buf;
     Mapping h_map[2];
     std::atomic<int> h_pending[2];
     h_pending[0] = 0; h_pending[1] = 0;
@@ -1735,7 +1741,7 @@ void run_pacbio(jlp_ctx* c, bool use_haps, const jlp_pacbio_params* P, int sink_
     d_strpool.upload(G.strpool, c->s_compute);
     d_totals.ensure(4);
     CK(cudaMemsetAsync(d_totals.p, 0, 4 * sizeof(uint64_t), c->s_compute));
-    uint64_t B = P->batch_reads ? P->batch_reads : 65536;
+    uint64_t B = P->batch_reads ? P->batch_reads : 32768;
     // a chain of duplicates never leaves its pool (src/hts.h:266-267): batches are whole pools, so a duplicate's leader is in
     // its batch
     if (dups) B = std::max<uint64_t>(P->read_pool_size, B / P->read_pool_size * P->read_pool_size);
