@@ -612,6 +612,8 @@ struct RunExtras {
     const PerJobBytes* base = nullptr;    // [jobs] where this call's bytes start in each job's files / in the memory sink
     bool shared_files = false;            // the files exist, created and sized by the caller: open without truncating, no EOF block
     std::string part_suffix;              // compressed multi-GPU runs: this call writes <name><suffix>, joined by the caller
+    bool no_eof = false;                  // ... and the caller appends the BGZF end-of-file block
+    const std::vector<std::string>* job_suffix = nullptr;   // [jobs] the same per job (overrides part_suffix)
 };
 
 void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jlp_run_stats* stats, const RunExtras& X = RunExtras()) {
@@ -885,7 +887,7 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
             for (Slot& s : c->slot) wait_writes(s);
             sink.close_files();
             for (int e = 0; e < n_ends; e++) {
-                sink.names[e] = file_name(job, e, want_gz, P) + X.part_suffix;
+                sink.names[e] = file_name(job, e, want_gz, P) + (X.job_suffix ? (*X.job_suffix)[jk] : X.part_suffix);
                 sink.pos[e] = sink.done[e] = X.base ? (*X.base)[jk][e] : 0;
                 sink.own_size[e] = !X.shared_files;
                 sink.fd[e] = ::open(sink.names[e].c_str(), X.shared_files ? O_RDWR : (O_RDWR | O_CREAT | O_TRUNC), 0644);
@@ -970,7 +972,7 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
         while (!computing.empty() || !copying.empty()) drain_one();
         if (z_pending) { wait_writes(*z_pending); z_pending = nullptr; }
         for (Slot& s : c->slot) wait_writes(s);
-        const bool eof_block = !X.shared_files && X.part_suffix.empty();      // a multi-GPU run appends it once, after joining the parts
+        const bool eof_block = !X.shared_files && X.part_suffix.empty() && !X.no_eof;      // a multi-GPU run appends it once, after joining the parts
         if (sink.kind == SINK_FILES && (zmethod == DEFLATE_BGZF || dev_z) && eof_block)
             for (int e = 0; e < n_ends; e++) {   // bgzf_close appends the empty end-of-file block
                 std::string w = pwrite_all(sink.fd[e], kBgzfEof, sizeof kBgzfEof, sink.pos[e]);
@@ -1038,27 +1040,27 @@ struct MultiShared {
 int multi_abort_cb(void* u) { return static_cast<MultiShared*>(u)->abort.load(std::memory_order_relaxed); }
 void multi_progress_cb(void* u, uint64_t reads) { static_cast<MultiShared*>(u)->progress.fetch_add(reads, std::memory_order_relaxed); }
 
-std::string copy_range(int out_fd, int in_fd, uint64_t n) {
+// n bytes from in_fd at in_off to out_fd at out_off (both files on any file system)
+std::string copy_range(int out_fd, uint64_t out_off, int in_fd, uint64_t in_off, uint64_t n) {
     std::vector<uint8_t> buf;
+    bool use_cfr = true;
     while (n) {
-        ssize_t w = ::copy_file_range(in_fd, nullptr, out_fd, nullptr, (size_t)std::min<uint64_t>(n, 1ull << 30), 0);
-        if (w < 0 && (errno == EXDEV || errno == EINVAL || errno == ENOSYS || errno == EOPNOTSUPP)) {
-            // file systems without copy_file_range: read + write
-            buf.resize(8u << 20);
-            ssize_t r = ::read(in_fd, buf.data(), (size_t)std::min<uint64_t>(n, buf.size()));
-            if (r < 0) { if (errno == EINTR) continue; return std::strerror(errno); }
-            if (r == 0) return "unexpected end of a part file";
-            for (ssize_t o = 0; o < r;) {
-                ssize_t x = ::write(out_fd, buf.data() + o, (size_t)(r - o));
-                if (x < 0) { if (errno == EINTR) continue; return std::strerror(errno); }
-                o += x;
-            }
-            n -= (uint64_t)r;
-            continue;
+        if (use_cfr) {
+            off_t oi = (off_t)in_off, oo = (off_t)out_off;
+            const ssize_t w = ::copy_file_range(in_fd, &oi, out_fd, &oo, (size_t)std::min<uint64_t>(n, 1ull << 30), 0);
+            if (w > 0) { n -= (uint64_t)w; in_off += (uint64_t)w; out_off += (uint64_t)w; continue; }
+            if (w < 0 && errno == EINTR) continue;
+            if (w == 0) return "unexpected end of a part file";
+            if (errno != EXDEV && errno != EINVAL && errno != ENOSYS && errno != EOPNOTSUPP) return std::strerror(errno);
+            use_cfr = false;                                  // file systems without copy_file_range: read + write
         }
-        if (w < 0) { if (errno == EINTR) continue; return std::strerror(errno); }
-        if (w == 0) return "unexpected end of a part file";
-        n -= (uint64_t)w;
+        buf.resize(8u << 20);
+        const ssize_t r = ::pread(in_fd, buf.data(), (size_t)std::min<uint64_t>(n, buf.size()), (off_t)in_off);
+        if (r < 0) { if (errno == EINTR) continue; return std::strerror(errno); }
+        if (r == 0) return "unexpected end of a part file";
+        const std::string w = pwrite_all(out_fd, buf.data(), (uint64_t)r, out_off);
+        if (!w.empty()) return w;
+        n -= (uint64_t)r; in_off += (uint64_t)r; out_off += (uint64_t)r;
     }
     return std::string();
 }
@@ -1175,10 +1177,14 @@ void run_multi(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& si
         std::vector<std::string> names;
         ~Cleanup() { for (const std::string& n : names) ::unlink(n.c_str()); }
     } cleanup;
+    // compressed: for every job the first device with a part in it writes the file itself, the others write parts
+    std::vector<size_t> first_dev(nj, N);
+    for (size_t k = 0; k < nj; k++)
+        for (size_t r = N; r-- > 0;) if (ranges[r][k].second > ranges[r][k].first) first_dev[k] = r;
     if (parts)
         for (size_t r = 0; r < N; r++)
             for (size_t k = 0; k < nj; k++)
-                if (ranges[r][k].second > ranges[r][k].first)
+                if (ranges[r][k].second > ranges[r][k].first && r != first_dev[k])
                     for (int e = 0; e < n_ends; e++) cleanup.names.push_back(file_name(Y.jobs[k], e, true, P) + ".part" + std::to_string(r));
     on_devices([&](size_t r) {
         Sink sk;
@@ -1187,34 +1193,68 @@ void run_multi(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& si
         RunExtras X;
         X.ranges = &ranges[r];
         if (sized) { X.base = &base[r]; X.shared_files = sink.kind == SINK_FILES; }
-        if (parts) X.part_suffix = ".part" + std::to_string(r);
+        std::vector<std::string> suffix;
+        if (parts) {
+            // per job: the job's first device writes <name> itself (no EOF block yet), every other one <name>.part<r>
+            X.no_eof = true;
+            X.job_suffix = &suffix;
+            for (size_t k = 0; k < nj; k++) suffix.push_back(r == first_dev[k] ? std::string() : ".part" + std::to_string(r));
+        }
         run(c->kids[r], use_haps, &Pk, sk, &st[r], X);
     }, true);
 
-    // --- compressed: join the parts in device order, one end-of-file block per file
-    if (parts)
+    // --- compressed: the parts move behind the first device's bytes in device order (their offsets are known now),
+    //     slices of them copied by several threads at once; one end-of-file block per file
+    if (parts) {
+        struct CopyTask { int in_fd, out_fd; uint64_t in_off, out_off, len; };
+        std::vector<CopyTask> tasks;
+        std::vector<int> fds;
+        struct CloseAll { std::vector<int>& f; ~CloseAll() { for (int x : f) ::close(x); } } close_all{fds};
+        const bool eof = Z.dev_z || Z.zmethod == DEFLATE_BGZF;
         for (size_t k = 0; k < nj; k++)
             for (int e = 0; e < n_ends; e++) {
                 const std::string name = file_name(Y.jobs[k], e, true, P);
-                const int fd = ::open(name.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+                const int fd = ::open(name.c_str(), first_dev[k] < N ? O_RDWR : (O_RDWR | O_CREAT | O_TRUNC), 0644);
                 if (fd < 0) throw IoErr("Unable to open file " + name + ".\n");
-                std::string w;
-                for (size_t r = 0; r < N && w.empty(); r++) {
-                    if (ranges[r][k].second <= ranges[r][k].first) continue;
+                fds.push_back(fd);
+                struct stat sb;
+                if (::fstat(fd, &sb) != 0) throw IoErr("Error writing to file " + name + ": " + std::strerror(errno));
+                uint64_t pos = (uint64_t)sb.st_size;
+                for (size_t r = 0; r < N; r++) {
+                    if (ranges[r][k].second <= ranges[r][k].first || r == first_dev[k]) continue;
                     const std::string part = name + ".part" + std::to_string(r);
                     const int in = ::open(part.c_str(), O_RDONLY);
-                    struct stat sb;
-                    if (in < 0 || ::fstat(in, &sb) != 0) { w = "cannot read " + part; if (in >= 0) ::close(in); break; }
-                    w = copy_range(fd, in, (uint64_t)sb.st_size);
-                    ::close(in);
+                    if (in < 0 || ::fstat(in, &sb) != 0) { if (in >= 0) ::close(in); throw IoErr("cannot read " + part); }
+                    fds.push_back(in);
+                    const uint64_t slice = 64ull << 20;
+                    for (uint64_t o = 0; o < (uint64_t)sb.st_size; o += slice)
+                        tasks.push_back(CopyTask{in, fd, o, pos + o, std::min<uint64_t>(slice, (uint64_t)sb.st_size - o)});
+                    pos += (uint64_t)sb.st_size;
                 }
-                if (w.empty() && (Z.dev_z || Z.zmethod == DEFLATE_BGZF)) {
-                    const off_t end = ::lseek(fd, 0, SEEK_END);
-                    w = end < 0 ? std::string(std::strerror(errno)) : pwrite_all(fd, kBgzfEof, sizeof kBgzfEof, (uint64_t)end);
+                if (::ftruncate(fd, (off_t)(pos + (eof ? sizeof kBgzfEof : 0))) != 0)
+                    throw IoErr("Error writing to file " + name + ": " + std::strerror(errno));
+                if (eof) {
+                    const std::string w = pwrite_all(fd, kBgzfEof, sizeof kBgzfEof, pos);
+                    if (!w.empty()) throw IoErr("Error writing to file " + name + ": " + w);
                 }
-                ::close(fd);
-                if (!w.empty()) throw IoErr("Error writing to file " + name + ": " + w);
             }
+        std::atomic<size_t> next{0};
+        std::mutex em;
+        std::string first_err;
+        auto worker = [&]() {
+            for (size_t i = next.fetch_add(1); i < tasks.size(); i = next.fetch_add(1)) {
+                const CopyTask& t = tasks[i];
+                const std::string w = copy_range(t.out_fd, t.out_off, t.in_fd, t.in_off, t.len);
+                if (!w.empty()) { std::lock_guard<std::mutex> l(em); if (first_err.empty()) first_err = w; }
+            }
+        };
+        const size_t nth = std::min<size_t>(std::max<size_t>(tasks.size(), 1), std::min<uint64_t>(std::max<uint64_t>(P->n_threads, 4), 32));
+        std::vector<std::thread> th;
+        for (size_t i = 1; i < nth; i++) th.emplace_back(worker);
+        worker();
+        for (std::thread& t : th) t.join();
+        if (!first_err.empty()) throw IoErr("Error joining the devices' parts: " + first_err);
+    }
 
     jlp_run_stats tot;
     std::memset(&tot, 0, sizeof tot);

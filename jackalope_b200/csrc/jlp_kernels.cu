@@ -847,9 +847,9 @@ k_reads(const __grid_constant__ GenParams p) {
                 __syncwarp();
             }
             // ---- phase A: template base codes into the end's code line, 16 positions per lane from the staged window
-            if (mine && !(flags & (kPlanManyEv | kPlanBarcode)) && 16u * hl < max(ln, S)) {
+            if (mine && !(flags & (kPlanManyEv | kPlanBarcode)))
+            for (uint32_t tb = 16u * hl; tb < max(ln, S); tb += 256u) {                 // one round up to 256 positions
                 const bool reverse = flags & kPlanReverse;
-                const uint32_t tb = 16u * hl;
                 const uint32_t d0 = (pa.x & 15u) + 16u;                               // seg's place in the window: 16 .. 31
                 // forward: seg[tb .. tb+16); reverse: seg[S-1-tb-15 .. S-1-tb] read backwards and complemented
                 // (positions past the read's end hold garbage nobody reads)

@@ -277,3 +277,36 @@ def test_create_genome_on_device(ctx):
         J.create_genome(0, 100, ctx=ctx)
     with pytest.raises(J.JackalopeError):
         J.create_genome(2, 100, pi_tcag=[0, 0, 0, 0], ctx=ctx)
+
+
+def _flat_profile_file(path, L, quals=(2, 20, 30, 38), counts=(10, 100, 1000, 5000)):
+    """An ART-format profile with the same four qualities at every position (cumulative counts)."""
+    cum = np.cumsum(counts)
+    with open(path, "w") as fh:
+        for nt in "ACGT":
+            for pos in range(L):
+                fh.write("%s\t%d\t%s\n%s\t%d\t%s\n" % (nt, pos, "\t".join(map(str, quals)), nt, pos, "\t".join(map(str, cum))))
+
+
+def test_long_reads_custom_profile(ctx, tmp_path):
+    """Read lengths beyond one round of the per-lane work (256 positions per end in phase A, 256 bytes of template
+    window per cp.async round): a custom 300-position profile, paired, with indels and duplicates, byte for byte."""
+    prof = str(tmp_path / "p300.txt")
+    _flat_profile_file(prof, 300)
+    g = J.random_genome(3, 50_000, seed=61)
+    kw = dict(profile1=prof, profile2=prof, frag_mean=700, frag_sd=120, ins_prob1=0.002, del_prob1=0.002, ins_prob2=0.003,
+              del_prob2=0.001, prob_dup=0.1)
+    r1, r2, st = J.illumina(g, "", 6000, 300, True, seed=62, ctx=ctx, sink="memory", **kw)
+    o = oracle_run(g, 6000, 300, True, 62, **kw)
+    assert first_diff(r1, o["r1"]) is None and first_diff(r2, o["r2"]) is None
+    assert all(len(x) == 300 for x in r1.split(b"\n")[1:4 * 50:4])
+
+
+def test_read_length_too_long_for_the_read_kernel_is_reported(ctx, tmp_path):
+    """A read whose record does not fit the shared memory of an SM (several thousand positions): a clear
+    JLP_ERR_UNSUPPORTED instead of a CUDA launch failure (the reference has no such limit)."""
+    prof = str(tmp_path / "p40k.txt")
+    _flat_profile_file(prof, 40_000, quals=(30,), counts=(1,))
+    g = J.random_genome(1, 200_000, seed=63)
+    with pytest.raises(RuntimeError, match="shared memory"):
+        J.illumina(g, "", 10, 40_000, False, seed=64, ctx=ctx, sink="memory", profile1=prof, frag_mean=60_000, frag_sd=100)
