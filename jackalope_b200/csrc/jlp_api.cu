@@ -730,12 +730,13 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
         CK(cudaMemsetAsync(s.totals.p, 0, 4 * sizeof(uint64_t), c->s_compute));
         for (int e = 0; e < n_ends && !sizes_only; e++) {
             s.out[e].ensure(B * max_rec + 64);
-            if (need_host) s.h_out[e].ensure(dev_z ? (size_t)nblk_max * kBgzfSlot : B * max_rec);
+            // compressed bytes of a batch never exceed its FASTQ bytes plus the members' framing (an incompressible block is stored)
+            if (need_host) s.h_out[e].ensure(B * max_rec + (size_t)nblk_max * 64 + 64);
         }
         if (dev_z && !sizes_only)
             for (int e = 0; e < 2; e++) {
                 s.zslots[e].ensure((size_t)nblk_max * kBgzfSlot);
-                s.zdev[e].ensure((size_t)nblk_max * kBgzfSlot);
+                s.zdev[e].ensure(B * max_rec + (size_t)nblk_max * 64 + 64);
                 s.zlen[e].ensure(nblk_max);
                 s.zoff[e].ensure(nblk_max);
             }
@@ -1241,10 +1242,22 @@ void run_multi(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& si
         std::atomic<size_t> next{0};
         std::mutex em;
         std::string first_err;
+        // a slice is copied through mappings of both files where that works (threads writing one file through
+        // write() / copy_file_range queue on its inode lock; page-cache pages filled through a mapping do not), else by copy_range
         auto worker = [&]() {
+            static const uint64_t page = (uint64_t)sysconf(_SC_PAGESIZE);
             for (size_t i = next.fetch_add(1); i < tasks.size(); i = next.fetch_add(1)) {
                 const CopyTask& t = tasks[i];
-                const std::string w = copy_range(t.out_fd, t.out_off, t.in_fd, t.in_off, t.len);
+                std::string w;
+                const uint64_t o0 = t.out_off / page * page, i0 = t.in_off / page * page;
+                void* mo = ::mmap(nullptr, (size_t)(t.out_off + t.len - o0), PROT_READ | PROT_WRITE, MAP_SHARED, t.out_fd, (off_t)o0);
+                void* mi = mo == MAP_FAILED ? MAP_FAILED : ::mmap(nullptr, (size_t)(t.in_off + t.len - i0), PROT_READ, MAP_SHARED, t.in_fd, (off_t)i0);
+                if (mo != MAP_FAILED && mi != MAP_FAILED)
+                    std::memcpy(static_cast<uint8_t*>(mo) + (t.out_off - o0), static_cast<const uint8_t*>(mi) + (t.in_off - i0), t.len);
+                else
+                    w = copy_range(t.out_fd, t.out_off, t.in_fd, t.in_off, t.len);
+                if (mi != MAP_FAILED) ::munmap(mi, (size_t)(t.in_off + t.len - i0));
+                if (mo != MAP_FAILED) ::munmap(mo, (size_t)(t.out_off + t.len - o0));
                 if (!w.empty()) { std::lock_guard<std::mutex> l(em); if (first_err.empty()) first_err = w; }
             }
         };

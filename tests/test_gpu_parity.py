@@ -305,8 +305,15 @@ def test_long_reads_custom_profile(ctx, tmp_path):
 def test_read_length_too_long_for_the_read_kernel_is_reported(ctx, tmp_path):
     """A read whose record does not fit the shared memory of an SM (several thousand positions): a clear
     JLP_ERR_UNSUPPORTED instead of a CUDA launch failure (the reference has no such limit)."""
-    prof = str(tmp_path / "p40k.txt")
-    _flat_profile_file(prof, 40_000, quals=(30,), counts=(1,))
+    prof = str(tmp_path / "p60k.txt")
+    _flat_profile_file(prof, 60_000, quals=(30,), counts=(1,))
     g = J.random_genome(1, 200_000, seed=63)
     with pytest.raises(RuntimeError, match="shared memory"):
-        J.illumina(g, "", 10, 40_000, False, seed=64, ctx=ctx, sink="memory", profile1=prof, frag_mean=60_000, frag_sd=100)
+        J.illumina(g, "", 10, 60_000, False, seed=64, ctx=ctx, sink="memory", profile1=prof, frag_mean=80_000, frag_sd=100)
+    # 20 000 positions still fit (one warp per CTA, tables in global memory) and must be right
+    prof = str(tmp_path / "p20k.txt")
+    _flat_profile_file(prof, 20_000, quals=(20, 35), counts=(1, 9))
+    kw = dict(profile1=prof, frag_mean=30_000, frag_sd=500)
+    r1, _, _ = J.illumina(g, "", 12, 20_000, False, seed=65, ctx=ctx, sink="memory", **kw)
+    o = oracle_run(g, 12, 20_000, False, 65, **kw)
+    assert first_diff(r1, o["r1"]) is None and r1.count(b"\n") == 48

@@ -18,10 +18,7 @@ out = {"n_gpus": n_gpu, "numa_nodes": len(glob.glob("/sys/devices/system/node/no
 
 
 def local_cpus(i):
-    try:
-        bdf = torch.cuda.get_device_properties(i).pci_bus_id if hasattr(torch.cuda.get_device_properties(i), "pci_bus_id") else None
-    except Exception:
-        bdf = None
+    bdf = None
     if bdf is None:
         import pynvml
         pynvml.nvmlInit()

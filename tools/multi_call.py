@@ -67,6 +67,9 @@ try:
     out["files_identical_to_single_device_slices"] = True
     for f in os.listdir(d):
         os.unlink(os.path.join(d, f))
+    J.illumina(g, os.path.join(d, "w"), 2 * (1 << 20) * n_gpus, L, True, seed=1, ctx=m, n_threads=nthr, compress=True, overwrite=True, **kw)   # warm-up: the coder's buffers
+    for f in os.listdir(d):
+        os.unlink(os.path.join(d, f))
     m._genome = None
     t0 = time.perf_counter()
     J.illumina(g, os.path.join(d, "z"), 2 * n_pairs, L, True, seed=5, ctx=m, n_threads=nthr, compress=True, overwrite=True, **kw)
