@@ -630,8 +630,8 @@ __device__ __forceinline__ uint32_t codes4_acc(uint32_t x, bool reverse, uint32_
 #else
 #define JLP_PHASEB_ATTR __forceinline__
 #endif
-template <bool SMEM, uint32_t NE>
-__device__ JLP_PHASEB_ATTR void phase_b(const GenParams& p, uint64_t j, uint32_t lane, uint32_t sq0, uint32_t sq1, uint32_t len0, uint32_t len1,
+template <bool SMEM, uint32_t NE, bool EVEN>
+__device__ __forceinline__ void phase_b_loop(const GenParams& p, uint64_t j, uint32_t lane, uint32_t sq0, uint32_t sq1, uint32_t len0, uint32_t len1,
                                      uint32_t cd, uint32_t codw, uint32_t mA0, uint32_t mA1, uint32_t eA0, uint32_t eA1) {
     const uint32_t nb0 = (len0 + 1u) >> 1, nbt = nb0 + ((len1 + 1u) >> 1);
     // what differs between the two ends enters as base + e * difference: multiply-adds (the FMA pipe has room, the ALU
@@ -646,7 +646,7 @@ __device__ JLP_PHASEB_ATTR void phase_b(const GenParams& p, uint64_t j, uint32_t
         const uint32_t s0 = sq0 + e * d_sq + pos;
         const uint32_t q0 = s0 + ln + 3u;
         const uint32_t meta_a = mA0 + e * d_m, ent_a = eA0 + e * d_e;
-        const bool two = pos + 1u < ln;
+        const bool two = EVEN || pos + 1u < ln;        // EVEN: both reads have an even length, every block holds two bases
         const U4 w = qual_block(p, j, blk, e);
         const uint32_t cc = lds16(cd + e * codw + pos);
         const uint32_t c0 = cc & 0xffu, c1 = two ? cc >> 8 : 0u, pos1 = two ? pos + 1u : pos;
@@ -685,6 +685,13 @@ __device__ JLP_PHASEB_ATTR void phase_b(const GenParams& p, uint64_t j, uint32_t
             sts8(q0 + 1u, qq >> 8);
         }
     }
+}
+
+template <bool SMEM, uint32_t NE>
+__device__ JLP_PHASEB_ATTR void phase_b(const GenParams& p, uint64_t j, uint32_t lane, uint32_t sq0, uint32_t sq1, uint32_t len0, uint32_t len1,
+                                     uint32_t cd, uint32_t codw, uint32_t mA0, uint32_t mA1, uint32_t eA0, uint32_t eA1) {
+    if (((len0 | len1) & 1u) == 0u) phase_b_loop<SMEM, NE, true>(p, j, lane, sq0, sq1, len0, len1, cd, codw, mA0, mA1, eA0, eA1);
+    else phase_b_loop<SMEM, NE, false>(p, j, lane, sq0, sq1, len0, len1, cd, codw, mA0, mA1, eA0, eA1);
 }
 
 // One warp per run of consecutive read pairs: the R1 records of a run are one contiguous span of file 1, its R2
