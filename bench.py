@@ -653,16 +653,24 @@ def main():
                            n_threads=nthr, overwrite=True, **kw)
                 for f in os.listdir(d):
                     os.unlink(os.path.join(d, f))
-                ctx._genome = None
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                J.illumina(genome, os.path.join(d, "r"), 2 * n_l * B, L, True, seed=a.seed, ctx=ctx, batch_pairs=B,
-                           n_threads=nthr, overwrite=True, **kw)
-                t_files = time.perf_counter() - t0
+                # two runs, the second reported: the boxes are VMs whose memory is handed over by the host page by page
+                # on first touch, so the first pass over 11 GB of never-used page cache measures the hypervisor
+                t_runs = []
+                for rep in range(2):
+                    for f in os.listdir(d):
+                        os.unlink(os.path.join(d, f))
+                    ctx._genome = None
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    J.illumina(genome, os.path.join(d, "r"), 2 * n_l * B, L, True, seed=a.seed, ctx=ctx, batch_pairs=B,
+                               n_threads=nthr, overwrite=True, **kw)
+                    t_runs.append(time.perf_counter() - t0)
+                t_files = t_runs[1]
                 sz = os.path.getsize(os.path.join(d, "r_R1.fq")) + os.path.getsize(os.path.join(d, "r_R2.fq"))
-                e2e_files = {"value": n_l * B / t_files, "unit": UNIT, "seconds": t_files, "pairs": n_l * B,
+                e2e_files = {"value": n_l * B / t_files, "unit": UNIT, "seconds": t_files, "first_run_seconds": t_runs[0], "pairs": n_l * B,
                              "writer_threads": nthr, "bytes_written": sz, "GBps": sz / t_files / 1e9,
-                             "note": "illumina(obj, out_prefix, ...) writing <prefix>_R{1,2}.fq on tmpfs; genome H2D inside"}
+                             "note": "illumina(obj, out_prefix, ...) writing <prefix>_R{1,2}.fq on tmpfs; genome H2D inside; "
+                                     "second of two runs (the first touches the VM's memory for the first time)"}
                 for f in os.listdir(d):
                     os.unlink(os.path.join(d, f))
                 # compress = TRUE (the reference's default level 6 -> the device coder)
@@ -696,11 +704,11 @@ def main():
             nthr = min(host_threads(), 32)
             J.pacbio(genome, "", 1 << 13, seed=a.seed, ctx=ctx, sink="device", n_threads=nthr)
             runs = []
-            for rep in range(3):        # three runs, the median reported (the host preparation shares the cores with whatever else runs)
+            for rep in range(5):        # five runs, the median reported (the host preparation shares the cores with whatever else runs)
                 t0 = time.perf_counter()
                 stp = J.pacbio(genome, "", 1 << 16, seed=a.seed + 1 + rep, ctx=ctx, sink="device", n_threads=nthr)
                 runs.append(time.perf_counter() - t0)
-            t_pb = sorted(runs)[1]
+            t_pb = sorted(runs)[len(runs) // 2]
             pacbio = {"reads": stp["pairs"], "bases": stp["bytes_out"][0] / 2, "reads_per_s": stp["pairs"] / t_pb, "wall_s_runs": runs,
                       "kernel_ms": stp["reads_ms"], "kernel_reads_per_s": stp["pairs"] / (stp["reads_ms"] / 1e3),
                       "kernel_fastq_GBps": stp["bytes_out"][0] / (stp["reads_ms"] / 1e3) / 1e9, "host_threads": nthr,

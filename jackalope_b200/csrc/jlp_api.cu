@@ -21,6 +21,7 @@
 #include <mutex>
 #include <thread>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <stdexcept>
@@ -614,6 +615,8 @@ struct RunExtras {
     std::string part_suffix;              // compressed multi-GPU runs: this call writes <name><suffix>, joined by the caller
     bool no_eof = false;                  // ... and the caller appends the BGZF end-of-file block
     const std::vector<std::string>* job_suffix = nullptr;   // [jobs] the same per job (overrides part_suffix)
+    PerJobBytes* zsizes_out = nullptr;    // the compressed bytes per job and end this call produced (device coder)
+    bool dry_files = false;               // generate and compress as for files, deliver nothing (sink NONE): the compressed size pass
 };
 
 void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jlp_run_stats* stats, const RunExtras& X = RunExtras()) {
@@ -622,10 +625,11 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
     const bool matepair = P->matepair != 0;
     if (use_haps) finish_upload(c);
     const uint64_t h2d_before = c->h2d_bytes;
-    const Compression Z = compression_of(P, sink.kind);
+    const Compression Z = compression_of(P, X.dry_files ? SINK_FILES : sink.kind);
     const bool dev_z = Z.dev_z, want_gz = Z.want_gz;
     const int zmethod = Z.zmethod;
     const bool sizes_only = X.sizes_out != nullptr;
+    if (X.zsizes_out) X.zsizes_out->assign(X.ranges ? X.ranges->size() : 0, std::array<uint64_t, 2>{0, 0});
     const double insp[2] = {P->ins_prob1, P->ins_prob2}, delp[2] = {P->del_prob1, P->del_prob2};
     const uint32_t L = (uint32_t)c->tab[0].L;
 
@@ -718,7 +722,8 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
     const uint64_t n_rec_max = B * n_ends;
     const uint32_t nsb_max = (uint32_t)((B + kScanBlock - 1) / kScanBlock);
     const bool need_host = sink.kind != SINK_NONE && !sizes_only;
-    const uint32_t nblk_max = dev_z && !sizes_only ? (uint32_t)((B * max_rec + kBgzfIn - 1) / kBgzfIn) + 1 : 0;
+    const uint32_t nblk_all = (uint32_t)((B * max_rec + kBgzfIn - 1) / kBgzfIn) + 1;
+    const uint32_t nblk_max = dev_z && !sizes_only ? nblk_all : 0;
     for (Slot& s : c->slot) {
         s.plan.ensure(n_rec_max);
         s.rec_len.ensure(n_rec_max);
@@ -731,7 +736,8 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
         for (int e = 0; e < n_ends && !sizes_only; e++) {
             s.out[e].ensure(B * max_rec + 64);
             // compressed bytes of a batch never exceed its FASTQ bytes plus the members' framing (an incompressible block is stored)
-            if (need_host) s.h_out[e].ensure(B * max_rec + (size_t)nblk_max * 64 + 64);
+            // (the same size with and without compression: pinning a gigabyte again for the first compressed call took seconds)
+            if (need_host) s.h_out[e].ensure(B * max_rec + (size_t)nblk_all * 64 + 64);
         }
         if (dev_z && !sizes_only)
             for (int e = 0; e < 2; e++) {
@@ -806,6 +812,7 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
         for (int e = 0; e < n_ends; e++) {
             s.tot[e] = s.h_totals.p[e]; st.bytes_out[e] += s.tot[e];
             s.ztot[e] = dev_z ? s.h_totals.p[2 + e] : 0; st.z_bytes[e] += s.ztot[e];
+            if (X.zsizes_out && job_index < X.zsizes_out->size()) (*X.zsizes_out)[job_index][e] += s.ztot[e];
         }
         st.pairs += s.pairs;
         st.batches++;
@@ -829,22 +836,45 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
                 s.file_end[e] = 0;
                 if (sink.kind == SINK_FILES && zmethod < 0) {
                     // R1 and R2 stay record-aligned: both files receive the same batches in the same order.
-                    // With several writer threads the file's new range is reserved (posix_fallocate: a full file
-                    // system is an error here, not a SIGBUS in a writer thread later) and the slices are copied into
-                    // a mapping of it; with one thread, or when the range cannot be reserved or mapped, plain pwrite.
+                    // With several writer threads the file is extended and the batch's range mapped; ONE task per file
+                    // reserves the range's pages (posix_fallocate: a full file system is an error in that task, not a
+                    // SIGBUS later) and then hands the 8 MiB slices to the pool, which copies them into the mapping.
+                    // Page allocation is what the kernel serialises per file and it costs more than the copy, so it
+                    // must neither sit on the driver thread nor be fought over by all the writers (tools/fill_probe.cpp,
+                    // tools/files_probe.py; tmpfs, 16 threads: reserved by the driver thread 11.1 GB/s, by every writer
+                    // for its own slice 8.5, by page faults in the copies 9.2, this way 13.3).
+                    // With one thread, or when the range cannot be mapped, plain pwrite.
                     bool mapped = P->n_threads > 1 && n > 0;
                     if (mapped) {
-                        if (sink.own_size[e]) mapped = ::posix_fallocate(sink.fd[e], (off_t)sink.pos[e], (off_t)n) == 0;
+                        if (sink.own_size[e]) mapped = ::ftruncate(sink.fd[e], (off_t)(sink.pos[e] + n)) == 0;
                         mapped = mapped && map_range(sink.fd[e], sink.pos[e], n, s.map[e]);
                     }
                     const uint64_t slice = 8ull << 20;
-                    for (uint64_t o = 0; o < n; o += slice) {
+                    if (mapped) {
                         const int fd = sink.fd[e];
-                        const uint8_t* src = s.h_out[e].p + o;
-                        const uint64_t len = std::min(slice, n - o), off = sink.pos[e] + o;
-                        uint8_t* dst = mapped ? s.map[e].at + o : nullptr;
-                        if (mapped) c->writers.submit(&s.writes, [dst, src, len]() { std::memcpy(dst, src, len); return std::string(); });
-                        else c->writers.submit(&s.writes, [fd, src, len, off]() { return pwrite_all(fd, src, len, off); });
+                        const uint8_t* src0 = s.h_out[e].p;
+                        uint8_t* dst0 = s.map[e].at;
+                        const uint64_t off0 = sink.pos[e];
+                        WriterPool* pool = &c->writers;
+                        std::atomic<int>* pend = &s.writes;
+                        c->writers.submit(&s.writes, [fd, src0, dst0, off0, n, slice, pool, pend]() {
+                            const int rc = ::posix_fallocate(fd, (off_t)off0, (off_t)n);
+                            if (rc != 0 && rc != EOPNOTSUPP && rc != EINVAL) return std::string(std::strerror(rc));
+                            for (uint64_t o = 0; o < n; o += slice) {
+                                uint8_t* dst = dst0 + o;
+                                const uint8_t* src = src0 + o;
+                                const uint64_t len = std::min(slice, n - o);
+                                pool->submit(pend, [dst, src, len]() { std::memcpy(dst, src, len); return std::string(); });
+                            }
+                            return std::string();
+                        });
+                    } else {
+                        for (uint64_t o = 0; o < n; o += slice) {
+                            const int fd = sink.fd[e];
+                            const uint8_t* src = s.h_out[e].p + o;
+                            const uint64_t len = std::min(slice, n - o), off = sink.pos[e] + o;
+                            c->writers.submit(&s.writes, [fd, src, len, off]() { return pwrite_all(fd, src, len, off); });
+                        }
                     }
                     sink.pos[e] += n;
                     s.file_end[e] = sink.pos[e];
@@ -1028,8 +1058,11 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
 //   plain FASTQ   a size pass (placement + scan only, a few hundred microseconds per batch) tells every device how
 //                 many bytes it will write per job and file, so the devices write into disjoint ranges of the
 //                 same, pre-sized R1 / R2 files (or of the caller's memory buffers) -- R1 and R2 stay aligned;
-//   compressed    sizes are not known beforehand: device r writes whole BGZF members into <file>.part<r>, the
-//                 parts are joined in device order (copy_file_range) and the EOF block is appended once.
+//   compressed    by the device coder: the devices first generate and compress their pieces without delivering them
+//                 (a dry run: they are some fifty times faster than any sink), which gives every piece's compressed
+//                 size; then the files are pre-sized and every device writes its BGZF members straight to their
+//                 final place.  By zlib on the host (levels 7-9): the job's first device writes the file, device r
+//                 writes <file>.part<r>, the parts are moved in behind it and the EOF block is appended once.
 // Only the haplotype chromosomes a device's piece touches are materialised there (ensure_hap_chrom).
 // Callbacks run on the calling thread only (R is single-threaded): the device threads count progress in an atomic
 // and poll an abort flag; the calling thread polls both while it waits.
@@ -1080,7 +1113,11 @@ void run_multi(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& si
     if (Z.want_gz && Z.dev_z && sink.kind == SINK_MEMORY)
         throw Unsupported("compressed output into memory on a multi-GPU context");
     const bool sized = sink.kind == SINK_MEMORY || (sink.kind == SINK_FILES && !Z.want_gz);   // plain bytes at known offsets
-    const bool parts = sink.kind == SINK_FILES && Z.want_gz;
+    // compressed by the device coder: the sizes come from a dry run (the devices generate and compress everything once
+    // without delivering it -- they are some fifty times faster than any sink), then every device writes its members
+    // straight to their final place; compressed by zlib on the host: part files, joined afterwards
+    const bool zsized = sink.kind == SINK_FILES && Z.want_gz && Z.dev_z;
+    const bool parts = sink.kind == SINK_FILES && Z.want_gz && !Z.dev_z;
 
     // --- the devices' pieces of the pair-index space, per job
     std::vector<Ranges> ranges(N, Ranges(nj));
@@ -1139,6 +1176,16 @@ void run_multi(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& si
         }
     };
 
+    // a shared output file gets its final size at once (no pages yet); a file system that cannot hold everything the
+    // run will write is reported here rather than half-way through
+    uint64_t need_bytes = 0;
+    auto presize = [](int fd, uint64_t size, uint64_t& need) -> int {
+        need += size;
+        struct statvfs vfs;
+        if (::fstatvfs(fd, &vfs) == 0 && (uint64_t)vfs.f_bavail * vfs.f_frsize < need) return ENOSPC;
+        return ::ftruncate(fd, (off_t)size) == 0 ? 0 : errno;
+    };
+
     // --- size pass
     std::vector<PerJobBytes> sizes(N), base(N, PerJobBytes(nj, std::array<uint64_t, 2>{0, 0}));
     std::vector<std::array<uint64_t, 2>> job_total(nj, std::array<uint64_t, 2>{0, 0});
@@ -1165,12 +1212,42 @@ void run_multi(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& si
                     const std::string name = file_name(Y.jobs[k], e, false, P);
                     const int fd = ::open(name.c_str(), O_RDWR | O_CREAT | O_TRUNC, 0644);
                     if (fd < 0) throw IoErr("Unable to open file " + name + ".\n");      // src/io.h:288-290
-                    int rc = job_total[k][e] ? ::posix_fallocate(fd, 0, (off_t)job_total[k][e]) : 0;
-                    if (rc == EOPNOTSUPP || rc == EINVAL) rc = ::ftruncate(fd, (off_t)job_total[k][e]) == 0 ? 0 : errno;
+                    // sized now, pages reserved slice by slice by the devices' writer threads (see deliver() in run())
+                    const int rc = presize(fd, job_total[k][e], need_bytes);
                     ::close(fd);
                     if (rc != 0) throw IoErr("Error writing to file " + name + ": " + std::strerror(rc));
                 }
         if (sink.kind == SINK_MEMORY) { sink.len[0] = mem_off[0]; sink.len[1] = mem_off[1]; }
+    }
+
+    // --- compressed size pass (device coder)
+    std::vector<PerJobBytes> zsizes(N), zcheck(N);
+    if (zsized) {
+        jlp_illumina_params Pdry = Pk;
+        Pdry.progress_cb = nullptr;
+        on_devices([&](size_t r) {
+            Sink none;
+            RunExtras X;
+            X.ranges = &ranges[r]; X.zsizes_out = &zsizes[r]; X.dry_files = true;
+            run(c->kids[r], use_haps, &Pdry, none, &st[r], X);
+        }, true);
+        for (size_t r = 0; r < N; r++) launches += st[r].kernel_launches;
+        for (size_t k = 0; k < nj; k++)
+            for (int e = 0; e < n_ends; e++) {
+                uint64_t o = 0;
+                for (size_t r = 0; r < N; r++) { base[r][k][e] = o; o += zsizes[r][k][e]; }
+                job_total[k][e] = o;
+                const std::string name = file_name(Y.jobs[k], e, true, P);
+                const int fd = ::open(name.c_str(), O_RDWR | O_CREAT | O_TRUNC, 0644);
+                if (fd < 0) throw IoErr("Unable to open file " + name + ".\n");      // src/io.h:288-290
+                const uint64_t size = o + sizeof kBgzfEof;                            // bgzf_close: one empty block ends the file
+                const int rc = presize(fd, size, need_bytes);
+                std::string w;
+                if (rc == 0) w = pwrite_all(fd, kBgzfEof, sizeof kBgzfEof, o);
+                ::close(fd);
+                if (rc != 0) throw IoErr("Error writing to file " + name + ": " + std::strerror(rc));
+                if (!w.empty()) throw IoErr("Error writing to file " + name + ": " + w);
+            }
     }
 
     // --- the run proper
@@ -1194,6 +1271,7 @@ void run_multi(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& si
         RunExtras X;
         X.ranges = &ranges[r];
         if (sized) { X.base = &base[r]; X.shared_files = sink.kind == SINK_FILES; }
+        if (zsized) { X.base = &base[r]; X.shared_files = true; X.zsizes_out = &zcheck[r]; }
         std::vector<std::string> suffix;
         if (parts) {
             // per job: the job's first device writes <name> itself (no EOF block yet), every other one <name>.part<r>
@@ -1203,6 +1281,10 @@ void run_multi(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& si
         }
         run(c->kids[r], use_haps, &Pk, sk, &st[r], X);
     }, true);
+
+    if (zsized)         // the coder is deterministic; a difference between the two passes would have put members in the wrong place
+        for (size_t r = 0; r < N; r++)
+            if (zcheck[r] != zsizes[r]) throw std::runtime_error("internal: compressed sizes differ between the size pass and the run");
 
     // --- compressed: the parts move behind the first device's bytes in device order (their offsets are known now),
     //     slices of them copied by several threads at once; one end-of-file block per file
@@ -1881,11 +1963,19 @@ void run_pacbio(jlp_ctx* c, bool use_haps, const jlp_pacbio_params* P, int sink_
             Prepared prep[2];
             std::thread prep_thread;
             struct JoinPrep { std::thread& t; ~JoinPrep() { if (t.joinable()) t.join(); } } join_prep{prep_thread};
+            // JLP_TRACE=1: where the host side of the call spends its time (stderr, one line per job)
+            const bool trace = std::getenv("JLP_TRACE") != nullptr;
+            double t_first = 0, t_join = 0, t_alloc = 0, t_sync = 0;
+            auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+            const double t_job = now();
             if (s_lo < s_hi) prepare(s_lo, (uint32_t)std::min<uint64_t>(B, s_hi - s_lo), prep[0]);
+            t_first = now() - t_job;
             uint64_t bk = 0;
             for (uint64_t b0 = s_lo; b0 < s_hi; b0 += B, bk++) {
                 const uint32_t n = (uint32_t)std::min<uint64_t>(B, s_hi - b0);
+                double t0 = now();
                 if (prep_thread.joinable()) prep_thread.join();
+                t_join += now() - t0;
                 Prepared& cur = prep[bk & 1];
                 if (!cur.err.empty()) throw ArgErr(cur.err);
                 if (P->abort_cb && P->abort_cb(P->cb_user)) throw Aborted();      // Progress::check_abort, src/hts.h:396-399
@@ -1897,11 +1987,13 @@ void run_pacbio(jlp_ctx* c, bool use_haps, const jlp_pacbio_params* P, int sink_
                 }
                 std::vector<PbRead>& plan = cur.plan;
                 const uint64_t bound = cur.bound;
+                t0 = now();
                 d_reads.ensure(n);
                 d_rec_len.ensure(n); d_rec_local.ensure(n);
                 const uint32_t nsb = (n + kScanBlock - 1) / kScanBlock;
                 d_block_tot.ensure(nsb); d_block_base.ensure(nsb);
                 if (bound + 64 > d_out.n) d_out.ensure(bound + bound / 4 + 64);       // batches differ in size: grow with slack
+                t_alloc += now() - t0;
                 CK(cudaMemcpyAsync(d_reads.p, plan.data(), n * sizeof(PbRead), cudaMemcpyHostToDevice, c->s_compute));
                 st.h2d_bytes += n * sizeof(PbRead);
                 CK(cudaEventRecord(ev[0], c->s_compute));
@@ -1923,7 +2015,9 @@ void run_pacbio(jlp_ctx* c, bool use_haps, const jlp_pacbio_params* P, int sink_
                 CK(cudaEventRecord(ev[2], c->s_compute));
                 uint64_t tot[4];
                 CK(cudaMemcpyAsync(tot, d_totals.p, sizeof tot, cudaMemcpyDeviceToHost, c->s_compute));
+                t0 = now();
                 CK(cudaStreamSynchronize(c->s_compute));
+                t_sync += now() - t0;
                 if (tot[0] > bound) throw std::runtime_error("internal: PacBio batch larger than its bound");
                 float ms = 0;
                 CK(cudaEventElapsedTime(&ms, ev[0], ev[1])); st.reads_ms += ms; st.device_ms += ms;
@@ -1974,6 +2068,10 @@ void run_pacbio(jlp_ctx* c, bool use_haps, const jlp_pacbio_params* P, int sink_
             }
             if (prep_thread.joinable()) prep_thread.join();
             settle(0); settle(1);
+            if (trace)
+                std::fprintf(stderr, "[jlp trace] pacbio job %llu reads: %.4f s (first prepare %.4f, waiting for later ones %.4f, "
+                             "device allocations %.4f, waiting for the device %.4f)\n", (unsigned long long)(s_hi - s_lo), now() - t_job,
+                             t_first, t_join, t_alloc, t_sync);
             if (fd >= 0 && (dev_z || zmethod == DEFLATE_BGZF)) {
                 const std::string w = pwrite_all(fd, kBgzfEof, sizeof kBgzfEof, fpos);
                 if (!w.empty()) throw IoErr("Error writing to file " + fname + ": " + w);

@@ -1,6 +1,6 @@
 """One call, several GPUs (jlp_ctx_create_multi): the run is cut into one contiguous piece per device, every device
-writes its piece into the SAME ordered files -- plain FASTQ at offsets known from a size pass, compressed output as
-per-device parts joined in device order -- and the result must be the single-device run byte for byte
+writes its piece into the SAME ordered files -- plain FASTQ at offsets known from a size pass, device-compressed output at
+offsets known from a dry run of the coder, host-compressed output as per-device parts joined in device order -- and the result must be the single-device run byte for byte
 (/root/reference/src/hts.h:334-353 split over threads, :401-416 one set of files, :512-552 sep_files).
 On a one-GPU host the devices of the multi-GPU context are device 0 listed several times (the pieces then share the
 GPU: same code path); with more GPUs visible the same tests also run over all of them."""
@@ -51,16 +51,17 @@ def test_reference_run_one_file_set_from_several_devices(ctx, tmp_path, devices)
         # device-only: every pair generated exactly once
         st = J.illumina(g, "", n_reads, 150, True, seed=5, ctx=m, sink="device", **kw)
         assert st["pairs"] == n_reads // 2 and st["bytes_out"] == [len(o["r1"]), len(o["r2"])]
-        # compressed: BGZF members in per-device parts, joined in device order, one EOF block, no parts left behind
+        # compressed on the device: sizes from a dry run, every device writes its BGZF members to their final place; one EOF block
         J.illumina(g, many, n_reads, 150, True, seed=5, ctx=m, batch_pairs=3000, compress=True, n_threads=2, **kw)
         for r in (1, 2):
             z = read("%s_R%d.fq.gz" % (many, r))
             assert z[-28:-24] == b"\x1f\x8b\x08\x04" and z.count(b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00\x1b\x00\x03\x00") == 1
             assert gzip.decompress(z) == (o["r1"] if r == 1 else o["r2"])
         assert not [f for f in os.listdir(tmp_path) if ".part" in f]
-        # zlib on the writer threads (levels 7-9) goes through the same parts
+        # zlib on the writer threads (levels 7-9): per-device parts, joined in device order, no parts left behind
         J.illumina(g, many + "9", n_reads, 150, True, seed=5, ctx=m, batch_pairs=3000, compress=9, n_threads=2, **kw)
         assert gzip.decompress(read(many + "9_R2.fq.gz")) == o["r2"]
+        assert not [f for f in os.listdir(tmp_path) if ".part" in f]
         # the stream sink has no order over several devices
         with pytest.raises(RuntimeError, match="multi-GPU"):
             J.illumina(g, "", n_reads, 150, True, seed=5, ctx=m, sink=lambda *a: None, **kw)
