@@ -7,14 +7,14 @@
 //                  FASTQ record length (chrom_indels_frag / sample_indels /
 //                  adjust_chrom_spaces, src/hts_illumina.cpp:116-265)
 //   k_scan_*       exclusive scan of FASTQ record lengths -> output offsets
-//   k_reads        one warp per pair: template gather, ART quality/error model and FASTQ
-//                  record assembly in shared memory, 128-bit stores to the final offset
+//   k_reads        one warp per run of consecutive pairs: template gather, ART quality/error model, ID line and
+//                  FASTQ record assembly in shared memory at file alignment, 128-bit stores
 //                  (append_pools / fill_read_qual / fill_fq_lines, src/hts_illumina.cpp:285-482,
 //                  src/hts_illumina.h:202-259)
 //
 // None of this is a dense contraction, so no tensor-core path exists here; the
 // kernels are integer/byte work bounded by HBM traffic and integer issue rate
-// (DESIGN.md section 6).
+// (DESIGN.md section 5).
 #include "jlp_kernels.cuh"
 #include "jlp_draws.h"
 
@@ -247,13 +247,24 @@ k_place(const __grid_constant__ GenParams p) {
     uint32_t frag_pos = 0, length_now = 0, n_ev = 0, ev0 = 0xffffffffu, ev1 = 0xffffffffu;
     const uint32_t frag_cap = frag_len > 0xffffffffull ? 0xffffffffu : (uint32_t)frag_len;
     const uint32_t hA = p.end[e].hA;
+    // all eight fields of a block above the gate, tested two at a time: with hA + 1 <= 0x8000 a field f is above it iff
+    // f has its top bit set or (f | 0x8000) - (hA + 1) keeps it (no borrow crosses the halves: each is >= 0x8000 > hA)
+    const bool swar = hA < 0x8000u;
+    const uint32_t gate2 = (hA + 1u) * 0x00010001u;
     while (length_now < L && frag_pos < frag_cap) {
         // 8 template positions per Philox block, 16 bits each: a field above the gate is a plain base.
         // (An 8-bit gate would halve the Philox work but make a candidate -- and with it the slow path of
         // the whole warp -- 256 times more likely; measured: 0.46 ms instead of 0.25 ms.)
         U4 w = draw_block(p.seed, j, frag_pos >> 3, PL_INDEL, e);
-        bool plain = ((w.w0 & 0xffffu) > hA) & ((w.w0 >> 16) > hA) & ((w.w1 & 0xffffu) > hA) & ((w.w1 >> 16) > hA) &
-                     ((w.w2 & 0xffffu) > hA) & ((w.w2 >> 16) > hA) & ((w.w3 & 0xffffu) > hA) & ((w.w3 >> 16) > hA);
+        bool plain;
+        if (swar) {
+            const uint32_t a0 = w.w0 | ((w.w0 | 0x80008000u) - gate2), a1 = w.w1 | ((w.w1 | 0x80008000u) - gate2);
+            const uint32_t a2 = w.w2 | ((w.w2 | 0x80008000u) - gate2), a3 = w.w3 | ((w.w3 | 0x80008000u) - gate2);
+            plain = (a0 & a1 & a2 & a3 & 0x80008000u) == 0x80008000u;
+        } else {
+            plain = ((w.w0 & 0xffffu) > hA) & ((w.w0 >> 16) > hA) & ((w.w1 & 0xffffu) > hA) & ((w.w1 >> 16) > hA) &
+                    ((w.w2 & 0xffffu) > hA) & ((w.w2 >> 16) > hA) & ((w.w3 & 0xffffu) > hA) & ((w.w3 >> 16) > hA);
+        }
         if (plain && (frag_pos & 7u) == 0 && length_now + 8 <= L && frag_pos + 8 <= frag_cap) {
             length_now += 8; frag_pos += 8;
             continue;
