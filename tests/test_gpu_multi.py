@@ -97,6 +97,17 @@ def test_haplotypes_sep_files_from_several_devices(ctx, tmp_path, devices):
         assert gzip.decompress(read(many + "p_R1.fq.gz")) == o2["r1"] and gzip.decompress(read(many + "p_R2.fq.gz")) == o2["r2"]
         r1, r2, _ = J.illumina(haps, "", n_reads, 100, True, seed=6, ctx=m, sink="memory", **kw)
         assert r1 == o["r1"] and r2 == o["r2"]
+        # one compressed file pair per haplotype from several devices: the dry run sizes every job's files (a job may
+        # have several writers, a device several jobs); a haplotype without reads gets a file with the EOF block only
+        J.illumina(haps, many + "z", n_reads, 100, True, seed=6, ctx=m, batch_pairs=2500, compress=True, n_threads=3, **kw)
+        eof = b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00\x1b\x00\x03\x00\x00\x00\x00\x00\x00\x00\x00\x00"
+        for h in haps.hap_names:
+            for r in (1, 2):
+                z = read("%sz_%s_R%d.fq.gz" % (many, h, r))
+                assert z.endswith(eof) and z.count(eof[:20]) == 1, (h, r)
+                assert gzip.decompress(z) == read("%s_%s_R%d.fq" % (one, h, r)), (h, r)
+        assert read("%sz_hap3_R2.fq.gz" % many) == eof
+        assert not [f for f in os.listdir(tmp_path) if ".part" in f]
     finally:
         m.close()
 
