@@ -343,7 +343,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ U4 qual_block(const GenParams& p, uint64_t j, uint32_t blk, uint32_t e) {
-    return philox4x32_rk<kQualRounds>((uint32_t)j, (uint32_t)(j >> 32), blk, PL_QUAL | (e << 8), p.rk);
+    return philox4x32_rk<kQualRounds>((uint32_t)j, (uint32_t)(j >> 32), blk, PL_QUAL + e * 256u, p.rk);
 }
 
 // One base evaluated exactly (full 64-bit draws wherever the 16 high bits do not decide);
@@ -644,55 +644,75 @@ __device__ __forceinline__ uint32_t codes4_acc(uint32_t x, bool reverse, uint32_
 template <bool SMEM, uint32_t NE, bool EVEN>
 __device__ __forceinline__ void phase_b_loop(const GenParams& p, uint64_t j, uint32_t lane, uint32_t sq0, uint32_t sq1, uint32_t len0, uint32_t len1,
                                      uint32_t cd, uint32_t codw, uint32_t mA0, uint32_t mA1, uint32_t eA0, uint32_t eA1) {
-    const uint32_t nb0 = (len0 + 1u) >> 1, nbt = nb0 + ((len1 + 1u) >> 1);
-    // what differs between the two ends enters as base + e * difference: multiply-adds (the FMA pipe has room, the ALU
-    // pipe, which selects would use, is the kernel's bound)
-    const uint32_t d_len = len1 - len0, d_sq = sq1 - sq0, d_m = mA1 - mA0, d_e = eA1 - eA0;
+    // One half-warp per end (single-end: the whole warp): which end a lane works on never changes, so everything that
+    // depends on the end is set up once per pair, outside the loop.  Same number of passes as one index space over both
+    // ends (ceil(n / 16) = ceil(2n / 32) for equally long reads).
+    const uint32_t e = NE == 2 ? lane >> 4 : 0u;
+    const uint32_t W = NE == 2 ? 16u : 32u;
+    const uint32_t ln = e ? len1 : len0;
+    const uint32_t nb = (ln + 1u) >> 1;
+    const uint32_t sq = e ? sq1 : sq0, meta_a = e ? mA1 : mA0, ent_a = e ? eA1 : eA0, ca = cd + e * codw;
 #pragma unroll 1
-    for (uint32_t q = lane; q < nbt; q += 32) {
-        const uint32_t e = NE == 2 && q >= nb0 ? 1u : 0u;
-        const uint32_t blk = q - e * nb0;
+    for (uint32_t blk = NE == 2 ? lane & 15u : lane; blk < nb; blk += W) {
         const uint32_t pos = 2u * blk;
-        const uint32_t ln = len0 + e * d_len;
-        const uint32_t s0 = sq0 + e * d_sq + pos;
+        const uint32_t s0 = sq + pos;
         const uint32_t q0 = s0 + ln + 3u;
-        const uint32_t meta_a = mA0 + e * d_m, ent_a = eA0 + e * d_e;
         const bool two = EVEN || pos + 1u < ln;        // EVEN: both reads have an even length, every block holds two bases
         const U4 w = qual_block(p, j, blk, e);
-        const uint32_t cc = lds16(cd + e * codw + pos);
-        const uint32_t c0 = cc & 0xffu, c1 = two ? cc >> 8 : 0u, pos1 = two ? pos + 1u : pos;
+        const uint32_t cl = lds16(ca + pos);
+        const uint32_t cc = two ? cl : cl & 0xffu;          // the block's two base codes, one per byte
+        const uint32_t c0 = cc & 0xffu, c1 = cc >> 8, pos1 = two ? pos + 1u : pos;
         const uint32_t ct0 = min(c0, 3u), ct1 = min(c1, 3u);
         uint32_t x0, x1;
         bool self0, self1, rare0, rare1, mis0, mis1;
         base_fast<SMEM>(p, meta_a, ent_a, e, pos, ct0, w.w0, w.w1, x0, self0, rare0, mis0);
         base_fast<SMEM>(p, meta_a, ent_a, e, pos1, ct1, w.w2, w.w3, x1, self1, rare1, mis1);
-        // both quality characters with one byte permute, both letters with another
+        // both quality characters with one byte permute; both letters with another whose selector is the pair of codes
+        // itself (nibbles c0, 0, c1, 0: T C A G, and N for code 4): letters in bytes 0 and 2
         uint32_t qq = __byte_perm(x0, x1, (self0 ? 1u : 0u) | (self1 ? 0x50u : 0x40u));
-        uint32_t k0 = ct0, k1 = ct1;
+        uint32_t asc = __byte_perm(0x47414354u, 0x4e4e4e4eu, cc);
         if (mis0 | mis1) {
             // mm_nucleos[nt][(uint64)(u * 3)] (src/hts.h:46): the si-th code other than the base's, si from the 8 high
             // bits of X_sub unless the low bits could change it (3 of 256 values: the exact path decides)
-            const uint32_t p0 = (w.w0 & 0xffu) * 3u, p1 = (w.w2 & 0xffu) * 3u;
-            if (mis0) { if ((p0 & 0xffu) >= 253u) rare0 = true; else { const uint32_t si = p0 >> 8; k0 = si + (si >= ct0 ? 1u : 0u); } }
-            if (mis1) { if ((p1 & 0xffu) >= 253u) rare1 = true; else { const uint32_t si = p1 >> 8; k1 = si + (si >= ct1 ? 1u : 0u); } }
+            if (mis0 && !rare0 && c0 <= 3u) {
+                const uint32_t p0 = (w.w0 & 0xffu) * 3u;
+                if ((p0 & 0xffu) >= 253u) {
+                    const uint32_t r = base_rare<SMEM>(p, meta_a, ent_a, e, j, pos, c0, w.w0, w.w1);
+                    asc = (asc & 0xff0000u) | (r & 0xffu);
+                    qq = (qq & 0xff00u) | (r >> 8);
+                } else {
+                    const uint32_t si = p0 >> 8, k0 = si + (si >= ct0 ? 1u : 0u);
+                    asc = (asc & 0xff0000u) | (__byte_perm(0x47414354u, 0u, k0) & 0xffu);
+                }
+            }
+            if (mis1 && !rare1 && c1 <= 3u && two) {
+                const uint32_t p1 = (w.w2 & 0xffu) * 3u;
+                if ((p1 & 0xffu) >= 253u) {
+                    const uint32_t r = base_rare<SMEM>(p, meta_a, ent_a, e, j, pos1, c1, w.w2, w.w3);
+                    asc = (asc & 0xffu) | ((r & 0xffu) << 16);
+                    qq = (qq & 0xffu) | (r & 0xff00u);
+                } else {
+                    const uint32_t si = p1 >> 8, k1 = si + (si >= ct1 ? 1u : 0u);
+                    asc = (asc & 0xffu) | ((__byte_perm(0x47414354u, 0u, k1) & 0xffu) << 16);
+                }
+            }
         }
-        uint32_t asc = __byte_perm(0x47414354u, 0u, k0 | (k1 << 4));
-        if (rare0 || rare1 || (c0 | c1) > 3u) {
+        if (rare0 || rare1 || (cc & 0x0404u) != 0u) {          // undecided draws; a base that is not T, C, A or G (code 4)
             if (rare0 || c0 > 3u) {
                 uint32_t r = base_rare<SMEM>(p, meta_a, ent_a, e, j, pos, c0, w.w0, w.w1);
-                asc = (asc & 0xff00u) | (r & 0xffu);
+                asc = (asc & 0xff0000u) | (r & 0xffu);
                 qq = (qq & 0xff00u) | (r >> 8);
             }
             if (two && (rare1 || c1 > 3u)) {
                 uint32_t r = base_rare<SMEM>(p, meta_a, ent_a, e, j, pos1, c1, w.w2, w.w3);
-                asc = (asc & 0xffu) | ((r & 0xffu) << 8);
+                asc = (asc & 0xffu) | ((r & 0xffu) << 16);
                 qq = (qq & 0xffu) | (r & 0xff00u);
             }
         }
         sts8(s0, asc);
         sts8(q0, qq);
         if (two) {
-            sts8(s0 + 1u, asc >> 8);
+            sts8(s0 + 1u, asc >> 16);
             sts8(q0 + 1u, qq >> 8);
         }
     }
