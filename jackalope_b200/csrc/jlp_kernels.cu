@@ -522,7 +522,7 @@ __device__ __noinline__ void gather_barcode(uint32_t w, const uint8_t* seg, cons
 
 #ifndef JLP_READS_THREADS
 // 20 warps, one CTA per SM sharing one copy of the tables: 96 registers per thread, nothing spilled.  Measured
-// (DESIGN.md section 5): 896 threads (72 registers, spills) 1.56 ms, 768 1.54, 640 1.46, 512 1.50.
+// (before the last changes to phase B): 896 threads (72 registers, spills) 1.56 ms, 768 1.54, 640 1.46, 512 1.50.
 #define JLP_READS_THREADS 640
 #define JLP_READS_CTAS 1
 #endif
