@@ -279,8 +279,16 @@ struct jlp_ctx {
     // scratch of the haplotype materialisation (mutation records of one chromosome)
     HapArena hap_mem;
     // PacBio driver: FASTQ of a batch on the device, its compressed form, and the two pinned host buffers batches alternate between
-    DevBuf<uint8_t> pb_out, pb_zslots, pb_zout;
+    DevBuf<uint8_t> pb_out, pb_zslots, pb_zout, pb_strpool;
+    DevBuf<PbRead> pb_reads;
+    DevBuf<GroupDev> pb_groups;
+    DevBuf<uint32_t> pb_rec_len, pb_rec_local, pb_zlen;
+    DevBuf<uint64_t> pb_block_tot, pb_block_base, pb_totals, pb_zoff;
     PinBuf<uint8_t> pb_h_buf[2];
+    // PacBioPassSampler's outlier thresholds (one chi-squared quantile per read length up to chi2_params_n[2]) of the last call
+    std::shared_ptr<std::atomic<double>[]> pb_qcache;
+    double pb_qcache_key[3] = {0, 0, 0};
+    size_t pb_qcache_n = 0;
     DevBuf<uint64_t> m_old, m_new, m_off;
     DevBuf<int64_t> m_sm;
     DevBuf<uint8_t> m_pool;
@@ -1840,6 +1848,14 @@ void run_pacbio(jlp_ctx* c, bool use_haps, const jlp_pacbio_params* P, int sink_
                 jlp_run_stats* stats) {
     PbModel model;
     pb_model_from(P, model);
+    // the quantiles computed by earlier calls with the same pass-sampler parameters are kept (each costs a bisection on
+    // the incomplete gamma function; a fresh table made the first thousands of reads of every call slow)
+    if (c->pb_qcache && c->pb_qcache_n == model.qchisq_n && std::equal(model.chi2_n, model.chi2_n + 3, c->pb_qcache_key))
+        model.qchisq_cache = c->pb_qcache;
+    else {
+        c->pb_qcache = model.qchisq_cache; c->pb_qcache_n = model.qchisq_n;
+        std::copy(model.chi2_n, model.chi2_n + 3, c->pb_qcache_key);
+    }
     if (!(P->prob_dup >= 0 && P->prob_dup <= 1)) throw ArgErr("prob_dup must be in [0,1]");
     if (P->read_pool_size < 1) throw ArgErr("read_pool_size must be >= 1");
     const Thr t_dup = thr_double_lt(P->prob_dup);
@@ -1856,14 +1872,13 @@ void run_pacbio(jlp_ctx* c, bool use_haps, const jlp_pacbio_params* P, int sink_
                        (P->comp_engine == JLP_COMP_DEVICE || (P->comp_engine == JLP_COMP_AUTO && P->compress <= 6));
     const int zmethod = P->compress <= 0 || dev_z || sink_kind != SINK_FILES ? -1
                         : (P->n_threads > 1 || std::string(P->comp_method) == "bgzip") ? DEFLATE_BGZF : DEFLATE_GZIP;
-    DevBuf<GroupDev> d_groups;
-    DevBuf<uint8_t> d_strpool;
-    // the big buffers belong to the context: pinning (and unpinning) a gigabyte of host memory on every call cost
-    // more than generating the reads
-    DevBuf<uint8_t>&d_out = c->pb_out, &d_zslots = c->pb_zslots, &d_zout = c->pb_zout;
-    DevBuf<PbRead> d_reads;
-    DevBuf<uint32_t> d_rec_len, d_rec_local, d_zlen;
-    DevBuf<uint64_t> d_block_tot, d_block_base, d_totals, d_zoff;
+    // every buffer belongs to the context: pinning (and unpinning) a gigabyte of host memory on every call cost more than
+    // generating the reads, and a dozen device allocations and frees per call several milliseconds
+    DevBuf<GroupDev>& d_groups = c->pb_groups;
+    DevBuf<uint8_t>&d_strpool = c->pb_strpool, &d_out = c->pb_out, &d_zslots = c->pb_zslots, &d_zout = c->pb_zout;
+    DevBuf<PbRead>& d_reads = c->pb_reads;
+    DevBuf<uint32_t>&d_rec_len = c->pb_rec_len, &d_rec_local = c->pb_rec_local, &d_zlen = c->pb_zlen;
+    DevBuf<uint64_t>&d_block_tot = c->pb_block_tot, &d_block_base = c->pb_block_base, &d_totals = c->pb_totals, &d_zoff = c->pb_zoff;
     // two host buffers: the writer threads copy batch k into the file while batch k + 1 is prepared, generated and copied
     PinBuf<uint8_t>* h_buf = c->pb_h_buf;
     Mapping h_map[2];
@@ -1968,21 +1983,39 @@ void run_pacbio(jlp_ctx* c, bool use_haps, const jlp_pacbio_params* P, int sink_
             double t_first = 0, t_join = 0, t_alloc = 0, t_sync = 0;
             auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
             const double t_job = now();
-            if (s_lo < s_hi) prepare(s_lo, (uint32_t)std::min<uint64_t>(B, s_hi - s_lo), prep[0]);
+            // with the default batch size the first batches are small (8192 reads, doubling): the first preparation is the
+            // one nothing overlaps, so the device should not wait for a full batch of it
+            auto batch_size = [&](uint64_t k) -> uint64_t {
+                if (P->batch_reads) return B;
+                uint64_t b = std::min<uint64_t>(B, 8192ull << std::min<uint64_t>(k, 8));
+                if (dups) b = std::max<uint64_t>(P->read_pool_size, b / P->read_pool_size * P->read_pool_size);
+                return b;
+            };
+            {   // the per-read device arrays once, for the largest batch of the job (growing them batch by batch would
+                // free and allocate -- and synchronise -- at every step of the ramp)
+                const uint64_t n_max = std::min<uint64_t>(B, s_hi - s_lo);
+                d_reads.ensure(n_max); d_rec_len.ensure(n_max); d_rec_local.ensure(n_max);
+                const uint64_t nsb_max = (n_max + kScanBlock - 1) / kScanBlock;
+                d_block_tot.ensure(nsb_max); d_block_base.ensure(nsb_max);
+            }
+            uint64_t n_next = std::min<uint64_t>(batch_size(0), s_hi - s_lo), b0_next = s_lo;
+            if (s_lo < s_hi) prepare(s_lo, (uint32_t)n_next, prep[0]);
             t_first = now() - t_job;
             uint64_t bk = 0;
-            for (uint64_t b0 = s_lo; b0 < s_hi; b0 += B, bk++) {
-                const uint32_t n = (uint32_t)std::min<uint64_t>(B, s_hi - b0);
+            for (uint64_t b0 = s_lo; b0 < s_hi; b0 = b0_next, bk++) {
+                const uint32_t n = (uint32_t)n_next;
                 double t0 = now();
                 if (prep_thread.joinable()) prep_thread.join();
                 t_join += now() - t0;
                 Prepared& cur = prep[bk & 1];
                 if (!cur.err.empty()) throw ArgErr(cur.err);
                 if (P->abort_cb && P->abort_cb(P->cb_user)) throw Aborted();      // Progress::check_abort, src/hts.h:396-399
-                if (b0 + B < s_hi) {
+                b0_next = b0 + n;
+                if (b0_next < s_hi) {
                     Prepared* nxt = &prep[(bk + 1) & 1];
-                    const uint64_t nb0 = b0 + B;
-                    const uint32_t nn = (uint32_t)std::min<uint64_t>(B, s_hi - nb0);
+                    const uint64_t nb0 = b0_next;
+                    n_next = std::min<uint64_t>(batch_size(bk + 1), s_hi - nb0);
+                    const uint32_t nn = (uint32_t)n_next;
                     prep_thread = std::thread([&prepare, nb0, nn, nxt]() { prepare(nb0, nn, *nxt); });
                 }
                 std::vector<PbRead>& plan = cur.plan;
@@ -1992,7 +2025,11 @@ void run_pacbio(jlp_ctx* c, bool use_haps, const jlp_pacbio_params* P, int sink_
                 d_rec_len.ensure(n); d_rec_local.ensure(n);
                 const uint32_t nsb = (n + kScanBlock - 1) / kScanBlock;
                 d_block_tot.ensure(nsb); d_block_base.ensure(nsb);
-                if (bound + 64 > d_out.n) d_out.ensure(bound + bound / 4 + 64);       // batches differ in size: grow with slack
+                if (bound + 64 > d_out.n) {      // batches differ in size: grow with slack, and at once to what a full batch will need
+                    const uint64_t full = n ? bound / n * std::min<uint64_t>(B, s_hi - s_lo) : bound;
+                    const uint64_t want = std::max(bound, full);
+                    d_out.ensure(want + want / 4 + 64);
+                }
                 t_alloc += now() - t0;
                 CK(cudaMemcpyAsync(d_reads.p, plan.data(), n * sizeof(PbRead), cudaMemcpyHostToDevice, c->s_compute));
                 st.h2d_bytes += n * sizeof(PbRead);

@@ -27,20 +27,43 @@ long double runif_01(uint64_t x) { return ((long double)x + 1) / ((long double)U
 
 // Standard normal distribution function and quantile.  The reference calls R::pnorm5 / R::qnorm5 here
 // (src/hts_pacbio.h:349-352); these agree with Rmath to a few ulp: the lower tail through erfc, the quantile by
-// Newton steps on it from Abramowitz and Stegun 26.2.23, the upper half by symmetry.
+// Wichura's AS 241 (the algorithm R's qnorm5 uses), the same expressions as oracle/rmath_standin.h.
 double pnorm(double x) { return 0.5 * std::erfc(-x * 0.70710678118654752440); }
 double qnorm(double p) {
+    /* Wichura (1988), Algorithm AS 241, routine PPND16 -- the algorithm R's qnorm5 itself uses: rational approximations
+     * in q = p - 1/2 (central part) and in r = std::sqrt(-std::log(min(p, 1 - p))) (the tails), about 16 digits */
     if (!(p > 0.0)) return -INFINITY;
     if (!(p < 1.0)) return INFINITY;
-    if (p > 0.5) return -qnorm(1.0 - p);
-    const double t = std::sqrt(-2.0 * std::log(p));
-    double x = -(t - (2.515517 + 0.802853 * t + 0.010328 * t * t) / (1.0 + 1.432788 * t + 0.189269 * t * t + 0.001308 * t * t * t));
-    for (int i = 0; i < 5; i++) {
-        const double d = 0.39894228040143267794 * std::exp(-0.5 * x * x);
-        if (!(d > 1e-300)) break;
-        x -= (pnorm(x) - p) / d;
+    const double q = p - 0.5;
+    if (std::fabs(q) <= 0.425) {
+        const double r = 0.180625 - q * q;
+        return q * (((((((2.5090809287301226727e+3 * r + 3.3430575583588128105e+4) * r + 6.7265770927008700853e+4) * r +
+                        4.5921953931549871457e+4) * r + 1.3731693765509461125e+4) * r + 1.9715909503065514427e+3) * r +
+                      1.3314166789178437745e+2) * r + 3.3871328727963666080) /
+               (((((((5.2264952788528545610e+3 * r + 2.8729085735721942674e+4) * r + 3.9307895800092710610e+4) * r +
+                    2.1213794301586595867e+4) * r + 5.3941960214247511077e+3) * r + 6.8718700749205790830e+2) * r +
+                  4.2313330701600911252e+1) * r + 1.0);
     }
-    return x;
+    double r = std::sqrt(-std::log(q < 0 ? p : 1.0 - p));
+    double v;
+    if (r <= 5.0) {
+        r -= 1.6;
+        v = (((((((7.74545014278341407640e-4 * r + 2.27238449892691845833e-2) * r + 2.41780725177450611770e-1) * r +
+                 1.27045825245236838258) * r + 3.64784832476320460504) * r + 5.76949722146069140550) * r +
+               4.63033784615654529590) * r + 1.42343711074968357734) /
+            (((((((1.05075007164441684324e-9 * r + 5.47593808499534494600e-4) * r + 1.51986665636164571966e-2) * r +
+                 1.48103976427480074590e-1) * r + 6.89767334985100004550e-1) * r + 1.67638483018380384940) * r +
+               2.05319162663775882187) * r + 1.0);
+    } else {
+        r -= 5.0;
+        v = (((((((2.01033439929228813265e-7 * r + 2.71155556874348757815e-5) * r + 1.24266094738807843860e-3) * r +
+                 2.65321895265761230930e-2) * r + 2.96560571828504891230e-1) * r + 1.78482653991729133580) * r +
+               5.46378491116411436990) * r + 6.65790464350110377720) /
+            (((((((2.04426310338993978564e-15 * r + 1.42151175831644588870e-7) * r + 1.84631831751005468180e-5) * r +
+                 7.86869131145613259100e-4) * r + 1.48753612908506148525e-2) * r + 1.36929880922735805310e-1) * r +
+               5.99832206555887937690e-1) * r + 1.0);
+    }
+    return q < 0 ? -v : v;
 }
 
 // quantile of the chi-squared distribution (R::qchisq, src/hts_pacbio.h:178) by bisection on gamma_p
@@ -63,8 +86,10 @@ double sigmoid(double x) { return 1 / (1 + std::pow(2, (-2.5 / 3 * x + 6.5 / 3))
 struct SampleStream {
     uint64_t seed, j;
     uint32_t k = 0;
+    U4 w{};                 // the Philox block draws k and k ^ 1 come from
     double next() {
-        const uint64_t x = pb_draw(seed, j, 3, k >> 1, k & 1);
+        if ((k & 1u) == 0u) w = draw_block(seed, j, k >> 1, PL_PB, 3);
+        const uint64_t x = (k & 1u) ? hi64(w) : lo64(w);
         k++;
         return ((double)(x >> 11) + 0.5) * (1.0 / 9007199254740992.0);
     }
@@ -110,7 +135,19 @@ void pb_prepare(PbModel& m) {
     m.min_exp = min_exp;
     m.qchisq_n = (size_t)std::max(1.0, std::floor(m.chi2_n[2])) + 2;
     m.qchisq_cache.reset(new std::atomic<double>[m.qchisq_n]);
-    for (size_t i = 0; i < m.qchisq_n; i++) m.qchisq_cache[i].store(-1.0, std::memory_order_relaxed);
+    for (size_t i = 0; i < m.qchisq_n; i++) m.qchisq_cache.get()[i].store(-1.0, std::memory_order_relaxed);
+    // the number of passes of a side is a whole number in [1, max_passes]: everything update_probs and trunc_norm derive
+    // from it alone is computed once (the same expressions, so the same doubles)
+    m.pass_tab.resize((size_t)std::min<uint64_t>(m.max_passes, 4096) + 2);
+    for (size_t i = 0; i < m.pass_tab.size(); i++) {
+        PbModel::PassTab& T = m.pass_tab[i];
+        const double pass = (double)i;
+        T.sig = sigmoid(pass);
+        T.root = std::sqrt(pass + m.sqrt_params[0]) - m.sqrt_params[1];
+        T.thresh = (m.min_exp - T.root) / T.sig;
+        T.a_bar = (T.thresh - m.norm_params[0]) / m.norm_params[1];
+        T.p_low = pnorm(T.a_bar);
+    }
     if (!m.read_probs.empty()) {
         m.len_prob.resize(m.read_probs.size());
         m.len_alias.resize(m.read_probs.size());
@@ -134,7 +171,7 @@ void pb_passes(const PbModel& m, SampleStream& S, PbSample& r) {
     }
     // the outlier threshold is a pure function of lcap (an integer): filled on first use; concurrent callers may compute
     // the same value twice
-    std::atomic<double>& slot = m.qchisq_cache[(size_t)std::floor(lcap)];
+    std::atomic<double>& slot = m.qchisq_cache.get()[(size_t)std::floor(lcap)];
     double thr = slot.load(std::memory_order_relaxed);
     if (thr < 0) { thr = qchisq(0.9925, n); slot.store(thr, std::memory_order_relaxed); }
     double passes = 2.0 * sample_gamma(0.5 * n, S);
@@ -193,10 +230,8 @@ uint64_t pb_dup_draw(uint64_t seed, uint64_t j) { return pb_draw(seed, j, 0, 2, 
 namespace {
 
 // PacBioQualityError::trunc_norm (src/hts_pacbio.h:340-370); side 0 = left, 1 = right
-double trunc_norm(const PbModel& m, double lower_thresh, uint64_t seed, uint64_t j, uint32_t side) {
-    const double a_bar = (lower_thresh - m.norm_params[0]) / m.norm_params[1];
+double trunc_norm(const PbModel& m, double lower_thresh, double a_bar, double p, uint64_t seed, uint64_t j, uint32_t side) {
     if (lower_thresh < (m.norm_params[0] + 5 * m.norm_params[1])) {
-        const double p = pnorm(a_bar);
         const long double u = (long double)p + runif_01(pb_draw(seed, j, 0, 0, side)) * ((long double)1 - (long double)p);   // runif_ab
         return qnorm((double)u) * m.norm_params[1] + m.norm_params[0];
     }
@@ -217,10 +252,18 @@ void pb_read_model(const PbModel& m, uint64_t seed, uint64_t j, const PbSample& 
     const double pass[2] = {s.passes_left, s.passes_right};
     double cum[2][3];
     for (uint32_t side = 0; side < 2; side++) {
-        const double root = std::sqrt(pass[side] + m.sqrt_params[0]) - m.sqrt_params[1];
-        const double thresh = (m.min_exp - root) / sigmoid(pass[side]);
-        const double incr = trunc_norm(m, thresh, seed, j, side);
-        double e = incr * sigmoid(pass[side]) + std::sqrt(pass[side] + m.sqrt_params[0]) - m.sqrt_params[1];
+        PbModel::PassTab T;
+        const size_t pi = pass[side] >= 0 && pass[side] < (double)m.pass_tab.size() ? (size_t)pass[side] : m.pass_tab.size();
+        if (pi < m.pass_tab.size() && (double)pi == pass[side]) T = m.pass_tab[pi];
+        else {
+            T.sig = sigmoid(pass[side]);
+            T.root = std::sqrt(pass[side] + m.sqrt_params[0]) - m.sqrt_params[1];
+            T.thresh = (m.min_exp - T.root) / T.sig;
+            T.a_bar = (T.thresh - m.norm_params[0]) / m.norm_params[1];
+            T.p_low = pnorm(T.a_bar);
+        }
+        const double incr = trunc_norm(m, T.thresh, T.a_bar, T.p_low, seed, j, side);
+        double e = incr * T.sig + std::sqrt(pass[side] + m.sqrt_params[0]) - m.sqrt_params[1];
         if (e < 0.6) e = 0.6;
         cum[side][0] = std::pow(m.prob_ins, e);
         cum[side][1] = std::pow(m.prob_del, e) + cum[side][0];

@@ -27,10 +27,13 @@ struct PbModel {
     double norm_params[2] = {0, 0.2};
     double prob_thresh = 0.2, prob_ins = 0.11, prob_del = 0.04, prob_subst = 0.01;
     double min_exp = 0;                       // calc_min_exp(), set by pb_prepare
-    mutable std::unique_ptr<std::atomic<double>[]> qchisq_cache;   // outlier threshold per min(read_length, chi2_n[2]), filled on first use
+    mutable std::shared_ptr<std::atomic<double>[]> qchisq_cache;   // outlier threshold per min(read_length, chi2_n[2]), filled on first use (a context keeps it from call to call)
     size_t qchisq_n = 0;
     std::vector<double> len_prob;             // alias tables of the custom read lengths
     std::vector<uint64_t> len_alias;
+    // update_probs / trunc_norm: what depends only on the (whole) number of passes, per value 0 .. max_passes + 1
+    struct PassTab { double sig, root, thresh, a_bar, p_low; };
+    std::vector<PassTab> pass_tab;
 };
 // PacBioQualityError::calc_min_exp (src/hts_pacbio.cpp) and the tables of the samplers.  Throws on bad input.
 void pb_prepare(PbModel& m);

@@ -23,7 +23,8 @@ g = J.RefGenome(["chrom%d" % i for i in range(len(lens))], [flat[off[i]:off[i + 
 ctx = J.Context(0)
 nthr = min(len(os.sched_getaffinity(0)), 32)
 J.pacbio(g, "", 1 << 13, seed=1, ctx=ctx, sink="device", n_threads=nthr)
-for rep in range(8):
+n_reads = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 16
+for rep in range(6):
     t0 = time.perf_counter()
-    st = J.pacbio(g, "", 1 << 16, seed=2 + rep, ctx=ctx, sink="device", n_threads=nthr)
+    st = J.pacbio(g, "", n_reads, seed=2 + rep, ctx=ctx, sink="device", n_threads=nthr)
     print("run %d: %.4f s, kernels %.1f ms, %d reads" % (rep, time.perf_counter() - t0, st["reads_ms"], st["pairs"]), flush=True)
