@@ -639,6 +639,17 @@ def main():
             log("[bench] full job (%.3g pairs, %d GPU): %.2f s device-resident, %.2f s plain e2e, %.2f s BGZF e2e"
                 % (full_pairs, world, dev_s, times["e2e_plain_s"], times["e2e_bgzf6_s"]))
 
+    # ---- BASELINE configs[0..3] as whole calls (before the legs that churn tens of gigabytes of page cache: the 96-haplotype
+    #      call allocates 17 GB of host memory for its records and ran 2x slower after them)
+    extras = None
+    if not a.no_extras and rank == 0 and world == 1:
+        try:
+            t0 = time.perf_counter()
+            extras = extra_workloads(J, ctx, a.seed, log)
+            log("[bench] extra workloads took %.1f s" % (time.perf_counter() - t0))
+        except Exception as e:
+            extras = {"error": str(e)[:300]}
+
     # ---- the same through FILES (the reference-facing default sink): tmpfs, all host threads writing
     e2e_files = None
     if not a.no_e2e and not a.no_extras and rank == 0 and world == 1 and os.path.isdir("/dev/shm"):
@@ -750,13 +761,8 @@ def main():
             log("[bench] parity slices vs the oracle: %s (%.1f s)" % (verdict, time.perf_counter() - t0))
         except Exception as e:
             out["parity_slice"] = "error: " + str(e)[:200]
-        if not a.no_extras and world == 1:
-            try:
-                t0 = time.perf_counter()
-                out["extra_workloads"] = extra_workloads(J, ctx, a.seed, log)
-                log("[bench] extra workloads took %.1f s" % (time.perf_counter() - t0))
-            except Exception as e:
-                out["extra_workloads"] = {"error": str(e)[:300]}
+        if extras is not None:
+            out["extra_workloads"] = extras
         if not a.no_cpu_baseline and world == 1:
             prof1, prof2 = (J.flatten_profile(J.read_profile(None, "HS25", L, r)) for r in (1, 2))
             t0 = time.perf_counter()
