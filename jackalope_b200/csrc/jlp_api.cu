@@ -2066,7 +2066,11 @@ void run_pacbio(jlp_ctx* c, bool use_haps, const jlp_pacbio_params* P, int sink_
                 const int hk = (int)(n_batch++ & 1);
                 settle(hk);                                     // the slices of the batch before last are in the file
                 PinBuf<uint8_t>& h_out = h_buf[hk];
-                if (nb + 64 > h_out.n) h_out.ensure(nb + nb / 4 + 64);
+                if (nb + 64 > h_out.n) {          // like d_out: at once to what a full batch will need (pinning is slow)
+                    const uint64_t full = n ? nb / n * std::min<uint64_t>(B, s_hi - s_lo) : nb;
+                    const uint64_t want = std::max(nb, full);
+                    h_out.ensure(want + want / 4 + 64);
+                }
                 CK(cudaMemcpy(h_out.p, dev_z ? d_zout.p : d_out.p, nb, cudaMemcpyDeviceToHost));
                 st.d2h_bytes += nb;
                 if (sink_kind == SINK_MEMORY) {
