@@ -229,6 +229,7 @@ struct Slot {
     DevBuf<uint8_t> zslots[2], zdev[2];
     DevBuf<uint32_t> zlen[2];
     DevBuf<uint64_t> zoff[2];
+    DevBuf<uint8_t> zcode;        // launch_bgzf's scratch (the codes of the batch)
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // start, placed, scanned, reads done, copied, all kernels done
     uint32_t pairs = 0;
     uint64_t tot[2] = {0, 0};     // FASTQ bytes of the batch per file (read back from the device)
@@ -279,7 +280,7 @@ struct jlp_ctx {
     // scratch of the haplotype materialisation (mutation records of one chromosome)
     HapArena hap_mem;
     // PacBio driver: FASTQ of a batch on the device, its compressed form, and the two pinned host buffers batches alternate between
-    DevBuf<uint8_t> pb_out, pb_zslots, pb_zout, pb_strpool;
+    DevBuf<uint8_t> pb_out, pb_zslots, pb_zout, pb_strpool, pb_zcode;
     DevBuf<PbRead> pb_reads;
     DevBuf<GroupDev> pb_groups;
     DevBuf<uint32_t> pb_rec_len, pb_rec_local, pb_zlen;
@@ -753,6 +754,7 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
                 s.zdev[e].ensure(B * max_rec + (size_t)nblk_max * 64 + 64);
                 s.zlen[e].ensure(nblk_max);
                 s.zoff[e].ensure(nblk_max);
+                s.zcode.ensure(kBgzfCodeBytes);
             }
         for (cudaEvent_t& ev : s.ev) if (!ev) CK(cudaEventCreate(&ev));
         s.busy = false;
@@ -995,8 +997,8 @@ void run(jlp_ctx* c, bool use_haps, const jlp_illumina_params* P, Sink& sink, jl
             CK(cudaEventRecord(s.ev[3], c->s_compute));
             if (dev_z) {
                 CK(launch_bgzf(s.out[0].p, s.out[1].p, s.totals.p, nblk_max, P->compress >= 4, s.zslots[0].p, s.zslots[1].p, s.zlen[0].p,
-                               s.zlen[1].p, s.zoff[0].p, s.zoff[1].p, s.zdev[0].p, s.zdev[1].p, c->s_compute));
-                st.kernel_launches += 3;
+                               s.zlen[1].p, s.zoff[0].p, s.zoff[1].p, s.zdev[0].p, s.zdev[1].p, s.zcode.p, c->s_compute));
+                st.kernel_launches += kBgzfLaunches;
             }
             CK(cudaMemcpyAsync(s.h_totals.p, s.totals.p, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->s_compute));
             CK(cudaEventRecord(s.ev[5], c->s_compute));
@@ -1875,7 +1877,7 @@ void run_pacbio(jlp_ctx* c, bool use_haps, const jlp_pacbio_params* P, int sink_
     // every buffer belongs to the context: pinning (and unpinning) a gigabyte of host memory on every call cost more than
     // generating the reads, and a dozen device allocations and frees per call several milliseconds
     DevBuf<GroupDev>& d_groups = c->pb_groups;
-    DevBuf<uint8_t>&d_strpool = c->pb_strpool, &d_out = c->pb_out, &d_zslots = c->pb_zslots, &d_zout = c->pb_zout;
+    DevBuf<uint8_t>&d_strpool = c->pb_strpool, &d_out = c->pb_out, &d_zslots = c->pb_zslots, &d_zout = c->pb_zout, &d_zcode = c->pb_zcode;
     DevBuf<PbRead>& d_reads = c->pb_reads;
     DevBuf<uint32_t>&d_rec_len = c->pb_rec_len, &d_rec_local = c->pb_rec_local, &d_zlen = c->pb_zlen;
     DevBuf<uint64_t>&d_block_tot = c->pb_block_tot, &d_block_base = c->pb_block_base, &d_totals = c->pb_totals, &d_zoff = c->pb_zoff;
@@ -2044,10 +2046,10 @@ void run_pacbio(jlp_ctx* c, bool use_haps, const jlp_pacbio_params* P, int sink_
                 const uint32_t nblk = (uint32_t)((bound + kBgzfIn - 1) / kBgzfIn) + 1;
                 if (dev_z) {
                     d_zslots.ensure((size_t)nblk * kBgzfSlot); d_zout.ensure((size_t)nblk * kBgzfSlot);
-                    d_zlen.ensure(2 * nblk); d_zoff.ensure(2 * nblk);
+                    d_zlen.ensure(2 * nblk); d_zoff.ensure(2 * nblk); d_zcode.ensure(kBgzfCodeBytes);
                     CK(launch_bgzf(d_out.p, d_out.p, d_totals.p, nblk, P->compress >= 4, d_zslots.p, d_zslots.p, d_zlen.p, d_zlen.p + nblk,
-                                   d_zoff.p, d_zoff.p + nblk, d_zout.p, d_zout.p, c->s_compute));
-                    st.kernel_launches += 3;
+                                   d_zoff.p, d_zoff.p + nblk, d_zout.p, d_zout.p, d_zcode.p, c->s_compute));
+                    st.kernel_launches += kBgzfLaunches;
                 }
                 CK(cudaEventRecord(ev[2], c->s_compute));
                 uint64_t tot[4];
@@ -2225,16 +2227,16 @@ int jlp_bgzf_device(jlp_ctx* c, int level, const void* in, uint64_t n, void* out
         if ((n && !in) || !len) throw ArgErr("NULL argument");
         c = first_device(c);
         const uint32_t nblk = (uint32_t)((n + kBgzfIn - 1) / kBgzfIn);
-        DevBuf<uint8_t> d_in, d_slots, d_out;
+        DevBuf<uint8_t> d_in, d_slots, d_out, d_code;
         DevBuf<uint32_t> d_zlen;
         DevBuf<uint64_t> d_zoff, d_tot;
         d_in.ensure(n + 64); d_slots.ensure((size_t)nblk * kBgzfSlot); d_out.ensure((size_t)nblk * kBgzfSlot);
-        d_zlen.ensure(nblk); d_zoff.ensure(nblk); d_tot.ensure(4);
+        d_zlen.ensure(nblk); d_zoff.ensure(nblk); d_tot.ensure(4); d_code.ensure(kBgzfCodeBytes);
         const uint64_t tot[4] = {n, 0, 0, 0};
         if (n) CK(cudaMemcpyAsync(d_in.p, in, n, cudaMemcpyHostToDevice, c->s_compute));
         CK(cudaMemcpyAsync(d_tot.p, tot, sizeof tot, cudaMemcpyHostToDevice, c->s_compute));
         CK(launch_bgzf(d_in.p, d_in.p, d_tot.p, nblk, level >= 4, d_slots.p, d_slots.p, d_zlen.p, d_zlen.p, d_zoff.p, d_zoff.p, d_out.p,
-                       d_out.p, c->s_compute));
+                       d_out.p, d_code.p, c->s_compute));
         uint64_t back[4];
         CK(cudaMemcpyAsync(back, d_tot.p, sizeof back, cudaMemcpyDeviceToHost, c->s_compute));
         CK(cudaStreamSynchronize(c->s_compute));

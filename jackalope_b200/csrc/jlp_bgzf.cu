@@ -4,30 +4,50 @@
 // src/hts.h:140-180: gzip members (RFC 1952) of at most 0xff00 input bytes carrying the
 // "BC" extra field with the member's size, each holding one RFC 1951 deflate stream).
 //
-// One CTA per BGZF block, 512 threads, 3 CTAs per SM.  Thread t owns bytes [128 t, 128 t + 128)
-// of the block in the passes that need contiguous bytes, warp w the segment [4096 w, 4096 w + 4096).
-//   pass 0  line starts (the byte after every '\n', by a block scan of the newline counts); every
-//           line start is compared with the line start 4 lines earlier -- in FASTQ the same line of the
-//           previous record -- and a common prefix of >= 4 bytes (the "@<genome>-<chrom>-" of the
-//           ID lines, mostly) becomes one length/distance pair; a bit mask marks the bytes so covered
-//   pass 1  per-warp histograms of the remaining literals (shared atomics) and the CRC-32 of each
-//           thread's chunk; chunk CRCs are combined by a tree of "advance by 2^j zero bytes" operators
-//   build   one dynamic-Huffman block: code lengths by two-queue Huffman over the rank-sorted
-//           symbols (the tree by one thread, the depths by one thread per leaf), limited to 15 / 7
-//           bits by the usual count fix-up, canonical codes; the distance code and the code-length
-//           code by one warp; the run-length coded code lengths by one thread per run
-//   pass 2  every warp packs its segment, 4 bytes per lane and 128 contiguous bytes per round: the
-//           codes of a lane's bytes are joined, a warp scan of the lengths places them, and they are
-//           OR-ed into the block image in shared memory
-//   a block that would not shrink below 48 KiB is emitted as a stored block straight from the input.
-// The image leaves with 128-bit stores into a 64 KiB slot; k_bgzf_scan / k_bgzf_gather
-// then make the file contiguous.
+// Two kernels per batch.  FASTQ is stationary -- every block of a batch has the statistics of every other --
+// so the Huffman codes are built ONCE per file and batch, from the file's first block, and every block is
+// coded with them (each member still carries the code in its own dynamic-block header, as the format wants):
+//
+// k_bgzf_code   one CTA per file.  Block 0: literal histograms (shared atomics), the matches of its lines, and
+//               from the counts -- every symbol's count raised by one, so that a byte the sample does not hold
+//               still has a code -- the literal/length and distance codes (two-queue Huffman over the
+//               rank-sorted symbols, limited to 15 bits, canonical), the code-length code, and the bits of the
+//               member + block header, which are the same for every block.  Left in a ZCode in device memory.
+// k_bgzf        one CTA of 512 threads per BGZF block, 3 CTAs per SM; no code construction, nine barriers.
+//   pass 1  thread t owns bytes [128 t, 128 t + 128): the CRC-32 of the chunk (slicing by four; chunk CRCs are
+//           combined by a tree of "advance over 2^j zero bytes" operators) and its newlines as a bit mask
+//   match   (levels 4-6) line starts by a block scan of the newline counts; every line start is compared with
+//           the line start 4 lines earlier -- in FASTQ the same line of the previous record -- and a common
+//           prefix of >= 4 bytes becomes one length/distance pair; a bit mask marks the bytes so covered
+//   pass 2  warp w packs segment [4096 w, 4096 w + 4096), 4 bytes per lane and 128 contiguous bytes per round
+//           (the codes of a lane's bytes are joined, a warp scan of the lengths places them), into an image
+//           of its own in shared memory that starts at bit 0: no warp has to know the others' sizes
+//   join    the header bits, the 16 segment images, the end-of-block code and the CRC-32 / ISIZE trailer are
+//           pieces of known bit length now; every output word is funnel-shifted together from the one or
+//           two pieces it covers on its way to global memory
+//   a block that would not shrink, or a segment that outgrows its image (3 KiB per 4 KiB in a full block), is emitted as a
+//   stored block straight from the input.
+// The member lands in a 64 KiB slot; k_bgzf_scan / k_bgzf_gather then make the file contiguous.
+#ifdef JLP_CPU_EMU      // tests/emu: the kernels of this file on host threads (CPU test suite), see tests/emu/cuda_emu.h
+#include "cuda_emu.h"
+namespace jlp {
+constexpr uint32_t kBgzfIn = 0xff00;
+constexpr uint32_t kBgzfSlot = 65536;
+constexpr uint32_t kBgzfCodeBytes = 4096;
+}
+#define JLP_DYN_SMEM(name) uint8_t* name = jlp_emu::dyn_smem()
+#define JLP_LAUNCH(k, grid, block, smem, stream, ...) jlp_emu::launch(grid, block, smem, [&]() { k(__VA_ARGS__); })
+#else
 #include "jlp_kernels.cuh"
+#define JLP_DYN_SMEM(name) extern __shared__ __align__(16) uint8_t name[]
+#define JLP_LAUNCH(k, grid, block, smem, stream, ...) k<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#endif
 
 #include <cstddef>
 #include <cstring>
 
 namespace jlp {
+
 
 namespace {
 
@@ -45,8 +65,31 @@ constexpr uint32_t kLsCap = 1024;        // line starts kept per block (two per 
 constexpr uint32_t kMCap = 1024;         // matches kept per block
 constexpr uint32_t kBack = 4;            // a line is compared with the line this many lines earlier
 constexpr uint32_t kMaskWords = kBgzfIn / 32 + 2;
+// k_bgzf: the image of warp w's segment is words [w * kRegionWords, (w + 1) * kRegionWords) of ZMain::buf; behind the
+// images the other pieces of a member: the header words, the end-of-block code, CRC-32 and ISIZE
+constexpr uint32_t kRegionWords = 768;     // in a full block; the segments of a shorter one share the same space
+constexpr uint32_t kHdrWords = 160;      // 18 bytes of member header + at most 4498 bits of block header
+constexpr uint32_t kHdrOff = kZW * kRegionWords;
+constexpr uint32_t kEobOff = kHdrOff + kHdrWords;
+constexpr uint32_t kTailOff = kEobOff + 1;
+constexpr uint32_t kBufWords = kTailOff + 3;
+constexpr uint32_t kPieces = kZW + 3;
+constexpr uint32_t kOwnCode = 0xffffffffu;   // in zlen[]: k_bgzf leaves this block to k_bgzf_own
 
-__constant__ uint32_t c_crc_tab[256];
+// what k_bgzf_code leaves for k_bgzf, one per file
+struct ZCode {
+    uint32_t ctab[256];        // literal: code (bit-reversed, LSB first) | length << 16
+    uint32_t lcode[32];        // length symbol 257 + i, likewise
+    uint32_t dcode[32];        // distance symbol i
+    uint32_t eob;              // end of block
+    uint32_t hdr_bits;         // bits in use of hdr[]
+    uint32_t pad[2];
+    uint32_t hdr[kHdrWords];   // the member header (BSIZE left zero) and the dynamic block's header
+};
+static_assert(2 * sizeof(ZCode) <= kBgzfCodeBytes, "launch_bgzf's code scratch");
+static_assert(kBufWords % 4 == 0, "buf is cleared and read as uint4");
+
+__constant__ uint32_t c_crc_tab[4][256];  // slicing by four: [k][b] = the register after byte b and k zero bytes
 __constant__ uint32_t c_crc_adv[17][32];   // operator "advance the CRC register over 2^j zero bytes", by bit image
 __constant__ uint32_t c_crc_init_full;     // the initial register 0xffffffff advanced over a full block
 // the same operators for 2^7 .. 2^15 zero bytes (the sizes a full block's CRC tree combines) as 4 x 256-entry tables:
@@ -69,13 +112,14 @@ struct ZShared {
     uint32_t mask[kMaskWords];            // bit q + 1: byte q of the block is covered by a match
     uint64_t mbits[kMCap];                // the matches in block order: first their tokens (match_token), then their bits | bit count << 56
     uint32_t cnt[288];                    // literal/length counts; [256] = end of block, [257, 286) lengths
-    uint32_t crc_tab[256];
+    uint32_t crc_tab[4][256];
     uint32_t ctab[256];                   // code (bit-reversed, LSB first) | length << 16 per literal
     uint32_t sw[288];                     // Huffman: weights of the leaves in sorted order
     uint32_t w_int[288];                  // ... of the internal nodes in creation order
     uint32_t scan_tmp[kZW + 1];
     uint32_t crc_w[kZW];
     uint32_t wm[kZW];                     // matches that start in each warp's segment
+    uint32_t run_bal[kZW];                // bit per position of the code-length sequence: a run starts here
     uint32_t bl[16];                      // codes per length
     uint32_t dcnt[32];                    // counts of the distance alphabet
     uint32_t cl_cnt[19];                  // counts of the code-length alphabet
@@ -98,6 +142,25 @@ struct ZShared {
 
 static_assert(sizeof(ZShared) <= 75 * 1024, "three CTAs per SM");
 static_assert(offsetof(ZShared, mbits) % 8 == 0, "mbits alignment");
+
+// shared memory of k_bgzf
+struct ZMain {
+    uint32_t buf[kBufWords];              // 16 segment images, header words, end-of-block code, CRC-32, ISIZE, a zero word
+    uint64_t mbits[kMCap];                // the matches in block order: bits | bit count << 56
+    uint32_t mask[kMaskWords];            // bit q + 1: byte q of the block is covered by a match
+    uint32_t crc_tab[4][256];
+    uint32_t ctab[256];
+    uint32_t lcode[32], dcode[32];
+    uint32_t scan_tmp[kZW + 1];
+    uint32_t crc_w[kZW];
+    uint32_t wm[kZW];                     // matches that start in each warp's segment
+    uint32_t seg_bits[kZW];               // bits of each warp's image; 0xffffffff: it did not fit
+    uint32_t pdst[32], pend[32], pnb[32], psrc[32];   // the pieces of the member: first bit, end, bits, first word in buf
+    uint32_t eob, hdr_bits, z_bytes, stored;
+    uint16_t ls[kLsCap + 1];              // line starts, ascending; ls[0] = 0
+};
+static_assert(sizeof(ZMain) <= 75 * 1024, "three CTAs per SM");
+static_assert(offsetof(ZMain, mbits) % 8 == 0, "mbits alignment");
 
 __device__ __forceinline__ uint32_t crc_apply(const uint32_t* m, uint32_t v) {
     uint32_t r = 0;
@@ -295,6 +358,17 @@ __device__ __forceinline__ uint64_t match_bits(const ZShared& S, uint32_t tok, u
     n = ll + le + dl + de;
     return v;
 }
+__device__ __forceinline__ uint64_t match_bits(const ZMain& S, uint32_t tok, uint32_t& n) {
+    const uint32_t li = tok & 31u, lx = (tok >> 5) & 31u, ds = (tok >> 10) & 31u, dx = (tok >> 15) & 0x1fffu;
+    const uint32_t lc = S.lcode[li], dc = S.dcode[ds];
+    const uint32_t ll = lc >> 16, le = len_extra_bits(li), dl = dc >> 16, de = dist_extra_bits(ds);
+    uint64_t v = lc & 0xffffu;
+    v |= (uint64_t)lx << ll;
+    v |= (uint64_t)(dc & 0xffffu) << (ll + le);
+    v |= (uint64_t)dx << (ll + le + dl);
+    n = ll + le + dl + de;
+    return v;
+}
 
 // the mask bits of bytes [q, q + 32) of the block (bit i: byte q + i), q a multiple of 4
 __device__ __forceinline__ uint32_t mask_at(const uint32_t* mask, uint32_t q) {
@@ -312,10 +386,10 @@ __device__ __forceinline__ void load16(const uint8_t* a, uint32_t (&x)[4]) {
     x[2] = __funnelshift_r(w2, w3, sh); x[3] = __funnelshift_r(w3, w4, sh);
 }
 
-// pass 1 of a thread: its 128 contiguous bytes, 16 at a time from global memory -> warp histogram of all bytes
-// (the bytes a match covers are taken out again when the match is found), chunk CRC, and the chunk's newlines as
-// one bit per byte
-template <bool FULL>
+// pass 1 of a thread: its 128 contiguous bytes, 16 at a time from global memory -> chunk CRC, the chunk's newlines as
+// one bit per byte and (HIST, k_bgzf_code) the warp histogram of all bytes (the bytes a match covers are taken out
+// again when the match is found)
+template <bool FULL, bool HIST>
 __device__ __forceinline__ uint32_t pass1(const uint8_t* chunk, uint32_t my_len, uint32_t* hist, const uint32_t* tab,
                                           uint32_t (&nlm)[4]) {
     uint32_t reg = 0;
@@ -331,13 +405,20 @@ __device__ __forceinline__ uint32_t pass1(const uint8_t* chunk, uint32_t my_len,
             // the four "is a newline" bits of the word gathered into a nibble by one multiplication
             const uint32_t eq = __vcmpeq4(w[q], 0x0a0a0a0au) & 0x01010101u;
             nlm[k >> 1] |= ((eq * 0x01020408u) >> 24) << (((k & 1) * 16) + q * 4);
+            // the CRC register takes a whole word per step (slicing by four: one round of table look-ups instead of four
+            // dependent ones); the ragged end of a short chunk goes byte by byte
+            const bool whole = FULL || (uint32_t)(k * 16 + q * 4 + 3) < my_len;
+            if (whole) {
+                const uint32_t x = reg ^ w[q];
+                reg = tab[768 + (x & 0xffu)] ^ tab[512 + ((x >> 8) & 0xffu)] ^ tab[256 + ((x >> 16) & 0xffu)] ^ tab[x >> 24];
+            }
 #pragma unroll
             for (int r = 0; r < 4; r++) {
                 const int i = k * 16 + q * 4 + r;
                 if (FULL || (uint32_t)i < my_len) {
                     const uint32_t b = (w[q] >> (8 * r)) & 0xffu;
-                    atomicAdd(&hist[b], 1u);
-                    reg = tab[(reg ^ b) & 0xffu] ^ (reg >> 8);
+                    if (HIST) atomicAdd(&hist[b], 1u);
+                    if (!whole) reg = tab[(reg ^ b) & 0xffu] ^ (reg >> 8);
                 }
             }
         }
@@ -350,11 +431,14 @@ __device__ __forceinline__ uint32_t pass1(const uint8_t* chunk, uint32_t my_len,
     return reg;
 }
 
-// pass 2 of a warp: its segment again, 4 bytes per lane and 128 contiguous bytes per round.  A byte a match
-// covers sends nothing, except the first one, which sends the match.
-template <bool FULL, bool LZ>
-__device__ __forceinline__ void pack_warp(const ZShared& S, const uint8_t* seg, uint32_t seg_off, uint32_t seg_len, uint32_t* stage,
-                                          uint32_t base, uint32_t cursor, uint32_t lane) {
+// pass 2 of a warp: its segment again, 4 bytes per lane and 128 contiguous bytes per round, packed from bit 0 of the
+// warp's image.  A byte a match covers sends nothing, except the first one, which sends the match.
+// Returns the bit position behind the segment, or 0xffffffff when the segment outgrew the image or holds a byte that
+// has no code (uniform inside the warp).
+template <bool FULL, bool LZ, class SH>
+__device__ __forceinline__ uint32_t pack_warp(const SH& S, const uint8_t* seg, uint32_t seg_off, uint32_t seg_len, uint32_t* stage,
+                                              uint32_t base, uint32_t image_bits, uint32_t cursor, uint32_t lane) {
+    bool miss = false;
     const uint32_t* g = reinterpret_cast<const uint32_t*>(seg) + lane;
     for (uint32_t r0 = 0; r0 < 32; r0 += 4) {
         if (!FULL && r0 * 128u >= seg_len) break;
@@ -370,6 +454,8 @@ __device__ __forceinline__ void pack_warp(const ZShared& S, const uint8_t* seg, 
             const uint32_t q = seg_off + off;
             const uint32_t mb = LZ && (FULL || nv) ? __funnelshift_r(S.mask[q >> 5], S.mask[(q >> 5) + 1], q & 31u) & 0x1fu : 0u;
             uint32_t e0 = S.ctab[w[u] & 0xffu], e1 = S.ctab[(w[u] >> 8) & 0xffu], e2 = S.ctab[(w[u] >> 16) & 0xffu], e3 = S.ctab[w[u] >> 24];
+            if (FULL) miss |= !(e0 && e1 && e2 && e3);      // a byte the code has no word for
+            else miss |= (nv >= 1 && !e0) || (nv >= 2 && !e1) || (nv >= 3 && !e2) || (nv >= 4 && !e3);
             if (!FULL) { if (nv < 1) e0 = 0; if (nv < 2) e1 = 0; if (nv < 3) e2 = 0; if (nv < 4) e3 = 0; }
             if (LZ && (mb & 0x1eu)) { if (mb & 2u) e0 = 0; if (mb & 4u) e1 = 0; if (mb & 8u) e2 = 0; if (mb & 16u) e3 = 0; }
             const uint32_t l0 = e0 >> 16, l1 = e1 >> 16, l2 = e2 >> 16, l3 = e3 >> 16;
@@ -394,8 +480,10 @@ __device__ __forceinline__ void pack_warp(const ZShared& S, const uint8_t* seg, 
             uint32_t incl = l;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += x; }
+            const uint32_t round_bits = __shfl_sync(0xffffffffu, incl, 31);
+            if (base + round_bits + 128u > image_bits) return 0xffffffffu;     // a lane's bits touch at most four words
             const uint32_t at = base + incl - l;
-            base += __shfl_sync(0xffffffffu, incl, 31);
+            base += round_bits;
             const uint32_t i = at >> 5, sh = at & 31;
             const uint32_t x0 = (uint32_t)c, x1 = (uint32_t)(c >> 32);
             if (l) atomicOr(&stage[i], x0 << sh);
@@ -404,6 +492,7 @@ __device__ __forceinline__ void pack_warp(const ZShared& S, const uint8_t* seg, 
             if (LZ && sh + l > 96) atomicOr(&stage[i + 3], __funnelshift_l(top, 0u, sh));
         }
     }
+    return __any_sync(0xffffffffu, miss) ? 0xffffffffu : base;
 }
 
 // The run of equal code lengths starting at a position, as the tokens of RFC 1951 section 3.2.7:
@@ -428,10 +517,473 @@ __device__ __forceinline__ RunTok run_tokens(uint32_t v, uint32_t run) {
     return r;
 }
 
+// The match of line start k (ls[k]) with line start k - kBack, never beyond the line's last byte before its '\n':
+// position, length and token; tok = 0: none.
+__device__ __forceinline__ void find_match(const uint8_t* in, uint32_t len, const uint16_t* ls, uint32_t n_ls, uint32_t k, uint32_t& at,
+                                           uint32_t& mlen, uint32_t& tok) {
+    if (k < kBack || k >= n_ls) return;
+    const uint32_t i = ls[k];
+    if (i >= len) return;
+    const uint32_t p = ls[k - kBack];
+    const uint32_t next = k + 1 < n_ls ? (uint32_t)ls[k + 1] - 1u : len;   // the '\n' that ends this line, or the end
+    const uint32_t maxm = min(258u, next - i);
+    // common prefix, 16 bytes per round trip (reads may run up to 19 bytes past the block: the buffers have slack)
+    uint32_t m = 0;
+    while (m < maxm) {
+        uint32_t a[4], c[4];
+        load16(in + i + m, a);
+        load16(in + p + m, c);
+        uint32_t same = 16;
+#pragma unroll
+        for (int j = 3; j >= 0; j--) { const uint32_t x = a[j] ^ c[j]; if (x) same = 4 * j + (((uint32_t)__ffs(x) - 1u) >> 3); }
+        m += same;
+        if (same < 16) break;
+    }
+    m = min(m, maxm);
+    if (m >= 4 && i - p <= 32768u) { at = i; mlen = m; tok = match_token(m, i - p); }
+}
+
+// The codes of one file of a batch, from its first block (one CTA per file).
+__global__ void __launch_bounds__(kZT, 1)
+k_bgzf_code(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const uint64_t* __restrict__ totals, uint32_t lz,
+            ZCode* __restrict__ codes) {
+    JLP_DYN_SMEM(smem_raw);
+    ZShared& S = *reinterpret_cast<ZShared*>(smem_raw);
+    const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const bool second = blockIdx.x != 0;
+    const uint64_t n_all = totals[second ? 1 : 0];
+    if (n_all == 0) return;
+    const uint8_t* in = second ? in1 : in0;
+    const uint32_t len = (uint32_t)min((uint64_t)kBgzfIn, n_all);
+    ZCode& Z = codes[second ? 1 : 0];
+
+    const uint32_t my_off = t * kChunk;
+    const uint32_t my_len = my_off >= len ? 0u : min(kChunk, len - my_off);
+    const HuffScratch H1{S.sw, S.w_int, S.sorted, S.par_leaf, S.par_int, S.d_int, S.bl};
+    const HuffScratch H2{S.sw2, S.w_int2, S.sorted2, S.par_leaf2, S.par_int2, S.d_int2, S.bl2};
+
+    // ---- clear the header image (and with it the histograms) and the counters
+    {
+        uint4* s4 = reinterpret_cast<uint4*>(S.stage);
+        for (uint32_t i = t; i < kStageWords / 4; i += kZT) s4[i] = make_uint4(0, 0, 0, 0);
+        if (t < 256) { S.crc_tab[0][t] = c_crc_tab[0][t]; S.crc_tab[1][t] = c_crc_tab[1][t]; S.crc_tab[2][t] = c_crc_tab[2][t]; S.crc_tab[3][t] = c_crc_tab[3][t]; }
+        if (t < 288) { S.len[t] = 0; S.cnt[t] = 0; }
+        if (t < 32) { S.dcnt[t] = 0; S.dlen[t] = 0; }
+        if (t < 16) S.bl[t] = 0;
+        if (t < 19) S.cl_cnt[t] = 0;
+        if (t == 0) { S.maxd = 0; S.ls[0] = 0; }
+    }
+    __syncthreads();
+    // ---- pass 1: histogram of all bytes + the chunk's newlines (the CRC comes along unused)
+    uint32_t* hist = S.stage + kHistWord0 + warp * 256;
+    uint32_t nlm[4] = {0, 0, 0, 0};
+    if (my_len == kChunk) pass1<true, true>(in + my_off, my_len, hist, &S.crc_tab[0][0], nlm);
+    else pass1<false, true>(in + my_off, my_len, hist, &S.crc_tab[0][0], nlm);
+
+    if (lz) {       // uniform
+        // ---- line starts and matches as k_bgzf finds them; here only their symbols are counted
+        const uint32_t my_nl = __popc(nlm[0]) + __popc(nlm[1]) + __popc(nlm[2]) + __popc(nlm[3]);
+        uint32_t total_nl;
+        const uint32_t nl_before = block_scan(my_nl, S.scan_tmp, total_nl);
+        {
+            uint32_t idx = nl_before + 1;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                uint32_t m = nlm[j];
+                while (m) {
+                    const uint32_t bit = (uint32_t)__ffs(m) - 1u;
+                    m &= m - 1u;
+                    if (idx <= kLsCap) S.ls[idx] = (uint16_t)(my_off + 32u * j + bit + 1u);
+                    idx++;
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t n_ls = min(min(total_nl, kLsCap) + 1, 2u * kZT);
+        uint32_t m_at[2] = {0, 0}, m_len[2] = {0, 0}, m_tok[2] = {0, 0};
+#pragma unroll
+        for (int h = 0; h < 2; h++) find_match(in, len, S.ls, n_ls, 2 * t + h, m_at[h], m_len[h], m_tok[h]);
+        uint32_t total_m;
+        uint32_t mj = block_scan((m_tok[0] ? 1u : 0u) + (m_tok[1] ? 1u : 0u), S.scan_tmp, total_m);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            if (m_tok[h] && mj < kMCap) {
+                const uint32_t tok = m_tok[h], i = m_at[h];
+                atomicAdd(&S.cnt[257 + (tok & 31u)], 1u);
+                atomicAdd(&S.dcnt[(tok >> 10) & 31u], 1u);
+                // its bytes leave the literal histograms (of the warps whose segments hold them)
+                for (uint32_t q0 = 0; q0 < m_len[h]; q0 += 16) {
+                    uint32_t a[4];
+                    load16(in + i + q0, a);
+#pragma unroll
+                    for (int j = 0; j < 16; j++)
+                        if (q0 + j < m_len[h]) atomicSub(&S.stage[kHistWord0 + ((i + q0 + j) / kSeg) * 256 + ((a[j >> 2] >> (8 * (j & 3))) & 0xffu)], 1u);
+                }
+            }
+            if (m_tok[h]) mj++;
+        }
+    }
+    __syncthreads();
+
+    // ---- the counts, each raised by one: what the sample does not hold can still be coded in the other blocks
+    //      (level 1 sends no matches: its length and distance alphabets stay empty)
+    const uint32_t hlit = lz ? kNLit : 257u;
+    uint32_t my_cnt = 0;
+    if (t < hlit) {
+        if (t < 256) {
+            for (int w = 0; w < kZW; w++) my_cnt += S.stage[kHistWord0 + w * 256 + t];
+            if (t == '\n' || (t >= 0x20 && t < 0x7f)) my_cnt += 1u;
+        } else my_cnt = t == 256 ? 1u : S.cnt[t] + 1u;     // [256]: the end of block, once per block
+    }
+    // the active symbols, compacted in symbol order: count << 9 | symbol orders them by (count, symbol)
+    const uint32_t act = __ballot_sync(0xffffffffu, my_cnt != 0);
+    if (lane == 0) S.scan_tmp[warp] = __popc(act);
+    __syncthreads();
+    uint32_t n_active = 0, before = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < 9; w++) { const uint32_t c = S.scan_tmp[w]; n_active += c; before += w < warp ? c : 0u; }
+    if (my_cnt) S.w_int[before + __popc(act & ((1u << lane) - 1u))] = my_cnt << 9 | t;
+    __syncthreads();
+    // rank sort (ascending count, ties by symbol)
+    if (my_cnt) {
+        const uint32_t key = my_cnt << 9 | t;
+        uint32_t rank = 0;
+#pragma unroll 4
+        for (uint32_t q = 0; q < n_active; q++) rank += S.w_int[q] < key ? 1u : 0u;
+        S.sorted[rank] = (uint16_t)t;
+        S.sw[rank] = my_cnt;
+    }
+    __syncthreads();
+
+    // ---- literal/length code lengths: the tree by one thread, the depths by one thread per leaf
+    if (t == 0) huff_merge(H1, n_active);      // n_active >= 257
+    if (warp == 1) {                           // meanwhile the distance code
+        const uint32_t hd = warp_huffman(H2, lane < kNDist ? S.dcnt[lane] + (lz ? 1u : 0u) : 0u, kNDist, 15, S.dlen, S.dcode, lane);
+        if (lane == 0) S.hdist = hd;
+    }
+    __syncthreads();
+    if (t < n_active) {
+        uint32_t p = S.par_leaf[t], dep = 1;
+        const uint32_t root = n_active - 2;
+        while (p != root) { p = S.par_int[p]; dep++; }
+        S.len[S.sorted[t]] = (uint8_t)min(dep, 15u);
+        atomicAdd(&S.bl[min(dep, 15u)], 1u);
+        if (dep > 15) atomicMax(&S.maxd, dep);
+    }
+    __syncthreads();
+    if (S.maxd > 15) {                         // the 15-bit limit has to act (with the raised counts: nearly always)
+        if (t == 0) huff_limit(H1, n_active, 15, S.len);
+        __syncthreads();
+    }
+    // canonical codes: first code of the length + the symbols of the same length before this one
+    if (t < kNLit) {
+        const uint32_t l = S.len[t];
+        if (l) {
+            const uint32_t pat = l * 0x01010101u;
+            const uint32_t* lw = reinterpret_cast<const uint32_t*>(S.len);
+            uint32_t same = 0;
+#pragma unroll 4
+            for (uint32_t j = 0; j < t / 4; j++) same += __popc(__vcmpeq4(lw[j], pat));
+            same += __popc(__vcmpeq4(lw[t / 4], pat) & ((1u << (8 * (t & 3))) - 1u));
+            S.code[t] = (uint16_t)rev_bits(first_code(S.bl, l) + same / 8, l);
+        } else S.code[t] = 0;
+    }
+    __syncthreads();
+    // ---- the runs of the code-length sequence (HLIT literal/length lengths, then HDIST distance lengths): one thread
+    //      per run counts its tokens
+    const uint32_t n_seq = hlit + S.hdist;
+    auto seq = [&](uint32_t i) -> uint32_t { return i < hlit ? S.len[i] : S.dlen[i - hlit]; };
+    RunTok rt{0, 0, 0, 0, 0, 0};
+    // where the runs start, one bit per position (n_seq <= 316 < kZT): a run ends where the next one starts
+    const uint32_t v_seq = t < n_seq ? seq(t) : 0u;
+    const bool run_start = t < n_seq && (t == 0 || seq(t - 1) != v_seq);
+    {
+        const uint32_t bal = __ballot_sync(0xffffffffu, run_start);
+        if (lane == 0) S.run_bal[warp] = bal;
+    }
+    __syncthreads();
+    if (run_start) {
+        uint32_t next = n_seq;
+        uint32_t m = lane == 31 ? 0u : S.run_bal[warp] & (0xffffffffu << (lane + 1u));
+        for (uint32_t w = warp; ; ) {
+            if (m) { next = min(n_seq, w * 32u + (uint32_t)__ffs(m) - 1u); break; }
+            if (++w >= (uint32_t)kZW) break;
+            m = S.run_bal[w];
+        }
+        rt = run_tokens(v_seq, next - t);
+        if (v_seq == 0) {
+            if (rt.n_big) atomicAdd(&S.cl_cnt[18], rt.n_big);
+            if (rt.n_mid) atomicAdd(&S.cl_cnt[17], 1u);
+            if (rt.n_lit) atomicAdd(&S.cl_cnt[0], rt.n_lit);
+        } else {
+            if (rt.n_big) atomicAdd(&S.cl_cnt[16], rt.n_big);
+            atomicAdd(&S.cl_cnt[v_seq], rt.n_lit);
+        }
+    }
+    __syncthreads();
+
+    // ---- the code-length code and the fixed part of the headers (warp 0)
+    if (warp == 0) {
+        warp_huffman(H2, lane < 19 ? S.cl_cnt[lane] : 0u, 19, 7, S.cl_len, S.cl_code, lane);
+        const uint32_t l = lane < 19 ? S.cl_len[lane] : 0u;
+        const uint32_t order_lane = lane < 19 ? (uint32_t)"\x10\x11\x12\x00\x08\x07\x09\x06\x0a\x05\x0b\x04\x0c\x03\x0d\x02\x0e\x01\x0f"[lane] : 0u;
+        // HCLEN: the lengths are sent in the order 16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15 up to the last one used
+        const uint32_t l_ord = __shfl_sync(0xffffffffu, l, order_lane);
+        const uint32_t used = __ballot_sync(0xffffffffu, lane < 19 && l_ord != 0);
+        const uint32_t hclen = max(4u, 32u - (uint32_t)__clz(used));
+        if (lane == 0) {
+            // member header: ID1 ID2 CM FLG(FEXTRA) MTIME XFL OS(255) XLEN=6 'B' 'C' SLEN=2 BSIZE (= total - 1, left to k_bgzf)
+            S.stage[0] = 0x04088b1fu; S.stage[1] = 0; S.stage[2] = 0x0006ff00u; S.stage[3] = 0x00024342u;
+            uint32_t pos = kHdr * 8;
+            put_bits(S.stage, pos, 1, 1); put_bits(S.stage, pos, 2, 2);                   // BFINAL, BTYPE = dynamic Huffman
+            put_bits(S.stage, pos, hlit - 257, 5); put_bits(S.stage, pos, S.hdist - 1, 5); put_bits(S.stage, pos, hclen - 4, 4);
+            S.hdr_fixed_bits = pos + 3 * hclen;
+        }
+        if (lane < hclen) { uint32_t pos = kHdr * 8 + 17 + 3 * lane; put_bits(S.stage, pos, l_ord, 3); }
+    }
+    __syncthreads();
+    // ---- the tokens of the runs, placed by a scan of their bits
+    uint32_t hb = 0;
+    uint32_t l_big = 0, c_big = 0, l_mid = 0, c_mid = 0, l_lit = 0, c_lit = 0;
+    if (run_start) {
+        const uint32_t big = rt.v == 0 ? 18u : 16u, xb = rt.v == 0 ? 7u : 2u;
+        l_big = S.cl_len[big]; c_big = S.cl_code[big];
+        l_mid = S.cl_len[17]; c_mid = S.cl_code[17];
+        l_lit = S.cl_len[rt.v]; c_lit = S.cl_code[rt.v];
+        hb = rt.n_big * (l_big + xb) + rt.n_mid * (l_mid + 3u) + rt.n_lit * l_lit;
+    }
+    uint32_t total;
+    const uint32_t excl = block_scan(hb, S.scan_tmp, total);
+    if (run_start) {
+        uint32_t pos = S.hdr_fixed_bits + excl;
+        if (rt.v == 0) {
+            for (uint32_t q = 0; q < rt.n_big; q++) { put_bits(S.stage, pos, c_big, l_big); put_bits(S.stage, pos, q + 1 == rt.n_big ? rt.big_extra_last : 127u, 7); }
+            if (rt.n_mid) { put_bits(S.stage, pos, c_mid, l_mid); put_bits(S.stage, pos, rt.mid_extra, 3); }
+            for (uint32_t q = 0; q < rt.n_lit; q++) put_bits(S.stage, pos, c_lit, l_lit);
+        } else {
+            put_bits(S.stage, pos, c_lit, l_lit);
+            for (uint32_t q = 0; q < rt.n_big; q++) { put_bits(S.stage, pos, c_big, l_big); put_bits(S.stage, pos, q + 1 == rt.n_big ? rt.big_extra_last : 3u, 2); }
+            for (uint32_t q = 1; q < rt.n_lit; q++) put_bits(S.stage, pos, c_lit, l_lit);
+        }
+    }
+    __syncthreads();
+    // ---- hand over
+    const uint32_t hdr_bits = S.hdr_fixed_bits + total;
+    if (t < 256) Z.ctab[t] = S.len[t] ? (uint32_t)S.code[t] | (uint32_t)S.len[t] << 16 : 0u;
+    if (t < 32) {
+        Z.lcode[t] = t < kNLit - 257 && S.len[257 + t] ? (uint32_t)S.code[257 + t] | (uint32_t)S.len[257 + t] << 16 : 0u;
+        Z.dcode[t] = t < kNDist && S.dlen[t] ? (uint32_t)S.dcode[t] | (uint32_t)S.dlen[t] << 16 : 0u;
+    }
+    if (t < kHdrWords) Z.hdr[t] = t * 32u < hdr_bits ? S.stage[t] : 0u;
+    if (t == 0) { Z.eob = (uint32_t)S.code[256] | (uint32_t)S.len[256] << 16; Z.hdr_bits = hdr_bits; Z.pad[0] = 0; Z.pad[1] = 0; }
+}
+
+// One BGZF block per CTA, with the codes k_bgzf_code left.
 __global__ void __launch_bounds__(kZT, 3)
 k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const uint64_t* __restrict__ totals, uint32_t nblk_max,
+       uint32_t lz, const ZCode* __restrict__ codes, uint8_t* __restrict__ slots0, uint8_t* __restrict__ slots1,
+       uint32_t* __restrict__ zlen0, uint32_t* __restrict__ zlen1) {
+    JLP_DYN_SMEM(smem_raw);
+    ZMain& S = *reinterpret_cast<ZMain*>(smem_raw);
+    const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    // the grid is sized for the largest batch; the FASTQ byte counts of this one are on the device
+    const bool second = blockIdx.x >= nblk_max;
+    const uint32_t b = second ? blockIdx.x - nblk_max : blockIdx.x;
+    const uint64_t n_all = totals[second ? 1 : 0];
+    if ((uint64_t)b * kBgzfIn >= n_all) return;
+    const uint8_t* in = (second ? in1 : in0) + (uint64_t)b * kBgzfIn;
+    const uint32_t len = (uint32_t)min((uint64_t)kBgzfIn, n_all - (uint64_t)b * kBgzfIn);
+    uint8_t* slot = (second ? slots1 : slots0) + (uint64_t)b * kBgzfSlot;
+    uint32_t* zlen = (second ? zlen1 : zlen0) + b;
+    const ZCode& Z = codes[second ? 1 : 0];
+
+    const uint32_t my_off = t * kChunk;
+    const uint32_t my_len = my_off >= len ? 0u : min(kChunk, len - my_off);
+    // the segments of a short block share the whole image space
+    const uint32_t image_words = (kHdrOff / ((len + kSeg - 1) / kSeg)) & ~3u;
+
+    // ---- clear the segment images and the match mask, fetch the codes and the header
+    {
+        uint4* s4 = reinterpret_cast<uint4*>(S.buf);
+        for (uint32_t i = t; i < kHdrOff / 4; i += kZT) s4[i] = make_uint4(0, 0, 0, 0);
+        if (lz) for (uint32_t i = t; i < kMaskWords; i += kZT) S.mask[i] = 0;
+        if (t < 256) {
+            S.crc_tab[0][t] = c_crc_tab[0][t]; S.crc_tab[1][t] = c_crc_tab[1][t]; S.crc_tab[2][t] = c_crc_tab[2][t]; S.crc_tab[3][t] = c_crc_tab[3][t];
+            S.ctab[t] = __ldg(&Z.ctab[t]);
+        }
+        if (t < kHdrWords) S.buf[kHdrOff + t] = __ldg(&Z.hdr[t]);
+        if (t < 32) { S.lcode[t] = __ldg(&Z.lcode[t]); S.dcode[t] = __ldg(&Z.dcode[t]); }
+        if (t < kZW) S.wm[t] = 0;
+        if (t == 0) {
+            const uint32_t eob = __ldg(&Z.eob);
+            S.eob = eob; S.hdr_bits = __ldg(&Z.hdr_bits); S.ls[0] = 0;
+            S.buf[kEobOff] = eob & 0xffffu; S.buf[kTailOff + 2] = 0;
+        }
+    }
+    __syncthreads();
+    // ---- pass 1: chunk CRC + the chunk's newlines
+    uint32_t nlm[4] = {0, 0, 0, 0};
+    uint32_t crc = my_len == kChunk ? pass1<true, false>(in + my_off, my_len, nullptr, &S.crc_tab[0][0], nlm)
+                                    : pass1<false, false>(in + my_off, my_len, nullptr, &S.crc_tab[0][0], nlm);
+    // CRC tree inside the warp: the node at lane covers chunks [t, t + 2s); its right half has right_len bytes
+#pragma unroll
+    for (uint32_t j = 0; j < 5; j++) {
+        const uint32_t s = 1u << j;
+        const uint32_t other = __shfl_down_sync(0xffffffffu, crc, s);
+        if ((lane & (2 * s - 1)) == 0) {
+            const uint32_t r0 = (t + s) * kChunk;
+            const uint32_t right_len = r0 >= len ? 0u : min(s * kChunk, len - r0);
+            crc = (right_len == s * kChunk ? crc_advance_lvl(j, crc) : crc_advance(crc, right_len)) ^ other;
+        }
+    }
+    if (lane == 0) S.crc_w[warp] = crc;
+
+    if (lz) {       // uniform
+        // ---- line starts: the byte after every newline, numbered by a block scan of the newline counts
+        const uint32_t my_nl = __popc(nlm[0]) + __popc(nlm[1]) + __popc(nlm[2]) + __popc(nlm[3]);
+        uint32_t total_nl;
+        const uint32_t nl_before = block_scan(my_nl, S.scan_tmp, total_nl);
+        {
+            uint32_t idx = nl_before + 1;       // line start idx follows the idx-th newline
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                uint32_t m = nlm[j];
+                while (m) {
+                    const uint32_t bit = (uint32_t)__ffs(m) - 1u;
+                    m &= m - 1u;
+                    if (idx <= kLsCap) S.ls[idx] = (uint16_t)(my_off + 32u * j + bit + 1u);
+                    idx++;
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t n_ls = min(min(total_nl, kLsCap) + 1, 2u * kZT);   // entries of S.ls in use (a last one may equal len: no line there)
+        // ---- matches: thread t looks at line starts 2t and 2t + 1, a block scan numbers the matches in block order
+        uint32_t m_at[2] = {0, 0}, m_len[2] = {0, 0}, m_tok[2] = {0, 0};
+#pragma unroll
+        for (int h = 0; h < 2; h++) find_match(in, len, S.ls, n_ls, 2 * t + h, m_at[h], m_len[h], m_tok[h]);
+        uint32_t total_m;
+        uint32_t mj = block_scan((m_tok[0] ? 1u : 0u) + (m_tok[1] ? 1u : 0u), S.scan_tmp, total_m);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            if (m_tok[h] && mj < kMCap) {
+                const uint32_t i = m_at[h];
+                uint32_t hn;
+                const uint64_t hv = match_bits(S, m_tok[h], hn);
+                S.mbits[mj] = hv | (uint64_t)hn << 56;
+                atomicAdd(&S.wm[i / kSeg], 1u);
+                // its bytes are marked: bits [i + 1, i + m + 1) of the mask
+                uint32_t lo = i + 1, hi = i + m_len[h] + 1;
+                while (lo < hi) {
+                    const uint32_t wi = lo >> 5, b0 = lo & 31u, n = min(32u - b0, hi - lo);
+                    atomicOr(&S.mask[wi], (n == 32 ? 0xffffffffu : ((1u << n) - 1u)) << b0);
+                    lo += n;
+                }
+            }
+            if (m_tok[h]) mj++;
+        }
+        __syncthreads();
+    }
+
+    // ---- pass 2: every warp packs its segment into its own image
+    {
+        const uint32_t seg_off = warp * kSeg;
+        uint32_t m_first = 0;                       // matches before this warp's segment
+        if (lz) for (uint32_t w = 0; w < warp; w++) m_first += S.wm[w];
+        const uint32_t seg_len = seg_off >= len ? 0u : min(kSeg, len - seg_off);
+        uint32_t* image = S.buf + warp * image_words;
+        const uint32_t image_bits = image_words * 32u;
+        uint32_t bits = 0;
+        if (lz) {
+            if (seg_len == kSeg) bits = pack_warp<true, true>(S, in + seg_off, seg_off, seg_len, image, 0u, image_bits, m_first, lane);
+            else if (seg_len) bits = pack_warp<false, true>(S, in + seg_off, seg_off, seg_len, image, 0u, image_bits, m_first, lane);
+        } else {
+            if (seg_len == kSeg) bits = pack_warp<true, false>(S, in + seg_off, seg_off, seg_len, image, 0u, image_bits, m_first, lane);
+            else if (seg_len) bits = pack_warp<false, false>(S, in + seg_off, seg_off, seg_len, image, 0u, image_bits, m_first, lane);
+        }
+        if (lane == 0) S.seg_bits[warp] = bits;
+    }
+    __syncthreads();
+
+    // ---- the pieces of the member (warp 0) and the block's CRC (warp 1)
+    if (warp == 0) {
+        uint32_t nb = 0, src = 0;
+        if (lane == 0) { nb = S.hdr_bits; src = kHdrOff; }
+        else if (lane <= (uint32_t)kZW) { nb = S.seg_bits[lane - 1]; src = (lane - 1) * image_words; }
+        else if (lane == (uint32_t)kZW + 1) { nb = S.eob >> 16; src = kEobOff; }
+        const bool ovf = __any_sync(0xffffffffu, nb == 0xffffffffu);
+        if (ovf) nb = 0;
+        uint32_t incl = nb;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += x; }
+        uint32_t dst = incl - nb;
+        const uint32_t end_bits = __shfl_sync(0xffffffffu, incl, kZW + 1);
+        const uint32_t z_bytes = (end_bits + 7) / 8 + 8;                 // the member with a dynamic block
+        if (lane == (uint32_t)kZW + 2) { nb = 64; src = kTailOff; dst = (z_bytes - 8) * 8; }
+        S.pdst[lane] = dst; S.pnb[lane] = nb; S.psrc[lane] = src;
+        S.pend[lane] = lane < kPieces ? dst + nb : 0xffffffffu;
+        if (lane == 0) { S.z_bytes = z_bytes; S.stored = (ovf || z_bytes - kHdr - 8 >= len + 5) ? 1u : 0u; }
+    } else if (warp == 1) {
+        crc = lane < (uint32_t)kZW ? S.crc_w[lane] : 0u;
+#pragma unroll
+        for (uint32_t j = 0; j < 4; j++) {
+            const uint32_t s = 1u << j;
+            const uint32_t other = __shfl_down_sync(0xffffffffu, crc, s);
+            if ((lane & (2 * s - 1)) == 0 && lane < (uint32_t)kZW) {
+                const uint32_t r0 = (lane + s) * kSeg;
+                const uint32_t right_len = r0 >= len ? 0u : min(s * kSeg, len - r0);
+                crc = (right_len == s * kSeg ? crc_advance_lvl(5 + j, crc) : crc_advance(crc, right_len)) ^ other;
+            }
+        }
+        if (lane == 0) {
+            S.buf[kTailOff] = crc ^ (len == kBgzfIn ? c_crc_init_full : crc_advance(0xffffffffu, len)) ^ 0xffffffffu;
+            S.buf[kTailOff + 1] = len;
+        }
+    }
+    __syncthreads();
+
+    if (S.stored) {     // uniform: would not shrink with this code, a segment outgrew its image, or a byte has no code
+        if (t == 0) *zlen = kOwnCode;
+        return;
+    }
+    const uint32_t z_bytes = S.z_bytes;
+    uint32_t* s32 = reinterpret_cast<uint32_t*>(slot);
+    // ---- join: output word j is bits [32 j, 32 j + 32) of the member; the first piece that ends behind bit 32 j by
+    //      binary search (pend is ascending, padded to 32 entries), then along the pieces until the word is full
+    const uint32_t n_words = (z_bytes + 3) / 4;
+    for (uint32_t j = t; j < n_words; j += kZT) {
+        const uint32_t B = j * 32u;
+        uint32_t p = 0;
+#pragma unroll
+        for (uint32_t s = 16; s; s >>= 1) if (S.pend[p + s - 1] <= B) p += s;
+        uint32_t v = 0;
+        while (p < kPieces) {
+            const uint32_t d = S.pdst[p];
+            if (d >= B + 32u) break;
+            const uint32_t n = S.pnb[p];
+            if (n) {
+                const uint32_t o = d <= B ? B - d : 0u;       // the piece's first bit wanted
+                const uint32_t k = o >> 5;
+                const uint32_t* w = S.buf + S.psrc[p] + k;
+                const uint32_t lo = w[0], hi = (k + 1u) * 32u < n ? w[1] : 0u;     // what lies behind a piece's bits is not zero
+                const uint32_t x = __funnelshift_r(lo, hi, o & 31u);
+                v |= d <= B ? x : x << (d - B);
+            }
+            if (d + n >= B + 32u) break;
+            p++;
+        }
+        if (j == 4) v |= (z_bytes - 1u) & 0xffffu;            // BSIZE
+        s32[j] = v;
+    }
+    if (t == 0) *zlen = z_bytes;
+}
+
+// A block with a Huffman code of its own, for what k_bgzf left (zlen = kOwnCode): the same passes with per-warp
+// literal histograms in pass 1, the code construction of k_bgzf_code between the passes, one block image.
+__global__ void __launch_bounds__(kZT, 3)
+k_bgzf_own(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const uint64_t* __restrict__ totals, uint32_t nblk_max,
        uint32_t lz, uint8_t* __restrict__ slots0, uint8_t* __restrict__ slots1, uint32_t* __restrict__ zlen0, uint32_t* __restrict__ zlen1) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+    JLP_DYN_SMEM(smem_raw);
     ZShared& S = *reinterpret_cast<ZShared*>(smem_raw);
     const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
     // the grid is sized for the largest batch; the FASTQ byte counts of this one are on the device
@@ -443,6 +995,7 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
     const uint32_t len = (uint32_t)min((uint64_t)kBgzfIn, n_all - (uint64_t)b * kBgzfIn);
     uint8_t* slot = (second ? slots1 : slots0) + (uint64_t)b * kBgzfSlot;
     uint32_t* zlen = (second ? zlen1 : zlen0) + b;
+    if (*zlen != kOwnCode) return;      // uniform
 
     const uint32_t my_off = t * kChunk;
     const uint32_t my_len = my_off >= len ? 0u : min(kChunk, len - my_off);
@@ -454,7 +1007,7 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
         uint4* s4 = reinterpret_cast<uint4*>(S.stage);
         for (uint32_t i = t; i < kStageWords / 4; i += kZT) s4[i] = make_uint4(0, 0, 0, 0);
         for (uint32_t i = t; i < kMaskWords; i += kZT) S.mask[i] = 0;
-        if (t < 256) S.crc_tab[t] = c_crc_tab[t];
+        if (t < 256) { S.crc_tab[0][t] = c_crc_tab[0][t]; S.crc_tab[1][t] = c_crc_tab[1][t]; S.crc_tab[2][t] = c_crc_tab[2][t]; S.crc_tab[3][t] = c_crc_tab[3][t]; }
         if (t < 288) { S.len[t] = 0; S.cnt[t] = 0; }
         if (t < 32) { S.dcnt[t] = 0; S.dlen[t] = 0; }
         if (t < 16) S.bl[t] = 0;
@@ -467,7 +1020,7 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
     // ---- pass 1: histogram of all bytes + chunk CRC + the chunk's newlines
     uint32_t* hist = S.stage + kHistWord0 + warp * 256;
     uint32_t nlm[4] = {0, 0, 0, 0};
-    uint32_t crc = my_len == kChunk ? pass1<true>(in + my_off, my_len, hist, S.crc_tab, nlm) : pass1<false>(in + my_off, my_len, hist, S.crc_tab, nlm);
+    uint32_t crc = my_len == kChunk ? pass1<true, true>(in + my_off, my_len, hist, &S.crc_tab[0][0], nlm) : pass1<false, true>(in + my_off, my_len, hist, &S.crc_tab[0][0], nlm);
     // CRC tree inside the warp: the node at lane covers chunks [t, t + 2s); its right half has right_len bytes
 #pragma unroll
     for (uint32_t j = 0; j < 5; j++) {
@@ -506,31 +1059,7 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
     //      thread t looks at line starts 2t and 2t + 1, a block scan numbers the matches in block order
     uint32_t m_at[2] = {0, 0}, m_len[2] = {0, 0}, m_tok[2] = {0, 0};
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-        const uint32_t k = 2 * t + h;
-        if (k >= kBack && k < n_ls) {
-            const uint32_t i = S.ls[k];
-            if (i < len) {
-                const uint32_t p = S.ls[k - kBack];
-                const uint32_t next = k + 1 < n_ls ? (uint32_t)S.ls[k + 1] - 1u : len;   // the '\n' that ends this line, or the end
-                const uint32_t maxm = min(258u, next - i);
-                // common prefix, 16 bytes per round trip (reads may run up to 19 bytes past the block: the buffers have slack)
-                uint32_t m = 0;
-                while (m < maxm) {
-                    uint32_t a[4], c[4];
-                    load16(in + i + m, a);
-                    load16(in + p + m, c);
-                    uint32_t same = 16;
-#pragma unroll
-                    for (int j = 3; j >= 0; j--) { const uint32_t x = a[j] ^ c[j]; if (x) same = 4 * j + (((uint32_t)__ffs(x) - 1u) >> 3); }
-                    m += same;
-                    if (same < 16) break;
-                }
-                m = min(m, maxm);
-                if (m >= 4 && i - p <= 32768u) { m_at[h] = i; m_len[h] = m; m_tok[h] = match_token(m, i - p); }
-            }
-        }
-    }
+    for (int h = 0; h < 2; h++) find_match(in, len, S.ls, n_ls, 2 * t + h, m_at[h], m_len[h], m_tok[h]);
     uint32_t total_m;
     uint32_t mj = block_scan((m_tok[0] ? 1u : 0u) + (m_tok[1] ? 1u : 0u), S.scan_tmp, total_m);
 #pragma unroll
@@ -582,6 +1111,7 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
     if (my_cnt) {
         const uint32_t key = my_cnt << 9 | t;
         uint32_t rank = 0;
+#pragma unroll 4
         for (uint32_t q = 0; q < n_active; q++) rank += S.w_int[q] < key ? 1u : 0u;
         S.sorted[rank] = (uint16_t)t;
         S.sw[rank] = my_cnt;
@@ -629,6 +1159,7 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
             const uint32_t pat = l * 0x01010101u;
             const uint32_t* lw = reinterpret_cast<const uint32_t*>(S.len);
             uint32_t same = 0;
+#pragma unroll 4
             for (uint32_t j = 0; j < t / 4; j++) same += __popc(__vcmpeq4(lw[j], pat));
             same += __popc(__vcmpeq4(lw[t / 4], pat) & ((1u << (8 * (t & 3))) - 1u));
             S.code[t] = (uint16_t)rev_bits(first_code(S.bl, l) + same / 8, l);
@@ -647,13 +1178,26 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
     const uint32_t hlit = S.hlit, n_seq = hlit + S.hdist;
     auto seq = [&](uint32_t i) -> uint32_t { return i < hlit ? S.len[i] : S.dlen[i - hlit]; };
     RunTok rt{0, 0, 0, 0, 0, 0};
-    bool run_start = false;
+    // where the runs start, one bit per position (n_seq <= 316 < kZT): a run ends where the next one starts, so no thread
+    // has to walk its run (the zero lengths of the bytes FASTQ never uses make runs of a hundred and more)
+    const uint32_t v_seq = t < n_seq ? seq(t) : 0u;
+    const bool run_start = t < n_seq && (t == 0 || seq(t - 1) != v_seq);
+    {
+        const uint32_t bal = __ballot_sync(0xffffffffu, run_start);
+        if (lane == 0) S.run_bal[warp] = bal;
+    }
+    __syncthreads();
     if (t < n_seq) {
-        const uint32_t v = seq(t);
-        run_start = t == 0 || seq(t - 1) != v;
+        const uint32_t v = v_seq;
         if (run_start) {
-            uint32_t run = 1;
-            while (t + run < n_seq && seq(t + run) == v) run++;
+            uint32_t next = n_seq;
+            uint32_t m = lane == 31 ? 0u : S.run_bal[warp] & (0xffffffffu << (lane + 1u));
+            for (uint32_t w = warp; ; ) {
+                if (m) { next = min(n_seq, w * 32u + (uint32_t)__ffs(m) - 1u); break; }
+                if (++w >= kZW) break;
+                m = S.run_bal[w];
+            }
+            const uint32_t run = next - t;
             rt = run_tokens(v, run);
             if (v == 0) {
                 if (rt.n_big) atomicAdd(&S.cl_cnt[18], rt.n_big);
@@ -756,11 +1300,11 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
         const uint32_t bitpos = hdr_bits + (__shfl_sync(0xffffffffu, excl, 0) & 0xfffffu);
         const uint32_t seg_len = seg_off >= len ? 0u : min(kSeg, len - seg_off);
         if (lz) {
-            if (seg_len == kSeg) pack_warp<true, true>(S, in + seg_off, seg_off, seg_len, S.stage, bitpos, m_first, lane);
-            else if (seg_len) pack_warp<false, true>(S, in + seg_off, seg_off, seg_len, S.stage, bitpos, m_first, lane);
+            if (seg_len == kSeg) pack_warp<true, true>(S, in + seg_off, seg_off, seg_len, S.stage, bitpos, 0xffffffffu, m_first, lane);
+            else if (seg_len) pack_warp<false, true>(S, in + seg_off, seg_off, seg_len, S.stage, bitpos, 0xffffffffu, m_first, lane);
         } else {
-            if (seg_len == kSeg) pack_warp<true, false>(S, in + seg_off, seg_off, seg_len, S.stage, bitpos, m_first, lane);
-            else if (seg_len) pack_warp<false, false>(S, in + seg_off, seg_off, seg_len, S.stage, bitpos, m_first, lane);
+            if (seg_len == kSeg) pack_warp<true, false>(S, in + seg_off, seg_off, seg_len, S.stage, bitpos, 0xffffffffu, m_first, lane);
+            else if (seg_len) pack_warp<false, false>(S, in + seg_off, seg_off, seg_len, S.stage, bitpos, 0xffffffffu, m_first, lane);
         }
     }
     if (t == 0) {
@@ -778,7 +1322,6 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
     uint4* o4 = reinterpret_cast<uint4*>(slot);
     for (uint32_t i = t; i < (z_bytes + 15) / 16; i += kZT) o4[i] = s4[i];
 }
-
 // exclusive prefix of the member sizes of one file (one CTA per file); the file's compressed size into totals[2 + file]
 __global__ void __launch_bounds__(1024)
 k_bgzf_scan(const uint32_t* __restrict__ zlen0, const uint32_t* __restrict__ zlen1, uint64_t* __restrict__ zoff0,
@@ -853,7 +1396,12 @@ cudaError_t bgzf_init() {
             for (int q = 0; q < 32; q++) if ((v >> q) & 1u) r ^= adv[j - 1][q];
             adv[j][i] = r;
         }
-    cudaError_t e = cudaMemcpyToSymbol(c_crc_tab, tab, sizeof tab);
+    uint32_t tab4[4][256];
+    for (uint32_t i = 0; i < 256; i++) {
+        tab4[0][i] = tab[i];
+        for (int k = 1; k < 4; k++) tab4[k][i] = (tab4[k - 1][i] >> 8) ^ tab[tab4[k - 1][i] & 0xffu];
+    }
+    cudaError_t e = cudaMemcpyToSymbol(c_crc_tab, tab4, sizeof tab4);
     if (e != cudaSuccess) return e;
     e = cudaMemcpyToSymbol(c_crc_adv, adv, sizeof adv);
     if (e != cudaSuccess) return e;
@@ -877,16 +1425,25 @@ cudaError_t bgzf_init() {
             }
     e = cudaMemcpyToSymbol(g_crc_lvl, lvl, sizeof lvl);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_bgzf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZShared));
+    e = cudaFuncSetAttribute(k_bgzf_code, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZShared));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_bgzf_own, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZShared));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_bgzf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZMain));
 }
 
 cudaError_t launch_bgzf(const uint8_t* in0, const uint8_t* in1, uint64_t* totals, uint32_t nblk_max, bool matches, uint8_t* slots0,
                         uint8_t* slots1, uint32_t* zlen0, uint32_t* zlen1, uint64_t* zoff0, uint64_t* zoff1, uint8_t* out0,
-                        uint8_t* out1, cudaStream_t s) {
-    if (nblk_max) k_bgzf<<<2 * nblk_max, kZT, sizeof(ZShared), s>>>(in0, in1, totals, nblk_max, matches ? 1u : 0u, slots0, slots1, zlen0, zlen1);
-    k_bgzf_scan<<<2, 1024, 0, s>>>(zlen0, zlen1, zoff0, zoff1, totals);
+                        uint8_t* out1, uint8_t* codes, cudaStream_t s) {
+    ZCode* zc = reinterpret_cast<ZCode*>(codes);
+    if (nblk_max) {
+        JLP_LAUNCH(k_bgzf_code, 2, kZT, sizeof(ZShared), s, in0, in1, totals, matches ? 1u : 0u, zc);
+        JLP_LAUNCH(k_bgzf, 2 * nblk_max, kZT, sizeof(ZMain), s, in0, in1, totals, nblk_max, matches ? 1u : 0u, zc, slots0, slots1, zlen0, zlen1);
+        JLP_LAUNCH(k_bgzf_own, 2 * nblk_max, kZT, sizeof(ZShared), s, in0, in1, totals, nblk_max, matches ? 1u : 0u, slots0, slots1, zlen0, zlen1);
+    }
+    JLP_LAUNCH(k_bgzf_scan, 2, 1024, 0, s, zlen0, zlen1, zoff0, zoff1, totals);
     if (nblk_max)
-        k_bgzf_gather<<<2 * nblk_max, 256, 0, s>>>(slots0, slots1, zlen0, zlen1, zoff0, zoff1, totals, nblk_max, out0, out1);
+        JLP_LAUNCH(k_bgzf_gather, 2 * nblk_max, 256, 0, s, slots0, slots1, zlen0, zlen1, zoff0, zoff1, totals, nblk_max, out0, out1);
     return cudaGetLastError();
 }
 

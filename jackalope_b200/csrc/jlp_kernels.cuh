@@ -117,13 +117,16 @@ constexpr uint32_t kScanBlock = 1024;
 // memory, as launch_scan leaves them); the compressed sizes come back in totals[2..3].  Block b of a file is
 // compressed into slots + b * kBgzfSlot, then gathered to out + (sum of the sizes before it).  nblk_max sizes
 // the grids: an upper bound of the blocks of either file.  `matches`: also look for length/distance pairs (a line's
-// common prefix with the line four lines earlier); smaller output, about twice the kernel time.
+// common prefix with the line four lines earlier); smaller output, more kernel time.  `codes`: kBgzfCodeBytes of
+// device scratch of this launch's own (the Huffman codes of the two files, built from their first blocks).
 constexpr uint32_t kBgzfIn = 0xff00;     // input bytes per block, htslib's BGZF_BLOCK_SIZE
 constexpr uint32_t kBgzfSlot = 65536;    // a BGZF block never exceeds 64 KiB
+constexpr uint32_t kBgzfCodeBytes = 4096;
+constexpr int kBgzfLaunches = 5;         // kernels per launch_bgzf
 cudaError_t bgzf_init();
 cudaError_t launch_bgzf(const uint8_t* in0, const uint8_t* in1, uint64_t* totals, uint32_t nblk_max, bool matches, uint8_t* slots0,
                         uint8_t* slots1, uint32_t* zlen0, uint32_t* zlen1, uint64_t* zoff0, uint64_t* zoff1, uint8_t* out0,
-                        uint8_t* out1, cudaStream_t s);
+                        uint8_t* out1, uint8_t* codes, cudaStream_t s);
 
 }  // namespace jlp
 #endif

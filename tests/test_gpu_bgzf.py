@@ -96,6 +96,10 @@ CASES = {
     "empty_lines": b"\n" * 5000 + b"x\n\n" * 3000,
     # many distinct rare bytes before each line start: literal codes of 12+ bits next to a match (the lane's bits pass 64)
     "long_codes_before_matches": b"".join(bytes(np.random.default_rng(i).integers(128, 256, 45, dtype=np.uint8)) + b"\n" + b"PREFIX-%06d" % (i * 7919 % 10**6) + b"A" * (i % 5) + b"\n" + b"qq\n" + b"rr\n" for i in range(1500)),
+    # the codes of a call come from its first block: bytes that block does not hold (outside the printable range, which
+    # always gets a code), and blocks the first block's code fits badly, fall back to a code of their own
+    "late_binary_bytes": fastq_like(0xff00 + 5000, 8) + bytes(np.random.default_rng(9).integers(0, 32, 70000, dtype=np.uint8)) + fastq_like(30000, 10),
+    "nonstationary": b"A" * 0xff00 + fastq_like(2 * 0xff00, 11) + bytes(np.random.default_rng(12).integers(0, 256, 0xff00, dtype=np.uint8)) + b"\n".join(b"line %d" % (i % 13) for i in range(9000)),
     "chunk_tail_127": fastq_like(0xff00 + 127, 6),
     "chunk_tail_129": fastq_like(2 * 0xff00 + 129, 7),
 }
