@@ -63,22 +63,18 @@ constexpr uint32_t kStageWords = kStageBytes / 4;
 constexpr uint32_t kHistWord0 = kStageWords - kZW * 256;   // the histograms alias the end of the image
 constexpr uint32_t kLsCap = 1024;        // line starts kept per block (two per thread)
 constexpr uint32_t kMCap = 1024;         // matches kept per block
+constexpr uint32_t kSlots = 2;           // k_bgzf: matches kept per chunk (kSlots * kZT = kMCap)
 constexpr uint32_t kBack = 4;            // a line is compared with the line this many lines earlier
 constexpr uint32_t kMaskWords = kBgzfIn / 32 + 2;
-// k_bgzf: the image of warp w's segment is words [w * kRegionWords, (w + 1) * kRegionWords) of ZMain::buf; behind the
-// images the other pieces of a member: the header words, the end-of-block code, CRC-32 and ISIZE
-constexpr uint32_t kRegionWords = 768;     // in a full block; the segments of a shorter one share the same space
+constexpr uint32_t kImageBytes = 48 * 1024;   // k_bgzf: the image of a member in shared memory
+constexpr uint32_t kImageWords = kImageBytes / 4;
 constexpr uint32_t kHdrWords = 160;      // 18 bytes of member header + at most 4498 bits of block header
-constexpr uint32_t kHdrOff = kZW * kRegionWords;
-constexpr uint32_t kEobOff = kHdrOff + kHdrWords;
-constexpr uint32_t kTailOff = kEobOff + 1;
-constexpr uint32_t kBufWords = kTailOff + 3;
-constexpr uint32_t kPieces = kZW + 3;
+constexpr uint32_t kNoCode = 4096u << 16;    // more bits than a chunk of coded bytes can take
 constexpr uint32_t kOwnCode = 0xffffffffu;   // in zlen[]: k_bgzf leaves this block to k_bgzf_own
 
 // what k_bgzf_code leaves for k_bgzf, one per file
 struct ZCode {
-    uint32_t ctab[256];        // literal: code (bit-reversed, LSB first) | length << 16
+    uint32_t ctab[256];        // literal: code (bit-reversed, LSB first) | length << 16; kNoCode: the code has no word for it
     uint32_t lcode[32];        // length symbol 257 + i, likewise
     uint32_t dcode[32];        // distance symbol i
     uint32_t eob;              // end of block
@@ -87,14 +83,14 @@ struct ZCode {
     uint32_t hdr[kHdrWords];   // the member header (BSIZE left zero) and the dynamic block's header
 };
 static_assert(2 * sizeof(ZCode) <= kBgzfCodeBytes, "launch_bgzf's code scratch");
-static_assert(kBufWords % 4 == 0, "buf is cleared and read as uint4");
+static_assert(kHdrWords % 4 == 0 && kHdrWords < kHistWord0, "the header words are copied, the rest of the image is cleared as uint4");
 
 __constant__ uint32_t c_crc_tab[4][256];  // slicing by four: [k][b] = the register after byte b and k zero bytes
 __constant__ uint32_t c_crc_adv[17][32];   // operator "advance the CRC register over 2^j zero bytes", by bit image
 __constant__ uint32_t c_crc_init_full;     // the initial register 0xffffffff advanced over a full block
 // the same operators for 2^7 .. 2^15 zero bytes (the sizes a full block's CRC tree combines) as 4 x 256-entry tables:
 // advance(v) = T[0][v & 255] ^ T[1][v >> 8 & 255] ^ T[2][v >> 16 & 255] ^ T[3][v >> 24]
-__device__ uint32_t g_crc_lvl[9][4][256];
+__device__ uint32_t g_crc_lvl[10][4][256];     // [9]: 3840 zero bytes, the last segment of a full block
 
 // scratch of one Huffman construction
 struct HuffScratch {
@@ -145,18 +141,16 @@ static_assert(offsetof(ZShared, mbits) % 8 == 0, "mbits alignment");
 
 // shared memory of k_bgzf
 struct ZMain {
-    uint32_t buf[kBufWords];              // 16 segment images, header words, end-of-block code, CRC-32, ISIZE, a zero word
-    uint64_t mbits[kMCap];                // the matches in block order: bits | bit count << 56
+    uint32_t image[kImageWords];          // the member: the header words, then the bits of every chunk at their final place
+    uint64_t mbits[kMCap];                // the matches that start in chunk t, in order, from kSlots * t: bits | bit count << 56
     uint32_t mask[kMaskWords];            // bit q + 1: byte q of the block is covered by a match
     uint32_t crc_tab[4][256];
     uint32_t ctab[256];
     uint32_t lcode[32], dcode[32];
+    uint32_t cbits[kZT];                  // per chunk: the bits it sends
     uint32_t scan_tmp[kZW + 1];
     uint32_t crc_w[kZW];
-    uint32_t wm[kZW];                     // matches that start in each warp's segment
-    uint32_t seg_bits[kZW];               // bits of each warp's image; 0xffffffff: it did not fit
-    uint32_t pdst[32], pend[32], pnb[32], psrc[32];   // the pieces of the member: first bit, end, bits, first word in buf
-    uint32_t eob, hdr_bits, z_bytes, stored;
+    uint32_t eob, hdr_bits, miss;
     uint16_t ls[kLsCap + 1];              // line starts, ascending; ls[0] = 0
 };
 static_assert(sizeof(ZMain) <= 75 * 1024, "three CTAs per SM");
@@ -387,12 +381,13 @@ __device__ __forceinline__ void load16(const uint8_t* a, uint32_t (&x)[4]) {
 }
 
 // pass 1 of a thread: its 128 contiguous bytes, 16 at a time from global memory -> chunk CRC, the chunk's newlines as
-// one bit per byte and (HIST, k_bgzf_code) the warp histogram of all bytes (the bytes a match covers are taken out
-// again when the match is found)
-template <bool FULL, bool HIST>
+// one bit per byte; HIST (k_bgzf_code, k_bgzf_own): the warp histogram of all bytes (the bytes a match covers are
+// taken out again when the match is found); SIZE (k_bgzf): the bits the chunk's bytes take as literals (a byte without
+// a code counts kNoCode >> 16 of them)
+template <bool FULL, bool HIST, bool SIZE = false>
 __device__ __forceinline__ uint32_t pass1(const uint8_t* chunk, uint32_t my_len, uint32_t* hist, const uint32_t* tab,
-                                          uint32_t (&nlm)[4]) {
-    uint32_t reg = 0;
+                                          uint32_t (&nlm)[4], const uint32_t* ctab = nullptr, uint32_t* lit_bits = nullptr) {
+    uint32_t reg = 0, bits = 0;
     uint4 d[8];
 #pragma unroll
     for (int k = 0; k < 8; k++)
@@ -418,11 +413,13 @@ __device__ __forceinline__ uint32_t pass1(const uint8_t* chunk, uint32_t my_len,
                 if (FULL || (uint32_t)i < my_len) {
                     const uint32_t b = (w[q] >> (8 * r)) & 0xffu;
                     if (HIST) atomicAdd(&hist[b], 1u);
+                    if (SIZE) bits += ctab[b] >> 16;
                     if (!whole) reg = tab[(reg ^ b) & 0xffu] ^ (reg >> 8);
                 }
             }
         }
     }
+    if (SIZE) *lit_bits = bits;
     if (!FULL) {
 #pragma unroll
         for (int j = 0; j < 4; j++)
@@ -431,14 +428,11 @@ __device__ __forceinline__ uint32_t pass1(const uint8_t* chunk, uint32_t my_len,
     return reg;
 }
 
-// pass 2 of a warp: its segment again, 4 bytes per lane and 128 contiguous bytes per round, packed from bit 0 of the
-// warp's image.  A byte a match covers sends nothing, except the first one, which sends the match.
-// Returns the bit position behind the segment, or 0xffffffff when the segment outgrew the image or holds a byte that
-// has no code (uniform inside the warp).
-template <bool FULL, bool LZ, class SH>
-__device__ __forceinline__ uint32_t pack_warp(const SH& S, const uint8_t* seg, uint32_t seg_off, uint32_t seg_len, uint32_t* stage,
-                                              uint32_t base, uint32_t image_bits, uint32_t cursor, uint32_t lane) {
-    bool miss = false;
+// pass 2 of a warp of k_bgzf_own: its segment again, 4 bytes per lane and 128 contiguous bytes per round.  A byte a
+// match covers sends nothing, except the first one, which sends the match.
+template <bool FULL, bool LZ>
+__device__ __forceinline__ void pack_warp(const ZShared& S, const uint8_t* seg, uint32_t seg_off, uint32_t seg_len, uint32_t* stage,
+                                          uint32_t base, uint32_t cursor, uint32_t lane) {
     const uint32_t* g = reinterpret_cast<const uint32_t*>(seg) + lane;
     for (uint32_t r0 = 0; r0 < 32; r0 += 4) {
         if (!FULL && r0 * 128u >= seg_len) break;
@@ -454,8 +448,6 @@ __device__ __forceinline__ uint32_t pack_warp(const SH& S, const uint8_t* seg, u
             const uint32_t q = seg_off + off;
             const uint32_t mb = LZ && (FULL || nv) ? __funnelshift_r(S.mask[q >> 5], S.mask[(q >> 5) + 1], q & 31u) & 0x1fu : 0u;
             uint32_t e0 = S.ctab[w[u] & 0xffu], e1 = S.ctab[(w[u] >> 8) & 0xffu], e2 = S.ctab[(w[u] >> 16) & 0xffu], e3 = S.ctab[w[u] >> 24];
-            if (FULL) miss |= !(e0 && e1 && e2 && e3);      // a byte the code has no word for
-            else miss |= (nv >= 1 && !e0) || (nv >= 2 && !e1) || (nv >= 3 && !e2) || (nv >= 4 && !e3);
             if (!FULL) { if (nv < 1) e0 = 0; if (nv < 2) e1 = 0; if (nv < 3) e2 = 0; if (nv < 4) e3 = 0; }
             if (LZ && (mb & 0x1eu)) { if (mb & 2u) e0 = 0; if (mb & 4u) e1 = 0; if (mb & 8u) e2 = 0; if (mb & 16u) e3 = 0; }
             const uint32_t l0 = e0 >> 16, l1 = e1 >> 16, l2 = e2 >> 16, l3 = e3 >> 16;
@@ -480,10 +472,8 @@ __device__ __forceinline__ uint32_t pack_warp(const SH& S, const uint8_t* seg, u
             uint32_t incl = l;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += x; }
-            const uint32_t round_bits = __shfl_sync(0xffffffffu, incl, 31);
-            if (base + round_bits + 128u > image_bits) return 0xffffffffu;     // a lane's bits touch at most four words
             const uint32_t at = base + incl - l;
-            base += round_bits;
+            base += __shfl_sync(0xffffffffu, incl, 31);
             const uint32_t i = at >> 5, sh = at & 31;
             const uint32_t x0 = (uint32_t)c, x1 = (uint32_t)(c >> 32);
             if (l) atomicOr(&stage[i], x0 << sh);
@@ -492,7 +482,57 @@ __device__ __forceinline__ uint32_t pack_warp(const SH& S, const uint8_t* seg, u
             if (LZ && sh + l > 96) atomicOr(&stage[i + 3], __funnelshift_l(top, 0u, sh));
         }
     }
-    return __any_sync(0xffffffffu, miss) ? 0xffffffffu : base;
+}
+
+// pass 2 of a thread of k_bgzf: its chunk again, byte after byte into a 64-bit window that is emptied, a word at a time,
+// into the member's image at the chunk's own bit position (the first and the last word are shared with the
+// neighbours: OR-ed).  A byte a match covers sends nothing, except the first one, which sends the match.
+template <bool FULL, bool LZ>
+__device__ __forceinline__ void encode_chunk(const ZMain& S, uint32_t* image, const uint8_t* chunk, uint32_t my_off, uint32_t my_len,
+                                             uint32_t bitpos, uint32_t cursor) {
+    uint64_t acc = 0;
+    uint32_t fill = bitpos & 31u;
+    uint32_t* wp = image + (bitpos >> 5);
+    // n <= 32 bits behind the fill < 32 bits waiting in the window
+    auto put = [&](uint32_t v, uint32_t n) {
+        acc |= (uint64_t)v << fill;
+        fill += n;
+        if (fill >= 32) { atomicOr(wp, (uint32_t)acc); wp++; acc >>= 32; fill -= 32; }
+    };
+    uint4 nx = __ldg(reinterpret_cast<const uint4*>(chunk));
+#pragma unroll 1
+    for (uint32_t k = 0; k < 8; k++) {
+        if (!FULL && 16u * k >= my_len) break;
+        const uint4 d = nx;
+        if (k + 1 < 8 && (FULL || 16u * (k + 1) < my_len)) nx = __ldg(reinterpret_cast<const uint4*>(chunk) + k + 1);   // in flight while d is coded
+        const uint32_t w[4] = {d.x, d.y, d.z, d.w};
+        // bit 0: the byte before these sixteen is covered; bits 1..16: the sixteen
+        const uint32_t q0 = my_off + 16u * k;
+        const uint32_t mb16 = LZ ? __funnelshift_r(S.mask[q0 >> 5], S.mask[(q0 >> 5) + 1], q0 & 31u) : 0u;
+#pragma unroll
+        for (uint32_t q = 0; q < 4; q++) {
+            const uint32_t off = 16u * k + 4u * q;
+            const uint32_t nv = FULL ? 4u : (off >= my_len ? 0u : min(4u, my_len - off));
+            const uint32_t mb = (mb16 >> (4u * q)) & 0x1fu;
+            uint32_t e0 = S.ctab[w[q] & 0xffu], e1 = S.ctab[(w[q] >> 8) & 0xffu], e2 = S.ctab[(w[q] >> 16) & 0xffu], e3 = S.ctab[w[q] >> 24];
+            if (!FULL) { if (nv < 1) e0 = 0; if (nv < 2) e1 = 0; if (nv < 3) e2 = 0; if (nv < 4) e3 = 0; }
+            if (LZ && (mb & 0x1eu)) { if (mb & 2u) e0 = 0; if (mb & 4u) e1 = 0; if (mb & 8u) e2 = 0; if (mb & 16u) e3 = 0; }
+            const uint32_t l0 = e0 >> 16, l1 = e1 >> 16, l2 = e2 >> 16, l3 = e3 >> 16;
+            const uint32_t c01 = (e0 & 0xffffu) | (e1 & 0xffffu) << l0, l01 = l0 + l1;
+            const uint32_t c23 = (e2 & 0xffffu) | (e3 & 0xffffu) << l2, l23 = l2 + l3;
+            if (l01 + l23 <= 32) put(c01 | c23 << l01, l01 + l23);        // l01 <= 30
+            else { put(c01, l01); put(c23, l23); }
+            // a match starts at a covered byte whose predecessor is not covered (the byte before a line start is a '\n',
+            // which no match covers); everything after it in this word is covered, so its bits come last
+            if (LZ && ((mb >> 1) & ~mb & 0xfu) && (FULL || nv)) {
+                const uint64_t mbv = S.mbits[cursor++];
+                const uint32_t hn = (uint32_t)(mbv >> 56);
+                put((uint32_t)mbv, min(hn, 32u));
+                if (hn > 32) put((uint32_t)(mbv >> 32) & 0x00ffffffu, hn - 32);
+            }
+        }
+    }
+    if (fill) atomicOr(wp, (uint32_t)acc);
 }
 
 // The run of equal code lengths starting at a position, as the tokens of RFC 1951 section 3.2.7:
@@ -769,7 +809,7 @@ k_bgzf_code(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, co
     __syncthreads();
     // ---- hand over
     const uint32_t hdr_bits = S.hdr_fixed_bits + total;
-    if (t < 256) Z.ctab[t] = S.len[t] ? (uint32_t)S.code[t] | (uint32_t)S.len[t] << 16 : 0u;
+    if (t < 256) Z.ctab[t] = S.len[t] ? (uint32_t)S.code[t] | (uint32_t)S.len[t] << 16 : kNoCode;
     if (t < 32) {
         Z.lcode[t] = t < kNLit - 257 && S.len[257 + t] ? (uint32_t)S.code[257 + t] | (uint32_t)S.len[257 + t] << 16 : 0u;
         Z.dcode[t] = t < kNDist && S.dlen[t] ? (uint32_t)S.dcode[t] | (uint32_t)S.dlen[t] << 16 : 0u;
@@ -799,32 +839,28 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
 
     const uint32_t my_off = t * kChunk;
     const uint32_t my_len = my_off >= len ? 0u : min(kChunk, len - my_off);
-    // the segments of a short block share the whole image space
-    const uint32_t image_words = (kHdrOff / ((len + kSeg - 1) / kSeg)) & ~3u;
 
-    // ---- clear the segment images and the match mask, fetch the codes and the header
+    // ---- the image: the header words (the same for every block), zeros behind them; the match mask; the codes
     {
-        uint4* s4 = reinterpret_cast<uint4*>(S.buf);
-        for (uint32_t i = t; i < kHdrOff / 4; i += kZT) s4[i] = make_uint4(0, 0, 0, 0);
+        uint4* s4 = reinterpret_cast<uint4*>(S.image);
+        for (uint32_t i = kHdrWords / 4 + t; i < kImageWords / 4; i += kZT) s4[i] = make_uint4(0, 0, 0, 0);
+        if (t < kHdrWords) S.image[t] = __ldg(&Z.hdr[t]);
         if (lz) for (uint32_t i = t; i < kMaskWords; i += kZT) S.mask[i] = 0;
         if (t < 256) {
             S.crc_tab[0][t] = c_crc_tab[0][t]; S.crc_tab[1][t] = c_crc_tab[1][t]; S.crc_tab[2][t] = c_crc_tab[2][t]; S.crc_tab[3][t] = c_crc_tab[3][t];
             S.ctab[t] = __ldg(&Z.ctab[t]);
         }
-        if (t < kHdrWords) S.buf[kHdrOff + t] = __ldg(&Z.hdr[t]);
         if (t < 32) { S.lcode[t] = __ldg(&Z.lcode[t]); S.dcode[t] = __ldg(&Z.dcode[t]); }
-        if (t < kZW) S.wm[t] = 0;
-        if (t == 0) {
-            const uint32_t eob = __ldg(&Z.eob);
-            S.eob = eob; S.hdr_bits = __ldg(&Z.hdr_bits); S.ls[0] = 0;
-            S.buf[kEobOff] = eob & 0xffffu; S.buf[kTailOff + 2] = 0;
-        }
+        if (t == 0) { S.eob = __ldg(&Z.eob); S.hdr_bits = __ldg(&Z.hdr_bits); S.ls[0] = 0; S.miss = 0; }
     }
     __syncthreads();
-    // ---- pass 1: chunk CRC + the chunk's newlines
+    // ---- pass 1: chunk CRC, the chunk's newlines, the bits of its bytes as literals
     uint32_t nlm[4] = {0, 0, 0, 0};
-    uint32_t crc = my_len == kChunk ? pass1<true, false>(in + my_off, my_len, nullptr, &S.crc_tab[0][0], nlm)
-                                    : pass1<false, false>(in + my_off, my_len, nullptr, &S.crc_tab[0][0], nlm);
+    uint32_t lit_bits = 0;
+    uint32_t crc = my_len == kChunk ? pass1<true, false, true>(in + my_off, my_len, nullptr, &S.crc_tab[0][0], nlm, S.ctab, &lit_bits)
+                                    : pass1<false, false, true>(in + my_off, my_len, nullptr, &S.crc_tab[0][0], nlm, S.ctab, &lit_bits);
+    if (lit_bits >= (kNoCode >> 16)) { S.miss = 1; lit_bits = 0; }       // a byte the code has no word for
+    S.cbits[t] = lit_bits;
     // CRC tree inside the warp: the node at lane covers chunks [t, t + 2s); its right half has right_len bytes
 #pragma unroll
     for (uint32_t j = 0; j < 5; j++) {
@@ -857,73 +893,73 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
             }
         }
         __syncthreads();
-        const uint32_t n_ls = min(min(total_nl, kLsCap) + 1, 2u * kZT);   // entries of S.ls in use (a last one may equal len: no line there)
-        // ---- matches: thread t looks at line starts 2t and 2t + 1, a block scan numbers the matches in block order
-        uint32_t m_at[2] = {0, 0}, m_len[2] = {0, 0}, m_tok[2] = {0, 0};
-#pragma unroll
-        for (int h = 0; h < 2; h++) find_match(in, len, S.ls, n_ls, 2 * t + h, m_at[h], m_len[h], m_tok[h]);
-        uint32_t total_m;
-        uint32_t mj = block_scan((m_tok[0] ? 1u : 0u) + (m_tok[1] ? 1u : 0u), S.scan_tmp, total_m);
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            if (m_tok[h] && mj < kMCap) {
-                const uint32_t i = m_at[h];
+        // the line starts inside this chunk: first and last index (a line starts behind a newline, so the newline before the
+        // chunk counts and one in its last byte does not)
+        const bool prev_nl = t > 0 && my_len && __ldg(in + my_off - 1) == '\n';
+        const bool last_nl = my_len && __ldg(in + my_off + my_len - 1) == '\n';
+        const uint32_t n_ls = min(total_nl, kLsCap) + 1;   // entries of S.ls in use (a last one may equal len: no line there)
+        const uint32_t k_lo = max(nl_before + (prev_nl ? 0u : 1u), kBack);
+        const uint32_t k_hi = min(nl_before + my_nl + 1u - (last_nl ? 1u : 0u), n_ls);      // behind the last
+        // ---- matches: every thread looks at the line starts of its chunk -- the thread that will code them -- and keeps
+        //      up to kSlots matches, in order, in slots of its own
+        uint32_t slot = 0;
+        for (uint32_t k = k_lo; k < k_hi; k++) {
+            uint32_t i = 0, m = 0, tok = 0;
+            find_match(in, len, S.ls, n_ls, k, i, m, tok);
+            if (tok && slot < kSlots) {
                 uint32_t hn;
-                const uint64_t hv = match_bits(S, m_tok[h], hn);
-                S.mbits[mj] = hv | (uint64_t)hn << 56;
-                atomicAdd(&S.wm[i / kSeg], 1u);
-                // its bytes are marked: bits [i + 1, i + m + 1) of the mask
-                uint32_t lo = i + 1, hi = i + m_len[h] + 1;
+                const uint64_t hv = match_bits(S, tok, hn);
+                S.mbits[kSlots * t + slot++] = hv | (uint64_t)hn << 56;
+                atomicAdd(&S.cbits[t], hn);
+                // its bytes no longer send their literals ...
+                for (uint32_t q0 = 0; q0 < m; q0 += 16) {
+                    uint32_t a[4];
+                    load16(in + i + q0, a);
+#pragma unroll
+                    for (int j = 0; j < 16; j++)
+                        if (q0 + j < m) atomicSub(&S.cbits[(i + q0 + j) / kChunk], S.ctab[(a[j >> 2] >> (8 * (j & 3))) & 0xffu] >> 16);
+                }
+                // ... and are marked: bits [i + 1, i + m + 1) of the mask
+                uint32_t lo = i + 1, hi = i + m + 1;
                 while (lo < hi) {
                     const uint32_t wi = lo >> 5, b0 = lo & 31u, n = min(32u - b0, hi - lo);
                     atomicOr(&S.mask[wi], (n == 32 ? 0xffffffffu : ((1u << n) - 1u)) << b0);
                     lo += n;
                 }
             }
-            if (m_tok[h]) mj++;
         }
         __syncthreads();
     }
 
-    // ---- pass 2: every warp packs its segment into its own image
-    {
-        const uint32_t seg_off = warp * kSeg;
-        uint32_t m_first = 0;                       // matches before this warp's segment
-        if (lz) for (uint32_t w = 0; w < warp; w++) m_first += S.wm[w];
-        const uint32_t seg_len = seg_off >= len ? 0u : min(kSeg, len - seg_off);
-        uint32_t* image = S.buf + warp * image_words;
-        const uint32_t image_bits = image_words * 32u;
-        uint32_t bits = 0;
-        if (lz) {
-            if (seg_len == kSeg) bits = pack_warp<true, true>(S, in + seg_off, seg_off, seg_len, image, 0u, image_bits, m_first, lane);
-            else if (seg_len) bits = pack_warp<false, true>(S, in + seg_off, seg_off, seg_len, image, 0u, image_bits, m_first, lane);
-        } else {
-            if (seg_len == kSeg) bits = pack_warp<true, false>(S, in + seg_off, seg_off, seg_len, image, 0u, image_bits, m_first, lane);
-            else if (seg_len) bits = pack_warp<false, false>(S, in + seg_off, seg_off, seg_len, image, 0u, image_bits, m_first, lane);
-        }
-        if (lane == 0) S.seg_bits[warp] = bits;
+    // ---- where every chunk's bits go
+    uint32_t total;
+    const uint32_t excl = block_scan(S.cbits[t], S.scan_tmp, total);
+    const uint32_t hdr_bits = S.hdr_bits, eob = S.eob;
+    const uint32_t end_bits = hdr_bits + total + (eob >> 16);
+    const uint32_t z_bytes = (end_bits + 7) / 8 + 8;                 // the member with a dynamic block
+    if (S.miss || z_bytes - kHdr - 8 >= len + 5 || z_bytes > kImageBytes - 16) {     // uniform
+        // a byte without a code, or the block does not shrink with this code: k_bgzf_own takes it
+        if (t == 0) *zlen = kOwnCode;
+        return;
     }
-    __syncthreads();
-
-    // ---- the pieces of the member (warp 0) and the block's CRC (warp 1)
-    if (warp == 0) {
-        uint32_t nb = 0, src = 0;
-        if (lane == 0) { nb = S.hdr_bits; src = kHdrOff; }
-        else if (lane <= (uint32_t)kZW) { nb = S.seg_bits[lane - 1]; src = (lane - 1) * image_words; }
-        else if (lane == (uint32_t)kZW + 1) { nb = S.eob >> 16; src = kEobOff; }
-        const bool ovf = __any_sync(0xffffffffu, nb == 0xffffffffu);
-        if (ovf) nb = 0;
-        uint32_t incl = nb;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += x; }
-        uint32_t dst = incl - nb;
-        const uint32_t end_bits = __shfl_sync(0xffffffffu, incl, kZW + 1);
-        const uint32_t z_bytes = (end_bits + 7) / 8 + 8;                 // the member with a dynamic block
-        if (lane == (uint32_t)kZW + 2) { nb = 64; src = kTailOff; dst = (z_bytes - 8) * 8; }
-        S.pdst[lane] = dst; S.pnb[lane] = nb; S.psrc[lane] = src;
-        S.pend[lane] = lane < kPieces ? dst + nb : 0xffffffffu;
-        if (lane == 0) { S.z_bytes = z_bytes; S.stored = (ovf || z_bytes - kHdr - 8 >= len + 5) ? 1u : 0u; }
-    } else if (warp == 1) {
+    // ---- pass 2: every thread codes its chunk to its place
+    if (my_len) {
+        const uint32_t bitpos = hdr_bits + excl, cursor = kSlots * t;
+        if (lz) {
+            if (my_len == kChunk) encode_chunk<true, true>(S, S.image, in + my_off, my_off, my_len, bitpos, cursor);
+            else encode_chunk<false, true>(S, S.image, in + my_off, my_off, my_len, bitpos, cursor);
+        } else {
+            if (my_len == kChunk) encode_chunk<true, false>(S, S.image, in + my_off, my_off, my_len, bitpos, cursor);
+            else encode_chunk<false, false>(S, S.image, in + my_off, my_off, my_len, bitpos, cursor);
+        }
+    }
+    if (t == 0) {
+        uint32_t pos = end_bits - (eob >> 16);
+        put_bits(S.image, pos, eob & 0xffffu, eob >> 16);
+        atomicOr(&S.image[4], (z_bytes - 1) & 0xffffu);              // BSIZE
+        *zlen = z_bytes;
+    }
+    if (warp == 1) {    // the block's CRC from the warps' (all written before the scan's barriers), then the trailer
         crc = lane < (uint32_t)kZW ? S.crc_w[lane] : 0u;
 #pragma unroll
         for (uint32_t j = 0; j < 4; j++) {
@@ -932,50 +968,19 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
             if ((lane & (2 * s - 1)) == 0 && lane < (uint32_t)kZW) {
                 const uint32_t r0 = (lane + s) * kSeg;
                 const uint32_t right_len = r0 >= len ? 0u : min(s * kSeg, len - r0);
-                crc = (right_len == s * kSeg ? crc_advance_lvl(5 + j, crc) : crc_advance(crc, right_len)) ^ other;
+                crc = (right_len == s * kSeg ? crc_advance_lvl(5 + j, crc) : right_len == kBgzfIn % kSeg ? crc_advance_lvl(9, crc) : crc_advance(crc, right_len)) ^ other;
             }
         }
         if (lane == 0) {
-            S.buf[kTailOff] = crc ^ (len == kBgzfIn ? c_crc_init_full : crc_advance(0xffffffffu, len)) ^ 0xffffffffu;
-            S.buf[kTailOff + 1] = len;
+            uint32_t pos = (z_bytes - 8) * 8;
+            put_bits(S.image, pos, crc ^ (len == kBgzfIn ? c_crc_init_full : crc_advance(0xffffffffu, len)) ^ 0xffffffffu, 32);
+            put_bits(S.image, pos, len, 32);
         }
     }
     __syncthreads();
-
-    if (S.stored) {     // uniform: would not shrink with this code, a segment outgrew its image, or a byte has no code
-        if (t == 0) *zlen = kOwnCode;
-        return;
-    }
-    const uint32_t z_bytes = S.z_bytes;
-    uint32_t* s32 = reinterpret_cast<uint32_t*>(slot);
-    // ---- join: output word j is bits [32 j, 32 j + 32) of the member; the first piece that ends behind bit 32 j by
-    //      binary search (pend is ascending, padded to 32 entries), then along the pieces until the word is full
-    const uint32_t n_words = (z_bytes + 3) / 4;
-    for (uint32_t j = t; j < n_words; j += kZT) {
-        const uint32_t B = j * 32u;
-        uint32_t p = 0;
-#pragma unroll
-        for (uint32_t s = 16; s; s >>= 1) if (S.pend[p + s - 1] <= B) p += s;
-        uint32_t v = 0;
-        while (p < kPieces) {
-            const uint32_t d = S.pdst[p];
-            if (d >= B + 32u) break;
-            const uint32_t n = S.pnb[p];
-            if (n) {
-                const uint32_t o = d <= B ? B - d : 0u;       // the piece's first bit wanted
-                const uint32_t k = o >> 5;
-                const uint32_t* w = S.buf + S.psrc[p] + k;
-                const uint32_t lo = w[0], hi = (k + 1u) * 32u < n ? w[1] : 0u;     // what lies behind a piece's bits is not zero
-                const uint32_t x = __funnelshift_r(lo, hi, o & 31u);
-                v |= d <= B ? x : x << (d - B);
-            }
-            if (d + n >= B + 32u) break;
-            p++;
-        }
-        if (j == 4) v |= (z_bytes - 1u) & 0xffffu;            // BSIZE
-        s32[j] = v;
-    }
-    if (t == 0) *zlen = z_bytes;
+    const uint4* s4 = reinterpret_cast<const uint4*>(S.image);
+    uint4* o4 = reinterpret_cast<uint4*>(slot);
+    for (uint32_t i = t; i < (z_bytes + 15) / 16; i += kZT) o4[i] = s4[i];
 }
 
 // A block with a Huffman code of its own, for what k_bgzf left (zlen = kOwnCode): the same passes with per-warp
@@ -1300,11 +1305,11 @@ k_bgzf_own(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, con
         const uint32_t bitpos = hdr_bits + (__shfl_sync(0xffffffffu, excl, 0) & 0xfffffu);
         const uint32_t seg_len = seg_off >= len ? 0u : min(kSeg, len - seg_off);
         if (lz) {
-            if (seg_len == kSeg) pack_warp<true, true>(S, in + seg_off, seg_off, seg_len, S.stage, bitpos, 0xffffffffu, m_first, lane);
-            else if (seg_len) pack_warp<false, true>(S, in + seg_off, seg_off, seg_len, S.stage, bitpos, 0xffffffffu, m_first, lane);
+            if (seg_len == kSeg) pack_warp<true, true>(S, in + seg_off, seg_off, seg_len, S.stage, bitpos, m_first, lane);
+            else if (seg_len) pack_warp<false, true>(S, in + seg_off, seg_off, seg_len, S.stage, bitpos, m_first, lane);
         } else {
-            if (seg_len == kSeg) pack_warp<true, false>(S, in + seg_off, seg_off, seg_len, S.stage, bitpos, 0xffffffffu, m_first, lane);
-            else if (seg_len) pack_warp<false, false>(S, in + seg_off, seg_off, seg_len, S.stage, bitpos, 0xffffffffu, m_first, lane);
+            if (seg_len == kSeg) pack_warp<true, false>(S, in + seg_off, seg_off, seg_len, S.stage, bitpos, m_first, lane);
+            else if (seg_len) pack_warp<false, false>(S, in + seg_off, seg_off, seg_len, S.stage, bitpos, m_first, lane);
         }
     }
     if (t == 0) {
@@ -1414,14 +1419,18 @@ cudaError_t bgzf_init() {
         }
     e = cudaMemcpyToSymbol(c_crc_init_full, &init_full, sizeof init_full);
     if (e != cudaSuccess) return e;
-    static uint32_t lvl[9][4][256];
-    for (int j = 0; j < 9; j++)
+    static uint32_t lvl[10][4][256];
+    for (int j = 0; j < 10; j++)
         for (int k = 0; k < 4; k++)
             for (uint32_t x = 0; x < 256; x++) {
-                const uint32_t v = x << (8 * k);
-                uint32_t r = 0;
-                for (int q = 0; q < 32; q++) if ((v >> q) & 1u) r ^= adv[7 + j][q];
-                lvl[j][k][x] = r;
+                uint32_t v = x << (8 * k);
+                // j < 9: one operator; 9: kBgzfIn % kSeg = 3840 = 2^11 + 2^10 + 2^9 + 2^8 bytes, four of them in turn
+                for (int a = (j < 9 ? 7 + j : 8); a <= (j < 9 ? 7 + j : 11); a++) {
+                    uint32_t r = 0;
+                    for (int q = 0; q < 32; q++) if ((v >> q) & 1u) r ^= adv[a][q];
+                    v = r;
+                }
+                lvl[j][k][x] = v;
             }
     e = cudaMemcpyToSymbol(g_crc_lvl, lvl, sizeof lvl);
     if (e != cudaSuccess) return e;
