@@ -64,6 +64,9 @@ constexpr uint32_t kHistWord0 = kStageWords - kZW * 256;   // the histograms ali
 constexpr uint32_t kLsCap = 1024;        // line starts kept per block (two per thread)
 constexpr uint32_t kMCap = 1024;         // matches kept per block
 constexpr uint32_t kSlots = 2;           // k_bgzf: matches kept per chunk (kSlots * kZT = kMCap)
+constexpr uint32_t kWls = 96;            // k_bgzf: line starts kept per segment, the kBack before it included
+constexpr uint32_t kLookBack = 1024;     // k_bgzf: bytes before a segment searched for those
+constexpr uint32_t kNoLine = 0xffffu;
 constexpr uint32_t kBack = 4;            // a line is compared with the line this many lines earlier
 constexpr uint32_t kMaskWords = kBgzfIn / 32 + 2;
 constexpr uint32_t kImageBytes = 48 * 1024;   // k_bgzf: the image of a member in shared memory
@@ -148,10 +151,10 @@ struct ZMain {
     uint32_t ctab[256];
     uint32_t lcode[32], dcode[32];
     uint32_t cbits[kZT];                  // per chunk: the bits it sends
-    uint32_t scan_tmp[kZW + 1];
-    uint32_t crc_w[kZW];
+    uint32_t wtot[kZW];                   // per segment: the bits it sends
+    uint32_t crc_w[kZW];                  // per segment: its CRC register advanced over the bytes behind the segment
     uint32_t eob, hdr_bits, miss;
-    uint16_t ls[kLsCap + 1];              // line starts, ascending; ls[0] = 0
+    uint16_t ls[kZW][kWls];               // per segment: the last kBack line starts before it (kNoLine: none), then its own, ascending
 };
 static_assert(sizeof(ZMain) <= 75 * 1024, "three CTAs per SM");
 static_assert(offsetof(ZMain, mbits) % 8 == 0, "mbits alignment");
@@ -818,7 +821,25 @@ k_bgzf_code(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, co
     if (t == 0) { Z.eob = (uint32_t)S.code[256] | (uint32_t)S.len[256] << 16; Z.hdr_bits = hdr_bits; Z.pad[0] = 0; Z.pad[1] = 0; }
 }
 
-// One BGZF block per CTA, with the codes k_bgzf_code left.
+// The common prefix of the lines at i and p < i, at most maxm bytes (16 per round trip; reads may run up to 19 bytes
+// past the block: the buffers have slack)
+__device__ __forceinline__ uint32_t common_prefix(const uint8_t* in, uint32_t i, uint32_t p, uint32_t maxm) {
+    uint32_t m = 0;
+    while (m < maxm) {
+        uint32_t a[4], c[4];
+        load16(in + i + m, a);
+        load16(in + p + m, c);
+        uint32_t same = 16;
+#pragma unroll
+        for (int j = 3; j >= 0; j--) { const uint32_t x = a[j] ^ c[j]; if (x) same = 4 * j + (((uint32_t)__ffs(x) - 1u) >> 3); }
+        m += same;
+        if (same < 16) break;
+    }
+    return min(m, maxm);
+}
+
+// One BGZF block per CTA, with the codes k_bgzf_code left.  Between the first barrier and the one at which the
+// segments' sizes meet, every warp works on its own segment of 4096 bytes with warp-level synchronisation only.
 __global__ void __launch_bounds__(kZT, 3)
 k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const uint64_t* __restrict__ totals, uint32_t nblk_max,
        uint32_t lz, const ZCode* __restrict__ codes, uint8_t* __restrict__ slots0, uint8_t* __restrict__ slots1,
@@ -839,6 +860,7 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
 
     const uint32_t my_off = t * kChunk;
     const uint32_t my_len = my_off >= len ? 0u : min(kChunk, len - my_off);
+    const uint32_t seg_off = warp * kSeg, seg_end = min(len, seg_off + kSeg);
 
     // ---- the image: the header words (the same for every block), zeros behind them; the match mask; the codes
     {
@@ -851,7 +873,7 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
             S.ctab[t] = __ldg(&Z.ctab[t]);
         }
         if (t < 32) { S.lcode[t] = __ldg(&Z.lcode[t]); S.dcode[t] = __ldg(&Z.dcode[t]); }
-        if (t == 0) { S.eob = __ldg(&Z.eob); S.hdr_bits = __ldg(&Z.hdr_bits); S.ls[0] = 0; S.miss = 0; }
+        if (t == 0) { S.eob = __ldg(&Z.eob); S.hdr_bits = __ldg(&Z.hdr_bits); S.miss = 0; }
     }
     __syncthreads();
     // ---- pass 1: chunk CRC, the chunk's newlines, the bits of its bytes as literals
@@ -872,44 +894,86 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
             crc = (right_len == s * kChunk ? crc_advance_lvl(j, crc) : crc_advance(crc, right_len)) ^ other;
         }
     }
-    if (lane == 0) S.crc_w[warp] = crc;
+    if (lane == 0) {
+        // the segment's register advanced over the bytes behind the segment: the block's is the XOR of the sixteen
+        if (len == kBgzfIn) {
+            if (warp + 1 < (uint32_t)kZW) {
+                crc = crc_advance_lvl(9, crc);                                     // the last segment's 3840 bytes
+                const uint32_t n = kZW - 2 - warp;                                  // whole segments in between
+#pragma unroll
+                for (uint32_t q = 0; q < 4; q++) if ((n >> q) & 1u) crc = crc_advance_lvl(5 + q, crc);
+            }
+        } else crc = crc_advance(crc, len - seg_end);
+        S.crc_w[warp] = crc;
+    }
 
-    if (lz) {       // uniform
-        // ---- line starts: the byte after every newline, numbered by a block scan of the newline counts
+    if (lz && seg_off < len) {       // uniform in the warp
+        uint16_t* wls = S.ls[warp];
+        // ---- the last kBack line starts before the segment, from the newlines of the kLookBack bytes before it
+        //      (32 per lane); one in the byte just before the segment starts a line of the segment itself
+        if (lane < kBack) wls[lane] = kNoLine;
+        __syncwarp();
+        if (warp) {
+            const uint4* lb = reinterpret_cast<const uint4*>(in + seg_off - kLookBack + 32u * lane);
+            const uint4 d0 = __ldg(lb), d1 = __ldg(lb + 1);
+            const uint32_t w[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+            uint32_t m = 0;
+#pragma unroll
+            for (int q = 0; q < 8; q++) m |= (((__vcmpeq4(w[q], 0x0a0a0a0au) & 0x01010101u) * 0x01020408u) >> 24) << (4 * q);
+            if (lane == 31) m &= 0x7fffffffu;
+            // newlines behind this lane's, by a suffix sum
+            uint32_t after = __popc(m);
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_down_sync(0xffffffffu, after, o); if (lane + o < 32) after += x; }
+            after -= __popc(m);
+            while (m && after < kBack) {            // from the last one down
+                const uint32_t bit = 31u - (uint32_t)__clz(m);
+                m &= ~(1u << bit);
+                wls[kBack - 1 - after] = (uint16_t)(seg_off - kLookBack + 32u * lane + bit + 1u);
+                after++;
+            }
+        }
+        // ---- the line starts inside the segment: behind every newline but one in the chunk's last byte, and at the
+        //      chunk's first byte when the byte before is a newline (or the block starts there)
+        const bool prev_nl = my_len && (t == 0 || __ldg(in + my_off - 1) == '\n');
+        const bool last_nl = my_len && __ldg(in + my_off + my_len - 1) == '\n';
         const uint32_t my_nl = __popc(nlm[0]) + __popc(nlm[1]) + __popc(nlm[2]) + __popc(nlm[3]);
-        uint32_t total_nl;
-        const uint32_t nl_before = block_scan(my_nl, S.scan_tmp, total_nl);
+        const uint32_t my_ls = my_nl + (prev_nl ? 1u : 0u) - (last_nl ? 1u : 0u);
+        uint32_t incl = my_ls;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += x; }
+        const uint32_t n_ls = min(kBack + __shfl_sync(0xffffffffu, incl, 31), kWls);     // entries of wls in use
+        const uint32_t k_lo = kBack + incl - my_ls;
         {
-            uint32_t idx = nl_before + 1;       // line start idx follows the idx-th newline
+            uint32_t idx = k_lo;
+            if (prev_nl) { if (idx < kWls) wls[idx] = (uint16_t)my_off; idx++; }
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 uint32_t m = nlm[j];
                 while (m) {
                     const uint32_t bit = (uint32_t)__ffs(m) - 1u;
                     m &= m - 1u;
-                    if (idx <= kLsCap) S.ls[idx] = (uint16_t)(my_off + 32u * j + bit + 1u);
-                    idx++;
+                    const uint32_t pos = 32u * j + bit + 1u;
+                    if (pos < my_len) { if (idx < kWls) wls[idx] = (uint16_t)(my_off + pos); idx++; }
                 }
             }
         }
-        __syncthreads();
-        // the line starts inside this chunk: first and last index (a line starts behind a newline, so the newline before the
-        // chunk counts and one in its last byte does not)
-        const bool prev_nl = t > 0 && my_len && __ldg(in + my_off - 1) == '\n';
-        const bool last_nl = my_len && __ldg(in + my_off + my_len - 1) == '\n';
-        const uint32_t n_ls = min(total_nl, kLsCap) + 1;   // entries of S.ls in use (a last one may equal len: no line there)
-        const uint32_t k_lo = max(nl_before + (prev_nl ? 0u : 1u), kBack);
-        const uint32_t k_hi = min(nl_before + my_nl + 1u - (last_nl ? 1u : 0u), n_ls);      // behind the last
+        __syncwarp();
         // ---- matches: every thread looks at the line starts of its chunk -- the thread that will code them -- and keeps
-        //      up to kSlots matches, in order, in slots of its own
-        uint32_t slot = 0;
-        for (uint32_t k = k_lo; k < k_hi; k++) {
-            uint32_t i = 0, m = 0, tok = 0;
-            find_match(in, len, S.ls, n_ls, k, i, m, tok);
-            if (tok && slot < kSlots) {
+        //      up to kSlots matches, in order, in slots of its own; a match ends with its line and with the segment
+        //      (no match covers a newline: the coder finds a match's first byte by its uncovered predecessor)
+        const uint32_t last_end = seg_end - (__ldg(in + seg_end - 1) == '\n' ? 1u : 0u);
+        uint32_t slot_n = 0;
+        for (uint32_t k = k_lo; k < min(k_lo + my_ls, n_ls); k++) {
+            const uint32_t p = wls[k - kBack];
+            if (p == kNoLine || (k + 1 == kWls)) continue;     // the list's last entry when it is full: its line's end is not known
+            const uint32_t i = wls[k];
+            const uint32_t next = k + 1 < n_ls ? (uint32_t)wls[k + 1] - 1u : last_end;   // the '\n' that ends this line, or the segment's end
+            const uint32_t m = common_prefix(in, i, p, min(258u, next - i));
+            if (m >= 4 && slot_n < kSlots) {
                 uint32_t hn;
-                const uint64_t hv = match_bits(S, tok, hn);
-                S.mbits[kSlots * t + slot++] = hv | (uint64_t)hn << 56;
+                const uint64_t hv = match_bits(S, match_token(m, i - p), hn);
+                S.mbits[kSlots * t + slot_n++] = hv | (uint64_t)hn << 56;
                 atomicAdd(&S.cbits[t], hn);
                 // its bytes no longer send their literals ...
                 for (uint32_t q0 = 0; q0 < m; q0 += 16) {
@@ -928,12 +992,20 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
                 }
             }
         }
-        __syncthreads();
+        __syncwarp();
     }
 
-    // ---- where every chunk's bits go
-    uint32_t total;
-    const uint32_t excl = block_scan(S.cbits[t], S.scan_tmp, total);
+    // ---- where every chunk's bits go: a scan in the warp, the segments' sums through shared memory
+    const uint32_t my_bits = S.cbits[t];
+    uint32_t excl = my_bits;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, excl, o); if (lane >= (uint32_t)o) excl += x; }
+    if (lane == 31) S.wtot[warp] = excl;
+    excl -= my_bits;
+    __syncthreads();
+    uint32_t total = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < (uint32_t)kZW; w++) { const uint32_t x = S.wtot[w]; total += x; excl += w < warp ? x : 0u; }
     const uint32_t hdr_bits = S.hdr_bits, eob = S.eob;
     const uint32_t end_bits = hdr_bits + total + (eob >> 16);
     const uint32_t z_bytes = (end_bits + 7) / 8 + 8;                 // the member with a dynamic block
@@ -957,25 +1029,13 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
         uint32_t pos = end_bits - (eob >> 16);
         put_bits(S.image, pos, eob & 0xffffu, eob >> 16);
         atomicOr(&S.image[4], (z_bytes - 1) & 0xffffu);              // BSIZE
-        *zlen = z_bytes;
-    }
-    if (warp == 1) {    // the block's CRC from the warps' (all written before the scan's barriers), then the trailer
-        crc = lane < (uint32_t)kZW ? S.crc_w[lane] : 0u;
+        pos = (z_bytes - 8) * 8;
+        uint32_t crc_all = 0;
 #pragma unroll
-        for (uint32_t j = 0; j < 4; j++) {
-            const uint32_t s = 1u << j;
-            const uint32_t other = __shfl_down_sync(0xffffffffu, crc, s);
-            if ((lane & (2 * s - 1)) == 0 && lane < (uint32_t)kZW) {
-                const uint32_t r0 = (lane + s) * kSeg;
-                const uint32_t right_len = r0 >= len ? 0u : min(s * kSeg, len - r0);
-                crc = (right_len == s * kSeg ? crc_advance_lvl(5 + j, crc) : right_len == kBgzfIn % kSeg ? crc_advance_lvl(9, crc) : crc_advance(crc, right_len)) ^ other;
-            }
-        }
-        if (lane == 0) {
-            uint32_t pos = (z_bytes - 8) * 8;
-            put_bits(S.image, pos, crc ^ (len == kBgzfIn ? c_crc_init_full : crc_advance(0xffffffffu, len)) ^ 0xffffffffu, 32);
-            put_bits(S.image, pos, len, 32);
-        }
+        for (uint32_t w = 0; w < (uint32_t)kZW; w++) crc_all ^= S.crc_w[w];
+        put_bits(S.image, pos, crc_all ^ (len == kBgzfIn ? c_crc_init_full : crc_advance(0xffffffffu, len)) ^ 0xffffffffu, 32);
+        put_bits(S.image, pos, len, 32);
+        *zlen = z_bytes;
     }
     __syncthreads();
     const uint4* s4 = reinterpret_cast<const uint4*>(S.image);
