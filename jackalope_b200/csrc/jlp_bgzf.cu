@@ -72,8 +72,8 @@ constexpr uint32_t kMaskWords = kBgzfIn / 32 + 2;
 constexpr uint32_t kImageBytes = 48 * 1024;   // k_bgzf: the image of a member in shared memory
 constexpr uint32_t kImageWords = kImageBytes / 4;
 constexpr uint32_t kHdrWords = 160;      // 18 bytes of member header + at most 4498 bits of block header
-constexpr uint32_t kNoCode = 4096u << 16;    // more bits than a chunk of coded bytes can take
 constexpr uint32_t kOwnCode = 0xffffffffu;   // in zlen[]: k_bgzf leaves this block to k_bgzf_own
+constexpr uint32_t kNoCode = 4096u << 16;    // more bits than a chunk of coded bytes can take
 
 // what k_bgzf_code leaves for k_bgzf, one per file
 struct ZCode {
@@ -1043,17 +1043,14 @@ k_bgzf(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const u
     for (uint32_t i = t; i < (z_bytes + 15) / 16; i += kZT) o4[i] = s4[i];
 }
 
-// A block with a Huffman code of its own, for what k_bgzf left (zlen = kOwnCode): the same passes with per-warp
-// literal histograms in pass 1, the code construction of k_bgzf_code between the passes, one block image.
-__global__ void __launch_bounds__(kZT, 3)
-k_bgzf_own(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const uint64_t* __restrict__ totals, uint32_t nblk_max,
-       uint32_t lz, uint8_t* __restrict__ slots0, uint8_t* __restrict__ slots1, uint32_t* __restrict__ zlen0, uint32_t* __restrict__ zlen1) {
-    JLP_DYN_SMEM(smem_raw);
-    ZShared& S = *reinterpret_cast<ZShared*>(smem_raw);
+// A block with a Huffman code of its own, for what k_bgzf left (zlen = kOwnCode): warp-cooperative passes with
+// per-warp literal histograms in pass 1, the code construction of k_bgzf_code between the passes, one block image.
+__device__ __forceinline__ void own_block(ZShared& S, uint32_t blk, const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1,
+                                          const uint64_t* __restrict__ totals, uint32_t nblk_max, uint32_t lz, uint8_t* __restrict__ slots0,
+                                          uint8_t* __restrict__ slots1, uint32_t* __restrict__ zlen0, uint32_t* __restrict__ zlen1) {
     const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    // the grid is sized for the largest batch; the FASTQ byte counts of this one are on the device
-    const bool second = blockIdx.x >= nblk_max;
-    const uint32_t b = second ? blockIdx.x - nblk_max : blockIdx.x;
+    const bool second = blk >= nblk_max;
+    const uint32_t b = second ? blk - nblk_max : blk;
     const uint64_t n_all = totals[second ? 1 : 0];
     if ((uint64_t)b * kBgzfIn >= n_all) return;
     const uint8_t* in = (second ? in1 : in0) + (uint64_t)b * kBgzfIn;
@@ -1387,6 +1384,29 @@ k_bgzf_own(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, con
     uint4* o4 = reinterpret_cast<uint4*>(slot);
     for (uint32_t i = t; i < (z_bytes + 15) / 16; i += kZT) o4[i] = s4[i];
 }
+// The blocks k_bgzf left (usually none), one CTA per 32 blocks of the launch.
+__global__ void __launch_bounds__(kZT, 3)
+k_bgzf_own(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, const uint64_t* __restrict__ totals, uint32_t nblk_max,
+           uint32_t lz, uint8_t* __restrict__ slots0, uint8_t* __restrict__ slots1, uint32_t* __restrict__ zlen0, uint32_t* __restrict__ zlen1) {
+    JLP_DYN_SMEM(smem_raw);
+    ZShared& S = *reinterpret_cast<ZShared*>(smem_raw);
+    __shared__ uint32_t todo;
+    // CTA c looks after blocks [32 c, 32 c + 32) of the launch: one load per lane finds the ones left to it
+    if (threadIdx.x < 32) {
+        const uint32_t blk = 32 * blockIdx.x + threadIdx.x;
+        const bool second = blk >= nblk_max;
+        const uint32_t b = second ? blk - nblk_max : blk;
+        const bool mine = blk < 2 * nblk_max && (uint64_t)b * kBgzfIn < totals[second ? 1 : 0] && (second ? zlen1 : zlen0)[b] == kOwnCode;
+        const uint32_t bal = __ballot_sync(0xffffffffu, mine);
+        if (threadIdx.x == 0) todo = bal;
+    }
+    __syncthreads();
+    for (uint32_t m = todo; m; m &= m - 1u) {
+        own_block(S, 32 * blockIdx.x + (uint32_t)__ffs(m) - 1u, in0, in1, totals, nblk_max, lz, slots0, slots1, zlen0, zlen1);
+        __syncthreads();       // the next block reuses the shared memory
+    }
+}
+
 // exclusive prefix of the member sizes of one file (one CTA per file); the file's compressed size into totals[2 + file]
 __global__ void __launch_bounds__(1024)
 k_bgzf_scan(const uint32_t* __restrict__ zlen0, const uint32_t* __restrict__ zlen1, uint64_t* __restrict__ zoff0,
@@ -1508,7 +1528,7 @@ cudaError_t launch_bgzf(const uint8_t* in0, const uint8_t* in1, uint64_t* totals
     if (nblk_max) {
         JLP_LAUNCH(k_bgzf_code, 2, kZT, sizeof(ZShared), s, in0, in1, totals, matches ? 1u : 0u, zc);
         JLP_LAUNCH(k_bgzf, 2 * nblk_max, kZT, sizeof(ZMain), s, in0, in1, totals, nblk_max, matches ? 1u : 0u, zc, slots0, slots1, zlen0, zlen1);
-        JLP_LAUNCH(k_bgzf_own, 2 * nblk_max, kZT, sizeof(ZShared), s, in0, in1, totals, nblk_max, matches ? 1u : 0u, slots0, slots1, zlen0, zlen1);
+        JLP_LAUNCH(k_bgzf_own, (2 * nblk_max + 31) / 32, kZT, sizeof(ZShared), s, in0, in1, totals, nblk_max, matches ? 1u : 0u, slots0, slots1, zlen0, zlen1);
     }
     JLP_LAUNCH(k_bgzf_scan, 2, 1024, 0, s, zlen0, zlen1, zoff0, zoff1, totals);
     if (nblk_max)

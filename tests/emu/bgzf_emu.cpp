@@ -8,7 +8,7 @@
 
 namespace jlp_emu {
 thread_local Block* tl_block;
-thread_local uint3 tl_tid, tl_bid;
+thread_local uint3 tl_tid, tl_bid, tl_gdim;
 }
 
 int main(int argc, char** argv) {

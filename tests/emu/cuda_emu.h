@@ -53,7 +53,7 @@ struct Block {
     uint8_t* smem;
 };
 extern thread_local Block* tl_block;
-extern thread_local uint3 tl_tid, tl_bid;
+extern thread_local uint3 tl_tid, tl_bid, tl_gdim;
 inline uint8_t* dyn_smem() { return tl_block->smem; }
 inline Warp& my_warp() { return tl_block->warps[tl_tid.x >> 5]; }
 
@@ -70,7 +70,7 @@ void launch(unsigned grid, unsigned block, size_t smem_bytes, F body) {
         th.reserve(block);
         for (unsigned t = 0; t < block; t++)
             th.emplace_back([&, t]() {
-                tl_block = &B; tl_tid = uint3{t, 0, 0}; tl_bid = uint3{b, 0, 0};
+                tl_block = &B; tl_tid = uint3{t, 0, 0}; tl_bid = uint3{b, 0, 0}; tl_gdim = uint3{grid, 1, 1};
                 body();
             });
         for (auto& x : th) x.join();
@@ -82,6 +82,7 @@ void launch(unsigned grid, unsigned block, size_t smem_bytes, F body) {
 
 #define threadIdx (jlp_emu::tl_tid)
 #define blockIdx (jlp_emu::tl_bid)
+#define gridDim (jlp_emu::tl_gdim)
 
 static inline void __syncthreads() { pthread_barrier_wait(&jlp_emu::tl_block->bar); }
 static inline void __syncwarp() { pthread_barrier_wait(&jlp_emu::my_warp().bar); }
