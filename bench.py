@@ -573,7 +573,7 @@ def main():
     #      line-prefix matches) and level 1 (literals only)
     bgzf = None
     if not a.no_e2e:
-        bgzf = {"note": "compress=<level>, comp_engine=device: k_bgzf + scan + gather after k_reads; e2e hands BGZF bytes to the "
+        bgzf = {"note": "compress=<level>, comp_engine=device: k_bgzf_code + k_bgzf (+ k_bgzf_own) + scan + gather after k_reads (k_bgzf_ms_per_launch is all five); e2e hands BGZF bytes to the "
                         "caller from pinned host buffers (jlp_illumina_stream); GB/s counts FASTQ bytes read + BGZF bytes written"}
         for level in (6, 1):
             zkw = dict(compress=level, comp_engine="device")
