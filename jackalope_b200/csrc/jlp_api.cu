@@ -193,9 +193,11 @@ bool map_range(int fd, uint64_t off, uint64_t n, Mapping& m) {
 // "each GPU needs only the haplotypes its range touches"), so the records outlive jlp_add_haplotype.
 struct HapChromHost {
     uint64_t size = 0;                                   // mutated chromosome size
-    std::vector<uint64_t> old_pos, new_pos, nuc_off;
-    std::vector<int64_t> size_mod;                       // size_modifier per record, src/hap_classes.h:314-333
-    std::vector<uint8_t> pool;
+    uint64_t n_muts = 0;
+    // one array, one upload: old_pos[n] | new_pos[n] | nuc_off[n] | size_modifier[n] (src/hap_classes.h:314-333) | the
+    // nucleotide pool, padded to whole words
+    std::vector<uint64_t> packed;
+    uint64_t pool_bytes = 0;
 };
 struct HapStore {
     std::string name;
@@ -290,9 +292,13 @@ struct jlp_ctx {
     std::shared_ptr<std::atomic<double>[]> pb_qcache;
     double pb_qcache_key[3] = {0, 0, 0};
     size_t pb_qcache_n = 0;
-    DevBuf<uint64_t> m_old, m_new, m_off;
-    DevBuf<int64_t> m_sm;
-    DevBuf<uint8_t> m_pool;
+    // materialisation: the records of the next chromosomes are uploaded (s_upload) while k_materialize works on the
+    // ones before (s_compute); kMatBufs scratch buffers in turn
+    static constexpr int kMatBufs = 3;
+    DevBuf<uint64_t> m_pack[kMatBufs];
+    cudaEvent_t m_up[kMatBufs] = {nullptr, nullptr, nullptr}, m_done[kMatBufs] = {nullptr, nullptr, nullptr};
+    bool m_busy[kMatBufs] = {false, false, false};
+    uint64_t m_next = 0;
 };
 
 namespace {
@@ -602,14 +608,25 @@ void ensure_hap_chrom(jlp_ctx* c, size_t h, size_t ci) {
     const HapChromHost& M = H.store->chrom[ci];
     const uint64_t ref_size = c->chrom_off[ci + 1] - c->chrom_off[ci];
     const uint8_t* ref = c->genome.p + kPad + c->chrom_off[ci];
-    c->m_old.upload(M.old_pos, c->s_compute); c->m_new.upload(M.new_pos, c->s_compute); c->m_off.upload(M.nuc_off, c->s_compute);
-    c->m_sm.upload(M.size_mod, c->s_compute); c->m_pool.upload(M.pool, c->s_compute);
-    c->h2d_bytes += M.old_pos.size() * 32 + M.pool.size();
+    const int k = (int)(c->m_next++ % jlp_ctx::kMatBufs);
+    if (!c->m_up[k]) {
+        CK(cudaEventCreateWithFlags(&c->m_up[k], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->m_done[k], cudaEventDisableTiming));
+    }
+    // the kernel that read this buffer last must be done before the buffer can grow (cudaFree) or be written again
+    if (c->m_busy[k]) CK(cudaEventSynchronize(c->m_done[k]));
+    c->m_pack[k].upload(M.packed, c->s_upload);
+    CK(cudaEventRecord(c->m_up[k], c->s_upload));
+    c->h2d_bytes += M.n_muts * 32 + M.pool_bytes;
     uint8_t* out = c->hap_mem.alloc(M.size + 2 * kPad);
-    CK(launch_materialize(ref, ref_size, M.old_pos.size(), c->m_old.p, c->m_new.p, c->m_sm.p, c->m_off.p, c->m_pool.p, M.size,
-                          out + kPad, c->s_compute));
-    CK(cudaStreamSynchronize(c->s_compute));      // the scratch buffers are reused by the next chromosome
-    H.seq[ci] = out + kPad;
+    const uint64_t* w = c->m_pack[k].p;
+    const uint64_t n = M.n_muts;
+    CK(cudaStreamWaitEvent(c->s_compute, c->m_up[k], 0));
+    CK(launch_materialize(ref, ref_size, n, w, w + n, reinterpret_cast<const int64_t*>(w + 3 * n), w + 2 * n,
+                          reinterpret_cast<const uint8_t*>(w + 4 * n), M.size, out + kPad, c->s_compute));
+    CK(cudaEventRecord(c->m_done[k], c->s_compute));
+    c->m_busy[k] = true;
+    H.seq[ci] = out + kPad;       // valid in stream order: everything that reads it runs on s_compute
 }
 
 typedef std::vector<std::pair<uint64_t, uint64_t>> Ranges;
@@ -1446,6 +1463,7 @@ void jlp_ctx_destroy(jlp_ctx* c) {
     if (c->s_compute) cudaStreamDestroy(c->s_compute);
     if (c->s_copy) cudaStreamDestroy(c->s_copy);
     if (c->s_upload) cudaStreamDestroy(c->s_upload);
+    for (int k = 0; k < jlp_ctx::kMatBufs; k++) { if (c->m_up[k]) cudaEventDestroy(c->m_up[k]); if (c->m_done[k]) cudaEventDestroy(c->m_done[k]); }
     for (cudaEvent_t ev : c->chrom_ev) cudaEventDestroy(ev);
     c->writers.stop();
     delete c;
@@ -1589,7 +1607,8 @@ int jlp_clear_haplotypes(jlp_ctx* c) {
     });
 }
 
-// the host-side store of one haplotype: a copy of the caller's AllMutations arrays + size_modifier per record
+// the host-side store of one haplotype: a copy of the caller's AllMutations arrays + size_modifier per record, one packed
+// array per chromosome, built by a few threads (one chromosome at a time each)
 static std::shared_ptr<HapStore> make_hap_store(const jlp_ctx* c, const char* name, const uint64_t* n_muts, const uint64_t* const* old_pos,
                                                 const uint64_t* const* new_pos, const uint64_t* const* nuc_off,
                                                 const char* const* nuc_pool, const uint64_t* nuc_pool_len, const uint64_t* chrom_sizes) {
@@ -1599,29 +1618,48 @@ static std::shared_ptr<HapStore> make_hap_store(const jlp_ctx* c, const char* na
     auto S = std::make_shared<HapStore>();
     S->name = name ? name : "";
     S->chrom.resize(nc);
-    for (uint64_t ci = 0; ci < nc; ci++) {
-        const uint64_t M = n_muts[ci];
-        const uint64_t ref_size = c->chrom_off[ci + 1] - c->chrom_off[ci];
-        HapChromHost& H = S->chrom[ci];
-        H.size = chrom_sizes[ci];
-        if (M == 0) {   // get_chrom_full returns the reference string (src/hap_classes.cpp:82)
-            if (chrom_sizes[ci] != ref_size) throw ArgErr("chromosome without mutations must keep the reference size");
-            continue;
+    std::atomic<uint64_t> next{0};
+    std::mutex err_mu;
+    std::string err;
+    auto work = [&]() {
+        for (uint64_t ci; (ci = next.fetch_add(1)) < nc;) {
+            const char* bad = nullptr;
+            const uint64_t M = n_muts[ci];
+            const uint64_t ref_size = c->chrom_off[ci + 1] - c->chrom_off[ci];
+            HapChromHost& H = S->chrom[ci];
+            H.size = chrom_sizes[ci];
+            if (M == 0) {   // get_chrom_full returns the reference string (src/hap_classes.cpp:82)
+                if (chrom_sizes[ci] != ref_size) bad = "chromosome without mutations must keep the reference size";
+            } else if (!old_pos || !new_pos || !nuc_off || !nuc_pool || !nuc_pool_len || !old_pos[ci] || !new_pos[ci] || !nuc_off[ci]) {
+                bad = "mutation arrays are NULL";
+            } else {
+                const uint64_t pb = nuc_pool_len[ci];
+                H.n_muts = M; H.pool_bytes = pb;
+                H.packed.resize(4 * M + (pb + 7) / 8);
+                uint64_t* w = H.packed.data();
+                std::memcpy(w, old_pos[ci], M * 8);
+                std::memcpy(w + M, new_pos[ci], M * 8);
+                std::memcpy(w + 2 * M, nuc_off[ci], M * 8);
+                // size_modifier per record, src/hap_classes.h:314-333
+                int64_t* sm = reinterpret_cast<int64_t*>(w + 3 * M);
+                for (uint64_t i = 0; i < M; i++) {
+                    if (i && new_pos[ci][i] < new_pos[ci][i - 1]) { bad = "mutations must be sorted by new_pos"; break; }
+                    const int64_t s = (i + 1 < M) ? (int64_t)(new_pos[ci][i + 1] - old_pos[ci][i + 1]) : (int64_t)(chrom_sizes[ci] - ref_size);
+                    sm[i] = s + (int64_t)(old_pos[ci][i] - new_pos[ci][i]);
+                }
+                if (pb) std::memcpy(w + 4 * M, nuc_pool[ci], pb);
+            }
+            if (bad) { std::lock_guard<std::mutex> g(err_mu); if (err.empty()) err = bad; }
         }
-        if (!old_pos || !new_pos || !nuc_off || !nuc_pool || !nuc_pool_len || !old_pos[ci] || !new_pos[ci] || !nuc_off[ci])
-            throw ArgErr("mutation arrays are NULL");
-        // size_modifier per record, src/hap_classes.h:314-333
-        H.size_mod.resize(M);
-        for (uint64_t i = 0; i < M; i++) {
-            if (i && new_pos[ci][i] < new_pos[ci][i - 1]) throw ArgErr("mutations must be sorted by new_pos");
-            int64_t s = (i + 1 < M) ? (int64_t)(new_pos[ci][i + 1] - old_pos[ci][i + 1]) : (int64_t)(chrom_sizes[ci] - ref_size);
-            H.size_mod[i] = s + (int64_t)(old_pos[ci][i] - new_pos[ci][i]);
-        }
-        H.old_pos.assign(old_pos[ci], old_pos[ci] + M);
-        H.new_pos.assign(new_pos[ci], new_pos[ci] + M);
-        H.nuc_off.assign(nuc_off[ci], nuc_off[ci] + M);
-        H.pool.assign(nuc_pool[ci], nuc_pool[ci] + nuc_pool_len[ci]);
-    }
+    };
+    uint64_t total = 0;
+    for (uint64_t ci = 0; ci < nc; ci++) total += n_muts[ci];
+    const unsigned nt = total < (1u << 16) ? 1u : (unsigned)std::min<uint64_t>(std::min<uint64_t>(nc, 16), std::max(1u, std::thread::hardware_concurrency()));
+    std::vector<std::thread> th;
+    for (unsigned i = 1; i < nt; i++) th.emplace_back(work);
+    work();
+    for (std::thread& t : th) t.join();
+    if (!err.empty()) throw ArgErr(err);
     return S;
 }
 
@@ -1633,7 +1671,7 @@ static void attach_hap(jlp_ctx* c, const std::shared_ptr<HapStore>& S) {
     for (size_t ci = 0; ci < S->chrom.size(); ci++) {
         const HapChromHost& M = S->chrom[ci];
         H.len.push_back(M.size);
-        H.seq.push_back(device && M.old_pos.empty() ? c->genome.p + kPad + c->chrom_off[ci] : nullptr);
+        H.seq.push_back(device && M.n_muts == 0 ? c->genome.p + kPad + c->chrom_off[ci] : nullptr);
     }
     c->haps.push_back(std::move(H));
 }
@@ -1658,6 +1696,7 @@ int jlp_materialize_haplotypes(jlp_ctx* c) {
             finish_upload(d);
             for (size_t h = 0; h < d->haps.size(); h++)
                 for (size_t ci = 0; ci < d->haps[h].seq.size(); ci++) ensure_hap_chrom(d, h, ci);
+            CK(cudaStreamSynchronize(d->s_compute));
         });
     });
 }
@@ -1673,6 +1712,7 @@ int jlp_get_haplotype_chrom(jlp_ctx* c, uint64_t hap, uint64_t chrom, char* out,
         if (n > cap) throw ArgErr("output buffer too small");
         finish_upload(d);
         ensure_hap_chrom(d, hap, chrom);
+        CK(cudaStreamSynchronize(d->s_compute));
         if (n) CK(cudaMemcpy(out, d->haps[hap].seq[chrom], n, cudaMemcpyDeviceToHost));
     });
 }

@@ -367,12 +367,6 @@ __device__ __forceinline__ uint64_t match_bits(const ZMain& S, uint32_t tok, uin
     return v;
 }
 
-// the mask bits of bytes [q, q + 32) of the block (bit i: byte q + i), q a multiple of 4
-__device__ __forceinline__ uint32_t mask_at(const uint32_t* mask, uint32_t q) {
-    const uint32_t g = q + 1;
-    return __funnelshift_r(mask[g >> 5], mask[(g >> 5) + 1], g & 31u);
-}
-
 // 16 bytes starting at an arbitrary address, from five aligned word loads (all in flight together)
 __device__ __forceinline__ void load16(const uint8_t* a, uint32_t (&x)[4]) {
     const uintptr_t u = reinterpret_cast<uintptr_t>(a);
