@@ -4,29 +4,34 @@
 // src/hts.h:140-180: gzip members (RFC 1952) of at most 0xff00 input bytes carrying the
 // "BC" extra field with the member's size, each holding one RFC 1951 deflate stream).
 //
-// Two kernels per batch.  FASTQ is stationary -- every block of a batch has the statistics of every other --
-// so the Huffman codes are built ONCE per file and batch, from the file's first block, and every block is
-// coded with them (each member still carries the code in its own dynamic-block header, as the format wants):
+// FASTQ is stationary -- every block of a batch has the statistics of every other -- so the Huffman codes are built
+// ONCE per file and batch, from the file's first block, and every block is coded with them (each member still
+// carries the code in its own dynamic-block header, as the format wants):
 //
 // k_bgzf_code   one CTA per file.  Block 0: literal histograms (shared atomics), the matches of its lines, and
-//               from the counts -- every symbol's count raised by one, so that a byte the sample does not hold
-//               still has a code -- the literal/length and distance codes (two-queue Huffman over the
-//               rank-sorted symbols, limited to 15 bits, canonical), the code-length code, and the bits of the
-//               member + block header, which are the same for every block.  Left in a ZCode in device memory.
-// k_bgzf        one CTA of 512 threads per BGZF block, 3 CTAs per SM; no code construction, nine barriers.
-//   pass 1  thread t owns bytes [128 t, 128 t + 128): the CRC-32 of the chunk (slicing by four; chunk CRCs are
-//           combined by a tree of "advance over 2^j zero bytes" operators) and its newlines as a bit mask
-//   match   (levels 4-6) line starts by a block scan of the newline counts; every line start is compared with
-//           the line start 4 lines earlier -- in FASTQ the same line of the previous record -- and a common
-//           prefix of >= 4 bytes becomes one length/distance pair; a bit mask marks the bytes so covered
-//   pass 2  warp w packs segment [4096 w, 4096 w + 4096), 4 bytes per lane and 128 contiguous bytes per round
-//           (the codes of a lane's bytes are joined, a warp scan of the lengths places them), into an image
-//           of its own in shared memory that starts at bit 0: no warp has to know the others' sizes
-//   join    the header bits, the 16 segment images, the end-of-block code and the CRC-32 / ISIZE trailer are
-//           pieces of known bit length now; every output word is funnel-shifted together from the one or
-//           two pieces it covers on its way to global memory
-//   a block that would not shrink, or a segment that outgrows its image (3 KiB per 4 KiB in a full block), is emitted as a
-//   stored block straight from the input.
+//               from the counts -- those of the printable bytes, the lengths and the distances raised by one, so
+//               that what the sample does not hold still has a code -- the literal/length and distance codes
+//               (two-queue Huffman over the rank-sorted symbols, limited to 15 bits, canonical), the code-length
+//               code, and the bits of the member + block header, which are the same for every block.  Left in a
+//               ZCode in device memory.
+// k_bgzf        one CTA of 512 threads per BGZF block, 3 CTAs per SM; thread t owns bytes [128 t, 128 t + 128) in
+//               both passes, warp w the segment [4096 w, 4096 w + 4096); between the first barrier and the one at
+//               which the sizes meet a warp synchronises with nobody but itself.
+//   pass 1  the CRC-32 of the chunk (slicing by four; the warp's tree of "advance over 2^j zero bytes" operators
+//           gives the segment's, which is advanced over the bytes behind the segment: the block's is the XOR of the
+//           sixteen), its newlines as a bit mask, and the bits its bytes take as literals
+//   match   (levels 4-6) the line starts of the segment by a warp scan of the newline counts, the four before the
+//           segment from the newlines of the 1024 bytes in front of it; every thread compares the line starts of its
+//           chunk with the line start 4 lines earlier -- in FASTQ the same line of the previous record -- and a
+//           common prefix of >= 4 bytes becomes one length/distance pair (it ends with its line and with the
+//           segment; two per chunk are kept): a bit mask marks the bytes so covered, the chunk sizes lose their
+//           literals and gain the pair
+//   sizes   a warp scan of the chunk sizes, the segments' sums through shared memory: every chunk's bit position
+//   pass 2  every thread codes its chunk serially into a 64-bit window that is emptied, a word at a time, into the
+//           member's image in shared memory at the chunk's own bit position; the image leaves with 128-bit stores
+//   a block that holds a byte without a code, or would not shrink, is left to
+// k_bgzf_own    the same block with a Huffman code of its own (histograms in pass 1, the code construction of
+//               k_bgzf_code between the passes, warp-cooperative pass 2); stores the block when it does not shrink.
 // The member lands in a 64 KiB slot; k_bgzf_scan / k_bgzf_gather then make the file contiguous.
 #ifdef JLP_CPU_EMU      // tests/emu: the kernels of this file on host threads (CPU test suite), see tests/emu/cuda_emu.h
 #include "cuda_emu.h"
@@ -106,6 +111,7 @@ struct HuffScratch {
     uint32_t* bl;        // codes per length
 };
 
+// shared memory of k_bgzf_code and k_bgzf_own
 struct ZShared {
     uint32_t stage[kStageWords];          // the block image; its last 16 KiB hold the per-warp literal counts until the packing starts
     uint32_t mask[kMaskWords];            // bit q + 1: byte q of the block is covered by a match
