@@ -148,6 +148,30 @@ struct ZShared {
 static_assert(sizeof(ZShared) <= 75 * 1024, "three CTAs per SM");
 static_assert(offsetof(ZShared, mbits) % 8 == 0, "mbits alignment");
 
+// The literal/length code limited to 15 bits by the whole CTA (uniform call).  S.bl[] holds the leaves per depth, the
+// ones deeper than 15 counted at 15, so the Kraft sum exceeds one by E units of 2^-15.  zlib's step (gen_bitlen) --
+// a leaf of the deepest level above 15 moves one down and takes a leaf of level 15 up beside it -- lowers the sum by
+// exactly one unit, so E steps make the code complete again; then the lengths are handed out in sorted order, the
+// longest code to the rarest symbol, by one thread per symbol.
+__device__ __forceinline__ void limit_15(ZShared& S, uint32_t n, uint32_t t) {
+    if (t == 0) {
+        uint32_t kraft = 0;
+        for (uint32_t b = 1; b <= 15; b++) kraft += S.bl[b] << (15 - b);
+        for (int32_t e = (int32_t)kraft - (1 << 15); e > 0; e--) {
+            uint32_t b = 14;
+            while (S.bl[b] == 0) b--;
+            S.bl[b]--; S.bl[b + 1] += 2; S.bl[15]--;
+        }
+    }
+    __syncthreads();
+    if (t < n) {
+        uint32_t b = 15, cum = S.bl[15];
+        while (t >= cum && b > 1) cum += S.bl[--b];
+        S.len[S.sorted[t]] = (uint8_t)b;
+    }
+    __syncthreads();
+}
+
 // shared memory of k_bgzf
 struct ZMain {
     uint32_t image[kImageWords];          // the member: the header words, then the bits of every chunk at their final place
@@ -714,10 +738,7 @@ k_bgzf_code(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, co
         if (dep > 15) atomicMax(&S.maxd, dep);
     }
     __syncthreads();
-    if (S.maxd > 15) {                         // the 15-bit limit has to act (with the raised counts: nearly always)
-        if (t == 0) huff_limit(H1, n_active, 15, S.len);
-        __syncthreads();
-    }
+    if (S.maxd > 15) limit_15(S, n_active, t);   // the 15-bit limit has to act (with the raised counts: nearly always)
     // canonical codes: first code of the length + the symbols of the same length before this one
     if (t < kNLit) {
         const uint32_t l = S.len[t];
@@ -1210,10 +1231,7 @@ __device__ __forceinline__ void own_block(ZShared& S, uint32_t blk, const uint8_
         if (dep > 15) atomicMax(&S.maxd, dep);
     }
     __syncthreads();
-    if (S.maxd > 15) {                         // rare: the 15-bit limit has to act
-        if (t == 0) huff_limit(H1, n_active, 15, S.len);
-        __syncthreads();
-    }
+    if (S.maxd > 15) limit_15(S, n_active, t);   // rare: the 15-bit limit has to act
     // canonical codes: first code of the length + the symbols of the same length before this one
     if (t < kNLit) {
         const uint32_t l = S.len[t];
