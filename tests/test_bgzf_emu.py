@@ -35,7 +35,8 @@ def _gpu_cases():
 G = _gpu_cases()
 # a subset that reaches every path and keeps the CPU suite short (a block takes about half a second)
 NAMES = ["empty", "one_byte", "short_text", "block_plus_one", "three_blocks_ragged", "random_bytes_stored", "fibonacci_depth",
-         "repeated_lines", "short_lines", "long_codes_before_matches", "late_binary_bytes", "nonstationary", "chunk_tail_129"]
+         "repeated_lines", "short_lines", "long_codes_before_matches", "late_binary_bytes", "nonstationary", "lines_of_128",
+         "lines_of_129", "identical_300", "long_lines", "chunk_tail_129"]
 
 
 @pytest.fixture(scope="module")

@@ -100,6 +100,15 @@ CASES = {
     # always gets a code), and blocks the first block's code fits badly, fall back to a code of their own
     "late_binary_bytes": fastq_like(0xff00 + 5000, 8) + bytes(np.random.default_rng(9).integers(0, 32, 70000, dtype=np.uint8)) + fastq_like(30000, 10),
     "nonstationary": b"A" * 0xff00 + fastq_like(2 * 0xff00, 11) + bytes(np.random.default_rng(12).integers(0, 256, 0xff00, dtype=np.uint8)) + b"\n".join(b"line %d" % (i % 13) for i in range(9000)),
+    # the coder's units are chunks of 128 and segments of 4096 bytes: newlines in the last byte of every chunk, lines that
+    # drift through the chunks, identical 300-byte lines (matches of 258 bytes across chunk and segment boundaries), and
+    # lines longer than a segment and than the bytes searched for earlier line starts (PacBio-like records)
+    "lines_of_128": b"".join(b"%s\n" % (bytes([65 + (i * 7 + j) % 20 for j in range(120)]) + b"%07d" % (i % 97)) for i in range(1600)),
+    "lines_of_129": b"".join(b"%s\n" % (b"HDR-%04d-" % (i % 50) + bytes([97 + (i + j * j) % 13 for j in range(119)])) for i in range(1500)),
+    "identical_300": (b"ACGTTGCA" * 37 + b"xyz\n") * 700,
+    "long_lines": b"".join(b"@m%d/%d/ccs\n%s\n+\n%s\n" % (i, 1000 + i, bytes(np.random.default_rng(30 + i).choice(np.frombuffer(b"ACGT", np.uint8), 9000 + 911 * i)),
+                                                         bytes(np.random.default_rng(60 + i).choice(np.frombuffer(b"!+5?IS]", np.uint8), 9000 + 911 * i)))
+                           for i in range(9)),
     "chunk_tail_127": fastq_like(0xff00 + 127, 6),
     "chunk_tail_129": fastq_like(2 * 0xff00 + 129, 7),
 }
